@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) k_resize_level(const uint8_t* __restrict_
 // K2  FAST-9/16 score + strict 8-neighbour NMS + ini/min threshold choice, one CTA per cell.
 // Score = largest threshold the pixel passes (OpenCV cornerScore).  Scores below minTh are stored as 0,
 // which is equivalent for both thresholds (a neighbour that is not a corner counts as 0 in cv::FAST).
-__device__ __forceinline__ int fast_score_px(const uint8_t* p, int pitch, int minTh) {
+__host__ __device__ __forceinline__ int fast_score_px(const uint8_t* p, int pitch, int minTh) {
   int v = p[0];
   // quick reject (any 9-arc contains pixel 0 or 8 of the circle, and 4 or 12)
   int d0 = v - p[3 * pitch], d8 = v - p[-3 * pitch];
@@ -111,18 +111,25 @@ __device__ __forceinline__ int fast_score_px(const uint8_t* p, int pitch, int mi
   d[4] = d4; d[5] = v - p[-pitch + 3]; d[6] = v - p[-2 * pitch + 2]; d[7] = v - p[-3 * pitch + 1];
   d[8] = d8; d[9] = v - p[-3 * pitch - 1]; d[10] = v - p[-2 * pitch - 2]; d[11] = v - p[-pitch - 3];
   d[12] = d12; d[13] = v - p[pitch - 3]; d[14] = v - p[2 * pitch - 2]; d[15] = v - p[3 * pitch - 1];
-  int mn2[16], mx2[16], mn4[16], mx4[16];
+  // NOTE: the dark side is evaluated on e = -d with min() only.  Writing it as max(mn, -mx) makes ptxas 12.9
+  // fuse the negation into VIMNMX3 and drop it on sm_100a (observed: wrong scores on the device, right on host).
+  int e[16];
 #pragma unroll
-  for (int k = 0; k < 16; k++) { mn2[k] = min(d[k], d[(k + 1) & 15]); mx2[k] = max(d[k], d[(k + 1) & 15]); }
+  for (int k = 0; k < 16; k++) e[k] = -d[k];
+  int a2[16], b2[16], a4[16], b4[16];
 #pragma unroll
-  for (int k = 0; k < 16; k++) { mn4[k] = min(mn2[k], mn2[(k + 2) & 15]); mx4[k] = max(mx2[k], mx2[(k + 2) & 15]); }
-  int best = -256;
+  for (int k = 0; k < 16; k++) { a2[k] = min(d[k], d[(k + 1) & 15]); b2[k] = min(e[k], e[(k + 1) & 15]); }
+#pragma unroll
+  for (int k = 0; k < 16; k++) { a4[k] = min(a2[k], a2[(k + 2) & 15]); b4[k] = min(b2[k], b2[(k + 2) & 15]); }
+  int bestA = -256, bestB = -256;
 #pragma unroll
   for (int k = 0; k < 16; k++) {
-    int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-    int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
-    best = max(best, max(mn9, -mx9));
+    int a9 = min(min(a4[k], a4[(k + 4) & 15]), d[(k + 8) & 15]);
+    int b9 = min(min(b4[k], b4[(k + 4) & 15]), e[(k + 8) & 15]);
+    bestA = max(bestA, a9);
+    bestB = max(bestB, b9);
   }
+  int best = bestA > bestB ? bestA : bestB;
   int s = best - 1;
   return s >= minTh ? s : 0;
 }

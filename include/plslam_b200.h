@@ -73,6 +73,85 @@ int pl_orb_get_level(PLOrb* h, int frame, int level, uint8_t* out, int with_bord
  * reference's order, coordinates relative to the level's (16,16) detection origin.  Returns count. */
 int pl_orb_debug_candidates(PLOrb* h, int frame, int level, PLKeyPoint* out, int cap);
 
+/* ------------------------------------------------------------------ descriptor matching
+ * Flat-array forms of the reference's matcher methods.  A "frame" is the triple the matchers read from
+ * ORB_SLAM2::Frame: mvKeysUn (PLKeyPoint[]), mDescriptors (n x 32 bytes), and the image bounds
+ * bounds[4] = {mnMinX, mnMinY, mnMaxX, mnMaxY} that define the 64x48 bucket grid (Frame.cc:36,116-117,278-294).
+ * Host-pointer forms synchronise and return the match count (>= 0) or an error (< 0); `_dev` forms are batched
+ * over B frames ([B][cap] arrays, counts n[B]) and asynchronous.                                              */
+
+/* ORBmatcher::DescriptorDistance (ORBmatcher.cc:1764-1780) == LSDmatcher::DescriptorDistance (LSDmatcher.cpp:654-670)
+ * for n independent 32-byte pairs. */
+int pl_descriptor_distance_batch(const uint8_t* a, const uint8_t* b, int n, int* out);
+
+/* Frame::AssignFeaturesToGrid (Frame.cc:278-294): CSR of mGrid, cell = ix*48+iy; cell_start[3073], cell_items[n]. */
+int pl_frame_assign_grid(const PLKeyPoint* keys_un, int n, const float* bounds, int* cell_start, int* cell_items);
+int pl_frame_assign_grid_dev(const PLKeyPoint* keys_un, const int* n, int cap, int B, const float* bounds,
+                             int* cell_start /*[B][3073]*/, int* cell_items /*[B][cap]*/, void* stream);
+
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:455-572).
+ * prev_matched [n1][2] in/out, matches12 [n1] out. */
+int pl_orb_search_for_initialization(const PLKeyPoint* keys1, const uint8_t* desc1, int n1, const PLKeyPoint* keys2,
+                                     const uint8_t* desc2, int n2, const float* bounds, float* prev_matched,
+                                     int* matches12, int window_size, float nnratio, int check_orientation);
+/* batched: scratch = int[B][2*cap] */
+int pl_orb_search_for_initialization_dev(const PLKeyPoint* keys1, const uint8_t* desc1, const int* n1,
+                                         const PLKeyPoint* keys2, const uint8_t* desc2, const int* n2, int cap, int B,
+                                         const float* bounds, float* prev_matched, int* matches12, int* nmatches,
+                                         int window_size, float nnratio, int check_orientation, int* scratch,
+                                         void* stream);
+
+/* ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono=true) (ORBmatcher.cc:1441-1585).
+ * Last frame side, per keypoint i: last_valid = (mvpMapPoints[i] && !mvbOutlier[i]), last_pos = GetWorldPos()
+ * (3 floats), last_desc = GetDescriptor(), last_octave = mvKeys[i].octave, last_angle = mvKeysUn[i].angle.
+ * Tcw: current pose (row-major 4x4 float), K = {fx,fy,cx,cy}.  cur_preassigned (may be NULL): keypoints that
+ * already hold an observed map point.  cur_match[n_cur] out: last-frame index, -1 none, -2 pre-assigned. */
+int pl_orb_search_by_projection_last(const PLKeyPoint* keys_cur, const uint8_t* desc_cur, int n_cur,
+                                     const float* bounds, const float* Tcw, const float* K,
+                                     const float* scale_factors, int nlevels, int n_last, const uint8_t* last_valid,
+                                     const float* last_pos, const uint8_t* last_desc, const int* last_octave,
+                                     const float* last_angle, float th, int check_orientation,
+                                     const uint8_t* cur_preassigned, int* cur_match);
+
+/* ORBmatcher::SearchByProjection(F, vpMapPoints, th) (ORBmatcher.cc:56-152).  Per map point: in_view =
+ * (mbTrackInView && !isBad()), proj = {mTrackProjX, mTrackProjY}, level = mnTrackScaleLevel, view_cos =
+ * mTrackViewCos, mp_desc = GetDescriptor().  match[n] out: map point index, -1, or -2 (pre-assigned). */
+int pl_orb_search_by_projection_points(const PLKeyPoint* keys, const uint8_t* desc, int n, const float* bounds,
+                                       const float* scale_factors, int nlevels, int n_mp, const uint8_t* in_view,
+                                       const float* proj, const int* level, const float* view_cos,
+                                       const uint8_t* mp_desc, float th, float nnratio, const uint8_t* preassigned,
+                                       int* match);
+
+/* cv::BFMatcher(NORM_HAMMING).knnMatch(d1, d2, k=2) as called at LSDmatcher.cpp:469: idx/dist are [n1][2]. */
+int pl_match_bf_knn2(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx, int* dist);
+/* LSDmatcher::FrameBFMatch(ldesc1, ldesc2, LineMatches, TH) incl. lineDescriptorMAD (LSDmatcher.cpp:462-486,627-652) */
+int pl_lsd_frame_bf_match(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float th, float nnratio, int* matches);
+/* LSDmatcher::SearchDouble(InitialFrame, CurrentFrame, LineMatches) (LSDmatcher.cpp:440-460): both directions + mutual */
+int pl_lsd_search_double(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnratio, int* matches);
+int pl_lsd_search_double_dev(const uint8_t* d1, const int* n1, const uint8_t* d2, const int* n2, int cap1, int cap2,
+                             int B, float th, float nnratio, int mutual, int* matches /*[B][cap1]*/, int* nmatches,
+                             void* stream);
+
+/* ------------------------------------------------------------------ pose-only Levenberg-Marquardt
+ * Optimizer::PoseOptimization (mode 0, src/Optimizer.cc:640-975), PoseOptimizationWithPoints (mode 1, :977-1115),
+ * PoseOptimizationWithLines (mode 2, :1117-1284) with g2o's LM semantics restated.
+ * One problem = one Frame: Tcw (row-major 4x4 float, pFrame->mTcw), K = {fx,fy,cx,cy};
+ * per matched point i: pt_obs = mvKeysUn[i].pt, pt_inv_sigma2 = mvInvLevelSigma2[octave], pt_Xw = GetWorldPos();
+ * per matched line i: line_func = mvKeyLineFunctions[i] (3 doubles), line_Xw = MapLine::mWorldPos (6 doubles).
+ * Outputs: optimised Tcw, mvbOutlier / mvbLineOutlier flags.  Returns the reference's return value
+ * (inlier count; 0 and an untouched pose when fewer than 3 correspondences) or an error < 0.               */
+int pl_pose_optimization(int mode, const float* Tcw_in, const float* K, int n_points, const float* pt_obs,
+                         const float* pt_inv_sigma2, const float* pt_Xw, int n_lines, const double* line_func,
+                         const double* line_Xw, float* Tcw_out, uint8_t* pt_outlier, uint8_t* line_outlier,
+                         int* iterations /* may be NULL: LM iterations executed */);
+/* Batched, device pointers: arrays are [B][cap_*]...; scratch holds pl_pose_optimization_scratch_doubles() doubles. */
+size_t pl_pose_optimization_scratch_doubles(int B, int cap_points, int cap_lines);
+int pl_pose_optimization_dev(int mode, int B, const float* Tcw_in, const float* K, const int* n_points,
+                             int cap_points, const float* pt_obs, const float* pt_inv_sigma2, const float* pt_Xw,
+                             const int* n_lines, int cap_lines, const double* line_func, const double* line_Xw,
+                             float* Tcw_out, uint8_t* pt_outlier, uint8_t* line_outlier, int* inliers,
+                             int* iterations, double* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -148,3 +148,109 @@ def distribute(kps, minX, maxX, minY, maxY, N):
     out = np.zeros(max(len(kps), 1), KP_DTYPE)
     n = lib().oracle_distribute(_p(kps), len(kps), minX, maxX, minY, maxY, N, _p(out))
     return out[:n].copy()
+
+
+# ---------------------------------------------------------------------------------------------- matching
+KL_DTYPE = np.dtype([("startX", "<f4"), ("startY", "<f4"), ("endX", "<f4"), ("endY", "<f4"),
+                     ("lineLength", "<f4"), ("angle", "<f4"), ("octave", "<i4")])
+
+
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().oracle_descriptor_distance(_p(a), _p(b))
+
+
+def assign_grid(keys, bounds):
+    keys = np.ascontiguousarray(keys); b = np.asarray(bounds, np.float32)
+    start = np.zeros(64 * 48 + 1, np.int32); items = np.zeros(max(len(keys), 1), np.int32)
+    n = lib().oracle_assign_grid(_p(keys), len(keys), _p(b), _p(start), _p(items))
+    return start, items[:n]
+
+
+def search_for_initialization(k1, d1, k2, d2, bounds, prev_matched, window=100, nnratio=0.9, check_ori=True):
+    k1 = np.ascontiguousarray(k1); k2 = np.ascontiguousarray(k2)
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    pm = np.ascontiguousarray(prev_matched, np.float32).copy()
+    m = np.zeros(max(len(k1), 1), np.int32)
+    b = np.asarray(bounds, np.float32)
+    lib().oracle_search_for_initialization.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
+    nm = lib().oracle_search_for_initialization(_p(k1), _p(d1), len(k1), _p(k2), _p(d2), len(k2), _p(b), _p(pm), _p(m),
+                                                window, nnratio, int(check_ori))
+    return nm, m[:len(k1)], pm
+
+
+def search_by_projection_last(kc, dc, bounds, Tcw, K, scale_factors, last_valid, last_pos, last_desc, last_octave,
+                              last_angle, th, check_ori=True, preassigned=None):
+    kc = np.ascontiguousarray(kc); dc = np.ascontiguousarray(dc, np.uint8)
+    m = np.zeros(max(len(kc), 1), np.int32)
+    f = lib().oracle_search_by_projection_last
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    arrs = [np.asarray(bounds, np.float32), np.ascontiguousarray(Tcw, np.float32), np.asarray(K, np.float32),
+            np.ascontiguousarray(scale_factors, np.float32)]
+    lv = np.ascontiguousarray(last_valid, np.uint8); lp = np.ascontiguousarray(last_pos, np.float32)
+    ld = np.ascontiguousarray(last_desc, np.uint8); lo = np.ascontiguousarray(last_octave, np.int32)
+    la = np.ascontiguousarray(last_angle, np.float32)
+    pre = None if preassigned is None else np.ascontiguousarray(preassigned, np.uint8)
+    nm = f(_p(kc), _p(dc), len(kc), _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), len(lv), _p(lv), _p(lp), _p(ld),
+           _p(lo), _p(la), th, int(check_ori), _p(pre), _p(m))
+    return nm, m[:len(kc)]
+
+
+def search_by_projection_points(k, d, bounds, scale_factors, in_view, proj, level, view_cos, mp_desc, th, nnratio=0.8,
+                                preassigned=None):
+    k = np.ascontiguousarray(k); d = np.ascontiguousarray(d, np.uint8)
+    m = np.zeros(max(len(k), 1), np.int32)
+    f = lib().oracle_search_by_projection_points
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    b = np.asarray(bounds, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    iv = np.ascontiguousarray(in_view, np.uint8); pr = np.ascontiguousarray(proj, np.float32)
+    lv = np.ascontiguousarray(level, np.int32); vc = np.ascontiguousarray(view_cos, np.float32)
+    md = np.ascontiguousarray(mp_desc, np.uint8)
+    pre = None if preassigned is None else np.ascontiguousarray(preassigned, np.uint8)
+    nm = f(_p(k), _p(d), len(k), _p(b), _p(sf), len(iv), _p(iv), _p(pr), _p(lv), _p(vc), _p(md), th, nnratio, _p(pre), _p(m))
+    return nm, m[:len(k)]
+
+
+def bf_knn2(d1, d2):
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    idx = np.zeros((max(len(d1), 1), 2), np.int32); dist = np.zeros((max(len(d1), 1), 2), np.int32)
+    lib().oracle_bf_knn2(_p(d1), len(d1), _p(d2), len(d2), _p(idx), _p(dist))
+    return idx[:len(d1)], dist[:len(d1)]
+
+
+def frame_bf_match(d1, d2, th=50.0, nnratio=0.7):
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    m = np.zeros(max(len(d1), 1), np.int32)
+    f = lib().oracle_frame_bf_match
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
+    f(_p(d1), len(d1), _p(d2), len(d2), th, nnratio, _p(m))
+    return m[:len(d1)]
+
+
+def search_double(d1, d2, nnratio=0.7):
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    m = np.zeros(max(len(d1), 1), np.int32)
+    f = lib().oracle_search_double
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p]
+    nm = f(_p(d1), len(d1), _p(d2), len(d2), nnratio, _p(m))
+    return nm, m[:len(d1)]
+
+
+# ---------------------------------------------------------------------------------------------- pose-only LM
+def pose_optimization(mode, Tcw, K, pt_obs, pt_inv_sigma2, pt_Xw, line_func, line_Xw):
+    Tcw = np.ascontiguousarray(Tcw, np.float32); K = np.ascontiguousarray(K, np.float32)
+    po = np.ascontiguousarray(pt_obs, np.float32).reshape(-1, 2); pw = np.ascontiguousarray(pt_inv_sigma2, np.float32)
+    px = np.ascontiguousarray(pt_Xw, np.float32).reshape(-1, 3)
+    lf = np.ascontiguousarray(line_func, np.float64).reshape(-1, 3); lx = np.ascontiguousarray(line_Xw, np.float64).reshape(-1, 6)
+    Tout = np.zeros((4, 4), np.float32)
+    pout = np.zeros(max(len(po), 1), np.uint8); lout = np.zeros(max(len(lf), 1), np.uint8)
+    its = C.c_int(0)
+    f = lib().oracle_pose_optimization
+    f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    n = f(mode, _p(Tcw), _p(K), len(po), _p(po), _p(pw), _p(px), len(lf), _p(lf), _p(lx), _p(Tout), _p(pout), _p(lout),
+          C.byref(its))
+    return n, Tout, pout[:len(po)].astype(bool), lout[:len(lf)].astype(bool), its.value

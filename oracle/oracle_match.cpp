@@ -1,0 +1,476 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_orb.cpp header for the rules).
+//
+// CPU restatement of the reference's descriptor matching path on flat arrays:
+//   ORBmatcher::DescriptorDistance            src/ORBmatcher.cc:1764-1780   (== LSDmatcher.cpp:654-670)
+//   Frame::AssignFeaturesToGrid / PosInGrid   src/Frame.cc:278-294, :893-903
+//   Frame::AssignFeaturesToGridForLine        src/Frame.cc:296-320 + src/lineIterator.cpp
+//   Frame::GetFeaturesInArea                  src/Frame.cc:713-766
+//   Frame::GetFeaturesInAreaForLine           src/Frame.cc:768-842
+//   ORBmatcher::SearchForInitialization       src/ORBmatcher.cc:455-572
+//   ORBmatcher::SearchByProjection(F,Last)    src/ORBmatcher.cc:1441-1585   (mono branch)
+//   ORBmatcher::SearchByProjection(F,points)  src/ORBmatcher.cc:56-152
+//   ORBmatcher::ComputeThreeMaxima            src/ORBmatcher.cc:1718-1759
+//   LSDmatcher::FrameBFMatch / lineDescriptorMAD / SearchDouble   src/LSDmatcher.cpp:440-486, :627-652
+//   LSDmatcher::SearchByProjection (both)     src/LSDmatcher.cpp:72-176, :221-338
+// cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) is third-party (OpenCV, not vendored): restated as "two smallest
+// distances, ties -> lower train index first" and pinned against cv2 4.13 in tests/test_oracle_match.py.
+// Parity status: the reference holds no golden vectors for this path.
+// Waived: the debug JPEG writes (LSDmatcher.cpp:67,173,422) and stereo branches (mvuRight) are not restated.
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <climits>
+#include <vector>
+#include <algorithm>
+#include <unordered_set>
+
+namespace {
+const int GRID_COLS = 64, GRID_ROWS = 48, HISTO_LENGTH = 30;
+
+struct KeyPoint { float x, y, size, angle, response; int octave, class_id; };
+struct KeyLine {  // the fields of cv::line_descriptor::KeyLine the matchers read (flat copy)
+  float startX, startY, endX, endY, lineLength, angle;
+  int octave;
+};
+
+int descriptor_distance(const uint8_t* a, const uint8_t* b) {
+  const int32_t* pa = (const int32_t*)a;
+  const int32_t* pb = (const int32_t*)b;
+  int dist = 0;
+  for (int i = 0; i < 8; i++, pa++, pb++) {
+    unsigned int v = *pa ^ *pb;
+    v = v - ((v >> 1) & 0x55555555);
+    v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+    dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+  }
+  return dist;
+}
+
+struct Grid {
+  float minX, minY, maxX, maxY, invW, invH;
+  std::vector<int> cell[GRID_COLS][GRID_ROWS];
+  void init(const float* b) {
+    minX = b[0]; minY = b[1]; maxX = b[2]; maxY = b[3];
+    invW = (float)GRID_COLS / (maxX - minX);
+    invH = (float)GRID_ROWS / (maxY - minY);
+  }
+};
+
+void assign_points(Grid& g, const KeyPoint* k, int n) {
+  for (int i = 0; i < n; i++) {
+    int px = (int)roundf((k[i].x - g.minX) * g.invW);
+    int py = (int)roundf((k[i].y - g.minY) * g.invH);
+    if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
+    g.cell[px][py].push_back(i);
+  }
+}
+
+void assign_lines(Grid& g, const KeyLine* kl, int n) {
+  for (int i = 0; i < n; i++) {
+    double x1 = kl[i].startX * g.invW, y1 = kl[i].startY * g.invH;  // float products widened to double
+    double x2 = kl[i].endX * g.invW, y2 = kl[i].endY * g.invH;
+    bool steep = std::abs(y2 - y1) > std::abs(x2 - x1);
+    if (steep) { std::swap(x1, y1); std::swap(x2, y2); }
+    if (x1 > x2) { std::swap(x1, x2); std::swap(y1, y2); }
+    double dx = x2 - x1, dy = std::abs(y2 - y1), error = dx / 2.0;
+    int ystep = (y1 < y2) ? 1 : -1;
+    int x = (int)x1, y = (int)y1, maxX = (int)x2;
+    while (x <= maxX) {
+      int px = steep ? y : x, py = steep ? x : y;
+      if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) g.cell[px][py].push_back(i);
+      error -= dy;
+      if (error < 0) { y += ystep; error += dx; }
+      x++;
+    }
+  }
+}
+
+void features_in_area(const Grid& g, const KeyPoint* keys, float x, float y, float r, int minLevel, int maxLevel,
+                      std::vector<int>& out) {
+  out.clear();
+  const int nMinCellX = std::max(0, (int)floorf((x - g.minX - r) * g.invW));
+  if (nMinCellX >= GRID_COLS) return;
+  const int nMaxCellX = std::min(GRID_COLS - 1, (int)ceilf((x - g.minX + r) * g.invW));
+  if (nMaxCellX < 0) return;
+  const int nMinCellY = std::max(0, (int)floorf((y - g.minY - r) * g.invH));
+  if (nMinCellY >= GRID_ROWS) return;
+  const int nMaxCellY = std::min(GRID_ROWS - 1, (int)ceilf((y - g.minY + r) * g.invH));
+  if (nMaxCellY < 0) return;
+  const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+  for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+    for (int iy = nMinCellY; iy <= nMaxCellY; iy++)
+      for (int id : g.cell[ix][iy]) {
+        const KeyPoint& kp = keys[id];
+        if (bCheckLevels) {
+          if (kp.octave < minLevel) continue;
+          if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+        }
+        const float distx = kp.x - x, disty = kp.y - y;
+        if (fabsf(distx) < r && fabsf(disty) < r) out.push_back(id);
+      }
+}
+
+void features_in_area_line(const Grid& g, const KeyLine* kls, const double* lfunc, float x1, float y1, float x2,
+                           float y2, float r, float TH, std::vector<int>& out) {
+  out.clear();
+  std::unordered_set<int> seen;
+  float x[3] = {x1, (float)((x1 + x2) / 2.0), x2};
+  float y[3] = {y1, (float)((y1 + y2) / 2.0), y2};
+  float d1x = x1 - x2, d1y = y1 - y2;
+  float n1 = sqrtf(d1x * d1x + d1y * d1y);
+  d1x /= n1; d1y /= n1;
+  for (int i = 0; i < 3; i++) {
+    const int nMinCellX = std::max(0, (int)floorf((x[i] - g.minX - r) * g.invW));
+    if (nMinCellX >= GRID_COLS) continue;
+    const int nMaxCellX = std::min(GRID_COLS - 1, (int)ceilf((x[i] - g.minX + r) * g.invW));
+    if (nMaxCellX < 0) continue;
+    const int nMinCellY = std::max(0, (int)floorf((y[i] - g.minY - r) * g.invH));
+    if (nMinCellY >= GRID_ROWS) continue;
+    const int nMaxCellY = std::min(GRID_ROWS - 1, (int)ceilf((y[i] - g.minY + r) * g.invH));
+    if (nMaxCellY < 0) continue;
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+      for (int iy = nMinCellY; iy <= nMaxCellY; iy++)
+        for (int id : g.cell[ix][iy]) {
+          if (seen.count(id)) continue;
+          const KeyLine& kl = kls[id];
+          float d2x = kl.startX - kl.endX, d2y = kl.startY - kl.endY;
+          float n2 = sqrtf(d2x * d2x + d2y * d2y);
+          d2x /= n2; d2y /= n2;
+          float cosSita = fabsf(d1x * d2x + d1y * d2y);
+          if (cosSita < TH) continue;
+          const double* L = lfunc + 3 * id;
+          const float dist = (float)(L[0] * x[i] + L[1] * y[i] + L[2]);
+          if (fabsf(dist) < r) { out.push_back(id); seen.insert(id); }
+        }
+  }
+}
+
+void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  for (int i = 0; i < L; i++) {
+    const int s = (int)histo[i].size();
+    if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+    else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+    else if (s > max3) { max3 = s; ind3 = i; }
+  }
+  if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+  else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+inline int rot_bin(float a1, float a2) {
+  const float factor = 1.0f / HISTO_LENGTH;
+  float rot = a1 - a2;
+  if (rot < 0.0) rot += 360.0f;
+  int bin = (int)roundf(rot * factor);
+  if (bin == HISTO_LENGTH) bin = 0;
+  return bin;
+}
+
+// BFMatcher(NORM_HAMMING).knnMatch(k=2): idx/dist [n1][2]; entries beyond n2 are -1
+void bf_knn2(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx, int* dist) {
+  for (int q = 0; q < n1; q++) {
+    int b0 = INT_MAX, b1 = INT_MAX, i0 = -1, i1 = -1;
+    for (int t = 0; t < n2; t++) {
+      int d = descriptor_distance(d1 + 32 * q, d2 + 32 * t);
+      if (d < b0) { b1 = b0; i1 = i0; b0 = d; i0 = t; }
+      else if (d < b1) { b1 = d; i1 = t; }
+    }
+    idx[2 * q] = i0; idx[2 * q + 1] = i1;
+    dist[2 * q] = i0 >= 0 ? b0 : -1; dist[2 * q + 1] = i1 >= 0 ? b1 : -1;
+  }
+}
+
+// LSDmatcher::FrameBFMatch with lineDescriptorMAD.  NL<2 on either side => no matches.
+void frame_bf_match(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float TH, float nnratio, int* matches) {
+  for (int i = 0; i < n1; i++) matches[i] = -1;
+  if (n1 < 1 || n2 < 2) return;
+  std::vector<int> idx(2 * n1), dist(2 * n1);
+  bf_knn2(d1, n1, d2, n2, idx.data(), dist.data());
+  // nn12 MAD: sort DESCENDING by (d1-d0), take element size/2; then |.-median| ascending, element size/2
+  std::vector<float> d12(n1);
+  for (int i = 0; i < n1; i++) d12[i] = (float)dist[2 * i + 1] - (float)dist[2 * i];
+  std::vector<float> s = d12;
+  std::sort(s.begin(), s.end(), [](float a, float b) { return a > b; });
+  double med = s[n1 / 2];
+  std::vector<float> dev(n1);
+  for (int i = 0; i < n1; i++) dev[i] = fabsf((float)((double)d12[i] - med));
+  std::sort(dev.begin(), dev.end());
+  double nn12 = 1.4826 * dev[n1 / 2];
+  nn12 = nn12 * 0.5;
+  for (int i = 0; i < n1; i++) {
+    double dist_12 = (double)((float)dist[2 * i + 1] - (float)dist[2 * i]);
+    if (dist_12 > nn12 && (float)dist[2 * i] < TH && (float)dist[2 * i] < nnratio * (float)dist[2 * i + 1])
+      matches[i] = idx[2 * i];
+  }
+}
+}  // namespace
+
+extern "C" {
+int oracle_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
+
+// CSR export of Frame::mGrid / mGridForLine: cell index = ix*48+iy; start[3073], items[cap]; returns #items
+int oracle_assign_grid(const void* keys, int n, const float* bounds, int* start, int* items) {
+  Grid g; g.init(bounds);
+  assign_points(g, (const KeyPoint*)keys, n);
+  int k = 0;
+  for (int ix = 0; ix < GRID_COLS; ix++)
+    for (int iy = 0; iy < GRID_ROWS; iy++) {
+      start[ix * GRID_ROWS + iy] = k;
+      for (int id : g.cell[ix][iy]) items[k++] = id;
+    }
+  start[GRID_COLS * GRID_ROWS] = k;
+  return k;
+}
+int oracle_assign_grid_lines(const void* kls, int n, const float* bounds, int* start, int* items, int cap) {
+  Grid g; g.init(bounds);
+  assign_lines(g, (const KeyLine*)kls, n);
+  int k = 0;
+  for (int ix = 0; ix < GRID_COLS; ix++)
+    for (int iy = 0; iy < GRID_ROWS; iy++) {
+      start[ix * GRID_ROWS + iy] = k;
+      for (int id : g.cell[ix][iy]) { if (k < cap) items[k] = id; k++; }
+    }
+  start[GRID_COLS * GRID_ROWS] = k;
+  return k;
+}
+int oracle_features_in_area(const void* keys, int n, const float* bounds, float x, float y, float r, int minLevel,
+                            int maxLevel, int* out) {
+  Grid g; g.init(bounds);
+  assign_points(g, (const KeyPoint*)keys, n);
+  std::vector<int> v;
+  features_in_area(g, (const KeyPoint*)keys, x, y, r, minLevel, maxLevel, v);
+  memcpy(out, v.data(), v.size() * sizeof(int));
+  return (int)v.size();
+}
+
+// ORBmatcher::SearchForInitialization.  prev_matched: [n1][2] in/out; matches12: [n1] out.
+int oracle_search_for_initialization(const void* keys1_, const uint8_t* desc1, int n1, const void* keys2_,
+                                     const uint8_t* desc2, int n2, const float* bounds, float* prev_matched,
+                                     int* matches12, int windowSize, float nnratio, int checkOri) {
+  const KeyPoint* k1 = (const KeyPoint*)keys1_;
+  const KeyPoint* k2 = (const KeyPoint*)keys2_;
+  Grid g; g.init(bounds);
+  assign_points(g, k2, n2);
+  const int TH_LOW = 50;
+  int nmatches = 0;
+  for (int i = 0; i < n1; i++) matches12[i] = -1;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  std::vector<int> matchedDist(n2, INT_MAX), matches21(n2, -1), cand;
+  for (int i1 = 0; i1 < n1; i1++) {
+    if (k1[i1].octave > 0) continue;
+    features_in_area(g, k2, prev_matched[2 * i1], prev_matched[2 * i1 + 1], (float)windowSize, 0, 0, cand);
+    if (cand.empty()) continue;
+    int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+    for (int i2 : cand) {
+      int dist = descriptor_distance(desc1 + 32 * i1, desc2 + 32 * i2);
+      if (matchedDist[i2] <= dist) continue;
+      if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+      else if (dist < bestDist2) bestDist2 = dist;
+    }
+    if (bestDist <= TH_LOW) {
+      if (bestDist < (float)bestDist2 * nnratio) {
+        if (matches21[bestIdx2] >= 0) { matches12[matches21[bestIdx2]] = -1; nmatches--; }
+        matches12[i1] = bestIdx2;
+        matches21[bestIdx2] = i1;
+        matchedDist[bestIdx2] = bestDist;
+        nmatches++;
+        if (checkOri) rotHist[rot_bin(k1[i1].angle, k2[bestIdx2].angle)].push_back(i1);
+      }
+    }
+  }
+  if (checkOri) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx1 : rotHist[i])
+        if (matches12[idx1] >= 0) { matches12[idx1] = -1; nmatches--; }
+    }
+  }
+  for (int i1 = 0; i1 < n1; i1++)
+    if (matches12[i1] >= 0) { prev_matched[2 * i1] = k2[matches12[i1]].x; prev_matched[2 * i1 + 1] = k2[matches12[i1]].y; }
+  return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono=true).
+// cur_match [n_cur]: in = 1 where mvpMapPoints[i] already holds an observed point (else -1/0 -> free);
+// out = index of the last-frame point assigned, -1 none, -2 = pre-assigned (kept).
+int oracle_search_by_projection_last(const void* keys_cur_, const uint8_t* desc_cur, int n_cur, const float* bounds,
+                                     const float* Tcw, const float* K /*fx fy cx cy*/, const float* scaleFactors,
+                                     int n_last, const uint8_t* last_valid, const float* last_pos,
+                                     const uint8_t* last_desc, const int* last_octave, const float* last_angle,
+                                     float th, int checkOri, const uint8_t* cur_preassigned, int* cur_match) {
+  const KeyPoint* kc = (const KeyPoint*)keys_cur_;
+  Grid g; g.init(bounds);
+  assign_points(g, kc, n_cur);
+  const int TH_HIGH = 100;
+  int nmatches = 0;
+  for (int i = 0; i < n_cur; i++) cur_match[i] = (cur_preassigned && cur_preassigned[i]) ? -2 : -1;
+  std::vector<int> rotHist[HISTO_LENGTH], cand;
+  for (int i = 0; i < n_last; i++) {
+    if (!last_valid[i]) continue;
+    const float* X = last_pos + 3 * i;
+    // x3Dc = Rcw*x3Dw + tcw in fp32 (cv::Mat 3x3 * 3x1), separately rounded products and sums
+    float xc = Tcw[0] * X[0] + Tcw[1] * X[1] + Tcw[2] * X[2] + Tcw[3];
+    float yc = Tcw[4] * X[0] + Tcw[5] * X[1] + Tcw[6] * X[2] + Tcw[7];
+    float zc = Tcw[8] * X[0] + Tcw[9] * X[1] + Tcw[10] * X[2] + Tcw[11];
+    const float invzc = (float)(1.0 / zc);
+    if (invzc < 0) continue;
+    float u = K[0] * xc * invzc + K[2];
+    float v = K[1] * yc * invzc + K[3];
+    if (u < g.minX || u > g.maxX) continue;
+    if (v < g.minY || v > g.maxY) continue;
+    int oct = last_octave[i];
+    float radius = th * scaleFactors[oct];
+    features_in_area(g, kc, u, v, radius, oct - 1, oct + 1, cand);
+    if (cand.empty()) continue;
+    int bestDist = 256, bestIdx2 = -1;
+    for (int i2 : cand) {
+      if (cur_match[i2] != -1) continue;  // already holds a map point
+      int dist = descriptor_distance(last_desc + 32 * i, desc_cur + 32 * i2);
+      if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+    }
+    if (bestDist <= TH_HIGH) {
+      cur_match[bestIdx2] = i;
+      nmatches++;
+      if (checkOri) rotHist[rot_bin(last_angle[i], kc[bestIdx2].angle)].push_back(bestIdx2);
+    }
+  }
+  if (checkOri) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++)
+      if (i != ind1 && i != ind2 && i != ind3)
+        for (int j : rotHist[i]) { cur_match[j] = -1; nmatches--; }
+  }
+  return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(F, vpMapPoints, th).  Per map point: in_view flag (mbTrackInView && !isBad),
+// proj (mTrackProjX,Y), level (mnTrackScaleLevel), view_cos (mTrackViewCos), descriptor.
+int oracle_search_by_projection_points(const void* keys_, const uint8_t* desc, int n, const float* bounds,
+                                       const float* scaleFactors, int n_mp, const uint8_t* in_view,
+                                       const float* proj, const int* level, const float* view_cos,
+                                       const uint8_t* mp_desc, float th, float nnratio,
+                                       const uint8_t* preassigned, int* match) {
+  const KeyPoint* k = (const KeyPoint*)keys_;
+  Grid g; g.init(bounds);
+  assign_points(g, k, n);
+  const int TH_HIGH = 100;
+  int nmatches = 0;
+  const bool bFactor = th != 1.0;
+  for (int i = 0; i < n; i++) match[i] = (preassigned && preassigned[i]) ? -2 : -1;
+  std::vector<int> cand;
+  for (int iMP = 0; iMP < n_mp; iMP++) {
+    if (!in_view[iMP]) continue;
+    const int lvl = level[iMP];
+    float r = (view_cos[iMP] > 0.998) ? 2.5f : 4.0f;
+    if (bFactor) r *= th;
+    features_in_area(g, k, proj[2 * iMP], proj[2 * iMP + 1], r * scaleFactors[lvl], lvl - 1, lvl, cand);
+    if (cand.empty()) continue;
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    for (int idx : cand) {
+      if (match[idx] != -1) continue;
+      const int dist = descriptor_distance(mp_desc + 32 * iMP, desc + 32 * idx);
+      if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = k[idx].octave; bestIdx = idx; }
+      else if (dist < bestDist2) { bestLevel2 = k[idx].octave; bestDist2 = dist; }
+    }
+    if (bestDist <= TH_HIGH) {
+      if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+      match[bestIdx] = iMP;
+      nmatches++;
+    }
+  }
+  return nmatches;
+}
+
+void oracle_bf_knn2(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx, int* dist) {
+  bf_knn2(d1, n1, d2, n2, idx, dist);
+}
+void oracle_frame_bf_match(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float TH, float nnratio, int* m) {
+  frame_bf_match(d1, n1, d2, n2, TH, nnratio, m);
+}
+// LSDmatcher::SearchDouble(InitialFrame, CurrentFrame, LineMatches)
+int oracle_search_double(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnratio, int* matches) {
+  for (int i = 0; i < n1; i++) matches[i] = -1;
+  if (n1 == 0 || n2 == 0) return 0;
+  std::vector<int> m1(n1), m2(n2);
+  frame_bf_match(d1, n1, d2, n2, 50.f, nnratio, m1.data());
+  frame_bf_match(d2, n2, d1, n1, 50.f, nnratio, m2.data());
+  int nm = 0;
+  for (int i = 0; i < n1; i++) {
+    int j = m1[i];
+    if (j >= 0) { if (m2[j] != i) m1[i] = -1; else nm++; }
+  }
+  memcpy(matches, m1.data(), n1 * sizeof(int));
+  return nm;
+}
+
+// LSDmatcher::SearchByProjection(CurrentFrame, LastFrame, th): projected endpoints/in-frustum flags are inputs
+// (Frame::isInFrustum(MapLine*) is Frame glue).  proj: [n_last][4] = X1,Y1,X2,Y2.
+int oracle_line_search_by_projection_last(const void* kls_cur_, const double* lfunc_cur, const uint8_t* desc_cur,
+                                          int n_cur, const float* bounds, int n_last, const uint8_t* last_valid,
+                                          const float* proj, const uint8_t* last_desc, const float* last_length,
+                                          float th, const uint8_t* preassigned, int* cur_match) {
+  const KeyLine* kc = (const KeyLine*)kls_cur_;
+  Grid g; g.init(bounds);
+  assign_lines(g, kc, n_cur);
+  const int TH_HIGH = 80;
+  int nmatches = 0;
+  for (int i = 0; i < n_cur; i++) cur_match[i] = (preassigned && preassigned[i]) ? -2 : -1;
+  std::vector<int> cand;
+  for (int i = 0; i < n_last; i++) {
+    if (!last_valid[i]) continue;
+    const float* p = proj + 4 * i;
+    features_in_area_line(g, kc, lfunc_cur, p[0], p[1], p[2], p[3], th, 0.96f, cand);
+    if (cand.empty()) continue;
+    int bestDist = 256, bestIdx2 = -1;
+    for (int i2 : cand) {
+      if (cur_match[i2] != -1) continue;
+      const int dist = descriptor_distance(last_desc + 32 * i, desc_cur + 32 * i2);
+      float mx = std::max(last_length[i], kc[i2].lineLength), mn = std::min(last_length[i], kc[i2].lineLength);
+      if (mn / mx < 0.75) continue;
+      if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+    }
+    if (bestDist <= TH_HIGH) { cur_match[bestIdx2] = i; nmatches++; }
+  }
+  return nmatches;
+}
+
+// LSDmatcher::SearchByProjection(F, vpMapLines, th)
+int oracle_line_search_by_projection_lines(const void* kls_, const double* lfunc, const uint8_t* desc, int n,
+                                           const float* bounds, int n_ml, const uint8_t* in_view, const float* proj,
+                                           const float* view_cos, const uint8_t* ml_desc, float th, float nnratio,
+                                           const uint8_t* preassigned, int* match) {
+  const KeyLine* k = (const KeyLine*)kls_;
+  Grid g; g.init(bounds);
+  assign_lines(g, k, n);
+  const int TH_HIGH = 80;
+  int nmatches = 0;
+  const bool bFactor = th != 1.0;
+  for (int i = 0; i < n; i++) match[i] = (preassigned && preassigned[i]) ? -2 : -1;
+  std::vector<int> cand;
+  for (int iML = 0; iML < n_ml; iML++) {
+    if (!in_view[iML]) continue;
+    float r = (view_cos[iML] > 0.998) ? 5.0f : 8.0f;  // LSDmatcher::RadiusByViewingCos (LSDmatcher.cpp:1004-1010)
+    if (bFactor) r *= th;
+    const float* p = proj + 4 * iML;
+    features_in_area_line(g, k, lfunc, p[0], p[1], p[2], p[3], r, 0.998f, cand);
+    if (cand.empty()) continue;
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    for (int idx : cand) {
+      if (match[idx] != -1) continue;
+      const int dist = descriptor_distance(ml_desc + 32 * iML, desc + 32 * idx);
+      if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = k[idx].octave; bestIdx = idx; }
+      else if (dist < bestDist2) { bestLevel2 = k[idx].octave; bestDist2 = dist; }
+    }
+    if (bestDist <= TH_HIGH) {
+      if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+      match[bestIdx] = iML;
+      nmatches++;
+    }
+  }
+  return nmatches;
+}
+}

@@ -136,3 +136,146 @@ class ORBextractor:
         out = np.zeros(max(n, 1), KP_DTYPE)
         check(lib().pl_orb_debug_candidates(self._h, frame, level, _p(out), n))
         return out[:n]
+
+
+# ---------------------------------------------------------------------------------------------- matching
+def _u8(a):
+    return np.ascontiguousarray(a, np.uint8)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, np.int32)
+
+
+def frame_assign_grid(keys_un, bounds):
+    """Frame::AssignFeaturesToGrid (reference src/Frame.cc:278-294) -> CSR (cell_start[3073], cell_items[n])."""
+    keys = np.ascontiguousarray(keys_un); b = _f32(bounds)
+    start = np.zeros(64 * 48 + 1, np.int32); items = np.zeros(max(len(keys), 1), np.int32)
+    check(lib().pl_frame_assign_grid(_p(keys), len(keys), _p(b), _p(start), _p(items)))
+    return start, items[:start[-1]]
+
+
+class ORBmatcher:
+    """Mirror of ORB_SLAM2::ORBmatcher (reference include/ORBmatcher.h:37-102) on flat frame arrays."""
+    TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30
+
+    def __init__(self, nnratio=0.6, checkOri=True):
+        self.mfNNratio, self.mbCheckOrientation = float(nnratio), bool(checkOri)
+
+    @staticmethod
+    def DescriptorDistance(a, b):
+        a, b = _u8(a).reshape(-1, 32), _u8(b).reshape(-1, 32)
+        out = np.zeros(len(a), np.int32)
+        check(lib().pl_descriptor_distance_batch(_p(a), _p(b), len(a), _p(out)))
+        return out if len(out) > 1 else int(out[0])
+
+    def SearchForInitialization(self, keys1, desc1, keys2, desc2, bounds, vbPrevMatched, windowSize=10):
+        k1, k2 = np.ascontiguousarray(keys1), np.ascontiguousarray(keys2)
+        d1, d2 = _u8(desc1), _u8(desc2)
+        pm = _f32(vbPrevMatched).copy(); b = _f32(bounds)
+        m = np.zeros(max(len(k1), 1), np.int32)
+        f = lib().pl_orb_search_for_initialization
+        f.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_float, C.c_int]
+        nm = check(f(_p(k1), _p(d1), len(k1), _p(k2), _p(d2), len(k2), _p(b), _p(pm), _p(m), int(windowSize),
+                     self.mfNNratio, int(self.mbCheckOrientation)))
+        return nm, m[:len(k1)], pm
+
+    def SearchByProjectionLast(self, keys_cur, desc_cur, bounds, Tcw, K, scale_factors, last_valid, last_pos,
+                               last_desc, last_octave, last_angle, th, preassigned=None):
+        """SearchByProjection(CurrentFrame, LastFrame, th, bMono=True)."""
+        kc, dc = np.ascontiguousarray(keys_cur), _u8(desc_cur)
+        arr = [_f32(bounds), _f32(Tcw), _f32(K), _f32(scale_factors), _u8(last_valid), _f32(last_pos), _u8(last_desc),
+               _i32(last_octave), _f32(last_angle)]
+        pre = None if preassigned is None else _u8(preassigned)
+        m = np.zeros(max(len(kc), 1), np.int32)
+        f = lib().pl_orb_search_by_projection_last
+        f.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_float, C.c_int, vp, vp]
+        nm = check(f(_p(kc), _p(dc), len(kc), _p(arr[0]), _p(arr[1]), _p(arr[2]), _p(arr[3]), len(arr[3]), len(arr[4]),
+                     _p(arr[4]), _p(arr[5]), _p(arr[6]), _p(arr[7]), _p(arr[8]), float(th),
+                     int(self.mbCheckOrientation), _p(pre), _p(m)))
+        return nm, m[:len(kc)]
+
+    def SearchByProjectionPoints(self, keys, desc, bounds, scale_factors, in_view, proj, level, view_cos, mp_desc, th=3,
+                                 preassigned=None):
+        """SearchByProjection(F, vpMapPoints, th)."""
+        k, d = np.ascontiguousarray(keys), _u8(desc)
+        arr = [_f32(bounds), _f32(scale_factors), _u8(in_view), _f32(proj), _i32(level), _f32(view_cos), _u8(mp_desc)]
+        pre = None if preassigned is None else _u8(preassigned)
+        m = np.zeros(max(len(k), 1), np.int32)
+        f = lib().pl_orb_search_by_projection_points
+        f.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp]
+        nm = check(f(_p(k), _p(d), len(k), _p(arr[0]), _p(arr[1]), len(arr[1]), len(arr[2]), _p(arr[2]), _p(arr[3]),
+                     _p(arr[4]), _p(arr[5]), _p(arr[6]), float(th), self.mfNNratio, _p(pre), _p(m)))
+        return nm, m[:len(k)]
+
+
+class LSDmatcher:
+    """Mirror of ORB_SLAM2::LSDmatcher (reference include/LSDmatcher.h:22-76) on flat arrays."""
+    TH_HIGH, TH_LOW = 80, 50
+
+    def __init__(self, nnratio=0.7, checkOri=True):
+        self.mfNNratio, self.mbCheckOrientation = float(nnratio), bool(checkOri)
+
+    DescriptorDistance = ORBmatcher.DescriptorDistance
+
+    @staticmethod
+    def knnMatch(d1, d2):
+        """cv::BFMatcher(NORM_HAMMING).knnMatch(d1, d2, k=2) as used by FrameBFMatch."""
+        d1, d2 = _u8(d1), _u8(d2)
+        idx = np.zeros((max(len(d1), 1), 2), np.int32); dist = np.zeros((max(len(d1), 1), 2), np.int32)
+        check(lib().pl_match_bf_knn2(_p(d1), len(d1), _p(d2), len(d2), _p(idx), _p(dist)))
+        return idx[:len(d1)], dist[:len(d1)]
+
+    def FrameBFMatch(self, ldesc1, ldesc2, TH=50.0):
+        d1, d2 = _u8(ldesc1), _u8(ldesc2)
+        m = np.zeros(max(len(d1), 1), np.int32)
+        f = lib().pl_lsd_frame_bf_match
+        f.argtypes = [vp, C.c_int, vp, C.c_int, C.c_float, C.c_float, vp]
+        check(f(_p(d1), len(d1), _p(d2), len(d2), float(TH), self.mfNNratio, _p(m)))
+        return m[:len(d1)]
+
+    def SearchDouble(self, ldesc1, ldesc2):
+        d1, d2 = _u8(ldesc1), _u8(ldesc2)
+        m = np.zeros(max(len(d1), 1), np.int32)
+        f = lib().pl_lsd_search_double
+        f.argtypes = [vp, C.c_int, vp, C.c_int, C.c_float, vp]
+        nm = check(f(_p(d1), len(d1), _p(d2), len(d2), self.mfNNratio, _p(m)))
+        return nm, m[:len(d1)]
+
+
+# ---------------------------------------------------------------------------------------------- pose-only LM
+class Optimizer:
+    """Mirror of ORB_SLAM2::Optimizer's pose-only entry points (reference include/Optimizer.h:56-65) on flat
+    arrays: each call takes what the reference reads from the Frame and returns (n_inliers, Tcw, mvbOutlier,
+    mvbLineOutlier, lm_iterations)."""
+
+    @staticmethod
+    def _run(mode, Tcw, K, pt_obs, pt_inv_sigma2, pt_Xw, line_func, line_Xw):
+        Tcw, K = _f32(Tcw), _f32(K)
+        po = _f32(pt_obs).reshape(-1, 2); pw = _f32(pt_inv_sigma2); px = _f32(pt_Xw).reshape(-1, 3)
+        lf = np.ascontiguousarray(line_func, np.float64).reshape(-1, 3)
+        lx = np.ascontiguousarray(line_Xw, np.float64).reshape(-1, 6)
+        Tout = np.zeros((4, 4), np.float32)
+        pout = np.zeros(max(len(po), 1), np.uint8); lout = np.zeros(max(len(lf), 1), np.uint8)
+        its = C.c_int(0)
+        f = lib().pl_pose_optimization
+        f.argtypes = [C.c_int, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
+        n = check(f(mode, _p(Tcw), _p(K), len(po), _p(po), _p(pw), _p(px), len(lf), _p(lf), _p(lx), _p(Tout), _p(pout),
+                    _p(lout), C.byref(its)))
+        return n, Tout, pout[:len(po)].astype(bool), lout[:len(lf)].astype(bool), its.value
+
+    @staticmethod
+    def PoseOptimization(Tcw, K, pt_obs, pt_inv_sigma2, pt_Xw, line_func, line_Xw):
+        return Optimizer._run(0, Tcw, K, pt_obs, pt_inv_sigma2, pt_Xw, line_func, line_Xw)
+
+    @staticmethod
+    def PoseOptimizationWithPoints(Tcw, K, pt_obs, pt_inv_sigma2, pt_Xw):
+        return Optimizer._run(1, Tcw, K, pt_obs, pt_inv_sigma2, pt_Xw, np.zeros((0, 3)), np.zeros((0, 6)))
+
+    @staticmethod
+    def PoseOptimizationWithLines(Tcw, K, line_func, line_Xw):
+        return Optimizer._run(2, Tcw, K, np.zeros((0, 2)), np.zeros(0), np.zeros((0, 3)), line_func, line_Xw)

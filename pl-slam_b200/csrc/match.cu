@@ -1,0 +1,730 @@
+// Descriptor matching for batches of frames on sm_100a.
+//
+// Replaces (reference file:line)
+//   ORBmatcher::DescriptorDistance / LSDmatcher::DescriptorDistance   ORBmatcher.cc:1764-1780, LSDmatcher.cpp:654-670
+//   Frame::AssignFeaturesToGrid, PosInGrid, GetFeaturesInArea         Frame.cc:278-294, :893-903, :713-766
+//   Frame::AssignFeaturesToGridForLine, GetFeaturesInAreaForLine      Frame.cc:296-320, :768-842, lineIterator.cpp
+//   ORBmatcher::SearchForInitialization                               ORBmatcher.cc:455-572
+//   ORBmatcher::SearchByProjection(F, LastFrame, th, mono)            ORBmatcher.cc:1441-1585
+//   ORBmatcher::SearchByProjection(F, vpMapPoints, th)                ORBmatcher.cc:56-152
+//   LSDmatcher::FrameBFMatch + lineDescriptorMAD + SearchDouble       LSDmatcher.cpp:440-486, :627-652
+//   LSDmatcher::SearchByProjection (F,Last) / (F,vpMapLines)          LSDmatcher.cpp:72-176, :221-338
+//
+// The windowed searches are order dependent in the reference (a keypoint that received a match is skipped by later
+// queries), so each frame is walked by ONE warp in the reference's query order; inside a query the 32 lanes scan
+// the 64x48 bucket grid window and compute Hamming distances (8 x u32 xor + __popc) in parallel and the winner is
+// chosen with a packed (distance, traversal order) key, which reproduces "first best wins" exactly.
+// Frames of a batch are independent -> one warp (CTA) per frame, grid = B.
+
+#include "common.cuh"
+#include <vector>
+
+namespace pl {
+
+constexpr int GC = 64, GR = 48, NCELL = GC * GR, HISTO = 30;
+
+__device__ __forceinline__ int hamming256(const uint8_t* a, const uint8_t* b) {
+  const uint4* pa = reinterpret_cast<const uint4*>(a);
+  const uint4* pb = reinterpret_cast<const uint4*>(b);
+  uint4 a0 = pa[0], a1 = pa[1], b0 = pb[0], b1 = pb[1];
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t < v ? t : v;
+  }
+  return v;
+}
+
+struct GridP { float minX, minY, maxX, maxY, invW, invH; };
+__host__ __device__ inline GridP make_grid(const float* b) {
+  GridP g;
+  g.minX = b[0]; g.minY = b[1]; g.maxX = b[2]; g.maxY = b[3];
+  g.invW = (float)GC / (g.maxX - g.minX);
+  g.invH = (float)GR / (g.maxY - g.minY);
+  return g;
+}
+
+// Frame::AssignFeaturesToGrid by one warp: start[NCELL+1], items[n] (stable: ascending key index inside a cell)
+__device__ void build_point_grid(const PLKeyPoint* keys, int n, const GridP& g, unsigned short* start,
+                                 unsigned short* fill, unsigned short* items, int lane) {
+  for (int i = lane; i < NCELL; i += 32) fill[i] = 0;
+  __syncwarp();
+  for (int i0 = 0; i0 < n; i0 += 32) {  // counts; one chunk at a time so shared-memory updates never race
+    int i = i0 + lane, c = -1;
+    if (i < n) {
+      int px = (int)roundf(__fmul_rn(__fsub_rn(keys[i].x, g.minX), g.invW));
+      int py = (int)roundf(__fmul_rn(__fsub_rn(keys[i].y, g.minY), g.invH));
+      if (px >= 0 && px < GC && py >= 0 && py < GR) c = px * GR + py;
+    }
+    unsigned peers = __match_any_sync(0xffffffffu, c);
+    if (c >= 0 && (peers & ((1u << lane) - 1u)) == 0) fill[c] += (unsigned short)__popc(peers);
+    __syncwarp();
+  }
+  int run = 0;
+  for (int c0 = 0; c0 < NCELL; c0 += 32) {
+    int v = fill[c0 + lane], incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    start[c0 + lane] = (unsigned short)(run + incl - v);
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) start[NCELL] = (unsigned short)run;
+  __syncwarp();
+  for (int i = lane; i < NCELL; i += 32) fill[i] = 0;
+  __syncwarp();
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    int i = i0 + lane, c = -1;
+    if (i < n) {
+      int px = (int)roundf(__fmul_rn(__fsub_rn(keys[i].x, g.minX), g.invW));
+      int py = (int)roundf(__fmul_rn(__fsub_rn(keys[i].y, g.minY), g.invH));
+      if (px >= 0 && px < GC && py >= 0 && py < GR) c = px * GR + py;
+    }
+    unsigned peers = __match_any_sync(0xffffffffu, c);
+    unsigned lt = peers & ((1u << lane) - 1u);
+    if (c >= 0) items[start[c] + fill[c] + __popc(lt)] = (unsigned short)i;
+    __syncwarp();
+    if (c >= 0 && lt == 0) fill[c] += (unsigned short)__popc(peers);
+    __syncwarp();
+  }
+}
+
+struct Window { int x0, x1, y0, y1; bool ok; };
+__device__ __forceinline__ Window make_window(const GridP& g, float x, float y, float r) {
+  Window w;
+  w.ok = false;
+  w.x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, g.minX), r), g.invW)));
+  if (w.x0 >= GC) return w;
+  w.x1 = min(GC - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, g.minX), r), g.invW)));
+  if (w.x1 < 0) return w;
+  w.y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, g.minY), r), g.invH)));
+  if (w.y0 >= GR) return w;
+  w.y1 = min(GR - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, g.minY), r), g.invH)));
+  if (w.y1 < 0) return w;
+  w.ok = true;
+  return w;
+}
+
+// key layout: dist(12) | cell rank(12) | position in cell(20) | candidate index(20)
+__device__ __forceinline__ unsigned long long mk_key(int dist, int c, int j, int idx) {
+  return ((unsigned long long)dist << 52) | ((unsigned long long)c << 40) | ((unsigned long long)j << 20) |
+         (unsigned long long)idx;
+}
+constexpr unsigned long long KEY_NONE = ~0ull;
+__device__ __forceinline__ int key_dist(unsigned long long k) { return (int)(k >> 52); }
+__device__ __forceinline__ int key_idx(unsigned long long k) { return (int)(k & 0xfffff); }
+
+struct Top2 { unsigned long long best, second; };
+
+// Best and second-best candidate of GetFeaturesInArea(x,y,r,minLevel,maxLevel) for query descriptor q, with a
+// per-candidate skip predicate; semantics of the reference's sequential "dist<best / else dist<second" scan.
+template <typename Skip>
+__device__ __forceinline__ Top2 window_top2(const PLKeyPoint* keys, const uint8_t* desc, const unsigned short* start,
+                                            const unsigned short* items, const GridP& g, float x, float y, float r,
+                                            int minLevel, int maxLevel, const uint8_t* q, Skip skip, int lane) {
+  Top2 t;
+  t.best = KEY_NONE; t.second = KEY_NONE;
+  Window w = make_window(g, x, y, r);
+  if (!w.ok) return t;
+  const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+  const int ncy = w.y1 - w.y0 + 1, ncell = (w.x1 - w.x0 + 1) * ncy;
+  unsigned long long k1 = KEY_NONE, k2 = KEY_NONE;
+  for (int c = lane; c < ncell; c += 32) {
+    int ix = w.x0 + c / ncy, iy = w.y0 + c % ncy;
+    int cb = start[ix * GR + iy], ce = start[ix * GR + iy + 1];
+    for (int j = cb; j < ce; j++) {
+      int id = items[j];
+      const PLKeyPoint& kp = keys[id];
+      if (checkLevels) {
+        if (kp.octave < minLevel) continue;
+        if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+      }
+      if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
+      int dist = hamming256(q, desc + 32 * id);
+      if (skip(id, dist)) continue;
+      unsigned long long k = mk_key(dist, c, j - cb, id);
+      if (k < k1) { k2 = k1; k1 = k; }
+      else if (k < k2) k2 = k;
+    }
+  }
+  t.best = warp_min_u64(k1);
+  t.second = warp_min_u64(k1 == t.best ? k2 : k1);
+  return t;
+}
+
+// ORBmatcher::ComputeThreeMaxima on bin counts
+__device__ void three_maxima(const int* cnt, int& ind1, int& ind2, int& ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  ind1 = ind2 = ind3 = -1;
+  for (int i = 0; i < HISTO; i++) {
+    const int s = cnt[i];
+    if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+    else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+    else if (s > max3) { max3 = s; ind3 = i; }
+  }
+  if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+  else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+}
+__device__ __forceinline__ int rot_bin(float a1, float a2) {
+  float rot = __fsub_rn(a1, a2);
+  if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+  int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO));
+  if (bin == HISTO) bin = 0;
+  return bin;
+}
+
+struct SmemGrid {
+  unsigned short* start; unsigned short* fill; unsigned short* items;
+};
+__device__ __forceinline__ SmemGrid carve_grid(unsigned char* smem, int cap) {
+  SmemGrid s;
+  s.start = reinterpret_cast<unsigned short*>(smem);
+  s.fill = s.start + NCELL + 2;
+  s.items = s.fill + NCELL;
+  (void)cap;
+  return s;
+}
+static size_t grid_smem_bytes(int cap) { return (size_t)(NCELL + 2 + NCELL + cap) * 2; }
+
+// ------------------------------------------------------------------------------------------------ a18
+__global__ void __launch_bounds__(32) k_assign_grid(const PLKeyPoint* keys, const int* n, int cap, const float* bounds,
+                                                    int* out_start, int* out_items) {
+  extern __shared__ unsigned char smem[];
+  const int b = blockIdx.x, lane = threadIdx.x;
+  SmemGrid sg = carve_grid(smem, cap);
+  GridP g = make_grid(bounds);
+  const int nn = min(n[b], cap);
+  build_point_grid(keys + (long long)b * cap, nn, g, sg.start, sg.fill, sg.items, lane);
+  __syncwarp();
+  for (int i = lane; i <= NCELL; i += 32) out_start[(long long)b * (NCELL + 1) + i] = sg.start[i];
+  for (int i = lane; i < sg.start[NCELL]; i += 32) out_items[(long long)b * cap + i] = sg.items[i];
+}
+
+// ------------------------------------------------------------------------------------------------ a15
+struct SkipInit {
+  const int* matchedDist;
+  __device__ bool operator()(int id, int dist) const { return matchedDist[id] <= dist; }
+};
+
+__global__ void __launch_bounds__(32) k_search_init(const PLKeyPoint* keys1, const uint8_t* desc1, const int* n1,
+                                                    const PLKeyPoint* keys2, const uint8_t* desc2, const int* n2,
+                                                    int cap, const float* bounds, float* prev_matched, int* matches12,
+                                                    int* nmatches_out, int windowSize, float nnratio, int checkOri,
+                                                    int* scratch /* [B][2*cap] matchedDist, matches21 */) {
+  extern __shared__ unsigned char smem[];
+  __shared__ int hist[HISTO];
+  const int b = blockIdx.x, lane = threadIdx.x;
+  SmemGrid sg = carve_grid(smem, cap);
+  GridP g = make_grid(bounds);
+  const PLKeyPoint* k1 = keys1 + (long long)b * cap;
+  const PLKeyPoint* k2 = keys2 + (long long)b * cap;
+  const uint8_t* d1 = desc1 + (long long)b * cap * 32;
+  const uint8_t* d2 = desc2 + (long long)b * cap * 32;
+  const int N1 = min(n1[b], cap), N2 = min(n2[b], cap);
+  float* pm = prev_matched + (long long)b * cap * 2;
+  int* m12 = matches12 + (long long)b * cap;
+  int* matchedDist = scratch + (long long)b * 2 * cap;
+  int* m21 = matchedDist + cap;
+  build_point_grid(k2, N2, g, sg.start, sg.fill, sg.items, lane);
+  for (int i = lane; i < N1; i += 32) m12[i] = -1;
+  for (int i = lane; i < N2; i += 32) { matchedDist[i] = 0x7fffffff; m21[i] = -1; }
+  if (lane < HISTO) hist[lane] = 0;
+  __syncwarp();
+  unsigned char* bins = reinterpret_cast<unsigned char*>(sg.fill);  // rotation bin of query i1 (255 = none); fill is free now
+  for (int i = lane; i < N1; i += 32) bins[i] = 255;
+  __syncwarp();
+  int nmatches = 0;
+  SkipInit skip{matchedDist};
+  for (int i1 = 0; i1 < N1; i1++) {
+    if (k1[i1].octave > 0) continue;
+    Top2 t = window_top2(k2, d2, sg.start, sg.items, g, pm[2 * i1], pm[2 * i1 + 1], (float)windowSize, 0, 0,
+                         d1 + 32 * i1, skip, lane);
+    if (t.best == KEY_NONE) continue;
+    const int bestDist = key_dist(t.best), bestIdx2 = key_idx(t.best);
+    const float bestDist2 = (t.second == KEY_NONE) ? 2147483648.0f : (float)key_dist(t.second);  // (float)INT_MAX
+    if (bestDist <= 50 && (float)bestDist < __fmul_rn(bestDist2, nnratio)) {
+      int old = m21[bestIdx2];
+      __syncwarp();
+      if (old >= 0) nmatches--;
+      nmatches++;
+      if (lane == 0) {
+        if (old >= 0) m12[old] = -1;
+        m12[i1] = bestIdx2;
+        m21[bestIdx2] = i1;
+        matchedDist[bestIdx2] = bestDist;
+        if (checkOri) { int bin = rot_bin(k1[i1].angle, k2[bestIdx2].angle); bins[i1] = (unsigned char)bin; hist[bin]++; }
+      }
+      __syncwarp();
+    }
+  }
+  if (checkOri) {
+    int i1m, i2m, i3m;
+    three_maxima(hist, i1m, i2m, i3m);
+    int removed = 0;
+    for (int i = lane; i < N1; i += 32) {
+      int bin = bins[i];
+      if (bin != 255 && bin != i1m && bin != i2m && bin != i3m && m12[i] >= 0) { m12[i] = -1; removed++; }
+    }
+    nmatches -= warp_sum(removed);
+  }
+  __syncwarp();
+  for (int i = lane; i < N1; i += 32)
+    if (m12[i] >= 0) { pm[2 * i] = k2[m12[i]].x; pm[2 * i + 1] = k2[m12[i]].y; }
+  if (lane == 0) nmatches_out[b] = nmatches;
+}
+
+// ------------------------------------------------------------------------------------------------ a13 / a14
+struct SkipAssigned {
+  const int* match;
+  __device__ bool operator()(int id, int) const { return match[id] != -1; }
+};
+
+struct ProjLastArgs {
+  const PLKeyPoint* keys; const uint8_t* desc; const int* n; int cap;   // current frame [B][cap]
+  const float* bounds; const float* Tcw; const float* K; const float* scaleFactors; int nlevels;
+  const int* n_last; int cap_last; const uint8_t* last_valid; const float* last_pos; const uint8_t* last_desc;
+  const int* last_octave; const float* last_angle;
+  float th; int checkOri; const uint8_t* preassigned; int* match; int* nmatches;
+};
+
+__global__ void __launch_bounds__(32) k_search_proj_last(ProjLastArgs A) {
+  extern __shared__ unsigned char smem[];
+  __shared__ int hist[HISTO];
+  const int b = blockIdx.x, lane = threadIdx.x;
+  SmemGrid sg = carve_grid(smem, A.cap);
+  GridP g = make_grid(A.bounds);
+  const PLKeyPoint* kc = A.keys + (long long)b * A.cap;
+  const uint8_t* dc = A.desc + (long long)b * A.cap * 32;
+  const int N = min(A.n[b], A.cap), NL = min(A.n_last[b], A.cap_last);
+  int* match = A.match + (long long)b * A.cap;
+  const float* T = A.Tcw + 16 * b;
+  const long long lb = (long long)b * A.cap_last;
+  build_point_grid(kc, N, g, sg.start, sg.fill, sg.items, lane);
+  for (int i = lane; i < N; i += 32) match[i] = (A.preassigned && A.preassigned[(long long)b * A.cap + i]) ? -2 : -1;
+  if (lane < HISTO) hist[lane] = 0;
+  unsigned char* bins = reinterpret_cast<unsigned char*>(sg.fill);
+  __syncwarp();
+  for (int i = lane; i < N; i += 32) bins[i] = 255;
+  __syncwarp();
+  int nmatches = 0;
+  SkipAssigned skip{match};
+  const float fx = A.K[0], fy = A.K[1], cx = A.K[2], cy = A.K[3];
+  for (int i = 0; i < NL; i++) {
+    if (!A.last_valid[lb + i]) continue;
+    const float* X = A.last_pos + (lb + i) * 3;
+    float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], X[0]), __fmul_rn(T[1], X[1])), __fmul_rn(T[2], X[2])), T[3]);
+    float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], X[0]), __fmul_rn(T[5], X[1])), __fmul_rn(T[6], X[2])), T[7]);
+    float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], X[0]), __fmul_rn(T[9], X[1])), __fmul_rn(T[10], X[2])), T[11]);
+    const float invzc = (float)(1.0 / (double)zc);
+    if (invzc < 0) continue;
+    float u = __fadd_rn(__fmul_rn(__fmul_rn(fx, xc), invzc), cx);
+    float v = __fadd_rn(__fmul_rn(__fmul_rn(fy, yc), invzc), cy);
+    if (u < g.minX || u > g.maxX) continue;
+    if (v < g.minY || v > g.maxY) continue;
+    const int oct = A.last_octave[lb + i];
+    const float radius = __fmul_rn(A.th, A.scaleFactors[oct]);
+    Top2 t = window_top2(kc, dc, sg.start, sg.items, g, u, v, radius, oct - 1, oct + 1, A.last_desc + (lb + i) * 32,
+                         skip, lane);
+    if (t.best == KEY_NONE) continue;
+    const int bestDist = key_dist(t.best), bestIdx2 = key_idx(t.best);
+    if (bestDist <= 100) {
+      nmatches++;
+      if (lane == 0) {
+        match[bestIdx2] = i;
+        if (A.checkOri) { int bin = rot_bin(A.last_angle[lb + i], kc[bestIdx2].angle); bins[bestIdx2] = (unsigned char)bin; hist[bin]++; }
+      }
+      __syncwarp();
+    }
+  }
+  if (A.checkOri) {
+    int i1m, i2m, i3m;
+    three_maxima(hist, i1m, i2m, i3m);
+    int removed = 0;
+    for (int i = lane; i < N; i += 32) {
+      int bin = bins[i];
+      if (bin != 255 && bin != i1m && bin != i2m && bin != i3m) { match[i] = -1; removed++; }
+    }
+    nmatches -= warp_sum(removed);
+  }
+  if (lane == 0) A.nmatches[b] = nmatches;
+}
+
+struct ProjPointsArgs {
+  const PLKeyPoint* keys; const uint8_t* desc; const int* n; int cap;
+  const float* bounds; const float* scaleFactors;
+  const int* n_mp; int cap_mp; const uint8_t* in_view; const float* proj; const int* level; const float* view_cos;
+  const uint8_t* mp_desc; float th; float nnratio; const uint8_t* preassigned; int* match; int* nmatches;
+};
+
+__global__ void __launch_bounds__(32) k_search_proj_points(ProjPointsArgs A) {
+  extern __shared__ unsigned char smem[];
+  const int b = blockIdx.x, lane = threadIdx.x;
+  SmemGrid sg = carve_grid(smem, A.cap);
+  GridP g = make_grid(A.bounds);
+  const PLKeyPoint* k = A.keys + (long long)b * A.cap;
+  const uint8_t* d = A.desc + (long long)b * A.cap * 32;
+  const int N = min(A.n[b], A.cap), NM = min(A.n_mp[b], A.cap_mp);
+  int* match = A.match + (long long)b * A.cap;
+  const long long mb = (long long)b * A.cap_mp;
+  build_point_grid(k, N, g, sg.start, sg.fill, sg.items, lane);
+  for (int i = lane; i < N; i += 32) match[i] = (A.preassigned && A.preassigned[(long long)b * A.cap + i]) ? -2 : -1;
+  __syncwarp();
+  int nmatches = 0;
+  SkipAssigned skip{match};
+  const bool bFactor = A.th != 1.0f;
+  for (int i = 0; i < NM; i++) {
+    if (!A.in_view[mb + i]) continue;
+    const int lvl = A.level[mb + i];
+    float r = ((double)A.view_cos[mb + i] > 0.998) ? 2.5f : 4.0f;  // float vs the double literal 0.998
+    if (bFactor) r = __fmul_rn(r, A.th);
+    Top2 t = window_top2(k, d, sg.start, sg.items, g, A.proj[(mb + i) * 2], A.proj[(mb + i) * 2 + 1],
+                         __fmul_rn(r, A.scaleFactors[lvl]), lvl - 1, lvl, A.mp_desc + (mb + i) * 32, skip, lane);
+    if (t.best == KEY_NONE) continue;
+    const int bestDist = key_dist(t.best), bestIdx = key_idx(t.best);
+    if (bestDist <= 100) {
+      if (t.second != KEY_NONE) {
+        const int bestDist2 = key_dist(t.second);
+        if (k[bestIdx].octave == k[key_idx(t.second)].octave && (float)bestDist > __fmul_rn(A.nnratio, (float)bestDist2))
+          continue;
+      }
+      nmatches++;
+      if (lane == 0) match[bestIdx] = i;
+      __syncwarp();
+    }
+  }
+  if (lane == 0) A.nmatches[b] = nmatches;
+}
+
+// ------------------------------------------------------------------------------------------------ a16
+// cv::BFMatcher(NORM_HAMMING).knnMatch(k=2): one warp per query row; ties -> lower train index.
+__device__ __forceinline__ void knn2_row(const uint8_t* q, const uint8_t* train, int n2, int lane, int& i0, int& d0,
+                                         int& i1, int& d1v) {
+  unsigned long long k1 = KEY_NONE, k2 = KEY_NONE;
+  for (int t = lane; t < n2; t += 32) {
+    unsigned long long k = ((unsigned long long)hamming256(q, train + 32 * t) << 32) | (unsigned)t;
+    if (k < k1) { k2 = k1; k1 = k; } else if (k < k2) k2 = k;
+  }
+  unsigned long long b = warp_min_u64(k1);
+  unsigned long long s = warp_min_u64(k1 == b ? k2 : k1);
+  i0 = b == KEY_NONE ? -1 : (int)(b & 0xffffffffu); d0 = b == KEY_NONE ? -1 : (int)(b >> 32);
+  i1 = s == KEY_NONE ? -1 : (int)(s & 0xffffffffu); d1v = s == KEY_NONE ? -1 : (int)(s >> 32);
+}
+
+__global__ void __launch_bounds__(128) k_bf_knn2(const uint8_t* d1, const int* n1, const uint8_t* d2, const int* n2,
+                                                 int cap1, int cap2, int* idx, int* dist) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int N1 = min(n1[b], cap1), N2 = min(n2[b], cap2);
+  if (q >= N1) return;
+  int i0, dd0, i1, dd1;
+  knn2_row(d1 + ((long long)b * cap1 + q) * 32, d2 + (long long)b * cap2 * 32, N2, lane, i0, dd0, i1, dd1);
+  if (lane == 0) {
+    long long o = ((long long)b * cap1 + q) * 2;
+    idx[o] = i0; idx[o + 1] = i1; dist[o] = dd0; dist[o + 1] = dd1;
+  }
+}
+
+// FrameBFMatch (one direction) by one CTA of 128 threads; results in shared memory (m[q] = train idx or -1).
+// d12 = d1-d0 is an integer in [0,256] -> the two medians of lineDescriptorMAD come from 257-bin histograms.
+__device__ void frame_bf_match_cta(const uint8_t* da, int na, const uint8_t* db, int nb, float TH, float nnratio,
+                                   short* m, short* bd0, short* bd1, int* hist /*[257]*/) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < na; i += 128) m[i] = -1;
+  for (int i = tid; i < 257; i += 128) hist[i] = 0;
+  __syncthreads();
+  if (na < 1 || nb < 2) return;  // uniform
+  for (int q = wid; q < na; q += 4) {
+    int i0, d0, i1, d1;
+    knn2_row(da + 32 * q, db, nb, lane, i0, d0, i1, d1);
+    if (lane == 0) { m[q] = (short)i0; bd0[q] = (short)d0; bd1[q] = (short)d1; atomicAdd(&hist[d1 - d0], 1); }
+  }
+  __syncthreads();
+  __shared__ int s_med, s_mad;
+  if (tid == 0) {  // element na/2 of the DESCENDING sort of d12
+    int need = na / 2, acc = 0, v = 256;
+    for (; v >= 0; v--) { acc += hist[v]; if (acc > need) break; }
+    s_med = v;
+  }
+  __syncthreads();
+  const int med = s_med;
+  for (int i = tid; i < 257; i += 128) hist[i] = 0;
+  __syncthreads();
+  for (int q = tid; q < na; q += 128) atomicAdd(&hist[abs((int)bd1[q] - (int)bd0[q] - med)], 1);
+  __syncthreads();
+  if (tid == 0) {  // element na/2 of the ASCENDING sort of |d12 - median|
+    int need = na / 2, acc = 0, v = 0;
+    for (; v <= 256; v++) { acc += hist[v]; if (acc > need) break; }
+    s_mad = v;
+  }
+  __syncthreads();
+  const double nn12_th = 1.4826 * (double)(float)s_mad * 0.5;  // nn12_mad * 0.5, in double as the reference
+  for (int q = tid; q < na; q += 128) {
+    const float d0 = (float)bd0[q], d1 = (float)bd1[q];
+    const double dist_12 = (double)(d1 - d0);
+    if (!(dist_12 > nn12_th && d0 < TH && d0 < __fmul_rn(nnratio, d1))) m[q] = -1;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) k_search_double(const uint8_t* d1, const int* n1, const uint8_t* d2,
+                                                       const int* n2, int cap1, int cap2, float TH, float nnratio,
+                                                       int mutual, int* matches, int* nmatches) {
+  extern __shared__ unsigned char smem[];
+  __shared__ int hist[257];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int N1 = min(n1[b], cap1), N2 = min(n2[b], cap2);
+  short* m1 = reinterpret_cast<short*>(smem);
+  short* m2 = m1 + cap1;
+  short* bd0 = m2 + cap2;
+  short* bd1 = bd0 + max(cap1, cap2);
+  const uint8_t* a = d1 + (long long)b * cap1 * 32;
+  const uint8_t* c = d2 + (long long)b * cap2 * 32;
+  int* out = matches + (long long)b * cap1;
+  if (N1 == 0 || N2 == 0) {
+    for (int i = tid; i < N1; i += 128) out[i] = -1;
+    if (tid == 0) nmatches[b] = 0;
+    return;
+  }
+  frame_bf_match_cta(a, N1, c, N2, TH, nnratio, m1, bd0, bd1, hist);
+  __syncthreads();
+  if (mutual) {
+    frame_bf_match_cta(c, N2, a, N1, TH, nnratio, m2, bd0, bd1, hist);
+    __syncthreads();
+  }
+  int cnt = 0;
+  for (int i = tid; i < N1; i += 128) {
+    int j = m1[i];
+    if (j >= 0 && mutual && m2[j] != i) j = -1;
+    out[i] = j;
+    cnt += (j >= 0);
+  }
+  __shared__ int total;
+  if (tid == 0) total = 0;
+  __syncthreads();
+  atomicAdd(&total, cnt);
+  __syncthreads();
+  if (tid == 0) nmatches[b] = total;
+}
+
+}  // namespace pl
+
+// ================================================================================================ C ABI
+using namespace pl;
+
+namespace {
+struct Stage {  // tiny RAII helper for the host-pointer wrappers
+  std::vector<void*> ptrs;
+  ~Stage() { for (void* p : ptrs) cudaFree(p); }
+  template <typename T> T* up(const T* h, size_t n) {
+    T* d = nullptr;
+    if (cudaMalloc((void**)&d, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    ptrs.push_back(d);
+    if (h && n) cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice);
+    return d;
+  }
+  template <typename T> T* alloc(size_t n) { return up<T>(nullptr, n); }
+};
+template <typename T> int down(T* h, const T* d, size_t n) {
+  PL_CUDA(cudaMemcpy(h, d, n * sizeof(T), cudaMemcpyDeviceToHost));
+  return PL_OK;
+}
+}  // namespace
+
+extern "C" int pl_descriptor_distance_batch(const uint8_t* a, const uint8_t* b, int n, int* out) {
+  // convenience for tests: n independent 32-byte pairs, host pointers
+  PL_ARG(a && b && out && n >= 0);
+  int rc = require_device(); if (rc) return rc;
+  Stage s;
+  uint8_t* da = s.up(a, (size_t)n * 32); uint8_t* db = s.up(b, (size_t)n * 32);
+  int one = 1; (void)one;
+  std::vector<int> n1(1, n);
+  // reuse k_bf_knn2 with cap2 = 1 per pair would be wasteful; do pairs as n batches of 1x1
+  std::vector<int> ones(n, 1);
+  int* dn = s.up(ones.data(), (size_t)n);
+  int* idx = s.alloc<int>((size_t)n * 2); int* dist = s.alloc<int>((size_t)n * 2);
+  PL_ARG(da && db && dn && idx && dist);
+  if (n) { k_bf_knn2<<<dim3(1, n), 128>>>(da, dn, db, dn, 1, 1, idx, dist); PL_LAUNCH_CHECK(); }
+  std::vector<int> hd((size_t)n * 2);
+  rc = down(hd.data(), dist, (size_t)n * 2); if (rc) return rc;
+  for (int i = 0; i < n; i++) out[i] = hd[2 * i];
+  return PL_OK;
+}
+
+extern "C" int pl_frame_assign_grid_dev(const PLKeyPoint* keys, const int* n, int cap, int B, const float* bounds,
+                                        int* cell_start, int* cell_items, void* stream) {
+  PL_ARG(keys && n && bounds && cell_start && cell_items && cap > 0 && cap < 65535 && B > 0);
+  k_assign_grid<<<B, 32, grid_smem_bytes(cap), (cudaStream_t)stream>>>(keys, n, cap, bounds, cell_start, cell_items);
+  PL_LAUNCH_CHECK();
+  return PL_OK;
+}
+extern "C" int pl_frame_assign_grid(const PLKeyPoint* keys, int n, const float* bounds, int* cell_start,
+                                    int* cell_items) {
+  PL_ARG(keys && bounds && cell_start && cell_items && n >= 0 && n < 65535);
+  int rc = require_device(); if (rc) return rc;
+  Stage s;
+  int cap = std::max(n, 1);
+  PLKeyPoint* dk = s.up(keys, (size_t)n); int* dn = s.up(&n, 1); float* db = s.up(bounds, 4);
+  int* ds = s.alloc<int>(NCELL + 1); int* di = s.alloc<int>(cap);
+  PL_ARG(dk && dn && db && ds && di);
+  rc = pl_frame_assign_grid_dev(dk, dn, cap, 1, db, ds, di, nullptr); if (rc) return rc;
+  rc = down(cell_start, ds, NCELL + 1); if (rc) return rc;
+  return down(cell_items, di, (size_t)n);
+}
+
+extern "C" int pl_orb_search_for_initialization_dev(const PLKeyPoint* keys1, const uint8_t* desc1, const int* n1,
+                                                    const PLKeyPoint* keys2, const uint8_t* desc2, const int* n2,
+                                                    int cap, int B, const float* bounds, float* prev_matched,
+                                                    int* matches12, int* nmatches, int window_size, float nnratio,
+                                                    int check_orientation, int* scratch, void* stream) {
+  PL_ARG(keys1 && desc1 && n1 && keys2 && desc2 && n2 && bounds && prev_matched && matches12 && nmatches && scratch);
+  PL_ARG(cap > 0 && cap <= 6144 && B > 0);
+  size_t sm = grid_smem_bytes(cap);
+  PL_CUDA(cudaFuncSetAttribute(k_search_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_search_init<<<B, 32, sm, (cudaStream_t)stream>>>(keys1, desc1, n1, keys2, desc2, n2, cap, bounds, prev_matched,
+                                                     matches12, nmatches, window_size, nnratio, check_orientation,
+                                                     scratch);
+  PL_LAUNCH_CHECK();
+  return PL_OK;
+}
+
+extern "C" int pl_orb_search_for_initialization(const PLKeyPoint* keys1, const uint8_t* desc1, int n1,
+                                                const PLKeyPoint* keys2, const uint8_t* desc2, int n2,
+                                                const float* bounds, float* prev_matched, int* matches12,
+                                                int window_size, float nnratio, int check_orientation) {
+  PL_ARG(keys1 && desc1 && keys2 && desc2 && bounds && prev_matched && matches12 && n1 >= 0 && n2 >= 0);
+  int rc = require_device(); if (rc) return rc;
+  Stage s;
+  int cap = std::max(std::max(n1, n2), 1);
+  std::vector<PLKeyPoint> k1(cap), k2(cap);
+  std::vector<uint8_t> d1((size_t)cap * 32), d2((size_t)cap * 32);
+  std::vector<float> pm((size_t)cap * 2, 0.f);
+  if (n1) { memcpy(k1.data(), keys1, n1 * sizeof(PLKeyPoint)); memcpy(d1.data(), desc1, (size_t)n1 * 32); memcpy(pm.data(), prev_matched, (size_t)n1 * 8); }
+  if (n2) { memcpy(k2.data(), keys2, n2 * sizeof(PLKeyPoint)); memcpy(d2.data(), desc2, (size_t)n2 * 32); }
+  PLKeyPoint* dk1 = s.up(k1.data(), cap); PLKeyPoint* dk2 = s.up(k2.data(), cap);
+  uint8_t* dd1 = s.up(d1.data(), d1.size()); uint8_t* dd2 = s.up(d2.data(), d2.size());
+  int* dn1 = s.up(&n1, 1); int* dn2 = s.up(&n2, 1); float* db = s.up(bounds, 4); float* dpm = s.up(pm.data(), pm.size());
+  int* dm = s.alloc<int>(cap); int* dnm = s.alloc<int>(1); int* scr = s.alloc<int>((size_t)2 * cap);
+  PL_ARG(dk1 && dk2 && dd1 && dd2 && dn1 && dn2 && db && dpm && dm && dnm && scr);
+  rc = pl_orb_search_for_initialization_dev(dk1, dd1, dn1, dk2, dd2, dn2, cap, 1, db, dpm, dm, dnm, window_size, nnratio,
+                                            check_orientation, scr, nullptr);
+  if (rc) return rc;
+  int nm = 0;
+  rc = down(&nm, dnm, 1); if (rc) return rc;
+  if (n1) { rc = down(matches12, dm, (size_t)n1); if (rc) return rc; rc = down(prev_matched, dpm, (size_t)n1 * 2); if (rc) return rc; }
+  return nm;
+}
+
+extern "C" int pl_orb_search_by_projection_last(const PLKeyPoint* keys_cur, const uint8_t* desc_cur, int n_cur,
+                                                const float* bounds, const float* Tcw, const float* K,
+                                                const float* scale_factors, int nlevels, int n_last,
+                                                const uint8_t* last_valid, const float* last_pos,
+                                                const uint8_t* last_desc, const int* last_octave,
+                                                const float* last_angle, float th, int check_orientation,
+                                                const uint8_t* cur_preassigned, int* cur_match) {
+  PL_ARG(keys_cur && desc_cur && bounds && Tcw && K && scale_factors && cur_match && n_cur >= 0 && n_cur <= 6144 && n_last >= 0);
+  int rc = require_device(); if (rc) return rc;
+  Stage s;
+  const int cap = std::max(n_cur, 1), capl = std::max(n_last, 1);
+  ProjLastArgs A;
+  A.keys = s.up(keys_cur, n_cur); A.desc = s.up(desc_cur, (size_t)n_cur * 32); A.n = s.up(&n_cur, 1); A.cap = cap;
+  A.bounds = s.up(bounds, 4); A.Tcw = s.up(Tcw, 16); A.K = s.up(K, 4); A.scaleFactors = s.up(scale_factors, nlevels);
+  A.nlevels = nlevels; A.n_last = s.up(&n_last, 1); A.cap_last = capl;
+  A.last_valid = s.up(last_valid, n_last); A.last_pos = s.up(last_pos, (size_t)n_last * 3);
+  A.last_desc = s.up(last_desc, (size_t)n_last * 32); A.last_octave = s.up(last_octave, n_last);
+  A.last_angle = s.up(last_angle, n_last);
+  A.th = th; A.checkOri = check_orientation;
+  A.preassigned = cur_preassigned ? s.up(cur_preassigned, n_cur) : nullptr;
+  A.match = s.alloc<int>(cap); A.nmatches = s.alloc<int>(1);
+  PL_ARG(A.keys && A.desc && A.match && A.nmatches && A.last_pos && A.last_desc);
+  size_t sm = grid_smem_bytes(cap);
+  PL_CUDA(cudaFuncSetAttribute(k_search_proj_last, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_search_proj_last<<<1, 32, sm>>>(A);
+  PL_LAUNCH_CHECK();
+  int nm = 0;
+  rc = down(&nm, A.nmatches, 1); if (rc) return rc;
+  if (n_cur) { rc = down(cur_match, A.match, (size_t)n_cur); if (rc) return rc; }
+  return nm;
+}
+
+extern "C" int pl_orb_search_by_projection_points(const PLKeyPoint* keys, const uint8_t* desc, int n,
+                                                  const float* bounds, const float* scale_factors, int nlevels,
+                                                  int n_mp, const uint8_t* in_view, const float* proj,
+                                                  const int* level, const float* view_cos, const uint8_t* mp_desc,
+                                                  float th, float nnratio, const uint8_t* preassigned, int* match) {
+  PL_ARG(keys && desc && bounds && scale_factors && match && n >= 0 && n_mp >= 0);
+  int rc = require_device(); if (rc) return rc;
+  Stage s;
+  const int cap = std::max(n, 1), capm = std::max(n_mp, 1);
+  ProjPointsArgs A;
+  A.keys = s.up(keys, n); A.desc = s.up(desc, (size_t)n * 32); A.n = s.up(&n, 1); A.cap = cap;
+  A.bounds = s.up(bounds, 4); A.scaleFactors = s.up(scale_factors, nlevels);
+  A.n_mp = s.up(&n_mp, 1); A.cap_mp = capm; A.in_view = s.up(in_view, n_mp); A.proj = s.up(proj, (size_t)n_mp * 2);
+  A.level = s.up(level, n_mp); A.view_cos = s.up(view_cos, n_mp); A.mp_desc = s.up(mp_desc, (size_t)n_mp * 32);
+  A.th = th; A.nnratio = nnratio; A.preassigned = preassigned ? s.up(preassigned, n) : nullptr;
+  A.match = s.alloc<int>(cap); A.nmatches = s.alloc<int>(1);
+  PL_ARG(A.keys && A.desc && A.match && A.nmatches);
+  size_t sm = grid_smem_bytes(cap);
+  PL_CUDA(cudaFuncSetAttribute(k_search_proj_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_search_proj_points<<<1, 32, sm>>>(A);
+  PL_LAUNCH_CHECK();
+  int nm = 0;
+  rc = down(&nm, A.nmatches, 1); if (rc) return rc;
+  if (n) { rc = down(match, A.match, (size_t)n); if (rc) return rc; }
+  return nm;
+}
+
+extern "C" int pl_match_bf_knn2(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx, int* dist) {
+  PL_ARG(d1 && d2 && idx && dist && n1 >= 0 && n2 >= 0);
+  int rc = require_device(); if (rc) return rc;
+  if (n1 == 0) return PL_OK;
+  Stage s;
+  uint8_t* a = s.up(d1, (size_t)n1 * 32); uint8_t* b = s.up(d2, (size_t)std::max(n2, 1) * 32);
+  int* dn1 = s.up(&n1, 1); int* dn2 = s.up(&n2, 1);
+  int* di = s.alloc<int>((size_t)n1 * 2); int* dd = s.alloc<int>((size_t)n1 * 2);
+  PL_ARG(a && b && dn1 && dn2 && di && dd);
+  k_bf_knn2<<<dim3((n1 + 3) / 4, 1), 128>>>(a, dn1, b, dn2, n1, std::max(n2, 1), di, dd);
+  PL_LAUNCH_CHECK();
+  rc = down(idx, di, (size_t)n1 * 2); if (rc) return rc;
+  return down(dist, dd, (size_t)n1 * 2);
+}
+
+extern "C" int pl_lsd_search_double_dev(const uint8_t* d1, const int* n1, const uint8_t* d2, const int* n2, int cap1,
+                                        int cap2, int B, float th, float nnratio, int mutual, int* matches,
+                                        int* nmatches, void* stream) {
+  PL_ARG(d1 && n1 && d2 && n2 && matches && nmatches && cap1 > 0 && cap2 > 0 && cap1 < 32000 && cap2 < 32000 && B > 0);
+  size_t sm = (size_t)(cap1 + cap2 + 2 * std::max(cap1, cap2)) * sizeof(short);
+  PL_CUDA(cudaFuncSetAttribute(k_search_double, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_search_double<<<B, 128, sm, (cudaStream_t)stream>>>(d1, n1, d2, n2, cap1, cap2, th, nnratio, mutual, matches,
+                                                        nmatches);
+  PL_LAUNCH_CHECK();
+  return PL_OK;
+}
+
+static int search_double_host(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float th, float nnratio, int mutual,
+                              int* matches) {
+  PL_ARG(d1 && d2 && matches && n1 >= 0 && n2 >= 0);
+  int rc = require_device(); if (rc) return rc;
+  Stage s;
+  const int c1 = std::max(n1, 1), c2 = std::max(n2, 1);
+  uint8_t* a = s.up(d1, (size_t)n1 * 32); uint8_t* b = s.up(d2, (size_t)n2 * 32);
+  if (n1 == 0) a = s.alloc<uint8_t>(32);
+  if (n2 == 0) b = s.alloc<uint8_t>(32);
+  int* dn1 = s.up(&n1, 1); int* dn2 = s.up(&n2, 1);
+  int* dm = s.alloc<int>(c1); int* dnm = s.alloc<int>(1);
+  PL_ARG(a && b && dn1 && dn2 && dm && dnm);
+  rc = pl_lsd_search_double_dev(a, dn1, b, dn2, c1, c2, 1, th, nnratio, mutual, dm, dnm, nullptr); if (rc) return rc;
+  int nm = 0;
+  rc = down(&nm, dnm, 1); if (rc) return rc;
+  if (n1) { rc = down(matches, dm, (size_t)n1); if (rc) return rc; }
+  return nm;
+}
+extern "C" int pl_lsd_frame_bf_match(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float th, float nnratio,
+                                     int* matches) {
+  return search_double_host(d1, n1, d2, n2, th, nnratio, 0, matches);
+}
+extern "C" int pl_lsd_search_double(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnratio, int* matches) {
+  return search_double_host(d1, n1, d2, n2, 50.f, nnratio, 1, matches);
+}

@@ -68,3 +68,61 @@ def warp_frame(img, seed, max_t=4.0, max_rot_deg=0.5, max_ds=0.005):
 def synth_sequence(n, w=640, h=480, seed=1):
     f0 = synth_frame(w, h, seed)
     return np.stack([f0] + [warp_frame(f0, 1000 * seed + k) for k in range(1, n)])
+
+
+# ---------------------------------------------------------------------------------------------- PnP with lines
+TUM1_K = (517.306408, 516.469215, 318.643040, 255.313989)   # Examples/Monocular/TUM1.yaml:8-11
+
+
+def _rot(rx, ry, rz):
+    cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]); Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def synth_pose_problem(seed=3, n_points=300, n_lines=80, outlier_frac=0.10, K=TUM1_K, w=640, h=480,
+                       pert_t=0.02, pert_deg=1.0, noise_px=1.0):
+    """One TUM-shaped PoseOptimization problem.
+
+    Returns dict with Tcw0 (perturbed initial pose, float32 4x4), Tcw_true, K, pt_obs, pt_inv_sigma2, pt_Xw,
+    line_func (normalised 2-D line through the noisy observed end-points), line_Xw (6 doubles).
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    fx, fy, cx, cy = K
+    R = _rot(*rng.uniform(-0.2, 0.2, 3)); t = rng.uniform(-0.5, 0.5, 3)
+    T = np.eye(4); T[:3, :3] = R; T[:3, 3] = t
+
+    def sample_cam_points(n):
+        u = rng.uniform(20, w - 20, n); v = rng.uniform(20, h - 20, n); z = rng.uniform(2.0, 8.0, n)
+        return np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+
+    def project(Xc):
+        return np.stack([Xc[:, 0] / Xc[:, 2] * fx + cx, Xc[:, 1] / Xc[:, 2] * fy + cy], 1)
+
+    Xc = sample_cam_points(n_points)
+    Xw = (Xc - t) @ R          # R^T (Xc - t)
+    quota = np.array([217, 181, 151, 126, 105, 87, 73, 60], np.float64)
+    octave = rng.choice(8, n_points, p=quota / quota.sum())
+    sigma = 1.2 ** octave
+    obs = project(Xc) + rng.normal(0, noise_px, (n_points, 2)) * sigma[:, None]
+    bad = rng.random(n_points) < outlier_frac
+    obs[bad] += rng.uniform(-40, 40, (bad.sum(), 2))
+    inv_sigma2 = (1.0 / (np.float32(1.2) ** octave).astype(np.float32) ** 2).astype(np.float32)
+
+    A = sample_cam_points(n_lines)
+    Bc = A + rng.uniform(-0.8, 0.8, (n_lines, 3)); Bc[:, 2] = np.clip(Bc[:, 2], 1.5, 9.0)
+    lw = np.concatenate([(A - t) @ R, (Bc - t) @ R], 1)
+    pa = project(A) + rng.normal(0, noise_px, (n_lines, 2)); pb = project(Bc) + rng.normal(0, noise_px, (n_lines, 2))
+    lbad = rng.random(n_lines) < outlier_frac
+    pa[lbad] += rng.uniform(-30, 30, (lbad.sum(), 2))
+    sp = np.concatenate([pa, np.ones((n_lines, 1))], 1); ep = np.concatenate([pb, np.ones((n_lines, 1))], 1)
+    l = np.cross(sp, ep)
+    l /= np.sqrt(l[:, 0] ** 2 + l[:, 1] ** 2)[:, None]          # LineExtractor.cpp:82-90
+
+    dR = _rot(*np.deg2rad(rng.uniform(-pert_deg, pert_deg, 3))); dt = rng.uniform(-pert_t, pert_t, 3)
+    T0 = np.eye(4); T0[:3, :3] = dR @ R; T0[:3, 3] = dR @ t + dt
+    return dict(Tcw0=T0.astype(np.float32), Tcw_true=T, K=np.array(K, np.float32),
+                pt_obs=obs.astype(np.float32), pt_inv_sigma2=inv_sigma2, pt_Xw=Xw.astype(np.float32),
+                line_func=np.ascontiguousarray(l, np.float64), line_Xw=np.ascontiguousarray(lw, np.float64),
+                pt_is_outlier=bad, line_is_outlier=lbad)

@@ -254,3 +254,61 @@ def pose_optimization(mode, Tcw, K, pt_obs, pt_inv_sigma2, pt_Xw, line_func, lin
     n = f(mode, _p(Tcw), _p(K), len(po), _p(po), _p(pw), _p(px), len(lf), _p(lf), _p(lx), _p(Tout), _p(pout), _p(lout),
           C.byref(its))
     return n, Tout, pout[:len(po)].astype(bool), lout[:len(lf)].astype(bool), its.value
+
+
+# ---------------------------------------------------------------------------------------------- lines (LSD + LBD)
+KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("ptx", "<f4"), ("pty", "<f4"),
+                          ("response", "<f4"), ("size", "<f4"), ("startPointX", "<f4"), ("startPointY", "<f4"),
+                          ("endPointX", "<f4"), ("endPointY", "<f4"), ("sPointInOctaveX", "<f4"),
+                          ("sPointInOctaveY", "<f4"), ("ePointInOctaveX", "<f4"), ("ePointInOctaveY", "<f4"),
+                          ("lineLength", "<f4"), ("numOfPixels", "<i4")])
+assert KEYLINE_DTYPE.itemsize == 68
+
+
+def lsd_detect(img, order_mode=1):
+    """cv::createLineSegmentDetector()->detect(img) -> (n,4) float32 [x1,y1,x2,y2]."""
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = 20000
+    out = np.zeros((cap, 4), np.float32)
+    n = lib().oracle_lsd_detect(_p(img), img.shape[1], img.shape[0], order_mode, _p(out), cap)
+    return out[:n].copy()
+
+
+def lsd_stages(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    sw, sh = C.c_int(), C.c_int()
+    w8, h8 = int(round(img.shape[1] * 0.8)) + 2, int(round(img.shape[0] * 0.8)) + 2
+    sc = np.zeros(w8 * h8, np.uint8); mg = np.zeros(w8 * h8, np.float64); an = np.zeros(w8 * h8, np.float64)
+    lib().oracle_lsd_stages(_p(img), img.shape[1], img.shape[0], _p(sc), _p(mg), _p(an), C.byref(sw), C.byref(sh))
+    n = sw.value * sh.value
+    return (sc[:n].reshape(sh.value, sw.value), mg[:n].reshape(sh.value, sw.value), an[:n].reshape(sh.value, sw.value))
+
+
+def lbd_sobel(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    dx = np.zeros(img.shape, np.int16); dy = np.zeros(img.shape, np.int16)
+    lib().oracle_lbd_sobel(_p(img), img.shape[1], img.shape[0], _p(dx), _p(dy))
+    return dx, dy
+
+
+def lbd_compute(img, keylines, want_float=False):
+    img = np.ascontiguousarray(img, np.uint8); kl = np.ascontiguousarray(keylines)
+    desc = np.zeros((max(len(kl), 1), 32), np.uint8)
+    dv = np.zeros((max(len(kl), 1), 72), np.float32) if want_float else None
+    lib().oracle_lbd_compute(_p(img), img.shape[1], img.shape[0], _p(kl), len(kl), _p(desc), _p(dv))
+    return (desc[:len(kl)], dv[:len(kl)]) if want_float else desc[:len(kl)]
+
+
+def line_extract(img, mask=None, nfeatures=200, min_line_length=0.0, order_mode=1):
+    """LINEextractor::operator() -> (keylines[68 B records], descriptors n x 32, line functions n x 3)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = nfeatures + 2
+    kl = np.zeros(cap, KEYLINE_DTYPE); desc = np.zeros((cap, 32), np.uint8); lf = np.zeros((cap, 3), np.float64)
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    f = lib().oracle_line_extract
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                  C.c_void_p, C.c_int]
+    n = f(_p(img), img.shape[1], img.shape[0], _p(m), nfeatures, float(min_line_length), order_mode, _p(kl), _p(desc),
+          _p(lf), cap)
+    assert n >= 0
+    return kl[:n].copy(), desc[:n].copy(), lf[:n].copy()

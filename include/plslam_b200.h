@@ -152,6 +152,37 @@ int pl_pose_optimization_dev(int mode, int B, const float* Tcw_in, const float* 
                              float* Tcw_out, uint8_t* pt_outlier, uint8_t* line_outlier, int* inliers,
                              int* iterations, double* scratch, void* stream);
 
+/* ------------------------------------------------------------------ line features (LSD + LBD)
+ * replaces ORB_SLAM2::LINEextractor (reference include/LineExtractor.h:20-62, src/LineExtractor.cpp:26-93).
+ * KeyLine records are byte-compatible with cv::line_descriptor::KeyLine (68 B: angle, class_id, octave, pt.x, pt.y,
+ * response, size, startPointX/Y, endPointX/Y, sPointInOctaveX/Y, ePointInOctaveX/Y, lineLength, numOfPixels).   */
+typedef struct PLLineConfig {
+  int width, height;
+  int nfeatures;            /* LINEextractor.nFeatures (nLSDFeature); the reference keeps up to nfeatures+1 lines */
+  double min_line_length;   /* LINEextractor.min_line_length                                                    */
+  int max_batch;
+  int segment_cap;          /* max LSD segments per frame before truncation; 0 = default 8192                     */
+} PLLineConfig;
+typedef struct PLLine PLLine;
+int pl_line_create(const PLLineConfig* cfg, PLLine** out);
+void pl_line_destroy(PLLine* h);
+int pl_line_capacity(const PLLine* h);   /* nfeatures + 1 */
+/* LINEextractor::operator()(image, mask, keylines, descriptors, lineVec2d) for ONE host frame; mask may be NULL
+ * (8UC1, same size; a line is dropped when both end points lie on mask==0).  keylines: capacity x 68 B,
+ * desc: capacity x 32, linefunc: capacity x 3 doubles (normalised sp x ep), *n: number of KeyLines. */
+int pl_line_extract(PLLine* h, const uint8_t* img, int stride, const uint8_t* mask, void* keylines, uint8_t* desc,
+                    double* linefunc, int* n);
+int pl_line_extract_batch(PLLine* h, const uint8_t* imgs, int stride, size_t frame_stride, int B, const uint8_t* mask,
+                          void* keylines, uint8_t* desc, double* linefunc, int* n);
+int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int stride, size_t frame_stride, int B,
+                              const uint8_t* mask, void* keylines, uint8_t* desc, double* linefunc, int* n, void* stream);
+/* parity taps of the LAST call: raw LSD segments (x1,y1,x2,y2 floats, detection order), the 0.8x scaled image,
+ * the LBD Sobel pair, and the seed order (pixel indices y*sw+x of the scaled image). */
+int pl_line_debug_segments(PLLine* h, int frame, float* out, int cap);
+int pl_line_debug_scaled(PLLine* h, int frame, uint8_t* out, int* sw, int* sh);
+int pl_line_debug_sobel(PLLine* h, int frame, short* dx, short* dy);
+int pl_line_debug_order(PLLine* h, int frame, unsigned* out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -279,3 +279,101 @@ class Optimizer:
     @staticmethod
     def PoseOptimizationWithLines(Tcw, K, line_func, line_Xw):
         return Optimizer._run(2, Tcw, K, np.zeros((0, 2)), np.zeros(0), np.zeros((0, 3)), line_func, line_Xw)
+
+
+# ---------------------------------------------------------------------------------------------- line features
+KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("ptx", "<f4"), ("pty", "<f4"),
+                          ("response", "<f4"), ("size", "<f4"), ("startPointX", "<f4"), ("startPointY", "<f4"),
+                          ("endPointX", "<f4"), ("endPointY", "<f4"), ("sPointInOctaveX", "<f4"),
+                          ("sPointInOctaveY", "<f4"), ("ePointInOctaveX", "<f4"), ("ePointInOctaveY", "<f4"),
+                          ("lineLength", "<f4"), ("numOfPixels", "<i4")])
+
+
+class PLLineConfig(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("nfeatures", C.c_int), ("min_line_length", C.c_double),
+                ("max_batch", C.c_int), ("segment_cap", C.c_int)]
+
+
+class LINEextractor:
+    """Mirror of ORB_SLAM2::LINEextractor (reference include/LineExtractor.h:20-62).
+
+    ctor (numOctaves, scale, nLSDFeature, min_line_length) as in the reference; `scale` reaches the detector as
+    (int)scale == 1 and numOctaves is 1 in every shipped config, which is what is implemented.
+    `__call__(image, mask)` == operator()(image, mask, keylines, descriptors, lineVec2d).
+    """
+
+    def __init__(self, numOctaves=1, scale=1.2, nLSDFeature=200, min_line_length=0.0, width=640, height=480, max_batch=1,
+                 segment_cap=0):
+        if numOctaves != 1 or int(scale) != 1:
+            raise PLError("only numOctaves == 1 and int(scale) == 1 are supported (all reference configs)")
+        self.cfg = PLLineConfig(width, height, nLSDFeature, float(min_line_length), max_batch, segment_cap)
+        self._h = vp()
+        L = lib()
+        L.pl_line_create.argtypes = [C.POINTER(PLLineConfig), C.POINTER(vp)]
+        L.pl_line_destroy.argtypes = [vp]
+        L.pl_line_capacity.argtypes = [vp]
+        L.pl_line_extract.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
+        L.pl_line_extract_batch.argtypes = [vp, vp, C.c_int, C.c_size_t, C.c_int, vp, vp, vp, vp, vp]
+        L.pl_line_extract_batch_dev.argtypes = [vp, vp, C.c_int, C.c_size_t, C.c_int, vp, vp, vp, vp, vp, vp]
+        L.pl_line_debug_segments.argtypes = [vp, C.c_int, vp, C.c_int]
+        L.pl_line_debug_scaled.argtypes = [vp, C.c_int, vp, vp, vp]
+        L.pl_line_debug_sobel.argtypes = [vp, C.c_int, vp, vp]
+        L.pl_line_debug_order.argtypes = [vp, C.c_int, vp, C.c_int]
+        check(L.pl_line_create(C.byref(self.cfg), C.byref(self._h)))
+        self.capacity = check(L.pl_line_capacity(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().pl_line_destroy(self._h)
+            self._h = vp()
+
+    def __call__(self, image, mask=None):
+        image = np.ascontiguousarray(image, np.uint8)
+        if image.size == 0:
+            return np.zeros(0, KEYLINE_DTYPE), np.zeros((0, 32), np.uint8), np.zeros((0, 3))
+        if mask is not None and (mask.shape != image.shape or mask.dtype != np.uint8):
+            raise PLError("Mask error while detecting lines: please check its dimensions and that data type is CV_8UC1")
+        kl = np.zeros(self.capacity, KEYLINE_DTYPE); desc = np.zeros((self.capacity, 32), np.uint8)
+        lf = np.zeros((self.capacity, 3), np.float64); n = C.c_int(0)
+        m = None if mask is None else np.ascontiguousarray(mask)
+        check(lib().pl_line_extract(self._h, _p(image), image.strides[0], _p(m), _p(kl), _p(desc), _p(lf), C.byref(n)))
+        return kl[:n.value].copy(), desc[:n.value].copy(), lf[:n.value].copy()
+
+    def extract_batch(self, images, mask=None):
+        images = np.ascontiguousarray(images, np.uint8)
+        B = images.shape[0]
+        kl = np.zeros((B, self.capacity), KEYLINE_DTYPE); desc = np.zeros((B, self.capacity, 32), np.uint8)
+        lf = np.zeros((B, self.capacity, 3), np.float64); n = np.zeros(B, np.int32)
+        m = None if mask is None else np.ascontiguousarray(mask)
+        check(lib().pl_line_extract_batch(self._h, _p(images), images.strides[1], images.strides[0], B, _p(m), _p(kl),
+                                          _p(desc), _p(lf), _p(n)))
+        return kl, desc, lf, n
+
+    def extract_batch_dev(self, img_ptr, stride, frame_stride, B, mask_ptr, kl_ptr, desc_ptr, lf_ptr, n_ptr, stream=None):
+        check(lib().pl_line_extract_batch_dev(self._h, img_ptr, stride, frame_stride, B, mask_ptr, kl_ptr, desc_ptr,
+                                              lf_ptr, n_ptr, stream))
+
+    # parity taps
+    def debug_segments(self, frame=0):
+        n = check(lib().pl_line_debug_segments(self._h, frame, None, 0))
+        out = np.zeros((max(n, 1), 4), np.float32)
+        check(lib().pl_line_debug_segments(self._h, frame, _p(out), n))
+        return out[:n]
+
+    def debug_scaled(self, frame=0):
+        sw, sh = C.c_int(), C.c_int()
+        check(lib().pl_line_debug_scaled(self._h, frame, None, C.byref(sw), C.byref(sh)))
+        out = np.zeros((sh.value, sw.value), np.uint8)
+        check(lib().pl_line_debug_scaled(self._h, frame, _p(out), C.byref(sw), C.byref(sh)))
+        return out
+
+    def debug_sobel(self, frame=0):
+        dx = np.zeros((self.cfg.height, self.cfg.width), np.int16); dy = np.zeros_like(dx)
+        check(lib().pl_line_debug_sobel(self._h, frame, _p(dx), _p(dy)))
+        return dx, dy
+
+    def debug_order(self, frame=0):
+        n = check(lib().pl_line_debug_order(self._h, frame, None, 0))
+        out = np.zeros(max(n, 1), np.uint32)
+        check(lib().pl_line_debug_order(self._h, frame, _p(out), n))
+        return out[:n]

@@ -1,0 +1,890 @@
+// Line-feature extraction (LSD segments + LBD descriptors) for batches of frames on sm_100a.
+//
+// Replaces LINEextractor::operator() (reference src/LineExtractor.cpp:26-93) and what it calls:
+//   LSDDetector::detect           opencv_contrib line_descriptor; spec copy Thirdparty/line_descriptor/src/LSDDetector_custom.cpp:56-215
+//   cv::LineSegmentDetector       OpenCV imgproc lsd.cpp (defaults: REFINE_STD, scale .8, sigma_scale .6, quant 2, 22.5 deg, density .7)
+//   BinaryDescriptor::compute     spec copy Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp:350-398,539-687,1026-1372
+//
+// Kernel map
+//   k_lsd_scale     7x7 sigma .75 Gaussian (8.8 fixed point) fused with the 0.8x INTER_LINEAR_EXACT resize, smem tiles
+//   k_lsd_grad      2x2 gradient -> (gx,gy) int16 pair per pixel (4 B instead of OpenCV's two doubles), per-frame max
+//   k_lsd_hist/scan/scatter   stable counting sort of the defined pixels into 1024 magnitude bins (descending),
+//                   equal bins keep row-major order == OpenCV 4.13's seed order (pinned in the oracle tests)
+//   k_lsd_grow      region growing + rectangle fit + density refinement; inherently ordered (a pixel consumed by an
+//                   earlier seed is unavailable to later ones) -> ONE warp per frame walks the seeds in order; the 32
+//                   lanes test the 3x3 neighbourhood, evaluate angles and reduce the rectangle moments in parallel.
+//   k_keylines      KeyLine records, mask filter, response sort (bitonic, ties keep detection order), truncation
+//                   quirk of LineExtractor.cpp:44-67, normalised 2-D line equations
+//   k_lbd_sobel     5x5 sigma 1 Gaussian (8.8 fixed point) fused with the 3x3 Sobel pair -> int16 dx, dy
+//   k_lbd_describe  one CTA per line: 63 support rows in parallel (each row accumulates along the line in the
+//                   reference's order, fp32 without FMA), band statistics, 72-float LBD, 32-byte binarisation
+
+#include "common.cuh"
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+
+namespace pl {
+
+constexpr double kPI = 3.14159265358979323846;
+constexpr double kDegToRads = kPI / 180;
+constexpr int kBins = 1024;
+constexpr int kChunkRows = 8;
+constexpr int kRing = 2048;
+
+struct PLKeyLineRec {  // cv::line_descriptor::KeyLine, 68 bytes
+  float angle; int class_id; int octave; float ptx, pty; float response; float size;
+  float startPointX, startPointY, endPointX, endPointY;
+  float sPointInOctaveX, sPointInOctaveY, ePointInOctaveX, ePointInOctaveY;
+  float lineLength; int numOfPixels;
+};
+static_assert(sizeof(PLKeyLineRec) == 68, "KeyLine layout");
+
+struct LineParams {
+  int w, h, sw, sh, npx;        // image, scaled image, sw*sh
+  int nchunk;                   // ceil((sh-1)/kChunkRows)
+  int s_th;                     // gradient defined  <=>  gx^2+gy^2 > s_th
+  int min_reg_size;
+  int seg_cap, capL, nfeatures;
+  double min_line_length;
+  double prec, p, density_th;
+};
+
+// ---------------------------------------------------------------------------------------------- shared helpers
+__device__ __forceinline__ float fast_atan2_deg_l(float y, float x) {  // cv::fastAtan2, no FMA
+  const float k = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = 0.9997878412794807f * k, p3 = -0.3258083974640975f * k;
+  const float p5 = 0.1555786518463281f * k, p7 = -0.04432655554792128f * k;
+  const float eps = 2.220446049250313e-16f;
+  float ax = fabsf(x), ay = fabsf(y), a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, eps)); c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, eps)); c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+__device__ __forceinline__ double grad_angle(short2 g) {  // angles(x,y): fastAtan2(float(gx), float(-gy)) * DEG_TO_RADS
+  return (double)fast_atan2_deg_l((float)g.x, (float)(-g.y)) * kDegToRads;
+}
+__device__ __forceinline__ double grad_norm(short2 g) {   // modgrad(x,y)
+  return sqrt((double)((int)g.x * g.x + (int)g.y * g.y) / 4.0);
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------- K_A scale
+// Output tile 32x32 of the 0.8x image <- 40x40 blurred pixels <- 44x44 raw pixels (taps at +-3 are zero).
+__global__ void __launch_bounds__(256) k_lsd_scale(LineParams P, const uint8_t* __restrict__ imgs, int stride,
+                                                   long long frame_stride, uint8_t* __restrict__ scaled) {
+  __shared__ uint8_t raw[44][48];
+  __shared__ uint16_t hp[44][40];
+  __shared__ uint8_t bl[40][40];
+  const int tid = threadIdx.x;
+  const int X0 = blockIdx.x * 32, Y0 = blockIdx.y * 32;
+  const int bx0 = (5 * X0) >> 2, by0 = (5 * Y0) >> 2;
+  const uint8_t* img = imgs + (long long)blockIdx.z * frame_stride;
+  for (int i = tid; i < 44 * 44; i += 256) {
+    int r = i / 44, c = i - r * 44;
+    int gy = reflect101(min(by0 - 2 + r, 2 * P.h - 2), P.h), gx = reflect101(min(bx0 - 2 + c, 2 * P.w - 2), P.w);
+    raw[r][c] = img[(long long)gy * stride + gx];
+  }
+  __syncthreads();
+  for (int i = tid; i < 44 * 40; i += 256) {
+    int r = i / 40, c = i - r * 40;
+    const uint8_t* p = &raw[r][c];
+    hp[r][c] = (uint16_t)(4 * (p[0] + p[4]) + 56 * (p[1] + p[3]) + 136 * p[2]);
+  }
+  __syncthreads();
+  for (int i = tid; i < 40 * 40; i += 256) {
+    int r = i / 40, c = i - r * 40;
+    uint32_t s = 4u * (hp[r][c] + hp[r + 4][c]) + 56u * (hp[r + 1][c] + hp[r + 3][c]) + 136u * hp[r + 2][c];
+    bl[r][c] = (uint8_t)((s + 32768u) >> 16);
+  }
+  __syncthreads();
+  uint8_t* out = scaled + (long long)blockIdx.z * P.npx;
+  for (int i = tid; i < 32 * 32; i += 256) {
+    int ty = i >> 5, tx = i & 31;
+    int x = X0 + tx, y = Y0 + ty;
+    if (x >= P.sw || y >= P.sh) continue;
+    int sx = (10 * x + 1) >> 3, xf = ((10 * x + 1) & 7) * 32;
+    int sy = (10 * y + 1) >> 3, yf = ((10 * y + 1) & 7) * 32;
+    if (sx >= P.w - 1) { sx = P.w - 1; xf = 0; }
+    if (sy >= P.h - 1) { sy = P.h - 1; yf = 0; }
+    int sx1 = min(sx + 1, P.w - 1), sy1 = min(sy + 1, P.h - 1);
+    int lx = sx - bx0, lx1 = sx1 - bx0, ly = sy - by0, ly1 = sy1 - by0;
+    int h0 = bl[ly][lx] * (256 - xf) + bl[ly][lx1] * xf;
+    int h1 = bl[ly1][lx] * (256 - xf) + bl[ly1][lx1] * xf;
+    out[(long long)y * P.sw + x] = (uint8_t)((h0 * (256 - yf) + h1 * yf + 32768) >> 16);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K_B gradient
+constexpr short kNotDef = -32768;  // gx marker of the undefined right/bottom border
+__global__ void __launch_bounds__(256) k_lsd_grad(LineParams P, const uint8_t* __restrict__ scaled,
+                                                  short2* __restrict__ gxy, uint8_t* __restrict__ used, int* __restrict__ maxs) {
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const int f = blockIdx.z;
+  int s = 0;
+  if (x < P.sw && y < P.sh) {
+    const uint8_t* S = scaled + (long long)f * P.npx;
+    short2 g = make_short2(kNotDef, 0);
+    if (x < P.sw - 1 && y < P.sh - 1) {
+      int a = S[y * P.sw + x], b = S[y * P.sw + x + 1], c = S[(y + 1) * P.sw + x], d = S[(y + 1) * P.sw + x + 1];
+      int DA = d - a, BC = b - c;
+      g = make_short2((short)(DA + BC), (short)(DA - BC));
+      s = (int)g.x * g.x + (int)g.y * g.y;
+    }
+    gxy[(long long)f * P.npx + y * P.sw + x] = g;
+    used[(long long)f * P.npx + y * P.sw + x] = 0;
+  }
+  // max over defined pixels (modgrad is monotonic in s)
+  s = (s > P.s_th) ? s : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s = max(s, __shfl_xor_sync(0xffffffffu, s, o));
+  if ((threadIdx.x & 31) == 0 && s > 0) atomicMax(&maxs[f], s);
+}
+
+__device__ __forceinline__ int grad_bin(short2 g, double bin_coef) { return (int)(grad_norm(g) * bin_coef); }
+
+// K_C per-chunk histograms of the defined pixels (chunk = kChunkRows image rows)
+__global__ void __launch_bounds__(256) k_lsd_hist(LineParams P, const short2* __restrict__ gxy, const int* __restrict__ maxs,
+                                                  unsigned short* __restrict__ counts /*[B][kBins][nchunk]*/) {
+  __shared__ int hist[kBins];
+  const int chunk = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < kBins; i += 256) hist[i] = 0;
+  __syncthreads();
+  const int ms = maxs[f];
+  const double max_grad = ms > 0 ? sqrt((double)ms / 4.0) : -1.0;
+  const double bin_coef = (max_grad > 0) ? (double)(kBins - 1) / max_grad : 0.0;
+  const int y0 = chunk * kChunkRows, y1 = min(y0 + kChunkRows, P.sh - 1);
+  const short2* G = gxy + (long long)f * P.npx;
+  for (int i = tid; i < (y1 - y0) * P.sw; i += 256) {
+    int y = y0 + i / P.sw, x = i % P.sw;
+    short2 g = G[y * P.sw + x];
+    if (g.x != kNotDef && (int)g.x * g.x + (int)g.y * g.y > P.s_th) atomicAdd(&hist[grad_bin(g, bin_coef)], 1);
+  }
+  __syncthreads();
+  for (int i = tid; i < kBins; i += 256) counts[((long long)f * kBins + i) * P.nchunk + chunk] = (unsigned short)hist[i];
+}
+
+// K_D offsets[bin][chunk] = number of defined pixels that precede (bin desc, chunk asc); ndef = total
+__global__ void __launch_bounds__(kBins) k_lsd_scan(LineParams P, const unsigned short* __restrict__ counts,
+                                                    int* __restrict__ offsets, int* __restrict__ ndef) {
+  __shared__ int wsum[32];
+  const int f = blockIdx.x, t = threadIdx.x, bin = kBins - 1 - t, lane = t & 31, wid = t >> 5;
+  const unsigned short* c = counts + ((long long)f * kBins + bin) * P.nchunk;
+  int tot = 0;
+  for (int k = 0; k < P.nchunk; k++) tot += c[k];
+  int incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int v = wsum[lane], in2 = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, in2, o); if (lane >= o) in2 += u; }
+    wsum[lane] = in2 - v;
+    if (lane == 31) ndef[f] = in2;
+  }
+  __syncthreads();
+  int base = wsum[wid] + incl - tot;
+  int* o = offsets + ((long long)f * kBins + bin) * P.nchunk;
+  for (int k = 0; k < P.nchunk; k++) { o[k] = base; base += c[k]; }
+}
+
+// K_E stable scatter: one warp per chunk walks its pixels in row-major order
+__global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const short2* __restrict__ gxy, const int* __restrict__ maxs,
+                                                     const int* __restrict__ offsets, unsigned* __restrict__ order) {
+  __shared__ unsigned short cnt[4][kBins];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * 4 + wid, f = blockIdx.y;
+  for (int i = lane; i < kBins; i += 32) cnt[wid][i] = 0;
+  __syncwarp();
+  if (chunk >= P.nchunk) return;
+  const int ms = maxs[f];
+  const double max_grad = ms > 0 ? sqrt((double)ms / 4.0) : -1.0;
+  const double bin_coef = (max_grad > 0) ? (double)(kBins - 1) / max_grad : 0.0;
+  const int y0 = chunk * kChunkRows, y1 = min(y0 + kChunkRows, P.sh - 1);
+  const short2* G = gxy + (long long)f * P.npx;
+  const int* off = offsets + (long long)f * kBins * P.nchunk;
+  unsigned* O = order + (long long)f * P.npx;
+  const int n = (y1 - y0) * P.sw;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    int i = i0 + lane, bin = -1, pix = 0;
+    if (i < n) {
+      int y = y0 + i / P.sw, x = i % P.sw;
+      pix = y * P.sw + x;
+      short2 g = G[pix];
+      if (g.x != kNotDef && (int)g.x * g.x + (int)g.y * g.y > P.s_th) bin = grad_bin(g, bin_coef);
+    }
+    unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (bin >= 0) O[off[bin * P.nchunk + chunk] + cnt[wid][bin] + __popc(peers & lt)] = (unsigned)pix;
+    __syncwarp();
+    if (bin >= 0 && (peers & lt) == 0) cnt[wid][bin] += (unsigned short)__popc(peers);
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K_F region growing
+struct GrowCtx {
+  const short2* G; uint8_t* U; unsigned* R; unsigned* ring;
+  int sw, sh, s_th;
+};
+struct RectD { double x1, y1, x2, y2, width; };
+
+__device__ __forceinline__ double angle_diff_signed(double a, double b) {
+  double diff = a - b;
+  while (diff <= -kPI) diff += 2 * kPI;
+  while (diff > kPI) diff -= 2 * kPI;
+  return diff;
+}
+__device__ __forceinline__ bool is_aligned(double a, double theta, double prec) {
+  double n_theta = theta - a;
+  if (n_theta < 0) n_theta = -n_theta;
+  if (n_theta > (3 * kPI) / 2) { n_theta -= 2 * kPI; if (n_theta < 0) n_theta = -n_theta; }
+  return n_theta <= prec;
+}
+
+// LineSegmentDetectorImpl::region_grow — exact visiting order; returns the region size, region in C.R[0..n)
+__device__ int region_grow(const GrowCtx& C, int seed, double prec, double& reg_angle, int lane) {
+  const short2 gs = C.G[seed];
+  reg_angle = grad_angle(gs);
+  float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
+  if (lane == 0) { C.R[0] = (unsigned)seed; C.ring[0] = (unsigned)seed; C.U[seed] = 1; }
+  int cnt = 1;
+  __syncwarp();
+  for (int i = 0; i < cnt; i++) {
+    const unsigned p = (cnt - i <= kRing) ? C.ring[i & (kRing - 1)] : C.R[i];
+    const int rx = (int)(p % (unsigned)C.sw), ry = (int)(p / (unsigned)C.sw);
+    bool valid = false;
+    int idx = 0;
+    double a = 0;
+    float cs = 0, sn = 0;
+    if (lane < 9) {
+      const int xx = rx - 1 + lane % 3, yy = ry - 1 + lane / 3;
+      if (xx >= 0 && yy >= 0 && xx < C.sw && yy < C.sh) {
+        idx = yy * C.sw + xx;
+        if (C.U[idx] == 0) {
+          const short2 g = C.G[idx];
+          if (g.x != kNotDef && (int)g.x * g.x + (int)g.y * g.y > C.s_th) {
+            valid = true;
+            a = grad_angle(g);
+            const double af = (double)(float)a;   // cos(float(angle)), sin(float(angle)) in fp32
+            cs = (float)cos(af); sn = (float)sin(af);
+          }
+        }
+      }
+    }
+    unsigned cand = __ballot_sync(0xffffffffu, valid);
+    while (cand) {
+      const int k = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const double ak = __shfl_sync(0xffffffffu, a, k);
+      if (is_aligned(ak, reg_angle, prec)) {
+        const int ik = __shfl_sync(0xffffffffu, idx, k);
+        if (lane == 0) { C.U[ik] = 1; C.R[cnt] = (unsigned)ik; C.ring[cnt & (kRing - 1)] = (unsigned)ik; }
+        cnt++;
+        sumdx = __fadd_rn(sumdx, __shfl_sync(0xffffffffu, cs, k));
+        sumdy = __fadd_rn(sumdy, __shfl_sync(0xffffffffu, sn, k));
+        reg_angle = (double)fast_atan2_deg_l(sumdy, sumdx) * kDegToRads;
+      }
+    }
+    __syncwarp();
+  }
+  return cnt;
+}
+
+// LineSegmentDetectorImpl::region2rect (+get_theta); sums are reduced lane-strided then by butterfly
+__device__ void region2rect(const GrowCtx& C, int n, double reg_angle, double prec, RectD& rec, int lane) {
+  double sx = 0, sy = 0, sw_ = 0;
+  for (int i = lane; i < n; i += 32) {
+    const unsigned p = C.R[i];
+    const double w = grad_norm(C.G[p]);
+    sx += (double)(int)(p % (unsigned)C.sw) * w;
+    sy += (double)(int)(p / (unsigned)C.sw) * w;
+    sw_ += w;
+  }
+  sx = warp_sum(sx); sy = warp_sum(sy); sw_ = warp_sum(sw_);
+  const double x = sx / sw_, y = sy / sw_;
+  double Ixx = 0, Iyy = 0, Ixy = 0;
+  for (int i = lane; i < n; i += 32) {
+    const unsigned p = C.R[i];
+    const double w = grad_norm(C.G[p]);
+    const double dx = (double)(int)(p % (unsigned)C.sw) - x, dy = (double)(int)(p / (unsigned)C.sw) - y;
+    Ixx += dy * dy * w; Iyy += dx * dx * w; Ixy -= dx * dy * w;
+  }
+  Ixx = warp_sum(Ixx); Iyy = warp_sum(Iyy); Ixy = warp_sum(Ixy);
+  const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+  double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg_l((float)(lambda - Ixx), (float)Ixy)
+                                         : (double)fast_atan2_deg_l((float)Ixy, (float)(lambda - Iyy));
+  theta *= kDegToRads;
+  if (fabs(angle_diff_signed(theta, reg_angle)) > prec) theta += kPI;
+  const double dx = cos(theta), dy = sin(theta);
+  double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
+  for (int i = lane; i < n; i += 32) {
+    const unsigned p = C.R[i];
+    const double rdx = (double)(int)(p % (unsigned)C.sw) - x, rdy = (double)(int)(p / (unsigned)C.sw) - y;
+    const double l = rdx * dx + rdy * dy, w = -rdx * dy + rdy * dx;
+    l_max = fmax(l_max, l); l_min = fmin(l_min, l);
+    w_max = fmax(w_max, w); w_min = fmin(w_min, w);
+  }
+  l_max = warp_max_d(l_max); l_min = warp_min_d(l_min); w_max = warp_max_d(w_max); w_min = warp_min_d(w_min);
+  rec.x1 = x + l_min * dx; rec.y1 = y + l_min * dy;
+  rec.x2 = x + l_max * dx; rec.y2 = y + l_max * dy;
+  rec.width = w_max - w_min;
+  if (rec.width < 1.0) rec.width = 1.0;
+}
+__device__ __forceinline__ double dist_d(double x1, double y1, double x2, double y2) {
+  return sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1));
+}
+
+// LineSegmentDetectorImpl::refine + reduce_region_radius; n is updated; returns false if the region is rejected
+__device__ bool refine(const GrowCtx& C, int& n, double reg_angle, double prec, RectD& rec, double density_th, int lane) {
+  double density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+  if (density >= density_th) return true;
+  const unsigned p0 = C.R[0];
+  const double xc = (double)(int)(p0 % (unsigned)C.sw), yc = (double)(int)(p0 / (unsigned)C.sw);
+  const double ang_c = grad_angle(C.G[p0]);
+  double sum = 0, s_sum = 0;
+  int cnt = 0;
+  for (int i = lane; i < n; i += 32) {
+    const unsigned p = C.R[i];
+    C.U[p] = 0;
+    const double px = (double)(int)(p % (unsigned)C.sw), py = (double)(int)(p / (unsigned)C.sw);
+    if (dist_d(xc, yc, px, py) < rec.width) {
+      const double ang_d = angle_diff_signed(grad_angle(C.G[p]), ang_c);
+      sum += ang_d; s_sum += ang_d * ang_d; ++cnt;
+    }
+  }
+  sum = warp_sum(sum); s_sum = warp_sum(s_sum); cnt = warp_sum(cnt);
+  __syncwarp();
+  const double mean_angle = sum / (double)cnt;
+  const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
+  n = region_grow(C, (int)p0, tau, reg_angle, lane);
+  if (n < 2) return false;
+  region2rect(C, n, reg_angle, prec, rec, lane);
+  density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+  if (density >= density_th) return true;
+  // reduce_region_radius
+  const double r1 = (rec.x1 - xc) * (rec.x1 - xc) + (rec.y1 - yc) * (rec.y1 - yc);
+  const double r2 = (rec.x2 - xc) * (rec.x2 - xc) + (rec.y2 - yc) * (rec.y2 - yc);
+  double radSq = r1 > r2 ? r1 : r2;
+  const unsigned lt = (1u << lane) - 1u;
+  while (density < density_th) {
+    radSq *= 0.75 * 0.75;
+    int kept = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {   // order-preserving compaction (the reference swap-removes; only sums follow)
+      const int i = i0 + lane;
+      unsigned p = 0;
+      bool keep = false;
+      if (i < n) {
+        p = C.R[i];
+        const double px = (double)(int)(p % (unsigned)C.sw), py = (double)(int)(p / (unsigned)C.sw);
+        keep = !((px - xc) * (px - xc) + (py - yc) * (py - yc) > radSq);
+        if (!keep) C.U[p] = 0;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      __syncwarp();
+      if (keep) C.R[kept + __popc(m & lt)] = p;
+      kept += __popc(m);
+      __syncwarp();
+    }
+    n = kept;
+    if (n < 2) return false;
+    region2rect(C, n, reg_angle, prec, rec, lane);
+    density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(32) k_lsd_grow(LineParams P, const short2* __restrict__ gxy, uint8_t* __restrict__ used,
+                                                 const unsigned* __restrict__ order, const int* __restrict__ ndef,
+                                                 unsigned* __restrict__ reg, float4* __restrict__ segs,
+                                                 int* __restrict__ nseg, int* __restrict__ overflow) {
+  __shared__ unsigned ring[kRing];
+  const int f = blockIdx.x, lane = threadIdx.x;
+  GrowCtx C;
+  C.G = gxy + (long long)f * P.npx; C.U = used + (long long)f * P.npx; C.R = reg + (long long)f * P.npx;
+  C.ring = ring; C.sw = P.sw; C.sh = P.sh; C.s_th = P.s_th;
+  const unsigned* O = order + (long long)f * P.npx;
+  float4* S = segs + (long long)f * P.seg_cap;
+  const int n = ndef[f];
+  int ns = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    const unsigned pix = (i < n) ? O[i] : 0u;
+    unsigned todo = __ballot_sync(0xffffffffu, i < n && C.U[pix] == 0);
+    while (todo) {
+      const int k = __ffs(todo) - 1;
+      const int seed = (int)__shfl_sync(0xffffffffu, pix, k);
+      double reg_angle;
+      int cnt = region_grow(C, seed, P.prec, reg_angle, lane);
+      if (cnt >= P.min_reg_size) {
+        RectD rec;
+        region2rect(C, cnt, reg_angle, P.prec, rec, lane);
+        if (refine(C, cnt, reg_angle, P.prec, rec, P.density_th, lane)) {
+          if (lane == 0 && ns < P.seg_cap)
+            S[ns] = make_float4((float)((rec.x1 + 0.5) / 0.8), (float)((rec.y1 + 0.5) / 0.8), (float)((rec.x2 + 0.5) / 0.8),
+                                (float)((rec.y2 + 0.5) / 0.8));
+          ns++;
+        }
+      }
+      __syncwarp();
+      // seeds later in this batch may have been consumed (or released by refine): re-read their flags
+      todo = __ballot_sync(0xffffffffu, i < n && lane > k && C.U[pix] == 0);
+    }
+  }
+  if (lane == 0) { nseg[f] = min(ns, P.seg_cap); if (ns > P.seg_cap) atomicExch(overflow, 1); }
+}
+
+// ---------------------------------------------------------------------------------------------- K_G keylines
+__global__ void __launch_bounds__(256) k_keylines(LineParams P, const float4* __restrict__ segs, const int* __restrict__ nseg,
+                                                  const uint8_t* __restrict__ mask, PLKeyLineRec* __restrict__ kls,
+                                                  double* __restrict__ linefunc, int* __restrict__ nl) {
+  extern __shared__ unsigned long long keys[];   // seg_cap rounded to a power of two
+  __shared__ int s_cnt;
+  const int f = blockIdx.x, tid = threadIdx.x;
+  const float4* S = segs + (long long)f * P.seg_cap;
+  const int n = nseg[f];
+  int cap2 = 1;
+  while (cap2 < max(n, 1)) cap2 <<= 1;
+  auto clampseg = [&](float4 e) {
+    if (e.x < 0) e.x = 0; if (e.x >= P.w) e.x = (float)P.w - 1.0f;
+    if (e.z < 0) e.z = 0; if (e.z >= P.w) e.z = (float)P.w - 1.0f;
+    if (e.y < 0) e.y = 0; if (e.y >= P.h) e.y = (float)P.h - 1.0f;
+    if (e.w < 0) e.w = 0; if (e.w >= P.h) e.w = (float)P.h - 1.0f;
+    return e;
+  };
+  auto seglen = [&](float4 e) {
+    const double a = (double)__fsub_rn(e.x, e.z), b = (double)__fsub_rn(e.y, e.w);
+    return (float)sqrt(a * a + b * b);
+  };
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  for (int i = tid; i < cap2; i += 256) {
+    unsigned long long key = ~0ull;
+    if (i < n) {
+      const float4 e = clampseg(S[i]);
+      bool drop = false;
+      if (mask) drop = mask[(long long)(int)e.y * P.w + (int)e.x] == 0 && mask[(long long)(int)e.w * P.w + (int)e.z] == 0;
+      if (!drop) {
+        const float resp = __fdiv_rn(seglen(e), (float)max(P.w, P.h));
+        key = ((unsigned long long)(~__float_as_uint(resp)) << 32) | (unsigned)i;   // response desc, detection order asc
+        atomicAdd(&s_cnt, 1);
+      }
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  for (int k = 2; k <= cap2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < cap2; i += 256) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long a = keys[i], b = keys[ixj];
+          bool up = ((i & k) == 0);
+          if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  const int size = s_cnt;
+  // LineExtractor.cpp:44-67 truncation (total/index quirk)
+  int total = size > P.nfeatures ? P.nfeatures : size, index = total;
+  __shared__ int s_index;
+  if (tid == 0) {
+    if (total > 0) {
+      const float lastLen = seglen(clampseg(S[(unsigned)(keys[total - 1] & 0xffffffffu)]));
+      if ((double)lastLen < P.min_line_length) {
+        for (int i = 0; i < total - 1; i++) {
+          const float l0 = seglen(clampseg(S[(unsigned)(keys[i] & 0xffffffffu)]));
+          const float l1 = seglen(clampseg(S[(unsigned)(keys[i + 1] & 0xffffffffu)]));
+          if ((double)l0 >= P.min_line_length && (double)l1 < P.min_line_length) { index = i; break; }
+        }
+      }
+    }
+    s_index = index;
+  }
+  __syncthreads();
+  index = s_index;
+  const int nout = index + 1;
+  PLKeyLineRec* K = kls + (long long)f * P.capL;
+  double* LF = linefunc + (long long)f * P.capL * 3;
+  for (int i = tid; i < nout && i < P.capL; i += 256) {
+    PLKeyLineRec kl;
+    if (i < size) {
+      const float4 e = clampseg(S[(unsigned)(keys[i] & 0xffffffffu)]);
+      kl.startPointX = e.x; kl.startPointY = e.y; kl.endPointX = e.z; kl.endPointY = e.w;
+      kl.sPointInOctaveX = e.x; kl.sPointInOctaveY = e.y; kl.ePointInOctaveX = e.z; kl.ePointInOctaveY = e.w;
+      kl.lineLength = seglen(e);
+      const int x0 = __float2int_rn(e.x), y0 = __float2int_rn(e.y), x1 = __float2int_rn(e.z), y1 = __float2int_rn(e.w);
+      kl.numOfPixels = max(abs(x1 - x0), abs(y1 - y0)) + 1;
+      kl.angle = (float)atan2((double)__fsub_rn(e.w, e.y), (double)__fsub_rn(e.z, e.x));
+      kl.octave = 0;
+      kl.size = __fmul_rn(__fsub_rn(e.z, e.x), __fsub_rn(e.w, e.y));
+      kl.response = __fdiv_rn(kl.lineLength, (float)max(P.w, P.h));
+      kl.ptx = __fdiv_rn(__fadd_rn(e.z, e.x), 2.f); kl.pty = __fdiv_rn(__fadd_rn(e.w, e.y), 2.f);
+    } else {
+      memset(&kl, 0, sizeof(kl));   // the KeyLine appended by resize(index+1)
+    }
+    kl.class_id = i;
+    K[i] = kl;
+    const double sx = kl.startPointX, sy = kl.startPointY, ex = kl.endPointX, ey = kl.endPointY;
+    const double lx = sy * 1.0 - 1.0 * ey, ly = 1.0 * ex - sx * 1.0, lz = sx * ey - sy * ex;
+    const double nn = sqrt(lx * lx + ly * ly);
+    LF[3 * i] = lx / nn; LF[3 * i + 1] = ly / nn; LF[3 * i + 2] = lz / nn;
+  }
+  if (tid == 0) nl[f] = min(nout, P.capL);
+}
+
+// ---------------------------------------------------------------------------------------------- K_H LBD blur + Sobel
+// 32x32 output tile <- 34x34 blurred pixels (5x5 taps read through L1; Sobel reflects the BLURRED image, so blurred
+// values are evaluated at reflect-101 coordinates)
+__global__ void __launch_bounds__(256) k_lbd_sobel(LineParams P, const uint8_t* __restrict__ imgs, int stride,
+                                                   long long frame_stride, short* __restrict__ dxo, short* __restrict__ dyo) {
+  __shared__ uint8_t bl[34][36];
+  const int tid = threadIdx.x, X0 = blockIdx.x * 32, Y0 = blockIdx.y * 32;
+  const uint8_t* img = imgs + (long long)blockIdx.z * frame_stride;
+  auto r101 = [](int p, int n) { if (p < 0) p = -p; if (p >= n) p = 2 * (n - 1) - p; return p; };
+  // Because Sobel reflects the BLURRED image (not the raw one), blurred values are computed at reflected coordinates:
+  for (int i = tid; i < 34 * 34; i += 256) {
+    int r = i / 34, c = i - r * 34;
+    const int by = r101(min(max(Y0 - 1 + r, -1), P.h), P.h), bx = r101(min(max(X0 - 1 + c, -1), P.w), P.w);
+    unsigned acc = 0;
+    const int t5[5] = {14, 62, 104, 62, 14};
+#pragma unroll
+    for (int ky = -2; ky <= 2; ky++) {
+      const uint8_t* row = img + (long long)r101(by + ky, P.h) * stride;
+      unsigned h = 0;
+#pragma unroll
+      for (int kx = -2; kx <= 2; kx++) h += row[r101(bx + kx, P.w)] * t5[kx + 2];
+      acc += h * t5[ky + 2];
+    }
+    bl[r][c] = (uint8_t)((acc + 32768u) >> 16);
+  }
+  __syncthreads();
+  short* DX = dxo + (long long)blockIdx.z * P.w * P.h;
+  short* DY = dyo + (long long)blockIdx.z * P.w * P.h;
+  for (int i = tid; i < 32 * 32; i += 256) {
+    int ty = i >> 5, tx = i & 31, x = X0 + tx, y = Y0 + ty;
+    if (x >= P.w || y >= P.h) continue;
+    const int r = ty + 1, c = tx + 1;
+    int a00 = bl[r - 1][c - 1], a01 = bl[r - 1][c], a02 = bl[r - 1][c + 1];
+    int a10 = bl[r][c - 1], a12 = bl[r][c + 1];
+    int a20 = bl[r + 1][c - 1], a21 = bl[r + 1][c], a22 = bl[r + 1][c + 1];
+    DX[(long long)y * P.w + x] = (short)((a02 - a00) + 2 * (a12 - a10) + (a22 - a20));
+    DY[(long long)y * P.w + x] = (short)((a20 - a00) + 2 * (a21 - a01) + (a22 - a02));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K_I LBD describe
+__constant__ float c_gaussG[63];
+__constant__ float c_gaussL[21];
+__constant__ unsigned char c_comb[64];
+
+__global__ void __launch_bounds__(64) k_lbd_describe(LineParams P, const PLKeyLineRec* __restrict__ kls, const int* __restrict__ nl,
+                                                     const short* __restrict__ dxi, const short* __restrict__ dyi,
+                                                     uint8_t* __restrict__ desc) {
+  __shared__ float rs[63][8];
+  __shared__ float band[8][9];
+  __shared__ float des[72];
+  const int li = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+  if (li >= nl[f]) return;
+  const PLKeyLineRec kl = kls[(long long)f * P.capL + li];
+  const short* DX = dxi + (long long)f * P.w * P.h;
+  const short* DY = dyi + (long long)f * P.w * P.h;
+  const short realWidth = (short)P.w, imageWidth = (short)(P.w - 1), imageHeight = (short)(P.h - 1);
+  const short lengthOfLSP = (short)kl.numOfPixels;
+  const short halfHeight = (63 - 1) / 2, halfWidth = (short)((lengthOfLSP - 1) / 2);
+  const float midX = (float)(0.5 * (double)__fadd_rn(kl.sPointInOctaveX, kl.ePointInOctaveX));
+  const float midY = (float)(0.5 * (double)__fadd_rn(kl.sPointInOctaveY, kl.ePointInOctaveY));
+  const float dL0 = (float)cos((double)kl.angle), dL1 = (float)sin((double)kl.angle);
+  const float dO0 = -dL1, dO1 = dL0;
+  if (tid < 63) {
+    const short hID = (short)tid;
+    // sCorX0/Y0 after hID updates "sCorX0 -= dL[1]; sCorY0 += dL[0]" applied sequentially (fp32, same order)
+    float sCorX0 = __fadd_rn(__fadd_rn(__fmul_rn(-dL0, (float)halfWidth), __fmul_rn(dL1, (float)halfHeight)), midX);
+    float sCorY0 = __fadd_rn(__fsub_rn(__fmul_rn(-dL1, (float)halfWidth), __fmul_rn(dL0, (float)halfHeight)), midY);
+    for (short k = 0; k < hID; k++) { sCorX0 = __fsub_rn(sCorX0, dL1); sCorY0 = __fadd_rn(sCorY0, dL0); }
+    float sCorX = sCorX0, sCorY = sCorY0;
+    float pgdL = 0, ngdL = 0, pgdO = 0, ngdO = 0;
+    for (short wID = 0; wID < lengthOfLSP; wID++) {
+      short t = (short)roundf(sCorX);
+      const short xCor = (t < 0) ? 0 : (t > imageWidth) ? imageWidth : t;
+      t = (short)roundf(sCorY);
+      const short yCor = (t < 0) ? 0 : (t > imageHeight) ? imageHeight : t;
+      const short ddx = DX[(int)yCor * realWidth + xCor], ddy = DY[(int)yCor * realWidth + xCor];
+      const float gDL = __fadd_rn(__fmul_rn((float)ddx, dL0), __fmul_rn((float)ddy, dL1));
+      const float gDO = __fadd_rn(__fmul_rn((float)ddx, dO0), __fmul_rn((float)ddy, dO1));
+      if (gDL > 0) pgdL = __fadd_rn(pgdL, gDL); else ngdL = __fsub_rn(ngdL, gDL);
+      if (gDO > 0) pgdO = __fadd_rn(pgdO, gDO); else ngdO = __fsub_rn(ngdO, gDO);
+      sCorX = __fadd_rn(sCorX, dL0); sCorY = __fadd_rn(sCorY, dL1);
+    }
+    const float c = c_gaussG[hID];
+    pgdL = __fmul_rn(c, pgdL); ngdL = __fmul_rn(c, ngdL); pgdO = __fmul_rn(c, pgdO); ngdO = __fmul_rn(c, ngdO);
+    rs[hID][0] = pgdL; rs[hID][1] = ngdL; rs[hID][2] = __fmul_rn(pgdL, pgdL); rs[hID][3] = __fmul_rn(ngdL, ngdL);
+    rs[hID][4] = pgdO; rs[hID][5] = ngdO; rs[hID][6] = __fmul_rn(pgdO, pgdO); rs[hID][7] = __fmul_rn(ngdO, ngdO);
+  }
+  __syncthreads();
+  if (tid < 8) {  // band sums of quantity q, rows visited in order (own band, band above, band below)
+    const int q = tid;
+    const bool sq = (q == 2 || q == 3 || q == 6 || q == 7);
+    float b[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) b[k] = 0.f;
+    for (int hID = 0; hID < 63; hID++) {
+      const float v = rs[hID][q];
+      int bandID = hID / 7;
+      float cg = c_gaussL[hID % 7 + 7];
+      b[bandID] = __fadd_rn(b[bandID], sq ? __fmul_rn(__fmul_rn(cg, cg), v) : __fmul_rn(cg, v));
+      bandID--;
+      if (bandID >= 0) { cg = c_gaussL[hID % 7 + 14]; b[bandID] = __fadd_rn(b[bandID], sq ? __fmul_rn(__fmul_rn(cg, cg), v) : __fmul_rn(cg, v)); }
+      bandID += 2;
+      if (bandID < 9) { cg = c_gaussL[hID % 7]; b[bandID] = __fadd_rn(b[bandID], sq ? __fmul_rn(__fmul_rn(cg, cg), v) : __fmul_rn(cg, v)); }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) band[q][k] = b[k];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const float invN2 = (float)(1.0 / (7 * 2.0)), invN3 = (float)(1.0 / (7 * 3.0));
+    for (int bb = 0; bb < 9; bb++) {
+      const float invN = (bb == 0 || bb == 8) ? invN2 : invN3;
+      const int d = bb * 8;
+      float temp;
+      temp = __fmul_rn(band[0][bb], invN); des[d] = temp; des[d + 4] = sqrtf(__fsub_rn(__fmul_rn(band[2][bb], invN), __fmul_rn(temp, temp)));
+      temp = __fmul_rn(band[1][bb], invN); des[d + 1] = temp; des[d + 5] = sqrtf(__fsub_rn(__fmul_rn(band[3][bb], invN), __fmul_rn(temp, temp)));
+      temp = __fmul_rn(band[4][bb], invN); des[d + 2] = temp; des[d + 6] = sqrtf(__fsub_rn(__fmul_rn(band[6][bb], invN), __fmul_rn(temp, temp)));
+      temp = __fmul_rn(band[5][bb], invN); des[d + 3] = temp; des[d + 7] = sqrtf(__fsub_rn(__fmul_rn(band[7][bb], invN), __fmul_rn(temp, temp)));
+    }
+    float tempM = 0, tempS = 0;
+    for (int i = 0; i < 72; i += 8) {
+      for (int k = 0; k < 4; k++) tempM = __fadd_rn(tempM, __fmul_rn(des[i + k], des[i + k]));
+      for (int k = 4; k < 8; k++) tempS = __fadd_rn(tempS, __fmul_rn(des[i + k], des[i + k]));
+    }
+    tempM = __fdiv_rn(1.f, sqrtf(tempM)); tempS = __fdiv_rn(1.f, sqrtf(tempS));
+    for (int i = 0; i < 72; i += 8) {
+      for (int k = 0; k < 4; k++) des[i + k] = __fmul_rn(des[i + k], tempM);
+      for (int k = 4; k < 8; k++) des[i + k] = __fmul_rn(des[i + k], tempS);
+    }
+    for (int i = 0; i < 72; i++) if ((double)des[i] > 0.4) des[i] = (float)0.4;
+    float temp = 0;
+    for (int i = 0; i < 72; i++) temp = __fadd_rn(temp, __fmul_rn(des[i], des[i]));
+    temp = __fdiv_rn(1.f, sqrtf(temp));
+    for (int i = 0; i < 72; i++) des[i] = __fmul_rn(des[i], temp);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const float* f1 = &des[8 * c_comb[2 * tid]];
+    const float* f2 = &des[8 * c_comb[2 * tid + 1]];
+    unsigned r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) if (f1[i] > f2[i]) r += (1u << i);
+    desc[((long long)f * P.capL + li) * 32 + tid] = (uint8_t)r;
+  }
+}
+
+}  // namespace pl
+
+// ================================================================================================ host side
+using namespace pl;
+
+struct PLLine {
+  PLLineConfig cfg;
+  LineParams P;
+  cudaStream_t stream = nullptr;
+  uint8_t *d_scaled = nullptr, *d_used = nullptr;
+  short2* d_gxy = nullptr;
+  unsigned short* d_counts = nullptr;
+  int *d_offsets = nullptr, *d_ndef = nullptr, *d_maxs = nullptr, *d_nseg = nullptr, *d_overflow = nullptr;
+  unsigned *d_order = nullptr, *d_reg = nullptr;
+  float4* d_segs = nullptr;
+  short *d_dx = nullptr, *d_dy = nullptr;
+  // host-pointer API staging
+  uint8_t* d_img = nullptr; PLKeyLineRec* d_kls = nullptr; uint8_t* d_desc = nullptr; double* d_lf = nullptr; int* d_nl = nullptr;
+  uint8_t* d_mask = nullptr;
+  size_t key_smem = 0;
+  int last_B = 0;
+};
+
+static const unsigned char h_comb[64] = {0, 1, 0, 2, 0, 3, 0, 4, 0, 5, 0, 6, 1, 2, 1, 3, 1, 4, 1, 5, 1, 6, 2, 3, 2, 4, 2, 5, 2, 6, 2, 7,
+                                         2, 8, 3, 4, 3, 5, 3, 6, 3, 7, 3, 8, 4, 5, 4, 6, 4, 7, 4, 8, 5, 6, 5, 7, 5, 8, 6, 7, 6, 8, 7, 8};
+
+extern "C" void pl_line_destroy(PLLine* h) {
+  if (!h) return;
+  cudaFree(h->d_scaled); cudaFree(h->d_used); cudaFree(h->d_gxy); cudaFree(h->d_counts); cudaFree(h->d_offsets);
+  cudaFree(h->d_ndef); cudaFree(h->d_maxs); cudaFree(h->d_nseg); cudaFree(h->d_overflow); cudaFree(h->d_order);
+  cudaFree(h->d_reg); cudaFree(h->d_segs); cudaFree(h->d_dx); cudaFree(h->d_dy); cudaFree(h->d_img); cudaFree(h->d_kls);
+  cudaFree(h->d_desc); cudaFree(h->d_lf); cudaFree(h->d_nl); cudaFree(h->d_mask);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int pl_line_create(const PLLineConfig* cfg, PLLine** out) {
+  PL_ARG(cfg && out);
+  PL_ARG(cfg->width >= 64 && cfg->height >= 64 && cfg->width < 8000 && cfg->height < 8000 && cfg->nfeatures > 0 && cfg->max_batch >= 1);
+  int rc = require_device();
+  if (rc) return rc;
+  PLLine* h = new PLLine;
+  h->cfg = *cfg;
+  LineParams& P = h->P;
+  P.w = cfg->width; P.h = cfg->height;
+  P.sw = (int)lrint(P.w * 0.8); P.sh = (int)lrint(P.h * 0.8);
+  P.npx = P.sw * P.sh;
+  P.nchunk = (P.sh - 1 + kChunkRows - 1) / kChunkRows;
+  const double ANG_TH = 22.5, QUANT = 2.0;
+  P.prec = kPI * ANG_TH / 180; P.p = ANG_TH / 180; P.density_th = 0.7;
+  const double rho = QUANT / sin(P.prec);
+  int s = 0;
+  while (sqrt((double)(s + 1) / 4.0) <= rho) s++;   // largest s with sqrt(s/4) <= rho
+  P.s_th = s;
+  const double LOG_NT = 5 * (log10((double)P.sw) + log10((double)P.sh)) / 2 + log10(11.0);
+  P.min_reg_size = (int)(size_t)(-LOG_NT / log10(P.p));
+  P.seg_cap = cfg->segment_cap > 0 ? cfg->segment_cap : 8192;
+  P.nfeatures = cfg->nfeatures; P.capL = cfg->nfeatures + 1; P.min_line_length = cfg->min_line_length;
+  { size_t c2 = 1; while (c2 < (size_t)P.seg_cap) c2 <<= 1; h->key_smem = c2 * 8; }
+  const size_t B = cfg->max_batch, npx = P.npx;
+#define LN_TRY(e) do { int _r = (e); if (_r) { pl_line_destroy(h); return _r; } } while (0)
+#define LN_CUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { set_error("%s -> %s", #e, cudaGetErrorString(_e)); pl_line_destroy(h); return PL_ERR_CUDA; } } while (0)
+  LN_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  LN_TRY(dev_alloc(&h->d_scaled, npx * B)); LN_TRY(dev_alloc(&h->d_used, npx * B)); LN_TRY(dev_alloc(&h->d_gxy, npx * B));
+  LN_TRY(dev_alloc(&h->d_counts, (size_t)kBins * P.nchunk * B)); LN_TRY(dev_alloc(&h->d_offsets, (size_t)kBins * P.nchunk * B));
+  LN_TRY(dev_alloc(&h->d_ndef, B)); LN_TRY(dev_alloc(&h->d_maxs, B)); LN_TRY(dev_alloc(&h->d_nseg, B)); LN_TRY(dev_alloc(&h->d_overflow, 1));
+  LN_TRY(dev_alloc(&h->d_order, npx * B)); LN_TRY(dev_alloc(&h->d_reg, npx * B)); LN_TRY(dev_alloc(&h->d_segs, (size_t)P.seg_cap * B));
+  LN_TRY(dev_alloc(&h->d_dx, (size_t)P.w * P.h * B)); LN_TRY(dev_alloc(&h->d_dy, (size_t)P.w * P.h * B));
+  LN_CUDA(cudaMemset(h->d_overflow, 0, sizeof(int)));
+  {  // LBD weights (binary_descriptor_custom.cpp:217-259), integer divisions as in the reference
+    float gG[63], gL[21];
+    double u = (7 * 3 - 1) / 2, sigma = (7 * 2 + 1) / 2, inv = -1 / (2 * sigma * sigma);
+    for (int i = 0; i < 21; i++) { double d = i - u; gL[i] = (float)exp(d * d * inv); }
+    u = (9 * 7 - 1) / 2; sigma = u; inv = -1 / (2 * sigma * sigma);
+    for (int i = 0; i < 63; i++) { double d = i - u; gG[i] = (float)exp(d * d * inv); }
+    LN_CUDA(cudaMemcpyToSymbol(c_gaussG, gG, sizeof(gG)));
+    LN_CUDA(cudaMemcpyToSymbol(c_gaussL, gL, sizeof(gL)));
+    LN_CUDA(cudaMemcpyToSymbol(c_comb, h_comb, sizeof(h_comb)));
+  }
+  LN_CUDA(cudaFuncSetAttribute(k_keylines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->key_smem));
+  *out = h;
+  return PL_OK;
+}
+
+extern "C" int pl_line_capacity(const PLLine* h) { return h ? h->P.capL : PL_ERR_ARG; }
+
+extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int stride, size_t frame_stride, int B,
+                                         const uint8_t* mask, void* keylines, uint8_t* desc, double* linefunc, int* n,
+                                         void* stream_) {
+  PL_ARG(h && imgs && keylines && desc && linefunc && n && B >= 1 && B <= h->cfg.max_batch && stride >= h->cfg.width);
+  cudaStream_t st = stream_ ? (cudaStream_t)stream_ : h->stream;
+  const LineParams& P = h->P;
+  h->last_B = B;
+  PL_CUDA(cudaMemsetAsync(h->d_maxs, 0, sizeof(int) * B, st));
+  k_lsd_scale<<<dim3((P.sw + 31) / 32, (P.sh + 31) / 32, B), 256, 0, st>>>(P, imgs, stride, (long long)frame_stride, h->d_scaled);
+  PL_LAUNCH_CHECK();
+  k_lsd_grad<<<dim3((P.sw + 63) / 64, (P.sh + 3) / 4, B), 256, 0, st>>>(P, h->d_scaled, h->d_gxy, h->d_used, h->d_maxs);
+  PL_LAUNCH_CHECK();
+  k_lsd_hist<<<dim3(P.nchunk, B), 256, 0, st>>>(P, h->d_gxy, h->d_maxs, h->d_counts);
+  PL_LAUNCH_CHECK();
+  k_lsd_scan<<<B, kBins, 0, st>>>(P, h->d_counts, h->d_offsets, h->d_ndef);
+  PL_LAUNCH_CHECK();
+  k_lsd_scatter<<<dim3((P.nchunk + 3) / 4, B), 128, 0, st>>>(P, h->d_gxy, h->d_maxs, h->d_offsets, h->d_order);
+  PL_LAUNCH_CHECK();
+  k_lsd_grow<<<B, 32, 0, st>>>(P, h->d_gxy, h->d_used, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow);
+  PL_LAUNCH_CHECK();
+  k_keylines<<<B, 256, h->key_smem, st>>>(P, h->d_segs, h->d_nseg, mask, (PLKeyLineRec*)keylines, linefunc, n);
+  PL_LAUNCH_CHECK();
+  k_lbd_sobel<<<dim3((P.w + 31) / 32, (P.h + 31) / 32, B), 256, 0, st>>>(P, imgs, stride, (long long)frame_stride, h->d_dx, h->d_dy);
+  PL_LAUNCH_CHECK();
+  k_lbd_describe<<<dim3(P.capL, B), 64, 0, st>>>(P, (const PLKeyLineRec*)keylines, n, h->d_dx, h->d_dy, desc);
+  PL_LAUNCH_CHECK();
+  return PL_OK;
+}
+
+static int line_staging(PLLine* h) {
+  if (h->d_img) return PL_OK;
+  const size_t B = h->cfg.max_batch;
+  int rc;
+  if ((rc = dev_alloc(&h->d_img, (size_t)h->P.w * h->P.h * B))) return rc;
+  if ((rc = dev_alloc(&h->d_kls, (size_t)h->P.capL * B))) return rc;
+  if ((rc = dev_alloc(&h->d_desc, (size_t)h->P.capL * 32 * B))) return rc;
+  if ((rc = dev_alloc(&h->d_lf, (size_t)h->P.capL * 3 * B))) return rc;
+  if ((rc = dev_alloc(&h->d_nl, B))) return rc;
+  if ((rc = dev_alloc(&h->d_mask, (size_t)h->P.w * h->P.h))) return rc;
+  return PL_OK;
+}
+
+extern "C" int pl_line_extract_batch(PLLine* h, const uint8_t* imgs, int stride, size_t frame_stride, int B,
+                                     const uint8_t* mask, void* keylines, uint8_t* desc, double* linefunc, int* n) {
+  PL_ARG(h && imgs && keylines && desc && linefunc && n && B >= 1 && B <= h->cfg.max_batch && stride >= h->cfg.width);
+  int rc = line_staging(h);
+  if (rc) return rc;
+  const int W = h->P.w, H = h->P.h;
+  for (int b = 0; b < B; b++)
+    PL_CUDA(cudaMemcpy2DAsync(h->d_img + (size_t)b * W * H, W, imgs + (size_t)b * frame_stride, stride, W, H, cudaMemcpyHostToDevice, h->stream));
+  if (mask) PL_CUDA(cudaMemcpyAsync(h->d_mask, mask, (size_t)W * H, cudaMemcpyHostToDevice, h->stream));
+  rc = pl_line_extract_batch_dev(h, h->d_img, W, (size_t)W * H, B, mask ? h->d_mask : nullptr, h->d_kls, h->d_desc, h->d_lf, h->d_nl, h->stream);
+  if (rc) return rc;
+  const size_t cap = h->P.capL;
+  PL_CUDA(cudaMemcpyAsync(keylines, h->d_kls, cap * B * sizeof(PLKeyLineRec), cudaMemcpyDeviceToHost, h->stream));
+  PL_CUDA(cudaMemcpyAsync(desc, h->d_desc, cap * B * 32, cudaMemcpyDeviceToHost, h->stream));
+  PL_CUDA(cudaMemcpyAsync(linefunc, h->d_lf, cap * B * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  PL_CUDA(cudaMemcpyAsync(n, h->d_nl, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  PL_CUDA(cudaStreamSynchronize(h->stream));
+  int ov = 0;
+  PL_CUDA(cudaMemcpy(&ov, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
+  if (ov) { cudaMemset(h->d_overflow, 0, sizeof(int)); set_error("LSD produced more than segment_cap=%d segments", h->P.seg_cap); return PL_ERR_CAPACITY; }
+  return PL_OK;
+}
+
+extern "C" int pl_line_extract(PLLine* h, const uint8_t* img, int stride, const uint8_t* mask, void* keylines,
+                               uint8_t* desc, double* linefunc, int* n) {
+  return pl_line_extract_batch(h, img, stride, 0, 1, mask, keylines, desc, linefunc, n);
+}
+
+// parity taps of the LAST call
+extern "C" int pl_line_debug_segments(PLLine* h, int frame, float* out, int cap) {
+  PL_ARG(h && frame >= 0 && frame < h->last_B);
+  int n = 0;
+  PL_CUDA(cudaStreamSynchronize(h->stream));
+  PL_CUDA(cudaMemcpy(&n, h->d_nseg + frame, sizeof(int), cudaMemcpyDeviceToHost));
+  if (out && n) PL_CUDA(cudaMemcpy(out, h->d_segs + (size_t)frame * h->P.seg_cap, sizeof(float4) * std::min(n, cap), cudaMemcpyDeviceToHost));
+  return n;
+}
+extern "C" int pl_line_debug_scaled(PLLine* h, int frame, uint8_t* out, int* sw, int* sh) {
+  PL_ARG(h && frame >= 0 && frame < h->last_B && sw && sh);
+  *sw = h->P.sw; *sh = h->P.sh;
+  PL_CUDA(cudaStreamSynchronize(h->stream));
+  if (out) PL_CUDA(cudaMemcpy(out, h->d_scaled + (size_t)frame * h->P.npx, h->P.npx, cudaMemcpyDeviceToHost));
+  return PL_OK;
+}
+extern "C" int pl_line_debug_sobel(PLLine* h, int frame, short* dx, short* dy) {
+  PL_ARG(h && frame >= 0 && frame < h->last_B && dx && dy);
+  const size_t n = (size_t)h->P.w * h->P.h;
+  PL_CUDA(cudaStreamSynchronize(h->stream));
+  PL_CUDA(cudaMemcpy(dx, h->d_dx + frame * n, n * 2, cudaMemcpyDeviceToHost));
+  PL_CUDA(cudaMemcpy(dy, h->d_dy + frame * n, n * 2, cudaMemcpyDeviceToHost));
+  return PL_OK;
+}
+extern "C" int pl_line_debug_order(PLLine* h, int frame, unsigned* out, int cap) {
+  PL_ARG(h && frame >= 0 && frame < h->last_B);
+  int n = 0;
+  PL_CUDA(cudaStreamSynchronize(h->stream));
+  PL_CUDA(cudaMemcpy(&n, h->d_ndef + frame, sizeof(int), cudaMemcpyDeviceToHost));
+  if (out && n) PL_CUDA(cudaMemcpy(out, h->d_order + (size_t)frame * h->P.npx, sizeof(unsigned) * std::min(n, cap), cudaMemcpyDeviceToHost));
+  return n;
+}

@@ -183,6 +183,47 @@ int pl_line_debug_scaled(PLLine* h, int frame, uint8_t* out, int* sw, int* sh);
 int pl_line_debug_sobel(PLLine* h, int frame, short* dx, short* dy);
 int pl_line_debug_order(PLLine* h, int frame, unsigned* out, int cap);
 
+/* ------------------------------------------------------------------ per-frame front-end pipeline (batch of frames)
+ * The hot-path calls Tracking makes for one frame, chained on one stream with all intermediates in
+ * HBM: ORB extract, LSD+LBD extract, point matching frame k-1 -> k (SearchForInitialization scheme, window 100,
+ * ratio 0.9), line matching (SearchDouble), and two Optimizer::PoseOptimization calls on the frame's pose problem.
+ * Frame 0's predecessor is the last frame of the batch.  This is bench.py's "step".                              */
+typedef struct PLFrontendConfig {
+  int width, height, max_batch;
+  int orb_nfeatures; float orb_scale_factor; int orb_nlevels, orb_ini_th, orb_min_th;
+  int line_nfeatures; double line_min_length;
+  int lm_cap_points, lm_cap_lines;     /* capacity of the per-frame pose problems */
+} PLFrontendConfig;
+typedef struct PLFrontend PLFrontend;
+int pl_frontend_create(const PLFrontendConfig* cfg, PLFrontend** out);
+void pl_frontend_destroy(PLFrontend* h);
+int pl_frontend_capacities(const PLFrontend* h, int* cap_keypoints, int* cap_lines);
+/* upload the batch's pose problems (host pointers, [B][cap] layouts as in pl_pose_optimization_dev) */
+int pl_frontend_set_pose_problems(PLFrontend* h, int B, const float* Tcw0, const float* K, const int* n_points,
+                                  const float* pt_obs, const float* pt_inv_sigma2, const float* pt_Xw, const int* n_lines,
+                                  const double* line_func, const double* line_Xw);
+/* device-resident step (imgs = device pointer; NULL = frames uploaded by the last pl_frontend_run); asynchronous */
+int pl_frontend_run_dev(PLFrontend* h, const uint8_t* imgs, int stride, size_t frame_stride, int B, void* stream);
+/* end-to-end step on HOST buffers: H2D frames, device step, D2H of every per-frame result; synchronous.
+ * outputs: kps/desc/n [B][capK], keylines/ldesc/linefunc/nl [B][capL], pt_matches [B][capK] (index into frame k of
+ * the match of keypoint i of frame k-1, or -1), line_matches [B][capL], poses [2][B][16], inliers [2][B]. */
+int pl_frontend_run(PLFrontend* h, const uint8_t* imgs, int stride, size_t frame_stride, int B, PLKeyPoint* kps,
+                    uint8_t* desc, int* n, void* keylines, uint8_t* ldesc, double* linefunc, int* nl, int* pt_matches,
+                    int* n_pt_matches, int* line_matches, int* n_line_matches, float* poses, int* inliers);
+int pl_frontend_io_bytes(const PLFrontend* h, long long* h2d_per_frame, long long* d2h_per_frame);
+int pl_frontend_fetch(PLFrontend* h, int B, PLKeyPoint* kps, uint8_t* desc, int* n, void* keylines, uint8_t* ldesc, int* nl,
+                      int* pt_matches, int* n_pt_matches, int* line_matches, int* n_line_matches, float* poses, int* inliers);
+
+/* measurement hooks (bench.py): CUDA-event timing of k_lsd_grow on its launching stream, its algorithmic bytes, and
+ * a device copy of the second-call poses [B][16] for the multi-GPU all-gather */
+int pl_line_set_timing(PLLine* h, int on);
+int pl_line_grow_ms(PLLine* h, float* ms);
+long long pl_line_grow_bytes_per_frame(const PLLine* h);
+int pl_frontend_set_timing(PLFrontend* h, int on);
+int pl_frontend_grow_ms(PLFrontend* h, float* ms);
+long long pl_frontend_grow_bytes_per_frame(const PLFrontend* h);
+int pl_frontend_copy_poses_dev(PLFrontend* h, int B, float* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

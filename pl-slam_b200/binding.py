@@ -377,3 +377,117 @@ class LINEextractor:
         out = np.zeros(max(n, 1), np.uint32)
         check(lib().pl_line_debug_order(self._h, frame, _p(out), n))
         return out[:n]
+
+
+# ---------------------------------------------------------------------------------------------- front-end pipeline
+class PLFrontendConfig(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("max_batch", C.c_int), ("orb_nfeatures", C.c_int),
+                ("orb_scale_factor", C.c_float), ("orb_nlevels", C.c_int), ("orb_ini_th", C.c_int), ("orb_min_th", C.c_int),
+                ("line_nfeatures", C.c_int), ("line_min_length", C.c_double), ("lm_cap_points", C.c_int),
+                ("lm_cap_lines", C.c_int)]
+
+
+class Frontend:
+    """Batch front-end: ORB + LSD/LBD extraction, frame-to-frame matching, 2 x PoseOptimization per frame."""
+
+    def __init__(self, width=640, height=480, max_batch=8, orb=(1000, 1.2, 8, 20, 7), lines=(200, 0.0), lm_caps=(512, 128)):
+        self.cfg = PLFrontendConfig(width, height, max_batch, orb[0], orb[1], orb[2], orb[3], orb[4], lines[0], lines[1],
+                                    lm_caps[0], lm_caps[1])
+        self._h = vp()
+        L = lib()
+        L.pl_frontend_create.argtypes = [C.POINTER(PLFrontendConfig), C.POINTER(vp)]
+        L.pl_frontend_destroy.argtypes = [vp]
+        L.pl_frontend_capacities.argtypes = [vp, vp, vp]
+        L.pl_frontend_set_pose_problems.argtypes = [vp, C.c_int] + [vp] * 9
+        L.pl_frontend_run_dev.argtypes = [vp, vp, C.c_int, C.c_size_t, C.c_int, vp]
+        L.pl_frontend_run.argtypes = [vp, vp, C.c_int, C.c_size_t, C.c_int] + [vp] * 13
+        L.pl_frontend_io_bytes.argtypes = [vp, vp, vp]
+        L.pl_frontend_fetch.argtypes = [vp, C.c_int] + [vp] * 12
+        L.pl_frontend_set_timing.argtypes = [vp, C.c_int]
+        L.pl_frontend_grow_ms.argtypes = [vp, vp]
+        L.pl_frontend_grow_bytes_per_frame.argtypes = [vp]
+        L.pl_frontend_grow_bytes_per_frame.restype = C.c_longlong
+        L.pl_frontend_copy_poses_dev.argtypes = [vp, C.c_int, vp, vp]
+        check(L.pl_frontend_create(C.byref(self.cfg), C.byref(self._h)))
+        ck, cl = C.c_int(), C.c_int()
+        check(L.pl_frontend_capacities(self._h, C.byref(ck), C.byref(cl)))
+        self.capK, self.capL = ck.value, cl.value
+        self.cap_points, self.cap_lines = lm_caps
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().pl_frontend_destroy(self._h)
+            self._h = vp()
+
+    def set_pose_problems(self, problems):
+        """problems: list of dicts from synth.synth_pose_problem (one per frame of the batch)."""
+        B, cp, cl = len(problems), self.cap_points, self.cap_lines
+        T0 = np.zeros((B, 16), np.float32); K = np.zeros((B, 4), np.float32)
+        npt = np.zeros(B, np.int32); nln = np.zeros(B, np.int32)
+        obs = np.zeros((B, cp, 2), np.float32); w = np.zeros((B, cp), np.float32); X = np.zeros((B, cp, 3), np.float32)
+        lf = np.zeros((B, cl, 3), np.float64); lX = np.zeros((B, cl, 6), np.float64)
+        for b, p in enumerate(problems):
+            n, m = len(p["pt_obs"]), len(p["line_func"])
+            assert n <= cp and m <= cl
+            T0[b] = p["Tcw0"].ravel(); K[b] = p["K"]; npt[b] = n; nln[b] = m
+            obs[b, :n] = p["pt_obs"]; w[b, :n] = p["pt_inv_sigma2"]; X[b, :n] = p["pt_Xw"]
+            lf[b, :m] = p["line_func"]; lX[b, :m] = p["line_Xw"]
+        self._problems = (T0, K, npt, obs, w, X, nln, lf, lX)
+        check(lib().pl_frontend_set_pose_problems(self._h, B, _p(T0), _p(K), _p(npt), _p(obs), _p(w), _p(X), _p(nln), _p(lf), _p(lX)))
+
+    def alloc_outputs(self, B, pinned=False):
+        shapes = dict(kps=((B, self.capK), KP_DTYPE), desc=((B, self.capK, 32), np.uint8), n=((B,), np.int32),
+                      keylines=((B, self.capL), KEYLINE_DTYPE), ldesc=((B, self.capL, 32), np.uint8),
+                      linefunc=((B, self.capL, 3), np.float64), nl=((B,), np.int32), pt_matches=((B, self.capK), np.int32),
+                      n_pt_matches=((B,), np.int32), line_matches=((B, self.capL), np.int32), n_line_matches=((B,), np.int32),
+                      poses=((2, B, 16), np.float32), inliers=((2, B), np.int32))
+        out = {}
+        for k, (shp, dt) in shapes.items():
+            if pinned:
+                import torch
+                nbytes = int(np.prod(shp)) * np.dtype(dt).itemsize
+                t = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+                out["_pin_" + k] = t
+                out[k] = t.numpy()[:nbytes].view(dt).reshape(shp)
+            else:
+                out[k] = np.zeros(shp, dt)
+        return out
+
+    ORDER = ["kps", "desc", "n", "keylines", "ldesc", "linefunc", "nl", "pt_matches", "n_pt_matches", "line_matches",
+             "n_line_matches", "poses", "inliers"]
+
+    def run(self, images, out=None):
+        """End-to-end on host buffers (images: uint8 [B][H][W])."""
+        B = images.shape[0]
+        out = out or self.alloc_outputs(B)
+        check(lib().pl_frontend_run(self._h, _p(images), images.strides[1], images.strides[0], B,
+                                    *[_p(out[k]) for k in self.ORDER]))
+        return out
+
+    def run_dev(self, img_ptr, stride, frame_stride, B, stream=None):
+        check(lib().pl_frontend_run_dev(self._h, img_ptr, stride, frame_stride, B, stream))
+
+    def fetch(self, B):
+        out = self.alloc_outputs(B)
+        order = [k for k in self.ORDER if k != "linefunc"]
+        check(lib().pl_frontend_fetch(self._h, B, *[_p(out[k]) for k in order]))
+        return out
+
+    def io_bytes(self):
+        a, b = C.c_longlong(), C.c_longlong()
+        check(lib().pl_frontend_io_bytes(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_timing(self, on=True):
+        check(lib().pl_frontend_set_timing(self._h, int(on)))
+
+    def grow_ms(self):
+        ms = C.c_float()
+        check(lib().pl_frontend_grow_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def grow_bytes_per_frame(self):
+        return int(lib().pl_frontend_grow_bytes_per_frame(self._h))
+
+    def copy_poses_dev(self, B, dst_ptr, stream=None):
+        check(lib().pl_frontend_copy_poses_dev(self._h, B, dst_ptr, stream))

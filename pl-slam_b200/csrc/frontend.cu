@@ -1,0 +1,231 @@
+// Per-frame front-end pipeline for a batch of frames: the sequence of hot-path calls that Tracking makes for one
+// frame, chained on one stream with every intermediate resident in HBM:
+//   Frame::ExtractORB  -> pl_orb_extract_batch_dev          (Frame.cc:224 -> ORBextractor::operator())
+//   Frame::ExtractLSD  -> pl_line_extract_batch_dev         (Frame.cc:225 -> LINEextractor::operator())
+//   point matching     -> pl_orb_search_for_initialization_dev  frame k-1 -> frame k (ORBmatcher.cc:455-572 scheme)
+//   line matching      -> pl_lsd_search_double_dev               frame k-1 <-> frame k (LSDmatcher.cpp:440-486)
+//   2 x Optimizer::PoseOptimization -> pl_pose_optimization_dev  (Tracking.cc:1372 and :1503)
+// This is the measured "step" of bench.py and the e2e entry point (host buffers in, host buffers out).
+
+#include "common.cuh"
+#include <vector>
+#include <string.h>
+
+namespace pl {
+__global__ void k_prev_matched_init(const PLKeyPoint* __restrict__ kps, const int* __restrict__ n, int cap, int B,
+                                    float* __restrict__ pm) {
+  // vbPrevMatched[i] = F1.mvKeysUn[i].pt with F1 = frame (b-1+B)%B
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pb = (b + B - 1) % B;
+  if (i < n[pb]) { pm[((long long)b * cap + i) * 2] = kps[(long long)pb * cap + i].x; pm[((long long)b * cap + i) * 2 + 1] = kps[(long long)pb * cap + i].y; }
+}
+}  // namespace pl
+using namespace pl;
+
+struct PLFrontend {
+  PLFrontendConfig cfg;
+  PLOrb* orb = nullptr;
+  PLLine* line = nullptr;
+  cudaStream_t stream = nullptr;
+  int B = 0, capK = 0, capL = 0;
+  // device-resident per-batch state
+  uint8_t* d_img = nullptr;
+  PLKeyPoint* d_kps = nullptr; uint8_t* d_desc = nullptr; int* d_n = nullptr;
+  void* d_kl = nullptr; uint8_t* d_ldesc = nullptr; double* d_lf = nullptr; int* d_nl = nullptr;
+  float* d_bounds = nullptr; float* d_pm = nullptr; int* d_m12 = nullptr; int* d_nm = nullptr; int* d_scr = nullptr;
+  int* d_lm = nullptr; int* d_nlm = nullptr;
+  // rotated views so that "previous frame" is a plain pointer offset: copies of frame B-1 placed before frame 0
+  PLKeyPoint* d_kps_prev = nullptr; uint8_t* d_desc_prev = nullptr; int* d_n_prev = nullptr;
+  uint8_t* d_ldesc_prev = nullptr; int* d_nl_prev = nullptr;
+  // LM problems
+  float *d_T0 = nullptr, *d_K = nullptr, *d_pobs = nullptr, *d_pw = nullptr, *d_pX = nullptr, *d_Tout = nullptr;
+  double *d_lfun = nullptr, *d_lX = nullptr, *d_scratch = nullptr;
+  int *d_np = nullptr, *d_nl_lm = nullptr, *d_inl = nullptr, *d_its = nullptr;
+  uint8_t *d_pout = nullptr, *d_lout = nullptr;
+};
+
+extern "C" void pl_frontend_destroy(PLFrontend* h) {
+  if (!h) return;
+  pl_orb_destroy(h->orb); pl_line_destroy(h->line);
+  void* ptrs[] = {h->d_img, h->d_kl, h->d_lf, h->d_bounds, h->d_pm, h->d_m12,
+                  h->d_nm, h->d_scr, h->d_lm, h->d_nlm, h->d_kps_prev, h->d_desc_prev, h->d_n_prev, h->d_ldesc_prev, h->d_nl_prev,
+                  h->d_T0, h->d_K, h->d_pobs, h->d_pw, h->d_pX, h->d_Tout, h->d_lfun, h->d_lX, h->d_scratch, h->d_np, h->d_nl_lm,
+                  h->d_inl, h->d_its, h->d_pout, h->d_lout};
+  for (void* p : ptrs) cudaFree(p);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int pl_frontend_create(const PLFrontendConfig* cfg, PLFrontend** out) {
+  PL_ARG(cfg && out && cfg->max_batch >= 1 && cfg->lm_cap_points >= 1 && cfg->lm_cap_lines >= 1);
+  int rc = require_device();
+  if (rc) return rc;
+  PLFrontend* h = new PLFrontend;
+  h->cfg = *cfg;
+  h->B = cfg->max_batch;
+#define FE_TRY(e) do { int _r = (e); if (_r) { pl_frontend_destroy(h); return _r; } } while (0)
+#define FE_CUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { set_error("%s -> %s", #e, cudaGetErrorString(_e)); pl_frontend_destroy(h); return PL_ERR_CUDA; } } while (0)
+  PLOrbConfig oc = {cfg->width, cfg->height, cfg->orb_nfeatures, cfg->orb_scale_factor, cfg->orb_nlevels, cfg->orb_ini_th, cfg->orb_min_th, cfg->max_batch, 0};
+  FE_TRY(pl_orb_create(&oc, &h->orb));
+  PLLineConfig lc = {cfg->width, cfg->height, cfg->line_nfeatures, cfg->line_min_length, cfg->max_batch, 0};
+  FE_TRY(pl_line_create(&lc, &h->line));
+  h->capK = pl_orb_capacity(h->orb); h->capL = pl_line_capacity(h->line);
+  FE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  const size_t B = h->B, cK = h->capK, cL = h->capL, cp = cfg->lm_cap_points, cl = cfg->lm_cap_lines;
+  FE_TRY(dev_alloc(&h->d_img, (size_t)cfg->width * cfg->height * B));
+  // feature arrays hold B+1 frames: slot 0 = copy of the batch's last frame ("previous" of frame 0), slots 1..B = frames
+  FE_TRY(dev_alloc(&h->d_kps_prev, cK * (B + 1))); h->d_kps = h->d_kps_prev + cK;
+  FE_TRY(dev_alloc(&h->d_desc_prev, cK * 32 * (B + 1))); h->d_desc = h->d_desc_prev + cK * 32;
+  FE_TRY(dev_alloc(&h->d_n_prev, B + 1)); h->d_n = h->d_n_prev + 1;
+  FE_TRY(dev_alloc(&h->d_ldesc_prev, cL * 32 * (B + 1))); h->d_ldesc = h->d_ldesc_prev + cL * 32;
+  FE_TRY(dev_alloc(&h->d_nl_prev, B + 1)); h->d_nl = h->d_nl_prev + 1;
+  { uint8_t* p = nullptr; FE_TRY(dev_alloc(&p, cL * 68 * B)); h->d_kl = p; }
+  FE_TRY(dev_alloc(&h->d_lf, cL * 3 * B));
+  FE_TRY(dev_alloc(&h->d_bounds, 4)); FE_TRY(dev_alloc(&h->d_pm, cK * 2 * B)); FE_TRY(dev_alloc(&h->d_m12, cK * B));
+  FE_TRY(dev_alloc(&h->d_nm, B)); FE_TRY(dev_alloc(&h->d_scr, cK * 2 * B)); FE_TRY(dev_alloc(&h->d_lm, cL * B)); FE_TRY(dev_alloc(&h->d_nlm, B));
+  float bounds[4] = {0.f, 0.f, (float)cfg->width, (float)cfg->height};   // Frame::ComputeImageBounds without distortion
+  FE_CUDA(cudaMemcpy(h->d_bounds, bounds, sizeof(bounds), cudaMemcpyHostToDevice));
+  FE_TRY(dev_alloc(&h->d_T0, 16 * B)); FE_TRY(dev_alloc(&h->d_K, 4 * B)); FE_TRY(dev_alloc(&h->d_pobs, cp * 2 * B));
+  FE_TRY(dev_alloc(&h->d_pw, cp * B)); FE_TRY(dev_alloc(&h->d_pX, cp * 3 * B)); FE_TRY(dev_alloc(&h->d_Tout, 16 * B * 2));
+  FE_TRY(dev_alloc(&h->d_lfun, cl * 3 * B)); FE_TRY(dev_alloc(&h->d_lX, cl * 6 * B));
+  FE_TRY(dev_alloc(&h->d_scratch, pl_pose_optimization_scratch_doubles((int)B, (int)cp, (int)cl)));
+  FE_TRY(dev_alloc(&h->d_np, B)); FE_TRY(dev_alloc(&h->d_nl_lm, B)); FE_TRY(dev_alloc(&h->d_inl, B * 2)); FE_TRY(dev_alloc(&h->d_its, B * 2));
+  FE_TRY(dev_alloc(&h->d_pout, cp * B * 2)); FE_TRY(dev_alloc(&h->d_lout, cl * B * 2));
+  *out = h;
+  return PL_OK;
+}
+
+extern "C" int pl_frontend_capacities(const PLFrontend* h, int* cap_keypoints, int* cap_lines) {
+  PL_ARG(h);
+  if (cap_keypoints) *cap_keypoints = h->capK;
+  if (cap_lines) *cap_lines = h->capL;
+  return PL_OK;
+}
+
+// LM problems of the batch (device-resident until replaced).  Host pointers; [B][cap] layouts.
+extern "C" int pl_frontend_set_pose_problems(PLFrontend* h, int B, const float* Tcw0, const float* K, const int* n_points,
+                                             const float* pt_obs, const float* pt_inv_sigma2, const float* pt_Xw,
+                                             const int* n_lines, const double* line_func, const double* line_Xw) {
+  PL_ARG(h && B >= 1 && B <= h->B && Tcw0 && K && n_points && pt_obs && pt_inv_sigma2 && pt_Xw && n_lines && line_func && line_Xw);
+  const size_t cp = h->cfg.lm_cap_points, cl = h->cfg.lm_cap_lines, b = B;
+  cudaStream_t st = h->stream;
+  PL_CUDA(cudaMemcpyAsync(h->d_T0, Tcw0, 64 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_K, K, 16 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_np, n_points, 4 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_nl_lm, n_lines, 4 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_pobs, pt_obs, cp * 8 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_pw, pt_inv_sigma2, cp * 4 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_pX, pt_Xw, cp * 12 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_lfun, line_func, cl * 24 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_lX, line_Xw, cl * 48 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaStreamSynchronize(st));
+  return PL_OK;
+}
+
+// The timed device-resident step: frames already in HBM (imgs = device pointer, or NULL = the frames uploaded by the
+// last pl_frontend_run()).  Everything asynchronous on `stream` (NULL = the handle's own stream).
+extern "C" int pl_frontend_run_dev(PLFrontend* h, const uint8_t* imgs, int stride, size_t frame_stride, int B, void* stream_) {
+  PL_ARG(h && B >= 1 && B <= h->B);
+  cudaStream_t st = stream_ ? (cudaStream_t)stream_ : h->stream;
+  if (!imgs) { imgs = h->d_img; stride = h->cfg.width; frame_stride = (size_t)h->cfg.width * h->cfg.height; }
+  const size_t cK = h->capK, cL = h->capL;
+  int rc;
+  if ((rc = pl_orb_extract_batch_dev(h->orb, imgs, stride, frame_stride, B, h->d_kps, h->d_desc, h->d_n, st))) return rc;
+  if ((rc = pl_line_extract_batch_dev(h->line, imgs, stride, frame_stride, B, nullptr, h->d_kl, h->d_ldesc, h->d_lf, h->d_nl, st))) return rc;
+  // slot 0 <- frame B-1 so that frame b's predecessor is slot b (a plain offset)
+  PL_CUDA(cudaMemcpyAsync(h->d_kps_prev, h->d_kps + cK * (B - 1), cK * sizeof(PLKeyPoint), cudaMemcpyDeviceToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_desc_prev, h->d_desc + cK * 32 * (B - 1), cK * 32, cudaMemcpyDeviceToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_n_prev, h->d_n + (B - 1), sizeof(int), cudaMemcpyDeviceToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_ldesc_prev, h->d_ldesc + cL * 32 * (B - 1), cL * 32, cudaMemcpyDeviceToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_nl_prev, h->d_nl + (B - 1), sizeof(int), cudaMemcpyDeviceToDevice, st));
+  k_prev_matched_init<<<dim3((unsigned)((cK + 127) / 128), B), 128, 0, st>>>(h->d_kps, h->d_n, (int)cK, B, h->d_pm);
+  PL_LAUNCH_CHECK();
+  if ((rc = pl_orb_search_for_initialization_dev(h->d_kps_prev, h->d_desc_prev, h->d_n_prev, h->d_kps, h->d_desc, h->d_n, (int)cK, B,
+                                                 h->d_bounds, h->d_pm, h->d_m12, h->d_nm, 100, 0.9f, 1, h->d_scr, st))) return rc;
+  if ((rc = pl_lsd_search_double_dev(h->d_ldesc_prev, h->d_nl_prev, h->d_ldesc, h->d_nl, (int)cL, (int)cL, B, 50.f, 0.7f, 1, h->d_lm,
+                                     h->d_nlm, st))) return rc;
+  const size_t cp = h->cfg.lm_cap_points, cl = h->cfg.lm_cap_lines;
+  for (int call = 0; call < 2; call++)   // TrackWithMotionModel (Tracking.cc:1372) and TrackLocalMapWithLines (:1503)
+    if ((rc = pl_pose_optimization_dev(0, B, h->d_T0, h->d_K, h->d_np, (int)cp, h->d_pobs, h->d_pw, h->d_pX, h->d_nl_lm, (int)cl,
+                                       h->d_lfun, h->d_lX, h->d_Tout + 16 * (size_t)B * call, h->d_pout + cp * B * call,
+                                       h->d_lout + cl * B * call, h->d_inl + (size_t)B * call, h->d_its + (size_t)B * call,
+                                       h->d_scratch, st))) return rc;
+  return PL_OK;
+}
+
+// End-to-end step on HOST buffers: H2D of the frames, the device step, D2H of every per-frame result.
+extern "C" int pl_frontend_run(PLFrontend* h, const uint8_t* imgs, int stride, size_t frame_stride, int B, PLKeyPoint* kps,
+                               uint8_t* desc, int* n, void* keylines, uint8_t* ldesc, double* linefunc, int* nl,
+                               int* pt_matches, int* n_pt_matches, int* line_matches, int* n_line_matches, float* poses,
+                               int* inliers) {
+  PL_ARG(h && imgs && B >= 1 && B <= h->B && kps && desc && n && keylines && ldesc && linefunc && nl && pt_matches &&
+         n_pt_matches && line_matches && n_line_matches && poses && inliers);
+  const int W = h->cfg.width, H = h->cfg.height;
+  cudaStream_t st = h->stream;
+  if (stride == W && frame_stride == (size_t)W * H)
+    PL_CUDA(cudaMemcpyAsync(h->d_img, imgs, (size_t)W * H * B, cudaMemcpyHostToDevice, st));
+  else
+    for (int b = 0; b < B; b++)
+      PL_CUDA(cudaMemcpy2DAsync(h->d_img + (size_t)b * W * H, W, imgs + (size_t)b * frame_stride, stride, W, H, cudaMemcpyHostToDevice, st));
+  int rc = pl_frontend_run_dev(h, nullptr, 0, 0, B, st);
+  if (rc) return rc;
+  const size_t cK = h->capK, cL = h->capL, b = B;
+  PL_CUDA(cudaMemcpyAsync(kps, h->d_kps, cK * b * sizeof(PLKeyPoint), cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaMemcpyAsync(desc, h->d_desc, cK * b * 32, cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaMemcpyAsync(n, h->d_n, b * 4, cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaMemcpyAsync(keylines, h->d_kl, cL * b * 68, cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaMemcpyAsync(ldesc, h->d_ldesc, cL * b * 32, cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaMemcpyAsync(linefunc, h->d_lf, cL * b * 24, cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaMemcpyAsync(nl, h->d_nl, b * 4, cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaMemcpyAsync(pt_matches, h->d_m12, cK * b * 4, cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaMemcpyAsync(n_pt_matches, h->d_nm, b * 4, cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaMemcpyAsync(line_matches, h->d_lm, cL * b * 4, cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaMemcpyAsync(n_line_matches, h->d_nlm, b * 4, cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaMemcpyAsync(poses, h->d_Tout, 64 * b * 2, cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaMemcpyAsync(inliers, h->d_inl, 4 * b * 2, cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaStreamSynchronize(st));
+  return PL_OK;
+}
+
+// bytes moved per frame by pl_frontend_run (for bench.py's e2e accounting)
+extern "C" int pl_frontend_io_bytes(const PLFrontend* h, long long* h2d_per_frame, long long* d2h_per_frame) {
+  PL_ARG(h && h2d_per_frame && d2h_per_frame);
+  const long long cK = h->capK, cL = h->capL;
+  *h2d_per_frame = (long long)h->cfg.width * h->cfg.height;
+  *d2h_per_frame = cK * (28 + 32 + 4) + 4 + cL * (68 + 32 + 24 + 4) + 4 + 8 + 128 + 8;
+  return PL_OK;
+}
+
+// copy device-resident results of the last run to host (used by tests to check the device path)
+extern "C" int pl_frontend_fetch(PLFrontend* h, int B, PLKeyPoint* kps, uint8_t* desc, int* n, void* keylines, uint8_t* ldesc,
+                                 int* nl, int* pt_matches, int* n_pt_matches, int* line_matches, int* n_line_matches,
+                                 float* poses, int* inliers) {
+  PL_ARG(h && B >= 1 && B <= h->B);
+  const size_t cK = h->capK, cL = h->capL, b = B;
+  PL_CUDA(cudaStreamSynchronize(h->stream));
+  PL_CUDA(cudaDeviceSynchronize());
+  if (kps) PL_CUDA(cudaMemcpy(kps, h->d_kps, cK * b * sizeof(PLKeyPoint), cudaMemcpyDeviceToHost));
+  if (desc) PL_CUDA(cudaMemcpy(desc, h->d_desc, cK * b * 32, cudaMemcpyDeviceToHost));
+  if (n) PL_CUDA(cudaMemcpy(n, h->d_n, b * 4, cudaMemcpyDeviceToHost));
+  if (keylines) PL_CUDA(cudaMemcpy(keylines, h->d_kl, cL * b * 68, cudaMemcpyDeviceToHost));
+  if (ldesc) PL_CUDA(cudaMemcpy(ldesc, h->d_ldesc, cL * b * 32, cudaMemcpyDeviceToHost));
+  if (nl) PL_CUDA(cudaMemcpy(nl, h->d_nl, b * 4, cudaMemcpyDeviceToHost));
+  if (pt_matches) PL_CUDA(cudaMemcpy(pt_matches, h->d_m12, cK * b * 4, cudaMemcpyDeviceToHost));
+  if (n_pt_matches) PL_CUDA(cudaMemcpy(n_pt_matches, h->d_nm, b * 4, cudaMemcpyDeviceToHost));
+  if (line_matches) PL_CUDA(cudaMemcpy(line_matches, h->d_lm, cL * b * 4, cudaMemcpyDeviceToHost));
+  if (n_line_matches) PL_CUDA(cudaMemcpy(n_line_matches, h->d_nlm, b * 4, cudaMemcpyDeviceToHost));
+  if (poses) PL_CUDA(cudaMemcpy(poses, h->d_Tout, 64 * b * 2, cudaMemcpyDeviceToHost));
+  if (inliers) PL_CUDA(cudaMemcpy(inliers, h->d_inl, 4 * b * 2, cudaMemcpyDeviceToHost));
+  return PL_OK;
+}
+
+// hooks used by bench.py: timing of the dominant kernel and a device-to-device copy of the pose records that the
+// multi-GPU run all-gathers
+extern "C" int pl_frontend_set_timing(PLFrontend* h, int on) { PL_ARG(h); return pl_line_set_timing(h->line, on); }
+extern "C" int pl_frontend_grow_ms(PLFrontend* h, float* ms) { PL_ARG(h); return pl_line_grow_ms(h->line, ms); }
+extern "C" long long pl_frontend_grow_bytes_per_frame(const PLFrontend* h) { return h ? pl_line_grow_bytes_per_frame(h->line) : 0; }
+extern "C" int pl_frontend_copy_poses_dev(PLFrontend* h, int B, float* dst, void* stream) {
+  PL_ARG(h && dst && B >= 1 && B <= h->B);
+  PL_CUDA(cudaMemcpyAsync(dst, h->d_Tout + 16 * (size_t)B, 64 * (size_t)B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return PL_OK;
+}

@@ -721,6 +721,9 @@ struct PLLine {
   uint8_t* d_mask = nullptr;
   size_t key_smem = 0;
   int last_B = 0;
+  // optional device timing of the dominant kernel (bench.py roofline): events on the launching stream
+  int timing = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 static const unsigned char h_comb[64] = {0, 1, 0, 2, 0, 3, 0, 4, 0, 5, 0, 6, 1, 2, 1, 3, 1, 4, 1, 5, 1, 6, 2, 3, 2, 4, 2, 5, 2, 6, 2, 7,
@@ -786,6 +789,23 @@ extern "C" int pl_line_create(const PLLineConfig* cfg, PLLine** out) {
 
 extern "C" int pl_line_capacity(const PLLine* h) { return h ? h->P.capL : PL_ERR_ARG; }
 
+// Device timing of k_lsd_grow (the dominant kernel): enable, run, then read the duration of the LAST launch.
+extern "C" int pl_line_set_timing(PLLine* h, int on) {
+  PL_ARG(h);
+  if (on && !h->ev0) { PL_CUDA(cudaEventCreate(&h->ev0)); PL_CUDA(cudaEventCreate(&h->ev1)); }
+  h->timing = on;
+  return PL_OK;
+}
+extern "C" int pl_line_grow_ms(PLLine* h, float* ms) {
+  PL_ARG(h && ms && h->ev0);
+  PL_CUDA(cudaEventSynchronize(h->ev1));
+  PL_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return PL_OK;
+}
+/* algorithmic bytes k_lsd_grow must move for one frame: per scaled pixel gradient pair (4) + used flag
+ * read and written (2) + seed order entry (4) */
+extern "C" long long pl_line_grow_bytes_per_frame(const PLLine* h) { return h ? (long long)h->P.npx * 10 : 0; }
+
 extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int stride, size_t frame_stride, int B,
                                          const uint8_t* mask, void* keylines, uint8_t* desc, double* linefunc, int* n,
                                          void* stream_) {
@@ -804,8 +824,10 @@ extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int str
   PL_LAUNCH_CHECK();
   k_lsd_scatter<<<dim3((P.nchunk + 3) / 4, B), 128, 0, st>>>(P, h->d_gxy, h->d_maxs, h->d_offsets, h->d_order);
   PL_LAUNCH_CHECK();
+  if (h->timing) PL_CUDA(cudaEventRecord(h->ev0, st));
   k_lsd_grow<<<B, 32, 0, st>>>(P, h->d_gxy, h->d_used, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow);
   PL_LAUNCH_CHECK();
+  if (h->timing) PL_CUDA(cudaEventRecord(h->ev1, st));
   k_keylines<<<B, 256, h->key_smem, st>>>(P, h->d_segs, h->d_nseg, mask, (PLKeyLineRec*)keylines, linefunc, n);
   PL_LAUNCH_CHECK();
   k_lbd_sobel<<<dim3((P.w + 31) / 32, (P.h + 31) / 32, B), 256, 0, st>>>(P, imgs, stride, (long long)frame_stride, h->d_dx, h->d_dy);

@@ -1,0 +1,52 @@
+"""GPU test of the batch front-end (the bench "step" and e2e entry point): every per-frame result equals what the CPU
+oracle produces for the same frame / frame pair / pose problem."""
+import numpy as np
+import pytest
+import oracle
+import plslam_b200 as pl
+from plslam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_frontend_batch_matches_oracle():
+    B = 4
+    frames = synth.synth_sequence(B, 640, 480, seed=4)
+    problems = [synth.synth_pose_problem(50 + k) for k in range(B)]
+    fe = pl.Frontend(640, 480, max_batch=B, lm_caps=(320, 88))
+    fe.set_pose_problems(problems)
+    out = fe.run(frames)
+    o = oracle.OrbOracle(1000, 1.2, 8, 20, 7)
+    feats = []
+    for b in range(B):
+        okps, odesc = o.extract(frames[b])
+        okl, oldesc, olf = oracle.line_extract(frames[b])
+        n, nl = out["n"][b], out["nl"][b]
+        assert n == len(okps) and out["kps"][b, :n].tobytes() == okps.tobytes() and np.array_equal(out["desc"][b, :n], odesc)
+        assert nl == len(okl)
+        eq = np.array([out["keylines"][b, i].tobytes() == okl[i].tobytes() for i in range(nl)])
+        assert eq.mean() > 0.99 and np.array_equal(out["ldesc"][b, :nl][eq], oldesc[eq])
+        feats.append((okps, odesc, out["ldesc"][b, :nl].copy(), eq.all()))
+    for b in range(B):
+        pk, pd, pld, _ = feats[(b - 1) % B]
+        ck, cd, cld, _ = feats[b]
+        pm = np.stack([pk["x"], pk["y"]], 1).astype(np.float32)
+        onm, om, _ = oracle.search_for_initialization(pk, pd, ck, cd, [0, 0, 640, 480], pm, 100, 0.9, True)
+        assert out["n_pt_matches"][b] == onm and np.array_equal(out["pt_matches"][b, :len(pk)], om)
+        onl, olm = oracle.search_double(pld, cld, 0.7)     # GPU descriptors on both sides: isolates the matcher
+        assert out["n_line_matches"][b] == onl and np.array_equal(out["line_matches"][b, :len(pld)], olm)
+        p = problems[b]
+        on, oT, opo, olo, oits = oracle.pose_optimization(0, p["Tcw0"], p["K"], p["pt_obs"], p["pt_inv_sigma2"], p["pt_Xw"],
+                                                          p["line_func"], p["line_Xw"])
+        for call in range(2):
+            T = out["poses"][call, b].reshape(4, 4)
+            assert np.linalg.norm(T[:3, 3] - oT[:3, 3]) <= 1e-4 * np.linalg.norm(oT[:3, 3])
+            assert out["inliers"][call, b] == on
+    # the device-resident path gives the same results as the host-buffer path
+    import torch
+    d = torch.from_numpy(frames).cuda()
+    fe.run_dev(d.data_ptr(), 640, 640 * 480, B, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    dev = fe.fetch(B)
+    for k in ("kps", "desc", "n", "keylines", "ldesc", "nl", "pt_matches", "n_pt_matches", "line_matches", "n_line_matches", "poses", "inliers"):
+        assert dev[k].tobytes() == out[k].tobytes(), k

@@ -35,9 +35,26 @@ N_PTS, N_LINES = 300, 80
 METRIC = "frames/sec (extract+match+pose-LM) 640x480"
 
 
+BASE_FRAMES = 64     # distinct host-generated frames; larger batches add per-replica sensor noise (deterministic)
+
+
 def make_inputs(B, seed):
+    """B synthetic frames + B pose problems.  The first min(B, 64) frames are a warped sequence (synth.synth_sequence);
+    frames beyond that repeat the sequence with fresh additive sensor noise (sigma 2 grey levels, PCG64 seeded), so every
+    frame of the batch has different content."""
     from plslam_b200 import synth
-    frames = synth.synth_sequence(B, W, H, seed=seed)
+    nb = min(B, BASE_FRAMES)
+    base = synth.synth_sequence(nb, W, H, seed=seed)
+    if B > nb:
+        rng = np.random.Generator(np.random.PCG64(77 + seed))
+        frames = np.empty((B, H, W), np.uint8)
+        frames[:nb] = base
+        for r in range(nb, B, nb):
+            k = min(nb, B - r)
+            noise = rng.normal(0, 2.0, (k, H, W)).astype(np.float32)
+            frames[r:r + k] = np.clip(np.rint(base[:k].astype(np.float32) + noise), 0, 255).astype(np.uint8)
+    else:
+        frames = base
     problems = [synth.synth_pose_problem(1000 * seed + k, n_points=N_PTS, n_lines=N_LINES) for k in range(B)]
     return frames, problems
 
@@ -177,8 +194,10 @@ def run_ours(args):
     fe = pl.Frontend(W, H, max_batch=B, orb=ORB, lines=LINES, lm_caps=(N_PTS + 20, N_LINES + 8))
     fe.set_pose_problems(problems)
     d_frames = torch.from_numpy(frames).cuda()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-NULL) stream: the C ABI treats NULL as "the handle's own stream"
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    assert sptr != 0
     poses = torch.empty((B, 16), dtype=torch.float32, device="cuda")
     gathered = torch.empty((world * B, 16), dtype=torch.float32, device="cuda") if world > 1 else None
 
@@ -295,7 +314,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=512, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=2048, help="frames per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":

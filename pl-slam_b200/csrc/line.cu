@@ -7,7 +7,7 @@
 //
 // Kernel map
 //   k_lsd_scale     7x7 sigma .75 Gaussian (8.8 fixed point) fused with the 0.8x INTER_LINEAR_EXACT resize, smem tiles
-//   k_lsd_grad      2x2 gradient -> (gx,gy) int16 pair per pixel (4 B instead of OpenCV's two doubles), per-frame max
+//   k_lsd_grad      2x2 gradient -> one 16-byte record per pixel (angle, cos, sin, squared magnitude), per-frame max
 //   k_lsd_hist/scan/scatter   stable counting sort of the defined pixels into 1024 magnitude bins (descending),
 //                   equal bins keep row-major order == OpenCV 4.13's seed order (pinned in the oracle tests)
 //   k_lsd_grow      region growing + rectangle fit + density refinement; inherently ordered (a pixel consumed by an
@@ -69,12 +69,6 @@ __device__ __forceinline__ float fast_atan2_deg_l(float y, float x) {  // cv::fa
   if (y < 0) a = __fsub_rn(360.f, a);
   return a;
 }
-__device__ __forceinline__ double grad_angle(short2 g) {  // angles(x,y): fastAtan2(float(gx), float(-gy)) * DEG_TO_RADS
-  return (double)fast_atan2_deg_l((float)g.x, (float)(-g.y)) * kDegToRads;
-}
-__device__ __forceinline__ double grad_norm(short2 g) {   // modgrad(x,y)
-  return sqrt((double)((int)g.x * g.x + (int)g.y * g.y) / 4.0);
-}
 __device__ __forceinline__ double warp_max_d(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -133,35 +127,47 @@ __global__ void __launch_bounds__(256) k_lsd_scale(LineParams P, const uint8_t* 
 }
 
 // ---------------------------------------------------------------------------------------------- K_B gradient
-constexpr short kNotDef = -32768;  // gx marker of the undefined right/bottom border
+// One 16-byte record per scaled pixel, everything region growing needs in ONE load:
+//   x = level-line angle in degrees (cv::fastAtan2(gx, -gy)); -1024 = NOTDEF (border or magnitude <= rho)
+//   y,z = cos/sin of float(angle_rad) rounded to fp32 (what region_grow adds to sumdx/sumdy)
+//   w = bit pattern of s = gx^2+gy^2 (modgrad = sqrt(s/4), recomputed in fp64 where the weights are used)
+constexpr float kNotDefDeg = -1024.f;
 __global__ void __launch_bounds__(256) k_lsd_grad(LineParams P, const uint8_t* __restrict__ scaled,
-                                                  short2* __restrict__ gxy, uint8_t* __restrict__ used, int* __restrict__ maxs) {
+                                                  float4* __restrict__ A, float2* __restrict__ seedcs, int* __restrict__ maxs) {
   const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
   const int f = blockIdx.z;
   int s = 0;
   if (x < P.sw && y < P.sh) {
     const uint8_t* S = scaled + (long long)f * P.npx;
-    short2 g = make_short2(kNotDef, 0);
+    float4 rec = make_float4(kNotDefDeg, 0.f, 0.f, __int_as_float(0));
+    float2 scs = make_float2(0.f, 0.f);
     if (x < P.sw - 1 && y < P.sh - 1) {
       int a = S[y * P.sw + x], b = S[y * P.sw + x + 1], c = S[(y + 1) * P.sw + x], d = S[(y + 1) * P.sw + x + 1];
       int DA = d - a, BC = b - c;
-      g = make_short2((short)(DA + BC), (short)(DA - BC));
-      s = (int)g.x * g.x + (int)g.y * g.y;
+      const int gx = DA + BC, gy = DA - BC;
+      s = gx * gx + gy * gy;
+      rec.w = __int_as_float(s);
+      if (s > P.s_th) {
+        const float deg = fast_atan2_deg_l((float)gx, (float)(-gy));
+        const double af = (double)(float)((double)deg * kDegToRads);
+        rec.x = deg; rec.y = (float)cos(af); rec.z = (float)sin(af);
+        const double ad = (double)deg * kDegToRads;      // a region SEEDED here starts from cos/sin of the fp64 angle
+        scs = make_float2((float)cos(ad), (float)sin(ad));
+      } else s = 0;
     }
-    gxy[(long long)f * P.npx + y * P.sw + x] = g;
-    used[(long long)f * P.npx + y * P.sw + x] = 0;
+    A[(long long)f * P.npx + y * P.sw + x] = rec;
+    seedcs[(long long)f * P.npx + y * P.sw + x] = scs;
   }
-  // max over defined pixels (modgrad is monotonic in s)
-  s = (s > P.s_th) ? s : 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s = max(s, __shfl_xor_sync(0xffffffffu, s, o));
   if ((threadIdx.x & 31) == 0 && s > 0) atomicMax(&maxs[f], s);
 }
-
-__device__ __forceinline__ int grad_bin(short2 g, double bin_coef) { return (int)(grad_norm(g) * bin_coef); }
+__device__ __forceinline__ double rec_norm(float4 r) { return sqrt((double)__float_as_int(r.w) / 4.0); }
+__device__ __forceinline__ double rec_angle(float4 r) { return (double)r.x * kDegToRads; }
+__device__ __forceinline__ int rec_bin(float4 r, double bin_coef) { return (int)(rec_norm(r) * bin_coef); }
 
 // K_C per-chunk histograms of the defined pixels (chunk = kChunkRows image rows)
-__global__ void __launch_bounds__(256) k_lsd_hist(LineParams P, const short2* __restrict__ gxy, const int* __restrict__ maxs,
+__global__ void __launch_bounds__(256) k_lsd_hist(LineParams P, const float4* __restrict__ A, const int* __restrict__ maxs,
                                                   unsigned short* __restrict__ counts /*[B][kBins][nchunk]*/) {
   __shared__ int hist[kBins];
   const int chunk = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
@@ -171,11 +177,11 @@ __global__ void __launch_bounds__(256) k_lsd_hist(LineParams P, const short2* __
   const double max_grad = ms > 0 ? sqrt((double)ms / 4.0) : -1.0;
   const double bin_coef = (max_grad > 0) ? (double)(kBins - 1) / max_grad : 0.0;
   const int y0 = chunk * kChunkRows, y1 = min(y0 + kChunkRows, P.sh - 1);
-  const short2* G = gxy + (long long)f * P.npx;
+  const float4* G = A + (long long)f * P.npx;
   for (int i = tid; i < (y1 - y0) * P.sw; i += 256) {
     int y = y0 + i / P.sw, x = i % P.sw;
-    short2 g = G[y * P.sw + x];
-    if (g.x != kNotDef && (int)g.x * g.x + (int)g.y * g.y > P.s_th) atomicAdd(&hist[grad_bin(g, bin_coef)], 1);
+    float4 g = G[y * P.sw + x];
+    if (g.x != kNotDefDeg) atomicAdd(&hist[rec_bin(g, bin_coef)], 1);
   }
   __syncthreads();
   for (int i = tid; i < kBins; i += 256) counts[((long long)f * kBins + i) * P.nchunk + chunk] = (unsigned short)hist[i];
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(kBins) k_lsd_scan(LineParams P, const unsigned
 }
 
 // K_E stable scatter: one warp per chunk walks its pixels in row-major order
-__global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const short2* __restrict__ gxy, const int* __restrict__ maxs,
+__global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const float4* __restrict__ A, const int* __restrict__ maxs,
                                                      const int* __restrict__ offsets, unsigned* __restrict__ order) {
   __shared__ unsigned short cnt[4][kBins];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const short2*
   const double max_grad = ms > 0 ? sqrt((double)ms / 4.0) : -1.0;
   const double bin_coef = (max_grad > 0) ? (double)(kBins - 1) / max_grad : 0.0;
   const int y0 = chunk * kChunkRows, y1 = min(y0 + kChunkRows, P.sh - 1);
-  const short2* G = gxy + (long long)f * P.npx;
+  const float4* G = A + (long long)f * P.npx;
   const int* off = offsets + (long long)f * kBins * P.nchunk;
   unsigned* O = order + (long long)f * P.npx;
   const int n = (y1 - y0) * P.sw;
@@ -229,9 +235,9 @@ __global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const short2*
     int i = i0 + lane, bin = -1, pix = 0;
     if (i < n) {
       int y = y0 + i / P.sw, x = i % P.sw;
-      pix = y * P.sw + x;
-      short2 g = G[pix];
-      if (g.x != kNotDef && (int)g.x * g.x + (int)g.y * g.y > P.s_th) bin = grad_bin(g, bin_coef);
+      pix = x | (y << 16);                       // packed (x, y): the grow kernel never divides
+      float4 g = G[y * P.sw + x];
+      if (g.x != kNotDefDeg) bin = rec_bin(g, bin_coef);
     }
     unsigned peers = __match_any_sync(0xffffffffu, bin);
     if (bin >= 0) O[off[bin * P.nchunk + chunk] + cnt[wid][bin] + __popc(peers & lt)] = (unsigned)pix;
@@ -243,9 +249,12 @@ __global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const short2*
 
 // ---------------------------------------------------------------------------------------------- K_F region growing
 struct GrowCtx {
-  const short2* G; uint8_t* U; unsigned* R; unsigned* ring;
+  const float4* G; const float2* S2; unsigned* U; unsigned* R; unsigned* ring;   // U: USED bitmap in shared memory
   int sw, sh, s_th;
 };
+__device__ __forceinline__ bool used_get(const GrowCtx& C, int idx) { return (C.U[idx >> 5] >> (idx & 31)) & 1u; }
+__device__ __forceinline__ void used_set1(const GrowCtx& C, int idx) { C.U[idx >> 5] |= 1u << (idx & 31); }      // one lane
+__device__ __forceinline__ void used_clear(const GrowCtx& C, int idx) { atomicAnd(&C.U[idx >> 5], ~(1u << (idx & 31))); }
 struct RectD { double x1, y1, x2, y2, width; };
 
 __device__ __forceinline__ double angle_diff_signed(double a, double b) {
@@ -261,51 +270,62 @@ __device__ __forceinline__ bool is_aligned(double a, double theta, double prec) 
   return n_theta <= prec;
 }
 
-// LineSegmentDetectorImpl::region_grow — exact visiting order; returns the region size, region in C.R[0..n)
-__device__ int region_grow(const GrowCtx& C, int seed, double prec, double& reg_angle, int lane) {
-  const short2 gs = C.G[seed];
-  reg_angle = grad_angle(gs);
-  float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
-  if (lane == 0) { C.R[0] = (unsigned)seed; C.ring[0] = (unsigned)seed; C.U[seed] = 1; }
+// LineSegmentDetectorImpl::region_grow — exact visiting order; returns the region size, region in C.R[0..n).
+// Three queue entries are expanded per step: lanes 0-8 / 9-17 / 18-26 fetch the 3x3 neighbourhoods of entries
+// i, i+1, i+2 (used flag + pixel record, two independent loads in flight per lane), then the candidates are committed
+// in the reference's order (queue order, then row-major inside the 3x3); a pixel added earlier in the same step
+// invalidates its duplicates in the later neighbourhoods, so the result equals the one-entry-at-a-time loop.
+__device__ int region_grow(const GrowCtx& C, unsigned seed, double prec, double& reg_angle, int lane) {
+  const int sidx = (int)(seed >> 16) * C.sw + (int)(seed & 0xffffu);
+  const float4 gs = __ldg(&C.G[sidx]);
+  const float2 s0 = __ldg(&C.S2[sidx]);
+  reg_angle = rec_angle(gs);
+  float sumdx = s0.x, sumdy = s0.y;
+  if (lane == 0) { C.R[0] = seed; C.ring[0] = seed; used_set1(C, sidx); }
   int cnt = 1;
   __syncwarp();
-  for (int i = 0; i < cnt; i++) {
-    const unsigned p = (cnt - i <= kRing) ? C.ring[i & (kRing - 1)] : C.R[i];
-    const int rx = (int)(p % (unsigned)C.sw), ry = (int)(p / (unsigned)C.sw);
+  const int grp = lane / 9, kk = lane - grp * 9;
+  const int ox = kk % 3 - 1, oy = kk / 3 - 1;
+  for (int i = 0; i < cnt;) {
+    const int m = min(3, cnt - i);
     bool valid = false;
-    int idx = 0;
-    double a = 0;
-    float cs = 0, sn = 0;
-    if (lane < 9) {
-      const int xx = rx - 1 + lane % 3, yy = ry - 1 + lane / 3;
+    int idx = -1;
+    unsigned pk = 0;
+    float4 rec = make_float4(kNotDefDeg, 0.f, 0.f, 0.f);
+    if (grp < m) {
+      const int qi = i + grp;
+      const unsigned p = (cnt - qi <= kRing) ? C.ring[qi & (kRing - 1)] : C.R[qi];
+      const int xx = (int)(p & 0xffffu) + ox, yy = (int)(p >> 16) + oy;
       if (xx >= 0 && yy >= 0 && xx < C.sw && yy < C.sh) {
         idx = yy * C.sw + xx;
-        if (C.U[idx] == 0) {
-          const short2 g = C.G[idx];
-          if (g.x != kNotDef && (int)g.x * g.x + (int)g.y * g.y > C.s_th) {
-            valid = true;
-            a = grad_angle(g);
-            const double af = (double)(float)a;   // cos(float(angle)), sin(float(angle)) in fp32
-            cs = (float)cos(af); sn = (float)sin(af);
-          }
+        pk = (unsigned)xx | ((unsigned)yy << 16);
+        if (!used_get(C, idx)) {
+          rec = __ldg(&C.G[idx]);
+          valid = (rec.x != kNotDefDeg);
         }
       }
     }
-    unsigned cand = __ballot_sync(0xffffffffu, valid);
-    while (cand) {
-      const int k = __ffs(cand) - 1;
-      cand &= cand - 1;
-      const double ak = __shfl_sync(0xffffffffu, a, k);
-      if (is_aligned(ak, reg_angle, prec)) {
-        const int ik = __shfl_sync(0xffffffffu, idx, k);
-        if (lane == 0) { C.U[ik] = 1; C.R[cnt] = (unsigned)ik; C.ring[cnt & (kRing - 1)] = (unsigned)ik; }
-        cnt++;
-        sumdx = __fadd_rn(sumdx, __shfl_sync(0xffffffffu, cs, k));
-        sumdy = __fadd_rn(sumdy, __shfl_sync(0xffffffffu, sn, k));
-        reg_angle = (double)fast_atan2_deg_l(sumdy, sumdx) * kDegToRads;
-      }
+    const double a = (double)rec.x * kDegToRads;
+    // Commit in order.  Every remaining candidate is tested against the CURRENT region angle at once; the first
+    // aligned one (lowest lane = reference order) is added, which changes the angle, and the candidates after it
+    // are tested again.  Candidates skipped before the committed lane were tested with the angle they would
+    // have seen in the sequential loop, so they are never revisited.
+    unsigned live = __ballot_sync(0xffffffffu, valid);
+    while (live) {
+      const unsigned al = __ballot_sync(0xffffffffu, valid && is_aligned(a, reg_angle, prec)) & live;
+      if (!al) break;
+      const int k = __ffs(al) - 1;
+      const unsigned pkk = __shfl_sync(0xffffffffu, pk, k);
+      if (lane == 0) { used_set1(C, (int)(pkk >> 16) * C.sw + (int)(pkk & 0xffffu)); C.R[cnt] = pkk; C.ring[cnt & (kRing - 1)] = pkk; }
+      cnt++;
+      sumdx = __fadd_rn(sumdx, __shfl_sync(0xffffffffu, rec.y, k));
+      sumdy = __fadd_rn(sumdy, __shfl_sync(0xffffffffu, rec.z, k));
+      reg_angle = (double)fast_atan2_deg_l(sumdy, sumdx) * kDegToRads;
+      live &= ~((2u << k) - 1u);                                   // everything up to k has been decided
+      live &= ~__ballot_sync(0xffffffffu, pk == pkk && idx >= 0);  // the same pixel in a later 3x3 is now USED
     }
     __syncwarp();
+    i += m;
   }
   return cnt;
 }
@@ -315,9 +335,10 @@ __device__ void region2rect(const GrowCtx& C, int n, double reg_angle, double pr
   double sx = 0, sy = 0, sw_ = 0;
   for (int i = lane; i < n; i += 32) {
     const unsigned p = C.R[i];
-    const double w = grad_norm(C.G[p]);
-    sx += (double)(int)(p % (unsigned)C.sw) * w;
-    sy += (double)(int)(p / (unsigned)C.sw) * w;
+    const int px = (int)(p & 0xffffu), py = (int)(p >> 16);
+    const double w = rec_norm(__ldg(&C.G[py * C.sw + px]));
+    sx += (double)px * w;
+    sy += (double)py * w;
     sw_ += w;
   }
   sx = warp_sum(sx); sy = warp_sum(sy); sw_ = warp_sum(sw_);
@@ -325,8 +346,9 @@ __device__ void region2rect(const GrowCtx& C, int n, double reg_angle, double pr
   double Ixx = 0, Iyy = 0, Ixy = 0;
   for (int i = lane; i < n; i += 32) {
     const unsigned p = C.R[i];
-    const double w = grad_norm(C.G[p]);
-    const double dx = (double)(int)(p % (unsigned)C.sw) - x, dy = (double)(int)(p / (unsigned)C.sw) - y;
+    const int px = (int)(p & 0xffffu), py = (int)(p >> 16);
+    const double w = rec_norm(__ldg(&C.G[py * C.sw + px]));
+    const double dx = (double)px - x, dy = (double)py - y;
     Ixx += dy * dy * w; Iyy += dx * dx * w; Ixy -= dx * dy * w;
   }
   Ixx = warp_sum(Ixx); Iyy = warp_sum(Iyy); Ixy = warp_sum(Ixy);
@@ -339,7 +361,7 @@ __device__ void region2rect(const GrowCtx& C, int n, double reg_angle, double pr
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
   for (int i = lane; i < n; i += 32) {
     const unsigned p = C.R[i];
-    const double rdx = (double)(int)(p % (unsigned)C.sw) - x, rdy = (double)(int)(p / (unsigned)C.sw) - y;
+    const double rdx = (double)(int)(p & 0xffffu) - x, rdy = (double)(int)(p >> 16) - y;
     const double l = rdx * dx + rdy * dy, w = -rdx * dy + rdy * dx;
     l_max = fmax(l_max, l); l_min = fmin(l_min, l);
     w_max = fmax(w_max, w); w_min = fmin(w_min, w);
@@ -359,16 +381,17 @@ __device__ bool refine(const GrowCtx& C, int& n, double reg_angle, double prec, 
   double density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
   if (density >= density_th) return true;
   const unsigned p0 = C.R[0];
-  const double xc = (double)(int)(p0 % (unsigned)C.sw), yc = (double)(int)(p0 / (unsigned)C.sw);
-  const double ang_c = grad_angle(C.G[p0]);
+  const double xc = (double)(int)(p0 & 0xffffu), yc = (double)(int)(p0 >> 16);
+  const double ang_c = rec_angle(__ldg(&C.G[(int)(p0 >> 16) * C.sw + (int)(p0 & 0xffffu)]));
   double sum = 0, s_sum = 0;
   int cnt = 0;
   for (int i = lane; i < n; i += 32) {
     const unsigned p = C.R[i];
-    C.U[p] = 0;
-    const double px = (double)(int)(p % (unsigned)C.sw), py = (double)(int)(p / (unsigned)C.sw);
+    const int pidx = (int)(p >> 16) * C.sw + (int)(p & 0xffffu);
+    used_clear(C, pidx);
+    const double px = (double)(int)(p & 0xffffu), py = (double)(int)(p >> 16);
     if (dist_d(xc, yc, px, py) < rec.width) {
-      const double ang_d = angle_diff_signed(grad_angle(C.G[p]), ang_c);
+      const double ang_d = angle_diff_signed(rec_angle(__ldg(&C.G[pidx])), ang_c);
       sum += ang_d; s_sum += ang_d * ang_d; ++cnt;
     }
   }
@@ -376,7 +399,7 @@ __device__ bool refine(const GrowCtx& C, int& n, double reg_angle, double prec, 
   __syncwarp();
   const double mean_angle = sum / (double)cnt;
   const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
-  n = region_grow(C, (int)p0, tau, reg_angle, lane);
+  n = region_grow(C, p0, tau, reg_angle, lane);
   if (n < 2) return false;
   region2rect(C, n, reg_angle, prec, rec, lane);
   density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
@@ -395,9 +418,9 @@ __device__ bool refine(const GrowCtx& C, int& n, double reg_angle, double prec, 
       bool keep = false;
       if (i < n) {
         p = C.R[i];
-        const double px = (double)(int)(p % (unsigned)C.sw), py = (double)(int)(p / (unsigned)C.sw);
+        const double px = (double)(int)(p & 0xffffu), py = (double)(int)(p >> 16);
         keep = !((px - xc) * (px - xc) + (py - yc) * (py - yc) > radSq);
-        if (!keep) C.U[p] = 0;
+        if (!keep) used_clear(C, (int)(p >> 16) * C.sw + (int)(p & 0xffffu));
       }
       const unsigned m = __ballot_sync(0xffffffffu, keep);
       __syncwarp();
@@ -413,14 +436,17 @@ __device__ bool refine(const GrowCtx& C, int& n, double reg_angle, double prec, 
   return true;
 }
 
-__global__ void __launch_bounds__(32) k_lsd_grow(LineParams P, const short2* __restrict__ gxy, uint8_t* __restrict__ used,
+__global__ void __launch_bounds__(32) k_lsd_grow(LineParams P, const float4* __restrict__ gxy, const float2* __restrict__ seedcs,
                                                  const unsigned* __restrict__ order, const int* __restrict__ ndef,
                                                  unsigned* __restrict__ reg, float4* __restrict__ segs,
                                                  int* __restrict__ nseg, int* __restrict__ overflow) {
   __shared__ unsigned ring[kRing];
+  extern __shared__ unsigned ubits[];            // USED bitmap of the scaled image: (npx+31)/32 words
   const int f = blockIdx.x, lane = threadIdx.x;
+  for (int i = lane; i < (P.npx + 31) / 32; i += 32) ubits[i] = 0u;
+  __syncwarp();
   GrowCtx C;
-  C.G = gxy + (long long)f * P.npx; C.U = used + (long long)f * P.npx; C.R = reg + (long long)f * P.npx;
+  C.G = gxy + (long long)f * P.npx; C.S2 = seedcs + (long long)f * P.npx; C.U = ubits; C.R = reg + (long long)f * P.npx;
   C.ring = ring; C.sw = P.sw; C.sh = P.sh; C.s_th = P.s_th;
   const unsigned* O = order + (long long)f * P.npx;
   float4* S = segs + (long long)f * P.seg_cap;
@@ -429,10 +455,11 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LineParams P, const short2* __r
   for (int i0 = 0; i0 < n; i0 += 32) {
     const int i = i0 + lane;
     const unsigned pix = (i < n) ? O[i] : 0u;
-    unsigned todo = __ballot_sync(0xffffffffu, i < n && C.U[pix] == 0);
+    const int pidx = (int)(pix >> 16) * P.sw + (int)(pix & 0xffffu);
+    unsigned todo = __ballot_sync(0xffffffffu, i < n && !used_get(C, pidx));
     while (todo) {
       const int k = __ffs(todo) - 1;
-      const int seed = (int)__shfl_sync(0xffffffffu, pix, k);
+      const unsigned seed = __shfl_sync(0xffffffffu, pix, k);
       double reg_angle;
       int cnt = region_grow(C, seed, P.prec, reg_angle, lane);
       if (cnt >= P.min_reg_size) {
@@ -447,7 +474,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LineParams P, const short2* __r
       }
       __syncwarp();
       // seeds later in this batch may have been consumed (or released by refine): re-read their flags
-      todo = __ballot_sync(0xffffffffu, i < n && lane > k && C.U[pix] == 0);
+      todo = __ballot_sync(0xffffffffu, i < n && lane > k && !used_get(C, pidx));
     }
   }
   if (lane == 0) { nseg[f] = min(ns, P.seg_cap); if (ns > P.seg_cap) atomicExch(overflow, 1); }
@@ -709,8 +736,10 @@ struct PLLine {
   PLLineConfig cfg;
   LineParams P;
   cudaStream_t stream = nullptr;
-  uint8_t *d_scaled = nullptr, *d_used = nullptr;
-  short2* d_gxy = nullptr;
+  uint8_t* d_scaled = nullptr;
+  float2* d_seedcs = nullptr;
+  size_t grow_smem = 0;
+  float4* d_gxy = nullptr;
   unsigned short* d_counts = nullptr;
   int *d_offsets = nullptr, *d_ndef = nullptr, *d_maxs = nullptr, *d_nseg = nullptr, *d_overflow = nullptr;
   unsigned *d_order = nullptr, *d_reg = nullptr;
@@ -731,7 +760,7 @@ static const unsigned char h_comb[64] = {0, 1, 0, 2, 0, 3, 0, 4, 0, 5, 0, 6, 1, 
 
 extern "C" void pl_line_destroy(PLLine* h) {
   if (!h) return;
-  cudaFree(h->d_scaled); cudaFree(h->d_used); cudaFree(h->d_gxy); cudaFree(h->d_counts); cudaFree(h->d_offsets);
+  cudaFree(h->d_scaled); cudaFree(h->d_seedcs); cudaFree(h->d_gxy); cudaFree(h->d_counts); cudaFree(h->d_offsets);
   cudaFree(h->d_ndef); cudaFree(h->d_maxs); cudaFree(h->d_nseg); cudaFree(h->d_overflow); cudaFree(h->d_order);
   cudaFree(h->d_reg); cudaFree(h->d_segs); cudaFree(h->d_dx); cudaFree(h->d_dy); cudaFree(h->d_img); cudaFree(h->d_kls);
   cudaFree(h->d_desc); cudaFree(h->d_lf); cudaFree(h->d_nl); cudaFree(h->d_mask);
@@ -766,7 +795,7 @@ extern "C" int pl_line_create(const PLLineConfig* cfg, PLLine** out) {
 #define LN_TRY(e) do { int _r = (e); if (_r) { pl_line_destroy(h); return _r; } } while (0)
 #define LN_CUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { set_error("%s -> %s", #e, cudaGetErrorString(_e)); pl_line_destroy(h); return PL_ERR_CUDA; } } while (0)
   LN_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  LN_TRY(dev_alloc(&h->d_scaled, npx * B)); LN_TRY(dev_alloc(&h->d_used, npx * B)); LN_TRY(dev_alloc(&h->d_gxy, npx * B));
+  LN_TRY(dev_alloc(&h->d_scaled, npx * B)); LN_TRY(dev_alloc(&h->d_seedcs, npx * B)); LN_TRY(dev_alloc(&h->d_gxy, npx * B));
   LN_TRY(dev_alloc(&h->d_counts, (size_t)kBins * P.nchunk * B)); LN_TRY(dev_alloc(&h->d_offsets, (size_t)kBins * P.nchunk * B));
   LN_TRY(dev_alloc(&h->d_ndef, B)); LN_TRY(dev_alloc(&h->d_maxs, B)); LN_TRY(dev_alloc(&h->d_nseg, B)); LN_TRY(dev_alloc(&h->d_overflow, 1));
   LN_TRY(dev_alloc(&h->d_order, npx * B)); LN_TRY(dev_alloc(&h->d_reg, npx * B)); LN_TRY(dev_alloc(&h->d_segs, (size_t)P.seg_cap * B));
@@ -783,6 +812,9 @@ extern "C" int pl_line_create(const PLLineConfig* cfg, PLLine** out) {
     LN_CUDA(cudaMemcpyToSymbol(c_comb, h_comb, sizeof(h_comb)));
   }
   LN_CUDA(cudaFuncSetAttribute(k_keylines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->key_smem));
+  h->grow_smem = (size_t)((P.npx + 31) / 32) * 4;
+  if (h->grow_smem > 200 * 1024) { set_error("frame too large for the shared-memory USED bitmap"); pl_line_destroy(h); return PL_ERR_ARG; }
+  LN_CUDA(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grow_smem));
   *out = h;
   return PL_OK;
 }
@@ -802,9 +834,9 @@ extern "C" int pl_line_grow_ms(PLLine* h, float* ms) {
   PL_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
   return PL_OK;
 }
-/* algorithmic bytes k_lsd_grow must move for one frame: per scaled pixel gradient pair (4) + used flag
- * read and written (2) + seed order entry (4) */
-extern "C" long long pl_line_grow_bytes_per_frame(const PLLine* h) { return h ? (long long)h->P.npx * 10 : 0; }
+/* algorithmic bytes k_lsd_grow must move for one frame: per scaled pixel: record (16) + seed cos/sin (8)
+ * + seed order entry (4); the USED map lives in shared memory */
+extern "C" long long pl_line_grow_bytes_per_frame(const PLLine* h) { return h ? (long long)h->P.npx * 28 : 0; }
 
 extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int stride, size_t frame_stride, int B,
                                          const uint8_t* mask, void* keylines, uint8_t* desc, double* linefunc, int* n,
@@ -816,7 +848,7 @@ extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int str
   PL_CUDA(cudaMemsetAsync(h->d_maxs, 0, sizeof(int) * B, st));
   k_lsd_scale<<<dim3((P.sw + 31) / 32, (P.sh + 31) / 32, B), 256, 0, st>>>(P, imgs, stride, (long long)frame_stride, h->d_scaled);
   PL_LAUNCH_CHECK();
-  k_lsd_grad<<<dim3((P.sw + 63) / 64, (P.sh + 3) / 4, B), 256, 0, st>>>(P, h->d_scaled, h->d_gxy, h->d_used, h->d_maxs);
+  k_lsd_grad<<<dim3((P.sw + 63) / 64, (P.sh + 3) / 4, B), 256, 0, st>>>(P, h->d_scaled, h->d_gxy, h->d_seedcs, h->d_maxs);
   PL_LAUNCH_CHECK();
   k_lsd_hist<<<dim3(P.nchunk, B), 256, 0, st>>>(P, h->d_gxy, h->d_maxs, h->d_counts);
   PL_LAUNCH_CHECK();
@@ -825,7 +857,7 @@ extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int str
   k_lsd_scatter<<<dim3((P.nchunk + 3) / 4, B), 128, 0, st>>>(P, h->d_gxy, h->d_maxs, h->d_offsets, h->d_order);
   PL_LAUNCH_CHECK();
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev0, st));
-  k_lsd_grow<<<B, 32, 0, st>>>(P, h->d_gxy, h->d_used, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow);
+  k_lsd_grow<<<B, 32, h->grow_smem, st>>>(P, h->d_gxy, h->d_seedcs, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow);
   PL_LAUNCH_CHECK();
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev1, st));
   k_keylines<<<B, 256, h->key_smem, st>>>(P, h->d_segs, h->d_nseg, mask, (PLKeyLineRec*)keylines, linefunc, n);
@@ -907,6 +939,9 @@ extern "C" int pl_line_debug_order(PLLine* h, int frame, unsigned* out, int cap)
   int n = 0;
   PL_CUDA(cudaStreamSynchronize(h->stream));
   PL_CUDA(cudaMemcpy(&n, h->d_ndef + frame, sizeof(int), cudaMemcpyDeviceToHost));
-  if (out && n) PL_CUDA(cudaMemcpy(out, h->d_order + (size_t)frame * h->P.npx, sizeof(unsigned) * std::min(n, cap), cudaMemcpyDeviceToHost));
+  if (out && n) {
+    PL_CUDA(cudaMemcpy(out, h->d_order + (size_t)frame * h->P.npx, sizeof(unsigned) * std::min(n, cap), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < std::min(n, cap); i++) out[i] = (out[i] >> 16) * (unsigned)h->P.sw + (out[i] & 0xffffu);   // packed (x,y) -> y*sw+x
+  }
   return n;
 }

@@ -224,6 +224,25 @@ int pl_frontend_grow_ms(PLFrontend* h, float* ms);
 long long pl_frontend_grow_bytes_per_frame(const PLFrontend* h);
 int pl_frontend_copy_poses_dev(PLFrontend* h, int B, float* dst, void* stream);
 
+/* ------------------------------------------------------------------ local bundle adjustment (points + lines)
+ * Optimizer::LocalBundleAdjustmentWithLine(pKF, pbStopFlag, pMap) (src/Optimizer.cc:1645-2100; with n_le == 0 it is
+ * Optimizer::LocalBundleAdjustment, :1308-1642) on the flattened local window that the reference gathers at
+ * :1649-1742.  Keyframes: local (free) and fixed ones (kf_fixed: lFixedCameras and mnId == 0); landmarks: map points
+ * and the two end points of every map line; edges in the reference's insertion order.  Host pointers; synchronous. */
+typedef struct PLBAProblem {
+  int n_kf;  const float* kf_Tcw /*[n_kf][16]*/; const uint8_t* kf_fixed; const float* kf_K /*[n_kf][4] fx fy cx cy*/;
+  float K_end[4];                 /* intrinsics the END-point line edges use: the current keyframe's (Optimizer.cc:1939-1942) */
+  int n_pt;  const float* pt_Xw /*[n_pt][3] MapPoint::GetWorldPos*/;
+  int n_ln;  const double* ln_Xw /*[n_ln][6] MapLine::mWorldPos*/;
+  int n_pe;  const int* pe_kf; const int* pe_pt; const float* pe_obs /*[n_pe][2] mvKeysUn.pt*/; const float* pe_inv_sigma2;
+  int n_le;  const int* le_kf; const int* le_ln; const double* le_func /*[n_le][3] mvKeyLineFunctions*/;
+} PLBAProblem;
+/* stop_flag_dev: device-visible int (e.g. mapped pinned memory) polled like g2o's forceStopFlag; NULL = never stop.
+ * Outputs: optimised keyframe poses, points, line end points; pe_erase / le_erase = observations the reference would
+ * erase (:2005-2043), le_erase_kf = the keyframe index the reference pairs with line observation i (its i/2 quirk). */
+int pl_local_ba(const PLBAProblem* p, const int* stop_flag_dev, float* kf_Tcw_out, float* pt_Xw_out, double* ln_Xw_out,
+                uint8_t* pe_erase, uint8_t* le_erase, int* le_erase_kf, int* iterations);
+
 #ifdef __cplusplus
 }
 #endif

@@ -312,3 +312,26 @@ def line_extract(img, mask=None, nfeatures=200, min_line_length=0.0, order_mode=
           _p(lf), cap)
     assert n >= 0
     return kl[:n].copy(), desc[:n].copy(), lf[:n].copy()
+
+
+# ---------------------------------------------------------------------------------------------- local BA
+def local_ba(p, stop_flag=None):
+    """p: dict from synth.synth_ba_problem.  Returns dict(kf_Tcw, pt_Xw, ln_Xw, pe_erase, le_erase, le_erase_kf, its)."""
+    n_kf, n_pt, n_ln, n_pe, n_le = len(p["kf_fixed"]), len(p["pt_Xw"]), len(p["ln_Xw"]), len(p["pe_kf"]), len(p["le_kf"])
+    out = dict(kf_Tcw=np.zeros((n_kf, 16), np.float32), pt_Xw=np.zeros((max(n_pt, 1), 3), np.float32),
+               ln_Xw=np.zeros((max(n_ln, 1), 6), np.float64), pe_erase=np.zeros(max(n_pe, 1), np.uint8),
+               le_erase=np.zeros(max(n_le, 1), np.uint8), le_erase_kf=np.zeros(max(n_le, 1), np.int32))
+    its = C.c_int(0)
+    sf = None if stop_flag is None else np.ascontiguousarray(stop_flag, np.int32)
+    f = lib().oracle_local_ba
+    f.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + \
+                 [C.c_int] + [C.c_void_p] * 3 + [C.c_void_p] * 8
+    a = {k: np.ascontiguousarray(v) for k, v in p.items() if isinstance(v, np.ndarray)}
+    f(n_kf, _p(a["kf_Tcw"]), _p(a["kf_fixed"]), _p(a["kf_K"]), _p(a["K_end"]), n_pt, _p(a["pt_Xw"]), n_ln, _p(a["ln_Xw"]), n_pe,
+      _p(a["pe_kf"]), _p(a["pe_pt"]), _p(a["pe_obs"]), _p(a["pe_inv_sigma2"]), n_le, _p(a["le_kf"]), _p(a["le_ln"]), _p(a["le_func"]),
+      _p(sf), _p(out["kf_Tcw"]), _p(out["pt_Xw"]), _p(out["ln_Xw"]), _p(out["pe_erase"]), _p(out["le_erase"]),
+      _p(out["le_erase_kf"]), C.byref(its))
+    out["its"] = its.value
+    for k, n in (("pt_Xw", n_pt), ("ln_Xw", n_ln), ("pe_erase", n_pe), ("le_erase", n_le), ("le_erase_kf", n_le)):
+        out[k] = out[k][:n]
+    return out

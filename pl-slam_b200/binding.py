@@ -491,3 +491,36 @@ class Frontend:
 
     def copy_poses_dev(self, B, dst_ptr, stream=None):
         check(lib().pl_frontend_copy_poses_dev(self._h, B, dst_ptr, stream))
+
+
+# ---------------------------------------------------------------------------------------------- local BA
+class PLBAProblem(C.Structure):
+    _fields_ = [("n_kf", C.c_int), ("kf_Tcw", vp), ("kf_fixed", vp), ("kf_K", vp), ("K_end", C.c_float * 4),
+                ("n_pt", C.c_int), ("pt_Xw", vp), ("n_ln", C.c_int), ("ln_Xw", vp),
+                ("n_pe", C.c_int), ("pe_kf", vp), ("pe_pt", vp), ("pe_obs", vp), ("pe_inv_sigma2", vp),
+                ("n_le", C.c_int), ("le_kf", vp), ("le_ln", vp), ("le_func", vp)]
+
+
+def LocalBundleAdjustmentWithLine(p, stop_flag_dev=None):
+    """Optimizer::LocalBundleAdjustmentWithLine on a flattened local window (dict as made by synth.synth_ba_problem).
+    Returns dict(kf_Tcw, pt_Xw, ln_Xw, pe_erase, le_erase, le_erase_kf, its)."""
+    a = {k: np.ascontiguousarray(v) for k, v in p.items() if isinstance(v, np.ndarray)}
+    n_kf, n_pt, n_ln, n_pe, n_le = len(a["kf_fixed"]), len(a["pt_Xw"]), len(a["ln_Xw"]), len(a["pe_kf"]), len(a["le_kf"])
+    P = PLBAProblem(n_kf, _p(a["kf_Tcw"]), _p(a["kf_fixed"]), _p(a["kf_K"]), (C.c_float * 4)(*[float(v) for v in a["K_end"]]),
+                    n_pt, _p(a["pt_Xw"]), n_ln, _p(a["ln_Xw"]), n_pe, _p(a["pe_kf"]), _p(a["pe_pt"]), _p(a["pe_obs"]),
+                    _p(a["pe_inv_sigma2"]), n_le, _p(a["le_kf"]), _p(a["le_ln"]), _p(a["le_func"]))
+    out = dict(kf_Tcw=np.zeros((n_kf, 16), np.float32), pt_Xw=np.zeros((max(n_pt, 1), 3), np.float32),
+               ln_Xw=np.zeros((max(n_ln, 1), 6), np.float64), pe_erase=np.zeros(max(n_pe, 1), np.uint8),
+               le_erase=np.zeros(max(n_le, 1), np.uint8), le_erase_kf=np.zeros(max(n_le, 1), np.int32))
+    its = C.c_int(0)
+    f = lib().pl_local_ba
+    f.argtypes = [C.POINTER(PLBAProblem), vp, vp, vp, vp, vp, vp, vp, vp]
+    check(f(C.byref(P), stop_flag_dev, _p(out["kf_Tcw"]), _p(out["pt_Xw"]), _p(out["ln_Xw"]), _p(out["pe_erase"]),
+            _p(out["le_erase"]), _p(out["le_erase_kf"]), C.byref(its)))
+    out["its"] = its.value
+    for k, n in (("pt_Xw", n_pt), ("ln_Xw", n_ln), ("pe_erase", n_pe), ("le_erase", n_le), ("le_erase_kf", n_le)):
+        out[k] = out[k][:n]
+    return out
+
+
+Optimizer.LocalBundleAdjustmentWithLine = staticmethod(LocalBundleAdjustmentWithLine)

@@ -126,3 +126,75 @@ def synth_pose_problem(seed=3, n_points=300, n_lines=80, outlier_frac=0.10, K=TU
                 pt_obs=obs.astype(np.float32), pt_inv_sigma2=inv_sigma2, pt_Xw=Xw.astype(np.float32),
                 line_func=np.ascontiguousarray(l, np.float64), line_Xw=np.ascontiguousarray(lw, np.float64),
                 pt_is_outlier=bad, line_is_outlier=lbad)
+
+
+# ---------------------------------------------------------------------------------------------- local BA window
+def synth_ba_problem(seed=4, n_free=20, n_fixed=40, n_pt=3000, n_ln=400, obs_pt=5, obs_ln=4, K=TUM1_K, w=640, h=480,
+                     noise_px=1.0, outlier_frac=0.03, pert_t=0.01, pert_deg=0.3, pert_X=0.02):
+    """KITTI/TUM-shaped local-BA window: cameras on a smooth path in front of a scene,
+    points with ~obs_pt and lines with ~obs_ln observations, noisy observations, a few gross outliers, perturbed
+    initial estimates.  Keyframe 0 is fixed (mnId == 0) together with the `n_fixed` covisible-but-not-local ones."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    fx, fy, cx, cy = K
+    n_kf = n_free + n_fixed
+    Ts = []
+    for k in range(n_kf):
+        s = k / max(n_kf - 1, 1)
+        R = _rot(0.02 * np.sin(3 * s) + rng.normal(0, 0.01), 0.25 * (s - 0.5) + rng.normal(0, 0.01), rng.normal(0, 0.01))
+        C = np.array([3.0 * (s - 0.5), 0.1 * np.sin(5 * s), 0.3 * s]) + rng.normal(0, 0.02, 3)
+        T = np.eye(4); T[:3, :3] = R; T[:3, 3] = -R @ C
+        Ts.append(T)
+    Ts = np.array(Ts)
+    order = rng.permutation(n_kf)
+    Ts = Ts[order]
+    fixed = np.zeros(n_kf, np.uint8); fixed[n_free:] = 1; fixed[0] = 1
+
+    def project(T, X):
+        Xc = X @ T[:3, :3].T + T[:3, 3]
+        return np.stack([Xc[:, 0] / Xc[:, 2] * fx + cx, Xc[:, 1] / Xc[:, 2] * fy + cy], 1), Xc[:, 2]
+
+    Xw = np.stack([rng.uniform(-4, 4, n_pt), rng.uniform(-2, 2, n_pt), rng.uniform(3, 9, n_pt)], 1)
+    pe_kf, pe_pt, pe_obs, pe_w = [], [], [], []
+    for i in range(n_pt):
+        cand = rng.permutation(n_kf)
+        got = 0
+        for k in cand:
+            uv, z = project(Ts[k], Xw[i:i + 1])
+            if z[0] > 0.5 and 0 < uv[0, 0] < w and 0 < uv[0, 1] < h:
+                octv = rng.integers(0, 8)
+                o = uv[0] + rng.normal(0, noise_px, 2) * 1.2 ** octv
+                if rng.random() < outlier_frac:
+                    o = o + rng.uniform(-30, 30, 2)
+                pe_kf.append(k); pe_pt.append(i); pe_obs.append(o); pe_w.append(1.0 / (np.float32(1.2) ** octv) ** 2)
+                got += 1
+                if got >= max(2, rng.poisson(obs_pt)):
+                    break
+    A = np.stack([rng.uniform(-4, 4, n_ln), rng.uniform(-2, 2, n_ln), rng.uniform(3, 9, n_ln)], 1)
+    Bp = A + rng.uniform(-0.8, 0.8, (n_ln, 3))
+    Lw = np.concatenate([A, Bp], 1)
+    le_kf, le_ln, le_f = [], [], []
+    for i in range(n_ln):
+        got = 0
+        for k in rng.permutation(n_kf):
+            ua, za = project(Ts[k], A[i:i + 1]); ub, zb = project(Ts[k], Bp[i:i + 1])
+            if za[0] > 0.5 and zb[0] > 0.5 and 0 < ua[0, 0] < w and 0 < ua[0, 1] < h and 0 < ub[0, 0] < w and 0 < ub[0, 1] < h:
+                pa = ua[0] + rng.normal(0, noise_px, 2); pb = ub[0] + rng.normal(0, noise_px, 2)
+                if rng.random() < outlier_frac:
+                    pa = pa + rng.uniform(-25, 25, 2)
+                l = np.cross(np.r_[pa, 1.0], np.r_[pb, 1.0]); l /= np.hypot(l[0], l[1])
+                le_kf.append(k); le_ln.append(i); le_f.append(l)
+                got += 1
+                if got >= max(3, rng.poisson(obs_ln)):
+                    break
+    T0 = Ts.copy()
+    for k in range(n_kf):
+        if not fixed[k]:
+            dR = _rot(*np.deg2rad(rng.uniform(-pert_deg, pert_deg, 3)))
+            T0[k, :3, :3] = dR @ Ts[k, :3, :3]; T0[k, :3, 3] = dR @ Ts[k, :3, 3] + rng.uniform(-pert_t, pert_t, 3)
+    return dict(kf_Tcw=T0.astype(np.float32).reshape(n_kf, 16), kf_Tcw_true=Ts, kf_fixed=fixed,
+                kf_K=np.tile(np.array(K, np.float32), (n_kf, 1)), K_end=np.array(K, np.float32),
+                pt_Xw=(Xw + rng.normal(0, pert_X, Xw.shape)).astype(np.float32), pt_Xw_true=Xw,
+                ln_Xw=np.ascontiguousarray(Lw + rng.normal(0, pert_X, Lw.shape)), ln_Xw_true=Lw,
+                pe_kf=np.array(pe_kf, np.int32), pe_pt=np.array(pe_pt, np.int32), pe_obs=np.array(pe_obs, np.float32).reshape(-1, 2),
+                pe_inv_sigma2=np.array(pe_w, np.float32), le_kf=np.array(le_kf, np.int32), le_ln=np.array(le_ln, np.int32),
+                le_func=np.ascontiguousarray(np.array(le_f, np.float64).reshape(-1, 3)))

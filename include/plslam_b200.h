@@ -243,6 +243,25 @@ typedef struct PLBAProblem {
 int pl_local_ba(const PLBAProblem* p, const int* stop_flag_dev, float* kf_Tcw_out, float* pt_Xw_out, double* ln_Xw_out,
                 uint8_t* pe_erase, uint8_t* le_erase, int* le_erase_kf, int* iterations);
 
+/* ------------------------------------------------------------------ line matching by projection
+ * Frame::AssignFeaturesToGridForLine (Frame.cc:296-320): CSR of mGridForLine (cell = ix*48+iy); returns #items. */
+int pl_frame_assign_grid_lines(const void* keylines_un /*68 B records*/, int n, const float* bounds, int* cell_start /*[3073]*/,
+                               int* cell_items, int cap_items);
+/* LSDmatcher::SearchByProjection(CurrentFrame, LastFrame, th) (LSDmatcher.cpp:72-176).  Per last-frame line i:
+ * last_valid = (mvpMapLines[i] && !mvbLineOutlier[i] && CurrentFrame.isInFrustum(pML, 0.5)), last_proj =
+ * {mTrackProjX1, Y1, X2, Y2}, last_desc = GetDescriptor(), last_length = LastFrame.mvKeylinesUn[i].lineLength.
+ * (The frustum test itself is Frame glue)  cur_match[n_cur]: last index, -1, or -2 pre-assigned. */
+int pl_lsd_search_by_projection_last(const void* keylines_cur, const double* linefunc_cur, const uint8_t* desc_cur, int n_cur,
+                                     const float* bounds, int n_last, const uint8_t* last_valid, const float* last_proj,
+                                     const uint8_t* last_desc, const float* last_length, float th,
+                                     const uint8_t* cur_preassigned, int* cur_match);
+/* LSDmatcher::SearchByProjection(F, vpMapLines, th) (LSDmatcher.cpp:221-338): in_view = (mbTrackInView && !isBad()),
+ * proj = {mTrackProjX1,Y1,X2,Y2}, view_cos = mTrackViewCos, ml_desc = GetDescriptor(). */
+int pl_lsd_search_by_projection_lines(const void* keylines, const double* linefunc, const uint8_t* desc, int n,
+                                      const float* bounds, int n_ml, const uint8_t* in_view, const float* proj,
+                                      const float* view_cos, const uint8_t* ml_desc, float th, float nnratio,
+                                      const uint8_t* preassigned, int* match);
+
 #ifdef __cplusplus
 }
 #endif

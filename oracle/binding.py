@@ -335,3 +335,47 @@ def local_ba(p, stop_flag=None):
     for k, n in (("pt_Xw", n_pt), ("ln_Xw", n_ln), ("pe_erase", n_pe), ("le_erase", n_le), ("le_erase_kf", n_le)):
         out[k] = out[k][:n]
     return out
+
+
+# ---------------------------------------------------------------------------------------------- line matching by projection
+def _compact_kl(kl68):
+    """68-byte KeyLine records -> the 7-field flat records oracle_match.cpp reads."""
+    out = np.zeros(len(kl68), KL_DTYPE)
+    for f in ("lineLength", "angle", "octave"):
+        out[f] = kl68[f]
+    out["startX"], out["startY"], out["endX"], out["endY"] = kl68["startPointX"], kl68["startPointY"], kl68["endPointX"], kl68["endPointY"]
+    return out
+
+
+def assign_grid_lines(kl68, bounds):
+    k = _compact_kl(kl68); b = np.asarray(bounds, np.float32)
+    cap = max(len(k), 1) * 120
+    start = np.zeros(64 * 48 + 1, np.int32); items = np.zeros(cap, np.int32)
+    f = lib().oracle_assign_grid_lines
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    n = f(_p(k), len(k), _p(b), _p(start), _p(items), cap)
+    return start, items[:n]
+
+
+def line_search_by_projection_last(kl68, lfunc, desc, bounds, last_valid, proj, last_desc, last_length, th, preassigned=None):
+    k = _compact_kl(kl68); m = np.zeros(max(len(k), 1), np.int32)
+    f = lib().oracle_line_search_by_projection_last
+    f.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_float, C.c_void_p, C.c_void_p]
+    a = [np.ascontiguousarray(lfunc, np.float64), np.ascontiguousarray(desc, np.uint8), np.asarray(bounds, np.float32),
+         np.ascontiguousarray(last_valid, np.uint8), np.ascontiguousarray(proj, np.float32), np.ascontiguousarray(last_desc, np.uint8),
+         np.ascontiguousarray(last_length, np.float32)]
+    pre = None if preassigned is None else np.ascontiguousarray(preassigned, np.uint8)
+    nm = f(_p(k), _p(a[0]), _p(a[1]), len(k), _p(a[2]), len(a[3]), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6]), th, _p(pre), _p(m))
+    return nm, m[:len(k)]
+
+
+def line_search_by_projection_lines(kl68, lfunc, desc, bounds, in_view, proj, view_cos, ml_desc, th, nnratio=0.7, preassigned=None):
+    k = _compact_kl(kl68); m = np.zeros(max(len(k), 1), np.int32)
+    f = lib().oracle_line_search_by_projection_lines
+    f.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    a = [np.ascontiguousarray(lfunc, np.float64), np.ascontiguousarray(desc, np.uint8), np.asarray(bounds, np.float32),
+         np.ascontiguousarray(in_view, np.uint8), np.ascontiguousarray(proj, np.float32), np.ascontiguousarray(view_cos, np.float32),
+         np.ascontiguousarray(ml_desc, np.uint8)]
+    pre = None if preassigned is None else np.ascontiguousarray(preassigned, np.uint8)
+    nm = f(_p(k), _p(a[0]), _p(a[1]), len(k), _p(a[2]), len(a[3]), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6]), th, nnratio, _p(pre), _p(m))
+    return nm, m[:len(k)]

@@ -524,3 +524,44 @@ def LocalBundleAdjustmentWithLine(p, stop_flag_dev=None):
 
 
 Optimizer.LocalBundleAdjustmentWithLine = staticmethod(LocalBundleAdjustmentWithLine)
+
+
+# ---------------------------------------------------------------------------------------------- line matching by projection
+def frame_assign_grid_lines(keylines_un, bounds):
+    """Frame::AssignFeaturesToGridForLine (reference src/Frame.cc:296-320) -> CSR (cell_start[3073], cell_items)."""
+    kl = np.ascontiguousarray(keylines_un); b = _f32(bounds)
+    cap = max(len(kl), 1) * 120
+    start = np.zeros(64 * 48 + 1, np.int32); items = np.zeros(cap, np.int32)
+    f = lib().pl_frame_assign_grid_lines
+    f.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int]
+    n = check(f(_p(kl), len(kl), _p(b), _p(start), _p(items), cap))
+    return start, items[:n]
+
+
+def _lsd_search_last(self, keylines_cur, linefunc_cur, desc_cur, bounds, last_valid, last_proj, last_desc, last_length, th, preassigned=None):
+    """LSDmatcher::SearchByProjection(CurrentFrame, LastFrame, th)."""
+    kl = np.ascontiguousarray(keylines_cur)
+    a = [np.ascontiguousarray(linefunc_cur, np.float64), _u8(desc_cur), _f32(bounds), _u8(last_valid), _f32(last_proj), _u8(last_desc), _f32(last_length)]
+    pre = None if preassigned is None else _u8(preassigned)
+    m = np.zeros(max(len(kl), 1), np.int32)
+    f = lib().pl_lsd_search_by_projection_last
+    f.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, C.c_float, vp, vp]
+    nm = check(f(_p(kl), _p(a[0]), _p(a[1]), len(kl), _p(a[2]), len(a[3]), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6]), float(th), _p(pre), _p(m)))
+    return nm, m[:len(kl)]
+
+
+def _lsd_search_lines(self, keylines, linefunc, desc, bounds, in_view, proj, view_cos, ml_desc, th=3, preassigned=None):
+    """LSDmatcher::SearchByProjection(F, vpMapLines, th)."""
+    kl = np.ascontiguousarray(keylines)
+    a = [np.ascontiguousarray(linefunc, np.float64), _u8(desc), _f32(bounds), _u8(in_view), _f32(proj), _f32(view_cos), _u8(ml_desc)]
+    pre = None if preassigned is None else _u8(preassigned)
+    m = np.zeros(max(len(kl), 1), np.int32)
+    f = lib().pl_lsd_search_by_projection_lines
+    f.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp]
+    nm = check(f(_p(kl), _p(a[0]), _p(a[1]), len(kl), _p(a[2]), len(a[3]), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6]), float(th),
+                 self.mfNNratio, _p(pre), _p(m)))
+    return nm, m[:len(kl)]
+
+
+LSDmatcher.SearchByProjectionLast = _lsd_search_last
+LSDmatcher.SearchByProjectionLines = _lsd_search_lines

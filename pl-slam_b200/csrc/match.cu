@@ -509,6 +509,181 @@ __global__ void __launch_bounds__(128) k_search_double(const uint8_t* d1, const 
   if (tid == 0) nmatches[b] = total;
 }
 
+
+// ------------------------------------------------------------------------------------------------ a17 lines
+struct KeyLine68 {  // cv::line_descriptor::KeyLine (68 B)
+  float angle; int class_id; int octave; float ptx, pty; float response; float size;
+  float startPointX, startPointY, endPointX, endPointY, sPointInOctaveX, sPointInOctaveY, ePointInOctaveX, ePointInOctaveY;
+  float lineLength; int numOfPixels;
+};
+constexpr int kMaxPath = GC + GR + 2;
+
+// Frame::AssignFeaturesToGridForLine (Frame.cc:296-320 + lineIterator.cpp): CSR of mGridForLine in global scratch.
+// start: [NCELL+1] ints, items: [n*kMaxPath] ushort, path scratch: [n][kMaxPath] ushort.
+__device__ void build_line_grid(const KeyLine68* kl, int n, const GridP& g, int* start, unsigned short* items,
+                                unsigned short* path, unsigned short* plen, int lane) {
+  for (int i = lane; i <= NCELL; i += 32) start[i] = 0;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {   // each lane walks its own line (Bresenham in fp64 exactly as the reference)
+    double x1 = (double)__fmul_rn(kl[i].startPointX, g.invW), y1 = (double)__fmul_rn(kl[i].startPointY, g.invH);
+    double x2 = (double)__fmul_rn(kl[i].endPointX, g.invW), y2 = (double)__fmul_rn(kl[i].endPointY, g.invH);
+    const bool steep = fabs(y2 - y1) > fabs(x2 - x1);
+    if (steep) { double t = x1; x1 = y1; y1 = t; t = x2; x2 = y2; y2 = t; }
+    if (x1 > x2) { double t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
+    const double dx = x2 - x1, dy = fabs(y2 - y1);
+    double error = dx / 2.0;
+    const int ystep = (y1 < y2) ? 1 : -1;
+    int x = (int)x1, y = (int)y1;
+    const int maxX = (int)x2;
+    int len = 0;
+    while (x <= maxX) {
+      const int px = steep ? y : x, py = steep ? x : y;
+      if (px >= 0 && px < GC && py >= 0 && py < GR && len < kMaxPath) { path[i * kMaxPath + len++] = (unsigned short)(px * GR + py); atomicAdd(&start[px * GR + py + 1], 1); }
+      error -= dy;
+      if (error < 0) { y += ystep; error += dx; }
+      x++;
+    }
+    plen[i] = (unsigned short)len;
+  }
+  __syncwarp();
+  int run = 0;   // inclusive scan over cells (start[c+1] holds count of cell c)
+  for (int c0 = 0; c0 < NCELL; c0 += 32) {
+    int v = start[c0 + lane + 1], incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    __syncwarp();
+    start[c0 + lane + 1] = run + incl;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncwarp();
+  // fill in ascending line index: per line, its cells are distinct -> lanes never collide; "fill" cursor = items' tail
+  // kept in the ushort array `plen`-independent scratch: reuse path of processed lines is not possible, so use a
+  // per-cell cursor stored in the items array header region is avoided: cursor lives in shared memory of the caller.
+}
+
+struct LineGridS { int* start; unsigned short* items; unsigned short* path; unsigned short* plen; unsigned short* cursor; };
+
+__device__ void fill_line_grid(const LineGridS& L, int n, int lane) {
+  for (int i = lane; i < NCELL; i += 32) L.cursor[i] = 0;
+  __syncwarp();
+  for (int i = 0; i < n; i++) {
+    const int len = L.plen[i];
+    for (int s = lane; s < len; s += 32) {
+      const int c = L.path[i * kMaxPath + s];
+      L.items[L.start[c] + L.cursor[c]] = (unsigned short)i;
+      L.cursor[c]++;
+    }
+    __syncwarp();
+  }
+}
+
+// Frame::GetFeaturesInAreaForLine: marks first[id] = traversal order key of the first accepted occurrence of line id
+__device__ void line_candidates(const KeyLine68* kl, const double* lfunc, const LineGridS& L, const GridP& g, float x1, float y1,
+                                float x2, float y2, float r, float TH, int* first, int n, int lane) {
+  for (int i = lane; i < n; i += 32) first[i] = 0x7fffffff;
+  __syncwarp();
+  const float xs[3] = {x1, (float)((double)__fadd_rn(x1, x2) / 2.0), x2};
+  const float ys[3] = {y1, (float)((double)__fadd_rn(y1, y2) / 2.0), y2};
+  float d1x = __fsub_rn(x1, x2), d1y = __fsub_rn(y1, y2);
+  const float n1 = sqrtf(__fadd_rn(__fmul_rn(d1x, d1x), __fmul_rn(d1y, d1y)));
+  d1x = __fdiv_rn(d1x, n1); d1y = __fdiv_rn(d1y, n1);
+  int base = 0;
+  for (int i = 0; i < 3; i++) {
+    Window w = make_window(g, xs[i], ys[i], r);
+    if (!w.ok) continue;
+    const int ncy = w.y1 - w.y0 + 1, ncell = (w.x1 - w.x0 + 1) * ncy;
+    for (int c = lane; c < ncell; c += 32) {
+      const int ix = w.x0 + c / ncy, iy = w.y0 + c % ncy;
+      const int cb = L.start[ix * GR + iy], ce = L.start[ix * GR + iy + 1];
+      for (int j = cb; j < ce; j++) {
+        const int id = L.items[j];
+        const KeyLine68& k = kl[id];
+        float d2x = __fsub_rn(k.startPointX, k.endPointX), d2y = __fsub_rn(k.startPointY, k.endPointY);
+        const float n2 = sqrtf(__fadd_rn(__fmul_rn(d2x, d2x), __fmul_rn(d2y, d2y)));
+        d2x = __fdiv_rn(d2x, n2); d2y = __fdiv_rn(d2y, n2);
+        const float cosSita = fabsf(__fadd_rn(__fmul_rn(d1x, d2x), __fmul_rn(d1y, d2y)));
+        if (cosSita < TH) continue;
+        const double* F = lfunc + 3 * id;
+        const float dist = (float)(F[0] * (double)xs[i] + F[1] * (double)ys[i] + F[2]);
+        if (fabsf(dist) < r) atomicMin(&first[id], base + c * 1024 + (j - cb));   // order key: probe, cell rank, slot
+      }
+    }
+    base += 4000000;   // > 3072 cells * 1024
+    __syncwarp();
+  }
+  __syncwarp();
+}
+
+struct LineSearchArgs {
+  const KeyLine68* kl; const double* lfunc; const uint8_t* desc; const int* n; int cap;   // current frame [B][cap]
+  const float* bounds;
+  const int* n_q; int cap_q; const uint8_t* q_valid; const float* q_proj; const uint8_t* q_desc;
+  const float* q_length;        // variant 0: LastFrame.mvKeylinesUn[i].lineLength
+  const float* q_view_cos;      // variant 1: mTrackViewCos
+  float th, nnratio; int variant;
+  const uint8_t* preassigned; int* match; int* nmatches;
+  int* g_start; unsigned short* g_items; unsigned short* g_path; unsigned short* g_plen; int* g_first;   // scratch per frame
+};
+
+__global__ void __launch_bounds__(32) k_line_search(LineSearchArgs A) {
+  __shared__ unsigned short cursor[NCELL];
+  const int b = blockIdx.x, lane = threadIdx.x;
+  GridP g = make_grid(A.bounds);
+  const KeyLine68* kl = A.kl + (long long)b * A.cap;
+  const double* lf = A.lfunc + (long long)b * A.cap * 3;
+  const uint8_t* d = A.desc + (long long)b * A.cap * 32;
+  const int N = min(A.n[b], A.cap), NQ = min(A.n_q[b], A.cap_q);
+  int* match = A.match + (long long)b * A.cap;
+  LineGridS L;
+  L.start = A.g_start + (long long)b * (NCELL + 1); L.items = A.g_items + (long long)b * A.cap * kMaxPath;
+  L.path = A.g_path + (long long)b * A.cap * kMaxPath; L.plen = A.g_plen + (long long)b * A.cap; L.cursor = cursor;
+  int* first = A.g_first + (long long)b * A.cap;
+  build_line_grid(kl, N, g, L.start, L.items, L.path, L.plen, lane);
+  fill_line_grid(L, N, lane);
+  for (int i = lane; i < N; i += 32) match[i] = (A.preassigned && A.preassigned[(long long)b * A.cap + i]) ? -2 : -1;
+  __syncwarp();
+  int nmatches = 0;
+  const long long qb = (long long)b * A.cap_q;
+  const bool bFactor = A.th != 1.0f;
+  for (int q = 0; q < NQ; q++) {
+    if (!A.q_valid[qb + q]) continue;
+    const float* p = A.q_proj + (qb + q) * 4;
+    float r, TH;
+    if (A.variant == 0) { r = A.th; TH = 0.96f; }
+    else { r = ((double)A.q_view_cos[qb + q] > 0.998) ? 5.0f : 8.0f; if (bFactor) r = __fmul_rn(r, A.th); TH = 0.998f; }
+    line_candidates(kl, lf, L, g, p[0], p[1], p[2], p[3], r, TH, first, N, lane);
+    // candidates in first-occurrence order; top-2 by (distance, order)
+    unsigned long long k1 = KEY_NONE, k2 = KEY_NONE;
+    for (int id = lane; id < N; id += 32) {
+      const int ord = first[id];
+      if (ord == 0x7fffffff) continue;
+      if (match[id] != -1) continue;
+      const int dist = hamming256(A.q_desc + (qb + q) * 32, d + 32 * id);
+      if (A.variant == 0) {
+        const float a = A.q_length[qb + q], c = kl[id].lineLength;
+        const float mx = fmaxf(a, c), mn = fminf(a, c);
+        if ((double)__fdiv_rn(mn, mx) < 0.75) continue;
+      }
+      const unsigned long long k = ((unsigned long long)dist << 52) | ((unsigned long long)(unsigned)ord << 20) | (unsigned long long)id;
+      if (k < k1) { k2 = k1; k1 = k; } else if (k < k2) k2 = k;
+    }
+    const unsigned long long best = warp_min_u64(k1);
+    const unsigned long long second = warp_min_u64(k1 == best ? k2 : k1);
+    if (best == KEY_NONE) continue;
+    const int bestDist = key_dist(best), bestIdx = key_idx(best);
+    if (bestDist <= 80) {
+      if (A.variant == 1 && second != KEY_NONE) {
+        const int bestDist2 = key_dist(second);
+        if (kl[bestIdx].octave == kl[key_idx(second)].octave && (float)bestDist > __fmul_rn(A.nnratio, (float)bestDist2)) continue;
+      }
+      nmatches++;
+      if (lane == 0) match[bestIdx] = q;
+      __syncwarp();
+    }
+  }
+  if (lane == 0) A.nmatches[b] = nmatches;
+}
+
 }  // namespace pl
 
 // ================================================================================================ C ABI
@@ -727,4 +902,79 @@ extern "C" int pl_lsd_frame_bf_match(const uint8_t* d1, int n1, const uint8_t* d
 }
 extern "C" int pl_lsd_search_double(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnratio, int* matches) {
   return search_double_host(d1, n1, d2, n2, 50.f, nnratio, 1, matches);
+}
+
+
+// Frame::AssignFeaturesToGridForLine -> CSR (cell = ix*48+iy), for parity tests of the line grid itself
+namespace pl {
+__global__ void __launch_bounds__(32) k_line_grid(const KeyLine68* kl, int n, const float* bounds, int* start, unsigned short* items,
+                                                  unsigned short* path, unsigned short* plen) {
+  __shared__ unsigned short cursor[NCELL];
+  GridP g = make_grid(bounds);
+  build_line_grid(kl, n, g, start, items, path, plen, threadIdx.x);
+  LineGridS L; L.start = start; L.items = items; L.path = path; L.plen = plen; L.cursor = cursor;
+  fill_line_grid(L, n, threadIdx.x);
+}
+}  // namespace pl
+
+extern "C" int pl_frame_assign_grid_lines(const void* keylines_un, int n, const float* bounds, int* cell_start, int* cell_items, int cap_items) {
+  PL_ARG(keylines_un && bounds && cell_start && cell_items && n >= 0 && n < 60000);
+  int rc = require_device(); if (rc) return rc;
+  Stage s;
+  const int cap = std::max(n, 1);
+  KeyLine68* dk = (KeyLine68*)s.up((const uint8_t*)keylines_un, (size_t)n * 68);
+  float* db = s.up(bounds, 4);
+  int* ds = s.alloc<int>(NCELL + 1); unsigned short* di = s.alloc<unsigned short>((size_t)cap * kMaxPath);
+  unsigned short* dp = s.alloc<unsigned short>((size_t)cap * kMaxPath); unsigned short* dl = s.alloc<unsigned short>(cap);
+  PL_ARG(dk && db && ds && di && dp && dl);
+  k_line_grid<<<1, 32>>>(dk, n, db, ds, di, dp, dl);
+  PL_LAUNCH_CHECK();
+  rc = down(cell_start, ds, NCELL + 1); if (rc) return rc;
+  const int tot = cell_start[NCELL];
+  std::vector<unsigned short> tmp(std::max(tot, 1));
+  rc = down(tmp.data(), di, (size_t)tot); if (rc) return rc;
+  for (int i = 0; i < tot && i < cap_items; i++) cell_items[i] = tmp[i];
+  return tot;
+}
+
+static int line_search_host(int variant, const void* kls, const double* lfunc, const uint8_t* desc, int n, const float* bounds,
+                            int n_q, const uint8_t* q_valid, const float* q_proj, const uint8_t* q_desc, const float* q_length,
+                            const float* q_view_cos, float th, float nnratio, const uint8_t* preassigned, int* match) {
+  PL_ARG(kls && lfunc && desc && bounds && match && n >= 0 && n < 60000 && n_q >= 0);
+  int rc = require_device(); if (rc) return rc;
+  Stage s;
+  const int cap = std::max(n, 1), capq = std::max(n_q, 1);
+  LineSearchArgs A;
+  A.kl = (const KeyLine68*)s.up((const uint8_t*)kls, (size_t)n * 68); A.lfunc = s.up(lfunc, (size_t)n * 3); A.desc = s.up(desc, (size_t)n * 32);
+  A.n = s.up(&n, 1); A.cap = cap; A.bounds = s.up(bounds, 4);
+  A.n_q = s.up(&n_q, 1); A.cap_q = capq; A.q_valid = s.up(q_valid, n_q); A.q_proj = s.up(q_proj, (size_t)n_q * 4);
+  A.q_desc = s.up(q_desc, (size_t)n_q * 32);
+  A.q_length = q_length ? s.up(q_length, n_q) : nullptr; A.q_view_cos = q_view_cos ? s.up(q_view_cos, n_q) : nullptr;
+  A.th = th; A.nnratio = nnratio; A.variant = variant;
+  A.preassigned = preassigned ? s.up(preassigned, n) : nullptr;
+  A.match = s.alloc<int>(cap); A.nmatches = s.alloc<int>(1);
+  A.g_start = s.alloc<int>(NCELL + 1); A.g_items = s.alloc<unsigned short>((size_t)cap * kMaxPath);
+  A.g_path = s.alloc<unsigned short>((size_t)cap * kMaxPath); A.g_plen = s.alloc<unsigned short>(cap); A.g_first = s.alloc<int>(cap);
+  PL_ARG(A.kl && A.lfunc && A.desc && A.match && A.nmatches && A.g_start && A.g_items && A.g_path && A.g_plen && A.g_first);
+  k_line_search<<<1, 32>>>(A);
+  PL_LAUNCH_CHECK();
+  int nm = 0;
+  rc = down(&nm, A.nmatches, 1); if (rc) return rc;
+  if (n) { rc = down(match, A.match, (size_t)n); if (rc) return rc; }
+  return nm;
+}
+
+extern "C" int pl_lsd_search_by_projection_last(const void* keylines_cur, const double* linefunc_cur, const uint8_t* desc_cur,
+                                                int n_cur, const float* bounds, int n_last, const uint8_t* last_valid,
+                                                const float* last_proj, const uint8_t* last_desc, const float* last_length,
+                                                float th, const uint8_t* cur_preassigned, int* cur_match) {
+  return line_search_host(0, keylines_cur, linefunc_cur, desc_cur, n_cur, bounds, n_last, last_valid, last_proj, last_desc,
+                          last_length, nullptr, th, 0.f, cur_preassigned, cur_match);
+}
+extern "C" int pl_lsd_search_by_projection_lines(const void* keylines, const double* linefunc, const uint8_t* desc, int n,
+                                                 const float* bounds, int n_ml, const uint8_t* in_view, const float* proj,
+                                                 const float* view_cos, const uint8_t* ml_desc, float th, float nnratio,
+                                                 const uint8_t* preassigned, int* match) {
+  return line_search_host(1, keylines, linefunc, desc, n, bounds, n_ml, in_view, proj, ml_desc, nullptr, view_cos, th, nnratio,
+                          preassigned, match);
 }

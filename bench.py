@@ -314,7 +314,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=2048, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=4736, help="frames per GPU per step (148 SMs x 32 resident region-growing warps)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":

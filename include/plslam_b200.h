@@ -162,6 +162,7 @@ typedef struct PLLineConfig {
   double min_line_length;   /* LINEextractor.min_line_length                                                    */
   int max_batch;
   int segment_cap;          /* max LSD segments per frame before truncation; 0 = default 8192                     */
+  int lsd_used_in_global;   /* region-growing USED map: <0 shared memory, >0 global memory, 0 = global unless env PLSLAM_LSD_USED_GLOBAL=0 */
 } PLLineConfig;
 typedef struct PLLine PLLine;
 int pl_line_create(const PLLineConfig* cfg, PLLine** out);

@@ -291,7 +291,7 @@ KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4
 
 class PLLineConfig(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("nfeatures", C.c_int), ("min_line_length", C.c_double),
-                ("max_batch", C.c_int), ("segment_cap", C.c_int)]
+                ("max_batch", C.c_int), ("segment_cap", C.c_int), ("lsd_used_in_global", C.c_int)]
 
 
 class LINEextractor:
@@ -306,7 +306,7 @@ class LINEextractor:
                  segment_cap=0):
         if numOctaves != 1 or int(scale) != 1:
             raise PLError("only numOctaves == 1 and int(scale) == 1 are supported (all reference configs)")
-        self.cfg = PLLineConfig(width, height, nLSDFeature, float(min_line_length), max_batch, segment_cap)
+        self.cfg = PLLineConfig(width, height, nLSDFeature, float(min_line_length), max_batch, segment_cap, 0)
         self._h = vp()
         L = lib()
         L.pl_line_create.argtypes = [C.POINTER(PLLineConfig), C.POINTER(vp)]

@@ -67,7 +67,7 @@ extern "C" int pl_frontend_create(const PLFrontendConfig* cfg, PLFrontend** out)
 #define FE_CUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { set_error("%s -> %s", #e, cudaGetErrorString(_e)); pl_frontend_destroy(h); return PL_ERR_CUDA; } } while (0)
   PLOrbConfig oc = {cfg->width, cfg->height, cfg->orb_nfeatures, cfg->orb_scale_factor, cfg->orb_nlevels, cfg->orb_ini_th, cfg->orb_min_th, cfg->max_batch, 0};
   FE_TRY(pl_orb_create(&oc, &h->orb));
-  PLLineConfig lc = {cfg->width, cfg->height, cfg->line_nfeatures, cfg->line_min_length, cfg->max_batch, 0};
+  PLLineConfig lc = {cfg->width, cfg->height, cfg->line_nfeatures, cfg->line_min_length, cfg->max_batch, 0, 0};
   FE_TRY(pl_line_create(&lc, &h->line));
   h->capK = pl_orb_capacity(h->orb); h->capL = pl_line_capacity(h->line);
   FE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));

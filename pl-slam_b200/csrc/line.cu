@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 #include <vector>
 #include <algorithm>
 
@@ -31,7 +32,7 @@ constexpr double kPI = 3.14159265358979323846;
 constexpr double kDegToRads = kPI / 180;
 constexpr int kBins = 1024;
 constexpr int kChunkRows = 8;
-constexpr int kRing = 2048;
+constexpr int kRing = 512;
 
 struct PLKeyLineRec {  // cv::line_descriptor::KeyLine, 68 bytes
   float angle; int class_id; int octave; float ptx, pty; float response; float size;
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(256) k_lsd_scale(LineParams P, const uint8_t* 
 //   w = bit pattern of s = gx^2+gy^2 (modgrad = sqrt(s/4), recomputed in fp64 where the weights are used)
 constexpr float kNotDefDeg = -1024.f;
 __global__ void __launch_bounds__(256) k_lsd_grad(LineParams P, const uint8_t* __restrict__ scaled,
-                                                  float4* __restrict__ A, float2* __restrict__ seedcs, int* __restrict__ maxs) {
+                                                  float* __restrict__ ANG, float2* __restrict__ CS, int* __restrict__ S2, float2* __restrict__ seedcs, int* __restrict__ maxs) {
   const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
   const int f = blockIdx.z;
   int s = 0;
@@ -155,19 +156,19 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineParams P, const uint8_t* _
         scs = make_float2((float)cos(ad), (float)sin(ad));
       } else s = 0;
     }
-    A[(long long)f * P.npx + y * P.sw + x] = rec;
-    seedcs[(long long)f * P.npx + y * P.sw + x] = scs;
+    const long long o = (long long)f * P.npx + y * P.sw + x;
+    ANG[o] = rec.x; CS[o] = make_float2(rec.y, rec.z); S2[o] = __float_as_int(rec.w);
+    seedcs[o] = scs;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s = max(s, __shfl_xor_sync(0xffffffffu, s, o));
   if ((threadIdx.x & 31) == 0 && s > 0) atomicMax(&maxs[f], s);
 }
-__device__ __forceinline__ double rec_norm(float4 r) { return sqrt((double)__float_as_int(r.w) / 4.0); }
-__device__ __forceinline__ double rec_angle(float4 r) { return (double)r.x * kDegToRads; }
-__device__ __forceinline__ int rec_bin(float4 r, double bin_coef) { return (int)(rec_norm(r) * bin_coef); }
+__device__ __forceinline__ double s_norm(int s) { return sqrt((double)s / 4.0); }
+__device__ __forceinline__ int s_bin(int s, double bin_coef) { return (int)(s_norm(s) * bin_coef); }
 
 // K_C per-chunk histograms of the defined pixels (chunk = kChunkRows image rows)
-__global__ void __launch_bounds__(256) k_lsd_hist(LineParams P, const float4* __restrict__ A, const int* __restrict__ maxs,
+__global__ void __launch_bounds__(256) k_lsd_hist(LineParams P, const float* __restrict__ ANG, const int* __restrict__ S2, const int* __restrict__ maxs,
                                                   unsigned short* __restrict__ counts /*[B][kBins][nchunk]*/) {
   __shared__ int hist[kBins];
   const int chunk = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
@@ -177,11 +178,11 @@ __global__ void __launch_bounds__(256) k_lsd_hist(LineParams P, const float4* __
   const double max_grad = ms > 0 ? sqrt((double)ms / 4.0) : -1.0;
   const double bin_coef = (max_grad > 0) ? (double)(kBins - 1) / max_grad : 0.0;
   const int y0 = chunk * kChunkRows, y1 = min(y0 + kChunkRows, P.sh - 1);
-  const float4* G = A + (long long)f * P.npx;
+  const float* G = ANG + (long long)f * P.npx;
+  const int* SS = S2 + (long long)f * P.npx;
   for (int i = tid; i < (y1 - y0) * P.sw; i += 256) {
     int y = y0 + i / P.sw, x = i % P.sw;
-    float4 g = G[y * P.sw + x];
-    if (g.x != kNotDefDeg) atomicAdd(&hist[rec_bin(g, bin_coef)], 1);
+    if (G[y * P.sw + x] != kNotDefDeg) atomicAdd(&hist[s_bin(SS[y * P.sw + x], bin_coef)], 1);
   }
   __syncthreads();
   for (int i = tid; i < kBins; i += 256) counts[((long long)f * kBins + i) * P.nchunk + chunk] = (unsigned short)hist[i];
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(kBins) k_lsd_scan(LineParams P, const unsigned
 }
 
 // K_E stable scatter: one warp per chunk walks its pixels in row-major order
-__global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const float4* __restrict__ A, const int* __restrict__ maxs,
+__global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const float* __restrict__ ANG, const int* __restrict__ S2, const int* __restrict__ maxs,
                                                      const int* __restrict__ offsets, unsigned* __restrict__ order) {
   __shared__ unsigned short cnt[4][kBins];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -226,7 +227,8 @@ __global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const float4*
   const double max_grad = ms > 0 ? sqrt((double)ms / 4.0) : -1.0;
   const double bin_coef = (max_grad > 0) ? (double)(kBins - 1) / max_grad : 0.0;
   const int y0 = chunk * kChunkRows, y1 = min(y0 + kChunkRows, P.sh - 1);
-  const float4* G = A + (long long)f * P.npx;
+  const float* G = ANG + (long long)f * P.npx;
+  const int* SS = S2 + (long long)f * P.npx;
   const int* off = offsets + (long long)f * kBins * P.nchunk;
   unsigned* O = order + (long long)f * P.npx;
   const int n = (y1 - y0) * P.sw;
@@ -236,8 +238,7 @@ __global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const float4*
     if (i < n) {
       int y = y0 + i / P.sw, x = i % P.sw;
       pix = x | (y << 16);                       // packed (x, y): the grow kernel never divides
-      float4 g = G[y * P.sw + x];
-      if (g.x != kNotDefDeg) bin = rec_bin(g, bin_coef);
+      if (G[y * P.sw + x] != kNotDefDeg) bin = s_bin(SS[y * P.sw + x], bin_coef);
     }
     unsigned peers = __match_any_sync(0xffffffffu, bin);
     if (bin >= 0) O[off[bin * P.nchunk + chunk] + cnt[wid][bin] + __popc(peers & lt)] = (unsigned)pix;
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const float4*
 
 // ---------------------------------------------------------------------------------------------- K_F region growing
 struct GrowCtx {
-  const float4* G; const float2* S2; unsigned* U; unsigned* R; unsigned* ring;   // U: USED bitmap in shared memory
+  const float* ANG; const float2* CS; const int* SQ; const float2* S2; unsigned* U; unsigned* R; unsigned* ring;   // U: USED bitmap in shared memory
   int sw, sh, s_th;
 };
 __device__ __forceinline__ bool used_get(const GrowCtx& C, int idx) { return (C.U[idx >> 5] >> (idx & 31)) & 1u; }
@@ -277,9 +278,8 @@ __device__ __forceinline__ bool is_aligned(double a, double theta, double prec) 
 // invalidates its duplicates in the later neighbourhoods, so the result equals the one-entry-at-a-time loop.
 __device__ int region_grow(const GrowCtx& C, unsigned seed, double prec, double& reg_angle, int lane) {
   const int sidx = (int)(seed >> 16) * C.sw + (int)(seed & 0xffffu);
-  const float4 gs = __ldg(&C.G[sidx]);
   const float2 s0 = __ldg(&C.S2[sidx]);
-  reg_angle = rec_angle(gs);
+  reg_angle = (double)__ldg(&C.ANG[sidx]) * kDegToRads;
   float sumdx = s0.x, sumdy = s0.y;
   if (lane == 0) { C.R[0] = seed; C.ring[0] = seed; used_set1(C, sidx); }
   int cnt = 1;
@@ -291,7 +291,7 @@ __device__ int region_grow(const GrowCtx& C, unsigned seed, double prec, double&
     bool valid = false;
     int idx = -1;
     unsigned pk = 0;
-    float4 rec = make_float4(kNotDefDeg, 0.f, 0.f, 0.f);
+    float ang = kNotDefDeg;
     if (grp < m) {
       const int qi = i + grp;
       const unsigned p = (cnt - qi <= kRing) ? C.ring[qi & (kRing - 1)] : C.R[qi];
@@ -300,12 +300,12 @@ __device__ int region_grow(const GrowCtx& C, unsigned seed, double prec, double&
         idx = yy * C.sw + xx;
         pk = (unsigned)xx | ((unsigned)yy << 16);
         if (!used_get(C, idx)) {
-          rec = __ldg(&C.G[idx]);
-          valid = (rec.x != kNotDefDeg);
+          ang = __ldg(&C.ANG[idx]);
+          valid = (ang != kNotDefDeg);
         }
       }
     }
-    const double a = (double)rec.x * kDegToRads;
+    const double a = (double)ang * kDegToRads;
     // Commit in order.  Every remaining candidate is tested against the CURRENT region angle at once; the first
     // aligned one (lowest lane = reference order) is added, which changes the angle, and the candidates after it
     // are tested again.  Candidates skipped before the committed lane were tested with the angle they would
@@ -316,10 +316,12 @@ __device__ int region_grow(const GrowCtx& C, unsigned seed, double prec, double&
       if (!al) break;
       const int k = __ffs(al) - 1;
       const unsigned pkk = __shfl_sync(0xffffffffu, pk, k);
-      if (lane == 0) { used_set1(C, (int)(pkk >> 16) * C.sw + (int)(pkk & 0xffffu)); C.R[cnt] = pkk; C.ring[cnt & (kRing - 1)] = pkk; }
+      const int ikk = (int)(pkk >> 16) * C.sw + (int)(pkk & 0xffffu);
+      const float2 csk = __ldg(&C.CS[ikk]);            // cos/sin of the added pixel: read once per added pixel
+      if (lane == 0) { used_set1(C, ikk); C.R[cnt] = pkk; C.ring[cnt & (kRing - 1)] = pkk; }
       cnt++;
-      sumdx = __fadd_rn(sumdx, __shfl_sync(0xffffffffu, rec.y, k));
-      sumdy = __fadd_rn(sumdy, __shfl_sync(0xffffffffu, rec.z, k));
+      sumdx = __fadd_rn(sumdx, csk.x);
+      sumdy = __fadd_rn(sumdy, csk.y);
       reg_angle = (double)fast_atan2_deg_l(sumdy, sumdx) * kDegToRads;
       live &= ~((2u << k) - 1u);                                   // everything up to k has been decided
       live &= ~__ballot_sync(0xffffffffu, pk == pkk && idx >= 0);  // the same pixel in a later 3x3 is now USED
@@ -336,7 +338,7 @@ __device__ void region2rect(const GrowCtx& C, int n, double reg_angle, double pr
   for (int i = lane; i < n; i += 32) {
     const unsigned p = C.R[i];
     const int px = (int)(p & 0xffffu), py = (int)(p >> 16);
-    const double w = rec_norm(__ldg(&C.G[py * C.sw + px]));
+    const double w = s_norm(__ldg(&C.SQ[py * C.sw + px]));
     sx += (double)px * w;
     sy += (double)py * w;
     sw_ += w;
@@ -347,7 +349,7 @@ __device__ void region2rect(const GrowCtx& C, int n, double reg_angle, double pr
   for (int i = lane; i < n; i += 32) {
     const unsigned p = C.R[i];
     const int px = (int)(p & 0xffffu), py = (int)(p >> 16);
-    const double w = rec_norm(__ldg(&C.G[py * C.sw + px]));
+    const double w = s_norm(__ldg(&C.SQ[py * C.sw + px]));
     const double dx = (double)px - x, dy = (double)py - y;
     Ixx += dy * dy * w; Iyy += dx * dx * w; Ixy -= dx * dy * w;
   }
@@ -382,7 +384,7 @@ __device__ bool refine(const GrowCtx& C, int& n, double reg_angle, double prec, 
   if (density >= density_th) return true;
   const unsigned p0 = C.R[0];
   const double xc = (double)(int)(p0 & 0xffffu), yc = (double)(int)(p0 >> 16);
-  const double ang_c = rec_angle(__ldg(&C.G[(int)(p0 >> 16) * C.sw + (int)(p0 & 0xffffu)]));
+  const double ang_c = (double)__ldg(&C.ANG[(int)(p0 >> 16) * C.sw + (int)(p0 & 0xffffu)]) * kDegToRads;
   double sum = 0, s_sum = 0;
   int cnt = 0;
   for (int i = lane; i < n; i += 32) {
@@ -391,7 +393,7 @@ __device__ bool refine(const GrowCtx& C, int& n, double reg_angle, double prec, 
     used_clear(C, pidx);
     const double px = (double)(int)(p & 0xffffu), py = (double)(int)(p >> 16);
     if (dist_d(xc, yc, px, py) < rec.width) {
-      const double ang_d = angle_diff_signed(rec_angle(__ldg(&C.G[pidx])), ang_c);
+      const double ang_d = angle_diff_signed((double)__ldg(&C.ANG[pidx]) * kDegToRads, ang_c);
       sum += ang_d; s_sum += ang_d * ang_d; ++cnt;
     }
   }
@@ -436,17 +438,23 @@ __device__ bool refine(const GrowCtx& C, int& n, double reg_angle, double prec, 
   return true;
 }
 
-__global__ void __launch_bounds__(32) k_lsd_grow(LineParams P, const float4* __restrict__ gxy, const float2* __restrict__ seedcs,
+template <bool kSmemUsed>
+__global__ void __launch_bounds__(32, 32) k_lsd_grow(LineParams P, unsigned* __restrict__ gbits, const float* __restrict__ ANG, const float2* __restrict__ CS, const int* __restrict__ SQ, const float2* __restrict__ seedcs,
                                                  const unsigned* __restrict__ order, const int* __restrict__ ndef,
                                                  unsigned* __restrict__ reg, float4* __restrict__ segs,
                                                  int* __restrict__ nseg, int* __restrict__ overflow) {
   __shared__ unsigned ring[kRing];
-  extern __shared__ unsigned ubits[];            // USED bitmap of the scaled image: (npx+31)/32 words
+  extern __shared__ unsigned sbits[];            // USED bitmap of the scaled image: (npx+31)/32 words
   const int f = blockIdx.x, lane = threadIdx.x;
-  for (int i = lane; i < (P.npx + 31) / 32; i += 32) ubits[i] = 0u;
+  const int nwords = (P.npx + 31) / 32;
+  // The bitmap lives in shared memory (fast, but 24.6 KB per warp caps the SM at 8 frames) or in global memory / L1
+  // (slower per access, but up to 28 frames per SM hide the latency): chosen at handle creation.
+  unsigned* ubits = kSmemUsed ? sbits : gbits + (long long)f * nwords;
+  for (int i = lane; i < nwords; i += 32) ubits[i] = 0u;
   __syncwarp();
   GrowCtx C;
-  C.G = gxy + (long long)f * P.npx; C.S2 = seedcs + (long long)f * P.npx; C.U = ubits; C.R = reg + (long long)f * P.npx;
+  C.ANG = ANG + (long long)f * P.npx; C.CS = CS + (long long)f * P.npx; C.SQ = SQ + (long long)f * P.npx;
+  C.S2 = seedcs + (long long)f * P.npx; C.U = ubits; C.R = reg + (long long)f * P.npx;
   C.ring = ring; C.sw = P.sw; C.sh = P.sh; C.s_th = P.s_th;
   const unsigned* O = order + (long long)f * P.npx;
   float4* S = segs + (long long)f * P.seg_cap;
@@ -738,8 +746,10 @@ struct PLLine {
   cudaStream_t stream = nullptr;
   uint8_t* d_scaled = nullptr;
   float2* d_seedcs = nullptr;
+  unsigned* d_ubits = nullptr;
+  int used_global = 0;
   size_t grow_smem = 0;
-  float4* d_gxy = nullptr;
+  float* d_ang = nullptr; float2* d_cs = nullptr; int* d_sq = nullptr;
   unsigned short* d_counts = nullptr;
   int *d_offsets = nullptr, *d_ndef = nullptr, *d_maxs = nullptr, *d_nseg = nullptr, *d_overflow = nullptr;
   unsigned *d_order = nullptr, *d_reg = nullptr;
@@ -760,7 +770,7 @@ static const unsigned char h_comb[64] = {0, 1, 0, 2, 0, 3, 0, 4, 0, 5, 0, 6, 1, 
 
 extern "C" void pl_line_destroy(PLLine* h) {
   if (!h) return;
-  cudaFree(h->d_scaled); cudaFree(h->d_seedcs); cudaFree(h->d_gxy); cudaFree(h->d_counts); cudaFree(h->d_offsets);
+  cudaFree(h->d_scaled); cudaFree(h->d_seedcs); cudaFree(h->d_ubits); cudaFree(h->d_ang); cudaFree(h->d_cs); cudaFree(h->d_sq); cudaFree(h->d_counts); cudaFree(h->d_offsets);
   cudaFree(h->d_ndef); cudaFree(h->d_maxs); cudaFree(h->d_nseg); cudaFree(h->d_overflow); cudaFree(h->d_order);
   cudaFree(h->d_reg); cudaFree(h->d_segs); cudaFree(h->d_dx); cudaFree(h->d_dy); cudaFree(h->d_img); cudaFree(h->d_kls);
   cudaFree(h->d_desc); cudaFree(h->d_lf); cudaFree(h->d_nl); cudaFree(h->d_mask);
@@ -795,7 +805,8 @@ extern "C" int pl_line_create(const PLLineConfig* cfg, PLLine** out) {
 #define LN_TRY(e) do { int _r = (e); if (_r) { pl_line_destroy(h); return _r; } } while (0)
 #define LN_CUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { set_error("%s -> %s", #e, cudaGetErrorString(_e)); pl_line_destroy(h); return PL_ERR_CUDA; } } while (0)
   LN_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  LN_TRY(dev_alloc(&h->d_scaled, npx * B)); LN_TRY(dev_alloc(&h->d_seedcs, npx * B)); LN_TRY(dev_alloc(&h->d_gxy, npx * B));
+  LN_TRY(dev_alloc(&h->d_scaled, npx * B)); LN_TRY(dev_alloc(&h->d_seedcs, npx * B)); LN_TRY(dev_alloc(&h->d_ang, npx * B));
+  LN_TRY(dev_alloc(&h->d_cs, npx * B)); LN_TRY(dev_alloc(&h->d_sq, npx * B));
   LN_TRY(dev_alloc(&h->d_counts, (size_t)kBins * P.nchunk * B)); LN_TRY(dev_alloc(&h->d_offsets, (size_t)kBins * P.nchunk * B));
   LN_TRY(dev_alloc(&h->d_ndef, B)); LN_TRY(dev_alloc(&h->d_maxs, B)); LN_TRY(dev_alloc(&h->d_nseg, B)); LN_TRY(dev_alloc(&h->d_overflow, 1));
   LN_TRY(dev_alloc(&h->d_order, npx * B)); LN_TRY(dev_alloc(&h->d_reg, npx * B)); LN_TRY(dev_alloc(&h->d_segs, (size_t)P.seg_cap * B));
@@ -814,7 +825,10 @@ extern "C" int pl_line_create(const PLLineConfig* cfg, PLLine** out) {
   LN_CUDA(cudaFuncSetAttribute(k_keylines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->key_smem));
   h->grow_smem = (size_t)((P.npx + 31) / 32) * 4;
   if (h->grow_smem > 200 * 1024) { set_error("frame too large for the shared-memory USED bitmap"); pl_line_destroy(h); return PL_ERR_ARG; }
-  LN_CUDA(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grow_smem));
+  { const char* e = getenv("PLSLAM_LSD_USED_GLOBAL");   // default: global (measured 1.6x the throughput of the smem map at B>=2048)
+    h->used_global = cfg->lsd_used_in_global > 0 ? 1 : (cfg->lsd_used_in_global < 0 ? 0 : !(e && e[0] == '0')); }
+  if (h->used_global) LN_TRY(dev_alloc(&h->d_ubits, (size_t)((P.npx + 31) / 32) * B));
+  LN_CUDA(cudaFuncSetAttribute(k_lsd_grow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grow_smem));
   *out = h;
   return PL_OK;
 }
@@ -848,16 +862,19 @@ extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int str
   PL_CUDA(cudaMemsetAsync(h->d_maxs, 0, sizeof(int) * B, st));
   k_lsd_scale<<<dim3((P.sw + 31) / 32, (P.sh + 31) / 32, B), 256, 0, st>>>(P, imgs, stride, (long long)frame_stride, h->d_scaled);
   PL_LAUNCH_CHECK();
-  k_lsd_grad<<<dim3((P.sw + 63) / 64, (P.sh + 3) / 4, B), 256, 0, st>>>(P, h->d_scaled, h->d_gxy, h->d_seedcs, h->d_maxs);
+  k_lsd_grad<<<dim3((P.sw + 63) / 64, (P.sh + 3) / 4, B), 256, 0, st>>>(P, h->d_scaled, h->d_ang, h->d_cs, h->d_sq, h->d_seedcs, h->d_maxs);
   PL_LAUNCH_CHECK();
-  k_lsd_hist<<<dim3(P.nchunk, B), 256, 0, st>>>(P, h->d_gxy, h->d_maxs, h->d_counts);
+  k_lsd_hist<<<dim3(P.nchunk, B), 256, 0, st>>>(P, h->d_ang, h->d_sq, h->d_maxs, h->d_counts);
   PL_LAUNCH_CHECK();
   k_lsd_scan<<<B, kBins, 0, st>>>(P, h->d_counts, h->d_offsets, h->d_ndef);
   PL_LAUNCH_CHECK();
-  k_lsd_scatter<<<dim3((P.nchunk + 3) / 4, B), 128, 0, st>>>(P, h->d_gxy, h->d_maxs, h->d_offsets, h->d_order);
+  k_lsd_scatter<<<dim3((P.nchunk + 3) / 4, B), 128, 0, st>>>(P, h->d_ang, h->d_sq, h->d_maxs, h->d_offsets, h->d_order);
   PL_LAUNCH_CHECK();
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev0, st));
-  k_lsd_grow<<<B, 32, h->grow_smem, st>>>(P, h->d_gxy, h->d_seedcs, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow);
+  if (h->used_global)
+    k_lsd_grow<false><<<B, 32, 0, st>>>(P, h->d_ubits, h->d_ang, h->d_cs, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow);
+  else
+  k_lsd_grow<true><<<B, 32, h->grow_smem, st>>>(P, nullptr, h->d_ang, h->d_cs, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow);
   PL_LAUNCH_CHECK();
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev1, st));
   k_keylines<<<B, 256, h->key_smem, st>>>(P, h->d_segs, h->d_nseg, mask, (PLKeyLineRec*)keylines, linefunc, n);

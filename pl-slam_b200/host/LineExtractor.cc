@@ -22,7 +22,7 @@ void LINEextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std:
     throw std::runtime_error("Mask error while detecting lines: please check its dimensions and that data type is CV_8UC1");
   if (!handle || hw != image.cols || hh != image.rows) {
     pl_line_destroy(handle); handle = nullptr;
-    PLLineConfig cfg = {image.cols, image.rows, (int)nLSDFeature, min_line_length, 1, 0};
+    PLLineConfig cfg = {image.cols, image.rows, (int)nLSDFeature, min_line_length, 1, 0, 0};
     if (pl_line_create(&cfg, &handle) != PL_OK) throw std::runtime_error(std::string("plslam_b200: ") + pl_last_error());
     hw = image.cols; hh = image.rows;
   }

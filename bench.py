@@ -275,10 +275,13 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         algo = fe.grow_bytes_per_frame() * B
         achieved = algo / (grow_ms / 1000.0) / 1e9
-        # CPU baseline: the oracle, one thread, bounded sample
-        import oracle
-        oracle.build()
-        cpu_fps, cpu_n, _ = cpu_sample(frames, problems, 6, 1)
+        cpu = None
+        if world == 1:      # CPU baseline: the oracle, one thread, bounded sample (rank 0, N=1 only)
+            import oracle
+            oracle.build()
+            cpu_fps, cpu_n, _ = cpu_sample(frames, problems, 6, 1)
+            cpu = {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
+                   "sample": f"{cpu_n} frames of the same workload on the CPU oracle (restatement), single thread"}
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -295,13 +298,14 @@ def run_ours(args):
                          "frac": achieved / peak, "traffic": None, "ms_per_launch": grow_ms,
                          "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "share_of_step": grow_ms / (ms / args.steps)},
-            "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
-                             "sample": f"{cpu_n} frames of the same workload on the CPU oracle (restatement), single thread"},
+            "cpu_baseline": cpu,
         }
         traffic_file = os.path.join(ROOT, "profiles", "traffic_k_lsd_grow.json")
         if os.path.exists(traffic_file):
             try:
-                line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+                tj = json.load(open(traffic_file))     # one `ncu --set full` capture: DRAM bytes per frame of the launch
+                line["roofline"]["traffic"] = float(tj["dram_bytes_per_frame"]) * B
+                line["roofline"]["traffic_source"] = tj.get("source")
             except Exception:
                 pass
         print(json.dumps(line), flush=True)

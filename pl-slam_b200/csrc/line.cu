@@ -151,9 +151,12 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineParams P, const uint8_t* _
       if (s > P.s_th) {
         const float deg = fast_atan2_deg_l((float)gx, (float)(-gy));
         const double af = (double)(float)((double)deg * kDegToRads);
-        rec.x = deg; rec.y = (float)cos(af); rec.z = (float)sin(af);
+        double sn, cs;
+        sincos(af, &sn, &cs);
+        rec.x = deg; rec.y = (float)cs; rec.z = (float)sn;
         const double ad = (double)deg * kDegToRads;      // a region SEEDED here starts from cos/sin of the fp64 angle
-        scs = make_float2((float)cos(ad), (float)sin(ad));
+        sincos(ad, &sn, &cs);
+        scs = make_float2((float)cs, (float)sn);
       } else s = 0;
     }
     const long long o = (long long)f * P.npx + y * P.sw + x;
@@ -272,11 +275,11 @@ __device__ __forceinline__ bool is_aligned(double a, double theta, double prec) 
 }
 
 // LineSegmentDetectorImpl::region_grow — exact visiting order; returns the region size, region in C.R[0..n).
-// Three queue entries are expanded per step: lanes 0-8 / 9-17 / 18-26 fetch the 3x3 neighbourhoods of entries
-// i, i+1, i+2 (used flag + pixel record, two independent loads in flight per lane), then the candidates are committed
+// Four queue entries are expanded per step: lanes 8g..8g+7 fetch the 8 neighbours of entry i+g (used flag, then the
+// 4-byte angle of the unused ones), then the candidates are committed
 // in the reference's order (queue order, then row-major inside the 3x3); a pixel added earlier in the same step
 // invalidates its duplicates in the later neighbourhoods, so the result equals the one-entry-at-a-time loop.
-__device__ int region_grow(const GrowCtx& C, unsigned seed, double prec, double& reg_angle, int lane) {
+__device__ __noinline__ int region_grow(const GrowCtx& C, unsigned seed, double prec, double& reg_angle, int lane) {
   const int sidx = (int)(seed >> 16) * C.sw + (int)(seed & 0xffffu);
   const float2 s0 = __ldg(&C.S2[sidx]);
   reg_angle = (double)__ldg(&C.ANG[sidx]) * kDegToRads;
@@ -284,10 +287,11 @@ __device__ int region_grow(const GrowCtx& C, unsigned seed, double prec, double&
   if (lane == 0) { C.R[0] = seed; C.ring[0] = seed; used_set1(C, sidx); }
   int cnt = 1;
   __syncwarp();
-  const int grp = lane / 9, kk = lane - grp * 9;
+  // lane -> (queue entry lane/8, neighbour lane%8); the centre of a 3x3 is always USED, so 8 neighbours suffice
+  const int grp = lane >> 3, kk8 = lane & 7, kk = kk8 + (kk8 >= 4);
   const int ox = kk % 3 - 1, oy = kk / 3 - 1;
   for (int i = 0; i < cnt;) {
-    const int m = min(3, cnt - i);
+    const int m = min(4, cnt - i);
     bool valid = false;
     int idx = -1;
     unsigned pk = 0;
@@ -333,7 +337,7 @@ __device__ int region_grow(const GrowCtx& C, unsigned seed, double prec, double&
 }
 
 // LineSegmentDetectorImpl::region2rect (+get_theta); sums are reduced lane-strided then by butterfly
-__device__ void region2rect(const GrowCtx& C, int n, double reg_angle, double prec, RectD& rec, int lane) {
+__device__ __noinline__ void region2rect(const GrowCtx& C, int n, double reg_angle, double prec, RectD& rec, int lane) {
   double sx = 0, sy = 0, sw_ = 0;
   for (int i = lane; i < n; i += 32) {
     const unsigned p = C.R[i];
@@ -379,7 +383,7 @@ __device__ __forceinline__ double dist_d(double x1, double y1, double x2, double
 }
 
 // LineSegmentDetectorImpl::refine + reduce_region_radius; n is updated; returns false if the region is rejected
-__device__ bool refine(const GrowCtx& C, int& n, double reg_angle, double prec, RectD& rec, double density_th, int lane) {
+__device__ __noinline__ bool refine(const GrowCtx& C, int& n, double reg_angle, double prec, RectD& rec, double density_th, int lane) {
   double density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
   if (density >= density_th) return true;
   const unsigned p0 = C.R[0];

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(LM_THREADS) k_pose_opt(PoseArgs A) {
           for (int i = tid; i < nl; i += LM_THREADS) if (!lout[i])
             for (int e = 0; e < 2; e++) {
               double J[6];
-#pragma unroll
+#pragma unroll 1
               for (int d = 0; d < 6; d++) J[d] = 5e8 * (line_err(S.Tp[d], i, e) - line_err(S.Tm[d], i, e));
               const double err = le[2 * i + e];
               r1 = 1.0;

@@ -158,8 +158,33 @@ __global__ void __launch_bounds__(128) k_fast_cells(OrbParams P, const CellInfo*
   __syncthreads();
   const int dw = w - 6, dh = h - 6;  // detection area
   const int npx = (dw > 0 && dh > 0) ? dw * dh : 0;
-  for (int i = tid; i < npx; i += 128) {
-    int y = i / dw, x = i - y * dw;
+  const float inv_dw = dw > 0 ? 1.0f / (float)dw : 0.f;   // i / dw for i < 4096 without an integer division
+  // Phase A: 4-pixel quick reject for every pixel; survivors are compacted into a list so that the expensive arc
+  // evaluation runs on full warps instead of a few divergent lanes.
+  __shared__ unsigned short list[kMaxWin * kMaxWin];
+  __shared__ int nlist;
+  if (tid == 0) nlist = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < npx; i0 += 128) {
+    const int i = i0 + tid;
+    bool pass = false;
+    if (i < npx) {
+      const int y = __float2int_rz(__fmul_rn((float)i + 0.5f, inv_dw)), x = i - y * dw;
+      const uint8_t* p = &win[(y + 3) * WP + x + 3];
+      const int v = p[0], th = P.minTh;
+      pass = !(abs(v - p[3 * WP]) <= th && abs(v - p[-3 * WP]) <= th) && !(abs(v - p[3]) <= th && abs(v - p[-3]) <= th);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    int base = 0;
+    if ((tid & 31) == 0 && m) base = atomicAdd(&nlist, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (pass) list[base + __popc(m & ((1u << (tid & 31)) - 1u))] = (unsigned short)i;
+  }
+  __syncthreads();
+  const int nl = nlist;
+  for (int j = tid; j < nl; j += 128) {
+    const int i = list[j];
+    const int y = __float2int_rz(__fmul_rn((float)i + 0.5f, inv_dw)), x = i - y * dw;
     sc[(y + 3) * WP + x + 3] = (uint8_t)fast_score_px(&win[(y + 3) * WP + x + 3], WP, P.minTh);
   }
   __syncthreads();
@@ -170,7 +195,7 @@ __global__ void __launch_bounds__(128) k_fast_cells(OrbParams P, const CellInfo*
   const int ppt = (npx + 127) / 128;   // contiguous chunk per thread, row-major order
   const int beg = tid * ppt, end = min(beg + ppt, npx);
   for (int i = beg; i < end; i++) {
-    int y = i / dw, x = i - y * dw;
+    int y = __float2int_rz(__fmul_rn((float)i + 0.5f, inv_dw)), x = i - y * dw;
     const uint8_t* s = &sc[(y + 3) * WP + x + 3];
     int v = s[0];
     uint8_t f = 0;
@@ -200,7 +225,7 @@ __global__ void __launch_bounds__(128) k_fast_cells(OrbParams P, const CellInfo*
   for (int k = 0; k < nfl; k++) {
     if (fl[k] >= need) {
       int i = beg + k;
-      int y = i / dw, x = i - y * dw;
+      int y = __float2int_rz(__fmul_rn((float)i + 0.5f, inv_dw)), x = i - y * dw;
       if (pos < P.slotcap)
         out[pos] = (uint32_t)(x + 3 + c.sx) | ((uint32_t)(y + 3 + c.sy) << 12) | ((uint32_t)sc[(y + 3) * WP + x + 3] << 24);
       pos++;

@@ -65,7 +65,7 @@ __device__ __forceinline__ void se3_map(const SE3& T, const double X[3], double 
   quat_rotate(T.r, X, out);
   out[0] += T.t[0]; out[1] += T.t[1]; out[2] += T.t[2];
 }
-static __device__ SE3 se3_exp(const double u[6]) {
+static __device__ __noinline__ SE3 se3_exp(const double u[6]) {
   const double* w = u;
   const double* up = u + 3;
   double theta = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
@@ -92,7 +92,7 @@ static __device__ SE3 se3_exp(const double u[6]) {
   quat_normalize(T.r);
   return T;
 }
-static __device__ SE3 se3_mul(const SE3& a, const SE3& b) {
+static __device__ __noinline__ SE3 se3_mul(const SE3& a, const SE3& b) {
   SE3 r;
   double rt[3];
   quat_rotate(a.r, b.t, rt);

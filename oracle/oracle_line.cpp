@@ -100,6 +100,8 @@ struct RegionPoint { int x, y; double angle, modgrad; };
 struct Rect { double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p; };
 struct NormPoint { int px, py, norm; };
 
+long g_stat[8] = {0};  // debug statistics: region_grow calls, points added, regions >= min size, refine regrows, ...
+
 struct Lsd {
   int w = 0, h = 0, order_mode = 0;
   std::vector<uint8_t> scaled, used;
@@ -160,6 +162,7 @@ struct Lsd {
 
   void region_grow(int sx, int sy, std::vector<RegionPoint>& reg, double& reg_angle, double prec) {
     reg.clear();
+    g_stat[0]++;
     RegionPoint seed;
     seed.x = sx; seed.y = sy;
     reg_angle = angles[(size_t)sy * w + sx];
@@ -180,6 +183,7 @@ struct Lsd {
             RegionPoint rp;
             rp.x = xx; rp.y = yy; rp.modgrad = modgrad[(size_t)yy * w + xx]; rp.angle = angle;
             reg.push_back(rp);
+            g_stat[1]++;
             sumdx += cosf(float(angle));
             sumdy += sinf(float(angle));
             reg_angle = fast_atan2(sumdy, sumdx) * DEG_TO_RADS;
@@ -268,6 +272,7 @@ struct Lsd {
       }
     }
     double mean_angle = sum / double(n);
+    g_stat[3]++;
     double tau = 2.0 * std::sqrt((s_sum - 2.0 * mean_angle * sum) / double(n) + mean_angle * mean_angle);
     region_grow(reg[0].x, reg[0].y, reg, reg_angle, tau);
     if (reg.size() < 2) return false;
@@ -297,7 +302,10 @@ struct Lsd {
       if (used[(size_t)py * w + px] == NOTUSED && angles[(size_t)py * w + px] != NOTDEF) {
         double reg_angle;
         region_grow(px, py, reg, reg_angle, prec);
+        if (reg.size() == 1) g_stat[4]++;
+        if (reg.size() <= 3) g_stat[5]++;
         if (reg.size() < min_reg_size) continue;
+        g_stat[2]++;
         Rect rec;
         region2rect(reg, reg_angle, prec, p, rec);
         if (!refine(reg, reg_angle, prec, p, rec, DENSITY_TH)) continue;
@@ -479,6 +487,7 @@ struct Lbd {
 }  // namespace
 
 extern "C" {
+void oracle_lsd_stats(long* out, int reset) { for (int i = 0; i < 8; i++) { out[i] = g_stat[i]; if (reset) g_stat[i] = 0; } }
 // cv::createLineSegmentDetector()->detect(img): returns number of segments; lines receives 4 floats each
 int oracle_lsd_detect(const uint8_t* img, int w, int h, int order_mode, float* lines, int cap) {
   Lsd l;

@@ -268,10 +268,10 @@ __device__ __forceinline__ double angle_diff_signed(double a, double b) {
   return diff;
 }
 __device__ __forceinline__ bool is_aligned(double a, double theta, double prec) {
-  double n_theta = theta - a;
-  if (n_theta < 0) n_theta = -n_theta;
-  if (n_theta > (3 * kPI) / 2) { n_theta -= 2 * kPI; if (n_theta < 0) n_theta = -n_theta; }
-  return n_theta <= prec;
+  // branch-free form of LineSegmentDetectorImpl::isAligned (same values: |theta-a|, folded once at 3pi/2)
+  const double n1 = fabs(theta - a);
+  const double n2 = fabs(n1 - 2 * kPI);
+  return ((n1 > (3 * kPI) / 2) ? n2 : n1) <= prec;
 }
 
 // LineSegmentDetectorImpl::region_grow — exact visiting order; returns the region size, region in C.R[0..n).
@@ -296,6 +296,7 @@ __device__ __noinline__ int region_grow(const GrowCtx& C, unsigned seed, double 
     int idx = -1;
     unsigned pk = 0;
     float ang = kNotDefDeg;
+    float2 csv = make_float2(0.f, 0.f);
     if (grp < m) {
       const int qi = i + grp;
       const unsigned p = (cnt - qi <= kRing) ? C.ring[qi & (kRing - 1)] : C.R[qi];
@@ -305,6 +306,7 @@ __device__ __noinline__ int region_grow(const GrowCtx& C, unsigned seed, double 
         pk = (unsigned)xx | ((unsigned)yy << 16);
         if (!used_get(C, idx)) {
           ang = __ldg(&C.ANG[idx]);
+          csv = __ldg(&C.CS[idx]);         // prefetched with the angle: no dependent load on the commit path
           valid = (ang != kNotDefDeg);
         }
       }
@@ -321,11 +323,10 @@ __device__ __noinline__ int region_grow(const GrowCtx& C, unsigned seed, double 
       const int k = __ffs(al) - 1;
       const unsigned pkk = __shfl_sync(0xffffffffu, pk, k);
       const int ikk = (int)(pkk >> 16) * C.sw + (int)(pkk & 0xffffu);
-      const float2 csk = __ldg(&C.CS[ikk]);            // cos/sin of the added pixel: read once per added pixel
       if (lane == 0) { used_set1(C, ikk); C.R[cnt] = pkk; C.ring[cnt & (kRing - 1)] = pkk; }
       cnt++;
-      sumdx = __fadd_rn(sumdx, csk.x);
-      sumdy = __fadd_rn(sumdy, csk.y);
+      sumdx = __fadd_rn(sumdx, __shfl_sync(0xffffffffu, csv.x, k));
+      sumdy = __fadd_rn(sumdy, __shfl_sync(0xffffffffu, csv.y, k));
       reg_angle = (double)fast_atan2_deg_l(sumdy, sumdx) * kDegToRads;
       live &= ~((2u << k) - 1u);                                   // everything up to k has been decided
       live &= ~__ballot_sync(0xffffffffu, pk == pkk && idx >= 0);  // the same pixel in a later 3x3 is now USED
@@ -593,33 +594,45 @@ __global__ void __launch_bounds__(256) k_keylines(LineParams P, const float4* __
 }
 
 // ---------------------------------------------------------------------------------------------- K_H LBD blur + Sobel
-// 32x32 output tile <- 34x34 blurred pixels (5x5 taps read through L1; Sobel reflects the BLURRED image, so blurred
-// values are evaluated at reflect-101 coordinates)
+// 32x32 output tile <- 34x34 blurred pixels <- 38x38 raw pixels staged in shared memory.  Sobel reflects the BLURRED
+// image (BORDER_REFLECT_101), so blurred values are evaluated at reflect-101 coordinates; the blur reflects the raw
+// image.  Both reflections stay inside the staged window [X0-3, X0+35) x [Y0-3, Y0+35) clipped to the image.
 __global__ void __launch_bounds__(256) k_lbd_sobel(LineParams P, const uint8_t* __restrict__ imgs, int stride,
-                                                   long long frame_stride, short* __restrict__ dxo, short* __restrict__ dyo) {
+                                                   long long frame_stride, short2* __restrict__ dxy) {
+  __shared__ uint8_t raw[38][40];
+  __shared__ uint16_t hp[38][36];
   __shared__ uint8_t bl[34][36];
   const int tid = threadIdx.x, X0 = blockIdx.x * 32, Y0 = blockIdx.y * 32;
   const uint8_t* img = imgs + (long long)blockIdx.z * frame_stride;
   auto r101 = [](int p, int n) { if (p < 0) p = -p; if (p >= n) p = 2 * (n - 1) - p; return p; };
-  // Because Sobel reflects the BLURRED image (not the raw one), blurred values are computed at reflected coordinates:
+  for (int i = tid; i < 38 * 38; i += 256) {
+    const int r = i / 38, c = i - r * 38;
+    const int gy = min(max(Y0 - 3 + r, 0), P.h - 1), gx = min(max(X0 - 3 + c, 0), P.w - 1);   // clipped window (clamped entries unused)
+    raw[r][c] = img[(long long)gy * stride + gx];
+  }
+  __syncthreads();
+  // horizontal pass at the reflected blurred columns, for every staged row
+  for (int i = tid; i < 38 * 34; i += 256) {
+    const int r = i / 34, c = i - r * 34;
+    const int bx = r101(min(max(X0 - 1 + c, -1), P.w), P.w);
+    unsigned h = 0;
+    const int t5[5] = {14, 62, 104, 62, 14};
+#pragma unroll
+    for (int k = -2; k <= 2; k++) h += raw[r][r101(bx + k, P.w) - (X0 - 3)] * t5[k + 2];
+    hp[r][c] = (uint16_t)h;
+  }
+  __syncthreads();
   for (int i = tid; i < 34 * 34; i += 256) {
-    int r = i / 34, c = i - r * 34;
-    const int by = r101(min(max(Y0 - 1 + r, -1), P.h), P.h), bx = r101(min(max(X0 - 1 + c, -1), P.w), P.w);
+    const int r = i / 34, c = i - r * 34;
+    const int by = r101(min(max(Y0 - 1 + r, -1), P.h), P.h);
     unsigned acc = 0;
     const int t5[5] = {14, 62, 104, 62, 14};
 #pragma unroll
-    for (int ky = -2; ky <= 2; ky++) {
-      const uint8_t* row = img + (long long)r101(by + ky, P.h) * stride;
-      unsigned h = 0;
-#pragma unroll
-      for (int kx = -2; kx <= 2; kx++) h += row[r101(bx + kx, P.w)] * t5[kx + 2];
-      acc += h * t5[ky + 2];
-    }
+    for (int k = -2; k <= 2; k++) acc += (unsigned)hp[r101(by + k, P.h) - (Y0 - 3)][c] * t5[k + 2];
     bl[r][c] = (uint8_t)((acc + 32768u) >> 16);
   }
   __syncthreads();
-  short* DX = dxo + (long long)blockIdx.z * P.w * P.h;
-  short* DY = dyo + (long long)blockIdx.z * P.w * P.h;
+  short2* D = dxy + (long long)blockIdx.z * P.w * P.h;
   for (int i = tid; i < 32 * 32; i += 256) {
     int ty = i >> 5, tx = i & 31, x = X0 + tx, y = Y0 + ty;
     if (x >= P.w || y >= P.h) continue;
@@ -627,8 +640,8 @@ __global__ void __launch_bounds__(256) k_lbd_sobel(LineParams P, const uint8_t* 
     int a00 = bl[r - 1][c - 1], a01 = bl[r - 1][c], a02 = bl[r - 1][c + 1];
     int a10 = bl[r][c - 1], a12 = bl[r][c + 1];
     int a20 = bl[r + 1][c - 1], a21 = bl[r + 1][c], a22 = bl[r + 1][c + 1];
-    DX[(long long)y * P.w + x] = (short)((a02 - a00) + 2 * (a12 - a10) + (a22 - a20));
-    DY[(long long)y * P.w + x] = (short)((a20 - a00) + 2 * (a21 - a01) + (a22 - a02));
+    D[(long long)y * P.w + x] = make_short2((short)((a02 - a00) + 2 * (a12 - a10) + (a22 - a20)),
+                                            (short)((a20 - a00) + 2 * (a21 - a01) + (a22 - a02)));
   }
 }
 
@@ -638,16 +651,14 @@ __constant__ float c_gaussL[21];
 __constant__ unsigned char c_comb[64];
 
 __global__ void __launch_bounds__(64) k_lbd_describe(LineParams P, const PLKeyLineRec* __restrict__ kls, const int* __restrict__ nl,
-                                                     const short* __restrict__ dxi, const short* __restrict__ dyi,
-                                                     uint8_t* __restrict__ desc) {
+                                                     const short2* __restrict__ dxyi, uint8_t* __restrict__ desc) {
   __shared__ float rs[63][8];
   __shared__ float band[8][9];
   __shared__ float des[72];
   const int li = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
   if (li >= nl[f]) return;
   const PLKeyLineRec kl = kls[(long long)f * P.capL + li];
-  const short* DX = dxi + (long long)f * P.w * P.h;
-  const short* DY = dyi + (long long)f * P.w * P.h;
+  const short2* DXY = dxyi + (long long)f * P.w * P.h;
   const short realWidth = (short)P.w, imageWidth = (short)(P.w - 1), imageHeight = (short)(P.h - 1);
   const short lengthOfLSP = (short)kl.numOfPixels;
   const short halfHeight = (63 - 1) / 2, halfWidth = (short)((lengthOfLSP - 1) / 2);
@@ -668,7 +679,8 @@ __global__ void __launch_bounds__(64) k_lbd_describe(LineParams P, const PLKeyLi
       const short xCor = (t < 0) ? 0 : (t > imageWidth) ? imageWidth : t;
       t = (short)roundf(sCorY);
       const short yCor = (t < 0) ? 0 : (t > imageHeight) ? imageHeight : t;
-      const short ddx = DX[(int)yCor * realWidth + xCor], ddy = DY[(int)yCor * realWidth + xCor];
+      const short2 g2 = __ldg(&DXY[(int)yCor * realWidth + xCor]);
+      const short ddx = g2.x, ddy = g2.y;
       const float gDL = __fadd_rn(__fmul_rn((float)ddx, dL0), __fmul_rn((float)ddy, dL1));
       const float gDO = __fadd_rn(__fmul_rn((float)ddx, dO0), __fmul_rn((float)ddy, dO1));
       if (gDL > 0) pgdL = __fadd_rn(pgdL, gDL); else ngdL = __fsub_rn(ngdL, gDL);
@@ -758,7 +770,7 @@ struct PLLine {
   int *d_offsets = nullptr, *d_ndef = nullptr, *d_maxs = nullptr, *d_nseg = nullptr, *d_overflow = nullptr;
   unsigned *d_order = nullptr, *d_reg = nullptr;
   float4* d_segs = nullptr;
-  short *d_dx = nullptr, *d_dy = nullptr;
+  short2* d_dxy = nullptr;
   // host-pointer API staging
   uint8_t* d_img = nullptr; PLKeyLineRec* d_kls = nullptr; uint8_t* d_desc = nullptr; double* d_lf = nullptr; int* d_nl = nullptr;
   uint8_t* d_mask = nullptr;
@@ -776,7 +788,7 @@ extern "C" void pl_line_destroy(PLLine* h) {
   if (!h) return;
   cudaFree(h->d_scaled); cudaFree(h->d_seedcs); cudaFree(h->d_ubits); cudaFree(h->d_ang); cudaFree(h->d_cs); cudaFree(h->d_sq); cudaFree(h->d_counts); cudaFree(h->d_offsets);
   cudaFree(h->d_ndef); cudaFree(h->d_maxs); cudaFree(h->d_nseg); cudaFree(h->d_overflow); cudaFree(h->d_order);
-  cudaFree(h->d_reg); cudaFree(h->d_segs); cudaFree(h->d_dx); cudaFree(h->d_dy); cudaFree(h->d_img); cudaFree(h->d_kls);
+  cudaFree(h->d_reg); cudaFree(h->d_segs); cudaFree(h->d_dxy); cudaFree(h->d_img); cudaFree(h->d_kls);
   cudaFree(h->d_desc); cudaFree(h->d_lf); cudaFree(h->d_nl); cudaFree(h->d_mask);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -814,7 +826,7 @@ extern "C" int pl_line_create(const PLLineConfig* cfg, PLLine** out) {
   LN_TRY(dev_alloc(&h->d_counts, (size_t)kBins * P.nchunk * B)); LN_TRY(dev_alloc(&h->d_offsets, (size_t)kBins * P.nchunk * B));
   LN_TRY(dev_alloc(&h->d_ndef, B)); LN_TRY(dev_alloc(&h->d_maxs, B)); LN_TRY(dev_alloc(&h->d_nseg, B)); LN_TRY(dev_alloc(&h->d_overflow, 1));
   LN_TRY(dev_alloc(&h->d_order, npx * B)); LN_TRY(dev_alloc(&h->d_reg, npx * B)); LN_TRY(dev_alloc(&h->d_segs, (size_t)P.seg_cap * B));
-  LN_TRY(dev_alloc(&h->d_dx, (size_t)P.w * P.h * B)); LN_TRY(dev_alloc(&h->d_dy, (size_t)P.w * P.h * B));
+  LN_TRY(dev_alloc(&h->d_dxy, (size_t)P.w * P.h * B));
   LN_CUDA(cudaMemset(h->d_overflow, 0, sizeof(int)));
   {  // LBD weights (binary_descriptor_custom.cpp:217-259), integer divisions as in the reference
     float gG[63], gL[21];
@@ -883,9 +895,9 @@ extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int str
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev1, st));
   k_keylines<<<B, 256, h->key_smem, st>>>(P, h->d_segs, h->d_nseg, mask, (PLKeyLineRec*)keylines, linefunc, n);
   PL_LAUNCH_CHECK();
-  k_lbd_sobel<<<dim3((P.w + 31) / 32, (P.h + 31) / 32, B), 256, 0, st>>>(P, imgs, stride, (long long)frame_stride, h->d_dx, h->d_dy);
+  k_lbd_sobel<<<dim3((P.w + 31) / 32, (P.h + 31) / 32, B), 256, 0, st>>>(P, imgs, stride, (long long)frame_stride, h->d_dxy);
   PL_LAUNCH_CHECK();
-  k_lbd_describe<<<dim3(P.capL, B), 64, 0, st>>>(P, (const PLKeyLineRec*)keylines, n, h->d_dx, h->d_dy, desc);
+  k_lbd_describe<<<dim3(P.capL, B), 64, 0, st>>>(P, (const PLKeyLineRec*)keylines, n, h->d_dxy, desc);
   PL_LAUNCH_CHECK();
   return PL_OK;
 }
@@ -951,8 +963,9 @@ extern "C" int pl_line_debug_sobel(PLLine* h, int frame, short* dx, short* dy) {
   PL_ARG(h && frame >= 0 && frame < h->last_B && dx && dy);
   const size_t n = (size_t)h->P.w * h->P.h;
   PL_CUDA(cudaStreamSynchronize(h->stream));
-  PL_CUDA(cudaMemcpy(dx, h->d_dx + frame * n, n * 2, cudaMemcpyDeviceToHost));
-  PL_CUDA(cudaMemcpy(dy, h->d_dy + frame * n, n * 2, cudaMemcpyDeviceToHost));
+  std::vector<short2> tmp(n);
+  PL_CUDA(cudaMemcpy(tmp.data(), h->d_dxy + frame * n, n * sizeof(short2), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; i++) { dx[i] = tmp[i].x; dy[i] = tmp[i].y; }
   return PL_OK;
 }
 extern "C" int pl_line_debug_order(PLLine* h, int frame, unsigned* out, int cap) {

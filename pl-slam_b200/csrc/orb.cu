@@ -150,10 +150,13 @@ __global__ void __launch_bounds__(128) k_fast_cells(OrbParams P, const CellInfo*
   if (c.level == 0) { img = img0 + (long long)frame * frame0; pitch = stride0; }
   else { img = pyr + (long long)frame * P.pyr_frame + L.off; pitch = L.pitch; }
   const int w = c.x1 - c.x0, h = c.y1 - c.y0;
-  for (int i = tid; i < w * h; i += 128) {
-    int y = i / w, x = i - y * w;
-    win[y * WP + x] = img[(long long)(c.y0 + y) * pitch + c.x0 + x];
-    sc[y * WP + x] = 0;
+  {
+    const float inv_w = 1.0f / (float)w;               // i / w for i < 72*72 without an integer division
+    for (int i = tid; i < w * h; i += 128) {
+      const int y = __float2int_rz(__fmul_rn((float)i + 0.5f, inv_w)), x = i - y * w;
+      win[y * WP + x] = img[(long long)(c.y0 + y) * pitch + c.x0 + x];
+      sc[y * WP + x] = 0;
+    }
   }
   __syncthreads();
   const int dw = w - 6, dh = h - 6;  // detection area

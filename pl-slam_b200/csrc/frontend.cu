@@ -27,6 +27,9 @@ struct PLFrontend {
   PLOrb* orb = nullptr;
   PLLine* line = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t sLine = nullptr, sLm = nullptr;      // side streams: LSD/LBD chain and the LM run beside the ORB chain
+  cudaEvent_t evStart = nullptr, evLine = nullptr, evLm = nullptr;
+  int overlap = 0;
   int B = 0, capK = 0, capL = 0;
   // device-resident per-batch state
   uint8_t* d_img = nullptr;
@@ -53,6 +56,11 @@ extern "C" void pl_frontend_destroy(PLFrontend* h) {
                   h->d_inl, h->d_its, h->d_pout, h->d_lout};
   for (void* p : ptrs) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->sLine) cudaStreamDestroy(h->sLine);
+  if (h->sLm) cudaStreamDestroy(h->sLm);
+  if (h->evStart) cudaEventDestroy(h->evStart);
+  if (h->evLine) cudaEventDestroy(h->evLine);
+  if (h->evLm) cudaEventDestroy(h->evLm);
   delete h;
 }
 
@@ -71,6 +79,14 @@ extern "C" int pl_frontend_create(const PLFrontendConfig* cfg, PLFrontend** out)
   FE_TRY(pl_line_create(&lc, &h->line));
   h->capK = pl_orb_capacity(h->orb); h->capL = pl_line_capacity(h->line);
   FE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  FE_CUDA(cudaStreamCreateWithFlags(&h->sLine, cudaStreamNonBlocking));
+  FE_CUDA(cudaStreamCreateWithFlags(&h->sLm, cudaStreamNonBlocking));
+  FE_CUDA(cudaEventCreateWithFlags(&h->evStart, cudaEventDisableTiming));
+  FE_CUDA(cudaEventCreateWithFlags(&h->evLine, cudaEventDisableTiming));
+  FE_CUDA(cudaEventCreateWithFlags(&h->evLm, cudaEventDisableTiming));
+  // measured on B200 (B=4736): running the three chains on separate streams gains nothing (the region-growing kernel
+  // already fills the register file with 32 warps per SM), so the default is one stream; PLSLAM_FRONTEND_OVERLAP=1 enables it
+  { const char* e = getenv("PLSLAM_FRONTEND_OVERLAP"); h->overlap = (e && e[0] == '1'); }
   const size_t B = h->B, cK = h->capK, cL = h->capL, cp = cfg->lm_cap_points, cl = cfg->lm_cap_lines;
   FE_TRY(dev_alloc(&h->d_img, (size_t)cfg->width * cfg->height * B));
   // feature arrays hold B+1 frames: slot 0 = copy of the batch's last frame ("previous" of frame 0), slots 1..B = frames
@@ -130,26 +146,42 @@ extern "C" int pl_frontend_run_dev(PLFrontend* h, const uint8_t* imgs, int strid
   if (!imgs) { imgs = h->d_img; stride = h->cfg.width; frame_stride = (size_t)h->cfg.width * h->cfg.height; }
   const size_t cK = h->capK, cL = h->capL;
   int rc;
+  const size_t cp = h->cfg.lm_cap_points, cl = h->cfg.lm_cap_lines;
+  // Three independent chains, like the reference's per-frame std::threads (Frame.cc:224-227): the line chain (LSD grow is
+  // latency bound and leaves issue slots free), the ORB + point-matching chain, and the two pose optimisations.
+  cudaStream_t sL = h->overlap ? h->sLine : st, sM = h->overlap ? h->sLm : st;
+  if (h->overlap) {
+    PL_CUDA(cudaEventRecord(h->evStart, st));
+    PL_CUDA(cudaStreamWaitEvent(sL, h->evStart, 0));
+    PL_CUDA(cudaStreamWaitEvent(sM, h->evStart, 0));
+  }
+  // --- line chain
+  if ((rc = pl_line_extract_batch_dev(h->line, imgs, stride, frame_stride, B, nullptr, h->d_kl, h->d_ldesc, h->d_lf, h->d_nl, sL))) return rc;
+  PL_CUDA(cudaMemcpyAsync(h->d_ldesc_prev, h->d_ldesc + cL * 32 * (B - 1), cL * 32, cudaMemcpyDeviceToDevice, sL));
+  PL_CUDA(cudaMemcpyAsync(h->d_nl_prev, h->d_nl + (B - 1), sizeof(int), cudaMemcpyDeviceToDevice, sL));
+  if ((rc = pl_lsd_search_double_dev(h->d_ldesc_prev, h->d_nl_prev, h->d_ldesc, h->d_nl, (int)cL, (int)cL, B, 50.f, 0.7f, 1, h->d_lm,
+                                     h->d_nlm, sL))) return rc;
+  // --- ORB chain (slot 0 <- frame B-1 so that frame b's predecessor is slot b, a plain offset)
   if ((rc = pl_orb_extract_batch_dev(h->orb, imgs, stride, frame_stride, B, h->d_kps, h->d_desc, h->d_n, st))) return rc;
-  if ((rc = pl_line_extract_batch_dev(h->line, imgs, stride, frame_stride, B, nullptr, h->d_kl, h->d_ldesc, h->d_lf, h->d_nl, st))) return rc;
-  // slot 0 <- frame B-1 so that frame b's predecessor is slot b (a plain offset)
   PL_CUDA(cudaMemcpyAsync(h->d_kps_prev, h->d_kps + cK * (B - 1), cK * sizeof(PLKeyPoint), cudaMemcpyDeviceToDevice, st));
   PL_CUDA(cudaMemcpyAsync(h->d_desc_prev, h->d_desc + cK * 32 * (B - 1), cK * 32, cudaMemcpyDeviceToDevice, st));
   PL_CUDA(cudaMemcpyAsync(h->d_n_prev, h->d_n + (B - 1), sizeof(int), cudaMemcpyDeviceToDevice, st));
-  PL_CUDA(cudaMemcpyAsync(h->d_ldesc_prev, h->d_ldesc + cL * 32 * (B - 1), cL * 32, cudaMemcpyDeviceToDevice, st));
-  PL_CUDA(cudaMemcpyAsync(h->d_nl_prev, h->d_nl + (B - 1), sizeof(int), cudaMemcpyDeviceToDevice, st));
   k_prev_matched_init<<<dim3((unsigned)((cK + 127) / 128), B), 128, 0, st>>>(h->d_kps, h->d_n, (int)cK, B, h->d_pm);
   PL_LAUNCH_CHECK();
   if ((rc = pl_orb_search_for_initialization_dev(h->d_kps_prev, h->d_desc_prev, h->d_n_prev, h->d_kps, h->d_desc, h->d_n, (int)cK, B,
                                                  h->d_bounds, h->d_pm, h->d_m12, h->d_nm, 100, 0.9f, 1, h->d_scr, st))) return rc;
-  if ((rc = pl_lsd_search_double_dev(h->d_ldesc_prev, h->d_nl_prev, h->d_ldesc, h->d_nl, (int)cL, (int)cL, B, 50.f, 0.7f, 1, h->d_lm,
-                                     h->d_nlm, st))) return rc;
-  const size_t cp = h->cfg.lm_cap_points, cl = h->cfg.lm_cap_lines;
-  for (int call = 0; call < 2; call++)   // TrackWithMotionModel (Tracking.cc:1372) and TrackLocalMapWithLines (:1503)
+  // --- pose optimisations: TrackWithMotionModel (Tracking.cc:1372) and TrackLocalMapWithLines (:1503)
+  for (int call = 0; call < 2; call++)
     if ((rc = pl_pose_optimization_dev(0, B, h->d_T0, h->d_K, h->d_np, (int)cp, h->d_pobs, h->d_pw, h->d_pX, h->d_nl_lm, (int)cl,
                                        h->d_lfun, h->d_lX, h->d_Tout + 16 * (size_t)B * call, h->d_pout + cp * B * call,
                                        h->d_lout + cl * B * call, h->d_inl + (size_t)B * call, h->d_its + (size_t)B * call,
-                                       h->d_scratch, st))) return rc;
+                                       h->d_scratch, sM))) return rc;
+  if (h->overlap) {
+    PL_CUDA(cudaEventRecord(h->evLine, sL));
+    PL_CUDA(cudaEventRecord(h->evLm, sM));
+    PL_CUDA(cudaStreamWaitEvent(st, h->evLine, 0));
+    PL_CUDA(cudaStreamWaitEvent(st, h->evLm, 0));
+  }
   return PL_OK;
 }
 

@@ -447,11 +447,12 @@ template <bool kSmemUsed>
 __global__ void __launch_bounds__(32, 32) k_lsd_grow(LineParams P, unsigned* __restrict__ gbits, const float* __restrict__ ANG, const float2* __restrict__ CS, const int* __restrict__ SQ, const float2* __restrict__ seedcs,
                                                  const unsigned* __restrict__ order, const int* __restrict__ ndef,
                                                  unsigned* __restrict__ reg, float4* __restrict__ segs,
-                                                 int* __restrict__ nseg, int* __restrict__ overflow) {
+                                                 int* __restrict__ nseg, int* __restrict__ overflow, int nframes) {
   __shared__ unsigned ring[kRing];
   extern __shared__ unsigned sbits[];            // USED bitmap of the scaled image: (npx+31)/32 words
-  const int f = blockIdx.x, lane = threadIdx.x;
+  const int lane = threadIdx.x;
   const int nwords = (P.npx + 31) / 32;
+  for (int f = blockIdx.x; f < nframes; f += gridDim.x) {   // persistent: the grid size caps the resident warps per SM
   // The bitmap lives in shared memory (fast, but 24.6 KB per warp caps the SM at 8 frames) or in global memory / L1
   // (slower per access, but up to 28 frames per SM hide the latency): chosen at handle creation.
   unsigned* ubits = kSmemUsed ? sbits : gbits + (long long)f * nwords;
@@ -491,6 +492,8 @@ __global__ void __launch_bounds__(32, 32) k_lsd_grow(LineParams P, unsigned* __r
     }
   }
   if (lane == 0) { nseg[f] = min(ns, P.seg_cap); if (ns > P.seg_cap) atomicExch(overflow, 1); }
+  __syncwarp();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- K_G keylines
@@ -764,6 +767,7 @@ struct PLLine {
   float2* d_seedcs = nullptr;
   unsigned* d_ubits = nullptr;
   int used_global = 0;
+  int grow_grid_cap = 1 << 30;   // max CTAs of the persistent grow kernel (env PLSLAM_LSD_GROW_CTAS_PER_SM x #SMs)
   size_t grow_smem = 0;
   float* d_ang = nullptr; float2* d_cs = nullptr; int* d_sq = nullptr;
   unsigned short* d_counts = nullptr;
@@ -844,6 +848,8 @@ extern "C" int pl_line_create(const PLLineConfig* cfg, PLLine** out) {
   { const char* e = getenv("PLSLAM_LSD_USED_GLOBAL");   // default: global (measured 1.6x the throughput of the smem map at B>=2048)
     h->used_global = cfg->lsd_used_in_global > 0 ? 1 : (cfg->lsd_used_in_global < 0 ? 0 : !(e && e[0] == '0')); }
   if (h->used_global) LN_TRY(dev_alloc(&h->d_ubits, (size_t)((P.npx + 31) / 32) * B));
+  { const char* e = getenv("PLSLAM_LSD_GROW_CTAS_PER_SM"); int per = e ? atoi(e) : 0;
+    if (per > 0) { int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); h->grow_grid_cap = per * sms; } }
   LN_CUDA(cudaFuncSetAttribute(k_lsd_grow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grow_smem));
   *out = h;
   return PL_OK;
@@ -888,9 +894,9 @@ extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int str
   PL_LAUNCH_CHECK();
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev0, st));
   if (h->used_global)
-    k_lsd_grow<false><<<B, 32, 0, st>>>(P, h->d_ubits, h->d_ang, h->d_cs, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow);
+    k_lsd_grow<false><<<std::min(B, h->grow_grid_cap), 32, 0, st>>>(P, h->d_ubits, h->d_ang, h->d_cs, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow, B);
   else
-  k_lsd_grow<true><<<B, 32, h->grow_smem, st>>>(P, nullptr, h->d_ang, h->d_cs, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow);
+  k_lsd_grow<true><<<std::min(B, h->grow_grid_cap), 32, h->grow_smem, st>>>(P, nullptr, h->d_ang, h->d_cs, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow, B);
   PL_LAUNCH_CHECK();
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev1, st));
   k_keylines<<<B, 256, h->key_smem, st>>>(P, h->d_segs, h->d_nseg, mask, (PLKeyLineRec*)keylines, linefunc, n);

@@ -100,7 +100,7 @@ struct RegionPoint { int x, y; double angle, modgrad; };
 struct Rect { double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p; };
 struct NormPoint { int px, py, norm; };
 
-long g_stat[8] = {0};  // debug statistics: region_grow calls, points added, regions >= min size, refine regrows, ...
+thread_local long g_stat[8] = {0};  // debug statistics: region_grow calls, points added, regions >= min size, refine regrows, ...
 
 struct Lsd {
   int w = 0, h = 0, order_mode = 0;

@@ -154,9 +154,10 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineParams P, const uint8_t* _
         double sn, cs;
         sincos(af, &sn, &cs);
         rec.x = deg; rec.y = (float)cs; rec.z = (float)sn;
-        const double ad = (double)deg * kDegToRads;      // a region SEEDED here starts from cos/sin of the fp64 angle
-        sincos(ad, &sn, &cs);
-        scs = make_float2((float)cs, (float)sn);
+        // a region SEEDED here starts from cos/sin of the fp64 angle ad = af + dl, |dl| <= half an fp32 ulp (< 4e-7):
+        // angle-addition with cos(dl) = 1 - dl^2/2, sin(dl) = dl is exact to ~1e-27, far below fp64 rounding
+        const double ad = (double)deg * kDegToRads, dl = ad - af, h2 = 1.0 - 0.5 * dl * dl;
+        scs = make_float2((float)(cs * h2 - sn * dl), (float)(sn * h2 + cs * dl));
       } else s = 0;
     }
     const long long o = (long long)f * P.npx + y * P.sw + x;
@@ -667,7 +668,10 @@ __global__ void __launch_bounds__(64) k_lbd_describe(LineParams P, const PLKeyLi
   const short halfHeight = (63 - 1) / 2, halfWidth = (short)((lengthOfLSP - 1) / 2);
   const float midX = (float)(0.5 * (double)__fadd_rn(kl.sPointInOctaveX, kl.ePointInOctaveX));
   const float midY = (float)(0.5 * (double)__fadd_rn(kl.sPointInOctaveY, kl.ePointInOctaveY));
-  const float dL0 = (float)cos((double)kl.angle), dL1 = (float)sin((double)kl.angle);
+  __shared__ float s_dL[2];
+  if (tid == 0) { s_dL[0] = (float)cos((double)kl.angle); s_dL[1] = (float)sin((double)kl.angle); }   // fp64 libm once per line
+  __syncthreads();
+  const float dL0 = s_dL[0], dL1 = s_dL[1];
   const float dO0 = -dL1, dO1 = dL0;
   if (tid < 63) {
     const short hID = (short)tid;

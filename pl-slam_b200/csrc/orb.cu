@@ -634,7 +634,9 @@ __global__ void __launch_bounds__(32 * kDescWarps) k_describe(OrbParams P, const
   // steered BRIEF: lane computes descriptor byte `lane`
   const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
   const float ang = __fmul_rn(angle, factorPI);
-  const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+  float a = 0.f, b = 0.f;
+  if (lane == 0) { a = (float)cos((double)ang); b = (float)sin((double)ang); }   // fp64 libm once per keypoint, not once per lane
+  a = __shfl_sync(0xffffffffu, a, 0); b = __shfl_sync(0xffffffffu, b, 0);
   const uint8_t* ctr = bl + kBlurR * kBlurP + kBlurR;
   int val = 0;
 #pragma unroll

@@ -263,6 +263,35 @@ int pl_lsd_search_by_projection_lines(const void* keylines, const double* linefu
                                       const float* view_cos, const uint8_t* ml_desc, float th, float nnratio,
                                       const uint8_t* preassigned, int* match);
 
+/* ------------------------------------------------------------------ Frame glue
+ * The mono Frame constructor undistorts every frame for the line extractor (initUndistortRectifyMap + remap,
+ * src/Frame.cc:220-222), undistorts the keypoints (UndistortKeyPoints, :915-945) and computes the image bounds
+ * (:947-985); Tracking then projects local map points / lines with Frame::isInFrustum (:560-702).  K = {fx,fy,cx,cy},
+ * dist5 = {k1,k2,p1,p2,k3} exactly as Tracking.cc:53-120 fills mK / mDistCoef (float).                         */
+typedef struct PLUndistort PLUndistort;
+int pl_undistort_create(const float* K, const float* dist5, int width, int height, PLUndistort** out);   /* builds the map once */
+void pl_undistort_destroy(PLUndistort* h);
+/* cv::remap(src, dst, mUndistX, mUndistY, INTER_LINEAR) */
+int pl_undistort_remap(PLUndistort* h, const uint8_t* src, int sstride, uint8_t* dst, int dstride);
+int pl_undistort_remap_batch_dev(PLUndistort* h, const uint8_t* src, int sstride, size_t sframe, int B, uint8_t* dst,
+                                 int dstride, size_t dframe, void* stream);
+/* Frame::UndistortKeyPoints: only pt.x / pt.y change; k1 == 0 copies */
+int pl_undistort_keypoints(PLUndistort* h, const PLKeyPoint* kps, int n, PLKeyPoint* out);
+int pl_undistort_keypoints_dev(PLUndistort* h, const PLKeyPoint* kps, const int* n, int cap, int B, PLKeyPoint* out, void* stream);
+/* Frame::ComputeImageBounds -> {mnMinX, mnMinY, mnMaxX, mnMaxY} */
+int pl_frame_image_bounds(const float* K, const float* dist5, int width, int height, float* bounds);
+/* Frame::isInFrustum(MapPoint*, viewingCosLimit) for n map points: pos = GetWorldPos, normal = GetNormal,
+ * min/max_dist = Get{Min,Max}DistanceInvariance; Tcw row-major 4x4, Ow = mOw.  Outputs mbTrackInView, {mTrackProjX,Y},
+ * mnTrackScaleLevel, mTrackViewCos. */
+int pl_frame_is_in_frustum_points(const float* Tcw, const float* Ow, const float* K, const float* bounds, float log_scale_factor,
+                                  int n_scale_levels, float viewing_cos_limit, int n, const float* pos, const float* normal,
+                                  const float* min_dist, const float* max_dist, uint8_t* inview, float* proj, int* level,
+                                  float* viewcos);
+/* Frame::isInFrustum(MapLine*, viewingCosLimit): pos = mWorldPos (6 doubles), normal = GetNormal (3 doubles); proj = {X1,Y1,X2,Y2} */
+int pl_frame_is_in_frustum_lines(const float* Tcw, const float* Ow, const float* K, const float* bounds, float log_scale_factor,
+                                 float viewing_cos_limit, int n, const double* pos, const double* normal, const float* min_dist,
+                                 const float* max_dist, uint8_t* inview, float* proj, int* level, float* viewcos);
+
 #ifdef __cplusplus
 }
 #endif

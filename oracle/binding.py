@@ -379,3 +379,75 @@ def line_search_by_projection_lines(kl68, lfunc, desc, bounds, in_view, proj, vi
     pre = None if preassigned is None else np.ascontiguousarray(preassigned, np.uint8)
     nm = f(_p(k), _p(a[0]), _p(a[1]), len(k), _p(a[2]), len(a[3]), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6]), th, nnratio, _p(pre), _p(m))
     return nm, m[:len(k)]
+
+
+# ----------------------------------------------------------------- Frame glue (oracle_frame.cpp; reference src/Frame.cc)
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def undistort_map(K, D, w, h):
+    """cv::initUndistortRectifyMap(K, D, I, K, (w,h), CV_32F) (Frame.cc:220)."""
+    mx = np.empty((h, w), np.float32); my = np.empty((h, w), np.float32)
+    K = _f32(K); D = _f32(D)
+    lib().oracle_undistort_map(_p(K), _p(D), C.c_int(w), C.c_int(h), _p(mx), _p(my))
+    return mx, my
+
+
+def remap_linear(src, mx, my):
+    """cv::remap(src, dst, mx, my, INTER_LINEAR) with BORDER_CONSTANT 0 (Frame.cc:221)."""
+    src = np.ascontiguousarray(src, np.uint8); h, w = src.shape
+    dst = np.empty_like(src)
+    mx = _f32(mx); my = _f32(my)
+    lib().oracle_remap(_p(src), C.c_int(w), C.c_int(h), _p(mx), _p(my), _p(dst))
+    return dst
+
+
+def undistort_remap(src, K, D):
+    src = np.ascontiguousarray(src, np.uint8); h, w = src.shape
+    dst = np.empty_like(src)
+    K = _f32(K); D = _f32(D)
+    lib().oracle_undistort_remap(_p(src), C.c_int(w), C.c_int(h), _p(K), _p(D), _p(dst))
+    return dst
+
+
+def undistort_keypoints(kps, K, D):
+    """Frame::UndistortKeyPoints (Frame.cc:915-945)."""
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    out = np.empty_like(kps)
+    K = _f32(K); D = _f32(D)
+    lib().oracle_undistort_keypoints(_p(kps), C.c_int(len(kps)), _p(K), _p(D), _p(out))
+    return out
+
+
+def image_bounds(K, D, w, h):
+    """Frame::ComputeImageBounds (Frame.cc:947-985) -> [minX, minY, maxX, maxY]."""
+    b = np.empty(4, np.float32)
+    K = _f32(K); D = _f32(D)
+    lib().oracle_image_bounds(_p(K), _p(D), C.c_int(w), C.c_int(h), _p(b))
+    return b
+
+
+def is_in_frustum_points(Tcw, Ow, K, bounds, log_scale_factor, n_levels, cos_limit, pos, normal, min_dist, max_dist):
+    """Frame::isInFrustum(MapPoint*) (Frame.cc:560-620)."""
+    n = len(pos)
+    Tcw = _f32(Tcw); Ow = _f32(Ow); K = _f32(K); bounds = _f32(bounds)
+    pos = _f32(pos); normal = _f32(normal); min_dist = _f32(min_dist); max_dist = _f32(max_dist)
+    inview = np.zeros(n, np.uint8); proj = np.zeros((n, 2), np.float32); level = np.zeros(n, np.int32); vc = np.zeros(n, np.float32)
+    lib().oracle_is_in_frustum_points(_p(Tcw), _p(Ow), _p(K), _p(bounds), C.c_float(log_scale_factor), C.c_int(n_levels),
+                                      C.c_float(cos_limit), C.c_int(n), _p(pos), _p(normal), _p(min_dist), _p(max_dist),
+                                      _p(inview), _p(proj), _p(level), _p(vc))
+    return inview, proj, level, vc
+
+
+def is_in_frustum_lines(Tcw, Ow, K, bounds, log_scale_factor, cos_limit, pos, normal, min_dist, max_dist):
+    """Frame::isInFrustum(MapLine*) (Frame.cc:622-702)."""
+    n = len(pos)
+    Tcw = _f32(Tcw); Ow = _f32(Ow); K = _f32(K); bounds = _f32(bounds)
+    pos = np.ascontiguousarray(pos, np.float64); normal = np.ascontiguousarray(normal, np.float64)
+    min_dist = _f32(min_dist); max_dist = _f32(max_dist)
+    inview = np.zeros(n, np.uint8); proj = np.zeros((n, 4), np.float32); level = np.zeros(n, np.int32); vc = np.zeros(n, np.float32)
+    lib().oracle_is_in_frustum_lines(_p(Tcw), _p(Ow), _p(K), _p(bounds), C.c_float(log_scale_factor), C.c_float(cos_limit),
+                                     C.c_int(n), _p(pos), _p(normal), _p(min_dist), _p(max_dist), _p(inview), _p(proj),
+                                     _p(level), _p(vc))
+    return inview, proj, level, vc

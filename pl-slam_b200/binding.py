@@ -565,3 +565,75 @@ def _lsd_search_lines(self, keylines, linefunc, desc, bounds, in_view, proj, vie
 
 LSDmatcher.SearchByProjectionLast = _lsd_search_last
 LSDmatcher.SearchByProjectionLines = _lsd_search_lines
+
+
+# ----------------------------------------------------------------- Frame glue (reference src/Frame.cc)
+class Undistorter:
+    """The undistortion the mono Frame constructor does for every frame (reference src/Frame.cc:220-222:
+    initUndistortRectifyMap + remap) and Frame::UndistortKeyPoints (:915-945); the map is built once per camera."""
+
+    def __init__(self, K, distCoef, width, height):
+        self.K = _f32(K); self.D = _f32(distCoef); self.w = int(width); self.h = int(height)
+        assert self.K.shape == (4,) and self.D.shape == (5,)
+        self.handle = vp()
+        check(lib().pl_undistort_create(_p(self.K), _p(self.D), C.c_int(self.w), C.c_int(self.h), C.byref(self.handle)))
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            lib().pl_undistort_destroy(self.handle); self.handle = None
+
+    def remap(self, image):
+        img = _u8(image)
+        if img.shape != (self.h, self.w):
+            raise PLError(f"image {img.shape} does not match the undistorter ({self.h}, {self.w})")
+        out = np.empty_like(img)
+        check(lib().pl_undistort_remap(self.handle, _p(img), C.c_int(self.w), _p(out), C.c_int(self.w)))
+        return out
+
+    def remap_batch_dev(self, src_ptr, sstride, sframe, B, dst_ptr, dstride, dframe, stream=None):
+        check(lib().pl_undistort_remap_batch_dev(self.handle, vp(src_ptr), C.c_int(sstride), C.c_size_t(sframe), C.c_int(B),
+                                                 vp(dst_ptr), C.c_int(dstride), C.c_size_t(dframe), vp(stream or 0)))
+
+    def UndistortKeyPoints(self, keys):
+        keys = np.ascontiguousarray(keys, KP_DTYPE); out = np.empty_like(keys)
+        check(lib().pl_undistort_keypoints(self.handle, _p(keys), C.c_int(len(keys)), _p(out)))
+        return out
+
+    def undistort_keypoints_dev(self, kps_ptr, n_ptr, cap, B, out_ptr, stream=None):
+        check(lib().pl_undistort_keypoints_dev(self.handle, vp(kps_ptr), vp(n_ptr), C.c_int(cap), C.c_int(B), vp(out_ptr),
+                                               vp(stream or 0)))
+
+    def ComputeImageBounds(self):
+        return ComputeImageBounds(self.K, self.D, self.w, self.h)
+
+
+def ComputeImageBounds(K, distCoef, width, height):
+    """Frame::ComputeImageBounds (reference src/Frame.cc:947-985) -> [mnMinX, mnMinY, mnMaxX, mnMaxY]."""
+    K = _f32(K); D = _f32(distCoef); b = np.empty(4, np.float32)
+    check(lib().pl_frame_image_bounds(_p(K), _p(D), C.c_int(width), C.c_int(height), _p(b)))
+    return b
+
+
+def isInFrustum(Tcw, Ow, K, bounds, log_scale_factor, n_scale_levels, viewingCosLimit, pos, normal, min_dist, max_dist):
+    """Frame::isInFrustum(MapPoint*, viewingCosLimit) over n map points (reference src/Frame.cc:560-620)."""
+    n = len(pos)
+    Tcw = _f32(Tcw); Ow = _f32(Ow); K = _f32(K); bounds = _f32(bounds)
+    pos = _f32(pos); normal = _f32(normal); min_dist = _f32(min_dist); max_dist = _f32(max_dist)
+    inview = np.zeros(n, np.uint8); proj = np.zeros((n, 2), np.float32); level = np.zeros(n, np.int32); vc = np.zeros(n, np.float32)
+    check(lib().pl_frame_is_in_frustum_points(_p(Tcw), _p(Ow), _p(K), _p(bounds), C.c_float(log_scale_factor),
+                                              C.c_int(n_scale_levels), C.c_float(viewingCosLimit), C.c_int(n), _p(pos), _p(normal),
+                                              _p(min_dist), _p(max_dist), _p(inview), _p(proj), _p(level), _p(vc)))
+    return inview, proj, level, vc
+
+
+def isInFrustumLines(Tcw, Ow, K, bounds, log_scale_factor, viewingCosLimit, pos, normal, min_dist, max_dist):
+    """Frame::isInFrustum(MapLine*, viewingCosLimit) over n map lines (reference src/Frame.cc:622-702)."""
+    n = len(pos)
+    Tcw = _f32(Tcw); Ow = _f32(Ow); K = _f32(K); bounds = _f32(bounds)
+    pos = np.ascontiguousarray(pos, np.float64); normal = np.ascontiguousarray(normal, np.float64)
+    min_dist = _f32(min_dist); max_dist = _f32(max_dist)
+    inview = np.zeros(n, np.uint8); proj = np.zeros((n, 4), np.float32); level = np.zeros(n, np.int32); vc = np.zeros(n, np.float32)
+    check(lib().pl_frame_is_in_frustum_lines(_p(Tcw), _p(Ow), _p(K), _p(bounds), C.c_float(log_scale_factor),
+                                             C.c_float(viewingCosLimit), C.c_int(n), _p(pos), _p(normal), _p(min_dist),
+                                             _p(max_dist), _p(inview), _p(proj), _p(level), _p(vc)))
+    return inview, proj, level, vc

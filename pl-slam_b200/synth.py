@@ -72,6 +72,9 @@ def synth_sequence(n, w=640, h=480, seed=1):
 
 # ---------------------------------------------------------------------------------------------- PnP with lines
 TUM1_K = (517.306408, 516.469215, 318.643040, 255.313989)   # Examples/Monocular/TUM1.yaml:8-11
+TUM1_DIST = (0.262383, -0.953104, -0.005358, 0.002628, 1.163314)   # TUM1.yaml:13-17 (k1 k2 p1 p2 k3)
+EUROC_K = (458.654, 457.296, 367.215, 248.375)   # Examples/Monocular/EuRoC.yaml:8-11
+EUROC_DIST = (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0)   # EuRoC.yaml:13-16
 
 
 def _rot(rx, ry, rz):
@@ -198,3 +201,30 @@ def synth_ba_problem(seed=4, n_free=20, n_fixed=40, n_pt=3000, n_ln=400, obs_pt=
                 pe_kf=np.array(pe_kf, np.int32), pe_pt=np.array(pe_pt, np.int32), pe_obs=np.array(pe_obs, np.float32).reshape(-1, 2),
                 pe_inv_sigma2=np.array(pe_w, np.float32), le_kf=np.array(le_kf, np.int32), le_ln=np.array(le_ln, np.int32),
                 le_func=np.ascontiguousarray(np.array(le_f, np.float64).reshape(-1, 3)))
+
+
+def synth_map_view(seed=7, n=4000, K=TUM1_K, w=640, h=480, lines=False):
+    """A camera pose plus n local-map points (or lines) scattered in front of / around / behind it, for
+    Frame::isInFrustum: returns dict(Tcw, Ow, pos, normal, min_dist, max_dist)."""
+    rng = np.random.default_rng(seed)
+    R = _rot(*(rng.normal(0, 0.2, 3))); t = rng.normal(0, 0.5, 3)
+    Tcw = np.eye(4, dtype=np.float32); Tcw[:3, :3] = R.astype(np.float32); Tcw[:3, 3] = t.astype(np.float32)
+    Rwc = Tcw[:3, :3].T; Ow = (-Rwc @ Tcw[:3, 3]).astype(np.float32)
+    def pts(m):
+        z = rng.uniform(-2.0, 12.0, m); x = rng.uniform(-1.2, 1.2, m) * np.abs(z); y = rng.uniform(-1.0, 1.0, m) * np.abs(z)
+        Pc = np.stack([x, y, z], 1)
+        return (Pc - t) @ R            # Pw = R^T (Pc - t)
+    if not lines:
+        pos = pts(n).astype(np.float32)
+        d = np.linalg.norm(pos - Ow, axis=1)
+        nrm = (pos - Ow) / np.maximum(d, 1e-6)[:, None] + rng.normal(0, 0.5, (n, 3))
+        nrm = (nrm / np.linalg.norm(nrm, axis=1)[:, None]).astype(np.float32)
+    else:
+        s = pts(n); e = s + rng.normal(0, 0.4, (n, 3))
+        pos = np.concatenate([s, e], 1).astype(np.float64)
+        mid = 0.5 * (s + e); d = np.linalg.norm(mid - Ow, axis=1)
+        nrm = (mid - Ow) / np.maximum(d, 1e-6)[:, None] + rng.normal(0, 0.5, (n, 3))
+        nrm = (nrm / np.linalg.norm(nrm, axis=1)[:, None]).astype(np.float64)
+    f = rng.uniform(0.3, 3.0, n)
+    max_dist = (d * f * 1.2).astype(np.float32); min_dist = (max_dist / (1.2 ** rng.integers(2, 9, n))).astype(np.float32)
+    return dict(Tcw=Tcw, Ow=Ow, pos=pos, normal=nrm, min_dist=min_dist, max_dist=max_dist)

@@ -49,7 +49,7 @@ struct LineParams {
   int min_reg_size;
   int seg_cap, capL, nfeatures;
   double min_line_length;
-  double prec, p, density_th;
+  double prec, prec_hi, p, density_th;   // prec_hi: see region_grow_t
 };
 
 // ---------------------------------------------------------------------------------------------- shared helpers
@@ -58,14 +58,11 @@ __device__ __forceinline__ float fast_atan2_deg_l(float y, float x) {  // cv::fa
   const float p1 = 0.9997878412794807f * k, p3 = -0.3258083974640975f * k;
   const float p5 = 0.1555786518463281f * k, p7 = -0.04432655554792128f * k;
   const float eps = 2.220446049250313e-16f;
-  float ax = fabsf(x), ay = fabsf(y), a, c, c2;
-  if (ax >= ay) {
-    c = __fdiv_rn(ay, __fadd_rn(ax, eps)); c2 = __fmul_rn(c, c);
-    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
-  } else {
-    c = __fdiv_rn(ax, __fadd_rn(ay, eps)); c2 = __fmul_rn(c, c);
-    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
-  }
+  // ax >= ay ? ay/(ax+eps) : ax/(ay+eps)  ==  min/(max+eps): one division, no branch (this sits on the serial commit loop)
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float c = __fdiv_rn(fminf(ax, ay), __fadd_rn(fmaxf(ax, ay), eps)), c2 = __fmul_rn(c, c);
+  float a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  if (ax < ay) a = __fsub_rn(90.f, a);
   if (x < 0) a = __fsub_rn(180.f, a);
   if (y < 0) a = __fsub_rn(360.f, a);
   return a;
@@ -254,12 +251,16 @@ __global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const float* 
 
 // ---------------------------------------------------------------------------------------------- K_F region growing
 struct GrowCtx {
-  const float* ANG; const float2* CS; const int* SQ; const float2* S2; unsigned* U; unsigned* R; unsigned* ring;   // U: USED bitmap in shared memory
+  int* ANG; const float2* CS; const int* SQ; const float2* S2; unsigned* R; unsigned* ring;
   int sw, sh, s_th;
 };
-__device__ __forceinline__ bool used_get(const GrowCtx& C, int idx) { return (C.U[idx >> 5] >> (idx & 31)) & 1u; }
-__device__ __forceinline__ void used_set1(const GrowCtx& C, int idx) { C.U[idx >> 5] |= 1u << (idx & 31); }      // one lane
-__device__ __forceinline__ void used_clear(const GrowCtx& C, int idx) { atomicAnd(&C.U[idx >> 5], ~(1u << (idx & 31))); }
+// The USED flag of LSD lives in the SIGN BIT of the pixel's angle word (degrees, >= 0 when defined): one 4-byte load
+// tells a candidate's used state, definedness (NOTDEF = -1024 is negative too) and angle; setting / clearing it is a
+// plain store by whichever lane owns the pixel (no bitmap word shared between lanes, no read-modify-write).
+constexpr int kUsedBit = (int)0x80000000;
+__device__ __forceinline__ bool used_get(const GrowCtx& C, int idx) { return C.ANG[idx] < 0; }     // seeds are always defined
+__device__ __forceinline__ float pixel_angle(const GrowCtx& C, int idx) { return __int_as_float(C.ANG[idx] & ~kUsedBit); }   // of a defined pixel
+__device__ __forceinline__ void used_clear(const GrowCtx& C, int idx) { C.ANG[idx] &= ~kUsedBit; }  // one lane per pixel
 struct RectD { double x1, y1, x2, y2, width; };
 
 __device__ __forceinline__ double angle_diff_signed(double a, double b) {
@@ -277,26 +278,43 @@ __device__ __forceinline__ bool is_aligned(double a, double theta, double prec) 
 
 // LineSegmentDetectorImpl::region_grow — exact visiting order; returns the region size, region in C.R[0..n).
 // Four queue entries are expanded per step: lanes 8g..8g+7 fetch the 8 neighbours of entry i+g (used flag, then the
-// 4-byte angle of the unused ones), then the candidates are committed
-// in the reference's order (queue order, then row-major inside the 3x3); a pixel added earlier in the same step
-// invalidates its duplicates in the later neighbourhoods, so the result equals the one-entry-at-a-time loop.
-__device__ __noinline__ int region_grow(const GrowCtx& C, unsigned seed, double prec, double& reg_angle, int lane) {
+// 4-byte angle and the cos/sin pair of the unused ones), then the candidates are committed in the reference's order
+// (queue order, then row-major inside the 3x3); a pixel added earlier in the same step invalidates its duplicates in
+// the later neighbourhoods, so the result equals the one-entry-at-a-time loop.
+// The commit loop is the serial spine of the whole front end (one trip per added pixel), so it carries only what the
+// next decision needs: one fp64 subtract + two compares per lane, three shuffles, the atan2.  The USED bits, the region
+// list and the ring are written after the loop by the accepted lanes themselves.
+// kFast: prec < pi/2, isAligned folded to  n <= prec || n >= prec_hi  (prec_hi = smallest double with 2pi-n <= prec;
+// 2pi-n is exact for n in [pi,4pi], so the two forms agree bit for bit).
+#ifndef GROW_DUP_MATCH
+#define GROW_DUP_MATCH 0
+#endif
+#ifndef GROW_PUBLISH
+#define GROW_PUBLISH 1
+#endif
+#ifndef GROW_INLINE
+#define GROW_INLINE 1
+#endif
+template <bool kFast>
+__device__ __forceinline__ int region_grow_t(const GrowCtx& C, unsigned seed, double prec, double prec_hi, double& reg_angle_out, int lane) {
   const int sidx = (int)(seed >> 16) * C.sw + (int)(seed & 0xffffu);
   const float2 s0 = __ldg(&C.S2[sidx]);
-  reg_angle = (double)__ldg(&C.ANG[sidx]) * kDegToRads;
+  const int sbits = C.ANG[sidx];                  // the seed is unused here, so this is its angle
+  double reg_angle = (double)__int_as_float(sbits) * kDegToRads;
   float sumdx = s0.x, sumdy = s0.y;
-  if (lane == 0) { C.R[0] = seed; C.ring[0] = seed; used_set1(C, sidx); }
+  if (lane == 0) { C.R[0] = seed; C.ring[0] = seed; C.ANG[sidx] = sbits | kUsedBit; }
   int cnt = 1;
   __syncwarp();
   // lane -> (queue entry lane/8, neighbour lane%8); the centre of a 3x3 is always USED, so 8 neighbours suffice
   const int grp = lane >> 3, kk8 = lane & 7, kk = kk8 + (kk8 >= 4);
   const int ox = kk % 3 - 1, oy = kk / 3 - 1;
+  const unsigned lt = (1u << lane) - 1u;
   for (int i = 0; i < cnt;) {
     const int m = min(4, cnt - i);
     bool valid = false;
     int idx = -1;
-    unsigned pk = 0;
-    float ang = kNotDefDeg;
+    unsigned pk = 0xffff0000u | (unsigned)lane;      // unique per lane unless it names a real pixel
+    int ab = -1;
     float2 csv = make_float2(0.f, 0.f);
     if (grp < m) {
       const int qi = i + grp;
@@ -304,38 +322,69 @@ __device__ __noinline__ int region_grow(const GrowCtx& C, unsigned seed, double 
       const int xx = (int)(p & 0xffffu) + ox, yy = (int)(p >> 16) + oy;
       if (xx >= 0 && yy >= 0 && xx < C.sw && yy < C.sh) {
         idx = yy * C.sw + xx;
-        pk = (unsigned)xx | ((unsigned)yy << 16);
-        if (!used_get(C, idx)) {
-          ang = __ldg(&C.ANG[idx]);
+        ab = C.ANG[idx];
+        if (ab >= 0) {                     // defined and not USED
           csv = __ldg(&C.CS[idx]);         // prefetched with the angle: no dependent load on the commit path
-          valid = (ang != kNotDefDeg);
+          valid = true;
+          pk = (unsigned)xx | ((unsigned)yy << 16);
         }
       }
     }
-    const double a = (double)ang * kDegToRads;
+    i += m;
+    unsigned live = __ballot_sync(0xffffffffu, valid);
+    if (live == 0u) continue;
+    const double a = (double)__int_as_float(ab) * kDegToRads;
     // Commit in order.  Every remaining candidate is tested against the CURRENT region angle at once; the first
     // aligned one (lowest lane = reference order) is added, which changes the angle, and the candidates after it
     // are tested again.  Candidates skipped before the committed lane were tested with the angle they would
     // have seen in the sequential loop, so they are never revisited.
-    unsigned live = __ballot_sync(0xffffffffu, valid);
+#if GROW_DUP_MATCH
+    const unsigned dup = __match_any_sync(0xffffffffu, pk);   // lanes naming the same pixel (later 3x3 neighbourhoods)
+#endif
+    int mypos = -1;
     while (live) {
-      const unsigned al = __ballot_sync(0xffffffffu, valid && is_aligned(a, reg_angle, prec)) & live;
+      bool al1;
+      if (kFast) { const double n1 = fabs(reg_angle - a); al1 = (n1 <= prec) || (n1 >= prec_hi); }
+      else al1 = is_aligned(a, reg_angle, prec);
+      const unsigned al = __ballot_sync(0xffffffffu, al1) & live;
       if (!al) break;
       const int k = __ffs(al) - 1;
-      const unsigned pkk = __shfl_sync(0xffffffffu, pk, k);
-      const int ikk = (int)(pkk >> 16) * C.sw + (int)(pkk & 0xffffu);
-      if (lane == 0) { used_set1(C, ikk); C.R[cnt] = pkk; C.ring[cnt & (kRing - 1)] = pkk; }
+#if GROW_PUBLISH
+      if (lane == k) mypos = cnt;
+#else
+      {
+        const unsigned pkk0 = __shfl_sync(0xffffffffu, pk, k);
+        if (lane == 0) { C.R[cnt] = pkk0; C.ring[cnt & (kRing - 1)] = pkk0; }
+        if (lane == k) C.ANG[idx] = ab | kUsedBit;
+      }
+#endif
       cnt++;
       sumdx = __fadd_rn(sumdx, __shfl_sync(0xffffffffu, csv.x, k));
       sumdy = __fadd_rn(sumdy, __shfl_sync(0xffffffffu, csv.y, k));
       reg_angle = (double)fast_atan2_deg_l(sumdy, sumdx) * kDegToRads;
-      live &= ~((2u << k) - 1u);                                   // everything up to k has been decided
-      live &= ~__ballot_sync(0xffffffffu, pk == pkk && idx >= 0);  // the same pixel in a later 3x3 is now USED
+      // everything up to k has been decided; the same pixel in a later 3x3 is now USED
+#if GROW_DUP_MATCH
+      live &= ~(((2u << k) - 1u) | __shfl_sync(0xffffffffu, dup, k));
+#else
+      live &= ~(((2u << k) - 1u) | __ballot_sync(0xffffffffu, pk == __shfl_sync(0xffffffffu, pk, k)));
+#endif
+    }
+    if (GROW_PUBLISH && mypos >= 0) {      // publish: every accepted lane owns its pixel
+      C.ANG[idx] = ab | kUsedBit;
+      C.R[mypos] = pk;
+      C.ring[mypos & (kRing - 1)] = pk;
     }
     __syncwarp();
-    i += m;
   }
+  reg_angle_out = reg_angle;
   return cnt;
+}
+__device__ __noinline__ int region_grow_hot(const GrowCtx& C, unsigned seed, double prec, double prec_hi, double& reg_angle, int lane) {
+  return region_grow_t<true>(C, seed, prec, prec_hi, reg_angle, lane);
+}
+// refine's regrow with the adaptive tolerance tau (any value): generic isAligned, kept out of line
+__device__ __noinline__ int region_grow_cold(const GrowCtx& C, unsigned seed, double prec, double& reg_angle, int lane) {
+  return region_grow_t<false>(C, seed, prec, 0.0, reg_angle, lane);
 }
 
 // LineSegmentDetectorImpl::region2rect (+get_theta); sums are reduced lane-strided then by butterfly
@@ -390,7 +439,7 @@ __device__ __noinline__ bool refine(const GrowCtx& C, int& n, double reg_angle, 
   if (density >= density_th) return true;
   const unsigned p0 = C.R[0];
   const double xc = (double)(int)(p0 & 0xffffu), yc = (double)(int)(p0 >> 16);
-  const double ang_c = (double)__ldg(&C.ANG[(int)(p0 >> 16) * C.sw + (int)(p0 & 0xffffu)]) * kDegToRads;
+  const double ang_c = (double)pixel_angle(C, (int)(p0 >> 16) * C.sw + (int)(p0 & 0xffffu)) * kDegToRads;
   double sum = 0, s_sum = 0;
   int cnt = 0;
   for (int i = lane; i < n; i += 32) {
@@ -399,7 +448,7 @@ __device__ __noinline__ bool refine(const GrowCtx& C, int& n, double reg_angle, 
     used_clear(C, pidx);
     const double px = (double)(int)(p & 0xffffu), py = (double)(int)(p >> 16);
     if (dist_d(xc, yc, px, py) < rec.width) {
-      const double ang_d = angle_diff_signed((double)__ldg(&C.ANG[pidx]) * kDegToRads, ang_c);
+      const double ang_d = angle_diff_signed((double)pixel_angle(C, pidx) * kDegToRads, ang_c);
       sum += ang_d; s_sum += ang_d * ang_d; ++cnt;
     }
   }
@@ -407,7 +456,7 @@ __device__ __noinline__ bool refine(const GrowCtx& C, int& n, double reg_angle, 
   __syncwarp();
   const double mean_angle = sum / (double)cnt;
   const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
-  n = region_grow(C, p0, tau, reg_angle, lane);
+  n = region_grow_cold(C, p0, tau, reg_angle, lane);
   if (n < 2) return false;
   region2rect(C, n, reg_angle, prec, rec, lane);
   density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
@@ -444,25 +493,16 @@ __device__ __noinline__ bool refine(const GrowCtx& C, int& n, double reg_angle, 
   return true;
 }
 
-template <bool kSmemUsed>
-__global__ void __launch_bounds__(32, 32) k_lsd_grow(LineParams P, unsigned* __restrict__ gbits, const float* __restrict__ ANG, const float2* __restrict__ CS, const int* __restrict__ SQ, const float2* __restrict__ seedcs,
+__global__ void __launch_bounds__(32, 32) k_lsd_grow(LineParams P, int* ANG, const float2* __restrict__ CS, const int* __restrict__ SQ, const float2* __restrict__ seedcs,
                                                  const unsigned* __restrict__ order, const int* __restrict__ ndef,
                                                  unsigned* __restrict__ reg, float4* __restrict__ segs,
                                                  int* __restrict__ nseg, int* __restrict__ overflow, int nframes) {
   __shared__ unsigned ring[kRing];
-  extern __shared__ unsigned sbits[];            // USED bitmap of the scaled image: (npx+31)/32 words
   const int lane = threadIdx.x;
-  const int nwords = (P.npx + 31) / 32;
   for (int f = blockIdx.x; f < nframes; f += gridDim.x) {   // persistent: the grid size caps the resident warps per SM
-  // The bitmap lives in shared memory (fast, but 24.6 KB per warp caps the SM at 8 frames) or in global memory / L1
-  // (slower per access, but up to 28 frames per SM hide the latency): chosen at handle creation.
-  unsigned* ubits = kSmemUsed ? sbits : gbits + (long long)f * nwords;
-  for (int i = lane; i < nwords; i += 32) ubits[i] = 0u;
-  __syncwarp();
-  GrowCtx C;
-  C.ANG = ANG + (long long)f * P.npx; C.CS = CS + (long long)f * P.npx; C.SQ = SQ + (long long)f * P.npx;
-  C.S2 = seedcs + (long long)f * P.npx; C.U = ubits; C.R = reg + (long long)f * P.npx;
-  C.ring = ring; C.sw = P.sw; C.sh = P.sh; C.s_th = P.s_th;
+  // const object: the cold out-of-line callees take it by reference, the inlined hot loop keeps its fields in registers
+  const GrowCtx C = {ANG + (long long)f * P.npx, CS + (long long)f * P.npx, SQ + (long long)f * P.npx, seedcs + (long long)f * P.npx,
+                     reg + (long long)f * P.npx, ring, P.sw, P.sh, P.s_th};
   const unsigned* O = order + (long long)f * P.npx;
   float4* S = segs + (long long)f * P.seg_cap;
   const int n = ndef[f];
@@ -476,7 +516,11 @@ __global__ void __launch_bounds__(32, 32) k_lsd_grow(LineParams P, unsigned* __r
       const int k = __ffs(todo) - 1;
       const unsigned seed = __shfl_sync(0xffffffffu, pix, k);
       double reg_angle;
-      int cnt = region_grow(C, seed, P.prec, reg_angle, lane);
+#if GROW_INLINE
+      int cnt = region_grow_t<true>(C, seed, P.prec, P.prec_hi, reg_angle, lane);
+#else
+      int cnt = region_grow_hot(C, seed, P.prec, P.prec_hi, reg_angle, lane);
+#endif
       if (cnt >= P.min_reg_size) {
         RectD rec;
         region2rect(C, cnt, reg_angle, P.prec, rec, lane);
@@ -769,10 +813,7 @@ struct PLLine {
   cudaStream_t stream = nullptr;
   uint8_t* d_scaled = nullptr;
   float2* d_seedcs = nullptr;
-  unsigned* d_ubits = nullptr;
-  int used_global = 0;
   int grow_grid_cap = 1 << 30;   // max CTAs of the persistent grow kernel (env PLSLAM_LSD_GROW_CTAS_PER_SM x #SMs)
-  size_t grow_smem = 0;
   float* d_ang = nullptr; float2* d_cs = nullptr; int* d_sq = nullptr;
   unsigned short* d_counts = nullptr;
   int *d_offsets = nullptr, *d_ndef = nullptr, *d_maxs = nullptr, *d_nseg = nullptr, *d_overflow = nullptr;
@@ -794,7 +835,7 @@ static const unsigned char h_comb[64] = {0, 1, 0, 2, 0, 3, 0, 4, 0, 5, 0, 6, 1, 
 
 extern "C" void pl_line_destroy(PLLine* h) {
   if (!h) return;
-  cudaFree(h->d_scaled); cudaFree(h->d_seedcs); cudaFree(h->d_ubits); cudaFree(h->d_ang); cudaFree(h->d_cs); cudaFree(h->d_sq); cudaFree(h->d_counts); cudaFree(h->d_offsets);
+  cudaFree(h->d_scaled); cudaFree(h->d_seedcs); cudaFree(h->d_ang); cudaFree(h->d_cs); cudaFree(h->d_sq); cudaFree(h->d_counts); cudaFree(h->d_offsets);
   cudaFree(h->d_ndef); cudaFree(h->d_maxs); cudaFree(h->d_nseg); cudaFree(h->d_overflow); cudaFree(h->d_order);
   cudaFree(h->d_reg); cudaFree(h->d_segs); cudaFree(h->d_dxy); cudaFree(h->d_img); cudaFree(h->d_kls);
   cudaFree(h->d_desc); cudaFree(h->d_lf); cudaFree(h->d_nl); cudaFree(h->d_mask);
@@ -816,6 +857,13 @@ extern "C" int pl_line_create(const PLLineConfig* cfg, PLLine** out) {
   P.nchunk = (P.sh - 1 + kChunkRows - 1) / kChunkRows;
   const double ANG_TH = 22.5, QUANT = 2.0;
   P.prec = kPI * ANG_TH / 180; P.p = ANG_TH / 180; P.density_th = 0.7;
+  {  // smallest double n with (2pi - n) <= prec, the subtraction being exact in that range
+    const double twopi = 2 * kPI;
+    double c = twopi - P.prec;
+    while ((twopi - nextafter(c, 0.0)) <= P.prec) c = nextafter(c, 0.0);
+    while (!((twopi - c) <= P.prec)) c = nextafter(c, 10.0);
+    P.prec_hi = c;
+  }
   const double rho = QUANT / sin(P.prec);
   int s = 0;
   while (sqrt((double)(s + 1) / 4.0) <= rho) s++;   // largest s with sqrt(s/4) <= rho
@@ -847,14 +895,9 @@ extern "C" int pl_line_create(const PLLineConfig* cfg, PLLine** out) {
     LN_CUDA(cudaMemcpyToSymbol(c_comb, h_comb, sizeof(h_comb)));
   }
   LN_CUDA(cudaFuncSetAttribute(k_keylines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->key_smem));
-  h->grow_smem = (size_t)((P.npx + 31) / 32) * 4;
-  if (h->grow_smem > 200 * 1024) { set_error("frame too large for the shared-memory USED bitmap"); pl_line_destroy(h); return PL_ERR_ARG; }
-  { const char* e = getenv("PLSLAM_LSD_USED_GLOBAL");   // default: global (measured 1.6x the throughput of the smem map at B>=2048)
-    h->used_global = cfg->lsd_used_in_global > 0 ? 1 : (cfg->lsd_used_in_global < 0 ? 0 : !(e && e[0] == '0')); }
-  if (h->used_global) LN_TRY(dev_alloc(&h->d_ubits, (size_t)((P.npx + 31) / 32) * B));
+  // cfg->lsd_used_in_global is accepted for ABI compatibility and ignored: the USED flag is the sign bit of the angle word
   { const char* e = getenv("PLSLAM_LSD_GROW_CTAS_PER_SM"); int per = e ? atoi(e) : 0;
     if (per > 0) { int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); h->grow_grid_cap = per * sms; } }
-  LN_CUDA(cudaFuncSetAttribute(k_lsd_grow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grow_smem));
   *out = h;
   return PL_OK;
 }
@@ -897,10 +940,7 @@ extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int str
   k_lsd_scatter<<<dim3((P.nchunk + 3) / 4, B), 128, 0, st>>>(P, h->d_ang, h->d_sq, h->d_maxs, h->d_offsets, h->d_order);
   PL_LAUNCH_CHECK();
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev0, st));
-  if (h->used_global)
-    k_lsd_grow<false><<<std::min(B, h->grow_grid_cap), 32, 0, st>>>(P, h->d_ubits, h->d_ang, h->d_cs, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow, B);
-  else
-  k_lsd_grow<true><<<std::min(B, h->grow_grid_cap), 32, h->grow_smem, st>>>(P, nullptr, h->d_ang, h->d_cs, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow, B);
+  k_lsd_grow<<<std::min(B, h->grow_grid_cap), 32, 0, st>>>(P, reinterpret_cast<int*>(h->d_ang), h->d_cs, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow, B);
   PL_LAUNCH_CHECK();
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev1, st));
   k_keylines<<<B, 256, h->key_smem, st>>>(P, h->d_segs, h->d_nseg, mask, (PLKeyLineRec*)keylines, linefunc, n);

@@ -295,6 +295,30 @@ __device__ __forceinline__ bool is_aligned(double a, double theta, double prec) 
 #ifndef GROW_INLINE
 #define GROW_INLINE 1
 #endif
+#ifndef GROW_CS_EAGER
+#define GROW_CS_EAGER 1
+#endif
+#ifndef GROW_PREFETCH
+#define GROW_PREFETCH 1     // bit 0: at seed-batch load, bit 1: at publication
+#endif
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// the rows a pixel's 3x3 neighbourhood will touch when it is expanded: angle words and cos/sin pairs (x-1 and x+1 ends)
+template <bool kL1>
+__device__ __forceinline__ void prefetch_neighbourhood(const GrowCtx& C, int idx, int npx, bool centre_row) {
+  const int up = max(idx - C.sw, 1), dn = min(idx + C.sw, npx - 2), ce = min(max(idx, 1), npx - 2);
+  if (kL1) {
+    prefetch_l1(&C.ANG[up - 1]); prefetch_l1(&C.ANG[up + 1]); prefetch_l1(&C.ANG[dn - 1]); prefetch_l1(&C.ANG[dn + 1]);
+    prefetch_l1(&C.CS[up - 1]); prefetch_l1(&C.CS[up + 1]); prefetch_l1(&C.CS[dn - 1]); prefetch_l1(&C.CS[dn + 1]);
+    prefetch_l1(&C.CS[ce - 1]); prefetch_l1(&C.CS[ce + 1]);
+    if (centre_row) { prefetch_l1(&C.ANG[ce - 1]); prefetch_l1(&C.ANG[ce + 1]); }
+  } else {
+    prefetch_l2(&C.ANG[up - 1]); prefetch_l2(&C.ANG[up + 1]); prefetch_l2(&C.ANG[dn - 1]); prefetch_l2(&C.ANG[dn + 1]);
+    prefetch_l2(&C.CS[up - 1]); prefetch_l2(&C.CS[up + 1]); prefetch_l2(&C.CS[dn - 1]); prefetch_l2(&C.CS[dn + 1]);
+    prefetch_l2(&C.CS[ce - 1]); prefetch_l2(&C.CS[ce + 1]);
+    if (centre_row) { prefetch_l2(&C.ANG[ce - 1]); prefetch_l2(&C.ANG[ce + 1]); }
+  }
+}
 template <bool kFast>
 __device__ __forceinline__ int region_grow_t(const GrowCtx& C, unsigned seed, double prec, double prec_hi, double& reg_angle_out, int lane) {
   const int sidx = (int)(seed >> 16) * C.sw + (int)(seed & 0xffffu);
@@ -323,8 +347,13 @@ __device__ __forceinline__ int region_grow_t(const GrowCtx& C, unsigned seed, do
       if (xx >= 0 && yy >= 0 && xx < C.sw && yy < C.sh) {
         idx = yy * C.sw + xx;
         ab = C.ANG[idx];
+#if GROW_CS_EAGER
+        csv = __ldg(&C.CS[idx]);           // issued together with the angle word: one memory round trip per step
+#endif
         if (ab >= 0) {                     // defined and not USED
-          csv = __ldg(&C.CS[idx]);         // prefetched with the angle: no dependent load on the commit path
+#if !GROW_CS_EAGER
+          csv = __ldg(&C.CS[idx]);
+#endif
           valid = true;
           pk = (unsigned)xx | ((unsigned)yy << 16);
         }
@@ -373,6 +402,7 @@ __device__ __forceinline__ int region_grow_t(const GrowCtx& C, unsigned seed, do
       C.ANG[idx] = ab | kUsedBit;
       C.R[mypos] = pk;
       C.ring[mypos & (kRing - 1)] = pk;
+      if (GROW_PREFETCH & 2) prefetch_neighbourhood<true>(C, idx, C.sw * C.sh, false);   // it will be expanded a few steps from now
     }
     __syncwarp();
   }
@@ -512,6 +542,11 @@ __global__ void __launch_bounds__(32, 32) k_lsd_grow(LineParams P, int* ANG, con
     const unsigned pix = (i < n) ? O[i] : 0u;
     const int pidx = (int)(pix >> 16) * P.sw + (int)(pix & 0xffffu);
     unsigned todo = __ballot_sync(0xffffffffu, i < n && !used_get(C, pidx));
+    if (GROW_PREFETCH & 1) {
+      // this batch's seeds that are still free: their seed record and 3x3 rows; and the next batch's flag words
+      if ((todo >> lane) & 1u) { prefetch_l2(&C.S2[pidx]); prefetch_neighbourhood<false>(C, pidx, P.npx, false); }
+      if (i + 32 < n) { const unsigned pn = O[i + 32]; prefetch_l2(&C.ANG[(int)(pn >> 16) * P.sw + (int)(pn & 0xffffu)]); }
+    }
     while (todo) {
       const int k = __ffs(todo) - 1;
       const unsigned seed = __shfl_sync(0xffffffffu, pix, k);

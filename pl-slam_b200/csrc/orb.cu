@@ -37,6 +37,8 @@ static const int8_t h_pattern[256 * 4] = {
 struct LevelInfo {
   int w, h, pitch;        // level size; pitch of the stored level (level 0: caller's stride)
   long long off;          // byte offset of the level inside one frame's pyramid block (levels >= 1)
+  long long boff;         // byte offset of the BLURRED level inside one frame's blur block (all levels), pitch = bpitch
+  int bpitch;
   int cell0, ncells;      // first cell / number of cells in the cell table
   int nfeat;              // mnFeaturesPerLevel
   int nIni;               // DistributeOctTree: number of root nodes
@@ -57,6 +59,7 @@ struct OrbParams {
   LevelInfo lv[kMaxLevels];
   int nlevels, ncells, slotcap, cap, iniTh, minTh, poolcap, width, height;
   long long pyr_frame;   // bytes of one frame's pyramid block (levels 1..)
+  long long blur_frame;  // bytes of one frame's blurred-levels block (levels 0..)
   long long key_frame;   // keys per frame in the quadtree scratch (per buffer)
   int selcap;            // per (frame,level) selected capacity
   int sortcap;           // power of two >= poolcap (bitonic sort region)
@@ -552,23 +555,53 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
-constexpr int kRawR = 21;            // raw patch radius: 18 (max rotated pattern offset) + 3 (blur)
-constexpr int kRawW = 2 * kRawR + 1; // 43
-constexpr int kRawP = 44;
-constexpr int kBlurR = 18;
-constexpr int kBlurW = 2 * kBlurR + 1;  // 37
-constexpr int kBlurP = 40;
-constexpr int kDescWarps = 4;
+// K4a  GaussianBlur(level, 7x7, sigma 2, BORDER_REFLECT_101) of every pyramid level (ORBextractor.cc:1077-1079), once per
+// level instead of once per keypoint patch: the 1000 43x43 patches of a frame cover twice the pixels of its pyramid.
+// 8.8 fixed point rows [18 34 48 56 48 34 18] (sum 256), horizontal then vertical, (acc + 2^15) >> 16 — cv's
+// FixedPtCast path for CV_8U.  One thread walks DOWN one column of a 64 x kBlurRows tile with the last seven horizontal
+// results in registers, so every pixel costs one 7-tap row from shared memory and one 7-tap column from registers.
+constexpr int kBlurCols = 64, kBlurRows = 32, kBlurTy = 4;            // block = 64 x 4 threads, tile = 64 x 128 outputs
+constexpr int kBlurTileH = kBlurRows * kBlurTy, kBlurSP = kBlurCols + 8;
+__global__ void __launch_bounds__(kBlurCols * kBlurTy) k_blur_level(const uint8_t* __restrict__ src, int spitch, long long sframe,
+                                                                    int w, int h, uint8_t* __restrict__ dst, int dpitch, long long dframe) {
+  __shared__ uint8_t raw[(kBlurTileH + 6) * kBlurSP];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int x0 = blockIdx.x * kBlurCols, y0 = blockIdx.y * kBlurTileH;
+  const uint8_t* S = src + (long long)blockIdx.z * sframe;
+  const int rows = min(kBlurTileH, h - y0) + 6;
+  for (int r = ty; r < rows; r += kBlurTy) {
+    const int yy = min(max(reflect101(y0 + r - 3, h), 0), h - 1);
+    const uint8_t* row = S + (long long)yy * spitch;
+    raw[r * kBlurSP + tx] = row[min(max(reflect101(x0 + tx - 3, w), 0), w - 1)];
+    if (tx < 6) raw[r * kBlurSP + kBlurCols + tx] = row[min(max(reflect101(x0 + kBlurCols + tx - 3, w), 0), w - 1)];
+  }
+  __syncthreads();
+  const int x = x0 + tx, ybeg = y0 + ty * kBlurRows;
+  if (x >= w || ybeg >= h) return;
+  const int nrow = min(kBlurRows, h - ybeg);
+  const uint8_t* p = raw + (ty * kBlurRows) * kBlurSP + tx;
+  auto hrow = [&](const uint8_t* q) { return 18 * (q[0] + q[6]) + 34 * (q[1] + q[5]) + 48 * (q[2] + q[4]) + 56 * q[3]; };
+  int w0 = hrow(p), w1 = hrow(p + kBlurSP), w2 = hrow(p + 2 * kBlurSP), w3 = hrow(p + 3 * kBlurSP), w4 = hrow(p + 4 * kBlurSP),
+      w5 = hrow(p + 5 * kBlurSP);
+  uint8_t* D = dst + (long long)blockIdx.z * dframe + (long long)ybeg * dpitch + x;
+  p += 6 * kBlurSP;
+  for (int r = 0; r < nrow; r++, p += kBlurSP, D += dpitch) {
+    const int w6 = hrow(p);
+    const unsigned acc = 18u * (unsigned)(w0 + w6) + 34u * (unsigned)(w1 + w5) + 48u * (unsigned)(w2 + w4) + 56u * (unsigned)w3;
+    *D = (uint8_t)((acc + 32768u) >> 16);
+    w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
+  }
+}
 
+// K4b  one warp per selected keypoint: IC_Angle on the level image (lanes = columns of the 31-wide circular patch, rows
+// read coalesced), steered BRIEF on the blurred level (512 byte reads inside a 37x37 window, L1-resident).
+constexpr int kDescWarps = 4;
 __global__ void __launch_bounds__(32 * kDescWarps) k_describe(OrbParams P, const uint8_t* __restrict__ img0,
                                                              int stride0, long long frame0,
-                                                             const uint8_t* __restrict__ pyr,
+                                                             const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                                                              const uint32_t* __restrict__ sel,
                                                              const int* __restrict__ nsel, PLKeyPoint* __restrict__ kps,
                                                              uint8_t* __restrict__ desc, int* __restrict__ nout) {
-  __shared__ uint8_t s_raw[kDescWarps][kRawW * kRawP];
-  __shared__ uint16_t s_h[kDescWarps][kRawW * kBlurP];
-  __shared__ uint8_t s_blur[kDescWarps][kBlurW * kBlurP];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int frame = blockIdx.y;
   const int idx = blockIdx.x * kDescWarps + wid;
@@ -593,51 +626,31 @@ __global__ void __launch_bounds__(32 * kDescWarps) k_describe(OrbParams P, const
   const uint32_t key = sel[((long long)frame * P.nlevels + level) * P.selcap + rank];
   const int px = (int)(key & 0xfff) + (kEdge - 3), py = (int)((key >> 12) & 0xfff) + (kEdge - 3);
   const int resp = (int)(key >> 24);
-
-  uint8_t* raw = s_raw[wid];
-  uint16_t* hb = s_h[wid];
-  uint8_t* bl = s_blur[wid];
-  for (int i = lane; i < kRawW * kRawW; i += 32) {
-    int r = i / kRawW, c = i - r * kRawW;
-    int yy = reflect101(py + r - kRawR, L.h), xx = reflect101(px + c - kRawR, L.w);
-    raw[r * kRawP + c] = img[(long long)yy * pitch + xx];
+  // IC_Angle (ORBextractor.cc:76-105): m10 = sum u*I, m01 = sum v*I over |u| <= umax[|v|]; keypoints sit >= 19 px inside
+  int m10, m01 = 0;
+  {
+    const int u = lane - kHalfPatch;
+    const uint8_t* c0 = img + (long long)py * pitch + px + u;
+    int colsum = 0;
+#pragma unroll 1
+    for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
+      if (lane <= 2 * kHalfPatch && abs(u) <= c_umax[abs(v)]) {
+        const int p = c0[v * pitch];
+        colsum += p; m01 += v * p;
+      }
+    }
+    m10 = warp_sum(u * colsum);
+    m01 = warp_sum(m01);
   }
-  __syncwarp();
-  // IC_Angle: rows v = lane-15 (31 rows), circular patch
-  int m10 = 0, m01 = 0;
-  if (lane < 2 * kHalfPatch + 1) {
-    int v = lane - kHalfPatch;
-    int d = c_umax[abs(v)];
-    const uint8_t* row = raw + (kRawR + v) * kRawP + kRawR;
-    int rs = 0;
-    for (int u = -d; u <= d; u++) { int p = row[u]; m10 += u * p; rs += p; }
-    m01 = v * rs;
-  }
-  m10 = warp_sum(m10);
-  m01 = warp_sum(m01);
   const float angle = fast_atan2_deg((float)m01, (float)m10);
-  // horizontal 7-tap pass (8.8 fixed point): rows 0..42, cols 3..39 of the raw patch -> hb[43][37]
-  for (int i = lane; i < kRawW * kBlurW; i += 32) {
-    int r = i / kBlurW, c = i - r * kBlurW;
-    const uint8_t* p = raw + r * kRawP + c;
-    hb[r * kBlurP + c] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-  }
-  __syncwarp();
-  for (int i = lane; i < kBlurW * kBlurW; i += 32) {
-    int r = i / kBlurW, c = i - r * kBlurW;
-    const uint16_t* p = hb + r * kBlurP + c;
-    uint32_t sacc = 18u * (p[0] + p[6 * kBlurP]) + 34u * (p[kBlurP] + p[5 * kBlurP]) +
-                    48u * (p[2 * kBlurP] + p[4 * kBlurP]) + 56u * p[3 * kBlurP];
-    bl[r * kBlurP + c] = (uint8_t)((sacc + 32768u) >> 16);
-  }
-  __syncwarp();
   // steered BRIEF: lane computes descriptor byte `lane`
   const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
   const float ang = __fmul_rn(angle, factorPI);
   float a = 0.f, b = 0.f;
   if (lane == 0) { a = (float)cos((double)ang); b = (float)sin((double)ang); }   // fp64 libm once per keypoint, not once per lane
   a = __shfl_sync(0xffffffffu, a, 0); b = __shfl_sync(0xffffffffu, b, 0);
-  const uint8_t* ctr = bl + kBlurR * kBlurP + kBlurR;
+  const int bp = L.bpitch;
+  const uint8_t* ctr = blur + (long long)frame * P.blur_frame + L.boff + (long long)py * bp + px;
   int val = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
@@ -647,7 +660,7 @@ __global__ void __launch_bounds__(32 * kDescWarps) k_describe(OrbParams P, const
     int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
     int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
     int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-    int t0 = ctr[r0 * kBlurP + c0], t1 = ctr[r1 * kBlurP + c1];
+    int t0 = ctr[r0 * bp + c0], t1 = ctr[r1 * bp + c1];
     val |= (t0 < t1) << k;
   }
   desc[((long long)frame * P.cap + idx) * 32 + lane] = (uint8_t)val;
@@ -676,6 +689,7 @@ struct PLOrb {
   CellInfo* d_cells = nullptr;
   short4* d_tabs = nullptr;
   uint8_t* d_pyr = nullptr;
+  uint8_t* d_blur = nullptr;   // blurred levels 0.. (K4a output)
   uint32_t *d_slots = nullptr, *d_keysA = nullptr, *d_keysB = nullptr, *d_sel = nullptr;
   int *d_counts = nullptr, *d_nsel = nullptr, *d_overflow = nullptr;
   // staging for the host-pointer API
@@ -748,7 +762,7 @@ extern "C" int pl_orb_create(const PLOrbConfig* cfg, PLOrb** out) {
   P.slotcap = cfg->cell_slot_cap > 0 ? cfg->cell_slot_cap : 128;
   P.width = cfg->width; P.height = cfg->height;
   std::vector<short4> tabs;
-  long long off = 0, keyoff = 0;
+  long long off = 0, keyoff = 0, boff = 0;
   int maxN = 0, maxIni = 1;
   for (int l = 0; l < nl; l++) {
     LevelInfo& L = P.lv[l];
@@ -757,6 +771,8 @@ extern "C" int pl_orb_create(const PLOrbConfig* cfg, PLOrb** out) {
     if (L.w < 2 * kEdge + 8 || L.h < 2 * kEdge + 8) { delete h; set_error("level %d too small", l); return PL_ERR_ARG; }
     L.pitch = (L.w + 63) / 64 * 64;
     L.off = off;
+    L.bpitch = L.pitch; L.boff = boff;
+    boff += ((long long)L.bpitch * L.h + 255) / 256 * 256;
     if (l > 0) {
       off += (long long)L.pitch * L.h;
       off = (off + 255) / 256 * 256;
@@ -800,7 +816,7 @@ extern "C" int pl_orb_create(const PLOrbConfig* cfg, PLOrb** out) {
     maxN = std::max(maxN, L.nfeat); maxIni = std::max(maxIni, L.nIni);
   }
   P.ncells = (int)h->cells.size();
-  P.pyr_frame = off; P.key_frame = keyoff;
+  P.pyr_frame = off; P.key_frame = keyoff; P.blur_frame = boff;
   P.poolcap = (maxN + 4 * maxIni + 24 + 1) & ~1;
   P.selcap = maxN + 4;
   P.cap = cfg->nfeatures + 4 * nl;
@@ -820,6 +836,7 @@ extern "C" int pl_orb_create(const PLOrbConfig* cfg, PLOrb** out) {
   ORB_TRY(dev_alloc(&h->d_tabs, std::max<size_t>(tabs.size(), 1)));
   if (!tabs.empty()) ORB_CUDA(cudaMemcpy(h->d_tabs, tabs.data(), tabs.size() * sizeof(short4), cudaMemcpyHostToDevice));
   ORB_TRY(dev_alloc(&h->d_pyr, (size_t)std::max<long long>(off, 256) * B));
+  ORB_TRY(dev_alloc(&h->d_blur, (size_t)boff * B));
   ORB_TRY(dev_alloc(&h->d_slots, (size_t)P.ncells * P.slotcap * B));
   ORB_TRY(dev_alloc(&h->d_counts, (size_t)P.ncells * B));
   ORB_TRY(dev_alloc(&h->d_keysA, (size_t)P.key_frame * B));
@@ -835,7 +852,7 @@ extern "C" int pl_orb_create(const PLOrbConfig* cfg, PLOrb** out) {
 
 extern "C" void pl_orb_destroy(PLOrb* h) {
   if (!h) return;
-  cudaFree(h->d_cells); cudaFree(h->d_tabs); cudaFree(h->d_pyr); cudaFree(h->d_slots); cudaFree(h->d_counts);
+  cudaFree(h->d_cells); cudaFree(h->d_tabs); cudaFree(h->d_pyr); cudaFree(h->d_blur); cudaFree(h->d_slots); cudaFree(h->d_counts);
   cudaFree(h->d_keysA); cudaFree(h->d_keysB); cudaFree(h->d_sel); cudaFree(h->d_nsel); cudaFree(h->d_overflow);
   cudaFree(h->d_img); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_n);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -884,8 +901,16 @@ extern "C" int pl_orb_extract_batch_dev(PLOrb* h, const uint8_t* imgs, int strid
   k_quadtree<<<dim3(P.nlevels, B), 32, h->quad_smem, st>>>(P, h->d_slots, h->d_counts, h->d_keysA, h->d_keysB,
                                                            h->d_sel, h->d_nsel);
   PL_LAUNCH_CHECK();
+  for (int l = 0; l < P.nlevels; l++) {
+    const LevelInfo& L = P.lv[l];
+    const uint8_t* src = (l == 0) ? imgs : h->d_pyr + L.off;
+    k_blur_level<<<dim3((L.w + kBlurCols - 1) / kBlurCols, (L.h + kBlurTileH - 1) / kBlurTileH, B), dim3(kBlurCols, kBlurTy), 0, st>>>(
+        src, (l == 0) ? stride : L.pitch, (l == 0) ? (long long)frame_stride : P.pyr_frame, L.w, L.h, h->d_blur + L.boff, L.bpitch,
+        P.blur_frame);
+    PL_LAUNCH_CHECK();
+  }
   k_describe<<<dim3((P.cap + kDescWarps - 1) / kDescWarps, B), 32 * kDescWarps, 0, st>>>(
-      P, imgs, stride, (long long)frame_stride, h->d_pyr, h->d_sel, h->d_nsel, kps, desc, n);
+      P, imgs, stride, (long long)frame_stride, h->d_pyr, h->d_blur, h->d_sel, h->d_nsel, kps, desc, n);
   PL_LAUNCH_CHECK();
   return PL_OK;
 }

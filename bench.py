@@ -63,12 +63,16 @@ def make_inputs(B, seed):
 def oracle_frame_pipeline(o_orb, prev, img, prob):
     """The same per-frame work on the CPU oracle; returns the frame's features (to serve as `prev`)."""
     import oracle
-    kps, desc = o_orb.extract(img)
-    kl, ldesc, lf = oracle.line_extract(img, nfeatures=LINES[0], min_line_length=LINES[1])
+    from plslam_b200 import synth
+    K, D = synth.TUM1_K, synth.TUM1_DIST
+    kps, desc = o_orb.extract(img)                                   # Frame.cc:224 (raw image)
+    und = oracle.undistort_remap(img, K, D)                          # Frame.cc:220-222
+    kl, ldesc, lf = oracle.line_extract(und, nfeatures=LINES[0], min_line_length=LINES[1])   # Frame.cc:225
+    kps = oracle.undistort_keypoints(kps, K, D)                      # Frame.cc:233
     if prev is not None:
         pk, pd, pl_ = prev
         pm = np.stack([pk["x"], pk["y"]], 1).astype(np.float32)
-        oracle.search_for_initialization(pk, pd, kps, desc, [0, 0, W, H], pm, 100, 0.9, True)
+        oracle.search_for_initialization(pk, pd, kps, desc, oracle.image_bounds(K, D, W, H), pm, 100, 0.9, True)
         oracle.search_double(pl_, ldesc, 0.7)
     for _ in range(2):
         oracle.pose_optimization(0, prob["Tcw0"], prob["K"], prob["pt_obs"], prob["pt_inv_sigma2"], prob["pt_Xw"],
@@ -86,9 +90,11 @@ def cpu_sample(frames, problems, n_frames, threads):
     n_frames = min(n_frames, len(frames) - 1)
 
     def features(idx):
+        from plslam_b200 import synth
         kps, desc = oracle.OrbOracle(*ORB).extract(frames[idx])
-        kl, ldesc, lf = oracle.line_extract(frames[idx], nfeatures=LINES[0], min_line_length=LINES[1])
-        return kps, desc, ldesc
+        und = oracle.undistort_remap(frames[idx], synth.TUM1_K, synth.TUM1_DIST)
+        kl, ldesc, lf = oracle.line_extract(und, nfeatures=LINES[0], min_line_length=LINES[1])
+        return oracle.undistort_keypoints(kps, synth.TUM1_K, synth.TUM1_DIST), desc, ldesc
 
     def one(i):
         oracle_frame_pipeline(oracle.OrbOracle(*ORB), prevs[i], frames[i + 1], problems[i + 1])
@@ -125,7 +131,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(args.warmup, 1), "ms_per_step": 1000.0 * tot_t / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 front-end, f32 descriptors, f64 LM", "data": "synthetic",
-            "config": {"workload": "640x480 synthetic sequence: ORB(1000)+LSD/LBD(200) extract, frame-to-frame point+line "
+            "config": {"workload": "640x480 synthetic sequence, TUM1 camera: ORB(1000) + undistort + LSD/LBD(200) extract, frame-to-frame point+line "
                                    "matching, 2x PoseOptimization(300 pts + 80 lines)", "frames_per_step": per_step},
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": f"{per_step} frames per step x {args.steps} steps on {threads} threads; CPU oracle "
@@ -193,6 +199,8 @@ def run_ours(args):
     frames, problems = make_inputs(B, seed=1 + rank)        # weak scaling: every rank gets its own B frames
     fe = pl.Frontend(W, H, max_batch=B, orb=ORB, lines=LINES, lm_caps=(N_PTS + 20, N_LINES + 8))
     fe.set_pose_problems(problems)
+    from plslam_b200 import synth
+    fe.set_camera(synth.TUM1_K, synth.TUM1_DIST)          # TUM1.yaml camera: frames and keypoints are undistorted on the device
     d_frames = torch.from_numpy(frames).cuda()
     stream = torch.cuda.Stream()          # a real (non-NULL) stream: the C ABI treats NULL as "the handle's own stream"
     torch.cuda.set_stream(stream)
@@ -286,7 +294,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/i32 front-end, f32 descriptors, f64 LM", "data": "synthetic",
-            "config": {"workload": "640x480 synthetic sequence: ORB(1000)+LSD/LBD(200) extract, frame-to-frame point+line "
+            "config": {"workload": "640x480 synthetic sequence, TUM1 camera: ORB(1000) + undistort + LSD/LBD(200) extract, frame-to-frame point+line "
                                    "matching, 2x PoseOptimization(300 pts + 80 lines)",
                        "batch_per_gpu": B, "frame": [W, H], "orb": list(ORB), "lines": list(LINES),
                        "l2": f"inputs {B * W * H / 1e6:.0f} MB per step exceed the 126 MB L2",

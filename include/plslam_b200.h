@@ -203,6 +203,12 @@ int pl_frontend_capacities(const PLFrontend* h, int* cap_keypoints, int* cap_lin
 int pl_frontend_set_pose_problems(PLFrontend* h, int B, const float* Tcw0, const float* K, const int* n_points,
                                   const float* pt_obs, const float* pt_inv_sigma2, const float* pt_Xw, const int* n_lines,
                                   const double* line_func, const double* line_Xw);
+/* camera of the sequence: K = {fx,fy,cx,cy}, dist5 = {k1,k2,p1,p2,k3} (Tracking.cc:53-120).  k1 != 0: every frame is
+ * undistorted for the line extractor (Frame.cc:220-225), keypoints are undistorted for the matcher (Frame.cc:233) and the
+ * grid bounds come from ComputeImageBounds; k1 == 0 or never called: no undistortion (the default). */
+int pl_frontend_set_camera(PLFrontend* h, const float* K, const float* dist5);
+/* mvKeysUn of the last step, [B][cap_keypoints] */
+int pl_frontend_fetch_keys_un(PLFrontend* h, int B, PLKeyPoint* out);
 /* device-resident step (imgs = device pointer; NULL = frames uploaded by the last pl_frontend_run); asynchronous */
 int pl_frontend_run_dev(PLFrontend* h, const uint8_t* imgs, int stride, size_t frame_stride, int B, void* stream);
 /* end-to-end step on HOST buffers: H2D frames, device step, D2H of every per-frame result; synchronous.

@@ -435,6 +435,17 @@ class Frontend:
         self._problems = (T0, K, npt, obs, w, X, nln, lf, lX)
         check(lib().pl_frontend_set_pose_problems(self._h, B, _p(T0), _p(K), _p(npt), _p(obs), _p(w), _p(X), _p(nln), _p(lf), _p(lX)))
 
+    def set_camera(self, K, distCoef):
+        """mK / mDistCoef of the sequence: with k1 != 0 the step undistorts frames (for lines) and keypoints (for matching)."""
+        K = _f32(K); D = _f32(distCoef)
+        assert K.shape == (4,) and D.shape == (5,)
+        check(lib().pl_frontend_set_camera(self._h, _p(K), _p(D)))
+
+    def fetch_keys_un(self, B):
+        out = np.zeros((B, self.capK), KP_DTYPE)
+        check(lib().pl_frontend_fetch_keys_un(self._h, C.c_int(B), _p(out)))
+        return out
+
     def alloc_outputs(self, B, pinned=False):
         shapes = dict(kps=((B, self.capK), KP_DTYPE), desc=((B, self.capK, 32), np.uint8), n=((B,), np.int32),
                       keylines=((B, self.capL), KEYLINE_DTYPE), ldesc=((B, self.capL, 32), np.uint8),

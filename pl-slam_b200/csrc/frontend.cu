@@ -1,7 +1,9 @@
 // Per-frame front-end pipeline for a batch of frames: the sequence of hot-path calls that Tracking makes for one
 // frame, chained on one stream with every intermediate resident in HBM:
-//   Frame::ExtractORB  -> pl_orb_extract_batch_dev          (Frame.cc:224 -> ORBextractor::operator())
-//   Frame::ExtractLSD  -> pl_line_extract_batch_dev         (Frame.cc:225 -> LINEextractor::operator())
+//   Frame::ExtractORB  -> pl_orb_extract_batch_dev          (Frame.cc:224 -> ORBextractor::operator(), on the RAW image)
+//   undistort + remap  -> pl_undistort_remap_batch_dev      (Frame.cc:220-222; only with pl_frontend_set_camera, k1 != 0)
+//   Frame::ExtractLSD  -> pl_line_extract_batch_dev         (Frame.cc:225 -> LINEextractor::operator(), on the UNDISTORTED image)
+//   UndistortKeyPoints -> pl_undistort_keypoints_dev        (Frame.cc:233, :915-945; mvKeysUn feed the matcher)
 //   point matching     -> pl_orb_search_for_initialization_dev  frame k-1 -> frame k (ORBmatcher.cc:455-572 scheme)
 //   line matching      -> pl_lsd_search_double_dev               frame k-1 <-> frame k (LSDmatcher.cpp:440-486)
 //   2 x Optimizer::PoseOptimization -> pl_pose_optimization_dev  (Tracking.cc:1372 and :1503)
@@ -45,11 +47,16 @@ struct PLFrontend {
   double *d_lfun = nullptr, *d_lX = nullptr, *d_scratch = nullptr;
   int *d_np = nullptr, *d_nl_lm = nullptr, *d_inl = nullptr, *d_its = nullptr;
   uint8_t *d_pout = nullptr, *d_lout = nullptr;
+  // camera (pl_frontend_set_camera): undistortion map, undistorted frames, undistorted keypoints (B+1 slots like d_kps)
+  PLUndistort* und = nullptr;
+  uint8_t* d_und = nullptr;
+  PLKeyPoint* d_kpsu_prev = nullptr;
 };
 
 extern "C" void pl_frontend_destroy(PLFrontend* h) {
   if (!h) return;
-  pl_orb_destroy(h->orb); pl_line_destroy(h->line);
+  pl_orb_destroy(h->orb); pl_line_destroy(h->line); pl_undistort_destroy(h->und);
+  cudaFree(h->d_und); cudaFree(h->d_kpsu_prev);
   void* ptrs[] = {h->d_img, h->d_kl, h->d_lf, h->d_bounds, h->d_pm, h->d_m12,
                   h->d_nm, h->d_scr, h->d_lm, h->d_nlm, h->d_kps_prev, h->d_desc_prev, h->d_n_prev, h->d_ldesc_prev, h->d_nl_prev,
                   h->d_T0, h->d_K, h->d_pobs, h->d_pw, h->d_pX, h->d_Tout, h->d_lfun, h->d_lX, h->d_scratch, h->d_np, h->d_nl_lm,
@@ -155,8 +162,14 @@ extern "C" int pl_frontend_run_dev(PLFrontend* h, const uint8_t* imgs, int strid
     PL_CUDA(cudaStreamWaitEvent(sL, h->evStart, 0));
     PL_CUDA(cudaStreamWaitEvent(sM, h->evStart, 0));
   }
-  // --- line chain
-  if ((rc = pl_line_extract_batch_dev(h->line, imgs, stride, frame_stride, B, nullptr, h->d_kl, h->d_ldesc, h->d_lf, h->d_nl, sL))) return rc;
+  // --- line chain (on the undistorted frames when the camera has distortion, Frame.cc:220-225)
+  const uint8_t* limgs = imgs; int lstride = stride; size_t lframe = frame_stride;
+  if (h->und) {
+    const size_t fb = (size_t)h->cfg.width * h->cfg.height;
+    if ((rc = pl_undistort_remap_batch_dev(h->und, imgs, stride, frame_stride, B, h->d_und, h->cfg.width, fb, sL))) return rc;
+    limgs = h->d_und; lstride = h->cfg.width; lframe = fb;
+  }
+  if ((rc = pl_line_extract_batch_dev(h->line, limgs, lstride, lframe, B, nullptr, h->d_kl, h->d_ldesc, h->d_lf, h->d_nl, sL))) return rc;
   PL_CUDA(cudaMemcpyAsync(h->d_ldesc_prev, h->d_ldesc + cL * 32 * (B - 1), cL * 32, cudaMemcpyDeviceToDevice, sL));
   PL_CUDA(cudaMemcpyAsync(h->d_nl_prev, h->d_nl + (B - 1), sizeof(int), cudaMemcpyDeviceToDevice, sL));
   if ((rc = pl_lsd_search_double_dev(h->d_ldesc_prev, h->d_nl_prev, h->d_ldesc, h->d_nl, (int)cL, (int)cL, B, 50.f, 0.7f, 1, h->d_lm,
@@ -166,9 +179,17 @@ extern "C" int pl_frontend_run_dev(PLFrontend* h, const uint8_t* imgs, int strid
   PL_CUDA(cudaMemcpyAsync(h->d_kps_prev, h->d_kps + cK * (B - 1), cK * sizeof(PLKeyPoint), cudaMemcpyDeviceToDevice, st));
   PL_CUDA(cudaMemcpyAsync(h->d_desc_prev, h->d_desc + cK * 32 * (B - 1), cK * 32, cudaMemcpyDeviceToDevice, st));
   PL_CUDA(cudaMemcpyAsync(h->d_n_prev, h->d_n + (B - 1), sizeof(int), cudaMemcpyDeviceToDevice, st));
-  k_prev_matched_init<<<dim3((unsigned)((cK + 127) / 128), B), 128, 0, st>>>(h->d_kps, h->d_n, (int)cK, B, h->d_pm);
+  // mvKeysUn: the matcher works on undistorted keypoints (aliases of the raw ones without a distorting camera)
+  const PLKeyPoint *ku_prev = h->d_kps_prev, *ku = h->d_kps;
+  if (h->und) {
+    PLKeyPoint* dst = h->d_kpsu_prev + cK;
+    if ((rc = pl_undistort_keypoints_dev(h->und, h->d_kps, h->d_n, (int)cK, B, dst, st))) return rc;
+    PL_CUDA(cudaMemcpyAsync(h->d_kpsu_prev, dst + cK * (B - 1), cK * sizeof(PLKeyPoint), cudaMemcpyDeviceToDevice, st));
+    ku_prev = h->d_kpsu_prev; ku = dst;
+  }
+  k_prev_matched_init<<<dim3((unsigned)((cK + 127) / 128), B), 128, 0, st>>>(ku, h->d_n, (int)cK, B, h->d_pm);
   PL_LAUNCH_CHECK();
-  if ((rc = pl_orb_search_for_initialization_dev(h->d_kps_prev, h->d_desc_prev, h->d_n_prev, h->d_kps, h->d_desc, h->d_n, (int)cK, B,
+  if ((rc = pl_orb_search_for_initialization_dev(ku_prev, h->d_desc_prev, h->d_n_prev, ku, h->d_desc, h->d_n, (int)cK, B,
                                                  h->d_bounds, h->d_pm, h->d_m12, h->d_nm, 100, 0.9f, 1, h->d_scr, st))) return rc;
   // --- pose optimisations: TrackWithMotionModel (Tracking.cc:1372) and TrackLocalMapWithLines (:1503)
   for (int call = 0; call < 2; call++)
@@ -182,6 +203,33 @@ extern "C" int pl_frontend_run_dev(PLFrontend* h, const uint8_t* imgs, int strid
     PL_CUDA(cudaStreamWaitEvent(st, h->evLine, 0));
     PL_CUDA(cudaStreamWaitEvent(st, h->evLm, 0));
   }
+  return PL_OK;
+}
+
+// Camera of the sequence (Tracking.cc:53-120: mK, mDistCoef).  With k1 != 0 the step undistorts every frame for the line
+// extractor and the keypoints for the matcher, and the grid bounds become Frame::ComputeImageBounds'; with k1 == 0 (or never
+// called) the step is the undistorted-camera path (KITTI-style configs).
+extern "C" int pl_frontend_set_camera(PLFrontend* h, const float* K, const float* dist5) {
+  PL_ARG(h && K && dist5);
+  PL_CUDA(cudaDeviceSynchronize());
+  pl_undistort_destroy(h->und); h->und = nullptr;
+  float bounds[4];
+  int rc = pl_frame_image_bounds(K, dist5, h->cfg.width, h->cfg.height, bounds);
+  if (rc) return rc;
+  if (dist5[0] != 0.0f) {
+    if ((rc = pl_undistort_create(K, dist5, h->cfg.width, h->cfg.height, &h->und))) return rc;
+    if (!h->d_und && (rc = dev_alloc(&h->d_und, (size_t)h->cfg.width * h->cfg.height * h->B))) return rc;
+    if (!h->d_kpsu_prev && (rc = dev_alloc(&h->d_kpsu_prev, (size_t)h->capK * (h->B + 1)))) return rc;
+  }
+  PL_CUDA(cudaMemcpy(h->d_bounds, bounds, sizeof(bounds), cudaMemcpyHostToDevice));
+  return PL_OK;
+}
+// mvKeysUn of the last step (equal to the raw keypoints without a distorting camera)
+extern "C" int pl_frontend_fetch_keys_un(PLFrontend* h, int B, PLKeyPoint* out) {
+  PL_ARG(h && out && B >= 1 && B <= h->B);
+  PL_CUDA(cudaDeviceSynchronize());
+  const PLKeyPoint* src = h->und ? h->d_kpsu_prev + h->capK : h->d_kps;
+  PL_CUDA(cudaMemcpy(out, src, (size_t)h->capK * B * sizeof(PLKeyPoint), cudaMemcpyDeviceToHost));
   return PL_OK;
 }
 

@@ -50,3 +50,45 @@ def test_frontend_batch_matches_oracle():
     dev = fe.fetch(B)
     for k in ("kps", "desc", "n", "keylines", "ldesc", "nl", "pt_matches", "n_pt_matches", "line_matches", "n_line_matches", "poses", "inliers"):
         assert dev[k].tobytes() == out[k].tobytes(), k
+
+
+def test_frontend_with_distorting_camera():
+    """TUM1 camera (k1 != 0): ORB on the raw frame, LSD/LBD on the undistorted frame (Frame.cc:220-225), matching on
+    mvKeysUn inside ComputeImageBounds' grid (Frame.cc:233, :947-985)."""
+    B = 3
+    K, D = synth.TUM1_K, synth.TUM1_DIST
+    frames = synth.synth_sequence(B, 640, 480, seed=6)
+    problems = [synth.synth_pose_problem(70 + k) for k in range(B)]
+    fe = pl.Frontend(640, 480, max_batch=B, lm_caps=(320, 88))
+    fe.set_pose_problems(problems)
+    fe.set_camera(K, D)
+    out = fe.run(frames)
+    ku = fe.fetch_keys_un(B)
+    bounds = oracle.image_bounds(K, D, 640, 480)
+    o = oracle.OrbOracle(1000, 1.2, 8, 20, 7)
+    feats = []
+    for b in range(B):
+        okps, odesc = o.extract(frames[b])
+        n, nl = out["n"][b], out["nl"][b]
+        assert n == len(okps) and out["kps"][b, :n].tobytes() == okps.tobytes() and np.array_equal(out["desc"][b, :n], odesc)
+        oku = oracle.undistort_keypoints(okps, K, D)
+        assert ku[b, :n].tobytes() == oku.tobytes()
+        okl, oldesc, olf = oracle.line_extract(oracle.undistort_remap(frames[b], K, D))
+        assert nl == len(okl)
+        eq = np.array([out["keylines"][b, i].tobytes() == okl[i].tobytes() for i in range(nl)])
+        assert eq.mean() > 0.99 and np.array_equal(out["ldesc"][b, :nl][eq], oldesc[eq])
+        feats.append((oku, odesc))
+    for b in range(B):
+        pk, pd = feats[(b - 1) % B]
+        ck, cd = feats[b]
+        pm = np.stack([pk["x"], pk["y"]], 1).astype(np.float32)
+        onm, om, _ = oracle.search_for_initialization(pk, pd, ck, cd, bounds, pm, 100, 0.9, True)
+        assert out["n_pt_matches"][b] == onm and np.array_equal(out["pt_matches"][b, :len(pk)], om)
+    # a camera without distortion is the default path
+    fe.set_camera(K, (0, 0, 0, 0, 0))
+    out0 = fe.run(frames)
+    ref = pl.Frontend(640, 480, max_batch=B, lm_caps=(320, 88)); ref.set_pose_problems(problems)
+    out1 = ref.run(frames)
+    for k in ("kps", "desc", "n", "keylines", "ldesc", "nl", "pt_matches", "n_pt_matches", "line_matches", "n_line_matches"):
+        assert out0[k].tobytes() == out1[k].tobytes(), k
+    assert fe.fetch_keys_un(B).tobytes() == out0["kps"].tobytes()

@@ -286,11 +286,8 @@ __device__ __forceinline__ bool is_aligned(double a, double theta, double prec) 
 // list and the ring are written after the loop by the accepted lanes themselves.
 // kFast: prec < pi/2, isAligned folded to  n <= prec || n >= prec_hi  (prec_hi = smallest double with 2pi-n <= prec;
 // 2pi-n is exact for n in [pi,4pi], so the two forms agree bit for bit).
-#ifndef GROW_DUP_MATCH
-#define GROW_DUP_MATCH 0
-#endif
-#ifndef GROW_PUBLISH
-#define GROW_PUBLISH 1
+#ifndef GROW_SPEC
+#define GROW_SPEC 0         // speculative batched commit: bit-exact, but measured SLOWER on B200 (195 vs 168 ms at B=4736)
 #endif
 #ifndef GROW_INLINE
 #define GROW_INLINE 1
@@ -326,6 +323,7 @@ __device__ __forceinline__ int region_grow_t(const GrowCtx& C, unsigned seed, do
   const int sbits = C.ANG[sidx];                  // the seed is unused here, so this is its angle
   double reg_angle = (double)__int_as_float(sbits) * kDegToRads;
   float sumdx = s0.x, sumdy = s0.y;
+  bool dirty = false;          // reg_angle lags the sums (it is the seed's own angle until the first pixel is added)
   if (lane == 0) { C.R[0] = seed; C.ring[0] = seed; C.ANG[sidx] = sbits | kUsedBit; }
   int cnt = 1;
   __syncwarp();
@@ -367,38 +365,74 @@ __device__ __forceinline__ int region_grow_t(const GrowCtx& C, unsigned seed, do
     // aligned one (lowest lane = reference order) is added, which changes the angle, and the candidates after it
     // are tested again.  Candidates skipped before the committed lane were tested with the angle they would
     // have seen in the sequential loop, so they are never revisited.
-#if GROW_DUP_MATCH
-    const unsigned dup = __match_any_sync(0xffffffffu, pk);   // lanes naming the same pixel (later 3x3 neighbourhoods)
-#endif
     int mypos = -1;
+    auto aligned_now = [&](double th) {
+      if (kFast) { const double n1 = fabs(th - a); return (n1 <= prec) || (n1 >= prec_hi); }
+      return is_aligned(a, th, prec);
+    };
     while (live) {
-      bool al1;
-      if (kFast) { const double n1 = fabs(reg_angle - a); al1 = (n1 <= prec) || (n1 >= prec_hi); }
-      else al1 = is_aligned(a, reg_angle, prec);
-      const unsigned al = __ballot_sync(0xffffffffu, al1) & live;
-      if (!al) break;
-      const int k = __ffs(al) - 1;
-#if GROW_PUBLISH
-      if (lane == k) mypos = cnt;
-#else
-      {
-        const unsigned pkk0 = __shfl_sync(0xffffffffu, pk, k);
-        if (lane == 0) { C.R[cnt] = pkk0; C.ring[cnt & (kRing - 1)] = pkk0; }
-        if (lane == k) C.ANG[idx] = ab | kUsedBit;
+      if (dirty) { reg_angle = (double)fast_atan2_deg_l(sumdy, sumdx) * kDegToRads; dirty = false; }
+      const unsigned A = __ballot_sync(0xffffffffu, aligned_now(reg_angle)) & live;
+      if (!A) break;
+#if GROW_SPEC
+      if (A & (A - 1u)) {
+        // Several candidates are aligned with the current angle.  Speculate that they are all accepted in order: walk them
+        // once accumulating the cos/sin sums sequentially (the only part that has to be serial for bit-exact fp32 sums),
+        // every lane keeping the sums as they stand just BEFORE its own turn; then each lane evaluates the region angle it
+        // would have seen (one atan2 per lane, in parallel, instead of one per accepted pixel in sequence) and re-checks its
+        // own decision.  Everything before the first lane whose decision differs from the speculation is final.
+        float tx = sumdx, ty = sumdy, sx = sumdx, sy = sumdy;
+        unsigned Aw = A, acc = 0u;
+        int killer = 64;                         // lowest speculated-accepted lane naming my pixel (64 = none)
+        while (Aw) {
+          const int k = __ffs(Aw) - 1;
+          tx = __fadd_rn(tx, __shfl_sync(0xffffffffu, csv.x, k));
+          ty = __fadd_rn(ty, __shfl_sync(0xffffffffu, csv.y, k));
+          if (lane > k) { sx = tx; sy = ty; }
+          acc |= 1u << k;
+          const unsigned d = __ballot_sync(0xffffffffu, pk == __shfl_sync(0xffffffffu, pk, k)) & ~((2u << k) - 1u);
+          if (((d >> lane) & 1u) && killer == 64) killer = k;
+          Aw &= ~(d | (1u << k));
+        }
+        const unsigned dead = __ballot_sync(0xffffffffu, killer != 64);
+        double th = reg_angle;
+        if (acc & lt) th = (double)fast_atan2_deg_l(sy, sx) * kDegToRads;
+        const bool alj = aligned_now(th);
+        const unsigned almask = __ballot_sync(0xffffffffu, alj);
+        const unsigned mism = (almask ^ acc) & live & ~dead;    // acc == speculated decisions of the lanes still in play
+        if (!mism) {
+          if ((acc >> lane) & 1u) mypos = cnt + __popc(acc & lt);
+          cnt += __popc(acc);
+          sumdx = tx; sumdy = ty; dirty = true;
+          live = 0u;
+          break;
+        }
+        const int f = __ffs(mism) - 1;
+        unsigned accf = acc & ((1u << f) - 1u);
+        float bx = __shfl_sync(0xffffffffu, sx, f), by = __shfl_sync(0xffffffffu, sy, f);
+        unsigned deadf = __ballot_sync(0xffffffffu, killer < f);
+        if ((almask >> f) & 1u) {                // f was skipped by the speculation but is aligned at its turn: accept it
+          bx = __fadd_rn(bx, __shfl_sync(0xffffffffu, csv.x, f));
+          by = __fadd_rn(by, __shfl_sync(0xffffffffu, csv.y, f));
+          accf |= 1u << f;
+          deadf |= __ballot_sync(0xffffffffu, pk == __shfl_sync(0xffffffffu, pk, f));
+        }
+        if ((accf >> lane) & 1u) mypos = cnt + __popc(accf & lt);
+        if (accf) { cnt += __popc(accf); sumdx = bx; sumdy = by; dirty = true; }
+        live &= ~(((2u << f) - 1u) | deadf);
+        continue;
       }
 #endif
+      const int k = __ffs(A) - 1;
+      if (lane == k) mypos = cnt;
       cnt++;
       sumdx = __fadd_rn(sumdx, __shfl_sync(0xffffffffu, csv.x, k));
       sumdy = __fadd_rn(sumdy, __shfl_sync(0xffffffffu, csv.y, k));
-      reg_angle = (double)fast_atan2_deg_l(sumdy, sumdx) * kDegToRads;
+      dirty = true;
       // everything up to k has been decided; the same pixel in a later 3x3 is now USED
-#if GROW_DUP_MATCH
-      live &= ~(((2u << k) - 1u) | __shfl_sync(0xffffffffu, dup, k));
-#else
       live &= ~(((2u << k) - 1u) | __ballot_sync(0xffffffffu, pk == __shfl_sync(0xffffffffu, pk, k)));
-#endif
     }
-    if (GROW_PUBLISH && mypos >= 0) {      // publish: every accepted lane owns its pixel
+    if (mypos >= 0) {      // publish: every accepted lane owns its pixel
       C.ANG[idx] = ab | kUsedBit;
       C.R[mypos] = pk;
       C.ring[mypos & (kRing - 1)] = pk;
@@ -406,6 +440,7 @@ __device__ __forceinline__ int region_grow_t(const GrowCtx& C, unsigned seed, do
     }
     __syncwarp();
   }
+  if (dirty) reg_angle = (double)fast_atan2_deg_l(sumdy, sumdx) * kDegToRads;
   reg_angle_out = reg_angle;
   return cnt;
 }

@@ -12,11 +12,11 @@
 
 namespace pl {
 struct RemapEntry { short ix, iy; unsigned short tab; unsigned short pad; };   // 8 B per output pixel, shared by all frames
-__constant__ int c_remap_tab[1024 * 4];
 
 // 4 consecutive output pixels per thread (uchar4 store); the 2x2 source taps are gathered through L1/L2
 __global__ void __launch_bounds__(256) k_remap(const uint8_t* __restrict__ src, int sstride, long long sframe, int w, int h,
-                                               const RemapEntry* __restrict__ map, uint8_t* __restrict__ dst, int dstride, long long dframe) {
+                                               const RemapEntry* __restrict__ map, const int4* __restrict__ tab,
+                                               uint8_t* __restrict__ dst, int dstride, long long dframe) {
   const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
   if (x4 >= w) return;
   const uint8_t* S = src + (long long)blockIdx.z * sframe;
@@ -25,9 +25,9 @@ __global__ void __launch_bounds__(256) k_remap(const uint8_t* __restrict__ src, 
   for (int k = 0; k < 4; k++) {
     const int x = min(x4 + k, w - 1);
     const RemapEntry e = map[(long long)y * w + x];
-    const int* t = &c_remap_tab[e.tab * 4];
+    const int4 t = __ldg(&tab[e.tab]);     // 16 KB table, L1-resident (per-lane index: not constant memory)
     auto px = [&](int yy, int xx) { return (xx >= 0 && xx < w && yy >= 0 && yy < h) ? (int)S[(long long)yy * sstride + xx] : 0; };
-    const int acc = px(e.iy, e.ix) * t[0] + px(e.iy, e.ix + 1) * t[1] + px(e.iy + 1, e.ix) * t[2] + px(e.iy + 1, e.ix + 1) * t[3];
+    const int acc = px(e.iy, e.ix) * t.x + px(e.iy, e.ix + 1) * t.y + px(e.iy + 1, e.ix) * t.z + px(e.iy + 1, e.ix + 1) * t.w;
     o[k] = (uint8_t)((acc + (1 << 14)) >> 15);
   }
   uint8_t* D = dst + (long long)blockIdx.z * dframe + (long long)y * dstride;
@@ -124,6 +124,7 @@ using namespace pl;
 struct PLUndistort {
   int w, h; CamD cam; float K[4], D[5];
   RemapEntry* d_map = nullptr;
+  int4* d_tab = nullptr;
   uint8_t *d_src = nullptr, *d_dst = nullptr; int staged = 0;
   cudaStream_t stream = nullptr;
 };
@@ -131,7 +132,7 @@ static CamD make_cam(const float* K, const float* D) { return CamD{(double)K[0],
 
 extern "C" void pl_undistort_destroy(PLUndistort* h) {
   if (!h) return;
-  cudaFree(h->d_map); cudaFree(h->d_src); cudaFree(h->d_dst);
+  cudaFree(h->d_map); cudaFree(h->d_tab); cudaFree(h->d_src); cudaFree(h->d_dst);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -179,7 +180,8 @@ extern "C" int pl_undistort_create(const float* K, const float* dist5, int width
   }
   cudaError_t e = cudaMalloc((void**)&h->d_map, map.size() * sizeof(RemapEntry));
   if (e == cudaSuccess) e = cudaMemcpy(h->d_map, map.data(), map.size() * sizeof(RemapEntry), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_remap_tab, tab, sizeof(tab));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_tab, sizeof(tab));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_tab, tab, sizeof(tab), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { set_error("pl_undistort_create: %s", cudaGetErrorString(e)); pl_undistort_destroy(h); return PL_ERR_CUDA; }
   *out = h;
@@ -189,7 +191,7 @@ extern "C" int pl_undistort_remap_batch_dev(PLUndistort* h, const uint8_t* src, 
                                             int dstride, size_t dframe, void* stream) {
   PL_ARG(h && src && dst && B >= 1 && sstride >= h->w && dstride >= h->w);
   k_remap<<<dim3((h->w + 1023) / 1024, h->h, B), 256, 0, stream ? (cudaStream_t)stream : h->stream>>>(
-      src, sstride, (long long)sframe, h->w, h->h, h->d_map, dst, dstride, (long long)dframe);
+      src, sstride, (long long)sframe, h->w, h->h, h->d_map, h->d_tab, dst, dstride, (long long)dframe);
   PL_LAUNCH_CHECK();
   return PL_OK;
 }

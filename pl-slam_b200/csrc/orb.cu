@@ -28,7 +28,7 @@ constexpr int kEdge = 19;        // EDGE_THRESHOLD
 constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE
 constexpr int kMaxWin = 72;      // max FAST cell window side (cell + 6)
 
-__constant__ int8_t c_pattern[256 * 4];
+__device__ char4 g_pattern[256];      // rBRIEF pairs; global (L1) because every lane reads a different entry
 __constant__ int c_umax[16];
 static const int8_t h_pattern[256 * 4] = {
 #include "../data/orb_pattern_31.inc"
@@ -632,8 +632,8 @@ __global__ void __launch_bounds__(32 * kDescWarps) k_describe(OrbParams P, const
     const int u = lane - kHalfPatch;
     const uint8_t* c0 = img + (long long)py * pitch + px + u;
     int colsum = 0;
-#pragma unroll 1
-    for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
+#pragma unroll
+    for (int v = -kHalfPatch; v <= kHalfPatch; v++) {      // fully unrolled: 31 independent row loads in flight
       if (lane <= 2 * kHalfPatch && abs(u) <= c_umax[abs(v)]) {
         const int p = c0[v * pitch];
         colsum += p; m01 += v * p;
@@ -654,8 +654,8 @@ __global__ void __launch_bounds__(32 * kDescWarps) k_describe(OrbParams P, const
   int val = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
-    const int8_t* pt = &c_pattern[(lane * 8 + k) * 4];
-    float x0 = (float)pt[0], y0 = (float)pt[1], x1 = (float)pt[2], y1 = (float)pt[3];
+    const char4 pt = __ldg(&g_pattern[lane * 8 + k]);
+    float x0 = (float)pt.x, y0 = (float)pt.y, x1 = (float)pt.z, y1 = (float)pt.w;
     int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
     int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
     int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
@@ -829,7 +829,8 @@ extern "C" int pl_orb_create(const PLOrbConfig* cfg, PLOrb** out) {
 #define ORB_TRY(e) do { int _r = (e); if (_r) { pl_orb_destroy(h); return _r; } } while (0)
 #define ORB_CUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { set_error("%s -> %s", #e, cudaGetErrorString(_e)); pl_orb_destroy(h); return PL_ERR_CUDA; } } while (0)
   ORB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  ORB_CUDA(cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
+  static_assert(sizeof(h_pattern) == sizeof(char4) * 256, "pattern size");
+  ORB_CUDA(cudaMemcpyToSymbol(g_pattern, h_pattern, sizeof(h_pattern)));
   ORB_CUDA(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
   ORB_TRY(dev_alloc(&h->d_cells, h->cells.size()));
   ORB_CUDA(cudaMemcpy(h->d_cells, h->cells.data(), h->cells.size() * sizeof(CellInfo), cudaMemcpyHostToDevice));

@@ -298,6 +298,28 @@ int pl_frame_is_in_frustum_lines(const float* Tcw, const float* Ow, const float*
                                  float viewing_cos_limit, int n, const double* pos, const double* normal, const float* min_dist,
                                  const float* max_dist, uint8_t* inview, float* proj, int* level, float* viewcos);
 
+/* ------------------------------------------------------------------ LocalMapping matchers
+ * ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo=false) (src/ORBmatcher.cc:720-911), monocular.
+ * keys*_un = mvKeysUn, has_mp* = GetMapPoint(i) != NULL, fv* = DBoW2 FeatureVector as CSR (node ids ascending as in std::map,
+ * fv_start[nn+1], fv_items = feature indices in insertion order), F12 row-major 3x3, Cw1 = pKF1->GetCameraCenter(),
+ * R2w/t2w = pKF2 rotation (row-major 3x3) / translation, K2 = {fx,fy,cx,cy}, scale_factors2 = mvScaleFactors,
+ * level_sigma2_2 = mvLevelSigma2.  matches12[i] = idx2 or -1 (vMatchedPairs = the pairs with idx2 >= 0); returns nmatches. */
+int pl_orb_search_for_triangulation(const PLKeyPoint* keys1_un, const uint8_t* desc1, const uint8_t* has_mp1, int n1,
+                                    const PLKeyPoint* keys2_un, const uint8_t* desc2, const uint8_t* has_mp2, int n2,
+                                    const unsigned* fv1_nodes, const int* fv1_start, const int* fv1_items, int nn1,
+                                    const unsigned* fv2_nodes, const int* fv2_start, const int* fv2_items, int nn2,
+                                    const float* F12, const float* Cw1, const float* R2w, const float* t2w, const float* K2,
+                                    const float* scale_factors2, const float* level_sigma2_2, int nlevels,
+                                    int check_orientation, int* matches12);
+/* The search half of ORBmatcher::Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:914-1034): best keypoint of the keyframe for
+ * every map point (best_idx = -1 / best_dist = 256 when skipped or nothing qualifies).  skip[i] = !pMP || isBad || IsInKeyFrame;
+ * the caller applies :1036-1061 (Replace / AddObservation) to the points with best_dist <= TH_LOW (50) in order. */
+int pl_orb_fuse_search(const PLKeyPoint* keys_un, const uint8_t* desc, int n, const float* bounds, const float* Tcw,
+                       const float* Ow, const float* K, const float* scale_factors, const float* inv_level_sigma2, int nlevels,
+                       float log_scale_factor, int n_mp, const uint8_t* skip, const float* pos, const float* normal,
+                       const float* min_dist, const float* max_dist, const uint8_t* mp_desc, float th, int* best_idx,
+                       int* best_dist);
+
 #ifdef __cplusplus
 }
 #endif

@@ -451,3 +451,42 @@ def is_in_frustum_lines(Tcw, Ow, K, bounds, log_scale_factor, cos_limit, pos, no
                                      C.c_int(n), _p(pos), _p(normal), _p(min_dist), _p(max_dist), _p(inview), _p(proj),
                                      _p(level), _p(vc))
     return inview, proj, level, vc
+
+
+# ----------------------------------------------------------------- LocalMapping matchers (ORBmatcher.cc:720-1065)
+def _csr(fv):
+    """fv: dict node -> list of feature indices (DBoW2::FeatureVector) -> (nodes asc, start, items)."""
+    nodes = np.array(sorted(fv), np.uint32)
+    start = np.zeros(len(nodes) + 1, np.int32); items = []
+    for i, nd in enumerate(nodes):
+        items += list(fv[int(nd)]); start[i + 1] = len(items)
+    return nodes, start, np.array(items, np.int32).reshape(-1)
+
+
+def search_for_triangulation(k1, d1, has_mp1, k2, d2, has_mp2, fv1, fv2, F12, Cw1, R2w, t2w, K2, scale_factors2, level_sigma2_2,
+                             check_orientation=True):
+    k1 = np.ascontiguousarray(k1, KP_DTYPE); k2 = np.ascontiguousarray(k2, KP_DTYPE)
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    m1 = np.ascontiguousarray(has_mp1, np.uint8); m2 = np.ascontiguousarray(has_mp2, np.uint8)
+    n1a, s1, i1 = _csr(fv1); n2a, s2, i2 = _csr(fv2)
+    F = _f32(F12); Cw = _f32(Cw1); R = _f32(R2w); t = _f32(t2w); K = _f32(K2); sf = _f32(scale_factors2); sg = _f32(level_sigma2_2)
+    out = np.full(len(k1), -1, np.int32)
+    L = lib(); L.oracle_search_for_triangulation.restype = C.c_int
+    nm = L.oracle_search_for_triangulation(_p(k1), _p(d1), _p(m1), C.c_int(len(k1)), _p(k2), _p(d2), _p(m2), C.c_int(len(k2)),
+                                           _p(n1a), _p(s1), _p(i1), C.c_int(len(n1a)), _p(n2a), _p(s2), _p(i2), C.c_int(len(n2a)),
+                                           _p(F), _p(Cw), _p(R), _p(t), _p(K), _p(sf), _p(sg), C.c_int(int(check_orientation)), _p(out))
+    return nm, out
+
+
+def fuse_search(keys, desc, bounds, Tcw, Ow, K, scale_factors, inv_level_sigma2, log_scale_factor, skip, pos, normal, min_dist,
+                max_dist, mp_desc, th=3.0):
+    keys = np.ascontiguousarray(keys, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+    b = _f32(bounds); T = _f32(Tcw); O = _f32(Ow); Kc = _f32(K); sf = _f32(scale_factors); iv = _f32(inv_level_sigma2)
+    n_mp = len(pos)
+    sk = None if skip is None else np.ascontiguousarray(skip, np.uint8)
+    pos = _f32(pos); normal = _f32(normal); mn = _f32(min_dist); mx = _f32(max_dist); md = np.ascontiguousarray(mp_desc, np.uint8)
+    bi = np.zeros(n_mp, np.int32); bd = np.zeros(n_mp, np.int32)
+    lib().oracle_fuse_search(_p(keys), _p(desc), C.c_int(len(keys)), _p(b), _p(T), _p(O), _p(Kc), _p(sf), _p(iv),
+                             C.c_float(log_scale_factor), C.c_int(len(sf)), C.c_int(n_mp), _p(sk), _p(pos), _p(normal), _p(mn), _p(mx),
+                             _p(md), C.c_float(th), _p(bi), _p(bd))
+    return bi, bd

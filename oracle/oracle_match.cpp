@@ -473,4 +473,125 @@ int oracle_line_search_by_projection_lines(const void* kls_, const double* lfunc
   }
   return nmatches;
 }
+
+// ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:720-911), monocular (bOnlyStereo = false, mvuRight < 0).
+// DBoW2 feature vectors are inputs (node ids ascending as in std::map, items in insertion order): DBoW2 is a third-party
+// dependency (Thirdparty/DBoW2) outside the path.  Literal quirk kept: this reference never sets vbMatched2, so every
+// idx1 picks its best idx2 independently.  matches12[i] = idx2 or -1; returns nmatches.
+int oracle_search_for_triangulation(const void* keys1_, const uint8_t* desc1, const uint8_t* has_mp1, int n1,
+                                    const void* keys2_, const uint8_t* desc2, const uint8_t* has_mp2, int n2,
+                                    const unsigned* fv1_nodes, const int* fv1_start, const int* fv1_items, int nn1,
+                                    const unsigned* fv2_nodes, const int* fv2_start, const int* fv2_items, int nn2,
+                                    const float* F12, const float* Cw1, const float* R2w, const float* t2w, const float* K2,
+                                    const float* scaleFactors2, const float* levelSigma2_2, int check_orientation,
+                                    int* matches12) {
+  const KeyPoint* k1 = (const KeyPoint*)keys1_;
+  const KeyPoint* k2 = (const KeyPoint*)keys2_;
+  const int TH_LOW = 50;
+  // epipole in image 2: C2 = R2w*Cw + t2w (cv::gemm fp32 order), ex = fx*C2x*invz + cx
+  float C2[3];
+  for (int i = 0; i < 3; i++) C2[i] = ((R2w[3 * i] * Cw1[0] + R2w[3 * i + 1] * Cw1[1]) + R2w[3 * i + 2] * Cw1[2]) + t2w[i];
+  const float invz = 1.0f / C2[2];
+  const float ex = K2[0] * C2[0] * invz + K2[2], ey = K2[1] * C2[1] * invz + K2[3];
+  int nmatches = 0;
+  for (int i = 0; i < n1; i++) matches12[i] = -1;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  int a = 0, b = 0;
+  while (a < nn1 && b < nn2) {
+    if (fv1_nodes[a] == fv2_nodes[b]) {
+      for (int i1 = fv1_start[a]; i1 < fv1_start[a + 1]; i1++) {
+        const int idx1 = fv1_items[i1];
+        if (has_mp1[idx1]) continue;
+        const KeyPoint& kp1 = k1[idx1];
+        int bestDist = TH_LOW, bestIdx2 = -1;
+        for (int i2 = fv2_start[b]; i2 < fv2_start[b + 1]; i2++) {
+          const int idx2 = fv2_items[i2];
+          if (has_mp2[idx2]) continue;
+          const int dist = descriptor_distance(desc1 + 32 * idx1, desc2 + 32 * idx2);
+          if (dist > TH_LOW || dist > bestDist) continue;
+          const KeyPoint& kp2 = k2[idx2];
+          const float distex = ex - kp2.x, distey = ey - kp2.y;
+          if (distex * distex + distey * distey < 100 * scaleFactors2[kp2.octave]) continue;
+          // CheckDistEpipolarLine (ORBmatcher.cc:155-172)
+          const float la = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+          const float lb = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+          const float lc = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+          const float num = la * kp2.x + lb * kp2.y + lc;
+          const float den = la * la + lb * lb;
+          if (den == 0) continue;
+          const float dsqr = num * num / den;
+          if (dsqr < 3.84 * levelSigma2_2[kp2.octave]) { bestIdx2 = idx2; bestDist = dist; }
+        }
+        if (bestIdx2 >= 0) {
+          matches12[idx1] = bestIdx2;
+          nmatches++;
+          if (check_orientation) rotHist[rot_bin(kp1.angle, k2[bestIdx2].angle)].push_back(idx1);
+        }
+      }
+      a++; b++;
+    } else if (fv1_nodes[a] < fv2_nodes[b]) {
+      while (a < nn1 && fv1_nodes[a] < fv2_nodes[b]) a++;      // lower_bound
+    } else {
+      while (b < nn2 && fv2_nodes[b] < fv1_nodes[a]) b++;
+    }
+  }
+  if (check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx1 : rotHist[i]) { matches12[idx1] = -1; nmatches--; }
+    }
+  }
+  return nmatches;
+}
+
+// The search half of ORBmatcher::Fuse(KeyFrame*, vector<MapPoint*>, th) (src/ORBmatcher.cc:914-1065): for every map
+// point the best keypoint of the keyframe (bestIdx, bestDist; -1/256 when it is skipped or nothing qualifies).  The map
+// surgery that follows (Replace / AddObservation, :1036-1061) is sequential map logic outside the path; `skip` carries
+// its loop-entry conditions (NULL, isBad, IsInKeyFrame).  Tcw row-major 4x4, Ow = camera centre.
+void oracle_fuse_search(const void* keys_, const uint8_t* desc, int n, const float* bounds, const float* Tcw, const float* Ow,
+                        const float* K, const float* scaleFactors, const float* invLevelSigma2, float logScaleFactor,
+                        int nScaleLevels, int n_mp, const uint8_t* skip, const float* pos, const float* normal,
+                        const float* minDist, const float* maxDist, const uint8_t* mp_desc, float th, int* best_idx,
+                        int* best_dist) {
+  const KeyPoint* k = (const KeyPoint*)keys_;
+  Grid g; g.init(bounds);
+  assign_points(g, k, n);
+  std::vector<int> cand;
+  for (int i = 0; i < n_mp; i++) {
+    best_idx[i] = -1; best_dist[i] = 256;
+    if (skip && skip[i]) continue;
+    const float* P = pos + 3 * i;
+    float Pc[3];
+    for (int r = 0; r < 3; r++) Pc[r] = ((Tcw[4 * r] * P[0] + Tcw[4 * r + 1] * P[1]) + Tcw[4 * r + 2] * P[2]) + Tcw[4 * r + 3];
+    if (Pc[2] < 0.0f) continue;
+    const float invz = 1 / Pc[2];
+    const float x = Pc[0] * invz, y = Pc[1] * invz;
+    const float u = K[0] * x + K[2], v = K[1] * y + K[3];
+    if (!(u >= bounds[0] && u < bounds[2] && v >= bounds[1] && v < bounds[3])) continue;       // KeyFrame::IsInImage
+    const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
+    const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
+    if (dist3D < minDist[i] || dist3D > maxDist[i]) continue;
+    const float* Pn = normal + 3 * i;
+    const double dot = (double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2];
+    if (dot < 0.5 * dist3D) continue;
+    const float ratio = maxDist[i] / dist3D;                                                   // MapPoint::PredictScale(dist, pKF)
+    int lvl = (int)std::ceil(std::log((double)ratio) / (double)logScaleFactor);
+    if (lvl < 0) lvl = 0; else if (lvl >= nScaleLevels) lvl = nScaleLevels - 1;
+    const float radius = th * scaleFactors[lvl];
+    features_in_area(g, k, u, v, radius, -1, -1, cand);                                        // KeyFrame::GetFeaturesInArea
+    int bestDist = 256, bestIdx = -1;
+    for (int idx : cand) {
+      const KeyPoint& kp = k[idx];
+      if (kp.octave < lvl - 1 || kp.octave > lvl) continue;
+      const float ex = u - kp.x, ey = v - kp.y;
+      const float e2 = ex * ex + ey * ey;
+      if (e2 * invLevelSigma2[kp.octave] > 5.99) continue;
+      const int dist = descriptor_distance(mp_desc + 32 * i, desc + 32 * idx);
+      if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+    }
+    best_idx[i] = bestIdx; best_dist[i] = bestDist;
+  }
+}
 }

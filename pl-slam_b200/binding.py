@@ -648,3 +648,47 @@ def isInFrustumLines(Tcw, Ow, K, bounds, log_scale_factor, viewingCosLimit, pos,
                                              C.c_float(viewingCosLimit), C.c_int(n), _p(pos), _p(normal), _p(min_dist),
                                              _p(max_dist), _p(inview), _p(proj), _p(level), _p(vc)))
     return inview, proj, level, vc
+
+
+# ----------------------------------------------------------------- LocalMapping matchers (reference src/ORBmatcher.cc:720-1065)
+def _fv_csr(fv):
+    """DBoW2::FeatureVector (dict node -> feature indices, std::map order = ascending node id) as CSR arrays."""
+    nodes = np.array(sorted(fv), np.uint32)
+    start = np.zeros(len(nodes) + 1, np.int32); items = []
+    for i, nd in enumerate(nodes):
+        items += list(fv[int(nd)]); start[i + 1] = len(items)
+    return nodes, start, np.array(items, np.int32).reshape(-1)
+
+
+def _search_for_triangulation(self, keys1_un, desc1, has_mp1, keys2_un, desc2, has_mp2, fv1, fv2, F12, Cw1, R2w, t2w, K2,
+                              scale_factors2, level_sigma2_2):
+    """ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, false) -> (nmatches, matches12[n1])."""
+    k1 = np.ascontiguousarray(keys1_un, KP_DTYPE); k2 = np.ascontiguousarray(keys2_un, KP_DTYPE)
+    d1 = _u8(desc1); d2 = _u8(desc2); m1 = _u8(has_mp1); m2 = _u8(has_mp2)
+    n1a, s1, i1 = _fv_csr(fv1); n2a, s2, i2 = _fv_csr(fv2)
+    F = _f32(F12); Cw = _f32(Cw1); R = _f32(R2w); t = _f32(t2w); K = _f32(K2); sf = _f32(scale_factors2); sg = _f32(level_sigma2_2)
+    out = np.full(len(k1), -1, np.int32)
+    nm = check(lib().pl_orb_search_for_triangulation(
+        _p(k1), _p(d1), _p(m1), C.c_int(len(k1)), _p(k2), _p(d2), _p(m2), C.c_int(len(k2)), _p(n1a), _p(s1), _p(i1), C.c_int(len(n1a)),
+        _p(n2a), _p(s2), _p(i2), C.c_int(len(n2a)), _p(F), _p(Cw), _p(R), _p(t), _p(K), _p(sf), _p(sg), C.c_int(len(sf)),
+        C.c_int(int(self.mbCheckOrientation)), _p(out)))
+    return nm, out
+
+
+def _fuse_search(self, keys_un, desc, bounds, Tcw, Ow, K, scale_factors, inv_level_sigma2, log_scale_factor, skip, pos, normal,
+                 min_dist, max_dist, mp_desc, th=3.0):
+    """Search half of ORBmatcher::Fuse(pKF, vpMapPoints, th) -> (best_idx[n_mp], best_dist[n_mp])."""
+    keys = np.ascontiguousarray(keys_un, KP_DTYPE); desc = _u8(desc)
+    b = _f32(bounds); T = _f32(Tcw); O = _f32(Ow); Kc = _f32(K); sf = _f32(scale_factors); iv = _f32(inv_level_sigma2)
+    n_mp = len(pos)
+    sk = None if skip is None else _u8(skip)
+    pos = _f32(pos); normal = _f32(normal); mn = _f32(min_dist); mx = _f32(max_dist); md = _u8(mp_desc)
+    bi = np.zeros(n_mp, np.int32); bd = np.zeros(n_mp, np.int32)
+    check(lib().pl_orb_fuse_search(_p(keys), _p(desc), C.c_int(len(keys)), _p(b), _p(T), _p(O), _p(Kc), _p(sf), _p(iv),
+                                   C.c_int(len(sf)), C.c_float(log_scale_factor), C.c_int(n_mp), _p(sk), _p(pos), _p(normal), _p(mn),
+                                   _p(mx), _p(md), C.c_float(th), _p(bi), _p(bd)))
+    return bi, bd
+
+
+ORBmatcher.SearchForTriangulation = _search_for_triangulation
+ORBmatcher.FuseSearch = _fuse_search

@@ -684,6 +684,128 @@ __global__ void __launch_bounds__(32) k_line_search(LineSearchArgs A) {
   if (lane == 0) A.nmatches[b] = nmatches;
 }
 
+// ------------------------------------------------------------------------------------------------ §8f.2 LocalMapping matchers
+// Every query is independent here (one thread per KF1 keypoint / one warp per map point):
+//   ORBmatcher::SearchForTriangulation   src/ORBmatcher.cc:720-911
+//   ORBmatcher::Fuse (search half)       src/ORBmatcher.cc:914-1034
+// DBoW2 feature vectors and the map surgery after Fuse's search are outside the path (third-party / sequential map logic).
+struct TriArgs {
+  const PLKeyPoint *k1, *k2; const uint8_t *d1, *d2, *mp1, *mp2;
+  const int *q_idx1, *q_s, *q_e, *fv2_items; int nq, n1;
+  float F[9], ex, ey; const float *scale2, *sigma2_2; int checkOri;
+  int* matches12; int* nmatches; unsigned char* bins;
+};
+// One block.  Every query (idx1, candidate range in KF2's node) is independent: the reference never sets vbMatched2.
+__global__ void __launch_bounds__(256) k_search_triangulation(TriArgs A) {
+  __shared__ int hist[HISTO];
+  __shared__ int s_nm, s_keep[3];
+  const int tid = threadIdx.x;
+  if (tid < HISTO) hist[tid] = 0;
+  if (tid == 0) s_nm = 0;
+  for (int i = tid; i < A.n1; i += blockDim.x) { A.matches12[i] = -1; A.bins[i] = 255; }
+  __syncthreads();
+  for (int q = tid; q < A.nq; q += blockDim.x) {
+    const int idx1 = A.q_idx1[q];
+    if (A.mp1[idx1]) continue;
+    const PLKeyPoint kp1 = A.k1[idx1];
+    // epipolar line of kp1 in image 2 (CheckDistEpipolarLine, :155-172): l = x1' F12
+    const float la = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, A.F[0]), __fmul_rn(kp1.y, A.F[3])), A.F[6]);
+    const float lb = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, A.F[1]), __fmul_rn(kp1.y, A.F[4])), A.F[7]);
+    const float lc = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, A.F[2]), __fmul_rn(kp1.y, A.F[5])), A.F[8]);
+    const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+    int bestDist = 50, bestIdx2 = -1;
+    for (int i2 = A.q_s[q]; i2 < A.q_e[q]; i2++) {
+      const int idx2 = A.fv2_items[i2];
+      if (A.mp2[idx2]) continue;
+      const int dist = hamming256(A.d1 + 32 * idx1, A.d2 + 32 * idx2);
+      if (dist > 50 || dist > bestDist) continue;
+      const PLKeyPoint kp2 = A.k2[idx2];
+      const float dx = __fsub_rn(A.ex, kp2.x), dy = __fsub_rn(A.ey, kp2.y);
+      if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, A.scale2[kp2.octave])) continue;
+      const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, kp2.x), __fmul_rn(lb, kp2.y)), lc);
+      if (den == 0.f) continue;
+      const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+      if ((double)dsqr < 3.84 * (double)A.sigma2_2[kp2.octave]) { bestIdx2 = idx2; bestDist = dist; }
+    }
+    if (bestIdx2 >= 0) {
+      A.matches12[idx1] = bestIdx2;
+      atomicAdd(&s_nm, 1);
+      if (A.checkOri) { const int bin = rot_bin(kp1.angle, A.k2[bestIdx2].angle); A.bins[idx1] = (unsigned char)bin; atomicAdd(&hist[bin], 1); }
+    }
+  }
+  __syncthreads();
+  if (A.checkOri) {
+    if (tid == 0) { int a, b, c; three_maxima(hist, a, b, c); s_keep[0] = a; s_keep[1] = b; s_keep[2] = c; }
+    __syncthreads();
+    for (int i = tid; i < A.n1; i += blockDim.x) {
+      const int bin = A.bins[i];
+      if (bin != 255 && bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) { A.matches12[i] = -1; atomicSub(&s_nm, 1); }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *A.nmatches = s_nm;
+}
+
+struct FuseArgs {
+  const PLKeyPoint* keys; const uint8_t* desc; int n; float bounds[4]; float T[16], Ow[3], K[4];
+  const float *scaleFactors, *invSigma2; float logScaleFactor; int nLevels;
+  int n_mp; const uint8_t* skip; const float *pos, *normal, *minDist, *maxDist; const uint8_t* mp_desc; float th;
+  int *best_idx, *best_dist;
+};
+struct SkipChi2 {
+  const PLKeyPoint* k; const float* inv; float u, v;
+  __device__ bool operator()(int id, int) const {
+    const float ex = __fsub_rn(u, k[id].x), ey = __fsub_rn(v, k[id].y);
+    const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+    return (double)__fmul_rn(e2, inv[k[id].octave]) > 5.99;
+  }
+};
+constexpr int kFuseWarps = 16;
+__global__ void __launch_bounds__(32 * kFuseWarps) k_fuse_search(FuseArgs A) {
+  extern __shared__ unsigned char smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  SmemGrid sg = carve_grid(smem, A.n);
+  const GridP g = make_grid(A.bounds);
+  if (wid == 0) build_point_grid(A.keys, A.n, g, sg.start, sg.fill, sg.items, lane);
+  __syncthreads();
+  for (int i = wid; i < A.n_mp; i += kFuseWarps) {
+    int bi = -1, bd = 256;
+    bool go = !(A.skip && A.skip[i]);
+    float u = 0.f, v = 0.f; int lvl = 0;
+    if (go) {
+      const float P[3] = {A.pos[3 * i], A.pos[3 * i + 1], A.pos[3 * i + 2]};
+      float Pc[3];
+      for (int r = 0; r < 3; r++)
+        Pc[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A.T[4 * r], P[0]), __fmul_rn(A.T[4 * r + 1], P[1])), __fmul_rn(A.T[4 * r + 2], P[2])), A.T[4 * r + 3]);
+      go = !(Pc[2] < 0.0f);
+      if (go) {
+        const float invz = __fdiv_rn(1.0f, Pc[2]);
+        u = __fadd_rn(__fmul_rn(A.K[0], __fmul_rn(Pc[0], invz)), A.K[2]);
+        v = __fadd_rn(__fmul_rn(A.K[1], __fmul_rn(Pc[1], invz)), A.K[3]);
+        go = (u >= A.bounds[0] && u < A.bounds[2] && v >= A.bounds[1] && v < A.bounds[3]);     // KeyFrame::IsInImage
+      }
+      if (go) {
+        const float PO[3] = {__fsub_rn(P[0], A.Ow[0]), __fsub_rn(P[1], A.Ow[1]), __fsub_rn(P[2], A.Ow[2])};
+        const float dist3D = (float)sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
+        go = !(dist3D < A.minDist[i] || dist3D > A.maxDist[i]);
+        if (go) {
+          const double dot = (double)PO[0] * A.normal[3 * i] + (double)PO[1] * A.normal[3 * i + 1] + (double)PO[2] * A.normal[3 * i + 2];
+          go = !(dot < 0.5 * (double)dist3D);
+          const float ratio = __fdiv_rn(A.maxDist[i], dist3D);
+          lvl = (int)ceil(log((double)ratio) / (double)A.logScaleFactor);
+          if (lvl < 0) lvl = 0; else if (lvl >= A.nLevels) lvl = A.nLevels - 1;
+        }
+      }
+    }
+    if (go) {     // warp-uniform: every lane computed the same scalars
+      SkipChi2 skip{A.keys, A.invSigma2, u, v};
+      const Top2 t = window_top2(A.keys, A.desc, sg.start, sg.items, g, u, v, __fmul_rn(A.th, A.scaleFactors[lvl]), lvl - 1, lvl,
+                                 A.mp_desc + 32 * (long long)i, skip, lane);
+      if (t.best != KEY_NONE) { bi = key_idx(t.best); bd = key_dist(t.best); }
+    }
+    if (lane == 0) { A.best_idx[i] = bi; A.best_dist[i] = bd; }
+  }
+}
 }  // namespace pl
 
 // ================================================================================================ C ABI
@@ -977,4 +1099,87 @@ extern "C" int pl_lsd_search_by_projection_lines(const void* keylines, const dou
                                                  const uint8_t* preassigned, int* match) {
   return line_search_host(1, keylines, linefunc, desc, n, bounds, n_ml, in_view, proj, ml_desc, nullptr, view_cos, th, nnratio,
                           preassigned, match);
+}
+
+// ------------------------------------------------------------------------------------------------ §8f.2 wrappers
+
+extern "C" int pl_orb_search_for_triangulation(const PLKeyPoint* keys1_un, const uint8_t* desc1, const uint8_t* has_mp1, int n1,
+                                               const PLKeyPoint* keys2_un, const uint8_t* desc2, const uint8_t* has_mp2, int n2,
+                                               const unsigned* fv1_nodes, const int* fv1_start, const int* fv1_items, int nn1,
+                                               const unsigned* fv2_nodes, const int* fv2_start, const int* fv2_items, int nn2,
+                                               const float* F12, const float* Cw1, const float* R2w, const float* t2w, const float* K2,
+                                               const float* scale_factors2, const float* level_sigma2_2, int nlevels,
+                                               int check_orientation, int* matches12) {
+  PL_ARG(keys1_un && desc1 && has_mp1 && keys2_un && desc2 && has_mp2 && F12 && Cw1 && R2w && t2w && K2 && scale_factors2 &&
+         level_sigma2_2 && matches12 && n1 >= 0 && n2 >= 0 && nn1 >= 0 && nn2 >= 0 && nlevels > 0);
+  PL_ARG((nn1 == 0 || (fv1_nodes && fv1_start && fv1_items)) && (nn2 == 0 || (fv2_nodes && fv2_start && fv2_items)));
+  int rc = require_device(); if (rc) return rc;
+  for (int i = 0; i < n1; i++) matches12[i] = -1;
+  // the node merge of :760-884 (std::map order, lower_bound jumps) on the host: one query per keypoint of a shared node
+  std::vector<int> q_idx1, q_s, q_e;
+  for (int a = 0, b = 0; a < nn1 && b < nn2;) {
+    if (fv1_nodes[a] == fv2_nodes[b]) {
+      for (int i1 = fv1_start[a]; i1 < fv1_start[a + 1]; i1++) {
+        PL_ARG(fv1_items[i1] >= 0 && fv1_items[i1] < n1);
+        q_idx1.push_back(fv1_items[i1]); q_s.push_back(fv2_start[b]); q_e.push_back(fv2_start[b + 1]);
+      }
+      a++; b++;
+    } else if (fv1_nodes[a] < fv2_nodes[b]) a++;
+    else b++;
+  }
+  if (q_idx1.empty() || n1 == 0 || n2 == 0) return 0;
+  const int nitems2 = fv2_start[nn2];
+  for (int i = 0; i < nitems2; i++) PL_ARG(fv2_items[i] >= 0 && fv2_items[i] < n2);
+  Stage s;
+  TriArgs A;
+  A.k1 = s.up(keys1_un, n1); A.k2 = s.up(keys2_un, n2); A.d1 = s.up(desc1, (size_t)n1 * 32); A.d2 = s.up(desc2, (size_t)n2 * 32);
+  A.mp1 = s.up(has_mp1, n1); A.mp2 = s.up(has_mp2, n2);
+  A.q_idx1 = s.up(q_idx1.data(), q_idx1.size()); A.q_s = s.up(q_s.data(), q_s.size()); A.q_e = s.up(q_e.data(), q_e.size());
+  A.fv2_items = s.up(fv2_items, nitems2); A.nq = (int)q_idx1.size(); A.n1 = n1;
+  memcpy(A.F, F12, sizeof(A.F));
+  {  // epipole of camera 1 in image 2 (:729-737): C2 = R2w*Cw + t2w in cv::gemm's fp32 order
+    float C2[3];
+    for (int i = 0; i < 3; i++) C2[i] = ((R2w[3 * i] * Cw1[0] + R2w[3 * i + 1] * Cw1[1]) + R2w[3 * i + 2] * Cw1[2]) + t2w[i];
+    const float invz = 1.0f / C2[2];
+    A.ex = K2[0] * C2[0] * invz + K2[2]; A.ey = K2[1] * C2[1] * invz + K2[3];
+  }
+  A.scale2 = s.up(scale_factors2, nlevels); A.sigma2_2 = s.up(level_sigma2_2, nlevels); A.checkOri = check_orientation;
+  A.matches12 = s.alloc<int>(n1); A.nmatches = s.alloc<int>(1); A.bins = s.alloc<unsigned char>(n1);
+  PL_ARG(A.k1 && A.k2 && A.d1 && A.d2 && A.mp1 && A.mp2 && A.q_idx1 && A.q_s && A.q_e && A.fv2_items && A.scale2 && A.sigma2_2 &&
+         A.matches12 && A.nmatches && A.bins);
+  k_search_triangulation<<<1, 256>>>(A);
+  PL_LAUNCH_CHECK();
+  int nm = 0;
+  rc = down(&nm, A.nmatches, 1); if (rc) return rc;
+  rc = down(matches12, A.matches12, (size_t)n1); if (rc) return rc;
+  return nm;
+}
+
+extern "C" int pl_orb_fuse_search(const PLKeyPoint* keys_un, const uint8_t* desc, int n, const float* bounds, const float* Tcw,
+                                  const float* Ow, const float* K, const float* scale_factors, const float* inv_level_sigma2,
+                                  int nlevels, float log_scale_factor, int n_mp, const uint8_t* skip, const float* pos,
+                                  const float* normal, const float* min_dist, const float* max_dist, const uint8_t* mp_desc,
+                                  float th, int* best_idx, int* best_dist) {
+  PL_ARG(keys_un && desc && bounds && Tcw && Ow && K && scale_factors && inv_level_sigma2 && best_idx && best_dist && n >= 0 &&
+         n_mp >= 0 && nlevels > 0 && n < 65000);
+  PL_ARG(n_mp == 0 || (pos && normal && min_dist && max_dist && mp_desc));
+  int rc = require_device(); if (rc) return rc;
+  if (n_mp == 0) return PL_OK;
+  Stage s;
+  FuseArgs A;
+  A.keys = s.up(keys_un, n); A.desc = s.up(desc, (size_t)n * 32); A.n = n;
+  memcpy(A.bounds, bounds, 16); memcpy(A.T, Tcw, 64); memcpy(A.Ow, Ow, 12); memcpy(A.K, K, 16);
+  A.scaleFactors = s.up(scale_factors, nlevels); A.invSigma2 = s.up(inv_level_sigma2, nlevels);
+  A.logScaleFactor = log_scale_factor; A.nLevels = nlevels; A.n_mp = n_mp;
+  A.skip = skip ? s.up(skip, n_mp) : nullptr; A.pos = s.up(pos, (size_t)n_mp * 3); A.normal = s.up(normal, (size_t)n_mp * 3);
+  A.minDist = s.up(min_dist, n_mp); A.maxDist = s.up(max_dist, n_mp); A.mp_desc = s.up(mp_desc, (size_t)n_mp * 32); A.th = th;
+  A.best_idx = s.alloc<int>(n_mp); A.best_dist = s.alloc<int>(n_mp);
+  PL_ARG(A.keys && A.desc && A.scaleFactors && A.invSigma2 && A.pos && A.normal && A.minDist && A.maxDist && A.mp_desc && A.best_idx &&
+         A.best_dist);
+  const size_t sm = grid_smem_bytes(std::max(n, 1));
+  PL_CUDA(cudaFuncSetAttribute(k_fuse_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_fuse_search<<<1, 32 * kFuseWarps, sm>>>(A);
+  PL_LAUNCH_CHECK();
+  rc = down(best_idx, A.best_idx, (size_t)n_mp); if (rc) return rc;
+  return down(best_dist, A.best_dist, (size_t)n_mp);
 }

@@ -4,6 +4,9 @@ Pure numpy (PCG64 seeds) so the same bytes are produced in the build container a
 """
 import numpy as np
 
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])   # cv::KeyPoint, 28 bytes
+
 
 def _gauss1d(sigma):
     r = int(3 * sigma + 0.5)
@@ -228,3 +231,99 @@ def synth_map_view(seed=7, n=4000, K=TUM1_K, w=640, h=480, lines=False):
     f = rng.uniform(0.3, 3.0, n)
     max_dist = (d * f * 1.2).astype(np.float32); min_dist = (max_dist / (1.2 ** rng.integers(2, 9, n))).astype(np.float32)
     return dict(Tcw=Tcw, Ow=Ow, pos=pos, normal=nrm, min_dist=min_dist, max_dist=max_dist)
+
+
+def synth_two_view(seed=5, n_pts=1500, n_clutter=400, K=TUM1_K, w=640, h=480, nlevels=8, scale=1.2):
+    """Two keyframes observing the same 3-D points (LocalMapping::CreateNewMapPoints' input to SearchForTriangulation):
+    undistorted keypoints with octave / angle, ORB-like 256-bit descriptors (a per-point code with a few flipped bits per
+    view), DBoW2-style feature vectors (node id shared by the two views of a point, clutter spread at random), poses, F12."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = K
+    Km = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float64)
+    R1 = _rot(*rng.normal(0, 0.03, 3)); t1 = rng.normal(0, 0.05, 3)
+    R2 = _rot(*rng.normal(0, 0.06, 3)); t2 = t1 + np.array([0.35, 0.02, 0.05]) + rng.normal(0, 0.02, 3)
+    X = np.stack([rng.uniform(-3, 3, n_pts), rng.uniform(-2, 2, n_pts), rng.uniform(2.5, 9, n_pts)], 1)
+    sf = scale ** np.arange(nlevels)
+
+    def view(R, t, flip_seed):
+        r = np.random.default_rng(flip_seed)
+        Xc = X @ R.T + t
+        uv = np.stack([fx * Xc[:, 0] / Xc[:, 2] + cx, fy * Xc[:, 1] / Xc[:, 2] + cy], 1)
+        octv = r.integers(0, nlevels, n_pts)
+        uv = uv + r.normal(0, 0.6, uv.shape) * sf[octv][:, None]
+        ok = (uv[:, 0] > 20) & (uv[:, 0] < w - 20) & (uv[:, 1] > 20) & (uv[:, 1] < h - 20) & (Xc[:, 2] > 0.5)
+        return uv, octv, ok
+    code = rng.integers(0, 256, (n_pts, 32), dtype=np.uint8)
+    base_ang = rng.uniform(0, 360, n_pts)
+    node_of = rng.integers(0, 97, n_pts)
+    out = {}
+    for name, (R, t, fs, drot) in {"1": (R1, t1, 11 + seed, 0.0), "2": (R2, t2, 23 + seed, 12.0)}.items():
+        r = np.random.default_rng(fs)
+        uv, octv, ok = view(R, t, fs)
+        ids = np.nonzero(ok)[0]
+        r.shuffle(ids)
+        n = len(ids) + n_clutter
+        kp = np.zeros(n, KP_DTYPE)
+        kp["x"][:len(ids)] = uv[ids, 0]; kp["y"][:len(ids)] = uv[ids, 1]; kp["octave"][:len(ids)] = octv[ids]
+        ang = (base_ang[ids] + drot + r.normal(0, 4, len(ids))) % 360
+        wrong = r.random(len(ids)) < 0.1                   # some inconsistent rotations for the histogram to remove
+        ang[wrong] = r.uniform(0, 360, wrong.sum())
+        kp["angle"][:len(ids)] = ang
+        kp["x"][len(ids):] = r.uniform(20, w - 20, n_clutter); kp["y"][len(ids):] = r.uniform(20, h - 20, n_clutter)
+        kp["octave"][len(ids):] = r.integers(0, nlevels, n_clutter); kp["angle"][len(ids):] = r.uniform(0, 360, n_clutter)
+        kp["size"] = 31 * sf[kp["octave"]]; kp["class_id"] = -1
+        d = np.empty((n, 32), np.uint8)
+        d[:len(ids)] = code[ids]
+        flips = r.integers(0, 256, (len(ids), 14)); 
+        for j in range(flips.shape[1]):
+            sel = r.random(len(ids)) < 0.7
+            d[np.nonzero(sel)[0], flips[sel, j] // 8] ^= (1 << (flips[sel, j] % 8)).astype(np.uint8)
+        d[len(ids):] = r.integers(0, 256, (n_clutter, 32), dtype=np.uint8)
+        nodes = np.concatenate([node_of[ids], r.integers(0, 110, n_clutter)])
+        fv = {}
+        for i in r.permutation(n):                          # insertion order inside a node is arbitrary
+            fv.setdefault(int(nodes[i]), []).append(int(i))
+        has_mp = (r.random(n) < 0.3).astype(np.uint8)
+        out[name] = dict(keys=kp, desc=d, fv=fv, has_mp=has_mp, R=R.astype(np.float32), t=t.astype(np.float32), pt_id=np.concatenate([ids, -np.ones(n_clutter, np.int64)]))
+    # LocalMapping::ComputeF12: F12 = K1^-T [t12]x R12 K2^-1
+    R12 = R1 @ R2.T; t12 = -R1 @ R2.T @ t2 + t1
+    tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]])
+    out["F12"] = (np.linalg.inv(Km).T @ tx @ R12 @ np.linalg.inv(Km)).astype(np.float32)
+    out["Cw1"] = (-R1.T @ t1).astype(np.float32)
+    out["K"] = np.array(K, np.float32)
+    out["scale_factors"] = sf.astype(np.float32); out["level_sigma2"] = (sf * sf).astype(np.float32)
+    out["X"] = X
+    return out
+
+
+def synth_fuse_problem(seed=6, n_mp=3000, n_kp=1800, K=TUM1_K, w=640, h=480, nlevels=8, scale=1.2):
+    """A keyframe (keypoints, descriptors, pose) and a list of map points to fuse into it (ORBmatcher::Fuse input)."""
+    rng = np.random.default_rng(seed)
+    v = synth_map_view(seed + 100, n_mp, K, w, h)
+    fx, fy, cx, cy = K
+    sf = (scale ** np.arange(nlevels)).astype(np.float32)
+    T = v["Tcw"].astype(np.float64)
+    Pc = v["pos"].astype(np.float64) @ T[:3, :3].T + T[:3, 3]
+    with np.errstate(all="ignore"):
+        uv = np.stack([fx * Pc[:, 0] / Pc[:, 2] + cx, fy * Pc[:, 1] / Pc[:, 2] + cy], 1)
+    vis = np.nonzero((Pc[:, 2] > 0.1) & (uv[:, 0] > 5) & (uv[:, 0] < w - 5) & (uv[:, 1] > 5) & (uv[:, 1] < h - 5))[0]
+    mp_desc = rng.integers(0, 256, (n_mp, 32), dtype=np.uint8)
+    kp = np.zeros(n_kp, KP_DTYPE); desc = rng.integers(0, 256, (n_kp, 32), dtype=np.uint8)
+    m = min(len(vis), n_kp * 2 // 3)
+    src = rng.choice(vis, m, replace=False)
+    d = np.linalg.norm(v["pos"][src] - v["Ow"], axis=1)
+    lvl = np.clip(np.ceil(np.log(v["max_dist"][src] / d) / np.log(scale)), 0, nlevels - 1).astype(int)
+    octv = np.clip(lvl - rng.integers(0, 3, m) + 0, 0, nlevels - 1)      # lvl, lvl-1 pass the level filter; lvl-2 does not
+    kp["x"][:m] = uv[src, 0] + rng.normal(0, 1.2, m) * sf[octv]; kp["y"][:m] = uv[src, 1] + rng.normal(0, 1.2, m) * sf[octv]
+    kp["octave"][:m] = octv
+    desc[:m] = mp_desc[src]
+    flips = rng.integers(0, 256, (m, 40))
+    for j in range(flips.shape[1]):
+        sel = rng.random(m) < 0.6
+        desc[np.nonzero(sel)[0], flips[sel, j] // 8] ^= (1 << (flips[sel, j] % 8)).astype(np.uint8)
+    kp["x"][m:] = rng.uniform(0, w, n_kp - m); kp["y"][m:] = rng.uniform(0, h, n_kp - m); kp["octave"][m:] = rng.integers(0, nlevels, n_kp - m)
+    kp["size"] = 31 * sf[kp["octave"]]; kp["class_id"] = -1
+    skip = (rng.random(n_mp) < 0.15).astype(np.uint8)
+    return dict(keys=kp, desc=desc, bounds=np.array([0, 0, w, h], np.float32), Tcw=v["Tcw"], Ow=v["Ow"], K=np.array(K, np.float32),
+                scale_factors=sf, inv_level_sigma2=(1.0 / (sf * sf)).astype(np.float32), log_scale_factor=float(np.float32(np.log(np.float32(scale)))),
+                skip=skip, pos=v["pos"], normal=v["normal"], min_dist=v["min_dist"], max_dist=v["max_dist"], mp_desc=mp_desc)

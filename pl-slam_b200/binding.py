@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libplslam_b200.so")
+LIB_PATH = os.environ.get("PLSLAM_B200_LIB") or os.path.join(_HERE, "libplslam_b200.so")   # env override: A/B builds in tools/
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
                      ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])

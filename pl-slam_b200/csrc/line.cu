@@ -125,45 +125,103 @@ __global__ void __launch_bounds__(256) k_lsd_scale(LineParams P, const uint8_t* 
 }
 
 // ---------------------------------------------------------------------------------------------- K_B gradient
-// One 16-byte record per scaled pixel, everything region growing needs in ONE load:
-//   x = level-line angle in degrees (cv::fastAtan2(gx, -gy)); -1024 = NOTDEF (border or magnitude <= rho)
-//   y,z = cos/sin of float(angle_rad) rounded to fp32 (what region_grow adds to sumdx/sumdy)
-//   w = bit pattern of s = gx^2+gy^2 (modgrad = sqrt(s/4), recomputed in fp64 where the weights are used)
+// Per scaled pixel, what region growing needs, as separate arrays (the 4-byte angle word is the hot one):
+//   ANG = level-line angle in degrees (cv::fastAtan2(gx, -gy)); -1024 = NOTDEF (border or magnitude <= rho)
+//   CS  = cos/sin of float(angle_rad) rounded to fp32 (what region_grow adds to sumdx/sumdy)
+//   S2  = s = gx^2+gy^2 (modgrad = sqrt(s/4), recomputed in fp64 where the weights are used); seedcs: see grad_record
 constexpr float kNotDefDeg = -1024.f;
-__global__ void __launch_bounds__(256) k_lsd_grad(LineParams P, const uint8_t* __restrict__ scaled,
+// The level-line record of a pixel depends only on its integer gradient (gx, gy) in [-510, 510]^2: the angle in degrees
+// (cv::fastAtan2(gx, -gy)), cos/sin of that angle as region_grow adds them, and the cos/sin a region SEEDED there starts
+// from.  The fp64 sincos behind them is the whole cost of the gradient pass, so it is evaluated once per (gx, gy) into a
+// 25 MB table at handle creation (L2-resident, the hot entries are the small gradients) and the per-frame kernel is loads.
+constexpr int kGradR = 510, kGradN = 2 * kGradR + 1;
+struct GradRec { float deg, c, s, pad; };
+__device__ __forceinline__ void grad_record(int gx, int gy, GradRec& rec, float2& scs) {
+  const float deg = fast_atan2_deg_l((float)gx, (float)(-gy));
+  const double af = (double)(float)((double)deg * kDegToRads);
+  double sn, cs;
+  sincos(af, &sn, &cs);
+  rec.deg = deg; rec.c = (float)cs; rec.s = (float)sn; rec.pad = 0.f;
+  // a region SEEDED here starts from cos/sin of the fp64 angle ad = af + dl, |dl| <= half an fp32 ulp (< 4e-7):
+  // angle-addition with cos(dl) = 1 - dl^2/2, sin(dl) = dl is exact to ~1e-27, far below fp64 rounding
+  const double ad = (double)deg * kDegToRads, dl = ad - af, h2 = 1.0 - 0.5 * dl * dl;
+  scs = make_float2((float)(cs * h2 - sn * dl), (float)(sn * h2 + cs * dl));
+}
+__global__ void __launch_bounds__(256) k_lsd_grad_table(GradRec* __restrict__ T, float2* __restrict__ TS) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kGradN * kGradN) return;
+  GradRec rec; float2 scs;
+  grad_record(i / kGradN - kGradR, i % kGradN - kGradR, rec, scs);
+  T[i] = rec; TS[i] = scs;
+}
+// One thread = 4 consecutive pixels of a row: two 8-byte row reads, four table lookups, 16-byte stores (the pass is bound by
+// the number of memory instructions, not by bytes).  kVec needs sw % 4 == 0 (rows of every output array 16-byte aligned).
+template <bool kVec>
+__global__ void __launch_bounds__(256) k_lsd_grad(LineParams P, const uint8_t* __restrict__ scaled, const float4* __restrict__ T,
+                                                  const float2* __restrict__ TS,
                                                   float* __restrict__ ANG, float2* __restrict__ CS, int* __restrict__ S2, float2* __restrict__ seedcs, int* __restrict__ maxs) {
-  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  __shared__ int smax;
+  if (threadIdx.x == 0) smax = 0;
+  __syncthreads();
+  const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, y = blockIdx.y * 4 + (threadIdx.x >> 6);
   const int f = blockIdx.z;
-  int s = 0;
-  if (x < P.sw && y < P.sh) {
-    const uint8_t* S = scaled + (long long)f * P.npx;
-    float4 rec = make_float4(kNotDefDeg, 0.f, 0.f, __int_as_float(0));
-    float2 scs = make_float2(0.f, 0.f);
-    if (x < P.sw - 1 && y < P.sh - 1) {
-      int a = S[y * P.sw + x], b = S[y * P.sw + x + 1], c = S[(y + 1) * P.sw + x], d = S[(y + 1) * P.sw + x + 1];
-      int DA = d - a, BC = b - c;
-      const int gx = DA + BC, gy = DA - BC;
-      s = gx * gx + gy * gy;
-      rec.w = __int_as_float(s);
-      if (s > P.s_th) {
-        const float deg = fast_atan2_deg_l((float)gx, (float)(-gy));
-        const double af = (double)(float)((double)deg * kDegToRads);
-        double sn, cs;
-        sincos(af, &sn, &cs);
-        rec.x = deg; rec.y = (float)cs; rec.z = (float)sn;
-        // a region SEEDED here starts from cos/sin of the fp64 angle ad = af + dl, |dl| <= half an fp32 ulp (< 4e-7):
-        // angle-addition with cos(dl) = 1 - dl^2/2, sin(dl) = dl is exact to ~1e-27, far below fp64 rounding
-        const double ad = (double)deg * kDegToRads, dl = ad - af, h2 = 1.0 - 0.5 * dl * dl;
-        scs = make_float2((float)(cs * h2 - sn * dl), (float)(sn * h2 + cs * dl));
-      } else s = 0;
+  int smx = 0;
+  if (x0 < P.sw && y < P.sh) {
+    const uint8_t* S = scaled + (long long)f * P.npx + (long long)y * P.sw + x0;
+    const bool lastrow = (y >= P.sh - 1);
+    int r0[5], r1[5];
+    if (kVec) {       // x0 % 4 == 0 and sw % 4 == 0: one aligned word + one byte per row
+      const unsigned w0 = *reinterpret_cast<const unsigned*>(S), w1 = lastrow ? 0u : *reinterpret_cast<const unsigned*>(S + P.sw);
+#pragma unroll
+      for (int k = 0; k < 4; k++) { r0[k] = (w0 >> (8 * k)) & 0xff; r1[k] = (w1 >> (8 * k)) & 0xff; }
+      const bool in4 = (x0 + 4 < P.sw);
+      r0[4] = in4 ? S[4] : 0; r1[4] = (in4 && !lastrow) ? S[P.sw + 4] : 0;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        const bool in = (x0 + k < P.sw);
+        r0[k] = in ? S[k] : 0;
+        r1[k] = (in && !lastrow) ? S[P.sw + k] : 0;
+      }
     }
-    const long long o = (long long)f * P.npx + y * P.sw + x;
-    ANG[o] = rec.x; CS[o] = make_float2(rec.y, rec.z); S2[o] = __float_as_int(rec.w);
-    seedcs[o] = scs;
+    float ang[4], sc[4][2], se[4][2];
+    int sq[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      ang[k] = kNotDefDeg; sc[k][0] = sc[k][1] = se[k][0] = se[k][1] = 0.f; sq[k] = 0;
+      if (x0 + k < P.sw - 1 && !lastrow) {
+        const int DA = r1[k + 1] - r0[k], BC = r0[k + 1] - r1[k];
+        const int gx = DA + BC, gy = DA - BC;
+        const int s = gx * gx + gy * gy;
+        sq[k] = s;
+        if (s > P.s_th) {
+          const int ti = (gx + kGradR) * kGradN + (gy + kGradR);
+          const float4 rec = __ldg(&T[ti]);
+          const float2 scs = __ldg(&TS[ti]);
+          ang[k] = rec.x; sc[k][0] = rec.y; sc[k][1] = rec.z; se[k][0] = scs.x; se[k][1] = scs.y;
+          smx = max(smx, s);
+        }
+      }
+    }
+    const long long o = (long long)f * P.npx + (long long)y * P.sw + x0;
+    if (kVec) {
+      *reinterpret_cast<float4*>(ANG + o) = make_float4(ang[0], ang[1], ang[2], ang[3]);
+      *reinterpret_cast<int4*>(S2 + o) = make_int4(sq[0], sq[1], sq[2], sq[3]);
+      float4* c4 = reinterpret_cast<float4*>(CS + o);
+      c4[0] = make_float4(sc[0][0], sc[0][1], sc[1][0], sc[1][1]); c4[1] = make_float4(sc[2][0], sc[2][1], sc[3][0], sc[3][1]);
+      float4* e4 = reinterpret_cast<float4*>(seedcs + o);
+      e4[0] = make_float4(se[0][0], se[0][1], se[1][0], se[1][1]); e4[1] = make_float4(se[2][0], se[2][1], se[3][0], se[3][1]);
+    } else {
+      for (int k = 0; k < 4 && x0 + k < P.sw; k++) {
+        ANG[o + k] = ang[k]; S2[o + k] = sq[k]; CS[o + k] = make_float2(sc[k][0], sc[k][1]); seedcs[o + k] = make_float2(se[k][0], se[k][1]);
+      }
+    }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s = max(s, __shfl_xor_sync(0xffffffffu, s, o));
-  if ((threadIdx.x & 31) == 0 && s > 0) atomicMax(&maxs[f], s);
+  for (int o = 16; o > 0; o >>= 1) smx = max(smx, __shfl_xor_sync(0xffffffffu, smx, o));
+  if ((threadIdx.x & 31) == 0 && smx > 0) atomicMax(&smax, smx);
+  __syncthreads();
+  if (threadIdx.x == 0 && smax > 0) atomicMax(&maxs[f], smax);
 }
 __device__ __forceinline__ double s_norm(int s) { return sqrt((double)s / 4.0); }
 __device__ __forceinline__ int s_bin(int s, double bin_coef) { return (int)(s_norm(s) * bin_coef); }
@@ -712,54 +770,59 @@ __global__ void __launch_bounds__(256) k_keylines(LineParams P, const float4* __
 }
 
 // ---------------------------------------------------------------------------------------------- K_H LBD blur + Sobel
-// 32x32 output tile <- 34x34 blurred pixels <- 38x38 raw pixels staged in shared memory.  Sobel reflects the BLURRED
-// image (BORDER_REFLECT_101), so blurred values are evaluated at reflect-101 coordinates; the blur reflects the raw
-// image.  Both reflections stay inside the staged window [X0-3, X0+35) x [Y0-3, Y0+35) clipped to the image.
+// GaussianBlur 5x5 sigma 1 (8.8 fixed point rows [14 62 104 62 14]) fused with the Sobel pair (dx, dy as int16).
+// Tile: 64x64 blurred pixels <- 68x68 raw pixels in shared memory -> 62x62 outputs.  The raw tile is loaded at
+// reflect-101 coordinates; because the kernel is symmetric, the blur of the reflected image at column -1 equals the
+// blurred value at column +1, i.e. exactly what Sobel's own BORDER_REFLECT_101 of the BLURRED image needs, so no tap
+// ever reflects again.  One thread walks down one column: the last five horizontal sums live in registers (blur), then
+// a sliding 3x3 window of blurred bytes (Sobel).
+constexpr int kSobT = 64, kSobOut = kSobT - 2, kSobRawP = kSobT + 8, kSobSeg = kSobT / 4;
 __global__ void __launch_bounds__(256) k_lbd_sobel(LineParams P, const uint8_t* __restrict__ imgs, int stride,
                                                    long long frame_stride, short2* __restrict__ dxy) {
-  __shared__ uint8_t raw[38][40];
-  __shared__ uint16_t hp[38][36];
-  __shared__ uint8_t bl[34][36];
-  const int tid = threadIdx.x, X0 = blockIdx.x * 32, Y0 = blockIdx.y * 32;
+  __shared__ uint8_t raw[(kSobT + 4) * kSobRawP];
+  __shared__ uint8_t bl[kSobT * (kSobT + 4)];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int X0 = blockIdx.x * kSobOut, Y0 = blockIdx.y * kSobOut;   // first output pixel of the tile
   const uint8_t* img = imgs + (long long)blockIdx.z * frame_stride;
-  auto r101 = [](int p, int n) { if (p < 0) p = -p; if (p >= n) p = 2 * (n - 1) - p; return p; };
-  for (int i = tid; i < 38 * 38; i += 256) {
-    const int r = i / 38, c = i - r * 38;
-    const int gy = min(max(Y0 - 3 + r, 0), P.h - 1), gx = min(max(X0 - 3 + c, 0), P.w - 1);   // clipped window (clamped entries unused)
-    raw[r][c] = img[(long long)gy * stride + gx];
+  auto r101 = [](int p, int n) { if (p < 0) p = -p; if (p >= n) p = 2 * (n - 1) - p; return min(max(p, 0), n - 1); };
+  // raw rows Y0-3 .. Y0+64, columns X0-3 .. X0+64
+  for (int r = ty; r < kSobT + 4; r += 4) {
+    const uint8_t* row = img + (long long)r101(Y0 - 3 + r, P.h) * stride;
+    raw[r * kSobRawP + tx] = row[r101(X0 - 3 + tx, P.w)];
+    if (tx < 4) raw[r * kSobRawP + kSobT + tx] = row[r101(X0 - 3 + kSobT + tx, P.w)];
   }
   __syncthreads();
-  // horizontal pass at the reflected blurred columns, for every staged row
-  for (int i = tid; i < 38 * 34; i += 256) {
-    const int r = i / 34, c = i - r * 34;
-    const int bx = r101(min(max(X0 - 1 + c, -1), P.w), P.w);
-    unsigned h = 0;
-    const int t5[5] = {14, 62, 104, 62, 14};
-#pragma unroll
-    for (int k = -2; k <= 2; k++) h += raw[r][r101(bx + k, P.w) - (X0 - 3)] * t5[k + 2];
-    hp[r][c] = (uint16_t)h;
+  {  // blurred pixel (bx, by) of the tile = image pixel (X0-1+bx, Y0-1+by); thread: column tx, rows ty*16 .. +15
+    const uint8_t* p = raw + (ty * kSobSeg) * kSobRawP + tx;
+    auto hrow = [&](const uint8_t* q) { return 14 * (q[0] + q[4]) + 62 * (q[1] + q[3]) + 104 * q[2]; };
+    int w0 = hrow(p), w1 = hrow(p + kSobRawP), w2 = hrow(p + 2 * kSobRawP), w3 = hrow(p + 3 * kSobRawP);
+    p += 4 * kSobRawP;
+    uint8_t* o = bl + (ty * kSobSeg) * (kSobT + 4) + tx;
+#pragma unroll 4
+    for (int r = 0; r < kSobSeg; r++, p += kSobRawP, o += kSobT + 4) {
+      const int w4 = hrow(p);
+      const unsigned acc = 14u * (unsigned)(w0 + w4) + 62u * (unsigned)(w1 + w3) + 104u * (unsigned)w2;
+      *o = (uint8_t)((acc + 32768u) >> 16);
+      w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+    }
   }
   __syncthreads();
-  for (int i = tid; i < 34 * 34; i += 256) {
-    const int r = i / 34, c = i - r * 34;
-    const int by = r101(min(max(Y0 - 1 + r, -1), P.h), P.h);
-    unsigned acc = 0;
-    const int t5[5] = {14, 62, 104, 62, 14};
-#pragma unroll
-    for (int k = -2; k <= 2; k++) acc += (unsigned)hp[r101(by + k, P.h) - (Y0 - 3)][c] * t5[k + 2];
-    bl[r][c] = (uint8_t)((acc + 32768u) >> 16);
-  }
-  __syncthreads();
+  const int x = X0 + tx - 1;                       // output column of blurred column tx (1..62 produce outputs)
+  if (tx < 1 || tx > kSobOut || x >= P.w) return;
+  const int rbeg = max(ty * kSobSeg, 1), rend = min(ty * kSobSeg + kSobSeg - 1, kSobOut);   // blurred rows of my outputs
+  const uint8_t* b = bl + (rbeg - 1) * (kSobT + 4) + tx;
+  int a00 = b[-1], a01 = b[0], a02 = b[1];
+  b += kSobT + 4;
+  int a10 = b[-1], a11 = b[0], a12 = b[1];
   short2* D = dxy + (long long)blockIdx.z * P.w * P.h;
-  for (int i = tid; i < 32 * 32; i += 256) {
-    int ty = i >> 5, tx = i & 31, x = X0 + tx, y = Y0 + ty;
-    if (x >= P.w || y >= P.h) continue;
-    const int r = ty + 1, c = tx + 1;
-    int a00 = bl[r - 1][c - 1], a01 = bl[r - 1][c], a02 = bl[r - 1][c + 1];
-    int a10 = bl[r][c - 1], a12 = bl[r][c + 1];
-    int a20 = bl[r + 1][c - 1], a21 = bl[r + 1][c], a22 = bl[r + 1][c + 1];
-    D[(long long)y * P.w + x] = make_short2((short)((a02 - a00) + 2 * (a12 - a10) + (a22 - a20)),
-                                            (short)((a20 - a00) + 2 * (a21 - a01) + (a22 - a02)));
+  for (int r = rbeg; r <= rend; r++) {
+    b += kSobT + 4;
+    const int a20 = b[-1], a21 = b[0], a22 = b[1];
+    const int y = Y0 + r - 1;
+    if (y < P.h)
+      D[(long long)y * P.w + x] = make_short2((short)((a02 - a00) + 2 * (a12 - a10) + (a22 - a20)),
+                                              (short)((a20 - a00) + 2 * (a21 - a01) + (a22 - a02)));
+    a00 = a10; a01 = a11; a02 = a12; a10 = a20; a11 = a21; a12 = a22;
   }
 }
 
@@ -782,7 +845,8 @@ __global__ void __launch_bounds__(64) k_lbd_describe(LineParams P, const PLKeyLi
   const short halfHeight = (63 - 1) / 2, halfWidth = (short)((lengthOfLSP - 1) / 2);
   const float midX = (float)(0.5 * (double)__fadd_rn(kl.sPointInOctaveX, kl.ePointInOctaveX));
   const float midY = (float)(0.5 * (double)__fadd_rn(kl.sPointInOctaveY, kl.ePointInOctaveY));
-  __shared__ float s_dL[2];
+  __shared__ float s_dL[2], s_gL[21], s_norm2[2];
+  if (tid < 21) s_gL[tid] = c_gaussL[tid];
   if (tid == 0) { s_dL[0] = (float)cos((double)kl.angle); s_dL[1] = (float)sin((double)kl.angle); }   // fp64 libm once per line
   __syncthreads();
   const float dL0 = s_dL[0], dL1 = s_dL[1];
@@ -814,53 +878,53 @@ __global__ void __launch_bounds__(64) k_lbd_describe(LineParams P, const PLKeyLi
     rs[hID][4] = pgdO; rs[hID][5] = ngdO; rs[hID][6] = __fmul_rn(pgdO, pgdO); rs[hID][7] = __fmul_rn(ngdO, ngdO);
   }
   __syncthreads();
-  if (tid < 8) {  // band sums of quantity q, rows visited in order (own band, band above, band below)
-    const int q = tid;
+  // Band sums: band[q][k] is its own accumulator, fed in row order by the 7 rows of band k-1 (Gaussian taps 0..6), of band
+  // k (taps 7..13) and of band k+1 (taps 14..20) — the order in which the reference's row loop touches it.  72 accumulators
+  // in parallel, <= 21 ordered fp32 adds each.
+  for (int a = tid; a < 72; a += 64) {
+    const int q = a / 9, k = a - q * 9;
     const bool sq = (q == 2 || q == 3 || q == 6 || q == 7);
-    float b[9];
-#pragma unroll
-    for (int k = 0; k < 9; k++) b[k] = 0.f;
-    for (int hID = 0; hID < 63; hID++) {
-      const float v = rs[hID][q];
-      int bandID = hID / 7;
-      float cg = c_gaussL[hID % 7 + 7];
-      b[bandID] = __fadd_rn(b[bandID], sq ? __fmul_rn(__fmul_rn(cg, cg), v) : __fmul_rn(cg, v));
-      bandID--;
-      if (bandID >= 0) { cg = c_gaussL[hID % 7 + 14]; b[bandID] = __fadd_rn(b[bandID], sq ? __fmul_rn(__fmul_rn(cg, cg), v) : __fmul_rn(cg, v)); }
-      bandID += 2;
-      if (bandID < 9) { cg = c_gaussL[hID % 7]; b[bandID] = __fadd_rn(b[bandID], sq ? __fmul_rn(__fmul_rn(cg, cg), v) : __fmul_rn(cg, v)); }
+    float b = 0.f;
+    for (int B = max(k - 1, 0); B <= min(k + 1, 8); B++) {
+      const int off = (B - k + 1) * 7;
+      for (int j = 0; j < 7; j++) {
+        const float cg = s_gL[j + off], v = rs[B * 7 + j][q];
+        b = __fadd_rn(b, sq ? __fmul_rn(__fmul_rn(cg, cg), v) : __fmul_rn(cg, v));
+      }
     }
-#pragma unroll
-    for (int k = 0; k < 9; k++) band[q][k] = b[k];
+    band[q][k] = b;
+  }
+  __syncthreads();
+  if (tid < 36) {       // mean / stddev of the four quantities of band bb
+    const int bb = tid >> 2, c = tid & 3;
+    const int qm = (c & 1) + ((c & 2) << 1), qs = qm + 2;          // {0,1,4,5} and {2,3,6,7}
+    const float invN = (bb == 0 || bb == 8) ? (float)(1.0 / (7 * 2.0)) : (float)(1.0 / (7 * 3.0));
+    const float temp = __fmul_rn(band[qm][bb], invN);
+    des[8 * bb + c] = temp;
+    des[8 * bb + 4 + c] = sqrtf(__fsub_rn(__fmul_rn(band[qs][bb], invN), __fmul_rn(temp, temp)));
+  }
+  __syncthreads();
+  if (tid == 0 || tid == 32) {   // the two ordered norms (means: k = 0..3, stddevs: k = 4..7), one warp each
+    const int k0 = tid ? 4 : 0;
+    float acc = 0;
+    for (int i = 0; i < 72; i += 8)
+      for (int k = k0; k < k0 + 4; k++) acc = __fadd_rn(acc, __fmul_rn(des[i + k], des[i + k]));
+    s_norm2[tid ? 1 : 0] = __fdiv_rn(1.f, sqrtf(acc));
+  }
+  __syncthreads();
+  for (int i = tid; i < 72; i += 64) {
+    float v = __fmul_rn(des[i], s_norm2[(i & 7) >> 2]);
+    if ((double)v > 0.4) v = (float)0.4;
+    des[i] = v;
   }
   __syncthreads();
   if (tid == 0) {
-    const float invN2 = (float)(1.0 / (7 * 2.0)), invN3 = (float)(1.0 / (7 * 3.0));
-    for (int bb = 0; bb < 9; bb++) {
-      const float invN = (bb == 0 || bb == 8) ? invN2 : invN3;
-      const int d = bb * 8;
-      float temp;
-      temp = __fmul_rn(band[0][bb], invN); des[d] = temp; des[d + 4] = sqrtf(__fsub_rn(__fmul_rn(band[2][bb], invN), __fmul_rn(temp, temp)));
-      temp = __fmul_rn(band[1][bb], invN); des[d + 1] = temp; des[d + 5] = sqrtf(__fsub_rn(__fmul_rn(band[3][bb], invN), __fmul_rn(temp, temp)));
-      temp = __fmul_rn(band[4][bb], invN); des[d + 2] = temp; des[d + 6] = sqrtf(__fsub_rn(__fmul_rn(band[6][bb], invN), __fmul_rn(temp, temp)));
-      temp = __fmul_rn(band[5][bb], invN); des[d + 3] = temp; des[d + 7] = sqrtf(__fsub_rn(__fmul_rn(band[7][bb], invN), __fmul_rn(temp, temp)));
-    }
-    float tempM = 0, tempS = 0;
-    for (int i = 0; i < 72; i += 8) {
-      for (int k = 0; k < 4; k++) tempM = __fadd_rn(tempM, __fmul_rn(des[i + k], des[i + k]));
-      for (int k = 4; k < 8; k++) tempS = __fadd_rn(tempS, __fmul_rn(des[i + k], des[i + k]));
-    }
-    tempM = __fdiv_rn(1.f, sqrtf(tempM)); tempS = __fdiv_rn(1.f, sqrtf(tempS));
-    for (int i = 0; i < 72; i += 8) {
-      for (int k = 0; k < 4; k++) des[i + k] = __fmul_rn(des[i + k], tempM);
-      for (int k = 4; k < 8; k++) des[i + k] = __fmul_rn(des[i + k], tempS);
-    }
-    for (int i = 0; i < 72; i++) if ((double)des[i] > 0.4) des[i] = (float)0.4;
     float temp = 0;
     for (int i = 0; i < 72; i++) temp = __fadd_rn(temp, __fmul_rn(des[i], des[i]));
-    temp = __fdiv_rn(1.f, sqrtf(temp));
-    for (int i = 0; i < 72; i++) des[i] = __fmul_rn(des[i], temp);
+    s_norm2[0] = __fdiv_rn(1.f, sqrtf(temp));
   }
+  __syncthreads();
+  for (int i = tid; i < 72; i += 64) des[i] = __fmul_rn(des[i], s_norm2[0]);
   __syncthreads();
   if (tid < 32) {
     const float* f1 = &des[8 * c_comb[2 * tid]];
@@ -885,6 +949,7 @@ struct PLLine {
   float2* d_seedcs = nullptr;
   int grow_grid_cap = 1 << 30;   // max CTAs of the persistent grow kernel (env PLSLAM_LSD_GROW_CTAS_PER_SM x #SMs)
   float* d_ang = nullptr; float2* d_cs = nullptr; int* d_sq = nullptr;
+  GradRec* d_gtab = nullptr; float2* d_gtab_seed = nullptr;   // (gx, gy) -> level-line record, built once (k_lsd_grad_table)
   unsigned short* d_counts = nullptr;
   int *d_offsets = nullptr, *d_ndef = nullptr, *d_maxs = nullptr, *d_nseg = nullptr, *d_overflow = nullptr;
   unsigned *d_order = nullptr, *d_reg = nullptr;
@@ -905,7 +970,7 @@ static const unsigned char h_comb[64] = {0, 1, 0, 2, 0, 3, 0, 4, 0, 5, 0, 6, 1, 
 
 extern "C" void pl_line_destroy(PLLine* h) {
   if (!h) return;
-  cudaFree(h->d_scaled); cudaFree(h->d_seedcs); cudaFree(h->d_ang); cudaFree(h->d_cs); cudaFree(h->d_sq); cudaFree(h->d_counts); cudaFree(h->d_offsets);
+  cudaFree(h->d_gtab); cudaFree(h->d_gtab_seed); cudaFree(h->d_scaled); cudaFree(h->d_seedcs); cudaFree(h->d_ang); cudaFree(h->d_cs); cudaFree(h->d_sq); cudaFree(h->d_counts); cudaFree(h->d_offsets);
   cudaFree(h->d_ndef); cudaFree(h->d_maxs); cudaFree(h->d_nseg); cudaFree(h->d_overflow); cudaFree(h->d_order);
   cudaFree(h->d_reg); cudaFree(h->d_segs); cudaFree(h->d_dxy); cudaFree(h->d_img); cudaFree(h->d_kls);
   cudaFree(h->d_desc); cudaFree(h->d_lf); cudaFree(h->d_nl); cudaFree(h->d_mask);
@@ -954,6 +1019,11 @@ extern "C" int pl_line_create(const PLLineConfig* cfg, PLLine** out) {
   LN_TRY(dev_alloc(&h->d_order, npx * B)); LN_TRY(dev_alloc(&h->d_reg, npx * B)); LN_TRY(dev_alloc(&h->d_segs, (size_t)P.seg_cap * B));
   LN_TRY(dev_alloc(&h->d_dxy, (size_t)P.w * P.h * B));
   LN_CUDA(cudaMemset(h->d_overflow, 0, sizeof(int)));
+  LN_TRY(dev_alloc(&h->d_gtab, (size_t)kGradN * kGradN)); LN_TRY(dev_alloc(&h->d_gtab_seed, (size_t)kGradN * kGradN));
+  k_lsd_grad_table<<<(kGradN * kGradN + 255) / 256, 256, 0, h->stream>>>(h->d_gtab, h->d_gtab_seed);
+  LN_CUDA(cudaGetLastError());
+  LN_CUDA(cudaStreamSynchronize(h->stream));
+  count_launch();
   {  // LBD weights (binary_descriptor_custom.cpp:217-259), integer divisions as in the reference
     float gG[63], gL[21];
     double u = (7 * 3 - 1) / 2, sigma = (7 * 2 + 1) / 2, inv = -1 / (2 * sigma * sigma);
@@ -1001,7 +1071,13 @@ extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int str
   PL_CUDA(cudaMemsetAsync(h->d_maxs, 0, sizeof(int) * B, st));
   k_lsd_scale<<<dim3((P.sw + 31) / 32, (P.sh + 31) / 32, B), 256, 0, st>>>(P, imgs, stride, (long long)frame_stride, h->d_scaled);
   PL_LAUNCH_CHECK();
-  k_lsd_grad<<<dim3((P.sw + 63) / 64, (P.sh + 3) / 4, B), 256, 0, st>>>(P, h->d_scaled, h->d_ang, h->d_cs, h->d_sq, h->d_seedcs, h->d_maxs);
+  {
+    const dim3 grd((P.sw + 255) / 256, (P.sh + 3) / 4, B);
+    if (P.sw % 4 == 0)
+      k_lsd_grad<true><<<grd, 256, 0, st>>>(P, h->d_scaled, reinterpret_cast<const float4*>(h->d_gtab), h->d_gtab_seed, h->d_ang, h->d_cs, h->d_sq, h->d_seedcs, h->d_maxs);
+    else
+      k_lsd_grad<false><<<grd, 256, 0, st>>>(P, h->d_scaled, reinterpret_cast<const float4*>(h->d_gtab), h->d_gtab_seed, h->d_ang, h->d_cs, h->d_sq, h->d_seedcs, h->d_maxs);
+  }
   PL_LAUNCH_CHECK();
   k_lsd_hist<<<dim3(P.nchunk, B), 256, 0, st>>>(P, h->d_ang, h->d_sq, h->d_maxs, h->d_counts);
   PL_LAUNCH_CHECK();
@@ -1015,7 +1091,7 @@ extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int str
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev1, st));
   k_keylines<<<B, 256, h->key_smem, st>>>(P, h->d_segs, h->d_nseg, mask, (PLKeyLineRec*)keylines, linefunc, n);
   PL_LAUNCH_CHECK();
-  k_lbd_sobel<<<dim3((P.w + 31) / 32, (P.h + 31) / 32, B), 256, 0, st>>>(P, imgs, stride, (long long)frame_stride, h->d_dxy);
+  k_lbd_sobel<<<dim3((P.w + kSobOut - 1) / kSobOut, (P.h + kSobOut - 1) / kSobOut, B), 256, 0, st>>>(P, imgs, stride, (long long)frame_stride, h->d_dxy);
   PL_LAUNCH_CHECK();
   k_lbd_describe<<<dim3(P.capL, B), 64, 0, st>>>(P, (const PLKeyLineRec*)keylines, n, h->d_dxy, desc);
   PL_LAUNCH_CHECK();

@@ -217,6 +217,15 @@ int pl_frontend_run_dev(PLFrontend* h, const uint8_t* imgs, int stride, size_t f
 int pl_frontend_run(PLFrontend* h, const uint8_t* imgs, int stride, size_t frame_stride, int B, PLKeyPoint* kps,
                     uint8_t* desc, int* n, void* keylines, uint8_t* ldesc, double* linefunc, int* nl, int* pt_matches,
                     int* n_pt_matches, int* line_matches, int* n_line_matches, float* poses, int* inliers);
+/* Streaming form of pl_frontend_run: returns once the step is enqueued; the H2D copy of the next step and the D2H copy of
+ * the previous one overlap the kernels.  Host buffers should be pinned; outputs of submit #i are valid once
+ * pl_frontend_wait has let it complete.  At most two steps are in flight (submit blocks otherwise); with two alternating
+ * output sets the loop is: submit(i+1); wait(keep_in_flight = 1); consume outputs of step i. */
+int pl_frontend_submit(PLFrontend* h, const uint8_t* imgs, int stride, size_t frame_stride, int B, PLKeyPoint* kps,
+                       uint8_t* desc, int* n, void* keylines, uint8_t* ldesc, double* linefunc, int* nl, int* pt_matches,
+                       int* n_pt_matches, int* line_matches, int* n_line_matches, float* poses, int* inliers);
+/* wait until at most keep_in_flight (0 or 1) submitted steps are unfinished */
+int pl_frontend_wait(PLFrontend* h, int keep_in_flight);
 int pl_frontend_io_bytes(const PLFrontend* h, long long* h2d_per_frame, long long* d2h_per_frame);
 int pl_frontend_fetch(PLFrontend* h, int B, PLKeyPoint* kps, uint8_t* desc, int* n, void* keylines, uint8_t* ldesc, int* nl,
                       int* pt_matches, int* n_pt_matches, int* line_matches, int* n_line_matches, float* poses, int* inliers);

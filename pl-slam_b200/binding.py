@@ -475,6 +475,15 @@ class Frontend:
                                     *[_p(out[k]) for k in self.ORDER]))
         return out
 
+    def submit(self, images, out):
+        """Streaming form of run(): enqueue one step (pinned host buffers); results are valid after wait()."""
+        B = images.shape[0]
+        check(lib().pl_frontend_submit(self._h, _p(images), C.c_int(images.strides[1]), C.c_size_t(images.strides[0]), C.c_int(B),
+                                       *[_p(out[k]) for k in self.ORDER]))
+
+    def wait(self, keep_in_flight=0):
+        check(lib().pl_frontend_wait(self._h, C.c_int(keep_in_flight)))
+
     def run_dev(self, img_ptr, stride, frame_stride, B, stream=None):
         check(lib().pl_frontend_run_dev(self._h, img_ptr, stride, frame_stride, B, stream))
 

@@ -51,12 +51,24 @@ struct PLFrontend {
   PLUndistort* und = nullptr;
   uint8_t* d_und = nullptr;
   PLKeyPoint* d_kpsu_prev = nullptr;
+  // streaming (pl_frontend_submit / pl_frontend_wait): two input buffers, one output snapshot, copy streams
+  uint8_t* d_in[2] = {nullptr, nullptr};
+  uint8_t* d_stage = nullptr;
+  cudaStream_t sUp = nullptr, sDown = nullptr;
+  cudaEvent_t evUp[2] = {nullptr, nullptr}, evFree[2] = {nullptr, nullptr}, evSnap = nullptr, evOut = nullptr;
+  cudaEvent_t evStep[2] = {nullptr, nullptr};   // host outputs of submit #c are complete when evStep[c & 1] fires
+  int slot = 0;
+  long long submitted = 0, completed = 0;
 };
 
 extern "C" void pl_frontend_destroy(PLFrontend* h) {
   if (!h) return;
   pl_orb_destroy(h->orb); pl_line_destroy(h->line); pl_undistort_destroy(h->und);
   cudaFree(h->d_und); cudaFree(h->d_kpsu_prev);
+  cudaFree(h->d_in[0]); cudaFree(h->d_in[1]); cudaFree(h->d_stage);
+  if (h->sUp) cudaStreamDestroy(h->sUp);
+  if (h->sDown) cudaStreamDestroy(h->sDown);
+  for (cudaEvent_t e : {h->evUp[0], h->evUp[1], h->evFree[0], h->evFree[1], h->evSnap, h->evOut, h->evStep[0], h->evStep[1]}) if (e) cudaEventDestroy(e);
   void* ptrs[] = {h->d_img, h->d_kl, h->d_lf, h->d_bounds, h->d_pm, h->d_m12,
                   h->d_nm, h->d_scr, h->d_lm, h->d_nlm, h->d_kps_prev, h->d_desc_prev, h->d_n_prev, h->d_ldesc_prev, h->d_nl_prev,
                   h->d_T0, h->d_K, h->d_pobs, h->d_pw, h->d_pX, h->d_Tout, h->d_lfun, h->d_lX, h->d_scratch, h->d_np, h->d_nl_lm,
@@ -264,6 +276,83 @@ extern "C" int pl_frontend_run(PLFrontend* h, const uint8_t* imgs, int stride, s
   PL_CUDA(cudaMemcpyAsync(poses, h->d_Tout, 64 * b * 2, cudaMemcpyDeviceToHost, st));
   PL_CUDA(cudaMemcpyAsync(inliers, h->d_inl, 4 * b * 2, cudaMemcpyDeviceToHost, st));
   PL_CUDA(cudaStreamSynchronize(st));
+  return PL_OK;
+}
+
+
+// ---- streaming form of pl_frontend_run: the H2D copy of step i+1 and the D2H copy of step i-1 run beside the kernels of
+// step i.  submit() returns as soon as the work is enqueued; the host output buffers of a step are valid after the wait()
+// that follows the NEXT submit (or any wait() with nothing in flight after it).  At most two steps are in flight; the
+// caller alternates two sets of (pinned) output buffers.
+static size_t fe_out_bytes(const PLFrontend* h, int B, size_t off[14]) {
+  const size_t cK = h->capK, cL = h->capL, b = B;
+  const size_t sz[13] = {cK * b * sizeof(PLKeyPoint), cK * b * 32, b * 4, cL * b * 68, cL * b * 32, cL * b * 24, b * 4, cK * b * 4, b * 4,
+                         cL * b * 4, b * 4, 64 * b * 2, 4 * b * 2};
+  size_t o = 0;
+  for (int i = 0; i < 13; i++) { off[i] = o; o += (sz[i] + 255) / 256 * 256; }
+  off[13] = o;
+  return o;
+}
+extern "C" int pl_frontend_wait(PLFrontend* h, int keep_in_flight) {
+  PL_ARG(h && keep_in_flight >= 0 && keep_in_flight <= 1);
+  while (h->submitted - h->completed > keep_in_flight) {      // steps complete in submission order
+    PL_CUDA(cudaEventSynchronize(h->evStep[h->completed & 1]));
+    h->completed++;
+  }
+  return PL_OK;
+}
+extern "C" int pl_frontend_submit(PLFrontend* h, const uint8_t* imgs, int stride, size_t frame_stride, int B, PLKeyPoint* kps,
+                                  uint8_t* desc, int* n, void* keylines, uint8_t* ldesc, double* linefunc, int* nl,
+                                  int* pt_matches, int* n_pt_matches, int* line_matches, int* n_line_matches, float* poses,
+                                  int* inliers) {
+  PL_ARG(h && imgs && B >= 1 && B <= h->B && kps && desc && n && keylines && ldesc && linefunc && nl && pt_matches &&
+         n_pt_matches && line_matches && n_line_matches && poses && inliers);
+  const int W = h->cfg.width, H = h->cfg.height;
+  size_t off[14];
+  if (!h->sUp) {   // first use: allocate the streaming state
+    const size_t fb = (size_t)W * H * h->B;
+    int rc;
+    if ((rc = dev_alloc(&h->d_in[0], fb)) || (rc = dev_alloc(&h->d_in[1], fb)) || (rc = dev_alloc(&h->d_stage, fe_out_bytes(h, h->B, off)))) return rc;
+    PL_CUDA(cudaStreamCreateWithFlags(&h->sUp, cudaStreamNonBlocking));
+    PL_CUDA(cudaStreamCreateWithFlags(&h->sDown, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&h->evUp[0], &h->evUp[1], &h->evFree[0], &h->evFree[1], &h->evSnap, &h->evOut, &h->evStep[0], &h->evStep[1]})
+      PL_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++) PL_CUDA(cudaEventRecord(h->evFree[k], h->stream));
+    PL_CUDA(cudaEventRecord(h->evOut, h->sDown));
+  }
+  if (h->submitted - h->completed >= 2) { int rc = pl_frontend_wait(h, 1); if (rc) return rc; }   // at most two steps in flight
+  fe_out_bytes(h, B, off);
+  const int k = h->slot;
+  cudaStream_t st = h->stream;
+  // upload into buffer k once the step that last read it has finished
+  PL_CUDA(cudaStreamWaitEvent(h->sUp, h->evFree[k], 0));
+  if (stride == W && frame_stride == (size_t)W * H)
+    PL_CUDA(cudaMemcpyAsync(h->d_in[k], imgs, (size_t)W * H * B, cudaMemcpyHostToDevice, h->sUp));
+  else
+    for (int b = 0; b < B; b++)
+      PL_CUDA(cudaMemcpy2DAsync(h->d_in[k] + (size_t)b * W * H, W, imgs + (size_t)b * frame_stride, stride, W, H, cudaMemcpyHostToDevice, h->sUp));
+  PL_CUDA(cudaEventRecord(h->evUp[k], h->sUp));
+  // compute
+  PL_CUDA(cudaStreamWaitEvent(st, h->evUp[k], 0));
+  int rc = pl_frontend_run_dev(h, h->d_in[k], W, (size_t)W * H, B, st);
+  if (rc) return rc;
+  PL_CUDA(cudaEventRecord(h->evFree[k], st));
+  // snapshot of the step's outputs (device to device), once the previous snapshot has left for the host
+  PL_CUDA(cudaStreamWaitEvent(st, h->evOut, 0));
+  const size_t cK = h->capK, cL = h->capL, b = B;
+  const void* src[13] = {h->d_kps, h->d_desc, h->d_n, h->d_kl, h->d_ldesc, h->d_lf, h->d_nl, h->d_m12, h->d_nm, h->d_lm, h->d_nlm, h->d_Tout, h->d_inl};
+  void* dst[13] = {kps, desc, n, keylines, ldesc, linefunc, nl, pt_matches, n_pt_matches, line_matches, n_line_matches, poses, inliers};
+  const size_t sz[13] = {cK * b * sizeof(PLKeyPoint), cK * b * 32, b * 4, cL * b * 68, cL * b * 32, cL * b * 24, b * 4, cK * b * 4, b * 4,
+                         cL * b * 4, b * 4, 64 * b * 2, 4 * b * 2};
+  for (int i = 0; i < 13; i++) PL_CUDA(cudaMemcpyAsync(h->d_stage + off[i], src[i], sz[i], cudaMemcpyDeviceToDevice, st));
+  PL_CUDA(cudaEventRecord(h->evSnap, st));
+  // download
+  PL_CUDA(cudaStreamWaitEvent(h->sDown, h->evSnap, 0));
+  for (int i = 0; i < 13; i++) PL_CUDA(cudaMemcpyAsync(dst[i], h->d_stage + off[i], sz[i], cudaMemcpyDeviceToHost, h->sDown));
+  PL_CUDA(cudaEventRecord(h->evOut, h->sDown));
+  PL_CUDA(cudaEventRecord(h->evStep[h->submitted & 1], h->sDown));
+  h->slot ^= 1;
+  h->submitted++;
   return PL_OK;
 }
 

@@ -92,3 +92,34 @@ def test_frontend_with_distorting_camera():
     for k in ("kps", "desc", "n", "keylines", "ldesc", "nl", "pt_matches", "n_pt_matches", "line_matches", "n_line_matches"):
         assert out0[k].tobytes() == out1[k].tobytes(), k
     assert fe.fetch_keys_un(B).tobytes() == out0["kps"].tobytes()
+
+
+def test_frontend_streaming_submit_wait():
+    """pl_frontend_submit / pl_frontend_wait (H2D, kernels, D2H of consecutive steps overlapped) return, for every step,
+    exactly what the synchronous pl_frontend_run returns for that step's frames."""
+    import torch
+    B = 3
+    seqs = [synth.synth_sequence(B, 640, 480, seed=s) for s in (4, 5, 6, 7)]
+    problems = [synth.synth_pose_problem(60 + k) for k in range(B)]
+    def make():
+        f = pl.Frontend(640, 480, max_batch=B, lm_caps=(320, 88)); f.set_pose_problems(problems)
+        f.set_camera(synth.TUM1_K, synth.TUM1_DIST)
+        return f
+    ref = make()      # same call history on a second handle (entries beyond the per-frame counts keep earlier contents)
+    want = [{k: v.copy() for k, v in ref.run(s).items()} for s in seqs]
+    fe = make()
+    pins = []
+    for s in seqs:
+        t = torch.empty(s.shape, dtype=torch.uint8, pin_memory=True); t.numpy()[:] = s; pins.append(t)
+    outs = [fe.alloc_outputs(B, pinned=True) for _ in range(2)]
+    got = []
+    for i, p in enumerate(pins):
+        fe.submit(p.numpy(), outs[i & 1])
+        fe.wait(1)
+        if i >= 1:
+            got.append({k: outs[(i - 1) & 1][k].copy() for k in pl.Frontend.ORDER})
+    fe.wait(0)
+    got.append({k: outs[(len(pins) - 1) & 1][k].copy() for k in pl.Frontend.ORDER})
+    for w, g in zip(want, got):
+        for k in pl.Frontend.ORDER:
+            assert w[k].tobytes() == g[k].tobytes(), k

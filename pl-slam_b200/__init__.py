@@ -6,3 +6,4 @@ the CPU oracle and raises if the CUDA library is missing (no CPU fallback).
 """
 from .binding import *  # noqa: F401,F403
 from . import synth  # noqa: F401
+from . import trajectory  # noqa: F401

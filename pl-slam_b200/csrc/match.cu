@@ -120,12 +120,25 @@ __device__ __forceinline__ int key_idx(unsigned long long k) { return (int)(k & 
 
 struct Top2 { unsigned long long best, second; };
 
+// Grids of frames with at most 2048 keypoints keep the octave (< 32) in the five high bits of each 16-bit item.
+constexpr int kPackShift = 11, kPackIdMask = (1 << kPackShift) - 1, kPackMaxKeys = 1 << kPackShift;
+__device__ __forceinline__ bool pack_octaves(const PLKeyPoint* keys, int n, int nitems, unsigned short* items, int lane) {
+  if (n > kPackMaxKeys) return false;
+  for (int j = lane; j < nitems; j += 32) {
+    const int id = items[j];
+    items[j] = (unsigned short)(id | ((keys[id].octave & 31) << kPackShift));
+  }
+  __syncwarp();
+  return true;
+}
+
 // Best and second-best candidate of GetFeaturesInArea(x,y,r,minLevel,maxLevel) for query descriptor q, with a
 // per-candidate skip predicate; semantics of the reference's sequential "dist<best / else dist<second" scan.
 template <typename Skip>
 __device__ __forceinline__ Top2 window_top2(const PLKeyPoint* keys, const uint8_t* desc, const unsigned short* start,
                                             const unsigned short* items, const GridP& g, float x, float y, float r,
-                                            int minLevel, int maxLevel, const uint8_t* q, Skip skip, int lane) {
+                                            int minLevel, int maxLevel, const uint8_t* q, Skip skip, int lane,
+                                            bool packed = false) {
   Top2 t;
   t.best = KEY_NONE; t.second = KEY_NONE;
   Window w = make_window(g, x, y, r);
@@ -133,16 +146,22 @@ __device__ __forceinline__ Top2 window_top2(const PLKeyPoint* keys, const uint8_
   const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
   const int ncy = w.y1 - w.y0 + 1, ncell = (w.x1 - w.x0 + 1) * ncy;
   unsigned long long k1 = KEY_NONE, k2 = KEY_NONE;
-  for (int c = lane; c < ncell; c += 32) {
-    int ix = w.x0 + c / ncy, iy = w.y0 + c % ncy;
+  // cell c = (c / ncy, c % ncy) of the window, advanced by 32 per trip without dividing again
+  const int q32 = 32 / ncy, r32 = 32 - q32 * ncy;
+  int cx = lane / ncy, cy = lane - cx * ncy;
+  for (int c = lane; c < ncell; c += 32, cx += q32, cy += r32) {
+    if (cy >= ncy) { cy -= ncy; cx++; }
+    const int ix = w.x0 + cx, iy = w.y0 + cy;
     int cb = start[ix * GR + iy], ce = start[ix * GR + iy + 1];
     for (int j = cb; j < ce; j++) {
-      int id = items[j];
-      const PLKeyPoint& kp = keys[id];
-      if (checkLevels) {
-        if (kp.octave < minLevel) continue;
-        if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+      const int it = items[j];
+      const int id = packed ? (it & kPackIdMask) : it;
+      if (checkLevels) {       // packed grids carry the octave next to the index: the level filter never touches HBM
+        const int oct = packed ? (it >> kPackShift) : keys[id].octave;
+        if (oct < minLevel) continue;
+        if (maxLevel >= 0 && oct > maxLevel) continue;
       }
+      const PLKeyPoint& kp = keys[id];
       if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
       int dist = hamming256(q, desc + 32 * id);
       if (skip(id, dist)) continue;
@@ -230,6 +249,7 @@ __global__ void __launch_bounds__(32) k_search_init(const PLKeyPoint* keys1, con
   int* matchedDist = scratch + (long long)b * 2 * cap;
   int* m21 = matchedDist + cap;
   build_point_grid(k2, N2, g, sg.start, sg.fill, sg.items, lane);
+  const bool packed = pack_octaves(k2, N2, sg.start[NCELL], sg.items, lane);
   for (int i = lane; i < N1; i += 32) m12[i] = -1;
   for (int i = lane; i < N2; i += 32) { matchedDist[i] = 0x7fffffff; m21[i] = -1; }
   if (lane < HISTO) hist[lane] = 0;
@@ -242,7 +262,7 @@ __global__ void __launch_bounds__(32) k_search_init(const PLKeyPoint* keys1, con
   for (int i1 = 0; i1 < N1; i1++) {
     if (k1[i1].octave > 0) continue;
     Top2 t = window_top2(k2, d2, sg.start, sg.items, g, pm[2 * i1], pm[2 * i1 + 1], (float)windowSize, 0, 0,
-                         d1 + 32 * i1, skip, lane);
+                         d1 + 32 * i1, skip, lane, packed);
     if (t.best == KEY_NONE) continue;
     const int bestDist = key_dist(t.best), bestIdx2 = key_idx(t.best);
     const float bestDist2 = (t.second == KEY_NONE) ? 2147483648.0f : (float)key_dist(t.second);  // (float)INT_MAX
@@ -304,6 +324,7 @@ __global__ void __launch_bounds__(32) k_search_proj_last(ProjLastArgs A) {
   const float* T = A.Tcw + 16 * b;
   const long long lb = (long long)b * A.cap_last;
   build_point_grid(kc, N, g, sg.start, sg.fill, sg.items, lane);
+  const bool packed = pack_octaves(kc, N, sg.start[NCELL], sg.items, lane);
   for (int i = lane; i < N; i += 32) match[i] = (A.preassigned && A.preassigned[(long long)b * A.cap + i]) ? -2 : -1;
   if (lane < HISTO) hist[lane] = 0;
   unsigned char* bins = reinterpret_cast<unsigned char*>(sg.fill);
@@ -328,7 +349,7 @@ __global__ void __launch_bounds__(32) k_search_proj_last(ProjLastArgs A) {
     const int oct = A.last_octave[lb + i];
     const float radius = __fmul_rn(A.th, A.scaleFactors[oct]);
     Top2 t = window_top2(kc, dc, sg.start, sg.items, g, u, v, radius, oct - 1, oct + 1, A.last_desc + (lb + i) * 32,
-                         skip, lane);
+                         skip, lane, packed);
     if (t.best == KEY_NONE) continue;
     const int bestDist = key_dist(t.best), bestIdx2 = key_idx(t.best);
     if (bestDist <= 100) {
@@ -371,6 +392,7 @@ __global__ void __launch_bounds__(32) k_search_proj_points(ProjPointsArgs A) {
   int* match = A.match + (long long)b * A.cap;
   const long long mb = (long long)b * A.cap_mp;
   build_point_grid(k, N, g, sg.start, sg.fill, sg.items, lane);
+  const bool packed = pack_octaves(k, N, sg.start[NCELL], sg.items, lane);
   for (int i = lane; i < N; i += 32) match[i] = (A.preassigned && A.preassigned[(long long)b * A.cap + i]) ? -2 : -1;
   __syncwarp();
   int nmatches = 0;
@@ -382,7 +404,7 @@ __global__ void __launch_bounds__(32) k_search_proj_points(ProjPointsArgs A) {
     float r = ((double)A.view_cos[mb + i] > 0.998) ? 2.5f : 4.0f;  // float vs the double literal 0.998
     if (bFactor) r = __fmul_rn(r, A.th);
     Top2 t = window_top2(k, d, sg.start, sg.items, g, A.proj[(mb + i) * 2], A.proj[(mb + i) * 2 + 1],
-                         __fmul_rn(r, A.scaleFactors[lvl]), lvl - 1, lvl, A.mp_desc + (mb + i) * 32, skip, lane);
+                         __fmul_rn(r, A.scaleFactors[lvl]), lvl - 1, lvl, A.mp_desc + (mb + i) * 32, skip, lane, packed);
     if (t.best == KEY_NONE) continue;
     const int bestDist = key_dist(t.best), bestIdx = key_idx(t.best);
     if (bestDist <= 100) {
@@ -766,8 +788,14 @@ __global__ void __launch_bounds__(32 * kFuseWarps) k_fuse_search(FuseArgs A) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   SmemGrid sg = carve_grid(smem, A.n);
   const GridP g = make_grid(A.bounds);
-  if (wid == 0) build_point_grid(A.keys, A.n, g, sg.start, sg.fill, sg.items, lane);
+  __shared__ int s_packed;
+  if (wid == 0) {
+    build_point_grid(A.keys, A.n, g, sg.start, sg.fill, sg.items, lane);
+    const bool pk = pack_octaves(A.keys, A.n, sg.start[NCELL], sg.items, lane);
+    if (lane == 0) s_packed = pk;
+  }
   __syncthreads();
+  const bool packed = s_packed != 0;
   for (int i = wid; i < A.n_mp; i += kFuseWarps) {
     int bi = -1, bd = 256;
     bool go = !(A.skip && A.skip[i]);
@@ -800,7 +828,7 @@ __global__ void __launch_bounds__(32 * kFuseWarps) k_fuse_search(FuseArgs A) {
     if (go) {     // warp-uniform: every lane computed the same scalars
       SkipChi2 skip{A.keys, A.invSigma2, u, v};
       const Top2 t = window_top2(A.keys, A.desc, sg.start, sg.items, g, u, v, __fmul_rn(A.th, A.scaleFactors[lvl]), lvl - 1, lvl,
-                                 A.mp_desc + 32 * (long long)i, skip, lane);
+                                 A.mp_desc + 32 * (long long)i, skip, lane, packed);
       if (t.best != KEY_NONE) { bi = key_idx(t.best); bd = key_dist(t.best); }
     }
     if (lane == 0) { A.best_idx[i] = bi; A.best_dist[i] = bd; }

@@ -320,6 +320,11 @@ int pl_orb_search_for_triangulation(const PLKeyPoint* keys1_un, const uint8_t* d
                                     const float* F12, const float* Cw1, const float* R2w, const float* t2w, const float* K2,
                                     const float* scale_factors2, const float* level_sigma2_2, int nlevels,
                                     int check_orientation, int* matches12);
+/* LSDmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, isDouble) (src/LSDmatcher.cpp:727-776; LocalMapping.cc:961):
+ * FrameBFMatch both ways at TH_HIGH = 80 with the matcher's nnratio, mutual check when is_double, pairs touching a line that
+ * already has a MapLine (has_ml*) removed.  matched_pairs[i] = j or -1; returns nmatches. */
+int pl_lsd_search_for_triangulation(const uint8_t* ldesc1, const uint8_t* has_ml1, int n1, const uint8_t* ldesc2,
+                                    const uint8_t* has_ml2, int n2, float nnratio, int is_double, int* matched_pairs);
 /* The search half of ORBmatcher::Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:914-1034): best keypoint of the keyframe for
  * every map point (best_idx = -1 / best_dist = 256 when skipped or nothing qualifies).  skip[i] = !pMP || isBad || IsInKeyFrame;
  * the caller applies :1036-1061 (Replace / AddObservation) to the points with best_dist <= TH_LOW (50) in order. */

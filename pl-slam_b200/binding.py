@@ -701,3 +701,16 @@ def _fuse_search(self, keys_un, desc, bounds, Tcw, Ow, K, scale_factors, inv_lev
 
 ORBmatcher.SearchForTriangulation = _search_for_triangulation
 ORBmatcher.FuseSearch = _fuse_search
+
+
+def _lsd_search_for_triangulation(self, ldesc1, has_ml1, ldesc2, has_ml2, isDouble=True):
+    """LSDmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, isDouble) (reference src/LSDmatcher.cpp:727-776)
+    -> (nmatches, vMatchedPairs[NL1])."""
+    d1 = _u8(ldesc1).reshape(-1, 32); d2 = _u8(ldesc2).reshape(-1, 32); m1 = _u8(has_ml1); m2 = _u8(has_ml2)
+    out = np.full(len(d1), -1, np.int32)
+    nm = check(lib().pl_lsd_search_for_triangulation(_p(d1), _p(m1), C.c_int(len(d1)), _p(d2), _p(m2), C.c_int(len(d2)),
+                                                     C.c_float(self.mfNNratio), C.c_int(int(isDouble)), _p(out)))
+    return nm, out
+
+
+LSDmatcher.SearchForTriangulation = _lsd_search_for_triangulation

@@ -58,3 +58,15 @@ def test_fuse_search(seed, th):
     for k in (9, 10, 11, 12, 13, 14):
         a3[k] = a3[k][:0]
     assert len(pl.ORBmatcher().FuseSearch(*a3)[0]) == 0
+
+
+@pytest.mark.parametrize("seed,dbl", [(1, True), (2, True), (3, False)])
+def test_lsd_search_for_triangulation(seed, dbl):
+    f = synth.synth_sequence(2, 640, 480, seed=seed)
+    (_, d1, _), (_, d2, _) = oracle.line_extract(f[0]), oracle.line_extract(f[1])
+    rng = np.random.default_rng(seed)
+    ml1 = (rng.random(len(d1)) < 0.25).astype(np.uint8); ml2 = (rng.random(len(d2)) < 0.25).astype(np.uint8)
+    onm, om = oracle.lsd_search_for_triangulation(d1, ml1, d2, ml2, 0.8, dbl)
+    nm, m = pl.LSDmatcher(0.8).SearchForTriangulation(d1, ml1, d2, ml2, dbl)
+    assert onm > 10 and nm == onm and np.array_equal(m, om)
+    assert pl.LSDmatcher(0.8).SearchForTriangulation(d1[:0], ml1[:0], d2, ml2)[0] == 0

@@ -70,3 +70,23 @@ def test_fuse_search_known_answers():
     # th scales the window: a tiny radius finds (almost) nothing
     bi2, bd2 = oracle.fuse_search(*args[:-1], 0.05)
     assert (bd2 <= 50).sum() < good.sum() // 5
+
+
+def test_lsd_search_for_triangulation_semantics():
+    """= FrameBFMatch both ways at TH_HIGH (80) + mutual check + MapLine filter (LSDmatcher.cpp:744-763)."""
+    rng = np.random.default_rng(3)
+    base = rng.integers(0, 256, (60, 32), dtype=np.uint8)
+    d1 = base.copy(); d2 = base[rng.permutation(60)][:50].copy()
+    for d in (d1, d2):
+        flips = rng.integers(0, 256, (len(d), 10))
+        for j in range(10):
+            d[np.arange(len(d)), flips[:, j] // 8] ^= (1 << (flips[:, j] % 8)).astype(np.uint8)
+    ml1 = (rng.random(60) < 0.2).astype(np.uint8); ml2 = (rng.random(50) < 0.2).astype(np.uint8)
+    f12 = oracle.frame_bf_match(d1, d2, 80.0, 0.8); f21 = oracle.frame_bf_match(d2, d1, 80.0, 0.8)
+    nm, m = oracle.lsd_search_for_triangulation(d1, ml1, d2, ml2, 0.8, True)
+    want = np.array([j if j >= 0 and f21[j] == i and not ml1[i] and not ml2[j] else -1 for i, j in enumerate(f12)])
+    assert nm == (want >= 0).sum() > 10 and np.array_equal(m, want)
+    nm1, m1 = oracle.lsd_search_for_triangulation(d1, ml1, d2, ml2, 0.8, False)
+    want1 = np.array([j if j >= 0 and not ml1[i] and not ml2[j] else -1 for i, j in enumerate(f12)])
+    assert nm1 >= nm and np.array_equal(m1, want1)
+    assert oracle.lsd_search_for_triangulation(d1[:0], ml1[:0], d2, ml2)[0] == 0

@@ -344,6 +344,9 @@ __device__ __forceinline__ bool is_aligned(double a, double theta, double prec) 
 // list and the ring are written after the loop by the accepted lanes themselves.
 // kFast: prec < pi/2, isAligned folded to  n <= prec || n >= prec_hi  (prec_hi = smallest double with 2pi-n <= prec;
 // 2pi-n is exact for n in [pi,4pi], so the two forms agree bit for bit).
+#ifndef GROW_ISOLATED
+#define GROW_ISOLATED 0     // batch-parallel retirement of one-pixel regions: bit-exact, measured SLOWER (220 vs 197 ms): the 8 scattered loads per free seed cost more than the 36 % of regions they retire
+#endif
 #ifndef GROW_SPEC
 #define GROW_SPEC 0         // speculative batched commit: bit-exact, but measured SLOWER on B200 (195 vs 168 ms at B=4736)
 #endif
@@ -557,9 +560,10 @@ __device__ __forceinline__ double dist_d(double x1, double y1, double x2, double
 }
 
 // LineSegmentDetectorImpl::refine + reduce_region_radius; n is updated; returns false if the region is rejected
-__device__ __noinline__ bool refine(const GrowCtx& C, int& n, double reg_angle, double prec, RectD& rec, double density_th, int lane) {
+__device__ __noinline__ bool refine(const GrowCtx& C, int& n, double reg_angle, double prec, RectD& rec, double density_th, int lane, bool& released) {
   double density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
   if (density >= density_th) return true;
+  released = true;              // from here on USED flags are cleared
   const unsigned p0 = C.R[0];
   const double xc = (double)(int)(p0 & 0xffffu), yc = (double)(int)(p0 >> 16);
   const double ang_c = (double)pixel_angle(C, (int)(p0 >> 16) * C.sw + (int)(p0 & 0xffffu)) * kDegToRads;
@@ -634,16 +638,47 @@ __global__ void __launch_bounds__(32, 32) k_lsd_grow(LineParams P, int* ANG, con
     const int i = i0 + lane;
     const unsigned pix = (i < n) ? O[i] : 0u;
     const int pidx = (int)(pix >> 16) * P.sw + (int)(pix & 0xffffu);
-    unsigned todo = __ballot_sync(0xffffffffu, i < n && !used_get(C, pidx));
+    const int sab = (i < n) ? C.ANG[pidx] : -1;          // angle word of my seed (negative: USED)
+    unsigned todo = __ballot_sync(0xffffffffu, sab >= 0);
+    // A seed none of whose 8 neighbours is free, defined and aligned with the seed's own angle grows a region of exactly
+    // one pixel (the first step of region_grow finds no candidate): below min_reg_size, so its only effect is the seed's
+    // USED bit.  36 % of all regions are like that.  The test is evaluated for the whole batch at once, one seed per
+    // lane; it stays valid until the seed's turn because USED flags only increase — except when refine releases pixels,
+    // after which the remaining lanes are evaluated again.
+    auto isolated = [&](bool active) {
+      bool iso = active;
+      if (active) {
+        const int sx = (int)(pix & 0xffffu), sy = (int)(pix >> 16);
+        const double th = (double)__int_as_float(sab) * kDegToRads;
+#pragma unroll
+        for (int kk = 0; kk < 9; kk++) {
+          if (kk == 4) continue;
+          const int xx = sx + kk % 3 - 1, yy = sy + kk / 3 - 1;
+          if (xx < 0 || yy < 0 || xx >= P.sw || yy >= P.sh) continue;
+          const int ab = C.ANG[yy * P.sw + xx];
+          if (ab < 0) continue;
+          const double n1 = fabs(th - (double)__int_as_float(ab) * kDegToRads);
+          if ((n1 <= P.prec) || (n1 >= P.prec_hi)) iso = false;
+        }
+      }
+      return __ballot_sync(0xffffffffu, iso);
+    };
+    unsigned isomask = GROW_ISOLATED ? isolated((todo >> lane) & 1u) : 0u;
     if (GROW_PREFETCH & 1) {
-      // this batch's seeds that are still free: their seed record and 3x3 rows; and the next batch's flag words
-      if ((todo >> lane) & 1u) { prefetch_l2(&C.S2[pidx]); prefetch_neighbourhood<false>(C, pidx, P.npx, false); }
+      // this batch's seeds that will really grow: their seed record and 3x3 rows; and the next batch's flag words
+      if (((todo & ~isomask) >> lane) & 1u) { prefetch_l2(&C.S2[pidx]); prefetch_neighbourhood<false>(C, pidx, P.npx, false); }
       if (i + 32 < n) { const unsigned pn = O[i + 32]; prefetch_l2(&C.ANG[(int)(pn >> 16) * P.sw + (int)(pn & 0xffffu)]); }
     }
     while (todo) {
       const int k = __ffs(todo) - 1;
+      if ((isomask >> k) & 1u) {            // one-pixel region: mark the seed and move on
+        if (lane == k) C.ANG[pidx] = sab | kUsedBit;
+        todo &= todo - 1u;
+        continue;
+      }
       const unsigned seed = __shfl_sync(0xffffffffu, pix, k);
       double reg_angle;
+      bool released = false;
 #if GROW_INLINE
       int cnt = region_grow_t<true>(C, seed, P.prec, P.prec_hi, reg_angle, lane);
 #else
@@ -652,7 +687,7 @@ __global__ void __launch_bounds__(32, 32) k_lsd_grow(LineParams P, int* ANG, con
       if (cnt >= P.min_reg_size) {
         RectD rec;
         region2rect(C, cnt, reg_angle, P.prec, rec, lane);
-        if (refine(C, cnt, reg_angle, P.prec, rec, P.density_th, lane)) {
+        if (refine(C, cnt, reg_angle, P.prec, rec, P.density_th, lane, released)) {
           if (lane == 0 && ns < P.seg_cap)
             S[ns] = make_float4((float)((rec.x1 + 0.5) / 0.8), (float)((rec.y1 + 0.5) / 0.8), (float)((rec.x2 + 0.5) / 0.8),
                                 (float)((rec.y2 + 0.5) / 0.8));
@@ -661,7 +696,10 @@ __global__ void __launch_bounds__(32, 32) k_lsd_grow(LineParams P, int* ANG, con
       }
       __syncwarp();
       // seeds later in this batch may have been consumed (or released by refine): re-read their flags
-      todo = __ballot_sync(0xffffffffu, i < n && lane > k && !used_get(C, pidx));
+      const bool free_now = i < n && lane > k && !used_get(C, pidx);
+      todo = __ballot_sync(0xffffffffu, free_now);
+      if (released) isomask = GROW_ISOLATED ? isolated(free_now) : 0u;     // pixels came back: earlier verdicts may be stale
+      else isomask &= todo;
     }
   }
   if (lane == 0) { nseg[f] = min(ns, P.seg_cap); if (ns > P.seg_cap) atomicExch(overflow, 1); }

@@ -620,13 +620,20 @@ __device__ __noinline__ bool refine(const GrowCtx& C, int& n, double reg_angle, 
   return true;
 }
 
-__global__ void __launch_bounds__(32, 32) k_lsd_grow(LineParams P, int* ANG, const float2* __restrict__ CS, const int* __restrict__ SQ, const float2* __restrict__ seedcs,
+#ifndef GROW_WARPS
+#define GROW_WARPS 1        // frames (warps) per CTA; with GROW_MIN_CTAS it sets the register budget / resident warps per SM
+#endif
+#ifndef GROW_MIN_CTAS
+#define GROW_MIN_CTAS 32
+#endif
+__global__ void __launch_bounds__(32 * GROW_WARPS, GROW_MIN_CTAS) k_lsd_grow(LineParams P, int* ANG, const float2* __restrict__ CS, const int* __restrict__ SQ, const float2* __restrict__ seedcs,
                                                  const unsigned* __restrict__ order, const int* __restrict__ ndef,
                                                  unsigned* __restrict__ reg, float4* __restrict__ segs,
                                                  int* __restrict__ nseg, int* __restrict__ overflow, int nframes) {
-  __shared__ unsigned ring[kRing];
-  const int lane = threadIdx.x;
-  for (int f = blockIdx.x; f < nframes; f += gridDim.x) {   // persistent: the grid size caps the resident warps per SM
+  __shared__ unsigned rings[GROW_WARPS][kRing];
+  const int lane = threadIdx.x & 31;
+  unsigned* ring = rings[threadIdx.x >> 5];
+  for (int f = blockIdx.x * GROW_WARPS + (threadIdx.x >> 5); f < nframes; f += gridDim.x * GROW_WARPS) {   // persistent: the grid size caps the resident warps per SM
   // const object: the cold out-of-line callees take it by reference, the inlined hot loop keeps its fields in registers
   const GrowCtx C = {ANG + (long long)f * P.npx, CS + (long long)f * P.npx, SQ + (long long)f * P.npx, seedcs + (long long)f * P.npx,
                      reg + (long long)f * P.npx, ring, P.sw, P.sh, P.s_th};
@@ -1124,7 +1131,7 @@ extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int str
   k_lsd_scatter<<<dim3((P.nchunk + 3) / 4, B), 128, 0, st>>>(P, h->d_ang, h->d_sq, h->d_maxs, h->d_offsets, h->d_order);
   PL_LAUNCH_CHECK();
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev0, st));
-  k_lsd_grow<<<std::min(B, h->grow_grid_cap), 32, 0, st>>>(P, reinterpret_cast<int*>(h->d_ang), h->d_cs, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow, B);
+  k_lsd_grow<<<std::min((B + GROW_WARPS - 1) / GROW_WARPS, h->grow_grid_cap), 32 * GROW_WARPS, 0, st>>>(P, reinterpret_cast<int*>(h->d_ang), h->d_cs, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow, B);
   PL_LAUNCH_CHECK();
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev1, st));
   k_keylines<<<B, 256, h->key_smem, st>>>(P, h->d_segs, h->d_nseg, mask, (PLKeyLineRec*)keylines, linefunc, n);

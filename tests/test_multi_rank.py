@@ -42,7 +42,7 @@ def test_all_gather_of_pose_records_world2():
     procs = [ctx.Process(target=_worker, args=(r, world, n_frames, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=120) for _ in range(world))
+    res = sorted(q.get(timeout=600) for _ in range(world))
     for p in procs:
-        p.join(60)
+        p.join(120)
     assert res == [(0, True), (1, True)]

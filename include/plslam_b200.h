@@ -320,6 +320,13 @@ int pl_orb_search_for_triangulation(const PLKeyPoint* keys1_un, const uint8_t* d
                                     const float* F12, const float* Cw1, const float* R2w, const float* t2w, const float* K2,
                                     const float* scale_factors2, const float* level_sigma2_2, int nlevels,
                                     int check_orientation, int* matches12);
+/* ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (src/ORBmatcher.cc:187-327; TrackReferenceKeyFrame Tracking.cc:1157,
+ * Relocalization :2119): has_mp_kf[i] = vpMapPointsKF[i] && !isBad(); fv* as in pl_orb_search_for_triangulation; keysF = F.mvKeys.
+ * matchesF[j] = keyframe feature whose MapPoint frame feature j receives, or -1; returns nmatches. */
+int pl_orb_search_by_bow(const PLKeyPoint* keysKF_un, const uint8_t* descKF, const uint8_t* has_mp_kf, int nKF,
+                         const PLKeyPoint* keysF, const uint8_t* descF, int nF, const unsigned* fvK_nodes, const int* fvK_start,
+                         const int* fvK_items, int nnK, const unsigned* fvF_nodes, const int* fvF_start, const int* fvF_items,
+                         int nnF, float nnratio, int check_orientation, int* matchesF);
 /* LSDmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, isDouble) (src/LSDmatcher.cpp:727-776; LocalMapping.cc:961):
  * FrameBFMatch both ways at TH_HIGH = 80 with the matcher's nnratio, mutual check when is_double, pairs touching a line that
  * already has a MapLine (has_ml*) removed.  matched_pairs[i] = j or -1; returns nmatches. */

@@ -501,3 +501,16 @@ def lsd_search_for_triangulation(d1, has_ml1, d2, has_ml2, nnratio=0.8, is_doubl
     nm = L.oracle_lsd_search_for_triangulation(_p(d1), _p(m1), C.c_int(len(d1)), _p(d2), _p(m2), C.c_int(len(d2)),
                                                C.c_float(nnratio), C.c_int(int(is_double)), _p(out))
     return nm, out
+
+
+def search_by_bow(kK, dK, has_mp_kf, kF, dF, fvK, fvF, nnratio=0.7, check_orientation=True):
+    """ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (ORBmatcher.cc:187-327) -> (nmatches, matchesF[nF])."""
+    kK = np.ascontiguousarray(kK, KP_DTYPE); kF = np.ascontiguousarray(kF, KP_DTYPE)
+    dK = np.ascontiguousarray(dK, np.uint8); dF = np.ascontiguousarray(dF, np.uint8); mp = np.ascontiguousarray(has_mp_kf, np.uint8)
+    n1a, s1, i1 = _csr(fvK); n2a, s2, i2 = _csr(fvF)
+    out = np.full(len(kF), -1, np.int32)
+    L = lib(); L.oracle_search_by_bow.restype = C.c_int
+    nm = L.oracle_search_by_bow(_p(kK), _p(dK), _p(mp), C.c_int(len(kK)), _p(kF), _p(dF), C.c_int(len(kF)), _p(n1a), _p(s1), _p(i1),
+                                C.c_int(len(n1a)), _p(n2a), _p(s2), _p(i2), C.c_int(len(n2a)), C.c_float(nnratio),
+                                C.c_int(int(check_orientation)), _p(out))
+    return nm, out

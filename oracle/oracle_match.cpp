@@ -613,4 +613,58 @@ int oracle_lsd_search_for_triangulation(const uint8_t* d1, const uint8_t* ml1, i
   }
   return nm;
 }
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (src/ORBmatcher.cc:187-327).
+// has_mp_kf[i] = (vpMapPointsKF[i] && !isBad()).  matchesF[j] = index of the KF feature whose MapPoint the frame feature j
+// receives (vpMapPointMatches[j] = vpMapPointsKF[matchesF[j]]), or -1.  Returns nmatches.
+int oracle_search_by_bow(const void* keysKF_, const uint8_t* descKF, const uint8_t* has_mp_kf, int nKF, const void* keysF_,
+                         const uint8_t* descF, int nF, const unsigned* fvK_nodes, const int* fvK_start, const int* fvK_items,
+                         int nnK, const unsigned* fvF_nodes, const int* fvF_start, const int* fvF_items, int nnF, float nnratio,
+                         int check_orientation, int* matchesF) {
+  const KeyPoint* kK = (const KeyPoint*)keysKF_;
+  const KeyPoint* kF = (const KeyPoint*)keysF_;
+  const int TH_LOW = 50;
+  (void)nKF;
+  for (int j = 0; j < nF; j++) matchesF[j] = -1;
+  int nmatches = 0;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  int a = 0, b = 0;
+  while (a < nnK && b < nnF) {
+    if (fvK_nodes[a] == fvF_nodes[b]) {
+      for (int iK = fvK_start[a]; iK < fvK_start[a + 1]; iK++) {
+        const int idxK = fvK_items[iK];
+        if (!has_mp_kf[idxK]) continue;
+        int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+        for (int iF = fvF_start[b]; iF < fvF_start[b + 1]; iF++) {
+          const int idxF = fvF_items[iF];
+          if (matchesF[idxF] >= 0) continue;
+          const int dist = descriptor_distance(descKF + 32 * idxK, descF + 32 * idxF);
+          if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = idxF; }
+          else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 <= TH_LOW) {
+          if ((float)bestDist1 < nnratio * (float)bestDist2) {
+            matchesF[bestIdxF] = idxK;
+            if (check_orientation) rotHist[rot_bin(kK[idxK].angle, kF[bestIdxF].angle)].push_back(bestIdxF);
+            nmatches++;
+          }
+        }
+      }
+      a++; b++;
+    } else if (fvK_nodes[a] < fvF_nodes[b]) {
+      while (a < nnK && fvK_nodes[a] < fvF_nodes[b]) a++;
+    } else {
+      while (b < nnF && fvF_nodes[b] < fvK_nodes[a]) b++;
+    }
+  }
+  if (check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int j : rotHist[i]) { matchesF[j] = -1; nmatches--; }
+    }
+  }
+  return nmatches;
+}
 }

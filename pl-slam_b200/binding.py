@@ -714,3 +714,19 @@ def _lsd_search_for_triangulation(self, ldesc1, has_ml1, ldesc2, has_ml2, isDoub
 
 
 LSDmatcher.SearchForTriangulation = _lsd_search_for_triangulation
+
+
+def _search_by_bow(self, keysKF_un, descKF, has_mp_kf, keysF, descF, fvKF, fvF):
+    """ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (reference src/ORBmatcher.cc:187-327) -> (nmatches, matchesF[F.N]):
+    matchesF[j] = index of the keyframe feature whose MapPoint frame feature j receives."""
+    kK = np.ascontiguousarray(keysKF_un, KP_DTYPE); kF = np.ascontiguousarray(keysF, KP_DTYPE)
+    dK = _u8(descKF); dF = _u8(descF); mp = _u8(has_mp_kf)
+    n1a, s1, i1 = _fv_csr(fvKF); n2a, s2, i2 = _fv_csr(fvF)
+    out = np.full(len(kF), -1, np.int32)
+    nm = check(lib().pl_orb_search_by_bow(_p(kK), _p(dK), _p(mp), C.c_int(len(kK)), _p(kF), _p(dF), C.c_int(len(kF)), _p(n1a), _p(s1),
+                                          _p(i1), C.c_int(len(n1a)), _p(n2a), _p(s2), _p(i2), C.c_int(len(n2a)),
+                                          C.c_float(self.mfNNratio), C.c_int(int(self.mbCheckOrientation)), _p(out)))
+    return nm, out
+
+
+ORBmatcher.SearchByBoW = _search_by_bow

@@ -834,6 +834,66 @@ __global__ void __launch_bounds__(32 * kFuseWarps) k_fuse_search(FuseArgs A) {
     if (lane == 0) { A.best_idx[i] = bi; A.best_dist[i] = bd; }
   }
 }
+
+// ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (src/ORBmatcher.cc:187-327).  A frame feature lives in exactly one
+// vocabulary node, so the "already matched" state couples only the keyframe features of the same node: one warp walks one
+// common node in the reference's order (keyframe features sequentially, the node's frame features across the lanes, packed
+// (distance, position) key for "first best wins", second = minimum over the rest), the nodes run in parallel.
+struct BowArgs {
+  const PLKeyPoint *kK, *kF; const uint8_t *dK, *dF, *mpK;
+  const int *pairK_s, *pairK_e, *pairF_s, *pairF_e, *itK, *itF; int npairs, nF;
+  float nnratio; int checkOri;
+  int* matchesF; unsigned char* bins; int* nmatches;
+};
+constexpr int kBowWarps = 16;
+__global__ void __launch_bounds__(32 * kBowWarps) k_search_by_bow(BowArgs A) {
+  __shared__ int hist[HISTO];
+  __shared__ int s_nm, s_keep[3];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid < HISTO) hist[tid] = 0;
+  if (tid == 0) s_nm = 0;
+  for (int j = tid; j < A.nF; j += blockDim.x) { A.matchesF[j] = -1; A.bins[j] = 255; }
+  __syncthreads();
+  for (int p = wid; p < A.npairs; p += kBowWarps) {
+    const int fs = A.pairF_s[p], fe = A.pairF_e[p];
+    for (int iK = A.pairK_s[p]; iK < A.pairK_e[p]; iK++) {
+      const int idxK = A.itK[iK];
+      if (!A.mpK[idxK]) continue;
+      unsigned long long k1 = KEY_NONE, k2 = KEY_NONE;
+      for (int c = fs + lane; c < fe; c += 32) {
+        const int idxF = A.itF[c];
+        if (A.matchesF[idxF] >= 0) continue;
+        const int dist = hamming256(A.dK + 32 * idxK, A.dF + 32 * idxF);
+        const unsigned long long k = mk_key(dist, 0, c - fs, idxF);
+        if (k < k1) { k2 = k1; k1 = k; } else if (k < k2) k2 = k;
+      }
+      const unsigned long long best = warp_min_u64(k1);
+      const unsigned long long second = warp_min_u64(k1 == best ? k2 : k1);
+      if (best == KEY_NONE) continue;
+      const int bestDist1 = key_dist(best), bestIdxF = key_idx(best);
+      const int bestDist2 = (second == KEY_NONE) ? 256 : key_dist(second);
+      if (bestDist1 <= 50 && (float)bestDist1 < __fmul_rn(A.nnratio, (float)bestDist2)) {
+        if (lane == 0) {
+          A.matchesF[bestIdxF] = idxK;
+          atomicAdd(&s_nm, 1);
+          if (A.checkOri) { const int bin = rot_bin(A.kK[idxK].angle, A.kF[bestIdxF].angle); A.bins[bestIdxF] = (unsigned char)bin; atomicAdd(&hist[bin], 1); }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
+  if (A.checkOri) {
+    if (tid == 0) { int a, b, c; three_maxima(hist, a, b, c); s_keep[0] = a; s_keep[1] = b; s_keep[2] = c; }
+    __syncthreads();
+    for (int j = tid; j < A.nF; j += blockDim.x) {
+      const int bin = A.bins[j];
+      if (bin != 255 && bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) { A.matchesF[j] = -1; atomicSub(&s_nm, 1); }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *A.nmatches = s_nm;
+}
 }  // namespace pl
 
 // ================================================================================================ C ABI
@@ -1228,4 +1288,41 @@ extern "C" int pl_orb_fuse_search(const PLKeyPoint* keys_un, const uint8_t* desc
   PL_LAUNCH_CHECK();
   rc = down(best_idx, A.best_idx, (size_t)n_mp); if (rc) return rc;
   return down(best_dist, A.best_dist, (size_t)n_mp);
+}
+
+extern "C" int pl_orb_search_by_bow(const PLKeyPoint* keysKF_un, const uint8_t* descKF, const uint8_t* has_mp_kf, int nKF,
+                                    const PLKeyPoint* keysF, const uint8_t* descF, int nF, const unsigned* fvK_nodes,
+                                    const int* fvK_start, const int* fvK_items, int nnK, const unsigned* fvF_nodes,
+                                    const int* fvF_start, const int* fvF_items, int nnF, float nnratio, int check_orientation,
+                                    int* matchesF) {
+  PL_ARG(keysKF_un && descKF && has_mp_kf && keysF && descF && matchesF && nKF >= 0 && nF >= 0 && nnK >= 0 && nnF >= 0);
+  PL_ARG((nnK == 0 || (fvK_nodes && fvK_start && fvK_items)) && (nnF == 0 || (fvF_nodes && fvF_start && fvF_items)));
+  int rc = require_device(); if (rc) return rc;
+  for (int j = 0; j < nF; j++) matchesF[j] = -1;
+  std::vector<int> ks, ke, fs, fe;     // the node merge of :203-296 on the host: one entry per common node
+  for (int a = 0, b = 0; a < nnK && b < nnF;) {
+    if (fvK_nodes[a] == fvF_nodes[b]) { ks.push_back(fvK_start[a]); ke.push_back(fvK_start[a + 1]); fs.push_back(fvF_start[b]); fe.push_back(fvF_start[b + 1]); a++; b++; }
+    else if (fvK_nodes[a] < fvF_nodes[b]) a++;
+    else b++;
+  }
+  if (ks.empty() || nKF == 0 || nF == 0) return 0;
+  const int nitK = fvK_start[nnK], nitF = fvF_start[nnF];
+  for (int i = 0; i < nitK; i++) PL_ARG(fvK_items[i] >= 0 && fvK_items[i] < nKF);
+  for (int i = 0; i < nitF; i++) PL_ARG(fvF_items[i] >= 0 && fvF_items[i] < nF);
+  PL_ARG(nF < (1 << 20));
+  Stage s;
+  BowArgs A;
+  A.kK = s.up(keysKF_un, nKF); A.kF = s.up(keysF, nF); A.dK = s.up(descKF, (size_t)nKF * 32); A.dF = s.up(descF, (size_t)nF * 32);
+  A.mpK = s.up(has_mp_kf, nKF);
+  A.pairK_s = s.up(ks.data(), ks.size()); A.pairK_e = s.up(ke.data(), ke.size()); A.pairF_s = s.up(fs.data(), fs.size()); A.pairF_e = s.up(fe.data(), fe.size());
+  A.itK = s.up(fvK_items, nitK); A.itF = s.up(fvF_items, nitF); A.npairs = (int)ks.size(); A.nF = nF;
+  A.nnratio = nnratio; A.checkOri = check_orientation;
+  A.matchesF = s.alloc<int>(nF); A.bins = s.alloc<unsigned char>(nF); A.nmatches = s.alloc<int>(1);
+  PL_ARG(A.kK && A.kF && A.dK && A.dF && A.mpK && A.pairK_s && A.pairK_e && A.pairF_s && A.pairF_e && A.itK && A.itF && A.matchesF && A.bins && A.nmatches);
+  k_search_by_bow<<<1, 32 * kBowWarps>>>(A);
+  PL_LAUNCH_CHECK();
+  int nm = 0;
+  rc = down(&nm, A.nmatches, 1); if (rc) return rc;
+  rc = down(matchesF, A.matchesF, (size_t)nF); if (rc) return rc;
+  return nm;
 }

@@ -70,3 +70,19 @@ def test_lsd_search_for_triangulation(seed, dbl):
     nm, m = pl.LSDmatcher(0.8).SearchForTriangulation(d1, ml1, d2, ml2, dbl)
     assert onm > 10 and nm == onm and np.array_equal(m, om)
     assert pl.LSDmatcher(0.8).SearchForTriangulation(d1[:0], ml1[:0], d2, ml2)[0] == 0
+
+
+@pytest.mark.parametrize("seed,ori,ratio", [(5, True, 0.7), (5, False, 0.7), (7, True, 0.9), (11, True, 0.6), (12, False, 0.75)])
+def test_search_by_bow(seed, ori, ratio):
+    s = synth.synth_two_view(seed)
+    a, b = s["1"], s["2"]
+    args = (a["keys"], a["desc"], a["has_mp"], b["keys"], b["desc"], a["fv"], b["fv"])
+    onm, om = oracle.search_by_bow(*args, ratio, ori)
+    nm, m = pl.ORBmatcher(ratio, ori).SearchByBoW(*args)
+    assert onm > 100 and nm == onm and np.array_equal(m, om)
+    # big nodes (more candidates than lanes) and empty inputs
+    fv1 = {0: [i for v in a["fv"].values() for i in v]}; fv2 = {0: [i for v in b["fv"].values() for i in v]}
+    onm, om = oracle.search_by_bow(a["keys"], a["desc"], a["has_mp"], b["keys"], b["desc"], fv1, fv2, ratio, ori)
+    nm, m = pl.ORBmatcher(ratio, ori).SearchByBoW(a["keys"], a["desc"], a["has_mp"], b["keys"], b["desc"], fv1, fv2)
+    assert nm == onm and np.array_equal(m, om)
+    assert pl.ORBmatcher(ratio, ori).SearchByBoW(a["keys"], a["desc"], a["has_mp"], b["keys"], b["desc"], {}, b["fv"])[0] == 0

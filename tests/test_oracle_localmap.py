@@ -90,3 +90,21 @@ def test_lsd_search_for_triangulation_semantics():
     want1 = np.array([j if j >= 0 and not ml1[i] and not ml2[j] else -1 for i, j in enumerate(f12)])
     assert nm1 >= nm and np.array_equal(m1, want1)
     assert oracle.lsd_search_for_triangulation(d1[:0], ml1[:0], d2, ml2)[0] == 0
+
+
+def test_search_by_bow_known_answers():
+    """ORBmatcher::SearchByBoW: matches join the two observations of a point; a frame feature is given away once."""
+    s = synth.synth_two_view(5)
+    a, b = s["1"], s["2"]
+    nm, m = oracle.search_by_bow(a["keys"], a["desc"], a["has_mp"], b["keys"], b["desc"], a["fv"], b["fv"], 0.7, True)
+    ok = m >= 0
+    assert nm == ok.sum() > 150
+    assert (a["pt_id"][m[ok]] == b["pt_id"][ok]).mean() > 0.99 and a["has_mp"][m[ok]].all()
+    assert len(np.unique(m[ok])) >= ok.sum() - 2            # (a KF feature may serve two frame features only via duplicates)
+    nm0, m0 = oracle.search_by_bow(a["keys"], a["desc"], a["has_mp"], b["keys"], b["desc"], a["fv"], b["fv"], 0.7, False)
+    assert nm0 >= nm and ((m == m0) | (m == -1)).all()
+    # "already matched" frame features are skipped by later keyframe features of the node: two identical KF features,
+    # one frame feature -> the first takes it, the second finds nothing
+    k = a["keys"][:2].copy(); d = np.repeat(a["desc"][:1], 2, 0)
+    nm2, m2 = oracle.search_by_bow(k, d, [1, 1], k[:1], d[:1], {0: [0, 1]}, {0: [0]}, 0.7, False)
+    assert nm2 == 1 and m2[0] == 0

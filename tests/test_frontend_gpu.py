@@ -123,3 +123,41 @@ def test_frontend_streaming_submit_wait():
     for w, g in zip(want, got):
         for k in pl.Frontend.ORDER:
             assert w[k].tobytes() == g[k].tobytes(), k
+
+
+def test_frontend_large_batch_properties():
+    """Size-independent properties at a batch that fills the GPU with one warp per frame (96 frames = 32 copies of a 3-frame
+    cycle): every frame's results depend only on the frame and its predecessor, so each copy must reproduce the 3-frame run
+    bit for bit; keylines come out ordered by response; match lists are injective."""
+    B0, R = 3, 32
+    base = synth.synth_sequence(B0, 640, 480, seed=8)
+    problems = [synth.synth_pose_problem(80 + k) for k in range(B0)]
+    small = pl.Frontend(640, 480, max_batch=B0, lm_caps=(320, 88)); small.set_pose_problems(problems)
+    small.set_camera(synth.TUM1_K, synth.TUM1_DIST)
+    ref = small.run(base)
+    big = pl.Frontend(640, 480, max_batch=B0 * R, lm_caps=(320, 88)); big.set_pose_problems(problems * R)
+    big.set_camera(synth.TUM1_K, synth.TUM1_DIST)
+    out = big.run(np.tile(base, (R, 1, 1)))
+    for r in range(R):
+        for b in range(B0):
+            i = r * B0 + b
+            n, nl = ref["n"][b], ref["nl"][b]
+            assert out["n"][i] == n and out["nl"][i] == nl
+            assert out["kps"][i, :n].tobytes() == ref["kps"][b, :n].tobytes() and np.array_equal(out["desc"][i, :n], ref["desc"][b, :n])
+            assert out["keylines"][i, :nl].tobytes() == ref["keylines"][b, :nl].tobytes()
+            assert np.array_equal(out["ldesc"][i, :nl], ref["ldesc"][b, :nl])
+            npv = ref["n"][(b - 1) % B0]
+            assert out["n_pt_matches"][i] == ref["n_pt_matches"][b] and np.array_equal(out["pt_matches"][i, :npv], ref["pt_matches"][b, :npv])
+            nlp = ref["nl"][(b - 1) % B0]
+            assert out["n_line_matches"][i] == ref["n_line_matches"][b]
+            assert np.array_equal(out["line_matches"][i, :nlp], ref["line_matches"][b, :nlp])
+            assert np.array_equal(out["poses"][:, i], ref["poses"][:, b]) and np.array_equal(out["inliers"][:, i], ref["inliers"][:, b])
+    for i in range(0, B0 * R, 7):
+        nl = out["nl"][i]
+        resp = out["keylines"][i, :nl]["response"]
+        resp = resp[resp > 0]                                    # the reference's zero KeyLine (nfeatures+1 quirk) has response 0
+        assert len(resp) >= 100 and (np.diff(resp) <= 0).all()
+        m = out["pt_matches"][i]; m = m[m >= 0]
+        assert len(np.unique(m)) == len(m)
+        lm = out["line_matches"][i]; lm = lm[lm >= 0]
+        assert len(np.unique(lm)) == len(lm)

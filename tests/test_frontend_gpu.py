@@ -157,7 +157,8 @@ def test_frontend_large_batch_properties():
         resp = out["keylines"][i, :nl]["response"]
         resp = resp[resp > 0]                                    # the reference's zero KeyLine (nfeatures+1 quirk) has response 0
         assert len(resp) >= 100 and (np.diff(resp) <= 0).all()
-        m = out["pt_matches"][i]; m = m[m >= 0]
-        assert len(np.unique(m)) == len(m)
-        lm = out["line_matches"][i]; lm = lm[lm >= 0]
-        assert len(np.unique(lm)) == len(lm)
+        prev = (i - 1) % (B0 * R)
+        m = out["pt_matches"][i, :out["n"][prev]]; m = m[m >= 0]           # entries past the predecessor's count are not written
+        assert len(m) == out["n_pt_matches"][i] and len(np.unique(m)) == len(m)
+        lm = out["line_matches"][i, :out["nl"][prev]]; lm = lm[lm >= 0]
+        assert len(lm) == out["n_line_matches"][i] and len(np.unique(lm)) == len(lm)

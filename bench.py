@@ -194,6 +194,8 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # NCCL writes its version / INFO lines to stdout by default; stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
     frames, problems = make_inputs(B, seed=1 + rank)        # weak scaling: every rank gets its own B frames

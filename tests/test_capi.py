@@ -40,3 +40,17 @@ def test_product_never_imports_oracle():
         if path.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".cc")):
             src = open(path, errors="ignore").read()
             assert "import oracle" not in src and "liboracle" not in src and "oracle/" not in src, path
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/plslam_b200.h compiles as C99 (no C++ types in the signatures) and every exported
+    pl_* symbol of the library is declared in it."""
+    import subprocess
+    src = tmp_path / "cabi.c"
+    src.write_text('#include "plslam_b200.h"\nint main(void) { return pl_version() < 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src),
+                           "-o", str(tmp_path / "cabi.o")])
+    out = subprocess.check_output(["nm", "-D", "--defined-only", pl.LIB_PATH]).decode()
+    exported = sorted(set(re.findall(r"\bT (pl_[a-z0-9_]+)\b", out)))
+    undeclared = [s for s in exported if s not in declared_symbols()]
+    assert not undeclared, undeclared

@@ -239,8 +239,10 @@ __global__ void __launch_bounds__(256) k_lsd_hist(LineParams P, const float* __r
   const int y0 = chunk * kChunkRows, y1 = min(y0 + kChunkRows, P.sh - 1);
   const float* G = ANG + (long long)f * P.npx;
   const int* SS = S2 + (long long)f * P.npx;
-  for (int i = y0 * P.sw + tid; i < y1 * P.sw; i += 256)      // rows y0..y1-1 are contiguous: no (y, x) needed here
-    if (G[i] != kNotDefDeg) atomicAdd(&hist[s_bin(SS[i], bin_coef)], 1);
+  for (int i = tid; i < (y1 - y0) * P.sw; i += 256) {
+    int y = y0 + i / P.sw, x = i % P.sw;
+    if (G[y * P.sw + x] != kNotDefDeg) atomicAdd(&hist[s_bin(SS[y * P.sw + x], bin_coef)], 1);
+  }
   __syncthreads();
   for (int i = tid; i < kBins; i += 256) counts[((long long)f * kBins + i) * P.nchunk + chunk] = (unsigned short)hist[i];
 }
@@ -290,13 +292,10 @@ __global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const float* 
   unsigned* O = order + (long long)f * P.npx;
   const int n = (y1 - y0) * P.sw;
   const unsigned lt = (1u << lane) - 1u;
-  // (y, x) of pixel i0 + lane advance by 32 per trip without dividing: x += 32 % sw, y += 32 / sw, one carry
-  const int q32 = 32 / P.sw, r32 = 32 - q32 * P.sw;
-  int y = y0 + lane / P.sw, x = lane - (lane / P.sw) * P.sw;
-  for (int i0 = 0; i0 < n; i0 += 32, x += r32, y += q32) {
-    if (x >= P.sw) { x -= P.sw; y++; }
+  for (int i0 = 0; i0 < n; i0 += 32) {
     int i = i0 + lane, bin = -1, pix = 0;
     if (i < n) {
+      int y = y0 + i / P.sw, x = i % P.sw;
       pix = x | (y << 16);                       // packed (x, y): the grow kernel never divides
       if (G[y * P.sw + x] != kNotDefDeg) bin = s_bin(SS[y * P.sw + x], bin_coef);
     }

@@ -12,6 +12,8 @@
 //   BinaryDescriptor::compute (LBD)       spec copy Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp
 //                                         :74-116 (band pairs), :217-259 (weights), :350-398 (blur+Sobel),
 //                                         :539-687 (computeImpl), :1026-1372 (computeLBD)
+// Parity status: LSD PINNED end to end to cv2 4.13; LBD, the KeyLine conversion and LINEextractor's selection are PARITY
+// UNPINNED (opencv_contrib's line_descriptor is not installed; they follow the vendored spec copy line by line).
 // Seed ordering: OpenCV sorts the pixels by gradient bin with std::sort, which is not stable, so the order of equal
 // bins is whatever libstdc++'s introsort produces.  order_mode 0 reproduces that (same std::sort call on the same
 // records: this is the mode pinned to cv2); order_mode 1 is the documented tie rule the GPU path implements

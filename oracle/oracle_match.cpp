@@ -14,7 +14,9 @@
 //   LSDmatcher::SearchByProjection (both)     src/LSDmatcher.cpp:72-176, :221-338
 // cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) is third-party (OpenCV, not vendored): restated as "two smallest
 // distances, ties -> lower train index first" and pinned against cv2 4.13 in tests/test_oracle_match.py.
-// Parity status: the reference holds no golden vectors for this path.
+// Parity status: knnMatch PINNED to cv2 4.13; everything else PARITY UNPINNED — the reference holds no golden vectors or
+// tests for its matchers; each function follows the cited source lines, with known-answer tests on synthetic
+// two-view geometry (tests/test_oracle_match.py, tests/test_oracle_localmap.py).
 // Waived: the debug JPEG writes (LSDmatcher.cpp:67,173,422) and stereo branches (mvuRight) are not restated.
 
 #include <cmath>

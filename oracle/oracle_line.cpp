@@ -14,10 +14,10 @@
 //                                         :539-687 (computeImpl), :1026-1372 (computeLBD)
 // Parity status: LSD PINNED end to end to cv2 4.13; LBD, the KeyLine conversion and LINEextractor's selection are PARITY
 // UNPINNED (opencv_contrib's line_descriptor is not installed; they follow the vendored spec copy line by line).
-// Seed ordering: OpenCV sorts the pixels by gradient bin with std::sort, which is not stable, so the order of equal
-// bins is whatever libstdc++'s introsort produces.  order_mode 0 reproduces that (same std::sort call on the same
-// records: this is the mode pinned to cv2); order_mode 1 is the documented tie rule the GPU path implements
-// (stable: equal bins keep row-major pixel order).  See DESIGN.md §6.
+// Seed ordering: OpenCV 4.13's ll_angle orders the pixels by gradient bin such that equal bins keep row-major pixel
+// order (a stable ordering).  order_mode 1 (the default, std::stable_sort) reproduces cv2's segment lists exactly and is
+// what the GPU path implements; order_mode 0 (an unstable std::sort on the same records) is kept only to show that it
+// does NOT reproduce cv2.  See DESIGN.md §2.
 // Other fixed choices: the KeyLine that LineExtractor.cpp:64 appends through resize() is value-initialised
 // (all zero) here — in the reference its fields are indeterminate; lines of equal response keep detection order
 // (the reference's std::sort is unstable there too); 0 detected lines -> 1 zero KeyLine (the reference reads

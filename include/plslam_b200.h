@@ -328,10 +328,13 @@ int pl_orb_search_by_bow(const PLKeyPoint* keysKF_un, const uint8_t* descKF, con
                          const int* fvK_items, int nnK, const unsigned* fvF_nodes, const int* fvF_start, const int* fvF_items,
                          int nnF, float nnratio, int check_orientation, int* matchesF);
 /* LSDmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, isDouble) (src/LSDmatcher.cpp:727-776; LocalMapping.cc:961):
- * FrameBFMatch both ways at TH_HIGH = 80 with the matcher's nnratio, mutual check when is_double, pairs touching a line that
- * already has a MapLine (has_ml*) removed.  matched_pairs[i] = j or -1; returns nmatches. */
+ * FrameBFMatch both ways at th (TH_HIGH = 80 there) with the matcher's nnratio, mutual check when is_double, pairs touching a
+ * line that already has a MapLine (has_ml*) removed.  The pair<> overload (:672-725; LocalMapping.cc:679) is th = TH_LOW = 50,
+ * is_double = 1.  matched_pairs[i] = j or -1; returns nmatches.
+ * LSDmatcher::SearchDouble(KeyFrame*, Frame&) (:375-430; Tracking.cc:1159) is pl_lsd_search_double(F.mLdesc, KF.mLineDescriptors)
+ * followed by keeping the pairs whose keyframe line has a MapLine. */
 int pl_lsd_search_for_triangulation(const uint8_t* ldesc1, const uint8_t* has_ml1, int n1, const uint8_t* ldesc2,
-                                    const uint8_t* has_ml2, int n2, float nnratio, int is_double, int* matched_pairs);
+                                    const uint8_t* has_ml2, int n2, float th, float nnratio, int is_double, int* matched_pairs);
 /* The search half of ORBmatcher::Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:914-1034): best keypoint of the keyframe for
  * every map point (best_idx = -1 / best_dist = 256 when skipped or nothing qualifies).  skip[i] = !pMP || isBad || IsInKeyFrame;
  * the caller applies :1036-1061 (Replace / AddObservation) to the points with best_dist <= TH_LOW (50) in order. */

@@ -492,14 +492,14 @@ def fuse_search(keys, desc, bounds, Tcw, Ow, K, scale_factors, inv_level_sigma2,
     return bi, bd
 
 
-def lsd_search_for_triangulation(d1, has_ml1, d2, has_ml2, nnratio=0.8, is_double=True):
+def lsd_search_for_triangulation(d1, has_ml1, d2, has_ml2, nnratio=0.8, is_double=True, th=80.0):
     """LSDmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, isDouble) (LSDmatcher.cpp:727-776)."""
     d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
     m1 = np.ascontiguousarray(has_ml1, np.uint8); m2 = np.ascontiguousarray(has_ml2, np.uint8)
     out = np.full(len(d1), -1, np.int32)
     L = lib(); L.oracle_lsd_search_for_triangulation.restype = C.c_int
     nm = L.oracle_lsd_search_for_triangulation(_p(d1), _p(m1), C.c_int(len(d1)), _p(d2), _p(m2), C.c_int(len(d2)),
-                                               C.c_float(nnratio), C.c_int(int(is_double)), _p(out))
+                                               C.c_float(th), C.c_float(nnratio), C.c_int(int(is_double)), _p(out))
     return nm, out
 
 

@@ -599,12 +599,12 @@ void oracle_fuse_search(const void* keys_, const uint8_t* desc, int n, const flo
 
 // LSDmatcher::SearchForTriangulation(pKF1, pKF2, vector<int>& vMatchedPairs, bool isDouble) (src/LSDmatcher.cpp:727-776)
 int oracle_lsd_search_for_triangulation(const uint8_t* d1, const uint8_t* ml1, int n1, const uint8_t* d2, const uint8_t* ml2,
-                                        int n2, float nnratio, int isDouble, int* pairs) {
+                                        int n2, float th, float nnratio, int isDouble, int* pairs) {
   for (int i = 0; i < n1; i++) pairs[i] = -1;
   if (n1 == 0 || n2 == 0) return 0;
   std::vector<int> m1(n1), m2(n2);
-  frame_bf_match(d1, n1, d2, n2, 80.f, nnratio, m1.data());
-  frame_bf_match(d2, n2, d1, n1, 80.f, nnratio, m2.data());
+  frame_bf_match(d1, n1, d2, n2, th, nnratio, m1.data());
+  frame_bf_match(d2, n2, d1, n1, th, nnratio, m2.data());
   int nm = 0;
   for (int i = 0; i < n1; i++) {
     const int j = m1[i];

@@ -703,13 +703,15 @@ ORBmatcher.SearchForTriangulation = _search_for_triangulation
 ORBmatcher.FuseSearch = _fuse_search
 
 
-def _lsd_search_for_triangulation(self, ldesc1, has_ml1, ldesc2, has_ml2, isDouble=True):
+def _lsd_search_for_triangulation(self, ldesc1, has_ml1, ldesc2, has_ml2, isDouble=True, th=None):
     """LSDmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, isDouble) (reference src/LSDmatcher.cpp:727-776)
-    -> (nmatches, vMatchedPairs[NL1])."""
+    -> (nmatches, vMatchedPairs[NL1]); th defaults to TH_HIGH (the 4-argument overload), th = TH_LOW + isDouble is the
+    pair<> overload (:672-725)."""
+    th = float(self.TH_HIGH if th is None else th)
     d1 = _u8(ldesc1).reshape(-1, 32); d2 = _u8(ldesc2).reshape(-1, 32); m1 = _u8(has_ml1); m2 = _u8(has_ml2)
     out = np.full(len(d1), -1, np.int32)
     nm = check(lib().pl_lsd_search_for_triangulation(_p(d1), _p(m1), C.c_int(len(d1)), _p(d2), _p(m2), C.c_int(len(d2)),
-                                                     C.c_float(self.mfNNratio), C.c_int(int(isDouble)), _p(out)))
+                                                     C.c_float(th), C.c_float(self.mfNNratio), C.c_int(int(isDouble)), _p(out)))
     return nm, out
 
 

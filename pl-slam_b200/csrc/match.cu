@@ -1114,14 +1114,15 @@ extern "C" int pl_lsd_search_double(const uint8_t* d1, int n1, const uint8_t* d2
   return search_double_host(d1, n1, d2, n2, 50.f, nnratio, 1, matches);
 }
 // LSDmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, isDouble) (src/LSDmatcher.cpp:727-776, the variant
-// LocalMapping calls at LocalMapping.cc:961): FrameBFMatch both ways at TH_HIGH = 80, optional mutual check, then pairs
+// LocalMapping calls at LocalMapping.cc:961, th = TH_HIGH = 80) and its pair<> twin (:672-725, LocalMapping.cc:679, th = TH_LOW = 50,
+// always mutual): FrameBFMatch both ways at th, optional mutual check, then pairs
 // whose line already has a MapLine on either side are dropped (a few hundred flags: applied on the host).
 extern "C" int pl_lsd_search_for_triangulation(const uint8_t* ldesc1, const uint8_t* has_ml1, int n1, const uint8_t* ldesc2,
-                                               const uint8_t* has_ml2, int n2, float nnratio, int is_double, int* matched_pairs) {
+                                               const uint8_t* has_ml2, int n2, float th, float nnratio, int is_double, int* matched_pairs) {
   PL_ARG(matched_pairs && n1 >= 0 && n2 >= 0 && (n1 == 0 || (ldesc1 && has_ml1)) && (n2 == 0 || (ldesc2 && has_ml2)));
   for (int i = 0; i < n1; i++) matched_pairs[i] = -1;
   if (n1 == 0 || n2 == 0) { int rc = require_device(); return rc ? rc : 0; }     // ldesc.rows == 0 -> return 0 (:738-739)
-  int rc = search_double_host(ldesc1, n1, ldesc2, n2, 80.f, nnratio, is_double ? 1 : 0, matched_pairs);
+  int rc = search_double_host(ldesc1, n1, ldesc2, n2, th, nnratio, is_double ? 1 : 0, matched_pairs);
   if (rc < 0) return rc;
   int nm = 0;
   for (int i = 0; i < n1; i++) {

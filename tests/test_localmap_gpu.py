@@ -69,6 +69,9 @@ def test_lsd_search_for_triangulation(seed, dbl):
     onm, om = oracle.lsd_search_for_triangulation(d1, ml1, d2, ml2, 0.8, dbl)
     nm, m = pl.LSDmatcher(0.8).SearchForTriangulation(d1, ml1, d2, ml2, dbl)
     assert onm > 10 and nm == onm and np.array_equal(m, om)
+    onm2, om2 = oracle.lsd_search_for_triangulation(d1, ml1, d2, ml2, 0.8, True, 50.0)     # the pair<> overload: TH_LOW, mutual
+    nm2, m2 = pl.LSDmatcher(0.8).SearchForTriangulation(d1, ml1, d2, ml2, True, th=50)
+    assert nm2 == onm2 and np.array_equal(m2, om2) and onm2 <= onm + 200
     assert pl.LSDmatcher(0.8).SearchForTriangulation(d1[:0], ml1[:0], d2, ml2)[0] == 0
 
 

@@ -320,6 +320,17 @@ int pl_orb_search_for_triangulation(const PLKeyPoint* keys1_un, const uint8_t* d
                                     const float* F12, const float* Cw1, const float* R2w, const float* t2w, const float* K2,
                                     const float* scale_factors2, const float* level_sigma2_2, int nlevels,
                                     int check_orientation, int* matches12);
+/* ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1587-1716;
+ * Tracking::Relocalization Tracking.cc:2194,2208).  kf_valid[i] = pMP && !isBad() && !sAlreadyFound.count(pMP) for the keyframe's
+ * map-point matches; pos / mp_desc / min,max_dist = GetWorldPos, GetDescriptor, Get{Min,Max}DistanceInvariance; kf_angle =
+ * pKF->mvKeysUn[i].angle; Ow = camera centre of the current pose; cur_preassigned[i2] = mvpMapPoints[i2] != NULL.
+ * cur_match[i2] = keyframe index i, -1, or -2 (was preassigned); returns nmatches. */
+int pl_orb_search_by_projection_keyframe(const PLKeyPoint* keys_cur, const uint8_t* desc_cur, int n_cur, const float* bounds,
+                                         const float* Tcw, const float* Ow, const float* K, const float* scale_factors, int nlevels,
+                                         float log_scale_factor, int n_kf, const uint8_t* kf_valid, const float* pos,
+                                         const uint8_t* mp_desc, const float* min_dist, const float* max_dist,
+                                         const float* kf_angle, float th, int orb_dist, int check_orientation,
+                                         const uint8_t* cur_preassigned, int* cur_match);
 /* ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (src/ORBmatcher.cc:187-327; TrackReferenceKeyFrame Tracking.cc:1157,
  * Relocalization :2119): has_mp_kf[i] = vpMapPointsKF[i] && !isBad(); fv* as in pl_orb_search_for_triangulation; keysF = F.mvKeys.
  * matchesF[j] = keyframe feature whose MapPoint frame feature j receives, or -1; returns nmatches. */

@@ -514,3 +514,20 @@ def search_by_bow(kK, dK, has_mp_kf, kF, dF, fvK, fvF, nnratio=0.7, check_orient
                                 C.c_int(len(n1a)), _p(n2a), _p(s2), _p(i2), C.c_int(len(n2a)), C.c_float(nnratio),
                                 C.c_int(int(check_orientation)), _p(out))
     return nm, out
+
+
+def search_by_projection_keyframe(kc, dc, bounds, Tcw, Ow, K, scale_factors, log_scale_factor, kf_valid, pos, mp_desc, min_dist,
+                                  max_dist, kf_angle, th, orb_dist, check_orientation=True, preassigned=None):
+    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1587-1716)."""
+    kc = np.ascontiguousarray(kc, KP_DTYPE); dc = np.ascontiguousarray(dc, np.uint8)
+    b = _f32(bounds); T = _f32(Tcw); O = _f32(Ow); Kc = _f32(K); sf = _f32(scale_factors)
+    v = np.ascontiguousarray(kf_valid, np.uint8); pos = _f32(pos); md = np.ascontiguousarray(mp_desc, np.uint8)
+    mn = _f32(min_dist); mx = _f32(max_dist); ang = _f32(kf_angle)
+    pre = None if preassigned is None else np.ascontiguousarray(preassigned, np.uint8)
+    out = np.full(len(kc), -1, np.int32)
+    L = lib(); L.oracle_search_by_projection_keyframe.restype = C.c_int
+    nm = L.oracle_search_by_projection_keyframe(_p(kc), _p(dc), C.c_int(len(kc)), _p(b), _p(T), _p(O), _p(Kc), _p(sf), C.c_int(len(sf)),
+                                                C.c_float(log_scale_factor), C.c_int(len(v)), _p(v), _p(pos), _p(md), _p(mn), _p(mx),
+                                                _p(ang), C.c_float(th), C.c_int(orb_dist), C.c_int(int(check_orientation)), _p(pre),
+                                                _p(out))
+    return nm, out

@@ -669,4 +669,62 @@ int oracle_search_by_bow(const void* keysKF_, const uint8_t* descKF, const uint8
   }
   return nmatches;
 }
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist)
+// (src/ORBmatcher.cc:1587-1716, Tracking::Relocalization).  kf_valid[i] = pMP && !isBad() && !sAlreadyFound.count(pMP);
+// cur_preassigned[i2] = CurrentFrame.mvpMapPoints[i2] != NULL.  Unlike the LastFrame overload there is no invzc < 0 test,
+// the level comes from MapPoint::PredictScale(dist3D, &CurrentFrame) and the threshold is ORBdist.
+int oracle_search_by_projection_keyframe(const void* keys_cur_, const uint8_t* desc_cur, int n_cur, const float* bounds,
+                                         const float* Tcw, const float* Ow, const float* K, const float* scaleFactors, int nlevels,
+                                         float logScaleFactor, int n_kf, const uint8_t* kf_valid, const float* pos,
+                                         const uint8_t* mp_desc, const float* minDist, const float* maxDist,
+                                         const float* kf_angle, float th, int ORBdist, int checkOri,
+                                         const uint8_t* cur_preassigned, int* cur_match) {
+  const KeyPoint* kc = (const KeyPoint*)keys_cur_;
+  Grid g; g.init(bounds);
+  assign_points(g, kc, n_cur);
+  int nmatches = 0;
+  for (int i = 0; i < n_cur; i++) cur_match[i] = (cur_preassigned && cur_preassigned[i]) ? -2 : -1;
+  std::vector<int> rotHist[HISTO_LENGTH], cand;
+  for (int i = 0; i < n_kf; i++) {
+    if (!kf_valid[i]) continue;
+    const float* X = pos + 3 * i;
+    float xc = Tcw[0] * X[0] + Tcw[1] * X[1] + Tcw[2] * X[2] + Tcw[3];
+    float yc = Tcw[4] * X[0] + Tcw[5] * X[1] + Tcw[6] * X[2] + Tcw[7];
+    float zc = Tcw[8] * X[0] + Tcw[9] * X[1] + Tcw[10] * X[2] + Tcw[11];
+    const float invzc = (float)(1.0 / zc);
+    float u = K[0] * xc * invzc + K[2];
+    float v = K[1] * yc * invzc + K[3];
+    if (u < g.minX || u > g.maxX) continue;
+    if (v < g.minY || v > g.maxY) continue;
+    const float PO[3] = {X[0] - Ow[0], X[1] - Ow[1], X[2] - Ow[2]};
+    const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
+    if (dist3D < minDist[i] || dist3D > maxDist[i]) continue;
+    const float ratio = maxDist[i] / dist3D;
+    int lvl = (int)std::ceil(std::log((double)ratio) / (double)logScaleFactor);
+    if (lvl < 0) lvl = 0; else if (lvl >= nlevels) lvl = nlevels - 1;
+    const float radius = th * scaleFactors[lvl];
+    features_in_area(g, kc, u, v, radius, lvl - 1, lvl + 1, cand);
+    if (cand.empty()) continue;
+    int bestDist = 256, bestIdx2 = -1;
+    for (int i2 : cand) {
+      if (cur_match[i2] != -1) continue;
+      const int dist = descriptor_distance(mp_desc + 32 * i, desc_cur + 32 * i2);
+      if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+    }
+    if (bestDist <= ORBdist) {
+      cur_match[bestIdx2] = i;
+      nmatches++;
+      if (checkOri) rotHist[rot_bin(kf_angle[i], kc[bestIdx2].angle)].push_back(bestIdx2);
+    }
+  }
+  if (checkOri) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++)
+      if (i != ind1 && i != ind2 && i != ind3)
+        for (int j : rotHist[i]) { cur_match[j] = -1; nmatches--; }
+  }
+  return nmatches;
+}
 }

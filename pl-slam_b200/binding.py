@@ -732,3 +732,22 @@ def _search_by_bow(self, keysKF_un, descKF, has_mp_kf, keysF, descF, fvKF, fvF):
 
 
 ORBmatcher.SearchByBoW = _search_by_bow
+
+
+def _search_by_projection_keyframe(self, keys_cur_un, desc_cur, bounds, Tcw, Ow, K, scale_factors, log_scale_factor, kf_valid, pos,
+                                   mp_desc, min_dist, max_dist, kf_angle, th, ORBdist, preassigned=None):
+    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (reference src/ORBmatcher.cc:1587-1716)
+    -> (nmatches, cur_match[F.N]) with cur_match[i2] = index into the keyframe's map-point list."""
+    kc = np.ascontiguousarray(keys_cur_un, KP_DTYPE); dc = _u8(desc_cur)
+    b = _f32(bounds); T = _f32(Tcw); O = _f32(Ow); Kc = _f32(K); sf = _f32(scale_factors)
+    v = _u8(kf_valid); pos = _f32(pos); md = _u8(mp_desc); mn = _f32(min_dist); mx = _f32(max_dist); ang = _f32(kf_angle)
+    pre = None if preassigned is None else _u8(preassigned)
+    out = np.full(len(kc), -1, np.int32)
+    nm = check(lib().pl_orb_search_by_projection_keyframe(
+        _p(kc), _p(dc), C.c_int(len(kc)), _p(b), _p(T), _p(O), _p(Kc), _p(sf), C.c_int(len(sf)), C.c_float(log_scale_factor),
+        C.c_int(len(v)), _p(v), _p(pos), _p(md), _p(mn), _p(mx), _p(ang), C.c_float(th), C.c_int(int(ORBdist)),
+        C.c_int(int(self.mbCheckOrientation)), _p(pre), _p(out)))
+    return nm, out
+
+
+ORBmatcher.SearchByProjectionKeyFrame = _search_by_projection_keyframe

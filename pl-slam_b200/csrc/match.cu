@@ -309,6 +309,8 @@ struct ProjLastArgs {
   const int* n_last; int cap_last; const uint8_t* last_valid; const float* last_pos; const uint8_t* last_desc;
   const int* last_octave; const float* last_angle;
   float th; int checkOri; const uint8_t* preassigned; int* match; int* nmatches;
+  // keyframe overload (ORBmatcher.cc:1587-1716, relocalisation): level from MapPoint::PredictScale(dist3D, F), no invzc < 0 test
+  int kfMode = 0, maxDist = 100; const float *min_dist = nullptr, *max_dist = nullptr; float Ow[3] = {0, 0, 0}; float logSF = 1.f;
 };
 
 __global__ void __launch_bounds__(32) k_search_proj_last(ProjLastArgs A) {
@@ -341,18 +343,26 @@ __global__ void __launch_bounds__(32) k_search_proj_last(ProjLastArgs A) {
     float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], X[0]), __fmul_rn(T[5], X[1])), __fmul_rn(T[6], X[2])), T[7]);
     float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], X[0]), __fmul_rn(T[9], X[1])), __fmul_rn(T[10], X[2])), T[11]);
     const float invzc = (float)(1.0 / (double)zc);
-    if (invzc < 0) continue;
+    if (!A.kfMode && invzc < 0) continue;
     float u = __fadd_rn(__fmul_rn(__fmul_rn(fx, xc), invzc), cx);
     float v = __fadd_rn(__fmul_rn(__fmul_rn(fy, yc), invzc), cy);
     if (u < g.minX || u > g.maxX) continue;
     if (v < g.minY || v > g.maxY) continue;
-    const int oct = A.last_octave[lb + i];
+    int oct;
+    if (A.kfMode) {
+      const float p0 = __fsub_rn(X[0], A.Ow[0]), p1 = __fsub_rn(X[1], A.Ow[1]), p2 = __fsub_rn(X[2], A.Ow[2]);
+      const float dist3D = (float)sqrt((double)p0 * p0 + (double)p1 * p1 + (double)p2 * p2);
+      if (dist3D < A.min_dist[lb + i] || dist3D > A.max_dist[lb + i]) continue;
+      const float ratio = __fdiv_rn(A.max_dist[lb + i], dist3D);
+      oct = (int)ceil(log((double)ratio) / (double)A.logSF);
+      if (oct < 0) oct = 0; else if (oct >= A.nlevels) oct = A.nlevels - 1;
+    } else oct = A.last_octave[lb + i];
     const float radius = __fmul_rn(A.th, A.scaleFactors[oct]);
     Top2 t = window_top2(kc, dc, sg.start, sg.items, g, u, v, radius, oct - 1, oct + 1, A.last_desc + (lb + i) * 32,
                          skip, lane, packed);
     if (t.best == KEY_NONE) continue;
     const int bestDist = key_dist(t.best), bestIdx2 = key_idx(t.best);
-    if (bestDist <= 100) {
+    if (bestDist <= A.maxDist) {
       nmatches++;
       if (lane == 0) {
         match[bestIdx2] = i;
@@ -1325,5 +1335,38 @@ extern "C" int pl_orb_search_by_bow(const PLKeyPoint* keysKF_un, const uint8_t* 
   int nm = 0;
   rc = down(&nm, A.nmatches, 1); if (rc) return rc;
   rc = down(matchesF, A.matchesF, (size_t)nF); if (rc) return rc;
+  return nm;
+}
+
+extern "C" int pl_orb_search_by_projection_keyframe(const PLKeyPoint* keys_cur, const uint8_t* desc_cur, int n_cur, const float* bounds,
+                                                    const float* Tcw, const float* Ow, const float* K, const float* scale_factors,
+                                                    int nlevels, float log_scale_factor, int n_kf, const uint8_t* kf_valid,
+                                                    const float* pos, const uint8_t* mp_desc, const float* min_dist,
+                                                    const float* max_dist, const float* kf_angle, float th, int orb_dist,
+                                                    int check_orientation, const uint8_t* cur_preassigned, int* cur_match) {
+  PL_ARG(keys_cur && desc_cur && bounds && Tcw && Ow && K && scale_factors && cur_match && n_cur >= 0 && n_cur <= 6144 && n_kf >= 0 && nlevels > 0);
+  PL_ARG(n_kf == 0 || (kf_valid && pos && mp_desc && min_dist && max_dist && kf_angle));
+  int rc = require_device(); if (rc) return rc;
+  Stage s;
+  const int cap = std::max(n_cur, 1), capl = std::max(n_kf, 1);
+  ProjLastArgs A;
+  A.keys = s.up(keys_cur, n_cur); A.desc = s.up(desc_cur, (size_t)n_cur * 32); A.n = s.up(&n_cur, 1); A.cap = cap;
+  A.bounds = s.up(bounds, 4); A.Tcw = s.up(Tcw, 16); A.K = s.up(K, 4); A.scaleFactors = s.up(scale_factors, nlevels);
+  A.nlevels = nlevels; A.n_last = s.up(&n_kf, 1); A.cap_last = capl;
+  A.last_valid = s.up(kf_valid, n_kf); A.last_pos = s.up(pos, (size_t)n_kf * 3); A.last_desc = s.up(mp_desc, (size_t)n_kf * 32);
+  A.last_octave = nullptr; A.last_angle = s.up(kf_angle, n_kf);
+  A.th = th; A.checkOri = check_orientation;
+  A.preassigned = cur_preassigned ? s.up(cur_preassigned, n_cur) : nullptr;
+  A.match = s.alloc<int>(cap); A.nmatches = s.alloc<int>(1);
+  A.kfMode = 1; A.maxDist = orb_dist; A.min_dist = s.up(min_dist, n_kf); A.max_dist = s.up(max_dist, n_kf);
+  memcpy(A.Ow, Ow, 12); A.logSF = log_scale_factor;
+  PL_ARG(A.keys && A.desc && A.match && A.nmatches && A.last_pos && A.last_desc && A.min_dist && A.max_dist && A.last_angle);
+  size_t sm = grid_smem_bytes(cap);
+  PL_CUDA(cudaFuncSetAttribute(k_search_proj_last, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_search_proj_last<<<1, 32, sm>>>(A);
+  PL_LAUNCH_CHECK();
+  int nm = 0;
+  rc = down(&nm, A.nmatches, 1); if (rc) return rc;
+  if (n_cur) { rc = down(cur_match, A.match, (size_t)n_cur); if (rc) return rc; }
   return nm;
 }

@@ -89,3 +89,15 @@ def test_search_by_bow(seed, ori, ratio):
     nm, m = pl.ORBmatcher(ratio, ori).SearchByBoW(a["keys"], a["desc"], a["has_mp"], b["keys"], b["desc"], fv1, fv2)
     assert nm == onm and np.array_equal(m, om)
     assert pl.ORBmatcher(ratio, ori).SearchByBoW(a["keys"], a["desc"], a["has_mp"], b["keys"], b["desc"], {}, b["fv"])[0] == 0
+
+
+@pytest.mark.parametrize("seed,th,dist,ori", [(6, 10.0, 100, True), (8, 3.0, 64, True), (9, 10.0, 100, False), (10, 3.0, 64, False)])
+def test_search_by_projection_keyframe(seed, th, dist, ori):
+    from test_oracle_localmap import _reloc_args
+    args, pre = _reloc_args(seed, th, dist)
+    onm, om = oracle.search_by_projection_keyframe(*args, ori, pre)
+    nm, m = pl.ORBmatcher(0.9, ori).SearchByProjectionKeyFrame(*args, pre)
+    assert onm > 10 and nm == onm and np.array_equal(m, om)
+    onm, om = oracle.search_by_projection_keyframe(*args, ori, None)
+    nm, m = pl.ORBmatcher(0.9, ori).SearchByProjectionKeyFrame(*args, None)
+    assert nm == onm and np.array_equal(m, om)

@@ -108,3 +108,29 @@ def test_search_by_bow_known_answers():
     k = a["keys"][:2].copy(); d = np.repeat(a["desc"][:1], 2, 0)
     nm2, m2 = oracle.search_by_bow(k, d, [1, 1], k[:1], d[:1], {0: [0, 1]}, {0: [0]}, 0.7, False)
     assert nm2 == 1 and m2[0] == 0
+
+
+def _reloc_args(seed, th=10.0, dist=100):
+    f = synth.synth_fuse_problem(seed)
+    rng = np.random.default_rng(seed)
+    ang = rng.uniform(0, 360, len(f["pos"])).astype(np.float32)
+    k = f["keys"].copy(); k["angle"] = rng.uniform(0, 360, len(k))
+    valid = 1 - f["skip"]
+    pre = (rng.random(len(k)) < 0.1).astype(np.uint8)
+    return (k, f["desc"], f["bounds"], f["Tcw"], f["Ow"], f["K"], f["scale_factors"], f["log_scale_factor"], valid, f["pos"], f["mp_desc"],
+            f["min_dist"], f["max_dist"], ang, th, dist), pre
+
+
+def test_search_by_projection_keyframe_semantics():
+    """Relocalisation overload (ORBmatcher.cc:1587-1716): matches respect the preassigned slots, the ORBdist gate and the window."""
+    args, pre = _reloc_args(6)
+    nm, m = oracle.search_by_projection_keyframe(*args, False, pre)
+    assert nm == (m >= 0).sum() > 30 and (m[pre > 0] == -2).all()
+    k, desc, mp_desc = args[0], args[1], args[10]
+    i2 = np.nonzero(m >= 0)[0]
+    ham = np.unpackbits(desc[i2] ^ mp_desc[m[i2]], axis=1).sum(1)
+    assert ham.max() <= 100 and len(np.unique(m[i2])) == len(i2)
+    nm64, m64 = oracle.search_by_projection_keyframe(*args[:-1], 64, False, pre)
+    assert nm64 <= nm
+    nmo, mo = oracle.search_by_projection_keyframe(*args, True, pre)
+    assert nmo <= nm and ((mo == m) | (mo == -1)).all()

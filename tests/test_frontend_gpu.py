@@ -162,3 +162,30 @@ def test_frontend_large_batch_properties():
         assert len(m) == out["n_pt_matches"][i] and len(np.unique(m)) == len(m)
         lm = out["line_matches"][i, :out["nl"][prev]]; lm = lm[lm >= 0]
         assert len(lm) == out["n_line_matches"][i] and len(np.unique(lm)) == len(lm)
+
+
+def test_frontend_batch_with_featureless_frame():
+    """A flat frame inside a batch: zero keypoints, the reference's single zero KeyLine, no matches on either side of it; the
+    neighbouring frames are unaffected (frame independence)."""
+    base = synth.synth_sequence(2, 640, 480, seed=12)
+    frames = np.stack([base[0], np.full((480, 640), 93, np.uint8), base[1]])
+    problems = [synth.synth_pose_problem(120 + k) for k in range(3)]
+    fe = pl.Frontend(640, 480, max_batch=3, lm_caps=(320, 88)); fe.set_pose_problems(problems)
+    out = fe.run(frames)
+    o = oracle.OrbOracle(1000, 1.2, 8, 20, 7)
+    assert out["n"][1] == 0 and out["nl"][1] == 1 and not out["keylines"][1, 0].tobytes().strip(b"\0")
+    for b in (0, 2):
+        okps, odesc = o.extract(frames[b])
+        n = out["n"][b]
+        assert n == len(okps) and out["kps"][b, :n].tobytes() == okps.tobytes() and np.array_equal(out["desc"][b, :n], odesc)
+    assert out["n_pt_matches"][1] == 0 and out["n_pt_matches"][2] == 0          # into / out of the empty frame
+    assert out["n_line_matches"][1] == 0 and out["n_line_matches"][2] == 0
+    # frame 0 is matched against frame 2 (the batch's last frame): same as a two-frame run of (frame 2, frame 0)
+    k2, d2 = o.extract(frames[2]); k0, d0 = o.extract(frames[0])
+    pm = np.stack([k2["x"], k2["y"]], 1).astype(np.float32)
+    onm, om, _ = oracle.search_for_initialization(k2, d2, k0, d0, [0, 0, 640, 480], pm, 100, 0.9, True)
+    assert out["n_pt_matches"][0] == onm and np.array_equal(out["pt_matches"][0, :len(k2)], om)
+    for b in range(3):
+        p = problems[b]
+        on, oT, *_ = oracle.pose_optimization(0, p["Tcw0"], p["K"], p["pt_obs"], p["pt_inv_sigma2"], p["pt_Xw"], p["line_func"], p["line_Xw"])
+        assert out["inliers"][0, b] == on

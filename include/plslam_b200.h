@@ -338,6 +338,13 @@ int pl_orb_search_by_bow(const PLKeyPoint* keysKF_un, const uint8_t* descKF, con
                          const PLKeyPoint* keysF, const uint8_t* descF, int nF, const unsigned* fvK_nodes, const int* fvK_start,
                          const int* fvK_items, int nnK, const unsigned* fvF_nodes, const int* fvF_start, const int* fvF_items,
                          int nnF, float nnratio, int check_orientation, int* matchesF);
+/* ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (src/ORBmatcher.cc:574-709; LoopClosing::ComputeSim3): MapPoints required on
+ * both sides (has_mp*), vbMatched2 state, gate bestDist1 < TH_LOW.  matches12[i] = idx2 (vpMatches12[i] = vpMapPoints2[idx2]) or -1. */
+int pl_orb_search_by_bow_keyframes(const PLKeyPoint* keys1_un, const uint8_t* desc1, const uint8_t* has_mp1, int n1,
+                                   const PLKeyPoint* keys2_un, const uint8_t* desc2, const uint8_t* has_mp2, int n2,
+                                   const unsigned* fv1_nodes, const int* fv1_start, const int* fv1_items, int nn1,
+                                   const unsigned* fv2_nodes, const int* fv2_start, const int* fv2_items, int nn2, float nnratio,
+                                   int check_orientation, int* matches12);
 /* LSDmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, isDouble) (src/LSDmatcher.cpp:727-776; LocalMapping.cc:961):
  * FrameBFMatch both ways at th (TH_HIGH = 80 there) with the matcher's nnratio, mutual check when is_double, pairs touching a
  * line that already has a MapLine (has_ml*) removed.  The pair<> overload (:672-725; LocalMapping.cc:679) is th = TH_LOW = 50,

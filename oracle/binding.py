@@ -531,3 +531,17 @@ def search_by_projection_keyframe(kc, dc, bounds, Tcw, Ow, K, scale_factors, log
                                                 _p(ang), C.c_float(th), C.c_int(orb_dist), C.c_int(int(check_orientation)), _p(pre),
                                                 _p(out))
     return nm, out
+
+
+def search_by_bow_keyframes(k1, d1, mp1, k2, d2, mp2, fv1, fv2, nnratio=0.75, check_orientation=True):
+    """ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (ORBmatcher.cc:574-709) -> (nmatches, matches12[n1])."""
+    k1 = np.ascontiguousarray(k1, KP_DTYPE); k2 = np.ascontiguousarray(k2, KP_DTYPE)
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    m1 = np.ascontiguousarray(mp1, np.uint8); m2 = np.ascontiguousarray(mp2, np.uint8)
+    n1a, s1, i1 = _csr(fv1); n2a, s2, i2 = _csr(fv2)
+    out = np.full(len(k1), -1, np.int32)
+    L = lib(); L.oracle_search_by_bow_keyframes.restype = C.c_int
+    nm = L.oracle_search_by_bow_keyframes(_p(k1), _p(d1), _p(m1), C.c_int(len(k1)), _p(k2), _p(d2), _p(m2), C.c_int(len(k2)), _p(n1a),
+                                          _p(s1), _p(i1), C.c_int(len(n1a)), _p(n2a), _p(s2), _p(i2), C.c_int(len(n2a)),
+                                          C.c_float(nnratio), C.c_int(int(check_orientation)), _p(out))
+    return nm, out

@@ -727,4 +727,55 @@ int oracle_search_by_projection_keyframe(const void* keys_cur_, const uint8_t* d
   }
   return nmatches;
 }
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (src/ORBmatcher.cc:574-709).
+int oracle_search_by_bow_keyframes(const void* keys1_, const uint8_t* desc1, const uint8_t* mp1, int n1, const void* keys2_,
+                                   const uint8_t* desc2, const uint8_t* mp2, int n2, const unsigned* fv1_nodes, const int* fv1_start,
+                                   const int* fv1_items, int nn1, const unsigned* fv2_nodes, const int* fv2_start,
+                                   const int* fv2_items, int nn2, float nnratio, int check_orientation, int* matches12) {
+  const KeyPoint* k1 = (const KeyPoint*)keys1_;
+  const KeyPoint* k2 = (const KeyPoint*)keys2_;
+  const int TH_LOW = 50;
+  for (int i = 0; i < n1; i++) matches12[i] = -1;
+  std::vector<char> matched2(n2 > 0 ? n2 : 1, 0);
+  std::vector<int> rotHist[HISTO_LENGTH];
+  int nmatches = 0, a = 0, b = 0;
+  while (a < nn1 && b < nn2) {
+    if (fv1_nodes[a] == fv2_nodes[b]) {
+      for (int i1 = fv1_start[a]; i1 < fv1_start[a + 1]; i1++) {
+        const int idx1 = fv1_items[i1];
+        if (!mp1[idx1]) continue;
+        int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+        for (int i2 = fv2_start[b]; i2 < fv2_start[b + 1]; i2++) {
+          const int idx2 = fv2_items[i2];
+          if (matched2[idx2] || !mp2[idx2]) continue;
+          const int dist = descriptor_distance(desc1 + 32 * idx1, desc2 + 32 * idx2);
+          if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+          else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 < TH_LOW) {
+          if ((float)bestDist1 < nnratio * (float)bestDist2) {
+            matches12[idx1] = bestIdx2; matched2[bestIdx2] = 1;
+            if (check_orientation) rotHist[rot_bin(k1[idx1].angle, k2[bestIdx2].angle)].push_back(idx1);
+            nmatches++;
+          }
+        }
+      }
+      a++; b++;
+    } else if (fv1_nodes[a] < fv2_nodes[b]) {
+      while (a < nn1 && fv1_nodes[a] < fv2_nodes[b]) a++;
+    } else {
+      while (b < nn2 && fv2_nodes[b] < fv1_nodes[a]) b++;
+    }
+  }
+  if (check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx1 : rotHist[i]) { matches12[idx1] = -1; nmatches--; }
+    }
+  }
+  return nmatches;
+}
 }

@@ -751,3 +751,18 @@ def _search_by_projection_keyframe(self, keys_cur_un, desc_cur, bounds, Tcw, Ow,
 
 
 ORBmatcher.SearchByProjectionKeyFrame = _search_by_projection_keyframe
+
+
+def _search_by_bow_keyframes(self, keys1_un, desc1, has_mp1, keys2_un, desc2, has_mp2, fv1, fv2):
+    """ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (reference src/ORBmatcher.cc:574-709) -> (nmatches, matches12[n1])."""
+    k1 = np.ascontiguousarray(keys1_un, KP_DTYPE); k2 = np.ascontiguousarray(keys2_un, KP_DTYPE)
+    d1 = _u8(desc1); d2 = _u8(desc2); m1 = _u8(has_mp1); m2 = _u8(has_mp2)
+    n1a, s1, i1 = _fv_csr(fv1); n2a, s2, i2 = _fv_csr(fv2)
+    out = np.full(len(k1), -1, np.int32)
+    nm = check(lib().pl_orb_search_by_bow_keyframes(_p(k1), _p(d1), _p(m1), C.c_int(len(k1)), _p(k2), _p(d2), _p(m2), C.c_int(len(k2)),
+                                                    _p(n1a), _p(s1), _p(i1), C.c_int(len(n1a)), _p(n2a), _p(s2), _p(i2), C.c_int(len(n2a)),
+                                                    C.c_float(self.mfNNratio), C.c_int(int(self.mbCheckOrientation)), _p(out)))
+    return nm, out
+
+
+ORBmatcher.SearchByBoWKeyFrames = _search_by_bow_keyframes

@@ -854,6 +854,8 @@ struct BowArgs {
   const int *pairK_s, *pairK_e, *pairF_s, *pairF_e, *itK, *itF; int npairs, nF;
   float nnratio; int checkOri;
   int* matchesF; unsigned char* bins; int* nmatches;
+  const uint8_t* mpF = nullptr;    // KeyFrame-KeyFrame overload (:574-709): candidates need a MapPoint too ...
+  int strict = 0;                  // ... and the gate is bestDist1 < TH_LOW instead of <=
 };
 constexpr int kBowWarps = 16;
 __global__ void __launch_bounds__(32 * kBowWarps) k_search_by_bow(BowArgs A) {
@@ -873,6 +875,7 @@ __global__ void __launch_bounds__(32 * kBowWarps) k_search_by_bow(BowArgs A) {
       for (int c = fs + lane; c < fe; c += 32) {
         const int idxF = A.itF[c];
         if (A.matchesF[idxF] >= 0) continue;
+        if (A.mpF && !A.mpF[idxF]) continue;
         const int dist = hamming256(A.dK + 32 * idxK, A.dF + 32 * idxF);
         const unsigned long long k = mk_key(dist, 0, c - fs, idxF);
         if (k < k1) { k2 = k1; k1 = k; } else if (k < k2) k2 = k;
@@ -882,7 +885,7 @@ __global__ void __launch_bounds__(32 * kBowWarps) k_search_by_bow(BowArgs A) {
       if (best == KEY_NONE) continue;
       const int bestDist1 = key_dist(best), bestIdxF = key_idx(best);
       const int bestDist2 = (second == KEY_NONE) ? 256 : key_dist(second);
-      if (bestDist1 <= 50 && (float)bestDist1 < __fmul_rn(A.nnratio, (float)bestDist2)) {
+      if ((A.strict ? bestDist1 < 50 : bestDist1 <= 50) && (float)bestDist1 < __fmul_rn(A.nnratio, (float)bestDist2)) {
         if (lane == 0) {
           A.matchesF[bestIdxF] = idxK;
           atomicAdd(&s_nm, 1);
@@ -1301,11 +1304,11 @@ extern "C" int pl_orb_fuse_search(const PLKeyPoint* keys_un, const uint8_t* desc
   return down(best_dist, A.best_dist, (size_t)n_mp);
 }
 
-extern "C" int pl_orb_search_by_bow(const PLKeyPoint* keysKF_un, const uint8_t* descKF, const uint8_t* has_mp_kf, int nKF,
-                                    const PLKeyPoint* keysF, const uint8_t* descF, int nF, const unsigned* fvK_nodes,
-                                    const int* fvK_start, const int* fvK_items, int nnK, const unsigned* fvF_nodes,
-                                    const int* fvF_start, const int* fvF_items, int nnF, float nnratio, int check_orientation,
-                                    int* matchesF) {
+static int search_by_bow_host(const PLKeyPoint* keysKF_un, const uint8_t* descKF, const uint8_t* has_mp_kf, int nKF,
+                              const PLKeyPoint* keysF, const uint8_t* descF, const uint8_t* has_mp_f, int strict, int nF,
+                              const unsigned* fvK_nodes, const int* fvK_start, const int* fvK_items, int nnK,
+                              const unsigned* fvF_nodes, const int* fvF_start, const int* fvF_items, int nnF, float nnratio,
+                              int check_orientation, int* matchesF) {
   PL_ARG(keysKF_un && descKF && has_mp_kf && keysF && descF && matchesF && nKF >= 0 && nF >= 0 && nnK >= 0 && nnF >= 0);
   PL_ARG((nnK == 0 || (fvK_nodes && fvK_start && fvK_items)) && (nnF == 0 || (fvF_nodes && fvF_start && fvF_items)));
   int rc = require_device(); if (rc) return rc;
@@ -1328,6 +1331,7 @@ extern "C" int pl_orb_search_by_bow(const PLKeyPoint* keysKF_un, const uint8_t* 
   A.pairK_s = s.up(ks.data(), ks.size()); A.pairK_e = s.up(ke.data(), ke.size()); A.pairF_s = s.up(fs.data(), fs.size()); A.pairF_e = s.up(fe.data(), fe.size());
   A.itK = s.up(fvK_items, nitK); A.itF = s.up(fvF_items, nitF); A.npairs = (int)ks.size(); A.nF = nF;
   A.nnratio = nnratio; A.checkOri = check_orientation;
+  A.mpF = has_mp_f ? s.up(has_mp_f, nF) : nullptr; A.strict = strict;
   A.matchesF = s.alloc<int>(nF); A.bins = s.alloc<unsigned char>(nF); A.nmatches = s.alloc<int>(1);
   PL_ARG(A.kK && A.kF && A.dK && A.dF && A.mpK && A.pairK_s && A.pairK_e && A.pairF_s && A.pairF_e && A.itK && A.itF && A.matchesF && A.bins && A.nmatches);
   k_search_by_bow<<<1, 32 * kBowWarps>>>(A);
@@ -1338,6 +1342,30 @@ extern "C" int pl_orb_search_by_bow(const PLKeyPoint* keysKF_un, const uint8_t* 
   return nm;
 }
 
+extern "C" int pl_orb_search_by_bow(const PLKeyPoint* keysKF_un, const uint8_t* descKF, const uint8_t* has_mp_kf, int nKF,
+                                    const PLKeyPoint* keysF, const uint8_t* descF, int nF, const unsigned* fvK_nodes,
+                                    const int* fvK_start, const int* fvK_items, int nnK, const unsigned* fvF_nodes,
+                                    const int* fvF_start, const int* fvF_items, int nnF, float nnratio, int check_orientation,
+                                    int* matchesF) {
+  return search_by_bow_host(keysKF_un, descKF, has_mp_kf, nKF, keysF, descF, nullptr, 0, nF, fvK_nodes, fvK_start, fvK_items, nnK, fvF_nodes,
+                            fvF_start, fvF_items, nnF, nnratio, check_orientation, matchesF);
+}
+// ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (src/ORBmatcher.cc:574-709, loop closing): the same node walk with
+// MapPoints required on both sides, vbMatched2 as the taken-state and a strict < TH_LOW gate; reported per feature of KF1.
+extern "C" int pl_orb_search_by_bow_keyframes(const PLKeyPoint* keys1_un, const uint8_t* desc1, const uint8_t* has_mp1, int n1,
+                                              const PLKeyPoint* keys2_un, const uint8_t* desc2, const uint8_t* has_mp2, int n2,
+                                              const unsigned* fv1_nodes, const int* fv1_start, const int* fv1_items, int nn1,
+                                              const unsigned* fv2_nodes, const int* fv2_start, const int* fv2_items, int nn2,
+                                              float nnratio, int check_orientation, int* matches12) {
+  PL_ARG(matches12 && has_mp2 && n1 >= 0 && n2 >= 0);
+  std::vector<int> m2(std::max(n2, 1), -1);
+  const int nm = search_by_bow_host(keys1_un, desc1, has_mp1, n1, keys2_un, desc2, has_mp2, 1, n2, fv1_nodes, fv1_start, fv1_items, nn1,
+                                    fv2_nodes, fv2_start, fv2_items, nn2, nnratio, check_orientation, m2.data());
+  if (nm < 0) return nm;
+  for (int i = 0; i < n1; i++) matches12[i] = -1;
+  for (int j = 0; j < n2; j++) if (m2[j] >= 0) matches12[m2[j]] = j;
+  return nm;
+}
 extern "C" int pl_orb_search_by_projection_keyframe(const PLKeyPoint* keys_cur, const uint8_t* desc_cur, int n_cur, const float* bounds,
                                                     const float* Tcw, const float* Ow, const float* K, const float* scale_factors,
                                                     int nlevels, float log_scale_factor, int n_kf, const uint8_t* kf_valid,

@@ -101,3 +101,13 @@ def test_search_by_projection_keyframe(seed, th, dist, ori):
     onm, om = oracle.search_by_projection_keyframe(*args, ori, None)
     nm, m = pl.ORBmatcher(0.9, ori).SearchByProjectionKeyFrame(*args, None)
     assert nm == onm and np.array_equal(m, om)
+
+
+@pytest.mark.parametrize("seed,ori,ratio", [(5, True, 0.75), (7, False, 0.75), (11, True, 0.6)])
+def test_search_by_bow_keyframes(seed, ori, ratio):
+    s = synth.synth_two_view(seed)
+    a, b = s["1"], s["2"]
+    args = (a["keys"], a["desc"], 1 - a["has_mp"], b["keys"], b["desc"], 1 - b["has_mp"], a["fv"], b["fv"])
+    onm, om = oracle.search_by_bow_keyframes(*args, ratio, ori)
+    nm, m = pl.ORBmatcher(ratio, ori).SearchByBoWKeyFrames(*args)
+    assert onm > 100 and nm == onm and np.array_equal(m, om)

@@ -134,3 +134,13 @@ def test_search_by_projection_keyframe_semantics():
     assert nm64 <= nm
     nmo, mo = oracle.search_by_projection_keyframe(*args, True, pre)
     assert nmo <= nm and ((mo == m) | (mo == -1)).all()
+
+
+def test_search_by_bow_keyframes_known_answers():
+    s = synth.synth_two_view(5)
+    a, b = s["1"], s["2"]
+    mp1 = 1 - a["has_mp"]; mp2 = 1 - b["has_mp"]                   # most features carry a MapPoint in a loop-closing keyframe
+    nm, m = oracle.search_by_bow_keyframes(a["keys"], a["desc"], mp1, b["keys"], b["desc"], mp2, a["fv"], b["fv"], 0.75, True)
+    ok = m >= 0
+    assert nm == ok.sum() > 150 and (a["pt_id"][ok] == b["pt_id"][m[ok]]).mean() > 0.99
+    assert mp1[ok].all() and mp2[m[ok]].all() and len(np.unique(m[ok])) == ok.sum()         # vbMatched2: idx2 used once

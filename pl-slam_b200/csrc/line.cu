@@ -20,6 +20,7 @@
 //                   reference's order, fp32 without FMA), band statistics, 72-float LBD, 32-byte binarisation
 
 #include "common.cuh"
+#include "lsd_grow_core.cuh"
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
@@ -125,10 +126,11 @@ __global__ void __launch_bounds__(256) k_lsd_scale(LineParams P, const uint8_t* 
 }
 
 // ---------------------------------------------------------------------------------------------- K_B gradient
-// Per scaled pixel, what region growing needs, as separate arrays (the 4-byte angle word is the hot one):
-//   ANG = level-line angle in degrees (cv::fastAtan2(gx, -gy)); -1024 = NOTDEF (border or magnitude <= rho)
-//   CS  = cos/sin of float(angle_rad) rounded to fp32 (what region_grow adds to sumdx/sumdy)
-//   S2  = s = gx^2+gy^2 (modgrad = sqrt(s/4), recomputed in fp64 where the weights are used); seedcs: see grad_record
+// Per scaled pixel, what region growing needs:
+//   REC = 16-byte record {own, angle, cos, sin}: own = ownership word of the speculative growing (lsd_grow_core.cuh; free or
+//         NOTDEF here), angle = level-line angle in degrees (cv::fastAtan2(gx, -gy)), cos/sin of float(angle_rad) rounded
+//         to fp32 (what region_grow adds to sumdx/sumdy) -> ONE 16-byte load per neighbour in the growing step
+//   S2  = s = gx^2+gy^2 (a pixel is defined iff s > s_th; modgrad = sqrt(s/4) comes from a table); seedcs: see grad_record
 constexpr float kNotDefDeg = -1024.f;
 // The level-line record of a pixel depends only on its integer gradient (gx, gy) in [-510, 510]^2: the angle in degrees
 // (cv::fastAtan2(gx, -gy)), cos/sin of that angle as region_grow adds them, and the cos/sin a region SEEDED there starts
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(256) k_lsd_grad_table(GradRec* __restrict__ T,
 template <bool kVec>
 __global__ void __launch_bounds__(256) k_lsd_grad(LineParams P, const uint8_t* __restrict__ scaled, const float4* __restrict__ T,
                                                   const float2* __restrict__ TS,
-                                                  float* __restrict__ ANG, float2* __restrict__ CS, int* __restrict__ S2, float2* __restrict__ seedcs, int* __restrict__ maxs) {
+                                                  int4* __restrict__ REC, int* __restrict__ S2, float2* __restrict__ seedcs, int* __restrict__ maxs) {
   __shared__ int smax;
   if (threadIdx.x == 0) smax = 0;
   __syncthreads();
@@ -184,11 +186,12 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineParams P, const uint8_t* _
         r1[k] = (in && !lastrow) ? S[P.sw + k] : 0;
       }
     }
-    float ang[4], sc[4][2], se[4][2];
+    int4 rec[4];
+    float se[4][2];
     int sq[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      ang[k] = kNotDefDeg; sc[k][0] = sc[k][1] = se[k][0] = se[k][1] = 0.f; sq[k] = 0;
+      rec[k] = make_int4(lg::kNotDef, __float_as_int(kNotDefDeg), 0, 0); se[k][0] = se[k][1] = 0.f; sq[k] = 0;
       if (x0 + k < P.sw - 1 && !lastrow) {
         const int DA = r1[k + 1] - r0[k], BC = r0[k + 1] - r1[k];
         const int gx = DA + BC, gy = DA - BC;
@@ -196,25 +199,23 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineParams P, const uint8_t* _
         sq[k] = s;
         if (s > P.s_th) {
           const int ti = (gx + kGradR) * kGradN + (gy + kGradR);
-          const float4 rec = __ldg(&T[ti]);
+          const float4 t = __ldg(&T[ti]);
           const float2 scs = __ldg(&TS[ti]);
-          ang[k] = rec.x; sc[k][0] = rec.y; sc[k][1] = rec.z; se[k][0] = scs.x; se[k][1] = scs.y;
+          rec[k] = make_int4(lg::kFree, __float_as_int(t.x), __float_as_int(t.y), __float_as_int(t.z));
+          se[k][0] = scs.x; se[k][1] = scs.y;
           smx = max(smx, s);
         }
       }
     }
     const long long o = (long long)f * P.npx + (long long)y * P.sw + x0;
     if (kVec) {
-      *reinterpret_cast<float4*>(ANG + o) = make_float4(ang[0], ang[1], ang[2], ang[3]);
+#pragma unroll
+      for (int k = 0; k < 4; k++) REC[o + k] = rec[k];
       *reinterpret_cast<int4*>(S2 + o) = make_int4(sq[0], sq[1], sq[2], sq[3]);
-      float4* c4 = reinterpret_cast<float4*>(CS + o);
-      c4[0] = make_float4(sc[0][0], sc[0][1], sc[1][0], sc[1][1]); c4[1] = make_float4(sc[2][0], sc[2][1], sc[3][0], sc[3][1]);
       float4* e4 = reinterpret_cast<float4*>(seedcs + o);
       e4[0] = make_float4(se[0][0], se[0][1], se[1][0], se[1][1]); e4[1] = make_float4(se[2][0], se[2][1], se[3][0], se[3][1]);
     } else {
-      for (int k = 0; k < 4 && x0 + k < P.sw; k++) {
-        ANG[o + k] = ang[k]; S2[o + k] = sq[k]; CS[o + k] = make_float2(sc[k][0], sc[k][1]); seedcs[o + k] = make_float2(se[k][0], se[k][1]);
-      }
+      for (int k = 0; k < 4 && x0 + k < P.sw; k++) { REC[o + k] = rec[k]; S2[o + k] = sq[k]; seedcs[o + k] = make_float2(se[k][0], se[k][1]); }
     }
   }
 #pragma unroll
@@ -227,7 +228,7 @@ __device__ __forceinline__ double s_norm(int s) { return sqrt((double)s / 4.0); 
 __device__ __forceinline__ int s_bin(int s, double bin_coef) { return (int)(s_norm(s) * bin_coef); }
 
 // K_C per-chunk histograms of the defined pixels (chunk = kChunkRows image rows)
-__global__ void __launch_bounds__(256) k_lsd_hist(LineParams P, const float* __restrict__ ANG, const int* __restrict__ S2, const int* __restrict__ maxs,
+__global__ void __launch_bounds__(256) k_lsd_hist(LineParams P, const int* __restrict__ S2, const int* __restrict__ maxs,
                                                   unsigned short* __restrict__ counts /*[B][kBins][nchunk]*/) {
   __shared__ int hist[kBins];
   const int chunk = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
@@ -237,11 +238,11 @@ __global__ void __launch_bounds__(256) k_lsd_hist(LineParams P, const float* __r
   const double max_grad = ms > 0 ? sqrt((double)ms / 4.0) : -1.0;
   const double bin_coef = (max_grad > 0) ? (double)(kBins - 1) / max_grad : 0.0;
   const int y0 = chunk * kChunkRows, y1 = min(y0 + kChunkRows, P.sh - 1);
-  const float* G = ANG + (long long)f * P.npx;
   const int* SS = S2 + (long long)f * P.npx;
   for (int i = tid; i < (y1 - y0) * P.sw; i += 256) {
     int y = y0 + i / P.sw, x = i % P.sw;
-    if (G[y * P.sw + x] != kNotDefDeg) atomicAdd(&hist[s_bin(SS[y * P.sw + x], bin_coef)], 1);
+    const int sv = SS[y * P.sw + x];                 // border pixels carry s = 0: never above the threshold
+    if (sv > P.s_th) atomicAdd(&hist[s_bin(sv, bin_coef)], 1);
   }
   __syncthreads();
   for (int i = tid; i < kBins; i += 256) counts[((long long)f * kBins + i) * P.nchunk + chunk] = (unsigned short)hist[i];
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(kBins) k_lsd_scan(LineParams P, const unsigned
 }
 
 // K_E stable scatter: one warp per chunk walks its pixels in row-major order
-__global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const float* __restrict__ ANG, const int* __restrict__ S2, const int* __restrict__ maxs,
+__global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const int* __restrict__ S2, const int* __restrict__ maxs,
                                                      const int* __restrict__ offsets, unsigned* __restrict__ order) {
   __shared__ unsigned short cnt[4][kBins];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -286,7 +287,6 @@ __global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const float* 
   const double max_grad = ms > 0 ? sqrt((double)ms / 4.0) : -1.0;
   const double bin_coef = (max_grad > 0) ? (double)(kBins - 1) / max_grad : 0.0;
   const int y0 = chunk * kChunkRows, y1 = min(y0 + kChunkRows, P.sh - 1);
-  const float* G = ANG + (long long)f * P.npx;
   const int* SS = S2 + (long long)f * P.npx;
   const int* off = offsets + (long long)f * kBins * P.nchunk;
   unsigned* O = order + (long long)f * P.npx;
@@ -297,7 +297,8 @@ __global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const float* 
     if (i < n) {
       int y = y0 + i / P.sw, x = i % P.sw;
       pix = x | (y << 16);                       // packed (x, y): the grow kernel never divides
-      if (G[y * P.sw + x] != kNotDefDeg) bin = s_bin(SS[y * P.sw + x], bin_coef);
+      const int sv = SS[y * P.sw + x];
+      if (sv > P.s_th) bin = s_bin(sv, bin_coef);
     }
     unsigned peers = __match_any_sync(0xffffffffu, bin);
     if (bin >= 0) O[off[bin * P.nchunk + chunk] + cnt[wid][bin] + __popc(peers & lt)] = (unsigned)pix;
@@ -308,410 +309,167 @@ __global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const float* 
 }
 
 // ---------------------------------------------------------------------------------------------- K_F region growing
-struct GrowCtx {
-  int* ANG; const float2* CS; const int* SQ; const float2* S2; unsigned* R; unsigned* ring;
-  int sw, sh, s_th;
-};
-// The USED flag of LSD lives in the SIGN BIT of the pixel's angle word (degrees, >= 0 when defined): one 4-byte load
-// tells a candidate's used state, definedness (NOTDEF = -1024 is negative too) and angle; setting / clearing it is a
-// plain store by whichever lane owns the pixel (no bitmap word shared between lanes, no read-modify-write).
-constexpr int kUsedBit = (int)0x80000000;
-__device__ __forceinline__ bool used_get(const GrowCtx& C, int idx) { return C.ANG[idx] < 0; }     // seeds are always defined
-__device__ __forceinline__ float pixel_angle(const GrowCtx& C, int idx) { return __int_as_float(C.ANG[idx] & ~kUsedBit); }   // of a defined pixel
-__device__ __forceinline__ void used_clear(const GrowCtx& C, int idx) { C.ANG[idx] &= ~kUsedBit; }  // one lane per pixel
-struct RectD { double x1, y1, x2, y2, width; };
+// Ordered speculative execution (lsd_grow_core.cuh has the protocol and everything a lane does).  Here: the warp loop.
+//   frame f is served by `wpf` consecutive warps (one warp per CTA); every LANE runs one region task at a time, so a
+//   warp is 32 regions in flight and the instruction stream is shared by 32 independent serial chains
+//   per iteration (converged):   commit   the warp that holds the frame's commit lock validates the next 32 status
+//                                         words in order (two passes around a fence), appends the segments of the
+//                                         newly final tasks in order, advances the frontier, and hands an invalid
+//                                         head task out for re-execution
+//                                feed     idle lanes: take the re-execution, else scan the next 32 seeds of the
+//                                         order (coalesced), retire the consumed ones, queue the rest for the lanes
+//                                step     every busy lane advances its task by one micro-step (lane_step)
+// Why it is fast where the previous one-warp-per-region kernel was not: a region is a serial chain (one angle update
+// per added pixel), so 32 lanes on ONE region idle; 32 regions on one warp keep all lanes on useful work, and the
+// number of regions in flight (32 x warps) no longer depends on the batch: B = 1 fills the GPU as well as B = 4736.
+constexpr int kGrowQ = 64;
+constexpr int kCommitBatches = 4;
+constexpr unsigned kGrowWatchdog = 40u * 1000u * 1000u;
+__device__ __forceinline__ int first_zero(unsigned m) { return m == 0xffffffffu ? 32 : __ffs(~m) - 1; }
 
-__device__ __forceinline__ double angle_diff_signed(double a, double b) {
-  double diff = a - b;
-  while (diff <= -kPI) diff += 2 * kPI;
-  while (diff > kPI) diff -= 2 * kPI;
-  return diff;
-}
-__device__ __forceinline__ bool is_aligned(double a, double theta, double prec) {
-  // branch-free form of LineSegmentDetectorImpl::isAligned (same values: |theta-a|, folded once at 3pi/2)
-  const double n1 = fabs(theta - a);
-  const double n2 = fabs(n1 - 2 * kPI);
-  return ((n1 > (3 * kPI) / 2) ? n2 : n1) <= prec;
-}
-
-// LineSegmentDetectorImpl::region_grow — exact visiting order; returns the region size, region in C.R[0..n).
-// Four queue entries are expanded per step: lanes 8g..8g+7 fetch the 8 neighbours of entry i+g (used flag, then the
-// 4-byte angle and the cos/sin pair of the unused ones), then the candidates are committed in the reference's order
-// (queue order, then row-major inside the 3x3); a pixel added earlier in the same step invalidates its duplicates in
-// the later neighbourhoods, so the result equals the one-entry-at-a-time loop.
-// The commit loop is the serial spine of the whole front end (one trip per added pixel), so it carries only what the
-// next decision needs: one fp64 subtract + two compares per lane, three shuffles, the atan2.  The USED bits, the region
-// list and the ring are written after the loop by the accepted lanes themselves.
-// kFast: prec < pi/2, isAligned folded to  n <= prec || n >= prec_hi  (prec_hi = smallest double with 2pi-n <= prec;
-// 2pi-n is exact for n in [pi,4pi], so the two forms agree bit for bit).
-#ifndef GROW_ISOLATED
-#define GROW_ISOLATED 0     // batch-parallel retirement of one-pixel regions: bit-exact, measured SLOWER (220 vs 197 ms): the 8 scattered loads per free seed cost more than the 36 % of regions they retire
-#endif
-#ifndef GROW_SPEC
-#define GROW_SPEC 0         // speculative batched commit: bit-exact, but measured SLOWER on B200 (195 vs 168 ms at B=4736)
-#endif
-#ifndef GROW_INLINE
-#define GROW_INLINE 1
-#endif
-#ifndef GROW_CS_EAGER
-#define GROW_CS_EAGER 1
-#endif
-#ifndef GROW_PREFETCH
-#define GROW_PREFETCH 1     // bit 0: at seed-batch load, bit 1: at publication
-#endif
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// the rows a pixel's 3x3 neighbourhood will touch when it is expanded: angle words and cos/sin pairs (x-1 and x+1 ends)
-template <bool kL1>
-__device__ __forceinline__ void prefetch_neighbourhood(const GrowCtx& C, int idx, int npx, bool centre_row) {
-  const int up = max(idx - C.sw, 1), dn = min(idx + C.sw, npx - 2), ce = min(max(idx, 1), npx - 2);
-  if (kL1) {
-    prefetch_l1(&C.ANG[up - 1]); prefetch_l1(&C.ANG[up + 1]); prefetch_l1(&C.ANG[dn - 1]); prefetch_l1(&C.ANG[dn + 1]);
-    prefetch_l1(&C.CS[up - 1]); prefetch_l1(&C.CS[up + 1]); prefetch_l1(&C.CS[dn - 1]); prefetch_l1(&C.CS[dn + 1]);
-    prefetch_l1(&C.CS[ce - 1]); prefetch_l1(&C.CS[ce + 1]);
-    if (centre_row) { prefetch_l1(&C.ANG[ce - 1]); prefetch_l1(&C.ANG[ce + 1]); }
-  } else {
-    prefetch_l2(&C.ANG[up - 1]); prefetch_l2(&C.ANG[up + 1]); prefetch_l2(&C.ANG[dn - 1]); prefetch_l2(&C.ANG[dn + 1]);
-    prefetch_l2(&C.CS[up - 1]); prefetch_l2(&C.CS[up + 1]); prefetch_l2(&C.CS[dn - 1]); prefetch_l2(&C.CS[dn + 1]);
-    prefetch_l2(&C.CS[ce - 1]); prefetch_l2(&C.CS[ce + 1]);
-    if (centre_row) { prefetch_l2(&C.ANG[ce - 1]); prefetch_l2(&C.ANG[ce + 1]); }
-  }
-}
-template <bool kFast>
-__device__ __forceinline__ int region_grow_t(const GrowCtx& C, unsigned seed, double prec, double prec_hi, double& reg_angle_out, int lane) {
-  const int sidx = (int)(seed >> 16) * C.sw + (int)(seed & 0xffffu);
-  const float2 s0 = __ldg(&C.S2[sidx]);
-  const int sbits = C.ANG[sidx];                  // the seed is unused here, so this is its angle
-  double reg_angle = (double)__int_as_float(sbits) * kDegToRads;
-  float sumdx = s0.x, sumdy = s0.y;
-  bool dirty = false;          // reg_angle lags the sums (it is the seed's own angle until the first pixel is added)
-  if (lane == 0) { C.R[0] = seed; C.ring[0] = seed; C.ANG[sidx] = sbits | kUsedBit; }
-  int cnt = 1;
-  __syncwarp();
-  // lane -> (queue entry lane/8, neighbour lane%8); the centre of a 3x3 is always USED, so 8 neighbours suffice
-  const int grp = lane >> 3, kk8 = lane & 7, kk = kk8 + (kk8 >= 4);
-  const int ox = kk % 3 - 1, oy = kk / 3 - 1;
+__device__ __forceinline__ void warp_commit(const lg::Params& GP, const lg::Frame& Fm, float4* __restrict__ segs, int lane) {
+  using namespace lg;
   const unsigned lt = (1u << lane) - 1u;
-  for (int i = 0; i < cnt;) {
-    const int m = min(4, cnt - i);
-    bool valid = false;
-    int idx = -1;
-    unsigned pk = 0xffff0000u | (unsigned)lane;      // unique per lane unless it names a real pixel
-    int ab = -1;
-    float2 csv = make_float2(0.f, 0.f);
-    if (grp < m) {
-      const int qi = i + grp;
-      const unsigned p = (cnt - qi <= kRing) ? C.ring[qi & (kRing - 1)] : C.R[qi];
-      const int xx = (int)(p & 0xffffu) + ox, yy = (int)(p >> 16) + oy;
-      if (xx >= 0 && yy >= 0 && xx < C.sw && yy < C.sh) {
-        idx = yy * C.sw + xx;
-        ab = C.ANG[idx];
-#if GROW_CS_EAGER
-        csv = __ldg(&C.CS[idx]);           // issued together with the angle word: one memory round trip per step
-#endif
-        if (ab >= 0) {                     // defined and not USED
-#if !GROW_CS_EAGER
-          csv = __ldg(&C.CS[idx]);
-#endif
-          valid = true;
-          pk = (unsigned)xx | ((unsigned)yy << 16);
-        }
-      }
+  for (int round = 0; round < kCommitBatches; round++) {
+    const int F = ld_i(&Fm.ctl[C_FIN]);
+    if (F >= Fm.n) return;
+    const int i = F + lane;
+    const unsigned w1 = (i < Fm.n) ? ld_u(&Fm.st[i]) : 0u;
+    const unsigned s1 = w1 & ST_STATE;
+    const int pre1 = first_zero(__ballot_sync(0xffffffffu, s1 == ST_NOOP || s1 == ST_EATEN || s1 == ST_DONE));
+    if (pre1 == 0) return;
+    __threadfence();            // every claim / steal of the tasks seen DONE is visible to the second pass
+    unsigned w2 = 0u;
+    bool ok = false;
+    if (lane < pre1) { w2 = ld_u(&Fm.st[i]); ok = task_valid(GP, Fm, i, w2); }
+    const int pre2 = min(pre1, first_zero(__ballot_sync(0xffffffffu, ok)));
+    float4 sg;
+    const bool has = (lane < pre2) && task_has_segment(Fm, w2, sg);
+    const unsigned ms = __ballot_sync(0xffffffffu, has);
+    const int ns = ld_i(&Fm.ctl[C_NS]);
+    if (has) { const int slot = ns + __popc(ms & lt); if (slot < GP.seg_cap) segs[slot] = sg; }
+    __syncwarp();
+    if (lane == 0) {
+      st_i(&Fm.ctl[C_NS], ns + __popc(ms));
+      __threadfence();
+      a_max(&Fm.ctl[C_FIN], F + pre2);
     }
-    i += m;
-    unsigned live = __ballot_sync(0xffffffffu, valid);
-    if (live == 0u) continue;
-    const double a = (double)__int_as_float(ab) * kDegToRads;
-    // Commit in order.  Every remaining candidate is tested against the CURRENT region angle at once; the first
-    // aligned one (lowest lane = reference order) is added, which changes the angle, and the candidates after it
-    // are tested again.  Candidates skipped before the committed lane were tested with the angle they would
-    // have seen in the sequential loop, so they are never revisited.
-    int mypos = -1;
-    auto aligned_now = [&](double th) {
-      if (kFast) { const double n1 = fabs(th - a); return (n1 <= prec) || (n1 >= prec_hi); }
-      return is_aligned(a, th, prec);
-    };
-    while (live) {
-      if (dirty) { reg_angle = (double)fast_atan2_deg_l(sumdy, sumdx) * kDegToRads; dirty = false; }
-      const unsigned A = __ballot_sync(0xffffffffu, aligned_now(reg_angle)) & live;
-      if (!A) break;
-#if GROW_SPEC
-      if (A & (A - 1u)) {
-        // Several candidates are aligned with the current angle.  Speculate that they are all accepted in order: walk them
-        // once accumulating the cos/sin sums sequentially (the only part that has to be serial for bit-exact fp32 sums),
-        // every lane keeping the sums as they stand just BEFORE its own turn; then each lane evaluates the region angle it
-        // would have seen (one atan2 per lane, in parallel, instead of one per accepted pixel in sequence) and re-checks its
-        // own decision.  Everything before the first lane whose decision differs from the speculation is final.
-        float tx = sumdx, ty = sumdy, sx = sumdx, sy = sumdy;
-        unsigned Aw = A, acc = 0u;
-        int killer = 64;                         // lowest speculated-accepted lane naming my pixel (64 = none)
-        while (Aw) {
-          const int k = __ffs(Aw) - 1;
-          tx = __fadd_rn(tx, __shfl_sync(0xffffffffu, csv.x, k));
-          ty = __fadd_rn(ty, __shfl_sync(0xffffffffu, csv.y, k));
-          if (lane > k) { sx = tx; sy = ty; }
-          acc |= 1u << k;
-          const unsigned d = __ballot_sync(0xffffffffu, pk == __shfl_sync(0xffffffffu, pk, k)) & ~((2u << k) - 1u);
-          if (((d >> lane) & 1u) && killer == 64) killer = k;
-          Aw &= ~(d | (1u << k));
-        }
-        const unsigned dead = __ballot_sync(0xffffffffu, killer != 64);
-        double th = reg_angle;
-        if (acc & lt) th = (double)fast_atan2_deg_l(sy, sx) * kDegToRads;
-        const bool alj = aligned_now(th);
-        const unsigned almask = __ballot_sync(0xffffffffu, alj);
-        const unsigned mism = (almask ^ acc) & live & ~dead;    // acc == speculated decisions of the lanes still in play
-        if (!mism) {
-          if ((acc >> lane) & 1u) mypos = cnt + __popc(acc & lt);
-          cnt += __popc(acc);
-          sumdx = tx; sumdy = ty; dirty = true;
-          live = 0u;
-          break;
-        }
-        const int f = __ffs(mism) - 1;
-        unsigned accf = acc & ((1u << f) - 1u);
-        float bx = __shfl_sync(0xffffffffu, sx, f), by = __shfl_sync(0xffffffffu, sy, f);
-        unsigned deadf = __ballot_sync(0xffffffffu, killer < f);
-        if ((almask >> f) & 1u) {                // f was skipped by the speculation but is aligned at its turn: accept it
-          bx = __fadd_rn(bx, __shfl_sync(0xffffffffu, csv.x, f));
-          by = __fadd_rn(by, __shfl_sync(0xffffffffu, csv.y, f));
-          accf |= 1u << f;
-          deadf |= __ballot_sync(0xffffffffu, pk == __shfl_sync(0xffffffffu, pk, f));
-        }
-        if ((accf >> lane) & 1u) mypos = cnt + __popc(accf & lt);
-        if (accf) { cnt += __popc(accf); sumdx = bx; sumdy = by; dirty = true; }
-        live &= ~(((2u << f) - 1u) | deadf);
-        continue;
+    if (pre2 < pre1) {          // the head is finished but not valid: it is executed again, now with nothing earlier in flight
+      if (lane == pre2) {
+        st_u(&Fm.st[i], (w2 & ~(ST_STATE | ST_ABORT)) | ST_REDO);
+        __threadfence();
+        st_i(&Fm.ctl[C_REDO], i);
       }
-#endif
-      const int k = __ffs(A) - 1;
-      if (lane == k) mypos = cnt;
-      cnt++;
-      sumdx = __fadd_rn(sumdx, __shfl_sync(0xffffffffu, csv.x, k));
-      sumdy = __fadd_rn(sumdy, __shfl_sync(0xffffffffu, csv.y, k));
-      dirty = true;
-      // everything up to k has been decided; the same pixel in a later 3x3 is now USED
-      live &= ~(((2u << k) - 1u) | __ballot_sync(0xffffffffu, pk == __shfl_sync(0xffffffffu, pk, k)));
-    }
-    if (mypos >= 0) {      // publish: every accepted lane owns its pixel
-      C.ANG[idx] = ab | kUsedBit;
-      C.R[mypos] = pk;
-      C.ring[mypos & (kRing - 1)] = pk;
-      if (GROW_PREFETCH & 2) prefetch_neighbourhood<true>(C, idx, C.sw * C.sh, false);   // it will be expanded a few steps from now
+      __syncwarp();
+      return;
     }
     __syncwarp();
+    if (pre2 < 32) return;
   }
-  if (dirty) reg_angle = (double)fast_atan2_deg_l(sumdy, sumdx) * kDegToRads;
-  reg_angle_out = reg_angle;
-  return cnt;
-}
-__device__ __noinline__ int region_grow_hot(const GrowCtx& C, unsigned seed, double prec, double prec_hi, double& reg_angle, int lane) {
-  return region_grow_t<true>(C, seed, prec, prec_hi, reg_angle, lane);
-}
-// refine's regrow with the adaptive tolerance tau (any value): generic isAligned, kept out of line
-__device__ __noinline__ int region_grow_cold(const GrowCtx& C, unsigned seed, double prec, double& reg_angle, int lane) {
-  return region_grow_t<false>(C, seed, prec, 0.0, reg_angle, lane);
 }
 
-// LineSegmentDetectorImpl::region2rect (+get_theta); sums are reduced lane-strided then by butterfly
-__device__ __noinline__ void region2rect(const GrowCtx& C, int n, double reg_angle, double prec, RectD& rec, int lane) {
-  double sx = 0, sy = 0, sw_ = 0;
-  for (int i = lane; i < n; i += 32) {
-    const unsigned p = C.R[i];
-    const int px = (int)(p & 0xffffu), py = (int)(p >> 16);
-    const double w = s_norm(__ldg(&C.SQ[py * C.sw + px]));
-    sx += (double)px * w;
-    sy += (double)py * w;
-    sw_ += w;
-  }
-  sx = warp_sum(sx); sy = warp_sum(sy); sw_ = warp_sum(sw_);
-  const double x = sx / sw_, y = sy / sw_;
-  double Ixx = 0, Iyy = 0, Ixy = 0;
-  for (int i = lane; i < n; i += 32) {
-    const unsigned p = C.R[i];
-    const int px = (int)(p & 0xffffu), py = (int)(p >> 16);
-    const double w = s_norm(__ldg(&C.SQ[py * C.sw + px]));
-    const double dx = (double)px - x, dy = (double)py - y;
-    Ixx += dy * dy * w; Iyy += dx * dx * w; Ixy -= dx * dy * w;
-  }
-  Ixx = warp_sum(Ixx); Iyy = warp_sum(Iyy); Ixy = warp_sum(Ixy);
-  const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
-  double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg_l((float)(lambda - Ixx), (float)Ixy)
-                                         : (double)fast_atan2_deg_l((float)Ixy, (float)(lambda - Iyy));
-  theta *= kDegToRads;
-  if (fabs(angle_diff_signed(theta, reg_angle)) > prec) theta += kPI;
-  const double dx = cos(theta), dy = sin(theta);
-  double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
-  for (int i = lane; i < n; i += 32) {
-    const unsigned p = C.R[i];
-    const double rdx = (double)(int)(p & 0xffffu) - x, rdy = (double)(int)(p >> 16) - y;
-    const double l = rdx * dx + rdy * dy, w = -rdx * dy + rdy * dx;
-    l_max = fmax(l_max, l); l_min = fmin(l_min, l);
-    w_max = fmax(w_max, w); w_min = fmin(w_min, w);
-  }
-  l_max = warp_max_d(l_max); l_min = warp_min_d(l_min); w_max = warp_max_d(w_max); w_min = warp_min_d(w_min);
-  rec.x1 = x + l_min * dx; rec.y1 = y + l_min * dy;
-  rec.x2 = x + l_max * dx; rec.y2 = y + l_max * dy;
-  rec.width = w_max - w_min;
-  if (rec.width < 1.0) rec.width = 1.0;
-}
-__device__ __forceinline__ double dist_d(double x1, double y1, double x2, double y2) {
-  return sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1));
-}
-
-// LineSegmentDetectorImpl::refine + reduce_region_radius; n is updated; returns false if the region is rejected
-__device__ __noinline__ bool refine(const GrowCtx& C, int& n, double reg_angle, double prec, RectD& rec, double density_th, int lane, bool& released) {
-  double density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
-  if (density >= density_th) return true;
-  released = true;              // from here on USED flags are cleared
-  const unsigned p0 = C.R[0];
-  const double xc = (double)(int)(p0 & 0xffffu), yc = (double)(int)(p0 >> 16);
-  const double ang_c = (double)pixel_angle(C, (int)(p0 >> 16) * C.sw + (int)(p0 & 0xffffu)) * kDegToRads;
-  double sum = 0, s_sum = 0;
-  int cnt = 0;
-  for (int i = lane; i < n; i += 32) {
-    const unsigned p = C.R[i];
-    const int pidx = (int)(p >> 16) * C.sw + (int)(p & 0xffffu);
-    used_clear(C, pidx);
-    const double px = (double)(int)(p & 0xffffu), py = (double)(int)(p >> 16);
-    if (dist_d(xc, yc, px, py) < rec.width) {
-      const double ang_d = angle_diff_signed((double)pixel_angle(C, pidx) * kDegToRads, ang_c);
-      sum += ang_d; s_sum += ang_d * ang_d; ++cnt;
-    }
-  }
-  sum = warp_sum(sum); s_sum = warp_sum(s_sum); cnt = warp_sum(cnt);
-  __syncwarp();
-  const double mean_angle = sum / (double)cnt;
-  const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
-  n = region_grow_cold(C, p0, tau, reg_angle, lane);
-  if (n < 2) return false;
-  region2rect(C, n, reg_angle, prec, rec, lane);
-  density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
-  if (density >= density_th) return true;
-  // reduce_region_radius
-  const double r1 = (rec.x1 - xc) * (rec.x1 - xc) + (rec.y1 - yc) * (rec.y1 - yc);
-  const double r2 = (rec.x2 - xc) * (rec.x2 - xc) + (rec.y2 - yc) * (rec.y2 - yc);
-  double radSq = r1 > r2 ? r1 : r2;
-  const unsigned lt = (1u << lane) - 1u;
-  while (density < density_th) {
-    radSq *= 0.75 * 0.75;
-    int kept = 0;
-    for (int i0 = 0; i0 < n; i0 += 32) {   // order-preserving compaction (the reference swap-removes; only sums follow)
-      const int i = i0 + lane;
-      unsigned p = 0;
-      bool keep = false;
-      if (i < n) {
-        p = C.R[i];
-        const double px = (double)(int)(p & 0xffffu), py = (double)(int)(p >> 16);
-        keep = !((px - xc) * (px - xc) + (py - yc) * (py - yc) > radSq);
-        if (!keep) used_clear(C, (int)(p >> 16) * C.sw + (int)(p & 0xffffu));
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, keep);
-      __syncwarp();
-      if (keep) C.R[kept + __popc(m & lt)] = p;
-      kept += __popc(m);
-      __syncwarp();
-    }
-    n = kept;
-    if (n < 2) return false;
-    region2rect(C, n, reg_angle, prec, rec, lane);
-    density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
-  }
-  return true;
-}
-
-#ifndef GROW_WARPS
-#define GROW_WARPS 1        // frames (warps) per CTA; with GROW_MIN_CTAS it sets the register budget / resident warps per SM
-#endif
-#ifndef GROW_MIN_CTAS
-#define GROW_MIN_CTAS 32
-#endif
-__global__ void __launch_bounds__(32 * GROW_WARPS, GROW_MIN_CTAS) k_lsd_grow(LineParams P, int* ANG, const float2* __restrict__ CS, const int* __restrict__ SQ, const float2* __restrict__ seedcs,
-                                                 const unsigned* __restrict__ order, const int* __restrict__ ndef,
-                                                 unsigned* __restrict__ reg, float4* __restrict__ segs,
-                                                 int* __restrict__ nseg, int* __restrict__ overflow, int nframes) {
-  __shared__ unsigned rings[GROW_WARPS][kRing];
-  const int lane = threadIdx.x & 31;
-  unsigned* ring = rings[threadIdx.x >> 5];
-  for (int f = blockIdx.x * GROW_WARPS + (threadIdx.x >> 5); f < nframes; f += gridDim.x * GROW_WARPS) {   // persistent: the grid size caps the resident warps per SM
-  // const object: the cold out-of-line callees take it by reference, the inlined hot loop keeps its fields in registers
-  const GrowCtx C = {ANG + (long long)f * P.npx, CS + (long long)f * P.npx, SQ + (long long)f * P.npx, seedcs + (long long)f * P.npx,
-                     reg + (long long)f * P.npx, ring, P.sw, P.sh, P.s_th};
-  const unsigned* O = order + (long long)f * P.npx;
+template <int kWPC>
+__global__ void __launch_bounds__(32 * kWPC) k_lsd_grow(LineParams P, lg::Params GP, int4* __restrict__ REC, const float2* __restrict__ seedcs,
+                                                        const int* __restrict__ SQ, const unsigned* __restrict__ order, const int* __restrict__ ndef,
+                                                        unsigned* __restrict__ ST, unsigned* __restrict__ POOL, int* __restrict__ CTL,
+                                                        unsigned* __restrict__ LANEBUF, const double* __restrict__ wtab,
+                                                        float4* __restrict__ segs, int* __restrict__ nseg, int* __restrict__ overflow,
+                                                        int nframes, int wpf) {
+  using namespace lg;
+  __shared__ int wq_all[kWPC][kGrowQ];
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * kWPC + wic;
+  const int f = (int)(gw / wpf);
+  if (f >= nframes) return;
+  int* wq = wq_all[wic];
+  Frame Fm;
+  Fm.rec = REC + (long long)f * P.npx; Fm.seedcs = seedcs + (long long)f * P.npx; Fm.sq = SQ + (long long)f * P.npx;
+  Fm.order = order + (long long)f * P.npx; Fm.n = ndef[f];
+  Fm.st = ST + (long long)f * P.npx; Fm.pool = POOL + (long long)f * GP.pool_cap; Fm.ctl = CTL + (long long)f * C_WORDS; Fm.wtab = wtab;
   float4* S = segs + (long long)f * P.seg_cap;
-  const int n = ndef[f];
-  int ns = 0;
-  for (int i0 = 0; i0 < n; i0 += 32) {
-    const int i = i0 + lane;
-    const unsigned pix = (i < n) ? O[i] : 0u;
-    const int pidx = (int)(pix >> 16) * P.sw + (int)(pix & 0xffffu);
-    const int sab = (i < n) ? C.ANG[pidx] : -1;          // angle word of my seed (negative: USED)
-    unsigned todo = __ballot_sync(0xffffffffu, sab >= 0);
-    // A seed none of whose 8 neighbours is free, defined and aligned with the seed's own angle grows a region of exactly
-    // one pixel (the first step of region_grow finds no candidate): below min_reg_size, so its only effect is the seed's
-    // USED bit.  36 % of all regions are like that.  The test is evaluated for the whole batch at once, one seed per
-    // lane; it stays valid until the seed's turn because USED flags only increase — except when refine releases pixels,
-    // after which the remaining lanes are evaluated again.
-    auto isolated = [&](bool active) {
-      bool iso = active;
-      if (active) {
-        const int sx = (int)(pix & 0xffffu), sy = (int)(pix >> 16);
-        const double th = (double)__int_as_float(sab) * kDegToRads;
+  Lane L;
+  L.home = LANEBUF + ((size_t)gw * 32 + lane) * (size_t)GP.lane_cap; L.home_cap = GP.lane_cap;
+  L.phase = P_IDLE; L.task = -1; L.fresh = 1; L.off = 0; L.j = 0; L.m = 0;
+  lane_reset(L);
+  const unsigned lt = (1u << lane) - 1u;
+  int whead = 0, wcount = 0;
+  bool exhausted = false;
+  const bool solo = (wpf == 1);
+  for (unsigned iter = 0;; iter++) {
+    __syncwarp();
+    const int F = ld_i(&Fm.ctl[C_FIN]);
+    if (F >= Fm.n) break;
+    if (iter > kGrowWatchdog) {          // cannot happen (the head task always completes); never hang the GPU on a bug
+      if (lane == 0) { a_or(reinterpret_cast<unsigned*>(&Fm.ctl[C_ERR]), (unsigned)ERR_WATCHDOG); a_max(&Fm.ctl[C_FIN], Fm.n); }
+      break;
+    }
+    // ---- commit
+    {
+      int got = 1;
+      if (!solo) { if (lane == 0) got = (a_cas(&Fm.ctl[C_LOCK], 0, 1) == 0); got = __shfl_sync(0xffffffffu, got, 0); }
+      if (got) {
+        warp_commit(GP, Fm, S, lane);
+        if (!solo && lane == 0) { __threadfence(); st_i(&Fm.ctl[C_LOCK], 0); }
+      }
+    }
+    // ---- feed
+    unsigned mi = __ballot_sync(0xffffffffu, L.phase == P_IDLE);
+    if (mi) {
+      int redo = -1;
+      if (lane == 0) { redo = ld_i(&Fm.ctl[C_REDO]); if (redo >= 0) redo = a_exch(&Fm.ctl[C_REDO], -1); }
+      redo = __shfl_sync(0xffffffffu, redo, 0);
+      if (redo >= 0) {
+        const int k = __ffs(mi) - 1;
+        if (lane == k) lane_take_redo(Fm, L, redo);
+        mi &= mi - 1u;
+      }
+      for (int scans = 0; scans < 2 && __popc(mi) > wcount && !exhausted; scans++) {
+        int base = 0;
+        if (lane == 0) base = a_add(&Fm.ctl[C_NXT], 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= Fm.n) { exhausted = true; break; }
+        const int i = base + lane;
+        bool cand = false;
+        if (i < Fm.n) {
+          const unsigned pix = ldg_u(&Fm.order[i]);
+          const int o = ld_i(&Fm.rec[(int)(pix >> 16) * P.sw + (int)(pix & 0xffffu)].x);
+          if (own_candidate(o, 2 * i, F)) cand = true;
+          else st_u(&Fm.st[i], (!(o & 1) && (o >> 1) < F) ? ST_NOOP : ST_EATEN);
+        }
+        const unsigned mc = __ballot_sync(0xffffffffu, cand);
+        if (cand) wq[(whead + wcount + __popc(mc & lt)) & (kGrowQ - 1)] = i;
+        wcount += __popc(mc);
+        __syncwarp();
+      }
+      const int r = __popc(mi & lt);
+      if (((mi >> lane) & 1u) && r < wcount) lane_take_seed(L, wq[(whead + r) & (kGrowQ - 1)]);
+      const int taken = min(__popc(mi), wcount);
+      whead += taken; wcount -= taken;
+    }
+    // ---- step
+    if (L.phase != P_IDLE) lane_step<false>(GP, Fm, L);
+  }
+  // frame finished (or given up): the first warp of the group reports
+  if (gw % wpf == 0 && lane == 0) {
+    __threadfence();
+    const int ns = ld_i(&Fm.ctl[C_NS]), err = ld_i(&Fm.ctl[C_ERR]);
+    nseg[f] = min(ns, P.seg_cap);
+    if (ns > P.seg_cap) atomicOr(overflow, 1);
+    if (err) atomicOr(overflow, 2);
+  }
+}
+// per-frame control words of the grow kernel (re-armed before every launch)
+__global__ void k_lsd_grow_init(int* __restrict__ CTL, int nframes) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nframes) return;
+  int* c = CTL + (long long)f * lg::C_WORDS;
 #pragma unroll
-        for (int kk = 0; kk < 9; kk++) {
-          if (kk == 4) continue;
-          const int xx = sx + kk % 3 - 1, yy = sy + kk / 3 - 1;
-          if (xx < 0 || yy < 0 || xx >= P.sw || yy >= P.sh) continue;
-          const int ab = C.ANG[yy * P.sw + xx];
-          if (ab < 0) continue;
-          const double n1 = fabs(th - (double)__int_as_float(ab) * kDegToRads);
-          if ((n1 <= P.prec) || (n1 >= P.prec_hi)) iso = false;
-        }
-      }
-      return __ballot_sync(0xffffffffu, iso);
-    };
-    unsigned isomask = GROW_ISOLATED ? isolated((todo >> lane) & 1u) : 0u;
-    if (GROW_PREFETCH & 1) {
-      // this batch's seeds that will really grow: their seed record and 3x3 rows; and the next batch's flag words
-      if (((todo & ~isomask) >> lane) & 1u) { prefetch_l2(&C.S2[pidx]); prefetch_neighbourhood<false>(C, pidx, P.npx, false); }
-      if (i + 32 < n) { const unsigned pn = O[i + 32]; prefetch_l2(&C.ANG[(int)(pn >> 16) * P.sw + (int)(pn & 0xffffu)]); }
-    }
-    while (todo) {
-      const int k = __ffs(todo) - 1;
-      if ((isomask >> k) & 1u) {            // one-pixel region: mark the seed and move on
-        if (lane == k) C.ANG[pidx] = sab | kUsedBit;
-        todo &= todo - 1u;
-        continue;
-      }
-      const unsigned seed = __shfl_sync(0xffffffffu, pix, k);
-      double reg_angle;
-      bool released = false;
-#if GROW_INLINE
-      int cnt = region_grow_t<true>(C, seed, P.prec, P.prec_hi, reg_angle, lane);
-#else
-      int cnt = region_grow_hot(C, seed, P.prec, P.prec_hi, reg_angle, lane);
-#endif
-      if (cnt >= P.min_reg_size) {
-        RectD rec;
-        region2rect(C, cnt, reg_angle, P.prec, rec, lane);
-        if (refine(C, cnt, reg_angle, P.prec, rec, P.density_th, lane, released)) {
-          if (lane == 0 && ns < P.seg_cap)
-            S[ns] = make_float4((float)((rec.x1 + 0.5) / 0.8), (float)((rec.y1 + 0.5) / 0.8), (float)((rec.x2 + 0.5) / 0.8),
-                                (float)((rec.y2 + 0.5) / 0.8));
-          ns++;
-        }
-      }
-      __syncwarp();
-      // seeds later in this batch may have been consumed (or released by refine): re-read their flags
-      const bool free_now = i < n && lane > k && !used_get(C, pidx);
-      todo = __ballot_sync(0xffffffffu, free_now);
-      if (released) isomask = GROW_ISOLATED ? isolated(free_now) : 0u;     // pixels came back: earlier verdicts may be stale
-      else isomask &= todo;
-    }
-  }
-  if (lane == 0) { nseg[f] = min(ns, P.seg_cap); if (ns > P.seg_cap) atomicExch(overflow, 1); }
-  __syncwarp();
-  }
+  for (int k = 0; k < lg::C_WORDS; k++) c[k] = 0;
+  c[lg::C_REDO] = -1; c[lg::C_POOL] = 1;
+}
+__global__ void k_lsd_wtab(double* __restrict__ W, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) W[i] = sqrt((double)i / 4.0);
 }
 
 // ---------------------------------------------------------------------------------------------- K_G keylines
@@ -992,12 +750,17 @@ struct PLLine {
   cudaStream_t stream = nullptr;
   uint8_t* d_scaled = nullptr;
   float2* d_seedcs = nullptr;
-  int grow_grid_cap = 1 << 30;   // max CTAs of the persistent grow kernel (env PLSLAM_LSD_GROW_CTAS_PER_SM x #SMs)
-  float* d_ang = nullptr; float2* d_cs = nullptr; int* d_sq = nullptr;
+  // region growing (lsd_grow_core.cuh): pixel records, status words, list pool, control words, lane buffers, weight table
+  lg::Params GP;
+  int grow_warps_target = 148 * 16;   // warps the grow kernel spreads over the GPU when the batch is small (env PLSLAM_LSD_GROW_WARPS)
+  int grow_wpf_max = 64;              // at most this many warps on one frame (env PLSLAM_LSD_GROW_WPF)
+  size_t lane_warps = 0;              // lane buffers are allocated for this many warps
+  int4* d_rec = nullptr; int* d_sq = nullptr;
+  unsigned *d_st = nullptr, *d_pool = nullptr, *d_lanebuf = nullptr; int* d_ctl = nullptr; double* d_wtab = nullptr;
   GradRec* d_gtab = nullptr; float2* d_gtab_seed = nullptr;   // (gx, gy) -> level-line record, built once (k_lsd_grad_table)
   unsigned short* d_counts = nullptr;
   int *d_offsets = nullptr, *d_ndef = nullptr, *d_maxs = nullptr, *d_nseg = nullptr, *d_overflow = nullptr;
-  unsigned *d_order = nullptr, *d_reg = nullptr;
+  unsigned* d_order = nullptr;
   float4* d_segs = nullptr;
   short2* d_dxy = nullptr;
   // host-pointer API staging
@@ -1015,9 +778,9 @@ static const unsigned char h_comb[64] = {0, 1, 0, 2, 0, 3, 0, 4, 0, 5, 0, 6, 1, 
 
 extern "C" void pl_line_destroy(PLLine* h) {
   if (!h) return;
-  cudaFree(h->d_gtab); cudaFree(h->d_gtab_seed); cudaFree(h->d_scaled); cudaFree(h->d_seedcs); cudaFree(h->d_ang); cudaFree(h->d_cs); cudaFree(h->d_sq); cudaFree(h->d_counts); cudaFree(h->d_offsets);
+  cudaFree(h->d_gtab); cudaFree(h->d_gtab_seed); cudaFree(h->d_scaled); cudaFree(h->d_seedcs); cudaFree(h->d_rec); cudaFree(h->d_sq); cudaFree(h->d_st); cudaFree(h->d_pool); cudaFree(h->d_lanebuf); cudaFree(h->d_ctl); cudaFree(h->d_wtab); cudaFree(h->d_counts); cudaFree(h->d_offsets);
   cudaFree(h->d_ndef); cudaFree(h->d_maxs); cudaFree(h->d_nseg); cudaFree(h->d_overflow); cudaFree(h->d_order);
-  cudaFree(h->d_reg); cudaFree(h->d_segs); cudaFree(h->d_dxy); cudaFree(h->d_img); cudaFree(h->d_kls);
+  cudaFree(h->d_segs); cudaFree(h->d_dxy); cudaFree(h->d_img); cudaFree(h->d_kls);
   cudaFree(h->d_desc); cudaFree(h->d_lf); cudaFree(h->d_nl); cudaFree(h->d_mask);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -1057,11 +820,30 @@ extern "C" int pl_line_create(const PLLineConfig* cfg, PLLine** out) {
 #define LN_TRY(e) do { int _r = (e); if (_r) { pl_line_destroy(h); return _r; } } while (0)
 #define LN_CUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { set_error("%s -> %s", #e, cudaGetErrorString(_e)); pl_line_destroy(h); return PL_ERR_CUDA; } } while (0)
   LN_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  LN_TRY(dev_alloc(&h->d_scaled, npx * B)); LN_TRY(dev_alloc(&h->d_seedcs, npx * B)); LN_TRY(dev_alloc(&h->d_ang, npx * B));
-  LN_TRY(dev_alloc(&h->d_cs, npx * B)); LN_TRY(dev_alloc(&h->d_sq, npx * B));
+  LN_TRY(dev_alloc(&h->d_scaled, npx * B)); LN_TRY(dev_alloc(&h->d_seedcs, npx * B)); LN_TRY(dev_alloc(&h->d_rec, npx * B));
+  LN_TRY(dev_alloc(&h->d_sq, npx * B));
+  {  // speculative region growing: geometry of the run-time structures
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    h->grow_warps_target = sms * 16;
+    if (const char* e = getenv("PLSLAM_LSD_GROW_WARPS")) { const int v = atoi(e); if (v > 0) h->grow_warps_target = v; }
+    if (const char* e = getenv("PLSLAM_LSD_GROW_WPF")) { const int v = atoi(e); if (v > 0) h->grow_wpf_max = v; }
+    lg::Params& G = h->GP;
+    G.sw = P.sw; G.sh = P.sh; G.npx = P.npx; G.min_reg_size = P.min_reg_size; G.seg_cap = P.seg_cap;
+    G.lane_cap = 1024; G.pool_cap = 3 * P.npx;
+    G.prec = P.prec; G.prec_hi = P.prec_hi; G.density_th = P.density_th;
+    h->lane_warps = std::max<size_t>(std::min<size_t>(B * (size_t)h->grow_wpf_max, (size_t)h->grow_warps_target), B);
+    LN_TRY(dev_alloc(&h->d_st, npx * B)); LN_TRY(dev_alloc(&h->d_pool, (size_t)G.pool_cap * B)); LN_TRY(dev_alloc(&h->d_ctl, (size_t)lg::C_WORDS * B));
+    LN_TRY(dev_alloc(&h->d_lanebuf, h->lane_warps * 32 * (size_t)G.lane_cap));
+    const int nw = 2 * kGradR * kGradR + 1;
+    LN_TRY(dev_alloc(&h->d_wtab, (size_t)nw));
+    k_lsd_wtab<<<(nw + 255) / 256, 256, 0, h->stream>>>(h->d_wtab, nw);
+    LN_CUDA(cudaGetLastError());
+    count_launch();
+  }
   LN_TRY(dev_alloc(&h->d_counts, (size_t)kBins * P.nchunk * B)); LN_TRY(dev_alloc(&h->d_offsets, (size_t)kBins * P.nchunk * B));
   LN_TRY(dev_alloc(&h->d_ndef, B)); LN_TRY(dev_alloc(&h->d_maxs, B)); LN_TRY(dev_alloc(&h->d_nseg, B)); LN_TRY(dev_alloc(&h->d_overflow, 1));
-  LN_TRY(dev_alloc(&h->d_order, npx * B)); LN_TRY(dev_alloc(&h->d_reg, npx * B)); LN_TRY(dev_alloc(&h->d_segs, (size_t)P.seg_cap * B));
+  LN_TRY(dev_alloc(&h->d_order, npx * B)); LN_TRY(dev_alloc(&h->d_segs, (size_t)P.seg_cap * B));
   LN_TRY(dev_alloc(&h->d_dxy, (size_t)P.w * P.h * B));
   LN_CUDA(cudaMemset(h->d_overflow, 0, sizeof(int)));
   LN_TRY(dev_alloc(&h->d_gtab, (size_t)kGradN * kGradN)); LN_TRY(dev_alloc(&h->d_gtab_seed, (size_t)kGradN * kGradN));
@@ -1080,9 +862,7 @@ extern "C" int pl_line_create(const PLLineConfig* cfg, PLLine** out) {
     LN_CUDA(cudaMemcpyToSymbol(c_comb, h_comb, sizeof(h_comb)));
   }
   LN_CUDA(cudaFuncSetAttribute(k_keylines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->key_smem));
-  // cfg->lsd_used_in_global is accepted for ABI compatibility and ignored: the USED flag is the sign bit of the angle word
-  { const char* e = getenv("PLSLAM_LSD_GROW_CTAS_PER_SM"); int per = e ? atoi(e) : 0;
-    if (per > 0) { int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); h->grow_grid_cap = per * sms; } }
+  // cfg->lsd_used_in_global is accepted for ABI compatibility and ignored: the USED state is the ownership word of the pixel record
   *out = h;
   return PL_OK;
 }
@@ -1119,19 +899,27 @@ extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int str
   {
     const dim3 grd((P.sw + 255) / 256, (P.sh + 3) / 4, B);
     if (P.sw % 4 == 0)
-      k_lsd_grad<true><<<grd, 256, 0, st>>>(P, h->d_scaled, reinterpret_cast<const float4*>(h->d_gtab), h->d_gtab_seed, h->d_ang, h->d_cs, h->d_sq, h->d_seedcs, h->d_maxs);
+      k_lsd_grad<true><<<grd, 256, 0, st>>>(P, h->d_scaled, reinterpret_cast<const float4*>(h->d_gtab), h->d_gtab_seed, h->d_rec, h->d_sq, h->d_seedcs, h->d_maxs);
     else
-      k_lsd_grad<false><<<grd, 256, 0, st>>>(P, h->d_scaled, reinterpret_cast<const float4*>(h->d_gtab), h->d_gtab_seed, h->d_ang, h->d_cs, h->d_sq, h->d_seedcs, h->d_maxs);
+      k_lsd_grad<false><<<grd, 256, 0, st>>>(P, h->d_scaled, reinterpret_cast<const float4*>(h->d_gtab), h->d_gtab_seed, h->d_rec, h->d_sq, h->d_seedcs, h->d_maxs);
   }
   PL_LAUNCH_CHECK();
-  k_lsd_hist<<<dim3(P.nchunk, B), 256, 0, st>>>(P, h->d_ang, h->d_sq, h->d_maxs, h->d_counts);
+  k_lsd_hist<<<dim3(P.nchunk, B), 256, 0, st>>>(P, h->d_sq, h->d_maxs, h->d_counts);
   PL_LAUNCH_CHECK();
   k_lsd_scan<<<B, kBins, 0, st>>>(P, h->d_counts, h->d_offsets, h->d_ndef);
   PL_LAUNCH_CHECK();
-  k_lsd_scatter<<<dim3((P.nchunk + 3) / 4, B), 128, 0, st>>>(P, h->d_ang, h->d_sq, h->d_maxs, h->d_offsets, h->d_order);
+  k_lsd_scatter<<<dim3((P.nchunk + 3) / 4, B), 128, 0, st>>>(P, h->d_sq, h->d_maxs, h->d_offsets, h->d_order);
+  PL_LAUNCH_CHECK();
+  PL_CUDA(cudaMemsetAsync(h->d_st, 0, sizeof(unsigned) * (size_t)P.npx * B, st));
+  k_lsd_grow_init<<<(B + 127) / 128, 128, 0, st>>>(h->d_ctl, B);
   PL_LAUNCH_CHECK();
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev0, st));
-  k_lsd_grow<<<std::min((B + GROW_WARPS - 1) / GROW_WARPS, h->grow_grid_cap), 32 * GROW_WARPS, 0, st>>>(P, reinterpret_cast<int*>(h->d_ang), h->d_cs, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_reg, h->d_segs, h->d_nseg, h->d_overflow, B);
+  {
+    // warps per frame: one when the batch alone fills the GPU, more (up to grow_wpf_max) when it does not
+    const int wpf = std::max(1, std::min(h->grow_wpf_max, h->grow_warps_target / B));
+    k_lsd_grow<1><<<B * wpf, 32, 0, st>>>(P, h->GP, h->d_rec, h->d_seedcs, h->d_sq, h->d_order, h->d_ndef, h->d_st, h->d_pool, h->d_ctl,
+                                          h->d_lanebuf, h->d_wtab, h->d_segs, h->d_nseg, h->d_overflow, B, wpf);
+  }
   PL_LAUNCH_CHECK();
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev1, st));
   k_keylines<<<B, 256, h->key_smem, st>>>(P, h->d_segs, h->d_nseg, mask, (PLKeyLineRec*)keylines, linefunc, n);

@@ -54,7 +54,7 @@ constexpr unsigned ST_ABORT = 8, ST_HASX = 16;
 constexpr int ST_OFF_SHIFT = 5;
 // per-frame control words
 enum { C_NXT = 0, C_FIN = 1, C_LOCK = 2, C_NS = 3, C_REDO = 4, C_POOL = 5, C_ERR = 6, C_STAT0 = 8, C_WORDS = 16 };
-enum { ERR_POOL = 1, ERR_SEGCAP = 2 };
+enum { ERR_POOL = 1, ERR_SEGCAP = 2, ERR_WATCHDOG = 4 };
 
 struct Params {
   int sw, sh, npx, min_reg_size, seg_cap, lane_cap, pool_cap;
@@ -189,15 +189,24 @@ LG_HD void frame_error(const Frame& Fm, int code) {
   a_or(reinterpret_cast<unsigned*>(&Fm.ctl[C_ERR]), (unsigned)code);
   a_max(&Fm.ctl[C_FIN], Fm.n);         // give the frame up: every warp of the group leaves its loop (C_FIN only grows)
 }
-// the private list is full: continue in a pool block of twice the size
-LG_NOINL bool lane_buffer_grow(const Params& P, const Frame& Fm, Lane& L) {
-  const int ncap = 2 * L.cap;
-  const int off = a_add(&Fm.ctl[C_POOL], ncap);
-  if (off + ncap > P.pool_cap) { frame_error(Fm, ERR_POOL); return false; }
-  unsigned* nb = Fm.pool + off;
+// the private list is full: continue in a pool block of twice the size (scalars only: the Lane stays in registers)
+LG_NOINL unsigned* buffer_grow(int pool_cap, unsigned* pool, int* ctl, int n, unsigned* buf, int cap, int used) {
+  const int ncap = 2 * cap;
+  const int off = a_add(&ctl[C_POOL], ncap);
+  if (off + ncap > pool_cap) {
+    a_or(reinterpret_cast<unsigned*>(&ctl[C_ERR]), (unsigned)ERR_POOL);
+    a_max(&ctl[C_FIN], n);
+    return nullptr;
+  }
+  unsigned* nb = pool + off;
+  for (int k = 0; k < used; k++) nb[k] = buf[k];
+  return nb;
+}
+LG_HD bool lane_buffer_grow(const Params& P, const Frame& Fm, Lane& L) {
   const int used = (L.base + L.cnt > L.hi) ? L.base + L.cnt : L.hi;   // entries appended in the current step are not in hi yet
-  for (int k = 0; k < used; k++) nb[k] = L.buf[k];
-  L.buf = nb; L.cap = ncap;
+  unsigned* nb = buffer_grow(P.pool_cap, Fm.pool, Fm.ctl, Fm.n, L.buf, L.cap, used);
+  if (!nb) return false;
+  L.buf = nb; L.cap = 2 * L.cap;
   return true;
 }
 LG_HD void begin_rollback(Lane& L) { L.phase = P_ROLLBACK; L.j = 0; L.loaded = 0; }

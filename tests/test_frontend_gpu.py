@@ -24,16 +24,15 @@ def test_frontend_batch_matches_oracle():
         n, nl = out["n"][b], out["nl"][b]
         assert n == len(okps) and out["kps"][b, :n].tobytes() == okps.tobytes() and np.array_equal(out["desc"][b, :n], odesc)
         assert nl == len(okl)
-        eq = np.array([out["keylines"][b, i].tobytes() == okl[i].tobytes() for i in range(nl)])
-        assert eq.mean() > 0.99 and np.array_equal(out["ldesc"][b, :nl][eq], oldesc[eq])
-        feats.append((okps, odesc, out["ldesc"][b, :nl].copy(), eq.all()))
+        assert out["keylines"][b, :nl].tobytes() == okl.tobytes() and np.array_equal(out["ldesc"][b, :nl], oldesc)
+        feats.append((okps, odesc, oldesc, True))
     for b in range(B):
         pk, pd, pld, _ = feats[(b - 1) % B]
         ck, cd, cld, _ = feats[b]
         pm = np.stack([pk["x"], pk["y"]], 1).astype(np.float32)
         onm, om, _ = oracle.search_for_initialization(pk, pd, ck, cd, [0, 0, 640, 480], pm, 100, 0.9, True)
         assert out["n_pt_matches"][b] == onm and np.array_equal(out["pt_matches"][b, :len(pk)], om)
-        onl, olm = oracle.search_double(pld, cld, 0.7)     # GPU descriptors on both sides: isolates the matcher
+        onl, olm = oracle.search_double(pld, cld, 0.7)     # the oracle's own descriptors on both sides
         assert out["n_line_matches"][b] == onl and np.array_equal(out["line_matches"][b, :len(pld)], olm)
         p = problems[b]
         on, oT, opo, olo, oits = oracle.pose_optimization(0, p["Tcw0"], p["K"], p["pt_obs"], p["pt_inv_sigma2"], p["pt_Xw"],
@@ -75,8 +74,7 @@ def test_frontend_with_distorting_camera():
         assert ku[b, :n].tobytes() == oku.tobytes()
         okl, oldesc, olf = oracle.line_extract(oracle.undistort_remap(frames[b], K, D))
         assert nl == len(okl)
-        eq = np.array([out["keylines"][b, i].tobytes() == okl[i].tobytes() for i in range(nl)])
-        assert eq.mean() > 0.99 and np.array_equal(out["ldesc"][b, :nl][eq], oldesc[eq])
+        assert out["keylines"][b, :nl].tobytes() == okl.tobytes() and np.array_equal(out["ldesc"][b, :nl], oldesc)
         feats.append((oku, odesc))
     for b in range(B):
         pk, pd = feats[(b - 1) % B]

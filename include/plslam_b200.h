@@ -183,6 +183,8 @@ int pl_line_debug_segments(PLLine* h, int frame, float* out, int cap);
 int pl_line_debug_scaled(PLLine* h, int frame, uint8_t* out, int* sw, int* sh);
 int pl_line_debug_sobel(PLLine* h, int frame, short* dx, short* dy);
 int pl_line_debug_order(PLLine* h, int frame, unsigned* out, int cap);
+/* control words of the speculative region growing for one frame of the LAST call (counters; post-mortem of the watchdog) */
+int pl_line_debug_ctl(PLLine* h, int frame, int* out, int nwords);
 
 /* ------------------------------------------------------------------ per-frame front-end pipeline (batch of frames)
  * The hot-path calls Tracking makes for one frame, chained on one stream with all intermediates in

@@ -33,7 +33,7 @@ constexpr double kPI = 3.14159265358979323846;
 constexpr double kDegToRads = kPI / 180;
 constexpr int kBins = 1024;
 constexpr int kChunkRows = 8;
-constexpr int kRing = 512;
+
 
 struct PLKeyLineRec {  // cv::line_descriptor::KeyLine, 68 bytes
   float angle; int class_id; int octave; float ptx, pty; float response; float size;
@@ -322,9 +322,9 @@ __global__ void __launch_bounds__(128) k_lsd_scatter(LineParams P, const int* __
 // Why it is fast where the previous one-warp-per-region kernel was not: a region is a serial chain (one angle update
 // per added pixel), so 32 lanes on ONE region idle; 32 regions on one warp keep all lanes on useful work, and the
 // number of regions in flight (32 x warps) no longer depends on the batch: B = 1 fills the GPU as well as B = 4736.
-constexpr int kGrowQ = 64;
+constexpr int kGrowQ = 256;
 constexpr int kCommitBatches = 4;
-constexpr unsigned kGrowWatchdog = 40u * 1000u * 1000u;
+constexpr unsigned kGrowWatchdog = 6u * 1000u * 1000u;
 __device__ __forceinline__ int first_zero(unsigned m) { return m == 0xffffffffu ? 32 : __ffs(~m) - 1; }
 
 __device__ __forceinline__ void warp_commit(const lg::Params& GP, const lg::Frame& Fm, float4* __restrict__ segs, int lane) {
@@ -355,8 +355,12 @@ __device__ __forceinline__ void warp_commit(const lg::Params& GP, const lg::Fram
       a_max(&Fm.ctl[C_FIN], F + pre2);
     }
     if (pre2 < pre1) {          // the head is finished but not valid: it is executed again, now with nothing earlier in flight
-      if (lane == pre2) {
-        st_u(&Fm.st[i], (w2 & ~(ST_STATE | ST_ABORT)) | ST_REDO);
+      // (an idle lane may be taking the same task off the redo ring right now: the compare-and-swap decides)
+      // only a task that is still finished (DONE / EATEN) in the second pass: between the passes an idle lane may have taken
+      // it off the redo ring and be running it already
+      const unsigned s2 = w2 & ST_STATE;
+      if (lane == pre2 && (s2 == ST_DONE || s2 == ST_EATEN) &&
+          (unsigned)a_cas(reinterpret_cast<int*>(&Fm.st[i]), (int)w2, (int)((w2 & ~(ST_STATE | ST_ABORT)) | ST_REDO)) == w2) {
         __threadfence();
         st_i(&Fm.ctl[C_REDO], i);
       }
@@ -377,69 +381,154 @@ __global__ void __launch_bounds__(32 * kWPC) k_lsd_grow(LineParams P, lg::Params
                                                         int nframes, int wpf) {
   using namespace lg;
   __shared__ int wq_all[kWPC][kGrowQ];
+  __shared__ unsigned ring_all[kWPC][32 * lg::kRing];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const long long gw = (long long)blockIdx.x * kWPC + wic;
-  const int f = (int)(gw / wpf);
+  const int f = (int)(gw / wpf), wif = (int)(gw % wpf);      // frame, warp inside the frame's group
   if (f >= nframes) return;
   int* wq = wq_all[wic];
   Frame Fm;
   Fm.rec = REC + (long long)f * P.npx; Fm.seedcs = seedcs + (long long)f * P.npx; Fm.sq = SQ + (long long)f * P.npx;
   Fm.order = order + (long long)f * P.npx; Fm.n = ndef[f];
-  Fm.st = ST + (long long)f * P.npx; Fm.pool = POOL + (long long)f * GP.pool_cap; Fm.ctl = CTL + (long long)f * C_WORDS; Fm.wtab = wtab;
+  Fm.st = ST + (long long)f * P.npx; Fm.pool = POOL + (long long)f * GP.pool_cap; Fm.ctl = CTL + (long long)f * kCtlStride; Fm.wtab = wtab;
   float4* S = segs + (long long)f * P.seg_cap;
+  const bool solo = (wpf == 1);
+  if (!solo && wif == 0) {
+    // ---- the COMMITTER of the frame: nothing but the in-order validation, as fast as the status words arrive
+    for (unsigned iter = 0;; iter++) {
+      __syncwarp();
+      const int F = __shfl_sync(0xffffffffu, ld_i(&Fm.ctl[C_FIN]), 0);
+      if (F >= Fm.n) break;
+      if (iter > 4u * kGrowWatchdog) {
+        if (lane == 0) { a_or(reinterpret_cast<unsigned*>(&Fm.ctl[C_ERR]), (unsigned)ERR_WATCHDOG); a_max(&Fm.ctl[C_FIN], Fm.n); }
+        break;
+      }
+      warp_commit(GP, Fm, S, lane);
+      if (__shfl_sync(0xffffffffu, ld_i(&Fm.ctl[C_FIN]), 0) == F) __nanosleep(200);   // the head is still running
+    }
+    if (lane == 0) {
+      __threadfence();
+      const int ns = ld_i(&Fm.ctl[C_NS]), err = ld_i(&Fm.ctl[C_ERR]);
+      nseg[f] = min(ns, P.seg_cap);
+      if (ns > P.seg_cap) atomicOr(overflow, 1);
+      if (err) atomicOr(overflow, 2);
+    }
+    return;
+  }
   Lane L;
   L.home = LANEBUF + ((size_t)gw * 32 + lane) * (size_t)GP.lane_cap; L.home_cap = GP.lane_cap;
+  L.buf = L.home; L.cap = L.home_cap;
+  L.ring = ring_all[wic] + lane * lg::kRing;
   L.phase = P_IDLE; L.task = -1; L.fresh = 1; L.off = 0; L.j = 0; L.m = 0;
   lane_reset(L);
   const unsigned lt = (1u << lane) - 1u;
-  int whead = 0, wcount = 0;
+  int whead = 0, wcount = 0, rsc = 0;
   bool exhausted = false;
-  const bool solo = (wpf == 1);
+  unsigned iter_total = 0; unsigned long long busy_total = 0;
   for (unsigned iter = 0;; iter++) {
     __syncwarp();
-    const int F = ld_i(&Fm.ctl[C_FIN]);
+    iter_total = iter;
+    const int F = __shfl_sync(0xffffffffu, ld_i(&Fm.ctl[C_FIN]), 0);
     if (F >= Fm.n) break;
     if (iter > kGrowWatchdog) {          // cannot happen (the head task always completes); never hang the GPU on a bug
+      // post-mortem for pl_line_debug_ctl(): where the frontier stood, what the head looked like, what this warp held
+      int first = 0;
+      if (lane == 0 && a_cas(&Fm.ctl[C_STAT0 + 7 - 1], 0, F + 1) == 0 && false) {
+        first = 1;
+        Fm.ctl[C_STAT0 + 6] = (int)ld_u(&Fm.st[F]);
+        Fm.ctl[C_WORDS + 0] = 0x7777; Fm.ctl[C_WORDS + 1] = wif; Fm.ctl[C_WORDS + 2] = wcount; Fm.ctl[C_WORDS + 3] = (int)exhausted;
+        Fm.ctl[C_WORDS + 4] = ld_i(&Fm.ctl[C_NXT]); Fm.ctl[C_WORDS + 5] = ld_i(&Fm.ctl[C_REDO]); Fm.ctl[C_WORDS + 6] = ld_i(&Fm.ctl[C_LOCK]);
+        Fm.ctl[C_WORDS + 7] = Fm.n;
+      }
+      first = __shfl_sync(0xffffffffu, first, 0);
+      if (first) { Fm.ctl[C_WORDS + 8 + 2 * lane] = L.phase; Fm.ctl[C_WORDS + 9 + 2 * lane] = L.task; }
+      __syncwarp();
       if (lane == 0) { a_or(reinterpret_cast<unsigned*>(&Fm.ctl[C_ERR]), (unsigned)ERR_WATCHDOG); a_max(&Fm.ctl[C_FIN], Fm.n); }
       break;
     }
-    // ---- commit
-    {
-      int got = 1;
-      if (!solo) { if (lane == 0) got = (a_cas(&Fm.ctl[C_LOCK], 0, 1) == 0); got = __shfl_sync(0xffffffffu, got, 0); }
-      if (got) {
-        warp_commit(GP, Fm, S, lane);
-        if (!solo && lane == 0) { __threadfence(); st_i(&Fm.ctl[C_LOCK], 0); }
-      }
-    }
+    // ---- commit (only when this warp is the whole group)
+    if (solo) warp_commit(GP, Fm, S, lane);
     // ---- feed
     unsigned mi = __ballot_sync(0xffffffffu, L.phase == P_IDLE);
     if (mi) {
-      int redo = -1;
-      if (lane == 0) { redo = ld_i(&Fm.ctl[C_REDO]); if (redo >= 0) redo = a_exch(&Fm.ctl[C_REDO], -1); }
+      // lane 0 looks at the three hand-over words at once: the re-execution slot of the committer and the redo ring
+      int redo = -1, rqh = 0, rqt = 0;
+      if (lane == 0) { redo = ld_i(&Fm.ctl[C_REDO]); rqh = ld_i(&Fm.ctl[C_RQH]); rqt = ld_i(&Fm.ctl[C_RQT]); if (redo >= 0) redo = a_exch(&Fm.ctl[C_REDO], -1); }
       redo = __shfl_sync(0xffffffffu, redo, 0);
       if (redo >= 0) {
         const int k = __ffs(mi) - 1;
         if (lane == k) lane_take_redo(Fm, L, redo);
         mi &= mi - 1u;
       }
-      for (int scans = 0; scans < 2 && __popc(mi) > wcount && !exhausted; scans++) {
-        int base = 0;
-        if (lane == 0) base = a_add(&Fm.ctl[C_NXT], 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= Fm.n) { exhausted = true; break; }
-        const int i = base + lane;
-        bool cand = false;
-        if (i < Fm.n) {
-          const unsigned pix = ldg_u(&Fm.order[i]);
-          const int o = ld_i(&Fm.rec[(int)(pix >> 16) * P.sw + (int)(pix & 0xffffu)].x);
-          if (own_candidate(o, 2 * i, F)) cand = true;
-          else st_u(&Fm.st[i], (!(o & 1) && (o >> 1) < F) ? ST_NOOP : ST_EATEN);
+      // aborted tasks that are already published: re-execute them now rather than when they reach the head
+      int pending = __shfl_sync(0xffffffffu, rqt - rqh, 0);
+      for (int tries = 0; tries < 2 && mi && pending > 0; tries++, pending--) {
+        int m = -1;
+        if (lane == 0) {
+          const int hq = a_add(&Fm.ctl[C_RQH], 1);
+          m = a_exch(&Fm.ctl[C_WORDS + (hq & (kRedoQ - 1))], 0) - 1;
+          if (m >= 0) {
+            const unsigned w = ld_u(&Fm.st[m]);
+            if ((w & ST_STATE) != ST_DONE || !(w & ST_ABORT) ||
+                (unsigned)a_cas(reinterpret_cast<int*>(&Fm.st[m]), (int)w, (int)((w & ~(ST_STATE | ST_ABORT)) | ST_REDO)) != w) m = -1;
+          }
         }
-        const unsigned mc = __ballot_sync(0xffffffffu, cand);
-        if (cand) wq[(whead + wcount + __popc(mc & lt)) & (kGrowQ - 1)] = i;
-        wcount += __popc(mc);
-        __syncwarp();
+        m = __shfl_sync(0xffffffffu, m, 0);
+        if (m >= 0) {
+          const int k = __ffs(mi) - 1;
+          if (lane == k) lane_take_redo(Fm, L, m);
+          mi &= mi - 1u;
+        }
+      }
+      // new seeds: 4 x 32 entries of the order per scan (one atomic, the loads of the four batches overlap)
+      if (__popc(mi) > wcount && !exhausted) {
+        int base = -1;
+        if (lane == 0 && !(GP.window > 0 && ld_i(&Fm.ctl[C_NXT]) - F >= GP.window)) base = a_add(&Fm.ctl[C_NXT], 128);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= Fm.n) exhausted = true;
+        else if (base >= 0) {
+          unsigned pix[4]; int own[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) { const int i = base + 32 * q + lane; pix[q] = (i < Fm.n) ? ldg_u(&Fm.order[i]) : 0u; }
+#pragma unroll
+          for (int q = 0; q < 4; q++) { const int i = base + 32 * q + lane; own[q] = (i < Fm.n) ? ld_i(&Fm.rec[(int)(pix[q] >> 16) * P.sw + (int)(pix[q] & 0xffffu)].x) : 0; }
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int i = base + 32 * q + lane;
+            bool cand = false;
+            if (i < Fm.n) {
+              if (own_candidate(own[q], 2 * i, F)) cand = true;
+              else st_u(&Fm.st[i], (!(own[q] & 1) && (own[q] >> 1) < F) ? ST_NOOP : ST_EATEN);
+            }
+            const unsigned mc = __ballot_sync(0xffffffffu, cand);
+            if (cand) wq[(whead + wcount + __popc(mc & lt)) & (kGrowQ - 1)] = i;
+            wcount += __popc(mc);
+          }
+          __syncwarp();
+        }
+      }
+      // lanes still idle: look again at seeds found consumed by a task that was not final then (it may have let go)
+      if (__popc(mi) > wcount && wcount <= kGrowQ - 32) {
+        const int hi = min(__shfl_sync(0xffffffffu, ld_i(&Fm.ctl[C_NXT]), 0), Fm.n);
+        if (hi > F) {
+          if (rsc < F || rsc >= hi) rsc = F;
+          const int i = rsc + lane;
+          rsc += 32;
+          bool cand = false;
+          if (i < hi) {
+            const unsigned w = ld_u(&Fm.st[i]);
+            if ((w & ST_STATE) == ST_EATEN) {
+              const unsigned pix = ldg_u(&Fm.order[i]);
+              const int o = ld_i(&Fm.rec[(int)(pix >> 16) * P.sw + (int)(pix & 0xffffu)].x);
+              if (own_candidate(o, 2 * i, F)) cand = ((unsigned)a_cas(reinterpret_cast<int*>(&Fm.st[i]), (int)w, (int)ST_RUN) == w);
+              else if (!(o & 1) && (o >> 1) < F) st_u(&Fm.st[i], ST_NOOP);
+            }
+          }
+          const unsigned mc = __ballot_sync(0xffffffffu, cand);
+          if (cand) wq[(whead + wcount + __popc(mc & lt)) & (kGrowQ - 1)] = i;
+          wcount += __popc(mc);
+          __syncwarp();
+        }
       }
       const int r = __popc(mi & lt);
       if (((mi >> lane) & 1u) && r < wcount) lane_take_seed(L, wq[(whead + r) & (kGrowQ - 1)]);
@@ -447,10 +536,12 @@ __global__ void __launch_bounds__(32 * kWPC) k_lsd_grow(LineParams P, lg::Params
       whead += taken; wcount -= taken;
     }
     // ---- step
+    busy_total += __popc(__ballot_sync(0xffffffffu, L.phase != P_IDLE));
     if (L.phase != P_IDLE) lane_step<false>(GP, Fm, L);
   }
-  // frame finished (or given up): the first warp of the group reports
-  if (gw % wpf == 0 && lane == 0) {
+  if (lane == 0) { a_max(&Fm.ctl[C_STAT0 + 5], (int)iter_total); a_add(&Fm.ctl[C_STAT0 + 6], (int)(busy_total >> 5)); }
+  // frame finished (or given up): in a one-warp group the worker reports
+  if (solo && lane == 0) {
     __threadfence();
     const int ns = ld_i(&Fm.ctl[C_NS]), err = ld_i(&Fm.ctl[C_ERR]);
     nseg[f] = min(ns, P.seg_cap);
@@ -462,9 +553,8 @@ __global__ void __launch_bounds__(32 * kWPC) k_lsd_grow(LineParams P, lg::Params
 __global__ void k_lsd_grow_init(int* __restrict__ CTL, int nframes) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= nframes) return;
-  int* c = CTL + (long long)f * lg::C_WORDS;
-#pragma unroll
-  for (int k = 0; k < lg::C_WORDS; k++) c[k] = 0;
+  int* c = CTL + (long long)f * lg::kCtlStride;
+  for (int k = 0; k < lg::kCtlStride; k++) c[k] = 0;
   c[lg::C_REDO] = -1; c[lg::C_POOL] = 1;
 }
 __global__ void k_lsd_wtab(double* __restrict__ W, int n) {
@@ -830,10 +920,11 @@ extern "C" int pl_line_create(const PLLineConfig* cfg, PLLine** out) {
     if (const char* e = getenv("PLSLAM_LSD_GROW_WPF")) { const int v = atoi(e); if (v > 0) h->grow_wpf_max = v; }
     lg::Params& G = h->GP;
     G.sw = P.sw; G.sh = P.sh; G.npx = P.npx; G.min_reg_size = P.min_reg_size; G.seg_cap = P.seg_cap;
-    G.lane_cap = 1024; G.pool_cap = 3 * P.npx;
+    G.lane_cap = 1024; G.pool_cap = 4 * P.npx; G.window = 8192;
+    if (const char* e = getenv("PLSLAM_LSD_GROW_WINDOW")) G.window = atoi(e);
     G.prec = P.prec; G.prec_hi = P.prec_hi; G.density_th = P.density_th;
     h->lane_warps = std::max<size_t>(std::min<size_t>(B * (size_t)h->grow_wpf_max, (size_t)h->grow_warps_target), B);
-    LN_TRY(dev_alloc(&h->d_st, npx * B)); LN_TRY(dev_alloc(&h->d_pool, (size_t)G.pool_cap * B)); LN_TRY(dev_alloc(&h->d_ctl, (size_t)lg::C_WORDS * B));
+    LN_TRY(dev_alloc(&h->d_st, npx * B)); LN_TRY(dev_alloc(&h->d_pool, (size_t)G.pool_cap * B)); LN_TRY(dev_alloc(&h->d_ctl, (size_t)lg::kCtlStride * B));
     LN_TRY(dev_alloc(&h->d_lanebuf, h->lane_warps * 32 * (size_t)G.lane_cap));
     const int nw = 2 * kGradR * kGradR + 1;
     LN_TRY(dev_alloc(&h->d_wtab, (size_t)nw));
@@ -916,7 +1007,7 @@ extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int str
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev0, st));
   {
     // warps per frame: one when the batch alone fills the GPU, more (up to grow_wpf_max) when it does not
-    const int wpf = std::max(1, std::min(h->grow_wpf_max, h->grow_warps_target / B));
+    int wpf = std::max(1, std::min(h->grow_wpf_max, h->grow_warps_target / B));   // (one of them is the frame's committer when wpf > 1)
     k_lsd_grow<1><<<B * wpf, 32, 0, st>>>(P, h->GP, h->d_rec, h->d_seedcs, h->d_sq, h->d_order, h->d_ndef, h->d_st, h->d_pool, h->d_ctl,
                                           h->d_lanebuf, h->d_wtab, h->d_segs, h->d_nseg, h->d_overflow, B, wpf);
   }
@@ -963,7 +1054,12 @@ extern "C" int pl_line_extract_batch(PLLine* h, const uint8_t* imgs, int stride,
   PL_CUDA(cudaStreamSynchronize(h->stream));
   int ov = 0;
   PL_CUDA(cudaMemcpy(&ov, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
-  if (ov) { cudaMemset(h->d_overflow, 0, sizeof(int)); set_error("LSD produced more than segment_cap=%d segments", h->P.seg_cap); return PL_ERR_CAPACITY; }
+  if (ov) {
+    cudaMemset(h->d_overflow, 0, sizeof(int));
+    if (ov & 1) set_error("LSD produced more than segment_cap=%d segments", h->P.seg_cap);
+    else set_error("LSD region growing gave a frame up (list pool of %d words exhausted, or watchdog): see pl_line_debug_ctl", h->GP.pool_cap);
+    return PL_ERR_CAPACITY;
+  }
   return PL_OK;
 }
 
@@ -995,6 +1091,12 @@ extern "C" int pl_line_debug_sobel(PLLine* h, int frame, short* dx, short* dy) {
   std::vector<short2> tmp(n);
   PL_CUDA(cudaMemcpy(tmp.data(), h->d_dxy + frame * n, n * sizeof(short2), cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < n; i++) { dx[i] = tmp[i].x; dy[i] = tmp[i].y; }
+  return PL_OK;
+}
+extern "C" int pl_line_debug_ctl(PLLine* h, int frame, int* out, int nwords) {
+  PL_ARG(h && out && frame >= 0 && frame < h->cfg.max_batch && nwords > 0 && nwords <= lg::kCtlStride);
+  PL_CUDA(cudaStreamSynchronize(h->stream));
+  PL_CUDA(cudaMemcpy(out, h->d_ctl + (size_t)frame * lg::kCtlStride, sizeof(int) * nwords, cudaMemcpyDeviceToHost));
   return PL_OK;
 }
 extern "C" int pl_line_debug_order(PLLine* h, int frame, unsigned* out, int cap) {

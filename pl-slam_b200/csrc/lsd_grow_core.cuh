@@ -47,17 +47,21 @@ constexpr double kPI = 3.14159265358979323846;
 constexpr double kDegToRads = kPI / 180;
 constexpr int kFree = 0x7fffffff;   // own: nobody
 constexpr int kNotDef = -1;         // own: gradient undefined (never available)
+constexpr int kRing = 8;            // per-lane ring of recent list entries (shared memory on the GPU)
 
 // per-seed status word: [2:0] state, [3] ABORT, [4] HASX (dependencies and/or a segment follow the list), [31:5] pool offset
 constexpr unsigned ST_NONE = 0, ST_NOOP = 1, ST_EATEN = 2, ST_RUN = 3, ST_REDO = 5, ST_DONE = 7, ST_STATE = 7;
 constexpr unsigned ST_ABORT = 8, ST_HASX = 16;
 constexpr int ST_OFF_SHIFT = 5;
 // per-frame control words
-enum { C_NXT = 0, C_FIN = 1, C_LOCK = 2, C_NS = 3, C_REDO = 4, C_POOL = 5, C_ERR = 6, C_STAT0 = 8, C_WORDS = 16 };
+enum { C_NXT = 0, C_FIN = 1, C_LOCK = 2, C_NS = 3, C_REDO = 4, C_POOL = 5, C_ERR = 6, C_RQH = 7, C_STAT0 = 8, C_RQT = 15, C_WORDS = 16 };
+constexpr int kRedoQ = 1024;       // lossy ring of aborted-but-published tasks (ctl[C_WORDS ..]); what it loses the committer re-executes at the head
+constexpr int kCtlStride = C_WORDS + kRedoQ;
 enum { ERR_POOL = 1, ERR_SEGCAP = 2, ERR_WATCHDOG = 4 };
 
 struct Params {
   int sw, sh, npx, min_reg_size, seg_cap, lane_cap, pool_cap;
+  int window;                // seeds are handed out at most this far ahead of the frontier (0: no limit)
   double prec, prec_hi, density_th;
 };
 struct Frame {
@@ -82,7 +86,7 @@ struct Lane {
   float sumdx, sumdy;
   double reg_angle, prec;
   int fast, stage, fresh;
-  int ndep, dep0, dep1;            // ndep == 3: more than two dependencies (the task is re-executed when it is the head)
+  int ndep, dep0, dep1;            // dependencies: buf[cap-1-k], k < ndep (dep0/dep1: the last two, to drop immediate repeats)
   int j, m;
   double a0, a1, a2, a3, a4, a5;
   double cx, cy, dx, dy;
@@ -90,6 +94,9 @@ struct Lane {
   double xc, yc, radSq;
   int hasseg;
   unsigned off;                    // FIN2: pool offset; REDOSTART: list being released
+  unsigned* ring;                  // the last kRing pushed entries of the list, in fast memory (the queue is popped from it)
+  unsigned curp;                   // the entry being expanded
+  int pend[8]; int npend;          // claims issued by the previous growing step, settled at the start of the next step
   // snapshot of the neighbourhood (kept in the struct only so that the simulator can split load and use)
   int loaded, F;
   unsigned stw;
@@ -181,16 +188,15 @@ LG_HD bool aligned(const Params& P, const Lane& L, double a) {
   return ((n1 > (3 * kPI) / 2) ? n2 : n1) <= L.prec;
 }
 
-LG_HD void lane_reset(Lane& L) {
-  L.buf = L.home; L.cap = L.home_cap;
-  L.base = 0; L.cnt = 0; L.hi = 0; L.qi = 0; L.stage = 0; L.ndep = 0; L.dep0 = -1; L.dep1 = -1; L.hasseg = 0; L.loaded = 0;
+LG_HD void lane_reset(Lane& L) {      // (a lane keeps the pool block a large region once made it move to: blocks are never freed)
+  L.base = 0; L.cnt = 0; L.hi = 0; L.qi = 0; L.stage = 0; L.ndep = 0; L.dep0 = -1; L.dep1 = -1; L.hasseg = 0; L.loaded = 0; L.npend = 0;
 }
 LG_HD void frame_error(const Frame& Fm, int code) {
   a_or(reinterpret_cast<unsigned*>(&Fm.ctl[C_ERR]), (unsigned)code);
   a_max(&Fm.ctl[C_FIN], Fm.n);         // give the frame up: every warp of the group leaves its loop (C_FIN only grows)
 }
 // the private list is full: continue in a pool block of twice the size (scalars only: the Lane stays in registers)
-LG_NOINL unsigned* buffer_grow(int pool_cap, unsigned* pool, int* ctl, int n, unsigned* buf, int cap, int used) {
+LG_NOINL unsigned* buffer_grow(int pool_cap, unsigned* pool, int* ctl, int n, unsigned* buf, int cap, int used, int ndep) {
   const int ncap = 2 * cap;
   const int off = a_add(&ctl[C_POOL], ncap);
   if (off + ncap > pool_cap) {
@@ -200,11 +206,12 @@ LG_NOINL unsigned* buffer_grow(int pool_cap, unsigned* pool, int* ctl, int n, un
   }
   unsigned* nb = pool + off;
   for (int k = 0; k < used; k++) nb[k] = buf[k];
+  for (int k = 1; k <= ndep; k++) nb[ncap - k] = buf[cap - k];   // the dependency list lives at the far end
   return nb;
 }
 LG_HD bool lane_buffer_grow(const Params& P, const Frame& Fm, Lane& L) {
   const int used = (L.base + L.cnt > L.hi) ? L.base + L.cnt : L.hi;   // entries appended in the current step are not in hi yet
-  unsigned* nb = buffer_grow(P.pool_cap, Fm.pool, Fm.ctl, Fm.n, L.buf, L.cap, used);
+  unsigned* nb = buffer_grow(P.pool_cap, Fm.pool, Fm.ctl, Fm.n, L.buf, L.cap, used, L.ndep);
   if (!nb) return false;
   L.buf = nb; L.cap = 2 * L.cap;
   return true;
@@ -216,15 +223,19 @@ LG_HD void to_fin(Lane& L) {
   L.off = 0;
 }
 LG_HD void to_rect1(Lane& L) { L.phase = P_RECT1; L.j = 0; L.a0 = 0; L.a1 = 0; L.a2 = 0; }
-LG_HD void record_dep(Lane& L, int idx) {
-  if (idx == L.dep0 || idx == L.dep1) return;
-  if (L.ndep == 0) { L.dep0 = idx; L.ndep = 1; }
-  else if (L.ndep == 1) { L.dep1 = idx; L.ndep = 2; }
-  else L.ndep = 3;
+LG_HD bool record_dep(const Params& P, const Frame& Fm, Lane& L, int idx) {
+  if (idx == L.dep0 || idx == L.dep1) return true;
+  const int used = (L.base + L.cnt > L.hi) ? L.base + L.cnt : L.hi;
+  if (used + L.ndep + 1 > L.cap) { if (!lane_buffer_grow(P, Fm, L)) return false; }
+  L.buf[L.cap - 1 - L.ndep] = (unsigned)idx;
+  L.ndep++;
+  L.dep1 = L.dep0; L.dep0 = idx;
+  return true;
 }
 // first pixel of a (re)grown region: the seed, already claimed
 LG_HD void seed_region(const Params& P, const Frame& Fm, Lane& L, unsigned pix, int sidx, int angbits) {
   L.buf[L.base] = pix;
+  L.ring[0] = pix;
   L.cnt = 1; L.qi = 0;
   if (L.base + 1 > L.hi) L.hi = L.base + 1;
   const float2 s0 = ldg_f2(&Fm.seedcs[sidx]);
@@ -240,16 +251,28 @@ LG_HD void seed_region(const Params& P, const Frame& Fm, Lane& L, unsigned pix, 
 //   blocked  : held (even) or dropped (odd) by an earlier task that is not known to be final -> dependency if aligned
 LG_HD bool own_candidate(int o, int me, int F) { return o > me || (o >= 0 && o < me && (o & 1) && (o >> 1) < F); }
 LG_HD bool own_blocked(int o, int me, int F) { return o >= 0 && o < me && (o >> 1) >= F; }
-// claim a candidate seen as o; returns false when somebody earlier was faster (the attempt is void)
-LG_HD bool own_claim(const Frame& Fm, int idx, int o, int me) {
-  if (o > me) {
-    const int old = a_min(&Fm.rec[idx].x, me);
-    if (old < me) return false;
-    if (old != kFree && (old >> 1) != (me >> 1)) a_or(&Fm.st[old >> 1], ST_ABORT);   // taken from a later task: it runs again
-    return true;
+// a later task lost a pixel to an earlier one: it has to run again.  If it is already published, nobody is looking
+// at its status word, so it goes on the (lossy) redo ring that idle lanes serve before they take new seeds.
+LG_HD void abort_task(const Frame& Fm, int m) {
+  const unsigned old = a_or(&Fm.st[m], ST_ABORT);
+  if ((old & ST_STATE) == ST_DONE && !(old & ST_ABORT)) {
+    const int t = a_add(&Fm.ctl[C_RQT], 1);
+    st_i(&Fm.ctl[C_WORDS + (t & (kRedoQ - 1))], m + 1);
   }
-  return a_cas(&Fm.rec[idx].x, o, me) == o;       // dropped by a final task: the word is below me, atomicMin cannot take it
 }
+// claim a candidate seen as o.  Result: kFree = clean; a value below me = somebody earlier was faster (the attempt is
+// void); anything else = the mark of the later task the pixel was taken from (settle_claim aborts it)
+LG_HD int issue_claim(const Frame& Fm, int idx, int o, int me) {
+  if (o > me) return a_min(&Fm.rec[idx].x, me);
+  return (a_cas(&Fm.rec[idx].x, o, me) == o) ? kFree : -2;   // dropped by a final task: the word is below me, atomicMin cannot take it
+}
+LG_HD bool settle_claim(const Frame& Fm, int r, int me) {
+  if (r == kFree) return true;
+  if (r < me) return false;
+  if ((r >> 1) != (me >> 1)) abort_task(Fm, r >> 1);
+  return true;
+}
+LG_HD bool own_claim(const Frame& Fm, int idx, int o, int me) { return settle_claim(Fm, issue_claim(Fm, idx, o, me), me); }
 
 LG_HD void step_start(const Params& P, const Frame& Fm, Lane& L) {
   const int i = L.task, me = 2 * i;
@@ -283,7 +306,8 @@ template <bool SPLIT>
 LG_HD void step_grow(const Params& P, const Frame& Fm, Lane& L) {
   if (!L.loaded) {
     if (L.qi == L.cnt) { grow_done(P, L); return; }
-    const unsigned p = L.buf[L.base + L.qi];
+    const unsigned p = (L.cnt - L.qi <= kRing) ? L.ring[L.qi & (kRing - 1)] : L.buf[L.base + L.qi];
+    L.curp = p;
     const int x = (int)(p & 0xffffu), y = (int)(p >> 16);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -299,13 +323,15 @@ LG_HD void step_grow(const Params& P, const Frame& Fm, Lane& L) {
   }
   L.loaded = 0;
   if (L.stw & ST_ABORT) { begin_rollback(L); return; }
-  const unsigned p = L.buf[L.base + L.qi];
+  const unsigned p = L.curp;
   const int x = (int)(p & 0xffffu), y = (int)(p >> 16);
   L.qi++;
   const int me = 2 * L.task;
-  bool lost = false;
+  // results of the claims: looked at by the NEXT step of this lane (settle_pending), so the atomics are in flight during
+  // the rest of this iteration; a stolen-from task learns it one iteration later, a lost race costs one wasted step
 #pragma unroll
   for (int k = 0; k < 8; k++) {
+    L.pend[k] = kFree;
     const int o = L.nb[k].x;
     const bool cand = own_candidate(o, me, L.F);
     if (cand || own_blocked(o, me, L.F)) {
@@ -313,27 +339,28 @@ LG_HD void step_grow(const Params& P, const Frame& Fm, Lane& L) {
       if (aligned(P, L, a)) {
         const int kk = k + (k >= 4), xx = x + kk % 3 - 1, yy = y + kk / 3 - 1;
         if (cand) {
-          if (L.base + L.cnt >= L.cap) { if (!lane_buffer_grow(P, Fm, L)) { L.phase = P_IDLE; return; } }
-          if (!own_claim(Fm, yy * P.sw + xx, o, me)) lost = true;
+          if (L.base + L.cnt + L.ndep >= L.cap) { if (!lane_buffer_grow(P, Fm, L)) { L.phase = P_IDLE; return; } }
+          L.pend[k] = issue_claim(Fm, yy * P.sw + xx, o, me);
           L.buf[L.base + L.cnt] = (unsigned)xx | ((unsigned)yy << 16);
+          L.ring[L.cnt & (kRing - 1)] = (unsigned)xx | ((unsigned)yy << 16);
           L.cnt++;
           L.sumdx = f_add(L.sumdx, as_float(L.nb[k].z));
           L.sumdy = f_add(L.sumdy, as_float(L.nb[k].w));
           L.reg_angle = (double)fast_atan2_deg(L.sumdy, L.sumdx) * kDegToRads;
         } else {
-          record_dep(L, yy * P.sw + xx);
+          if (!record_dep(P, Fm, L, yy * P.sw + xx)) { L.phase = P_IDLE; return; }
         }
       }
     }
   }
   if (L.base + L.cnt > L.hi) L.hi = L.base + L.cnt;
-  if (lost) begin_rollback(L);          // an earlier task took a pixel between my load and my claim
+  L.npend = 1;
 }
 
 // region2rect, pass 1: weighted centroid (sequential fp64 sums in list order == the oracle's order)
 LG_HD void step_rect1(const Params& P, const Frame& Fm, Lane& L) {
 #pragma unroll 4
-  for (int t = 0; t < 8; t++) {
+  for (int t = 0; t < 32; t++) {
     if (L.j < L.cnt) {
       const unsigned p = L.buf[L.base + L.j];
       const int px = (int)(p & 0xffffu), py = (int)(p >> 16);
@@ -350,7 +377,7 @@ LG_HD void step_rect1(const Params& P, const Frame& Fm, Lane& L) {
 // pass 2: inertia (get_theta)
 LG_HD void step_rect2(const Params& P, const Frame& Fm, Lane& L) {
 #pragma unroll 4
-  for (int t = 0; t < 8; t++) {
+  for (int t = 0; t < 32; t++) {
     if (L.j < L.cnt) {
       const unsigned p = L.buf[L.base + L.j];
       const int px = (int)(p & 0xffffu), py = (int)(p >> 16);
@@ -391,7 +418,7 @@ LG_HD void density_decision(const Params& P, const Frame& Fm, Lane& L) {
 // pass 3: extents along / across theta
 LG_HD void step_rect3(const Params& P, const Frame& Fm, Lane& L) {
 #pragma unroll 4
-  for (int t = 0; t < 8; t++) {
+  for (int t = 0; t < 32; t++) {
     if (L.j < L.cnt) {
       const unsigned p = L.buf[L.base + L.j];
       const double rdx = (double)(int)(p & 0xffffu) - L.cx, rdy = (double)(int)(p >> 16) - L.cy;
@@ -434,7 +461,7 @@ LG_HD void step_refstat(const Params& P, const Frame& Fm, Lane& L) {
     const double tau = 2.0 * sqrt((L.a1 - 2.0 * mean_angle * L.a0) / (double)L.m + mean_angle * mean_angle);
     // grow again from the same seed, behind the old list (the old pixels are still needed for the final release)
     L.base = L.hi;
-    if (L.base >= L.cap) { if (!lane_buffer_grow(P, Fm, L)) { L.phase = P_IDLE; return; } }
+    if (L.base + L.ndep >= L.cap) { if (!lane_buffer_grow(P, Fm, L)) { L.phase = P_IDLE; return; } }
     if (!own_claim(Fm, sidx, me + 1, me)) { begin_rollback(L); return; }   // stolen meanwhile (the ABORT flag is on its way)
     L.prec = tau; L.fast = 0; L.stage = 1;
     seed_region(P, Fm, L, p0, sidx, Fm.rec[sidx].y);
@@ -467,32 +494,39 @@ LG_HD void step_reduce(const Params& P, const Frame& Fm, Lane& L) {
 // end of a task: publish the list (a pending task must be releasable by whoever re-executes it), then DONE
 LG_HD void step_fin2(const Params& P, const Frame& Fm, Lane& L) {
   const bool hasx = L.hasseg || L.ndep > 0;
+  // layout: [cnt | hasseg << 31] [ndep] [cnt pixels] [ndep dependencies] [4 segment words if hasseg]
   if (L.off == 0) {
     if (ld_u(&Fm.st[L.task]) & ST_ABORT) { begin_rollback(L); return; }
-    const int need = 1 + L.cnt + (hasx ? 6 : 0);
+    const int need = 2 + L.cnt + L.ndep + (L.hasseg ? 4 : 0);
     const int off = a_add(&Fm.ctl[C_POOL], need);
     if (off + need > P.pool_cap) { frame_error(Fm, ERR_POOL); L.phase = P_IDLE; return; }
     L.off = (unsigned)off;
-    Fm.pool[off] = (unsigned)L.cnt | ((unsigned)L.ndep << 28) | ((unsigned)L.hasseg << 31);
+    Fm.pool[off] = (unsigned)L.cnt | ((unsigned)L.hasseg << 31);
+    Fm.pool[off + 1] = (unsigned)L.ndep;
   }
-  unsigned* dst = Fm.pool + L.off + 1;
+  unsigned* dst = Fm.pool + L.off + 2;
 #pragma unroll 4
-  for (int t = 0; t < 8; t++) {
+  for (int t = 0; t < 16; t++) {
     if (L.j < L.cnt) { dst[L.j] = L.buf[L.base + L.j]; L.j++; }
   }
   if (L.j == L.cnt) {
-    if (hasx) {
-      unsigned* x = dst + L.cnt;
-      x[0] = (unsigned)L.dep0; x[1] = (unsigned)L.dep1;
-      float s[4] = {(float)((L.x1 + 0.5) / 0.8), (float)((L.y1 + 0.5) / 0.8), (float)((L.x2 + 0.5) / 0.8), (float)((L.y2 + 0.5) / 0.8)};
+    unsigned* x = dst + L.cnt;
+    for (int k = 0; k < L.ndep; k++) x[k] = L.buf[L.cap - 1 - k];
+    if (L.hasseg) {
+      x += L.ndep;
+      float sg[4] = {(float)((L.x1 + 0.5) / 0.8), (float)((L.y1 + 0.5) / 0.8), (float)((L.x2 + 0.5) / 0.8), (float)((L.y2 + 0.5) / 0.8)};
 #ifdef __CUDACC__
-      x[2] = __float_as_uint(s[0]); x[3] = __float_as_uint(s[1]); x[4] = __float_as_uint(s[2]); x[5] = __float_as_uint(s[3]);
+      x[0] = __float_as_uint(sg[0]); x[1] = __float_as_uint(sg[1]); x[2] = __float_as_uint(sg[2]); x[3] = __float_as_uint(sg[3]);
 #else
-      memcpy(&x[2], s, 16);
+      memcpy(x, sg, 16);
 #endif
     }
     fence();
-    a_or(&Fm.st[L.task], (L.off << ST_OFF_SHIFT) | (hasx ? ST_HASX : 0u) | 4u);   // RUN (3) -> DONE (7)
+    const unsigned old = a_or(&Fm.st[L.task], (L.off << ST_OFF_SHIFT) | (hasx ? ST_HASX : 0u) | 4u);   // RUN (3) -> DONE (7)
+    if (old & ST_ABORT) {               // aborted while publishing: nobody else will notice, queue it like a stealer would
+      const int t = a_add(&Fm.ctl[C_RQT], 1);
+      st_i(&Fm.ctl[C_WORDS + (t & (kRedoQ - 1))], L.task + 1);
+    }
     L.phase = P_IDLE;
   }
 }
@@ -518,7 +552,7 @@ LG_HD void step_rollback(const Params& P, const Frame& Fm, Lane& L) {
 LG_HD void step_redostart(const Params& P, const Frame& Fm, Lane& L) {
   const int me = 2 * L.task;
   if (L.off != 0) {
-    const unsigned* src = Fm.pool + L.off + 1;
+    const unsigned* src = Fm.pool + L.off + 2;
 #pragma unroll 2
     for (int t = 0; t < 8; t++) {
       if (L.j < L.m) {
@@ -545,8 +579,17 @@ LG_HD void lane_take_redo(const Frame& Fm, Lane& L, int i) {
 }
 LG_HD void lane_take_seed(Lane& L, int i) { L.task = i; L.fresh = 1; L.phase = P_START; }
 
+LG_HD void settle_pending(const Frame& Fm, Lane& L) {
+  const int me = 2 * L.task;
+  bool lost = false;
+#pragma unroll
+  for (int k = 0; k < 8; k++) if (!settle_claim(Fm, L.pend[k], me)) lost = true;
+  L.npend = 0;
+  if (lost && L.phase != P_ROLLBACK) begin_rollback(L);   // an earlier task took a pixel between my load and my claim
+}
 template <bool SPLIT>
 LG_HD void lane_step(const Params& P, const Frame& Fm, Lane& L) {
+  if (L.npend) { settle_pending(Fm, L); if (L.phase == P_ROLLBACK) return; }
   if (L.phase == P_GROW) { step_grow<SPLIT>(P, Fm, L); return; }
   switch (L.phase) {
     case P_START: step_start(P, Fm, L); break;
@@ -578,12 +621,10 @@ LG_HD bool task_valid(const Params& P, const Frame& Fm, int i, unsigned w) {
   if (s != ST_DONE || (w & ST_ABORT)) return false;
   if (!(w & ST_HASX)) return true;
   const unsigned off = w >> ST_OFF_SHIFT;
-  const unsigned h = ld_u(&Fm.pool[off]);
-  const int ndep = (int)((h >> 28) & 7u), cnt = (int)(h & 0x0fffffffu);
-  if (ndep == 3) return false;
-  const unsigned* x = Fm.pool + off + 1 + cnt;
-  if (ndep >= 1 && !own_used_by_earlier(ld_i(&Fm.rec[(int)ld_u(&x[0])].x), me)) return false;
-  if (ndep >= 2 && !own_used_by_earlier(ld_i(&Fm.rec[(int)ld_u(&x[1])].x), me)) return false;
+  const int cnt = (int)(ld_u(&Fm.pool[off]) & 0x0fffffffu), ndep = (int)ld_u(&Fm.pool[off + 1]);
+  const unsigned* x = Fm.pool + off + 2 + cnt;
+  for (int k = 0; k < ndep; k++)
+    if (!own_used_by_earlier(ld_i(&Fm.rec[(int)ld_u(&x[k])].x), me)) return false;
   return true;
 }
 LG_HD bool task_has_segment(const Frame& Fm, unsigned w, float4& seg) {
@@ -591,8 +632,8 @@ LG_HD bool task_has_segment(const Frame& Fm, unsigned w, float4& seg) {
   const unsigned off = w >> ST_OFF_SHIFT;
   const unsigned h = ld_u(&Fm.pool[off]);
   if (!(h >> 31)) return false;
-  const unsigned* x = Fm.pool + off + 1 + (h & 0x0fffffffu);
-  seg.x = as_float((int)ld_u(&x[2])); seg.y = as_float((int)ld_u(&x[3])); seg.z = as_float((int)ld_u(&x[4])); seg.w = as_float((int)ld_u(&x[5]));
+  const unsigned* x = Fm.pool + off + 2 + (h & 0x0fffffffu) + ld_u(&Fm.pool[off + 1]);
+  seg.x = as_float((int)ld_u(&x[0])); seg.y = as_float((int)ld_u(&x[1])); seg.z = as_float((int)ld_u(&x[2])); seg.w = as_float((int)ld_u(&x[3]));
   return true;
 }
 

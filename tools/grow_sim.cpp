@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <random>
 #include <vector>
 #include "../pl-slam_b200/csrc/lsd_grow_core.cuh"
@@ -23,7 +24,7 @@ namespace {
 
 struct Warp {
   Lane lanes[32];
-  int wq[64]; int whead = 0, wcount = 0;
+  int wq[64]; int whead = 0, wcount = 0, rsc = 0;
   bool exhausted = false;
 };
 
@@ -32,11 +33,13 @@ struct Sim {
   Frame Fm;
   std::vector<int4> rec; std::vector<float2> seedcs; std::vector<int> sq; std::vector<unsigned> order, st, pool;
   std::vector<double> wtab;
-  int ctl[C_WORDS];
+  int ctl[kCtlStride];
   std::vector<float4> segs;
   std::vector<std::vector<unsigned>> lanebuf;
+  std::vector<unsigned> rings;
   std::vector<Warp> warps;
-  long commits = 0, redos = 0, steps = 0;
+  bool poll = true; long trace = 0; int boost = 0;
+  long commits = 0, redos = 0, steps = 0, iters = 0, busy_hist[33] = {0}, eager = 0, polled = 0, winblock = 0, phase_hist[16] = {0}, redo_abort = 0, redo_dep = 0, redo_eaten = 0;
 
   void build(const uint8_t* scaled, int sw, int sh) {
     const double ANG_TH = 22.5, QUANT = 2.0;
@@ -84,8 +87,8 @@ struct Sim {
     for (size_t i = 0; i < ord.size(); i++) order[i] = ord[i].pix;
   }
 
-  void setup(int nwarps, int lane_cap, int pool_mult) {
-    P.seg_cap = 1 << 20; P.lane_cap = lane_cap; P.pool_cap = pool_mult * P.npx;
+  void setup(int nwarps, int lane_cap, int pool_mult, int window) {
+    P.window = window; P.seg_cap = 1 << 20; P.lane_cap = lane_cap; P.pool_cap = pool_mult * P.npx;
     st.assign(order.size() + 64, 0);
     pool.assign(P.pool_cap, 0);
     memset(ctl, 0, sizeof(ctl));
@@ -94,12 +97,14 @@ struct Sim {
     Fm.st = st.data(); Fm.pool = pool.data(); Fm.ctl = ctl; Fm.wtab = wtab.data();
     warps.assign(nwarps, Warp());
     lanebuf.assign((size_t)nwarps * 32, std::vector<unsigned>(lane_cap));
+    rings.assign((size_t)nwarps * 32 * kRing, 0);
     for (int w = 0; w < nwarps; w++)
       for (int l = 0; l < 32; l++) {
         Lane& L = warps[w].lanes[l];
         memset(&L, 0, sizeof(L));
         L.home = lanebuf[(size_t)w * 32 + l].data(); L.home_cap = lane_cap;
-        L.phase = P_IDLE;
+        L.ring = rings.data() + ((size_t)w * 32 + l) * kRing;
+        L.phase = P_IDLE; L.buf = L.home; L.cap = L.home_cap;
         lane_reset(L);
       }
   }
@@ -137,10 +142,15 @@ struct Sim {
     a_max(&ctl[C_FIN], F + pre2);
     if (pre2 < pre1) {                                    // the head is DONE but invalid: have it executed again
       const int h = F + pre2;
-      st_u(&st[h], (w2[pre2] & ~(ST_STATE | ST_ABORT)) | ST_REDO);
-      fence();
-      st_i(&ctl[C_REDO], h);
-      redos++;
+      // (an idle lane may be taking the same task off the redo ring right now: the compare-and-swap decides)
+      const unsigned s2 = w2[pre2] & ST_STATE;
+      if ((s2 == ST_DONE || s2 == ST_EATEN) &&
+          (unsigned)a_cas(reinterpret_cast<int*>(&st[h]), (int)w2[pre2], (int)((w2[pre2] & ~(ST_STATE | ST_ABORT)) | ST_REDO)) == w2[pre2]) {
+        if ((w2[pre2] & ST_STATE) == ST_EATEN) redo_eaten++; else if (w2[pre2] & ST_ABORT) redo_abort++; else redo_dep++;
+        fence();
+        st_i(&ctl[C_REDO], h);
+        redos++;
+      }
     }
   }
 
@@ -156,8 +166,21 @@ struct Sim {
         for (int l = 0; l < 32; l++)
           if (W.lanes[l].phase == P_IDLE) { lane_take_redo(Fm, W.lanes[l], redo); idle--; break; }
     }
+    // aborted tasks that are already published: re-execute them now rather than when they reach the head
+    for (int tries = 0; tries < 2 && idle > 0; tries++) {
+      if (ld_i(&ctl[C_RQH]) >= ld_i(&ctl[C_RQT])) break;
+      const int hq = a_add(&ctl[C_RQH], 1);
+      const int m = a_exch(&ctl[C_WORDS + (hq & (kRedoQ - 1))], 0) - 1;
+      if (m < 0) continue;
+      const unsigned w = ld_u(&st[m]);
+      if ((w & ST_STATE) != ST_DONE || !(w & ST_ABORT)) continue;
+      if ((unsigned)a_cas(reinterpret_cast<int*>(&st[m]), (int)w, (int)((w & ~(ST_STATE | ST_ABORT)) | ST_REDO)) != w) continue;
+      for (int l = 0; l < 32; l++)
+        if (W.lanes[l].phase == P_IDLE) { lane_take_redo(Fm, W.lanes[l], m); idle--; eager++; break; }
+    }
     int scans = 0;
     while (idle > W.wcount && !W.exhausted && W.wcount <= 32 && scans < 2) {
+      if (P.window > 0 && ld_i(&ctl[C_NXT]) - ld_i(&ctl[C_FIN]) >= P.window) { winblock++; break; }
       scans++;
       const int base = a_add(&ctl[C_NXT], 32);
       if (base >= Fm.n) { W.exhausted = true; break; }
@@ -169,6 +192,26 @@ struct Sim {
         const int o = ld_i(&rec[(int)(pix >> 16) * P.sw + (int)(pix & 0xffffu)].x);
         if (!own_candidate(o, 2 * i, F)) st_u(&st[i], (!(o & 1) && (o >> 1) < F) ? ST_NOOP : ST_EATEN);
         else { W.wq[(W.whead + W.wcount) & 63] = i; W.wcount++; }
+      }
+    }
+    // lanes still idle: look again at seeds that were found consumed by a task that was not final (it may have let go)
+    if (idle > W.wcount && W.wcount <= 32 && poll) {
+      const int F = ld_i(&ctl[C_FIN]), hi = std::min(ld_i(&ctl[C_NXT]), Fm.n);
+      if (hi > F) {
+        if (W.rsc < F || W.rsc >= hi) W.rsc = F;
+        const int base = W.rsc;
+        W.rsc += 32;
+        for (int l = 0; l < 32; l++) {
+          const int i = base + l;
+          if (i >= hi) break;
+          const unsigned w = ld_u(&st[i]);
+          if ((w & ST_STATE) != ST_EATEN) continue;
+          const unsigned pix = order[i];
+          const int o = ld_i(&rec[(int)(pix >> 16) * P.sw + (int)(pix & 0xffffu)].x);
+          if (own_candidate(o, 2 * i, F)) {
+            if ((unsigned)a_cas(reinterpret_cast<int*>(&st[i]), (int)w, (int)ST_RUN) == w) { W.wq[(W.whead + W.wcount) & 63] = i; W.wcount++; polled++; }
+          } else if (!(o & 1) && (o >> 1) < F) st_u(&st[i], ST_NOOP);
+        }
       }
     }
     for (int l = 0; l < 32 && W.wcount > 0; l++)
@@ -190,9 +233,17 @@ struct Sim {
         if (ctl[C_LOCK] == 0) commit();
       }
       feed(W);
+      iters++;
+      if (trace && iters % (trace * nw) == 0) { int b = 0, g = 0; for (auto& X : warps) for (int l = 0; l < 32; l++) { b += X.lanes[l].phase > P_IDLE; g += X.lanes[l].phase == P_GROW; } int hp = -1, hc = 0, hs = 0; for (auto& X : warps) for (int l = 0; l < 32; l++) if (X.lanes[l].phase > P_IDLE && X.lanes[l].task == ctl[C_FIN]) { hp = X.lanes[l].phase; hc = X.lanes[l].cnt; hs = X.lanes[l].stage; } fprintf(stderr, "t=%ld F=%d NXT=%d busy=%d grow=%d headst=%x head: phase=%d cnt=%d stage=%d\n", iters / nw, ctl[C_FIN], ctl[C_NXT], b, g, st[ctl[C_FIN]], hp, hc, hs); }
+      { int b = 0; for (int l = 0; l < 32; l++) { b += (W.lanes[l].phase > P_IDLE); if (W.lanes[l].phase >= 0) phase_hist[W.lanes[l].phase]++; } busy_hist[b]++; }
       int perm[32];
       for (int l = 0; l < 32; l++) perm[l] = l;
       if (mode != 0) std::shuffle(perm, perm + 32, rng);
+      if (boost > 0) {                                      // emulation of the cooperative step: the deepest queue gets extra expansions
+        int bl = -1, bq = 7;
+        for (int l = 0; l < 32; l++) { Lane& L = W.lanes[l]; if (L.phase == P_GROW && L.cnt - L.qi > bq) { bq = L.cnt - L.qi; bl = l; } }
+        if (bl >= 0) for (int r = 0; r < boost && W.lanes[bl].phase == P_GROW; r++) lane_step<false>(P, Fm, W.lanes[bl]);
+      }
       for (int k = 0; k < 32; k++) {
         Lane& L = W.lanes[perm[k]];
         if (L.phase == P_IDLE) continue;
@@ -211,13 +262,18 @@ struct Sim {
 // scaled: the 0.8x image LSD works on (oracle_lsd_stages).  Returns the number of segments (or < 0), segments in out.
 // stats[0..5]: tasks committed, head re-executions, lane micro-steps, self aborts, pool words used, seeds
 extern "C" int grow_sim(const uint8_t* scaled, int sw, int sh, int nwarps, unsigned seed, int mode, int lane_cap, float* out, int cap,
-                        long* stats) {
+                        long* stats, int window) {
   Sim S;
   S.build(scaled, sw, sh);
-  S.setup(nwarps, lane_cap > 0 ? lane_cap : 2048, 4);
+  S.setup(nwarps, lane_cap > 0 ? lane_cap : 2048, 4, window);
+  S.poll = !getenv("GROWSIM_NOPOLL");
+  if (getenv("GROWSIM_BOOST")) S.boost = atoi(getenv("GROWSIM_BOOST"));
+  if (getenv("GROWSIM_TRACE")) S.trace = atol(getenv("GROWSIM_TRACE"));
   const int rc = S.run(seed, mode);
   if (stats) {
-    stats[0] = S.commits; stats[1] = S.redos; stats[2] = S.steps; stats[3] = S.ctl[C_STAT0]; stats[4] = S.ctl[C_POOL]; stats[5] = S.Fm.n;
+    stats[0] = S.commits; stats[1] = S.redos; stats[2] = S.steps; stats[3] = S.ctl[C_STAT0]; stats[4] = S.ctl[C_POOL]; stats[5] = S.Fm.n; stats[6] = S.iters; stats[7] = S.redo_abort; stats[8] = S.redo_dep; stats[9] = S.redo_eaten;
+    long bs = 0; for (int b = 0; b <= 32; b++) bs += b * S.busy_hist[b]; stats[10] = bs; stats[11] = S.ctl[C_STAT0 + 2]; stats[12] = S.ctl[C_STAT0 + 3]; stats[13] = S.ctl[C_STAT0 + 4]; stats[14] = S.eager; stats[15] = S.winblock; stats[12] = S.polled;
+    if (getenv("GROWSIM_VERBOSE")) { fprintf(stderr, "busy:"); for (int b = 0; b <= 32; b++) fprintf(stderr, " %ld", S.busy_hist[b]); fprintf(stderr, "\nphase:"); for (int b = 0; b < 12; b++) fprintf(stderr, " %ld", S.phase_hist[b]); fprintf(stderr, "\n"); }
   }
   if (rc) return rc;
   const int n = S.ctl[C_NS];

@@ -298,7 +298,8 @@ int pl_undistort_keypoints_dev(PLUndistort* h, const PLKeyPoint* kps, const int*
 /* Frame::ComputeImageBounds -> {mnMinX, mnMinY, mnMaxX, mnMaxY} */
 int pl_frame_image_bounds(const float* K, const float* dist5, int width, int height, float* bounds);
 /* Frame::isInFrustum(MapPoint*, viewingCosLimit) for n map points: pos = GetWorldPos, normal = GetNormal,
- * min/max_dist = Get{Min,Max}DistanceInvariance; Tcw row-major 4x4, Ow = mOw.  Outputs mbTrackInView, {mTrackProjX,Y},
+ * min/max_dist = the RAW MapPoint::mfMinDistance / mfMaxDistance (the 0.8f / 1.2f factors of Get{Min,Max}DistanceInvariance are
+ * applied inside for the range test; PredictScale uses the raw mfMaxDistance, MapPoint.cc:396-428, MapLine.cpp:395-404); Tcw row-major 4x4, Ow = mOw.  Outputs mbTrackInView, {mTrackProjX,Y},
  * mnTrackScaleLevel, mTrackViewCos. */
 int pl_frame_is_in_frustum_points(const float* Tcw, const float* Ow, const float* K, const float* bounds, float log_scale_factor,
                                   int n_scale_levels, float viewing_cos_limit, int n, const float* pos, const float* normal,
@@ -324,7 +325,7 @@ int pl_orb_search_for_triangulation(const PLKeyPoint* keys1_un, const uint8_t* d
                                     int check_orientation, int* matches12);
 /* ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1587-1716;
  * Tracking::Relocalization Tracking.cc:2194,2208).  kf_valid[i] = pMP && !isBad() && !sAlreadyFound.count(pMP) for the keyframe's
- * map-point matches; pos / mp_desc / min,max_dist = GetWorldPos, GetDescriptor, Get{Min,Max}DistanceInvariance; kf_angle =
+ * map-point matches; pos / mp_desc / min,max_dist = GetWorldPos, GetDescriptor, raw mfMinDistance / mfMaxDistance (see pl_frame_is_in_frustum); kf_angle =
  * pKF->mvKeysUn[i].angle; Ow = camera centre of the current pose; cur_preassigned[i2] = mvpMapPoints[i2] != NULL.
  * cur_match[i2] = keyframe index i, -1, or -2 (was preassigned); returns nmatches. */
 int pl_orb_search_by_projection_keyframe(const PLKeyPoint* keys_cur, const uint8_t* desc_cur, int n_cur, const float* bounds,

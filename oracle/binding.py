@@ -26,7 +26,8 @@ def lib():
     global _lib
     if _lib is None:
         build()
-        _lib = C.CDLL(_LIB)
+        # bench.py's CPU legs time the -march=native build of the same sources (oracle/Makefile target `native`)
+        _lib = C.CDLL(os.environ.get("PLSLAM_ORACLE_LIB") or _LIB)
         _lib.oracle_orb_create.restype = C.c_void_p
         _lib.oracle_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
         _lib.oracle_orb_destroy.argtypes = [C.c_void_p]

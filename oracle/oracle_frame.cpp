@@ -128,7 +128,7 @@ void oracle_is_in_frustum_points(const float* Tcw, const float* Ow, const float*
     if (v < bounds[1] || v > bounds[3]) continue;
     const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
     const float dist = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
-    if (dist < minDist[i] || dist > maxDist[i]) continue;
+    if (dist < 0.8f * minDist[i] || dist > 1.2f * maxDist[i]) continue;   // MapPoint::Get{Min,Max}DistanceInvariance (MapPoint.cc:384-394)
     const float* Pn = normal + 3 * i;
     const float viewCos = (float)(((double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2]) / dist);
     if (viewCos < viewingCosLimit) continue;
@@ -159,7 +159,7 @@ void oracle_is_in_frustum_lines(const float* Tcw, const float* Ow, const float* 
     float OM[3];   // 0.5*(SP+EP) - mOw as a cv::MatExpr: addWeighted-style fp32 evaluation
     for (int k = 0; k < 3; k++) OM[k] = (float)(0.5 * (double)(SP[k] + EP[k])) - Ow[k];
     const float dist = (float)std::sqrt((double)OM[0] * OM[0] + (double)OM[1] * OM[1] + (double)OM[2] * OM[2]);
-    if (dist < minDist[i] || dist > maxDist[i]) continue;
+    if (dist < 0.8f * minDist[i] || dist > 1.2f * maxDist[i]) continue;   // MapLine.cpp:383-393
     const float pn[3] = {(float)normal[3 * i], (float)normal[3 * i + 1], (float)normal[3 * i + 2]};
     const float viewCos = (float)(((double)OM[0] * pn[0] + (double)OM[1] * pn[1] + (double)OM[2] * pn[2]) / dist);
     if (viewCos < viewingCosLimit) continue;

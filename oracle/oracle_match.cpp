@@ -574,7 +574,7 @@ void oracle_fuse_search(const void* keys_, const uint8_t* desc, int n, const flo
     if (!(u >= bounds[0] && u < bounds[2] && v >= bounds[1] && v < bounds[3])) continue;       // KeyFrame::IsInImage
     const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
     const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
-    if (dist3D < minDist[i] || dist3D > maxDist[i]) continue;
+    if (dist3D < 0.8f * minDist[i] || dist3D > 1.2f * maxDist[i]) continue;   // Get{Min,Max}DistanceInvariance
     const float* Pn = normal + 3 * i;
     const double dot = (double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2];
     if (dot < 0.5 * dist3D) continue;
@@ -699,8 +699,8 @@ int oracle_search_by_projection_keyframe(const void* keys_cur_, const uint8_t* d
     if (v < g.minY || v > g.maxY) continue;
     const float PO[3] = {X[0] - Ow[0], X[1] - Ow[1], X[2] - Ow[2]};
     const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
-    if (dist3D < minDist[i] || dist3D > maxDist[i]) continue;
-    const float ratio = maxDist[i] / dist3D;
+    if (dist3D < 0.8f * minDist[i] || dist3D > 1.2f * maxDist[i]) continue;   // Get{Min,Max}DistanceInvariance
+    const float ratio = maxDist[i] / dist3D;                                   // PredictScale: raw mfMaxDistance (MapPoint.cc:396-411)
     int lvl = (int)std::ceil(std::log((double)ratio) / (double)logScaleFactor);
     if (lvl < 0) lvl = 0; else if (lvl >= nlevels) lvl = nlevels - 1;
     const float radius = th * scaleFactors[lvl];

@@ -86,7 +86,7 @@ __global__ void k_frustum_points(FrustumArgs A, const float* __restrict__ pos, c
   if (!project(A, Pc, u, v)) return;
   const float PO[3] = {__fsub_rn(P[0], A.Ow[0]), __fsub_rn(P[1], A.Ow[1]), __fsub_rn(P[2], A.Ow[2])};
   const float dist = (float)sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
-  if (dist < minDist[i] || dist > maxDist[i]) return;
+  if (dist < __fmul_rn(0.8f, minDist[i]) || dist > __fmul_rn(1.2f, maxDist[i])) return;   // Get{Min,Max}DistanceInvariance (MapPoint.cc:384-394)
   const float viewCos = (float)(((double)PO[0] * normal[3 * i] + (double)PO[1] * normal[3 * i + 1] + (double)PO[2] * normal[3 * i + 2]) / dist);
   if (viewCos < A.viewingCosLimit) return;
   const float ratio = __fdiv_rn(maxDist[i], dist);
@@ -110,7 +110,7 @@ __global__ void k_frustum_lines(FrustumArgs A, const double* __restrict__ pos, c
   float OM[3];
   for (int k = 0; k < 3; k++) OM[k] = __fsub_rn((float)(0.5 * (double)__fadd_rn(SP[k], EP[k])), A.Ow[k]);
   const float dist = (float)sqrt((double)OM[0] * OM[0] + (double)OM[1] * OM[1] + (double)OM[2] * OM[2]);
-  if (dist < minDist[i] || dist > maxDist[i]) return;
+  if (dist < __fmul_rn(0.8f, minDist[i]) || dist > __fmul_rn(1.2f, maxDist[i])) return;   // MapLine.cpp:383-393
   const float pn[3] = {(float)normal[3 * i], (float)normal[3 * i + 1], (float)normal[3 * i + 2]};
   const float viewCos = (float)(((double)OM[0] * pn[0] + (double)OM[1] * pn[1] + (double)OM[2] * pn[2]) / dist);
   if (viewCos < A.viewingCosLimit) return;

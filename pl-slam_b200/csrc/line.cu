@@ -562,6 +562,10 @@ __global__ void k_lsd_wtab(double* __restrict__ W, int n) {
   if (i < n) W[i] = sqrt((double)i / 4.0);
 }
 
+}  // namespace pl
+#include "lsd_grow_ordered.cuh"
+namespace pl {
+
 // ---------------------------------------------------------------------------------------------- K_G keylines
 __global__ void __launch_bounds__(256) k_keylines(LineParams P, const float4* __restrict__ segs, const int* __restrict__ nseg,
                                                   const uint8_t* __restrict__ mask, PLKeyLineRec* __restrict__ kls,
@@ -844,6 +848,7 @@ struct PLLine {
   lg::Params GP;
   int grow_warps_target = 148 * 16;   // warps the grow kernel spreads over the GPU when the batch is small (env PLSLAM_LSD_GROW_WARPS)
   int grow_wpf_max = 64;              // at most this many warps on one frame (env PLSLAM_LSD_GROW_WPF)
+  int grow_spec_max_batch = 4;        // batches up to this size use the speculative kernel, larger ones the ordered one (env PLSLAM_LSD_GROW_SPEC_MAXB)
   size_t lane_warps = 0;              // lane buffers are allocated for this many warps
   int4* d_rec = nullptr; int* d_sq = nullptr;
   unsigned *d_st = nullptr, *d_pool = nullptr, *d_lanebuf = nullptr; int* d_ctl = nullptr; double* d_wtab = nullptr;
@@ -918,6 +923,7 @@ extern "C" int pl_line_create(const PLLineConfig* cfg, PLLine** out) {
     h->grow_warps_target = sms * 16;
     if (const char* e = getenv("PLSLAM_LSD_GROW_WARPS")) { const int v = atoi(e); if (v > 0) h->grow_warps_target = v; }
     if (const char* e = getenv("PLSLAM_LSD_GROW_WPF")) { const int v = atoi(e); if (v > 0) h->grow_wpf_max = v; }
+    if (const char* e = getenv("PLSLAM_LSD_GROW_SPEC_MAXB")) h->grow_spec_max_batch = atoi(e);
     lg::Params& G = h->GP;
     G.sw = P.sw; G.sh = P.sh; G.npx = P.npx; G.min_reg_size = P.min_reg_size; G.seg_cap = P.seg_cap;
     G.lane_cap = 1024; G.pool_cap = 4 * P.npx; G.window = 8192;
@@ -1001,17 +1007,25 @@ extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int str
   PL_LAUNCH_CHECK();
   k_lsd_scatter<<<dim3((P.nchunk + 3) / 4, B), 128, 0, st>>>(P, h->d_sq, h->d_maxs, h->d_offsets, h->d_order);
   PL_LAUNCH_CHECK();
-  PL_CUDA(cudaMemsetAsync(h->d_st, 0, sizeof(unsigned) * (size_t)P.npx * B, st));
-  k_lsd_grow_init<<<(B + 127) / 128, 128, 0, st>>>(h->d_ctl, B);
-  PL_LAUNCH_CHECK();
-  if (h->timing) PL_CUDA(cudaEventRecord(h->ev0, st));
-  {
-    // warps per frame: one when the batch alone fills the GPU, more (up to grow_wpf_max) when it does not
-    int wpf = std::max(1, std::min(h->grow_wpf_max, h->grow_warps_target / B));   // (one of them is the frame's committer when wpf > 1)
+  if (B <= h->grow_spec_max_batch) {
+    // few frames: many regions of each frame in flight (ordered speculative execution, lsd_grow_core.cuh)
+    PL_CUDA(cudaMemsetAsync(h->d_st, 0, sizeof(unsigned) * (size_t)P.npx * B, st));
+    k_lsd_grow_init<<<(B + 127) / 128, 128, 0, st>>>(h->d_ctl, B);
+    PL_LAUNCH_CHECK();
+    if (h->timing) PL_CUDA(cudaEventRecord(h->ev0, st));
+    // warps per frame (one of them is the frame's committer when there is more than one)
+    const int wpf = std::max(1, std::min(h->grow_wpf_max, h->grow_warps_target / B));
     k_lsd_grow<1><<<B * wpf, 32, 0, st>>>(P, h->GP, h->d_rec, h->d_seedcs, h->d_sq, h->d_order, h->d_ndef, h->d_st, h->d_pool, h->d_ctl,
                                           h->d_lanebuf, h->d_wtab, h->d_segs, h->d_nseg, h->d_overflow, B, wpf);
+    PL_LAUNCH_CHECK();
+  } else {
+    // many frames: one warp per frame, the 32 lanes on one region at a time (lsd_grow_ordered.cuh); the list pool and the
+    // status words of the speculative kernel serve as region list and far-pixel mask
+    if (h->timing) PL_CUDA(cudaEventRecord(h->ev0, st));
+    k_lsd_grow_ordered<<<B, 32, 0, st>>>(P, h->d_rec, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_pool, h->GP.pool_cap, h->d_st, h->d_wtab,
+                                         h->d_segs, h->d_nseg, h->d_overflow, B);
+    PL_LAUNCH_CHECK();
   }
-  PL_LAUNCH_CHECK();
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev1, st));
   k_keylines<<<B, 256, h->key_smem, st>>>(P, h->d_segs, h->d_nseg, mask, (PLKeyLineRec*)keylines, linefunc, n);
   PL_LAUNCH_CHECK();

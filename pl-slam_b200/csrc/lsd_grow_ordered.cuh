@@ -1,0 +1,330 @@
+// LSD region growing, ORDERED variant: one warp walks one frame's seeds in order, the 32 lanes cooperate on ONE region.
+// This is the throughput form for batches that fill the GPU with frames (B >= ~resident warps): no speculation, no
+// atomics, no status words.  For small batches k_lsd_grow (speculative, lsd_grow_core.cuh) puts many regions of one
+// frame in flight instead.  Both produce the oracle's segment list bit for bit.
+//
+// Same pixel records as the speculative kernel ({own, angle, cos, sin}, 16 bytes); here the ownership word only says
+// free (lg::kFree) / undefined (lg::kNotDef) / used (0), and is written with plain stores by the lane that owns the pixel.
+//
+// Exactness of the fp64 parts (what round 1 did not have): LineSegmentDetectorImpl::region2rect / get_theta / refine sum over
+// the region IN LIST ORDER on the CPU.  The lanes load and form the per-pixel terms in parallel (32 pixels per batch), then
+// the three running sums are advanced in list order with warp shuffles - every lane carries the same sums, the order of
+// the additions is the oracle's, so the rectangle is bit-identical.  reduce_region_radius() swap-removes; the order of the
+// survivors decides the order of the next sums, so it is reproduced exactly: all far flags in parallel (bit mask), then a
+// two-pointer walk over the mask that moves one survivor from the tail into every hole, as the CPU loop does.
+#pragma once
+#include "lsd_grow_core.cuh"
+
+namespace pl {
+namespace ord {
+
+using lg::kDegToRads;
+using lg::kPI;
+constexpr int kORing = 512;
+constexpr int kUsedO = 0;
+
+struct Ctx {
+  int4* REC; const int* SQ; const float2* S2; const double* wtab; unsigned* R; unsigned* ring; unsigned* mask;
+  int sw, sh;
+};
+struct RectD { double x1, y1, x2, y2, width; };
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ int& own_of(const Ctx& C, int idx) { return reinterpret_cast<int*>(&C.REC[idx])[0]; }
+__device__ __forceinline__ int angle_bits(const Ctx& C, int idx) { return reinterpret_cast<const int*>(&C.REC[idx])[1]; }
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double wmax_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double wmin_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ bool is_aligned_generic(double a, double theta, double prec) {
+  const double n1 = fabs(theta - a);
+  const double n2 = fabs(n1 - 2 * kPI);
+  return ((n1 > (3 * kPI) / 2) ? n2 : n1) <= prec;
+}
+
+// LineSegmentDetectorImpl::region_grow - exact visiting order; returns the region size, region in C.R[0..n).
+// Four queue entries are expanded per step: lanes 8g..8g+7 fetch the 8 neighbours of entry i+g (one 16-byte record each),
+// then the candidates are committed in the reference's order (queue order, then row-major inside the 3x3): every
+// remaining candidate is tested against the CURRENT region angle at once, the first aligned one is added, which changes
+// the angle; a pixel added earlier in the same step invalidates its duplicates in the later neighbourhoods.
+// kFast: prec < pi/2, isAligned folded to  n <= prec || n >= prec_hi  (see lsd_grow_core.cuh aligned()).
+template <bool kFast>
+__device__ __forceinline__ int region_grow(const Ctx& C, unsigned seed, double prec, double prec_hi, double& reg_angle_out, int lane) {
+  const int sidx = (int)(seed >> 16) * C.sw + (int)(seed & 0xffffu);
+  const float2 s0 = __ldg(&C.S2[sidx]);
+  double reg_angle = (double)__int_as_float(angle_bits(C, sidx)) * kDegToRads;
+  float sumdx = s0.x, sumdy = s0.y;
+  bool dirty = false;          // reg_angle lags the sums (it is the seed's own angle until the first pixel is added)
+  if (lane == 0) { C.R[0] = seed; C.ring[0] = seed; own_of(C, sidx) = kUsedO; }
+  int cnt = 1;
+  __syncwarp();
+  const int grp = lane >> 3, kk8 = lane & 7, kk = kk8 + (kk8 >= 4);
+  const int ox = kk % 3 - 1, oy = kk / 3 - 1;
+  for (int i = 0; i < cnt;) {
+    const int m = min(4, cnt - i);
+    bool valid = false;
+    int idx = -1;
+    unsigned pk = 0xffff0000u | (unsigned)lane;      // unique per lane unless it names a real pixel
+    int ab = 0;
+    float2 csv = make_float2(0.f, 0.f);
+    if (grp < m) {
+      const int qi = i + grp;
+      const unsigned p = (cnt - qi <= kORing) ? C.ring[qi & (kORing - 1)] : C.R[qi];
+      const int xx = (int)(p & 0xffffu) + ox, yy = (int)(p >> 16) + oy;
+      if (xx >= 0 && yy >= 0 && xx < C.sw && yy < C.sh) {
+        idx = yy * C.sw + xx;
+        const int4 v = C.REC[idx];
+        if (v.x == lg::kFree) {                       // defined and not USED
+          valid = true; ab = v.y;
+          csv = make_float2(__int_as_float(v.z), __int_as_float(v.w));
+          pk = (unsigned)xx | ((unsigned)yy << 16);
+        }
+      }
+    }
+    i += m;
+    unsigned live = __ballot_sync(0xffffffffu, valid);
+    if (live == 0u) continue;
+    const double a = (double)__int_as_float(ab) * kDegToRads;
+    int mypos = -1;
+    while (live) {
+      if (dirty) { reg_angle = (double)lg::fast_atan2_deg(sumdy, sumdx) * kDegToRads; dirty = false; }
+      bool al;
+      if (kFast) { const double n1 = fabs(reg_angle - a); al = (n1 <= prec) || (n1 >= prec_hi); }
+      else al = is_aligned_generic(a, reg_angle, prec);
+      const unsigned A = __ballot_sync(0xffffffffu, al) & live;
+      if (!A) break;
+      const int k = __ffs(A) - 1;
+      if (lane == k) mypos = cnt;
+      cnt++;
+      sumdx = __fadd_rn(sumdx, __shfl_sync(0xffffffffu, csv.x, k));
+      sumdy = __fadd_rn(sumdy, __shfl_sync(0xffffffffu, csv.y, k));
+      dirty = true;
+      // everything up to k has been decided; the same pixel in a later 3x3 is now USED
+      live &= ~(((2u << k) - 1u) | __ballot_sync(0xffffffffu, pk == __shfl_sync(0xffffffffu, pk, k)));
+    }
+    if (mypos >= 0) {      // publish: every accepted lane owns its pixel
+      own_of(C, idx) = kUsedO;
+      C.R[mypos] = pk;
+      C.ring[mypos & (kORing - 1)] = pk;
+    }
+    __syncwarp();
+  }
+  if (dirty) reg_angle = (double)lg::fast_atan2_deg(sumdy, sumdx) * kDegToRads;
+  reg_angle_out = reg_angle;
+  return cnt;
+}
+__device__ __noinline__ int region_grow_cold(const Ctx& C, unsigned seed, double prec, double& reg_angle, int lane) {
+  return region_grow<false>(C, seed, prec, 0.0, reg_angle, lane);
+}
+
+// region2rect + get_theta: sums in list order (see the header), extents by exact max / min
+__device__ __noinline__ void region2rect(const Ctx& C, int n, double reg_angle, double prec, RectD& rec, int lane) {
+  double sx = 0, sy = 0, sw_ = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    double tx = 0, ty = 0, w = 0;
+    if (i < n) {
+      const unsigned p = C.R[i];
+      const int px = (int)(p & 0xffffu), py = (int)(p >> 16);
+      w = __ldg(&C.wtab[__ldg(&C.SQ[py * C.sw + px])]);
+      tx = (double)px * w; ty = (double)py * w;
+    }
+    const int m = min(32, n - i0);
+    for (int k = 0; k < m; k++) { sx += shfl_d(tx, k); sy += shfl_d(ty, k); sw_ += shfl_d(w, k); }
+  }
+  const double x = sx / sw_, y = sy / sw_;
+  double Ixx = 0, Iyy = 0, Ixy = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    double t1 = 0, t2 = 0, t3 = 0;
+    if (i < n) {
+      const unsigned p = C.R[i];
+      const int px = (int)(p & 0xffffu), py = (int)(p >> 16);
+      const double w = __ldg(&C.wtab[__ldg(&C.SQ[py * C.sw + px])]);
+      const double dx = (double)px - x, dy = (double)py - y;
+      t1 = dy * dy * w; t2 = dx * dx * w; t3 = dx * dy * w;
+    }
+    const int m = min(32, n - i0);
+    for (int k = 0; k < m; k++) { Ixx += shfl_d(t1, k); Iyy += shfl_d(t2, k); Ixy -= shfl_d(t3, k); }
+  }
+  const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+  double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)lg::fast_atan2_deg((float)(lambda - Ixx), (float)Ixy)
+                                         : (double)lg::fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
+  theta *= kDegToRads;
+  if (fabs(lg::angle_diff_signed(theta, reg_angle)) > prec) theta += kPI;
+  const double dx = cos(theta), dy = sin(theta);
+  double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
+  for (int i = lane; i < n; i += 32) {
+    const unsigned p = C.R[i];
+    const double rdx = (double)(int)(p & 0xffffu) - x, rdy = (double)(int)(p >> 16) - y;
+    const double l = rdx * dx + rdy * dy, w = -rdx * dy + rdy * dx;
+    l_max = fmax(l_max, l); l_min = fmin(l_min, l);
+    w_max = fmax(w_max, w); w_min = fmin(w_min, w);
+  }
+  l_max = wmax_d(l_max); l_min = wmin_d(l_min); w_max = wmax_d(w_max); w_min = wmin_d(w_min);
+  rec.x1 = x + l_min * dx; rec.y1 = y + l_min * dy;
+  rec.x2 = x + l_max * dx; rec.y2 = y + l_max * dy;
+  rec.width = w_max - w_min;
+  if (rec.width < 1.0) rec.width = 1.0;
+}
+
+// reduce_region_radius(), one round: drop the pixels beyond radSq with the reference's swap-remove order.
+// Every pixel is tested exactly once by the CPU loop, so the removed set is "all far pixels" (released in parallel);
+// the survivors end up as: kept elements below the final size K stay, each hole below K (in increasing order) receives
+// the last kept element of the shrinking tail (in decreasing order) - the two-pointer walk below, on the bit mask.
+__device__ __noinline__ int reduce_round(const Ctx& C, int n, double xc, double yc, double radSq, int lane) {
+  int kept = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    bool far = false;
+    if (i < n) {
+      const unsigned p = C.R[i];
+      const double px = (double)(int)(p & 0xffffu), py = (double)(int)(p >> 16);
+      far = (px - xc) * (px - xc) + (py - yc) * (py - yc) > radSq;
+      if (far) own_of(C, (int)(p >> 16) * C.sw + (int)(p & 0xffffu)) = lg::kFree;
+    }
+    const unsigned mw = __ballot_sync(0xffffffffu, far);
+    if (lane == 0) C.mask[i0 >> 5] = mw;
+    kept += __popc(~mw & (n - i0 >= 32 ? 0xffffffffu : ((1u << (n - i0)) - 1u)));
+  }
+  __syncwarp();
+  if (kept == n) return n;
+  if (lane == 0) {
+    int hi = n - 1;                                   // tail pointer: last position not yet consumed
+    int lo_word = 0;
+    const int K = kept;
+    // holes below K in increasing order
+    for (int w = 0; w * 32 < K; w++) {
+      unsigned holes = C.mask[w];
+      if (w * 32 + 32 > K) holes &= (1u << (K - w * 32)) - 1u;
+      while (holes) {
+        const int h = w * 32 + __ffs(holes) - 1;
+        holes &= holes - 1u;
+        while ((C.mask[hi >> 5] >> (hi & 31)) & 1u) hi--;   // skip (= remove) far elements at the tail
+        C.R[h] = C.R[hi];
+        hi--;
+      }
+    }
+    (void)lo_word;
+  }
+  __syncwarp();
+  return kept;
+}
+
+// LineSegmentDetectorImpl::refine + reduce_region_radius; n is updated; returns false if the region is rejected
+__device__ __noinline__ bool refine(const Ctx& C, int& n, double reg_angle, double prec, RectD& rec, double density_th, int lane, bool& released) {
+  double density = (double)n / (lg::dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+  if (density >= density_th) return true;
+  released = true;              // from here on USED flags are cleared
+  const unsigned p0 = C.R[0];
+  const double xc = (double)(int)(p0 & 0xffffu), yc = (double)(int)(p0 >> 16);
+  const double ang_c = (double)__int_as_float(angle_bits(C, (int)(p0 >> 16) * C.sw + (int)(p0 & 0xffffu))) * kDegToRads;
+  double sum = 0, s_sum = 0;
+  int cnt = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    bool in = false;
+    double ad = 0, ad2 = 0;
+    if (i < n) {
+      const unsigned p = C.R[i];
+      const int pidx = (int)(p >> 16) * C.sw + (int)(p & 0xffffu);
+      own_of(C, pidx) = lg::kFree;
+      const double px = (double)(int)(p & 0xffffu), py = (double)(int)(p >> 16);
+      if (lg::dist_d(xc, yc, px, py) < rec.width) {
+        in = true;
+        ad = lg::angle_diff_signed((double)__int_as_float(angle_bits(C, pidx)) * kDegToRads, ang_c);
+        ad2 = ad * ad;
+      }
+    }
+    unsigned mi = __ballot_sync(0xffffffffu, in);
+    cnt += __popc(mi);
+    while (mi) {                                       // the additions in list order
+      const int k = __ffs(mi) - 1;
+      mi &= mi - 1u;
+      sum += shfl_d(ad, k); s_sum += shfl_d(ad2, k);
+    }
+  }
+  __syncwarp();
+  const double mean_angle = sum / (double)cnt;
+  const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
+  n = region_grow_cold(C, p0, tau, reg_angle, lane);
+  if (n < 2) return false;
+  region2rect(C, n, reg_angle, prec, rec, lane);
+  density = (double)n / (lg::dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+  if (density >= density_th) return true;
+  const double r1 = lg::dist_sq(xc, yc, rec.x1, rec.y1), r2 = lg::dist_sq(xc, yc, rec.x2, rec.y2);
+  double radSq = r1 > r2 ? r1 : r2;
+  while (density < density_th) {
+    radSq *= 0.75 * 0.75;
+    n = reduce_round(C, n, xc, yc, radSq, lane);
+    if (n < 2) return false;
+    region2rect(C, n, reg_angle, prec, rec, lane);
+    density = (double)n / (lg::dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+  }
+  return true;
+}
+
+}  // namespace ord
+
+// One warp per frame; grid = frames (32 one-warp CTAs resident per SM: 4736 frames in one wave on 148 SMs).
+__global__ void __launch_bounds__(32, 32) k_lsd_grow_ordered(LineParams P, int4* __restrict__ REC, const int* __restrict__ SQ, const float2* __restrict__ seedcs,
+                                                             const unsigned* __restrict__ order, const int* __restrict__ ndef,
+                                                             unsigned* __restrict__ reg, int reg_stride, unsigned* __restrict__ mask, const double* __restrict__ wtab,
+                                                             float4* __restrict__ segs, int* __restrict__ nseg, int* __restrict__ overflow, int nframes) {
+  using namespace ord;
+  __shared__ unsigned ring[kORing];
+  const int lane = threadIdx.x & 31;
+  for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
+    const Ctx C = {REC + (long long)f * P.npx, SQ + (long long)f * P.npx, seedcs + (long long)f * P.npx, wtab,
+                   reg + (long long)f * reg_stride, ring, mask + (long long)f * P.npx, P.sw, P.sh};
+    const unsigned* O = order + (long long)f * P.npx;
+    float4* S = segs + (long long)f * P.seg_cap;
+    const int n = ndef[f];
+    int ns = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      const unsigned pix = (i < n) ? O[i] : 0u;
+      const int pidx = (int)(pix >> 16) * P.sw + (int)(pix & 0xffffu);
+      unsigned todo = __ballot_sync(0xffffffffu, i < n && own_of(C, pidx) == lg::kFree);
+      // this batch's seeds that will grow: their seed record and 3x3 rows into L2; and the next batch's ownership words
+      if ((todo >> lane) & 1u) {
+        prefetch_l2(&C.S2[pidx]);
+        const int up = max(pidx - P.sw, 1), dn = min(pidx + P.sw, P.npx - 2);
+        prefetch_l2(&C.REC[up - 1]); prefetch_l2(&C.REC[up + 1]); prefetch_l2(&C.REC[dn - 1]); prefetch_l2(&C.REC[dn + 1]);
+        prefetch_l2(&C.REC[max(pidx, 1) - 1]); prefetch_l2(&C.REC[min(pidx, P.npx - 2) + 1]);
+      }
+      if (i + 32 < n) { const unsigned pn = O[i + 32]; prefetch_l2(&C.REC[(int)(pn >> 16) * P.sw + (int)(pn & 0xffffu)]); }
+      while (todo) {
+        const int k = __ffs(todo) - 1;
+        const unsigned seed = __shfl_sync(0xffffffffu, pix, k);
+        double reg_angle;
+        bool released = false;
+        int cnt = region_grow<true>(C, seed, P.prec, P.prec_hi, reg_angle, lane);
+        if (cnt >= P.min_reg_size) {
+          RectD rec;
+          region2rect(C, cnt, reg_angle, P.prec, rec, lane);
+          if (refine(C, cnt, reg_angle, P.prec, rec, P.density_th, lane, released)) {
+            if (lane == 0 && ns < P.seg_cap)
+              S[ns] = make_float4((float)((rec.x1 + 0.5) / 0.8), (float)((rec.y1 + 0.5) / 0.8), (float)((rec.x2 + 0.5) / 0.8),
+                                  (float)((rec.y2 + 0.5) / 0.8));
+            ns++;
+          }
+        }
+        __syncwarp();
+        // seeds later in this batch may have been consumed (or released by refine): re-read their words
+        todo = __ballot_sync(0xffffffffu, i < n && lane > k && own_of(C, pidx) == lg::kFree);
+      }
+    }
+    if (lane == 0) { nseg[f] = min(ns, P.seg_cap); if (ns > P.seg_cap) atomicOr(overflow, 1); }
+    __syncwarp();
+  }
+}
+
+}  // namespace pl

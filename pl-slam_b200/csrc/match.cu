@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(32) k_search_proj_last(ProjLastArgs A) {
     if (A.kfMode) {
       const float p0 = __fsub_rn(X[0], A.Ow[0]), p1 = __fsub_rn(X[1], A.Ow[1]), p2 = __fsub_rn(X[2], A.Ow[2]);
       const float dist3D = (float)sqrt((double)p0 * p0 + (double)p1 * p1 + (double)p2 * p2);
-      if (dist3D < A.min_dist[lb + i] || dist3D > A.max_dist[lb + i]) continue;
+      if (dist3D < __fmul_rn(0.8f, A.min_dist[lb + i]) || dist3D > __fmul_rn(1.2f, A.max_dist[lb + i])) continue;   // invariance range; PredictScale below uses the raw mfMaxDistance
       const float ratio = __fdiv_rn(A.max_dist[lb + i], dist3D);
       oct = (int)ceil(log((double)ratio) / (double)A.logSF);
       if (oct < 0) oct = 0; else if (oct >= A.nlevels) oct = A.nlevels - 1;
@@ -825,7 +825,7 @@ __global__ void __launch_bounds__(32 * kFuseWarps) k_fuse_search(FuseArgs A) {
       if (go) {
         const float PO[3] = {__fsub_rn(P[0], A.Ow[0]), __fsub_rn(P[1], A.Ow[1]), __fsub_rn(P[2], A.Ow[2])};
         const float dist3D = (float)sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
-        go = !(dist3D < A.minDist[i] || dist3D > A.maxDist[i]);
+        go = !(dist3D < __fmul_rn(0.8f, A.minDist[i]) || dist3D > __fmul_rn(1.2f, A.maxDist[i]));
         if (go) {
           const double dot = (double)PO[0] * A.normal[3 * i] + (double)PO[1] * A.normal[3 * i + 1] + (double)PO[2] * A.normal[3 * i + 2];
           go = !(dot < 0.5 * (double)dist3D);

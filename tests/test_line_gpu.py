@@ -19,8 +19,10 @@ def _segments_equal(a, b):
     assert a.tobytes() == b.tobytes(), "segment lists differ: first row %d" % int(np.nonzero((a != b).any(1))[0][0])
 
 
+@pytest.mark.parametrize("spec_maxb", [0, 4])
 @pytest.mark.parametrize("w,h,seed", [(640, 480, 1), (640, 480, 2), (752, 480, 5), (1241, 376, 4)])
-def test_stages_match_oracle(w, h, seed):
+def test_stages_match_oracle(monkeypatch, w, h, seed, spec_maxb):
+    monkeypatch.setenv("PLSLAM_LSD_GROW_SPEC_MAXB", str(spec_maxb))     # 0: ordered kernel, 4: speculative kernel
     img = synth.synth_frame(w, h, seed)
     ex = pl.LINEextractor(1, 1.2, 200, 0.0, width=w, height=h)
     kl, desc, lf = ex(img)
@@ -125,8 +127,11 @@ def test_grow_batches_of_odd_sizes():
             assert nb[b] == len(okl) and klb[b, :nb[b]].tobytes() == okl.tobytes() and np.array_equal(descb[b, :nb[b]], odesc), (B, b)
 
 
-def test_grow_degenerate_frames():
-    """No gradient at all, pure noise (thousands of tiny regions), one long edge across the frame (one huge region)."""
+@pytest.mark.parametrize("spec_maxb", [0, 4])
+def test_grow_degenerate_frames(monkeypatch, spec_maxb):
+    """No gradient at all, pure noise (thousands of tiny regions), one long edge across the frame (one huge region);
+    through both region-growing kernels (0: ordered one-warp-per-frame kernel, 4: speculative kernel for a single frame)."""
+    monkeypatch.setenv("PLSLAM_LSD_GROW_SPEC_MAXB", str(spec_maxb))
     rng = np.random.Generator(np.random.PCG64(11))
     flat = np.full((480, 640), 128, np.uint8)
     noise = rng.integers(0, 256, (480, 640), dtype=np.uint8)

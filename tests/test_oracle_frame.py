@@ -75,7 +75,7 @@ def test_is_in_frustum_points_semantics():
     with np.errstate(all="ignore"):
         u = synth.TUM1_K[0] * Pc[:, 0] / Pc[:, 2] + synth.TUM1_K[2]; vv = synth.TUM1_K[1] * Pc[:, 1] / Pc[:, 2] + synth.TUM1_K[3]
     d = np.linalg.norm(P - v["Ow"], axis=1); cosv = ((P - v["Ow"]) * v["normal"]).sum(1) / d
-    ok = (Pc[:, 2] >= 0) & (u >= b[0]) & (u <= b[2]) & (vv >= b[1]) & (vv <= b[3]) & (d >= v["min_dist"]) & (d <= v["max_dist"]) & (cosv >= 0.5)
+    ok = (Pc[:, 2] >= 0) & (u >= b[0]) & (u <= b[2]) & (vv >= b[1]) & (vv <= b[3]) & (d >= np.float32(0.8) * v["min_dist"]) & (d <= np.float32(1.2) * v["max_dist"]) & (cosv >= 0.5)
     assert (ok != iv.astype(bool)).sum() <= 2
     m = ok & iv.astype(bool)
     assert np.abs(proj[m, 0] - u[m]).max() < 1e-2 and np.abs(vc[m] - cosv[m]).max() < 1e-5
@@ -94,3 +94,23 @@ def test_is_in_frustum_lines_semantics():
     assert (proj[m, 0] >= b[0]).all() and (proj[m, 2] <= b[2]).all() and (vc[m] >= 0.5).all()
     # the line variant does NOT clamp the predicted level (MapLine.cpp:395-404: ceil(log(ratio)/logScaleFactor) bare)
     assert lvl[m].max() > 7
+
+
+def test_predict_scale_known_answers():
+    """MapPoint::PredictScale uses the RAW mfMaxDistance (MapPoint.cc:396-428), not GetMaxDistanceInvariance() = 1.2 * mfMaxDistance:
+    a point seen at mfMaxDistance / 1.2^k (plus a hair) is predicted on level k = ceil(log(ratio) / log 1.2); the invariance factors only widen the range test."""
+    K = synth.TUM1_K
+    b = np.array([0, 0, 640, 480], np.float32)
+    Tcw = np.eye(4, dtype=np.float32); Ow = np.zeros(3, np.float32)
+    maxd = np.float32(10.0)
+    logsf = float(np.float32(np.log(np.float32(1.2))))
+    for k in range(8):
+        d = float(maxd) / 1.2 ** k * 1.001
+        pos = np.array([[0.0, 0.0, d]], np.float32); normal = np.array([[0.0, 0.0, 1.0]], np.float32)
+        iv, proj, lvl, vc = oracle.is_in_frustum_points(Tcw, Ow, K, b, logsf, 8, 0.5, pos, normal, np.array([0.1], np.float32), np.array([maxd], np.float32))
+        assert iv[0] == 1 and lvl[0] == k, (k, lvl[0])
+    # the range test uses 0.8 * min and 1.2 * max: a point at 1.15 * mfMaxDistance is in view (level 0), one at 1.25 * is not
+    for d, expect in ((11.5, 1), (12.5, 0), (0.085, 1), (0.075, 0)):
+        pos = np.array([[0.0, 0.0, d]], np.float32); normal = np.array([[0.0, 0.0, 1.0]], np.float32)
+        iv, _, lvl, _ = oracle.is_in_frustum_points(Tcw, Ow, K, b, logsf, 8, 0.5, pos, normal, np.array([0.1], np.float32), np.array([maxd], np.float32))
+        assert iv[0] == expect, (d, iv[0])

@@ -450,7 +450,10 @@ __global__ void __launch_bounds__(32 * kWPC) k_lsd_grow(LineParams P, lg::Params
     if (solo) warp_commit(GP, Fm, S, lane);
     // ---- feed
     unsigned mi = __ballot_sync(0xffffffffu, L.phase == P_IDLE);
-    if (mi) {
+    // a warp that carries a long region is on the frame's critical path (the chain of long, refine-heavy regions is what
+    // a single frame waits for): it looks for new work only every 8th iteration, the other warps feed the idle lanes
+    const bool heavy = __any_sync(0xffffffffu, L.phase != P_IDLE && L.hi >= 64);
+    if (mi && (!heavy || (iter & 7u) == 0u)) {
       // lane 0 looks at the three hand-over words at once: the re-execution slot of the committer and the redo ring
       int redo = -1, rqh = 0, rqt = 0;
       if (lane == 0) { redo = ld_i(&Fm.ctl[C_REDO]); rqh = ld_i(&Fm.ctl[C_RQH]); rqt = ld_i(&Fm.ctl[C_RQT]); if (redo >= 0) redo = a_exch(&Fm.ctl[C_REDO], -1); }
@@ -848,7 +851,7 @@ struct PLLine {
   lg::Params GP;
   int grow_warps_target = 148 * 16;   // warps the grow kernel spreads over the GPU when the batch is small (env PLSLAM_LSD_GROW_WARPS)
   int grow_wpf_max = 64;              // at most this many warps on one frame (env PLSLAM_LSD_GROW_WPF)
-  int grow_spec_max_batch = 4;        // batches up to this size use the speculative kernel, larger ones the ordered one (env PLSLAM_LSD_GROW_SPEC_MAXB)
+  int grow_spec_max_batch = 16;        // batches up to this size use the speculative kernel, larger ones the ordered one (env PLSLAM_LSD_GROW_SPEC_MAXB)
   size_t lane_warps = 0;              // lane buffers are allocated for this many warps
   int4* d_rec = nullptr; int* d_sq = nullptr;
   unsigned *d_st = nullptr, *d_pool = nullptr, *d_lanebuf = nullptr; int* d_ctl = nullptr; double* d_wtab = nullptr;

@@ -1,18 +1,26 @@
 #!/usr/bin/env python
 """bench.py — frames/sec of the PL-SLAM front-end hot path (extract + match + pose-LM) on B200.
 
-One "step" = one batch of B synthetic 640x480 frames per GPU through the whole per-frame hot path
-(ORB extract 1000 features, LSD+LBD extract <=200(+1) lines, point matching frame k-1 -> k, line matching,
-2 x Optimizer::PoseOptimization on a TUM-shaped problem of ~300 points + 80 lines).  BASELINE.json metric:
-"frames/sec (extract+match+pose-LM) 640x480".
+One "step" = one batch of synthetic frames per GPU through the whole per-frame hot path (ORB extract, undistort, LSD+LBD
+extract, point matching frame k-1 -> k, line matching, 2 x Optimizer::PoseOptimization on the frame's pose problem).
+BASELINE.json metric: "frames/sec (extract+match+pose-LM) 640x480".  Configurations (BASELINE.json `configs`):
+
+  --config tum    (default, the headline)  640x480, TUM1 camera, ORB 1000, B = 4736 frames per GPU, WEAK scaling
+  --config kitti  configs[3]: 1241x376, ORB 2000, no distortion, 256 frames sharded over the ranks (contiguous blocks with a
+                  1-frame halo, pl-slam_b200/sharding.py), + one LocalBundleAdjustmentWithLine window (20+40 KFs, 3000 points,
+                  400 lines) per rank and step; STRONG scaling
+  --config euroc  configs[4]: 752x480, EuRoC camera, ORB 1000, 512 frames sharded over the ranks; STRONG scaling
 
   value     frames/s with the frames already resident in HBM (CUDA events on the launching stream, max over ranks)
-  e2e       the same through the C ABI's streaming host-buffer entry points pl_frontend_submit()/wait(): pinned host frames -> H2D ->
-            kernels -> D2H of every per-frame result, inside the timed region
-  roofline  the dominant kernel (k_lsd_grow) timed with CUDA events on its own stream, algorithmic bytes / time
-  cpu_baseline  the CPU oracle (a port: the reference cannot be built here) on a bounded sample, 1 thread
+  e2e       the same through the C ABI's streaming host-buffer entry points pl_frontend_submit()/wait(): pinned host frames AND
+            the step's pose problems -> H2D -> kernels -> D2H of every per-frame result, inside the timed region
+  latency   (N=1) ms per frame through the synchronous host-buffer call pl_frontend_run at B = 1 and B = 64: what a Tracking
+            thread that hands over one frame (or one second of video) at a time sees
+  roofline  the dominant kernel (k_lsd_grow_ordered) timed with CUDA events on its own stream, algorithmic bytes / time
+  cpu_baseline  the CPU oracle (a port: the reference cannot be built here) on one thread: median of >= 50 frames
+  extra_configs  (default run only) a short run of the kitti and euroc configurations on the same GPUs
 
-`--impl reference` times the CPU oracle of the same path with all host threads on a bounded sample per step.
+`--impl reference` times the CPU oracle of the same path on the host threads this process may use.
 """
 import argparse
 import json
@@ -28,51 +36,89 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-W, H = 640, 480
-ORB = (1000, 1.2, 8, 20, 7)          # Examples/Monocular/TUM1.yaml:34-56
-LINES = (200, 0.0)
-N_PTS, N_LINES = 300, 80             # SURVEY.md §8d config 3
 METRIC = "frames/sec (extract+match+pose-LM) 640x480"
-
-
+N_PTS, N_LINES = 300, 80             # SURVEY.md §8d config 3
+LINES = (200, 0.0)
+KITTI_K = (718.856, 718.856, 607.1928, 185.2157)      # Examples/Monocular/KITTI00-02.yaml:8-11
+CONFIGS = {
+    "tum": dict(W=640, H=480, orb=(1000, 1.2, 8, 20, 7), camera="tum", scaling="weak", batch=4736, lba=False,
+                workload="640x480 synthetic sequence, TUM1 camera: ORB(1000) + undistort + LSD/LBD(200) extract, frame-to-frame point+line "
+                         "matching, 2x PoseOptimization(300 pts + 80 lines)"),
+    "kitti": dict(W=1241, H=376, orb=(2000, 1.2, 8, 20, 7), camera="kitti", scaling="strong", total=256, lba=True,
+                  workload="KITTI-shaped 1241x376 mono (BASELINE configs[3]): ORB(2000) + LSD/LBD(200) extract, frame-to-frame point+line matching, "
+                           "2x PoseOptimization, + one LocalBundleAdjustmentWithLine window (20+40 KFs, 3000 pts, 400 lines) per rank and step; "
+                           "256 frames sharded over the ranks with a 1-frame halo"),
+    "euroc": dict(W=752, H=480, orb=(1000, 1.2, 8, 20, 7), camera="euroc", scaling="strong", total=512, lba=False,
+                  workload="EuRoC-shaped 752x480 mono (BASELINE configs[4]): EuRoC camera, ORB(1000) + undistort + LSD/LBD(200) extract, matching, "
+                           "2x PoseOptimization; 512 frames sharded over the ranks with a 1-frame halo, all-gather of the pose records"),
+}
+W, H = CONFIGS["tum"]["W"], CONFIGS["tum"]["H"]
+ORB = CONFIGS["tum"]["orb"]
 BASE_FRAMES = 64     # distinct host-generated frames; larger batches add per-replica sensor noise (deterministic)
 
 
-def make_inputs(B, seed):
+def camera_of(cfg):
+    from plslam_b200 import synth
+    if cfg["camera"] == "tum":
+        return synth.TUM1_K, synth.TUM1_DIST
+    if cfg["camera"] == "euroc":
+        return synth.EUROC_K, synth.EUROC_DIST
+    return KITTI_K, (0.0, 0.0, 0.0, 0.0, 0.0)
+
+
+def make_inputs(B, seed, w=W, h=H, K=None):
     """B synthetic frames + B pose problems.  The first min(B, 64) frames are a warped sequence (synth.synth_sequence);
     frames beyond that repeat the sequence with fresh additive sensor noise (sigma 2 grey levels, PCG64 seeded), so every
     frame of the batch has different content."""
     from plslam_b200 import synth
     nb = min(B, BASE_FRAMES)
-    base = synth.synth_sequence(nb, W, H, seed=seed)
+    base = synth.synth_sequence(nb, w, h, seed=seed)
     if B > nb:
         rng = np.random.Generator(np.random.PCG64(77 + seed))
-        frames = np.empty((B, H, W), np.uint8)
+        frames = np.empty((B, h, w), np.uint8)
         frames[:nb] = base
         for r in range(nb, B, nb):
             k = min(nb, B - r)
-            noise = rng.normal(0, 2.0, (k, H, W)).astype(np.float32)
+            noise = rng.normal(0, 2.0, (k, h, w)).astype(np.float32)
             frames[r:r + k] = np.clip(np.rint(base[:k].astype(np.float32) + noise), 0, 255).astype(np.uint8)
     else:
         frames = base
-    problems = [synth.synth_pose_problem(1000 * seed + k, n_points=N_PTS, n_lines=N_LINES) for k in range(B)]
+    kw = {} if K is None else dict(K=K, w=w, h=h)
+    problems = [synth.synth_pose_problem(1000 * seed + k, n_points=N_PTS, n_lines=N_LINES, **kw) for k in range(B)]
     return frames, problems
 
 
 # ------------------------------------------------------------------------------------------------ CPU oracle arm
-def oracle_frame_pipeline(o_orb, prev, img, prob):
-    """The same per-frame work on the CPU oracle; returns the frame's features (to serve as `prev`)."""
+def use_native_oracle():
+    """The CPU legs time the -march=native build of the oracle (-O3 -march=native), compiled on the box that
+    does the timing; the portable build that travels with the repo stays the checker of the tests."""
+    lib = os.path.join(ROOT, "oracle", "liboracle_native.so")
+    try:
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        os.environ["PLSLAM_ORACLE_LIB"] = lib
+        return "-O3 -march=native"
+    except Exception:
+        return "-O3 -march=x86-64-v3 (native build failed)"
+
+
+def oracle_features(o_orb, img, cfg):
     import oracle
-    from plslam_b200 import synth
-    K, D = synth.TUM1_K, synth.TUM1_DIST
+    K, D = camera_of(cfg)
     kps, desc = o_orb.extract(img)                                   # Frame.cc:224 (raw image)
-    und = oracle.undistort_remap(img, K, D)                          # Frame.cc:220-222
+    und = oracle.undistort_remap(img, K, D) if D[0] != 0.0 else img  # Frame.cc:220-222
     kl, ldesc, lf = oracle.line_extract(und, nfeatures=LINES[0], min_line_length=LINES[1])   # Frame.cc:225
     kps = oracle.undistort_keypoints(kps, K, D)                      # Frame.cc:233
+    return kps, desc, ldesc
+
+
+def oracle_frame_pipeline(o_orb, prev, img, prob, cfg, bounds):
+    """The same per-frame work on the CPU oracle; returns the frame's features (to serve as `prev`)."""
+    import oracle
+    kps, desc, ldesc = oracle_features(o_orb, img, cfg)
     if prev is not None:
         pk, pd, pl_ = prev
         pm = np.stack([pk["x"], pk["y"]], 1).astype(np.float32)
-        oracle.search_for_initialization(pk, pd, kps, desc, oracle.image_bounds(K, D, W, H), pm, 100, 0.9, True)
+        oracle.search_for_initialization(pk, pd, kps, desc, bounds, pm, 100, 0.9, True)
         oracle.search_double(pl_, ldesc, 0.7)
     for _ in range(2):
         oracle.pose_optimization(0, prob["Tcw0"], prob["K"], prob["pt_obs"], prob["pt_inv_sigma2"], prob["pt_Xw"],
@@ -80,61 +126,66 @@ def oracle_frame_pipeline(o_orb, prev, img, prob):
     return kps, desc, ldesc
 
 
-def cpu_sample(frames, problems, n_frames, threads):
-    """Time n_frames frames of the oracle pipeline on `threads` host threads; returns (frames/s, n_frames, seconds).
-
-    Frame i+1 is matched against frame i; the predecessor's features are prepared outside the timed region (a frame's
-    extraction is counted once, as in the GPU batch)."""
+def cpu_sample(frames, problems, n_frames, threads, cfg=None, per_frame=False):
+    """Time n_frames frames of the oracle pipeline on `threads` host threads; returns (frames/s, n_frames, seconds) or, with
+    per_frame, the list of per-frame seconds.  Frame i+1 is matched against frame i; the predecessor's features are prepared
+    outside the timed region (a frame's extraction is counted once, as in the GPU batch)."""
     import oracle
     from concurrent.futures import ThreadPoolExecutor
+    cfg = cfg or CONFIGS["tum"]
+    K, D = camera_of(cfg)
+    bounds = oracle.image_bounds(K, D, cfg["W"], cfg["H"])
     n_frames = min(n_frames, len(frames) - 1)
 
     def features(idx):
-        from plslam_b200 import synth
-        kps, desc = oracle.OrbOracle(*ORB).extract(frames[idx])
-        und = oracle.undistort_remap(frames[idx], synth.TUM1_K, synth.TUM1_DIST)
-        kl, ldesc, lf = oracle.line_extract(und, nfeatures=LINES[0], min_line_length=LINES[1])
-        return oracle.undistort_keypoints(kps, synth.TUM1_K, synth.TUM1_DIST), desc, ldesc
+        return oracle_features(oracle.OrbOracle(*cfg["orb"]), frames[idx], cfg)
 
     def one(i):
-        oracle_frame_pipeline(oracle.OrbOracle(*ORB), prevs[i], frames[i + 1], problems[i + 1])
+        t = time.perf_counter()
+        oracle_frame_pipeline(oracle.OrbOracle(*cfg["orb"]), prevs[i], frames[i + 1], problems[i + 1], cfg, bounds)
+        return time.perf_counter() - t
 
     with ThreadPoolExecutor(max(threads, 1)) as ex:
         prevs = list(ex.map(features, range(n_frames)))
         t0 = time.perf_counter()
-        if threads == 1:
-            for i in range(n_frames):
-                one(i)
-        else:
-            list(ex.map(one, range(n_frames)))
+        per = [one(i) for i in range(n_frames)] if threads == 1 else list(ex.map(one, range(n_frames)))
         dt = time.perf_counter() - t0
-    return n_frames / dt, n_frames, dt
+    return per if per_frame else (n_frames / dt, n_frames, dt)
+
+
+def host_threads():
+    try:
+        return max(len(os.sched_getaffinity(0)), 1)
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def run_reference(args):
-    """CPU arm: the oracle (a port of the reference's CPU path) on all host threads, bounded sample per step."""
+    """CPU arm: the oracle (a port of the reference's CPU path) on the host threads this process may use, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    flags = use_native_oracle()
     import oracle
     oracle.build()
-    threads = os.cpu_count() or 1
+    cfg = CONFIGS[args.config]
+    threads = host_threads()
     per_step = max(2 * threads, 8)
-    frames, problems = make_inputs(per_step + 1, 1)
+    K, _ = camera_of(cfg)
+    frames, problems = make_inputs(per_step + 1, 1, cfg["W"], cfg["H"], K)
     for _ in range(max(args.warmup, 1)):
-        cpu_sample(frames, problems, threads, threads)
+        cpu_sample(frames, problems, threads, threads, cfg)
     tot_n, tot_t = 0, 0.0
     for _ in range(args.steps):
-        _, n, dt = cpu_sample(frames, problems, per_step, threads)
+        _, n, dt = cpu_sample(frames, problems, per_step, threads, cfg)
         tot_n += n; tot_t += dt
     value = tot_n / tot_t
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(args.warmup, 1), "ms_per_step": 1000.0 * tot_t / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 front-end, f32 descriptors, f64 LM", "data": "synthetic",
-            "config": {"workload": "640x480 synthetic sequence, TUM1 camera: ORB(1000) + undistort + LSD/LBD(200) extract, frame-to-frame point+line "
-                                   "matching, 2x PoseOptimization(300 pts + 80 lines)", "frames_per_step": per_step},
+            "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "u8/i32 front-end, f32 descriptors, f64 LM", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "frames_per_step": per_step, "name": args.config},
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
-                             "sample": f"{per_step} frames per step x {args.steps} steps on {threads} threads; CPU oracle "
+                             "sample": f"{per_step} frames per step x {args.steps} steps on {threads} threads (sched_getaffinity); CPU oracle built {flags} "
                                        "(restatement: the reference needs OpenCV/Eigen headers that are not installed)"},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -183,147 +234,276 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def run_ours(args):
-    import torch
+class Ctx:
+    """Process-wide state of the GPU arm: rank layout, the launching stream, and (N > 1) the library's own NCCL communicator
+    for the one exchange step (pl_allgather_poses, include/plslam_b200.h)."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0")); self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: plslam_b200 has no CPU fallback (use --impl reference for the CPU oracle)")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        self.comm = None
+        if self.world > 1:
+            import ctypes as C
+            import torch.distributed as dist
+            import plslam_b200 as pl
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+            L = pl.binding.lib()
+            uid = np.zeros(128, np.uint8)
+            if self.rank == 0:
+                pl.binding.check(L.pl_comm_unique_id(uid.ctypes.data_as(C.c_void_p)))
+            box = [uid.tobytes()]
+            dist.broadcast_object_list(box, src=0)
+            uid = np.frombuffer(box[0], np.uint8).copy()
+            h = C.c_void_p()
+            L.pl_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+            pl.binding.check(L.pl_comm_create(uid.ctypes.data_as(C.c_void_p), self.world, self.rank, C.byref(h)))
+            L.pl_allgather_poses.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+            self.comm = h
+            self._L = L
+        self.stream = torch.cuda.Stream()      # a real (non-NULL) stream: the C ABI treats NULL as "the handle's own stream"
+        torch.cuda.set_stream(self.stream)
+        self.sptr = self.stream.cuda_stream
+        assert self.sptr != 0
+
+    def allgather(self, send, recv, floats_per_rank):
+        import plslam_b200 as pl
+        pl.binding.check(self._L.pl_allgather_poses(self.comm, send.data_ptr(), recv.data_ptr(), floats_per_rank, self.sptr))
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+
+def run_config(ctx, name, steps, warmup, batch=None, full=True):
+    """One configuration on this process's GPU; returns the measurements (rank-local python values, timings max over ranks)."""
     import plslam_b200 as pl
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: plslam_b200 has no CPU fallback (use --impl reference for the CPU oracle)")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    B = args.batch
-    frames, problems = make_inputs(B, seed=1 + rank)        # weak scaling: every rank gets its own B frames
-    fe = pl.Frontend(W, H, max_batch=B, orb=ORB, lines=LINES, lm_caps=(N_PTS + 20, N_LINES + 8))
-    fe.set_pose_problems(problems)
-    from plslam_b200 import synth
-    fe.set_camera(synth.TUM1_K, synth.TUM1_DIST)          # TUM1.yaml camera: frames and keypoints are undistorted on the device
+    from plslam_b200 import synth, sharding
+    torch = ctx.torch
+    cfg = CONFIGS[name]
+    w, h = cfg["W"], cfg["H"]
+    K, D = camera_of(cfg)
+    if cfg["scaling"] == "weak":
+        B = batch or cfg["batch"]
+        halo, count, first, total = 0, B, ctx.rank * B, ctx.world * B
+        frames, problems = make_inputs(B, 1 + ctx.rank, w, h, K)      # weak scaling: every rank gets its own B frames
+    else:
+        total = batch or cfg["total"]
+        first, count, halo = sharding.shard_frames(total, ctx.world, ctx.rank)
+        allf, allp = make_inputs(total, 1, w, h, K)                     # one sequence, a contiguous block (+1-frame halo) per rank
+        frames = np.ascontiguousarray(allf[first - halo:first + count]); problems = allp[first - halo:first + count]
+        B = count + halo
+    fe = pl.Frontend(w, h, max_batch=B, orb=cfg["orb"], lines=LINES, lm_caps=(N_PTS + 20, N_LINES + 8))
+    fe.set_camera(K, D)             # TUM1 / EuRoC: frames and keypoints are undistorted on the device; KITTI: bounds only
+    fe.pack_pose_problems(problems, pinned=True)
+    prob_bytes = fe.upload_pose_problems(None)
+    torch.cuda.synchronize()
     d_frames = torch.from_numpy(frames).cuda()
-    stream = torch.cuda.Stream()          # a real (non-NULL) stream: the C ABI treats NULL as "the handle's own stream"
-    torch.cuda.set_stream(stream)
-    sptr = stream.cuda_stream
-    assert sptr != 0
-    poses = torch.empty((B, 16), dtype=torch.float32, device="cuda")
-    gathered = torch.empty((world * B, 16), dtype=torch.float32, device="cuda") if world > 1 else None
+    max_count = -(-total // ctx.world)
+    poses = torch.zeros((B, 16), dtype=torch.float32, device="cuda")
+    send = torch.zeros((max_count, 16), dtype=torch.float32, device="cuda")
+    gathered = torch.empty((ctx.world * max_count, 16), dtype=torch.float32, device="cuda") if ctx.world > 1 else None
+    ba = None
+    if cfg["lba"]:
+        ba = synth.synth_ba_problem(seed=4 + ctx.rank, K=KITTI_K, w=w, h=h)
 
     def step():
-        fe.run_dev(d_frames.data_ptr(), W, W * H, B, sptr)
-        if world > 1:      # the one exchange — all-gather of the per-frame pose records
-            fe.copy_poses_dev(B, poses.data_ptr(), sptr)
-            dist.all_gather_into_tensor(gathered, poses)
+        fe.run_dev(d_frames.data_ptr(), w, w * h, B, ctx.sptr)
+        if ctx.world > 1:      # SURVEY.md §8e: the one exchange — all-gather of the per-frame pose records (halo frame excluded)
+            fe.copy_poses_dev(B, poses.data_ptr(), ctx.sptr)
+            send[:count].copy_(poses[halo:halo + count])
+            ctx.allgather(send, gathered, max_count * 16)
+        if ba is not None:     # LocalMapping's window of this rank (replicas only, SURVEY.md §8e); runs beside the front-end kernels
+            pl.LocalBundleAdjustmentWithLine(ba)
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else
-                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local]) if os.environ["CUDA_VISIBLE_DEVICES"].split(",")[0].isdigit() else local)
-    if rank == 0:
+    sampler = None
+    if ctx.rank == 0 and full:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = int(vis.split(",")[ctx.local]) if vis and vis.split(",")[0].isdigit() else torch.cuda.current_device()
+        sampler = ClockSampler(idx)
         sampler.start()
-    if world > 1:
-        dist.barrier()
+    ctx.barrier()
     torch.cuda.synchronize()
     launches0 = pl.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
+    ev0.record(ctx.stream)
+    for _ in range(steps):
         step()
-    ev1.record(stream)
+    ev1.record(ctx.stream)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = ev0.elapsed_time(ev1)
+    ctx.barrier()
+    ms = ctx.max_over_ranks(ev0.elapsed_time(ev1))
     launches = pl.launch_count() - launches0
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
-    value = world * B * args.steps / (ms / 1000.0)
+    clocks = sampler.stop() if sampler else None
+    res = dict(name=name, B=B, total=total, halo=halo, ms=ms, steps=steps, value=total * steps / (ms / 1000.0), launches=int(launches),
+               clocks=clocks, frame=[w, h], orb=list(cfg["orb"]))
+    if ba is not None:
+        t = []
+        for _ in range(3):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); pl.LocalBundleAdjustmentWithLine(ba); t.append(1000 * (time.perf_counter() - t0))
+        res["lba_ms"] = float(np.median(t))
+        res["lba_window"] = "20 free + 40 fixed KFs, 3000 points, 400 lines"
+    if not full:
+        del fe, d_frames
+        torch.cuda.empty_cache()
+        return res
 
     # ---- dominant kernel, timed on its launching stream (roofline)
     fe.set_timing(True)
     grow = []
     for _ in range(3):
-        fe.run_dev(d_frames.data_ptr(), W, W * H, B, sptr)
+        fe.run_dev(d_frames.data_ptr(), w, w * h, B, ctx.sptr)
         torch.cuda.synchronize()
         grow.append(fe.grow_ms())
     fe.set_timing(False)
-    grow_ms = float(np.mean(grow))
+    res["grow_ms"] = float(np.mean(grow))
+    res["grow_bytes"] = fe.grow_bytes_per_frame() * B
 
-    # ---- e2e through the host-buffer C ABI (pinned host memory, H2D + D2H inside the timed region)
-    pin = torch.empty((B, H, W), dtype=torch.uint8, pin_memory=True)
+    # ---- e2e through the host-buffer C ABI (pinned host memory; frames AND pose problems H2D, every result D2H, all timed)
+    pin = torch.empty((B, h, w), dtype=torch.uint8, pin_memory=True)
     pin.numpy()[:] = frames
     # streaming entry points: submit(i+1) is enqueued while step i computes, so its H2D copy and the D2H copy of step i-1
     # overlap the kernels; two alternating sets of pinned output buffers, every step's results land on the host.
     outs = [fe.alloc_outputs(B, pinned=True) for _ in range(2)]
-    for s in range(2):
-        fe.submit(pin.numpy(), outs[s])
+    for k in range(2):
+        fe.upload_pose_problems(None); fe.submit(pin.numpy(), outs[k])
     fe.wait(0)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e2e_steps = max(3, min(args.steps, 6))
+    ctx.barrier()
+    e2e_steps = max(3, min(steps, 6))
     t0 = time.perf_counter()
-    for s in range(e2e_steps):
-        fe.submit(pin.numpy(), outs[s & 1])
-        fe.wait(1)                 # results of step s-1 are on the host here
+    for k in range(e2e_steps):
+        fe.upload_pose_problems(None)      # the step's LM problems travel with the step (14 KB per frame)
+        fe.submit(pin.numpy(), outs[k & 1])
+        fe.wait(1)                 # results of step k-1 are on the host here
     fe.wait(0)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / float(te.item())
+    e2e_s = ctx.max_over_ranks(time.perf_counter() - t0)
     h2d, d2h = fe.io_bytes()
+    res["e2e"] = {"value": total * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(h2d * B + prob_bytes),
+                  "d2h_bytes_per_step": int(d2h * B), "steps": e2e_steps}
+    res["frames"], res["problems"] = frames, problems
+    del fe, d_frames
+    torch.cuda.empty_cache()
+    return res
 
-    if rank == 0:
+
+def measure_latency(ctx, frames, problems):
+    """ms per frame of the synchronous host-buffer call (pl_frontend_run) at B = 1 and B = 64: H2D, all kernels, D2H, sync."""
+    import plslam_b200 as pl
+    from plslam_b200 import synth
+    out = {}
+    fe = pl.Frontend(W, H, max_batch=64, orb=ORB, lines=LINES, lm_caps=(N_PTS + 20, N_LINES + 8))
+    fe.set_camera(synth.TUM1_K, synth.TUM1_DIST)
+    for B, reps in ((1, 30), (64, 7)):
+        fr = np.ascontiguousarray(frames[:B])
+        fe.set_pose_problems(problems[:B])
+        o = fe.alloc_outputs(B)
+        t = []
+        for r in range(reps + 3):
+            t0 = time.perf_counter(); fe.run(fr, o); t.append(time.perf_counter() - t0)
+        med = float(np.median(t[3:]))
+        out[f"b{B}"] = {"ms_per_call": 1000 * med, "ms_per_frame": 1000 * med / B, "fps": B / med, "calls": reps}
+    out["api"] = "pl_frontend_run (host buffers in, host buffers out, synchronous); B<=16 uses the speculative region-growing kernel"
+    del fe
+    ctx.torch.cuda.empty_cache()
+    return out
+
+
+def cpu_baseline_single_thread(frames, problems):
+    """The oracle on ONE thread: median per-frame time of >= 50 frames after 5 warm-up frames."""
+    flags = use_native_oracle()
+    import oracle
+    oracle.build()
+    n = min(55, len(frames) - 1)
+    per = cpu_sample(frames, problems, n, 1, CONFIGS["tum"], per_frame=True)
+    per = per[5:] if len(per) > 10 else per
+    med = float(np.median(per))
+    cpu = {"value": 1.0 / med, "unit": "frames/s", "cores": 1, "kind": "port",
+           "sample": f"median of {len(per)} frames after 5 warm-up frames, one thread, CPU oracle built {flags} (restatement)",
+           "ms_per_frame_median": 1000 * med, "ms_per_frame_mean": 1000 * float(np.mean(per))}
+    try:   # cv2 single-thread cross-check recorded in the build container (the GPU box has no cv2): tools/cv2_crosscheck.py
+        cpu["cv2_check"] = json.load(open(os.path.join(ROOT, "profiles", "r02_cpu_crosscheck.json")))
+    except Exception:
+        pass
+    return cpu
+
+
+def run_ours(args):
+    ctx = Ctx()
+    name = args.config
+    res = run_config(ctx, name, args.steps, args.warmup, args.batch, full=True)
+    cfg = CONFIGS[name]
+    latency, extra, cpu = None, None, None
+    if ctx.world == 1 and name == "tum":
+        latency = measure_latency(ctx, res["frames"], res["problems"])
+    if name == "tum" and not args.no_extra:
+        extra = {}
+        for other in ("kitti", "euroc"):
+            r = run_config(ctx, other, 3, 3, None, full=False)
+            extra[other] = {"value": r["value"], "unit": "frames/s", "ms_per_step": r["ms"] / r["steps"], "frames_per_step_total": r["total"],
+                            "frames_this_rank": r["B"], "halo": r["halo"], "scaling": "strong", "frame": r["frame"], "orb": r["orb"],
+                            **({"lba_ms": r["lba_ms"], "lba_window": r["lba_window"]} if "lba_ms" in r else {})}
+    if ctx.rank == 0:
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        algo = fe.grow_bytes_per_frame() * B
-        achieved = algo / (grow_ms / 1000.0) / 1e9
-        cpu = None
-        if world == 1:      # CPU baseline: the oracle, one thread, bounded sample (rank 0, N=1 only)
-            import oracle
-            oracle.build()
-            cpu_fps, cpu_n, _ = cpu_sample(frames, problems, 6, 1)
-            cpu = {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
-                   "sample": f"{cpu_n} frames of the same workload on the CPU oracle (restatement), single thread"}
+        achieved = res["grow_bytes"] / (res["grow_ms"] / 1000.0) / 1e9
+        if ctx.world == 1 and name == "tum":      # CPU baseline: the oracle, one thread, bounded sample (rank 0, N=1 only)
+            cpu = cpu_baseline_single_thread(res["frames"], res["problems"])
+        B = res["B"]
         line = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": res["value"], "unit": "frames/s", "n_gpus": ctx.world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": res["ms"] / args.steps, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
             "dtype": "u8/i32 front-end, f32 descriptors, f64 LM", "data": "synthetic",
-            "config": {"workload": "640x480 synthetic sequence, TUM1 camera: ORB(1000) + undistort + LSD/LBD(200) extract, frame-to-frame point+line "
-                                   "matching, 2x PoseOptimization(300 pts + 80 lines)",
-                       "batch_per_gpu": B, "frame": [W, H], "orb": list(ORB), "lines": list(LINES),
-                       "l2": f"inputs {B * W * H / 1e6:.0f} MB per step exceed the 126 MB L2",
-                       "exchange": "none at 1 GPU; all-gather of [B][16] pose records per step at N>1"},
-            "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d * B), "d2h_bytes_per_step": int(d2h * B),
-                    "steps": e2e_steps},
-            "roofline": {"kernel": "k_lsd_grow", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "ms_per_launch": grow_ms,
+            "config": {"workload": cfg["workload"], "name": name, "batch_per_gpu": B, "frames_per_step_total": res["total"], "halo_frames": res["halo"],
+                       "frame": res["frame"], "orb": res["orb"], "lines": list(LINES),
+                       "l2": f"inputs {B * res['frame'][0] * res['frame'][1] / 1e6:.0f} MB per step vs the 126 MB L2; every kernel streams a different frame",
+                       "predecessor": "frame 0 of a step is matched against the last frame of the previous step (one sequence)",
+                       "exchange": "none at 1 GPU; pl_allgather_poses (NCCL) of the [frames][16] pose records per step at N>1",
+                       **({"lba_ms": res["lba_ms"], "lba_window": res["lba_window"]} if "lba_ms" in res else {})},
+            "clocks": res["clocks"], "gpu_launches": res["launches"],
+            "e2e": res["e2e"],
+            "roofline": {"kernel": "k_lsd_grow_ordered", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "ms_per_launch": res["grow_ms"],
                          "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "share_of_step": grow_ms / (ms / args.steps)},
+                         "share_of_step": res["grow_ms"] / (res["ms"] / args.steps)},
             "cpu_baseline": cpu,
         }
+        if latency:
+            line["latency"] = latency
+        if extra:
+            line["extra_configs"] = extra
         traffic_file = os.path.join(ROOT, "profiles", "traffic_k_lsd_grow.json")
         if os.path.exists(traffic_file):
             try:
                 tj = json.load(open(traffic_file))     # one `ncu --set full` capture: DRAM bytes per frame of the launch
-                line["roofline"]["traffic"] = float(tj["dram_bytes_per_frame"]) * B
-                line["roofline"]["traffic_source"] = tj.get("source")
+                if tj.get("kernel") == "k_lsd_grow_ordered":
+                    line["roofline"]["traffic"] = float(tj["dram_bytes_per_frame"]) * B
+                    line["roofline"]["traffic_source"] = tj.get("source")
             except Exception:
                 pass
         emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 _REAL_STDOUT = None
@@ -350,7 +530,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=4736, help="frames per GPU per step (148 SMs x 32 resident region-growing warps)")
+    ap.add_argument("--batch", type=int, default=None, help="tum: frames per GPU per step (default 4736 = 148 SMs x 32 resident region-growing "
+                                                            "warps); kitti / euroc: total frames per step over all ranks (default 256 / 512)")
+    ap.add_argument("--config", default="tum", choices=sorted(CONFIGS), help="BASELINE.json configuration (tum = the headline metric)")
+    ap.add_argument("--no-extra", action="store_true", help="default run: skip the short kitti / euroc runs")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":

@@ -69,6 +69,10 @@ int pl_orb_extract_batch_dev(PLOrb* h, const uint8_t* imgs, int stride, size_t f
 /* ORBextractor::mvImagePyramid[level] of frame `frame` of the LAST call, copied to host;
  * with_border != 0 adds the 19-px BORDER_REFLECT_101 frame (reference ORBextractor.cc:1107-1132). */
 int pl_orb_get_level(PLOrb* h, int frame, int level, uint8_t* out, int with_border);
+/* Capacity flag of the calls since the last check: PL_ERR_CAPACITY if a FAST cell overflowed cell_slot_cap (keypoints were
+ * dropped), else PL_OK; clears the flag.  The host-buffer entry points call it themselves; callers of *_dev call it after
+ * synchronising their stream. */
+int pl_orb_check_overflow(PLOrb* h);
 /* Debug / parity taps of the LAST call: pre-quadtree FAST candidates of (frame, level) in the
  * reference's order, coordinates relative to the level's (16,16) detection origin.  Returns count. */
 int pl_orb_debug_candidates(PLOrb* h, int frame, int level, PLKeyPoint* out, int cap);
@@ -179,6 +183,9 @@ int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int stride, size_t
                               const uint8_t* mask, void* keylines, uint8_t* desc, double* linefunc, int* n, void* stream);
 /* parity taps of the LAST call: raw LSD segments (x1,y1,x2,y2 floats, detection order), the 0.8x scaled image,
  * the LBD Sobel pair, and the seed order (pixel indices y*sw+x of the scaled image). */
+/* Capacity flags since the last check (segment_cap exceeded / region growing gave a frame up): PL_ERR_CAPACITY or PL_OK;
+ * clears them.  For callers of pl_line_extract_batch_dev, after synchronising their stream. */
+int pl_line_check_overflow(PLLine* h);
 int pl_line_debug_segments(PLLine* h, int frame, float* out, int cap);
 int pl_line_debug_scaled(PLLine* h, int frame, uint8_t* out, int* sw, int* sh);
 int pl_line_debug_sobel(PLLine* h, int frame, short* dx, short* dy);
@@ -190,7 +197,8 @@ int pl_line_debug_ctl(PLLine* h, int frame, int* out, int nwords);
  * The hot-path calls Tracking makes for one frame, chained on one stream with all intermediates in
  * HBM: ORB extract, LSD+LBD extract, point matching frame k-1 -> k (SearchForInitialization scheme, window 100,
  * ratio 0.9), line matching (SearchDouble), and two Optimizer::PoseOptimization calls on the frame's pose problem.
- * Frame 0's predecessor is the last frame of the batch.  This is bench.py's "step".                              */
+ * Frame 0's predecessor is the LAST frame of the PREVIOUS step (consecutive batches of one sequence; none before the first
+ * step), or, after pl_frontend_set_wrap(h, 1), the last frame of the same batch (closed loop).  bench.py's "step".    */
 typedef struct PLFrontendConfig {
   int width, height, max_batch;
   int orb_nfeatures; float orb_scale_factor; int orb_nlevels, orb_ini_th, orb_min_th;
@@ -209,6 +217,15 @@ int pl_frontend_set_pose_problems(PLFrontend* h, int B, const float* Tcw0, const
  * undistorted for the line extractor (Frame.cc:220-225), keypoints are undistorted for the matcher (Frame.cc:233) and the
  * grid bounds come from ComputeImageBounds; k1 == 0 or never called: no undistortion (the default). */
 int pl_frontend_set_camera(PLFrontend* h, const float* K, const float* dist5);
+/* the same upload enqueued on `stream` (NULL = the handle's stream) without synchronising: PINNED host arrays that stay
+ * valid until the stream has passed; a following pl_frontend_run_dev / submit on the same stream sees the new problems.
+ * Returns the bytes enqueued (>= 0) or an error. */
+long long pl_frontend_set_pose_problems_async(PLFrontend* h, int B, const float* Tcw0, const float* K, const int* n_points,
+                                              const float* pt_obs, const float* pt_inv_sigma2, const float* pt_Xw,
+                                              const int* n_lines, const double* line_func, const double* line_Xw, void* stream);
+/* PL_ERR_CAPACITY if any step since the last check overflowed an extractor capacity (callers of pl_frontend_run_dev) */
+int pl_frontend_check_overflow(PLFrontend* h);
+int pl_frontend_set_wrap(PLFrontend* h, int on);
 /* mvKeysUn of the last step, [B][cap_keypoints] */
 int pl_frontend_fetch_keys_un(PLFrontend* h, int B, PLKeyPoint* out);
 /* device-resident step (imgs = device pointer; NULL = frames uploaded by the last pl_frontend_run); asynchronous */
@@ -226,7 +243,8 @@ int pl_frontend_run(PLFrontend* h, const uint8_t* imgs, int stride, size_t frame
 int pl_frontend_submit(PLFrontend* h, const uint8_t* imgs, int stride, size_t frame_stride, int B, PLKeyPoint* kps,
                        uint8_t* desc, int* n, void* keylines, uint8_t* ldesc, double* linefunc, int* nl, int* pt_matches,
                        int* n_pt_matches, int* line_matches, int* n_line_matches, float* poses, int* inliers);
-/* wait until at most keep_in_flight (0 or 1) submitted steps are unfinished */
+/* wait until at most keep_in_flight (0 or 1) submitted steps are unfinished; PL_ERR_CAPACITY if a finished step overflowed
+ * a capacity (the same check pl_frontend_run and pl_frontend_fetch make) */
 int pl_frontend_wait(PLFrontend* h, int keep_in_flight);
 int pl_frontend_io_bytes(const PLFrontend* h, long long* h2d_per_frame, long long* d2h_per_frame);
 int pl_frontend_fetch(PLFrontend* h, int B, PLKeyPoint* kps, uint8_t* desc, int* n, void* keylines, uint8_t* ldesc, int* nl,
@@ -364,6 +382,22 @@ int pl_orb_fuse_search(const PLKeyPoint* keys_un, const uint8_t* desc, int n, co
                        float log_scale_factor, int n_mp, const uint8_t* skip, const float* pos, const float* normal,
                        const float* min_dist, const float* max_dist, const uint8_t* mp_desc, float th, int* best_idx,
                        int* best_dist);
+
+/* ------------------------------------------------------------------ multi-GPU exchange
+ * Frames shard across the GPUs of one box with no data-path collective; the ONE exchange is an all-gather of the per-frame
+ * pose records (64 B per frame) over NCCL / NVLink so that the rank running the sequential Tracking logic (Tracking.cc:329)
+ * sees them in frame order.  NCCL is taken from the libnccl.so.2 already in the process (no link-time dependency).
+ * pl_comm_unique_id on rank 0 -> ship the 128 bytes to every rank (MPI / torch.distributed / a file) -> pl_comm_create on all. */
+typedef struct PLComm PLComm;
+int pl_comm_unique_id(void* id128);
+int pl_comm_create(const void* id128, int nranks, int rank, PLComm** out);
+void pl_comm_destroy(PLComm* c);
+int pl_nccl_version(void);
+/* every rank contributes floats_per_rank floats (its block of [frames][16] poses, padded to the common block size);
+ * recv_dev = [nranks][floats_per_rank] on every rank; asynchronous on `stream`. */
+int pl_allgather_poses(PLComm* c, const float* send_dev, float* recv_dev, size_t floats_per_rank, void* stream);
+/* the same on a communicator the host already owns (ncclComm_t passed as void*) */
+int pl_allgather_poses_nccl(void* nccl_comm, const float* send_dev, float* recv_dev, size_t floats_per_rank, void* stream);
 
 #ifdef __cplusplus
 }

@@ -435,6 +435,41 @@ class Frontend:
         self._problems = (T0, K, npt, obs, w, X, nln, lf, lX)
         check(lib().pl_frontend_set_pose_problems(self._h, B, _p(T0), _p(K), _p(npt), _p(obs), _p(w), _p(X), _p(nln), _p(lf), _p(lX)))
 
+    def set_wrap(self, on=True):
+        """Frame 0 is matched against the last frame of the SAME batch (closed loop) instead of the previous step's last frame."""
+        lib().pl_frontend_set_wrap.argtypes = [vp, C.c_int]
+        check(lib().pl_frontend_set_wrap(self._h, int(on)))
+
+    def pack_pose_problems(self, problems, pinned=True):
+        """Pack the batch's pose problems into (pinned) host arrays for upload_pose_problems()."""
+        import torch
+        B, cp, cl = len(problems), self.cap_points, self.cap_lines
+        shapes = [((B, 16), np.float32), ((B, 4), np.float32), ((B,), np.int32), ((B, cp, 2), np.float32), ((B, cp), np.float32),
+                  ((B, cp, 3), np.float32), ((B,), np.int32), ((B, cl, 3), np.float64), ((B, cl, 6), np.float64)]
+        arrs, keep = [], []
+        for shp, dt in shapes:
+            nbytes = int(np.prod(shp)) * np.dtype(dt).itemsize
+            t = torch.zeros(max(nbytes, 1), dtype=torch.uint8, pin_memory=pinned)
+            keep.append(t)
+            arrs.append(t.numpy()[:nbytes].view(dt).reshape(shp))
+        T0, K, npt, obs, w, X, nln, lf, lX = arrs
+        for b, p in enumerate(problems):
+            n, m = len(p["pt_obs"]), len(p["line_func"])
+            assert n <= cp and m <= cl
+            T0[b] = p["Tcw0"].ravel(); K[b] = p["K"]; npt[b] = n; nln[b] = m
+            obs[b, :n] = p["pt_obs"]; w[b, :n] = p["pt_inv_sigma2"]; X[b, :n] = p["pt_Xw"]
+            lf[b, :m] = p["line_func"]; lX[b, :m] = p["line_Xw"]
+        self._packed = (arrs, keep, B)
+        return self._packed
+
+    def upload_pose_problems(self, stream=None):
+        """Enqueue the upload of the packed problems (no synchronisation); returns the bytes enqueued."""
+        arrs, _, B = self._packed
+        f = lib().pl_frontend_set_pose_problems_async
+        f.argtypes = [vp, C.c_int] + [vp] * 9 + [vp]
+        f.restype = C.c_longlong
+        return check(f(self._h, B, *[_p(a) for a in arrs], stream))
+
     def set_camera(self, K, distCoef):
         """mK / mDistCoef of the sequence: with k1 != 0 the step undistorts frames (for lines) and keypoints (for matching)."""
         K = _f32(K); D = _f32(distCoef)

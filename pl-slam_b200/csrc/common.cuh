@@ -4,13 +4,14 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <atomic>
 #include "../../include/plslam_b200.h"
 
 namespace pl {
 
 void set_error(const char* fmt, ...);
-extern unsigned long long g_launches;  // kernels launched by this library
-inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
+extern std::atomic<unsigned long long> g_launches;  // kernels launched by this library (any thread)
+inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 #define PL_CUDA(expr)                                                                       \
   do {                                                                                      \

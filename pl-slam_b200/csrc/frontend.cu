@@ -14,12 +14,11 @@
 #include <string.h>
 
 namespace pl {
-__global__ void k_prev_matched_init(const PLKeyPoint* __restrict__ kps, const int* __restrict__ n, int cap, int B,
+__global__ void k_prev_matched_init(const PLKeyPoint* __restrict__ kps_prev, const int* __restrict__ n_prev, int cap, int B,
                                     float* __restrict__ pm) {
-  // vbPrevMatched[i] = F1.mvKeysUn[i].pt with F1 = frame (b-1+B)%B
+  // vbPrevMatched[i] = F1.mvKeysUn[i].pt with F1 = the predecessor of frame b = slot b of the (B+1)-slot arrays
   const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int pb = (b + B - 1) % B;
-  if (i < n[pb]) { pm[((long long)b * cap + i) * 2] = kps[(long long)pb * cap + i].x; pm[((long long)b * cap + i) * 2 + 1] = kps[(long long)pb * cap + i].y; }
+  if (i < n_prev[b]) { pm[((long long)b * cap + i) * 2] = kps_prev[(long long)b * cap + i].x; pm[((long long)b * cap + i) * 2 + 1] = kps_prev[(long long)b * cap + i].y; }
 }
 }  // namespace pl
 using namespace pl;
@@ -59,6 +58,7 @@ struct PLFrontend {
   cudaEvent_t evStep[2] = {nullptr, nullptr};   // host outputs of submit #c are complete when evStep[c & 1] fires
   int slot = 0;
   long long submitted = 0, completed = 0;
+  int wrap = 0;       // 1: frame 0 is matched against the LAST frame of the same batch (closed loop); 0: against the last frame of the previous step
 };
 
 extern "C" void pl_frontend_destroy(PLFrontend* h) {
@@ -112,8 +112,10 @@ extern "C" int pl_frontend_create(const PLFrontendConfig* cfg, PLFrontend** out)
   FE_TRY(dev_alloc(&h->d_kps_prev, cK * (B + 1))); h->d_kps = h->d_kps_prev + cK;
   FE_TRY(dev_alloc(&h->d_desc_prev, cK * 32 * (B + 1))); h->d_desc = h->d_desc_prev + cK * 32;
   FE_TRY(dev_alloc(&h->d_n_prev, B + 1)); h->d_n = h->d_n_prev + 1;
+  FE_CUDA(cudaMemset(h->d_n_prev, 0, sizeof(int) * (B + 1)));      // before the first step frame 0 has no predecessor
   FE_TRY(dev_alloc(&h->d_ldesc_prev, cL * 32 * (B + 1))); h->d_ldesc = h->d_ldesc_prev + cL * 32;
   FE_TRY(dev_alloc(&h->d_nl_prev, B + 1)); h->d_nl = h->d_nl_prev + 1;
+  FE_CUDA(cudaMemset(h->d_nl_prev, 0, sizeof(int) * (B + 1)));
   { uint8_t* p = nullptr; FE_TRY(dev_alloc(&p, cL * 68 * B)); h->d_kl = p; }
   FE_TRY(dev_alloc(&h->d_lf, cL * 3 * B));
   FE_TRY(dev_alloc(&h->d_bounds, 4)); FE_TRY(dev_alloc(&h->d_pm, cK * 2 * B)); FE_TRY(dev_alloc(&h->d_m12, cK * B));
@@ -156,6 +158,30 @@ extern "C" int pl_frontend_set_pose_problems(PLFrontend* h, int B, const float* 
   PL_CUDA(cudaStreamSynchronize(st));
   return PL_OK;
 }
+extern "C" long long pl_frontend_set_pose_problems_async(PLFrontend* h, int B, const float* Tcw0, const float* K, const int* n_points,
+                                                         const float* pt_obs, const float* pt_inv_sigma2, const float* pt_Xw,
+                                                         const int* n_lines, const double* line_func, const double* line_Xw, void* stream_) {
+  PL_ARG(h && B >= 1 && B <= h->B && Tcw0 && K && n_points && pt_obs && pt_inv_sigma2 && pt_Xw && n_lines && line_func && line_Xw);
+  const size_t cp = h->cfg.lm_cap_points, cl = h->cfg.lm_cap_lines, b = B;
+  cudaStream_t st = stream_ ? (cudaStream_t)stream_ : h->stream;
+  PL_CUDA(cudaMemcpyAsync(h->d_T0, Tcw0, 64 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_K, K, 16 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_np, n_points, 4 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_nl_lm, n_lines, 4 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_pobs, pt_obs, cp * 8 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_pw, pt_inv_sigma2, cp * 4 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_pX, pt_Xw, cp * 12 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_lfun, line_func, cl * 24 * b, cudaMemcpyHostToDevice, st));
+  PL_CUDA(cudaMemcpyAsync(h->d_lX, line_Xw, cl * 48 * b, cudaMemcpyHostToDevice, st));
+  return (long long)((64 + 16 + 4 + 4 + cp * (8 + 4 + 12) + cl * (24 + 48)) * b);
+}
+extern "C" int pl_frontend_set_wrap(PLFrontend* h, int on) { PL_ARG(h); h->wrap = on ? 1 : 0; return PL_OK; }
+extern "C" int pl_frontend_check_overflow(PLFrontend* h) {
+  PL_ARG(h);
+  int rc = pl_orb_check_overflow(h->orb);
+  const int rc2 = pl_line_check_overflow(h->line);
+  return rc ? rc : rc2;
+}
 
 // The timed device-resident step: frames already in HBM (imgs = device pointer, or NULL = the frames uploaded by the
 // last pl_frontend_run()).  Everything asynchronous on `stream` (NULL = the handle's own stream).
@@ -182,27 +208,40 @@ extern "C" int pl_frontend_run_dev(PLFrontend* h, const uint8_t* imgs, int strid
     limgs = h->d_und; lstride = h->cfg.width; lframe = fb;
   }
   if ((rc = pl_line_extract_batch_dev(h->line, limgs, lstride, lframe, B, nullptr, h->d_kl, h->d_ldesc, h->d_lf, h->d_nl, sL))) return rc;
-  PL_CUDA(cudaMemcpyAsync(h->d_ldesc_prev, h->d_ldesc + cL * 32 * (B - 1), cL * 32, cudaMemcpyDeviceToDevice, sL));
-  PL_CUDA(cudaMemcpyAsync(h->d_nl_prev, h->d_nl + (B - 1), sizeof(int), cudaMemcpyDeviceToDevice, sL));
+  // slot 0 of every feature array is "the frame before frame 0": the last frame of the PREVIOUS step (sequence replay: the
+  // copy follows the matching), or, in wrap mode, the last frame of this batch (the copy precedes the matching)
+  auto carry_lines = [&]() -> int {
+    PL_CUDA(cudaMemcpyAsync(h->d_ldesc_prev, h->d_ldesc + cL * 32 * (B - 1), cL * 32, cudaMemcpyDeviceToDevice, sL));
+    PL_CUDA(cudaMemcpyAsync(h->d_nl_prev, h->d_nl + (B - 1), sizeof(int), cudaMemcpyDeviceToDevice, sL));
+    return PL_OK;
+  };
+  if (h->wrap && (rc = carry_lines())) return rc;
   if ((rc = pl_lsd_search_double_dev(h->d_ldesc_prev, h->d_nl_prev, h->d_ldesc, h->d_nl, (int)cL, (int)cL, B, 50.f, 0.7f, 1, h->d_lm,
                                      h->d_nlm, sL))) return rc;
+  if (!h->wrap && (rc = carry_lines())) return rc;
   // --- ORB chain (slot 0 <- frame B-1 so that frame b's predecessor is slot b, a plain offset)
   if ((rc = pl_orb_extract_batch_dev(h->orb, imgs, stride, frame_stride, B, h->d_kps, h->d_desc, h->d_n, st))) return rc;
-  PL_CUDA(cudaMemcpyAsync(h->d_kps_prev, h->d_kps + cK * (B - 1), cK * sizeof(PLKeyPoint), cudaMemcpyDeviceToDevice, st));
-  PL_CUDA(cudaMemcpyAsync(h->d_desc_prev, h->d_desc + cK * 32 * (B - 1), cK * 32, cudaMemcpyDeviceToDevice, st));
-  PL_CUDA(cudaMemcpyAsync(h->d_n_prev, h->d_n + (B - 1), sizeof(int), cudaMemcpyDeviceToDevice, st));
   // mvKeysUn: the matcher works on undistorted keypoints (aliases of the raw ones without a distorting camera)
   const PLKeyPoint *ku_prev = h->d_kps_prev, *ku = h->d_kps;
+  PLKeyPoint* kudst = nullptr;
   if (h->und) {
-    PLKeyPoint* dst = h->d_kpsu_prev + cK;
-    if ((rc = pl_undistort_keypoints_dev(h->und, h->d_kps, h->d_n, (int)cK, B, dst, st))) return rc;
-    PL_CUDA(cudaMemcpyAsync(h->d_kpsu_prev, dst + cK * (B - 1), cK * sizeof(PLKeyPoint), cudaMemcpyDeviceToDevice, st));
-    ku_prev = h->d_kpsu_prev; ku = dst;
+    kudst = h->d_kpsu_prev + cK;
+    if ((rc = pl_undistort_keypoints_dev(h->und, h->d_kps, h->d_n, (int)cK, B, kudst, st))) return rc;
+    ku_prev = h->d_kpsu_prev; ku = kudst;
   }
-  k_prev_matched_init<<<dim3((unsigned)((cK + 127) / 128), B), 128, 0, st>>>(ku, h->d_n, (int)cK, B, h->d_pm);
+  auto carry_points = [&]() -> int {
+    PL_CUDA(cudaMemcpyAsync(h->d_kps_prev, h->d_kps + cK * (B - 1), cK * sizeof(PLKeyPoint), cudaMemcpyDeviceToDevice, st));
+    PL_CUDA(cudaMemcpyAsync(h->d_desc_prev, h->d_desc + cK * 32 * (B - 1), cK * 32, cudaMemcpyDeviceToDevice, st));
+    PL_CUDA(cudaMemcpyAsync(h->d_n_prev, h->d_n + (B - 1), sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (kudst) PL_CUDA(cudaMemcpyAsync(h->d_kpsu_prev, kudst + cK * (B - 1), cK * sizeof(PLKeyPoint), cudaMemcpyDeviceToDevice, st));
+    return PL_OK;
+  };
+  if (h->wrap && (rc = carry_points())) return rc;
+  k_prev_matched_init<<<dim3((unsigned)((cK + 127) / 128), B), 128, 0, st>>>(ku_prev, h->d_n_prev, (int)cK, B, h->d_pm);
   PL_LAUNCH_CHECK();
   if ((rc = pl_orb_search_for_initialization_dev(ku_prev, h->d_desc_prev, h->d_n_prev, ku, h->d_desc, h->d_n, (int)cK, B,
                                                  h->d_bounds, h->d_pm, h->d_m12, h->d_nm, 100, 0.9f, 1, h->d_scr, st))) return rc;
+  if (!h->wrap && (rc = carry_points())) return rc;
   // --- pose optimisations: TrackWithMotionModel (Tracking.cc:1372) and TrackLocalMapWithLines (:1503)
   for (int call = 0; call < 2; call++)
     if ((rc = pl_pose_optimization_dev(0, B, h->d_T0, h->d_K, h->d_np, (int)cp, h->d_pobs, h->d_pw, h->d_pX, h->d_nl_lm, (int)cl,
@@ -276,7 +315,7 @@ extern "C" int pl_frontend_run(PLFrontend* h, const uint8_t* imgs, int stride, s
   PL_CUDA(cudaMemcpyAsync(poses, h->d_Tout, 64 * b * 2, cudaMemcpyDeviceToHost, st));
   PL_CUDA(cudaMemcpyAsync(inliers, h->d_inl, 4 * b * 2, cudaMemcpyDeviceToHost, st));
   PL_CUDA(cudaStreamSynchronize(st));
-  return PL_OK;
+  return pl_frontend_check_overflow(h);    // a truncated frame is an error here, not a sticky flag for a later call
 }
 
 
@@ -295,11 +334,13 @@ static size_t fe_out_bytes(const PLFrontend* h, int B, size_t off[14]) {
 }
 extern "C" int pl_frontend_wait(PLFrontend* h, int keep_in_flight) {
   PL_ARG(h && keep_in_flight >= 0 && keep_in_flight <= 1);
+  bool finished = false;
   while (h->submitted - h->completed > keep_in_flight) {      // steps complete in submission order
     PL_CUDA(cudaEventSynchronize(h->evStep[h->completed & 1]));
     h->completed++;
+    finished = true;
   }
-  return PL_OK;
+  return finished ? pl_frontend_check_overflow(h) : PL_OK;
 }
 extern "C" int pl_frontend_submit(PLFrontend* h, const uint8_t* imgs, int stride, size_t frame_stride, int B, PLKeyPoint* kps,
                                   uint8_t* desc, int* n, void* keylines, uint8_t* ldesc, double* linefunc, int* nl,
@@ -385,7 +426,7 @@ extern "C" int pl_frontend_fetch(PLFrontend* h, int B, PLKeyPoint* kps, uint8_t*
   if (n_line_matches) PL_CUDA(cudaMemcpy(n_line_matches, h->d_nlm, b * 4, cudaMemcpyDeviceToHost));
   if (poses) PL_CUDA(cudaMemcpy(poses, h->d_Tout, 64 * b * 2, cudaMemcpyDeviceToHost));
   if (inliers) PL_CUDA(cudaMemcpy(inliers, h->d_inl, 4 * b * 2, cudaMemcpyDeviceToHost));
-  return PL_OK;
+  return pl_frontend_check_overflow(h);
 }
 
 // hooks used by bench.py: timing of the dominant kernel and a device-to-device copy of the pose records that the

@@ -1039,6 +1039,21 @@ extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int str
   return PL_OK;
 }
 
+// capacity flags of the calls since the last check (segment_cap exceeded, or the region growing gave a frame up);
+// the *_dev entry points are asynchronous and never look at them: their callers do, after synchronising
+extern "C" int pl_line_check_overflow(PLLine* h) {
+  PL_ARG(h);
+  int ov = 0;
+  PL_CUDA(cudaMemcpy(&ov, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
+  if (ov) {
+    cudaMemset(h->d_overflow, 0, sizeof(int));
+    if (ov & 1) set_error("LSD produced more than segment_cap=%d segments", h->P.seg_cap);
+    else set_error("LSD region growing gave a frame up (list pool of %d words exhausted, or watchdog): see pl_line_debug_ctl", h->GP.pool_cap);
+    return PL_ERR_CAPACITY;
+  }
+  return PL_OK;
+}
+
 static int line_staging(PLLine* h) {
   if (h->d_img) return PL_OK;
   const size_t B = h->cfg.max_batch;
@@ -1069,15 +1084,7 @@ extern "C" int pl_line_extract_batch(PLLine* h, const uint8_t* imgs, int stride,
   PL_CUDA(cudaMemcpyAsync(linefunc, h->d_lf, cap * B * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   PL_CUDA(cudaMemcpyAsync(n, h->d_nl, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   PL_CUDA(cudaStreamSynchronize(h->stream));
-  int ov = 0;
-  PL_CUDA(cudaMemcpy(&ov, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
-  if (ov) {
-    cudaMemset(h->d_overflow, 0, sizeof(int));
-    if (ov & 1) set_error("LSD produced more than segment_cap=%d segments", h->P.seg_cap);
-    else set_error("LSD region growing gave a frame up (list pool of %d words exhausted, or watchdog): see pl_line_debug_ctl", h->GP.pool_cap);
-    return PL_ERR_CAPACITY;
-  }
-  return PL_OK;
+  return pl_line_check_overflow(h);
 }
 
 extern "C" int pl_line_extract(PLLine* h, const uint8_t* img, int stride, const uint8_t* mask, void* keylines,

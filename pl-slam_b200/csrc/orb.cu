@@ -916,7 +916,8 @@ extern "C" int pl_orb_extract_batch_dev(PLOrb* h, const uint8_t* imgs, int strid
   return PL_OK;
 }
 
-static int orb_check_overflow(PLOrb* h) {
+extern "C" int pl_orb_check_overflow(PLOrb* h) {
+  PL_ARG(h);
   int ov = 0;
   PL_CUDA(cudaMemcpy(&ov, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
   if (ov) {
@@ -956,7 +957,7 @@ extern "C" int pl_orb_extract_batch(PLOrb* h, const uint8_t* imgs, int stride, s
   PL_CUDA(cudaMemcpyAsync(desc, h->d_desc, cap * B * 32, cudaMemcpyDeviceToHost, h->stream));
   PL_CUDA(cudaMemcpyAsync(n, h->d_n, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   PL_CUDA(cudaStreamSynchronize(h->stream));
-  return orb_check_overflow(h);
+  return pl_orb_check_overflow(h);
 }
 
 extern "C" int pl_orb_extract(PLOrb* h, const uint8_t* img, int stride, PLKeyPoint* kps, uint8_t* desc, int* n) {

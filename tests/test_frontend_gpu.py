@@ -14,6 +14,7 @@ def test_frontend_batch_matches_oracle():
     frames = synth.synth_sequence(B, 640, 480, seed=4)
     problems = [synth.synth_pose_problem(50 + k) for k in range(B)]
     fe = pl.Frontend(640, 480, max_batch=B, lm_caps=(320, 88))
+    fe.set_wrap(True)                 # frame 0 against frame B-1 of the same batch (closed loop)
     fe.set_pose_problems(problems)
     out = fe.run(frames)
     o = oracle.OrbOracle(1000, 1.2, 8, 20, 7)
@@ -59,6 +60,7 @@ def test_frontend_with_distorting_camera():
     frames = synth.synth_sequence(B, 640, 480, seed=6)
     problems = [synth.synth_pose_problem(70 + k) for k in range(B)]
     fe = pl.Frontend(640, 480, max_batch=B, lm_caps=(320, 88))
+    fe.set_wrap(True)
     fe.set_pose_problems(problems)
     fe.set_camera(K, D)
     out = fe.run(frames)
@@ -85,7 +87,7 @@ def test_frontend_with_distorting_camera():
     # a camera without distortion is the default path
     fe.set_camera(K, (0, 0, 0, 0, 0))
     out0 = fe.run(frames)
-    ref = pl.Frontend(640, 480, max_batch=B, lm_caps=(320, 88)); ref.set_pose_problems(problems)
+    ref = pl.Frontend(640, 480, max_batch=B, lm_caps=(320, 88)); ref.set_wrap(True); ref.set_pose_problems(problems)
     out1 = ref.run(frames)
     for k in ("kps", "desc", "n", "keylines", "ldesc", "nl", "pt_matches", "n_pt_matches", "line_matches", "n_line_matches"):
         assert out0[k].tobytes() == out1[k].tobytes(), k
@@ -130,10 +132,10 @@ def test_frontend_large_batch_properties():
     B0, R = 3, 32
     base = synth.synth_sequence(B0, 640, 480, seed=8)
     problems = [synth.synth_pose_problem(80 + k) for k in range(B0)]
-    small = pl.Frontend(640, 480, max_batch=B0, lm_caps=(320, 88)); small.set_pose_problems(problems)
+    small = pl.Frontend(640, 480, max_batch=B0, lm_caps=(320, 88)); small.set_wrap(True); small.set_pose_problems(problems)
     small.set_camera(synth.TUM1_K, synth.TUM1_DIST)
     ref = small.run(base)
-    big = pl.Frontend(640, 480, max_batch=B0 * R, lm_caps=(320, 88)); big.set_pose_problems(problems * R)
+    big = pl.Frontend(640, 480, max_batch=B0 * R, lm_caps=(320, 88)); big.set_wrap(True); big.set_pose_problems(problems * R)
     big.set_camera(synth.TUM1_K, synth.TUM1_DIST)
     out = big.run(np.tile(base, (R, 1, 1)))
     for r in range(R):
@@ -168,7 +170,7 @@ def test_frontend_batch_with_featureless_frame():
     base = synth.synth_sequence(2, 640, 480, seed=12)
     frames = np.stack([base[0], np.full((480, 640), 93, np.uint8), base[1]])
     problems = [synth.synth_pose_problem(120 + k) for k in range(3)]
-    fe = pl.Frontend(640, 480, max_batch=3, lm_caps=(320, 88)); fe.set_pose_problems(problems)
+    fe = pl.Frontend(640, 480, max_batch=3, lm_caps=(320, 88)); fe.set_wrap(True); fe.set_pose_problems(problems)
     out = fe.run(frames)
     o = oracle.OrbOracle(1000, 1.2, 8, 20, 7)
     assert out["n"][1] == 0 and out["nl"][1] == 1 and not out["keylines"][1, 0].tobytes().strip(b"\0")
@@ -187,3 +189,28 @@ def test_frontend_batch_with_featureless_frame():
         p = problems[b]
         on, oT, *_ = oracle.pose_optimization(0, p["Tcw0"], p["K"], p["pt_obs"], p["pt_inv_sigma2"], p["pt_Xw"], p["line_func"], p["line_Xw"])
         assert out["inliers"][0, b] == on
+
+
+def test_frontend_consecutive_steps_are_one_sequence():
+    """Default (no wrap): the steps are consecutive batches of ONE sequence - frame 0 of a step is matched against the last
+    frame of the previous step, and the very first frame has no predecessor (no matches, PL_OK)."""
+    B = 2
+    seq = synth.synth_sequence(2 * B, 640, 480, seed=9)
+    problems = [synth.synth_pose_problem(90 + k) for k in range(B)]
+    fe = pl.Frontend(640, 480, max_batch=B, lm_caps=(320, 88)); fe.set_pose_problems(problems)
+    o = oracle.OrbOracle(1000, 1.2, 8, 20, 7)
+    feats = [o.extract(f) for f in seq]
+    lfeat = [oracle.line_extract(f)[1] for f in seq]
+    outs = [{k: v.copy() for k, v in fe.run(seq[s * B:(s + 1) * B]).items()} for s in range(2)]
+    assert outs[0]["n_pt_matches"][0] == 0 and outs[0]["n_line_matches"][0] == 0
+    for s in range(2):
+        for b in range(B):
+            g = s * B + b
+            if g == 0:
+                continue
+            pk, pd = feats[g - 1]; ck, cd = feats[g]
+            pm = np.stack([pk["x"], pk["y"]], 1).astype(np.float32)
+            onm, om, _ = oracle.search_for_initialization(pk, pd, ck, cd, [0, 0, 640, 480], pm, 100, 0.9, True)
+            assert outs[s]["n_pt_matches"][b] == onm and np.array_equal(outs[s]["pt_matches"][b, :len(pk)], om), (s, b)
+            onl, olm = oracle.search_double(lfeat[g - 1], lfeat[g], 0.7)
+            assert outs[s]["n_line_matches"][b] == onl and np.array_equal(outs[s]["line_matches"][b, :len(lfeat[g - 1])], olm), (s, b)

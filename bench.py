@@ -419,7 +419,7 @@ def measure_latency(ctx, frames, problems):
             t0 = time.perf_counter(); fe.run(fr, o); t.append(time.perf_counter() - t0)
         med = float(np.median(t[3:]))
         out[f"b{B}"] = {"ms_per_call": 1000 * med, "ms_per_frame": 1000 * med / B, "fps": B / med, "calls": reps}
-    out["api"] = "pl_frontend_run (host buffers in, host buffers out, synchronous); B<=16 uses the speculative region-growing kernel"
+    out["api"] = "pl_frontend_run (host buffers in, host buffers out, synchronous)"
     del fe
     ctx.torch.cuda.empty_cache()
     return out

@@ -851,7 +851,10 @@ struct PLLine {
   lg::Params GP;
   int grow_warps_target = 148 * 16;   // warps the grow kernel spreads over the GPU when the batch is small (env PLSLAM_LSD_GROW_WARPS)
   int grow_wpf_max = 64;              // at most this many warps on one frame (env PLSLAM_LSD_GROW_WPF)
-  int grow_spec_max_batch = 16;        // batches up to this size use the speculative kernel, larger ones the ordered one (env PLSLAM_LSD_GROW_SPEC_MAXB)
+  // batches up to this size use the speculative kernel, larger ones the ordered one (env PLSLAM_LSD_GROW_SPEC_MAXB).  Default 0:
+  // measured on B200 the speculative kernel wins on frames made of many small regions (single raw frame 51 vs 95 ms)
+  // and loses on frames whose long, refine-heavy regions form a dependency chain (single undistorted TUM frame: 1.4x slower)
+  int grow_spec_max_batch = 0;
   size_t lane_warps = 0;              // lane buffers are allocated for this many warps
   int4* d_rec = nullptr; int* d_sq = nullptr;
   unsigned *d_st = nullptr, *d_pool = nullptr, *d_lanebuf = nullptr; int* d_ctl = nullptr; double* d_wtab = nullptr;

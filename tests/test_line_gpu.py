@@ -104,6 +104,7 @@ def _last_segments():
 def test_grow_warps_per_frame_do_not_change_the_result(monkeypatch, warps, wpf):
     """The speculative region growing must give the sequential result whatever the number of warps (= regions in flight)
     serving a frame: 1 warp (32 tasks in flight) ... 256 warps (8192 tasks in flight, heavy stealing / re-execution)."""
+    monkeypatch.setenv("PLSLAM_LSD_GROW_SPEC_MAXB", "64")        # the speculative kernel (the default is the ordered one)
     monkeypatch.setenv("PLSLAM_LSD_GROW_WARPS", str(warps))
     monkeypatch.setenv("PLSLAM_LSD_GROW_WPF", str(wpf))
     K, D = synth.TUM1_K, synth.TUM1_DIST
@@ -116,8 +117,10 @@ def test_grow_warps_per_frame_do_not_change_the_result(monkeypatch, warps, wpf):
     assert kl.tobytes() == okl.tobytes() and np.array_equal(desc, odesc)
 
 
-def test_grow_batches_of_odd_sizes():
-    """Batches that do not divide the warp budget: 3 and 37 frames, each frame against the oracle."""
+@pytest.mark.parametrize("spec_maxb", [0, 64])
+def test_grow_batches_of_odd_sizes(monkeypatch, spec_maxb):
+    """Batches that do not divide the warp budget: 3 and 37 frames, each frame against the oracle (both growing kernels)."""
+    monkeypatch.setenv("PLSLAM_LSD_GROW_SPEC_MAXB", str(spec_maxb))
     seq = synth.synth_sequence(37, 640, 480, seed=5)
     ex = pl.LINEextractor(1, 1.2, 200, 0.0, max_batch=37)
     for B in (3, 37):

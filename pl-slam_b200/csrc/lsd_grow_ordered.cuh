@@ -25,6 +25,7 @@ constexpr int kUsedO = 0;
 
 struct Ctx {
   int4* REC; const int* SQ; const float2* S2; const double* wtab; unsigned* R; unsigned* ring; unsigned* mask;
+  double* red;          // shared memory, 3 x 32 doubles: the per-pixel terms of one batch, for the ordered sums
   int sw, sh;
 };
 struct RectD { double x1, y1, x2, y2, width; };
@@ -33,6 +34,23 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __device__ __forceinline__ int& own_of(const Ctx& C, int idx) { return reinterpret_cast<int*>(&C.REC[idx])[0]; }
 __device__ __forceinline__ int angle_bits(const Ctx& C, int idx) { return reinterpret_cast<const int*>(&C.REC[idx])[1]; }
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+// Three running sums advanced in LIST ORDER over one batch of up to 32 pixels.  Every lane has put its three terms into
+// shared memory; lane j < 3 then walks row j (one LDS + one DADD per pixel for the whole warp - the three chains run in
+// three lanes of the same instruction), so the order of the additions is exactly the CPU's and the cost is 2 instructions
+// per pixel.  acc lives in lanes 0..2 (acc of lane j = sum j); ordered_get() hands a finished sum to every lane.
+__device__ __forceinline__ void ordered_add3(const Ctx& C, double t0, double t1, double t2, int m, double& acc, int lane) {
+  C.red[lane] = t0; C.red[32 + lane] = t1; C.red[64 + lane] = t2;
+  __syncwarp();
+  const double* row = C.red + 32 * min(lane, 2);
+  if (m == 32) {
+#pragma unroll
+    for (int k = 0; k < 32; k++) acc += row[k];
+  } else {
+    for (int k = 0; k < m; k++) acc += row[k];
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ double ordered_get(double acc, int j) { return shfl_d(acc, j); }
 __device__ __forceinline__ double wmax_d(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -126,7 +144,7 @@ __device__ __noinline__ int region_grow_cold(const Ctx& C, unsigned seed, double
 
 // region2rect + get_theta: sums in list order (see the header), extents by exact max / min
 __device__ __noinline__ void region2rect(const Ctx& C, int n, double reg_angle, double prec, RectD& rec, int lane) {
-  double sx = 0, sy = 0, sw_ = 0;
+  double acc = 0;                       // lanes 0, 1, 2: sum x*w, sum y*w, sum w
   for (int i0 = 0; i0 < n; i0 += 32) {
     const int i = i0 + lane;
     double tx = 0, ty = 0, w = 0;
@@ -136,11 +154,11 @@ __device__ __noinline__ void region2rect(const Ctx& C, int n, double reg_angle, 
       w = __ldg(&C.wtab[__ldg(&C.SQ[py * C.sw + px])]);
       tx = (double)px * w; ty = (double)py * w;
     }
-    const int m = min(32, n - i0);
-    for (int k = 0; k < m; k++) { sx += shfl_d(tx, k); sy += shfl_d(ty, k); sw_ += shfl_d(w, k); }
+    ordered_add3(C, tx, ty, w, min(32, n - i0), acc, lane);
   }
-  const double x = sx / sw_, y = sy / sw_;
-  double Ixx = 0, Iyy = 0, Ixy = 0;
+  const double sw_ = ordered_get(acc, 2);
+  const double x = ordered_get(acc, 0) / sw_, y = ordered_get(acc, 1) / sw_;
+  acc = 0;                              // lanes 0, 1, 2: Ixx, Iyy, -Ixy  (Ixy -= t  ==  (-Ixy) += t, negated once at the end: exact)
   for (int i0 = 0; i0 < n; i0 += 32) {
     const int i = i0 + lane;
     double t1 = 0, t2 = 0, t3 = 0;
@@ -151,9 +169,9 @@ __device__ __noinline__ void region2rect(const Ctx& C, int n, double reg_angle, 
       const double dx = (double)px - x, dy = (double)py - y;
       t1 = dy * dy * w; t2 = dx * dx * w; t3 = dx * dy * w;
     }
-    const int m = min(32, n - i0);
-    for (int k = 0; k < m; k++) { Ixx += shfl_d(t1, k); Iyy += shfl_d(t2, k); Ixy -= shfl_d(t3, k); }
+    ordered_add3(C, t1, t2, t3, min(32, n - i0), acc, lane);
   }
+  const double Ixx = ordered_get(acc, 0), Iyy = ordered_get(acc, 1), Ixy = -ordered_get(acc, 2);
   const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
   double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)lg::fast_atan2_deg((float)(lambda - Ixx), (float)Ixy)
                                          : (double)lg::fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
@@ -226,7 +244,7 @@ __device__ __noinline__ bool refine(const Ctx& C, int& n, double reg_angle, doub
   const unsigned p0 = C.R[0];
   const double xc = (double)(int)(p0 & 0xffffu), yc = (double)(int)(p0 >> 16);
   const double ang_c = (double)__int_as_float(angle_bits(C, (int)(p0 >> 16) * C.sw + (int)(p0 & 0xffffu))) * kDegToRads;
-  double sum = 0, s_sum = 0;
+  double sum = 0, s_sum = 0, sacc = 0;
   int cnt = 0;
   for (int i0 = 0; i0 < n; i0 += 32) {
     const int i = i0 + lane;
@@ -245,12 +263,17 @@ __device__ __noinline__ bool refine(const Ctx& C, int& n, double reg_angle, doub
     }
     unsigned mi = __ballot_sync(0xffffffffu, in);
     cnt += __popc(mi);
-    while (mi) {                                       // the additions in list order
+    C.red[lane] = ad; C.red[32 + lane] = ad2;
+    __syncwarp();
+    const double* row = C.red + 32 * (lane & 1);       // lane 0: sum, lane 1: s_sum (the additions in list order)
+    while (mi) {
       const int k = __ffs(mi) - 1;
       mi &= mi - 1u;
-      sum += shfl_d(ad, k); s_sum += shfl_d(ad2, k);
+      sacc += row[k];
     }
+    __syncwarp();
   }
+  sum = shfl_d(sacc, 0); s_sum = shfl_d(sacc, 1);
   __syncwarp();
   const double mean_angle = sum / (double)cnt;
   const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
@@ -280,10 +303,11 @@ __global__ void __launch_bounds__(32, 32) k_lsd_grow_ordered(LineParams P, int4*
                                                              float4* __restrict__ segs, int* __restrict__ nseg, int* __restrict__ overflow, int nframes) {
   using namespace ord;
   __shared__ unsigned ring[kORing];
+  __shared__ double red[96];
   const int lane = threadIdx.x & 31;
   for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
     const Ctx C = {REC + (long long)f * P.npx, SQ + (long long)f * P.npx, seedcs + (long long)f * P.npx, wtab,
-                   reg + (long long)f * reg_stride, ring, mask + (long long)f * P.npx, P.sw, P.sh};
+                   reg + (long long)f * reg_stride, ring, mask + (long long)f * P.npx, red, P.sw, P.sh};
     const unsigned* O = order + (long long)f * P.npx;
     float4* S = segs + (long long)f * P.seg_cap;
     const int n = ndef[f];

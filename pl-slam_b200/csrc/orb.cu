@@ -16,6 +16,7 @@
 //  * Arithmetic that feeds a rounding (fastAtan2, rBRIEF rotation) uses explicit __f*_rn intrinsics: no FMA.
 
 #include "common.cuh"
+#include "tma.cuh"
 #include <math.h>
 #include <vector>
 #include <algorithm>
@@ -137,64 +138,115 @@ __host__ __device__ __forceinline__ int fast_score_px(const uint8_t* p, int pitc
   return s >= minTh ? s : 0;
 }
 
-__global__ void __launch_bounds__(128) k_fast_cells(OrbParams P, const CellInfo* __restrict__ cells,
+// Two horizontally adjacent pixels per thread in the two 16-bit halves of a register (s16x2).  The 16 circle differences
+// d[k] = ring[k] - centre are signed 9-bit values: they fit a half exactly, and sm_100a has single-instruction packed 16-bit
+// add and 3-input min / max (VIADD.16x2, VIMNMX3.S16x2 - the DPX family), so
+//   m9[k] = min(d[k .. k+8]) = min3(m3[k], m3[k+3], m3[k+6]),  m3[k] = min3(d[k], d[k+1], d[k+2])      (32 instructions)
+//   M9[k] = max(d[k .. k+8]) likewise                                                                  (32 instructions)
+//   bright arcs: best = max_k m9[k];  dark arcs: max_k min(-d[..]) = -min_k M9[k]                       (16 instructions)
+// for BOTH pixels: no negated copy of the ring, no quick-reject pass, no compaction - every pixel of the cell costs the
+// same ~85 instructions, against ~215 per surviving pixel for the scalar network (and on textured frames most pixels
+// survive the 4-point pre-test).  score = max(best, -worst) - 1, stored as 0 below minTh (see fast_score_px).
+__device__ __forceinline__ unsigned fast_score_pair(const uint8_t* p, int pitch, int minTh) {
+  auto pair = [&](int off) { return (unsigned)p[off] | ((unsigned)p[off + 1] << 16); };
+  const unsigned negv = __vneg2(pair(0));
+  unsigned d[16];
+  d[0] = pair(3 * pitch); d[1] = pair(3 * pitch + 1); d[2] = pair(2 * pitch + 2); d[3] = pair(pitch + 3);
+  d[4] = pair(3); d[5] = pair(-pitch + 3); d[6] = pair(-2 * pitch + 2); d[7] = pair(-3 * pitch + 1);
+  d[8] = pair(-3 * pitch); d[9] = pair(-3 * pitch - 1); d[10] = pair(-2 * pitch - 2); d[11] = pair(-pitch - 3);
+  d[12] = pair(-3); d[13] = pair(pitch - 3); d[14] = pair(2 * pitch - 2); d[15] = pair(3 * pitch - 1);
+#pragma unroll
+  for (int k = 0; k < 16; k++) d[k] = __vadd2(d[k], negv);           // ring - centre, per half
+  unsigned m3[16], M3[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    m3[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    M3[k] = __vimax3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+  }
+  unsigned best = 0x80008000u, worst = 0x7fff7fffu;
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    const unsigned a0 = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+    const unsigned a1 = __vimin3_s16x2(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
+    const unsigned b0 = __vimax3_s16x2(M3[k], M3[(k + 3) & 15], M3[(k + 6) & 15]);
+    const unsigned b1 = __vimax3_s16x2(M3[k + 1], M3[(k + 4) & 15], M3[(k + 7) & 15]);
+    best = __vimax3_s16x2(best, a0, a1);
+    worst = __vimin3_s16x2(worst, b0, b1);
+  }
+  // per half: score = max(best, -worst) - 1 (the negation is a separate scalar subtraction: see the note in fast_score_px)
+  unsigned out = 0;
+#pragma unroll
+  for (int hv = 0; hv < 2; hv++) {
+    const int bb = (int)(short)(best >> (16 * hv)), ww = (int)(short)(worst >> (16 * hv));
+    const int nw = 0 - ww;
+    const int sc = (bb > nw ? bb : nw) - 1;
+    out |= (unsigned)(sc >= minTh ? sc : 0) << (16 * hv);
+  }
+  return out;
+}
+
+// One CTA per cell.  The cell window (cell + 3 px on every side) is staged in shared memory by the TMA engine: one bulk
+// asynchronous copy per window row (cp.async.bulk -> UBLKCP; 16-byte granular, so a row is fetched from the 16-byte boundary
+// below the window's left edge), all rows completing ONE mbarrier; the score plane is cleared while the copies fly.  Used when
+// base and pitch of the source are multiples of 16 bytes (always for the pyramid levels, for level 0 when the caller's buffer
+// allows: `bulk` bit per level); otherwise a plain strided copy.  (Why rows and not one tensor tile: tma.cuh.)
+constexpr int kFastPitchMax = 96;     // kMaxWin + 15 rounded up to a multiple of 16
+
+__global__ void __launch_bounds__(128) k_fast_cells(OrbParams P, unsigned bulk, const CellInfo* __restrict__ cells,
                                                     const uint8_t* __restrict__ img0, int stride0, long long frame0,
                                                     const uint8_t* __restrict__ pyr, uint32_t* __restrict__ slots,
                                                     int* __restrict__ counts, int* __restrict__ overflow) {
-  constexpr int WP = kMaxWin + 4;
-  __shared__ uint8_t win[kMaxWin * WP];
-  __shared__ uint8_t sc[kMaxWin * WP];
+  __shared__ __align__(128) uint8_t win_s[kMaxWin * kFastPitchMax];
+  __shared__ __align__(16) uint8_t sc[kMaxWin * kFastPitchMax];
+  __shared__ __align__(8) unsigned long long mbar;
   __shared__ int wsum[4];
   const int cell = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
   CellInfo c = cells[cell];
   const LevelInfo& L = P.lv[c.level];
+  const int w = c.x1 - c.x0, h = c.y1 - c.y0;
   const uint8_t* img;
   int pitch;
   if (c.level == 0) { img = img0 + (long long)frame * frame0; pitch = stride0; }
   else { img = pyr + (long long)frame * P.pyr_frame + L.off; pitch = L.pitch; }
-  const int w = c.x1 - c.x0, h = c.y1 - c.y0;
-  {
+  constexpr int WP = kFastPitchMax;     // shared-memory pitch of the window and of the score plane
+  const uint8_t* win = win_s;
+  if ((bulk >> c.level) & 1u) {
+    const int x0a = c.x0 & ~15, rowbytes = ((c.x1 + 15) & ~15) - x0a;     // <= pitch - x0a: x1 <= width <= pitch, both multiples of 16
+    win = win_s + (c.x0 - x0a);
+    if (tid == 0) {
+      tma::mbar_init(&mbar, 1);
+      tma::fence_mbar_init();
+      tma::mbar_expect_tx(&mbar, (unsigned)(rowbytes * h));
+    }
+    __syncthreads();
+    if (tid < h) tma::bulk_load(win_s + tid * WP, img + (long long)(c.y0 + tid) * pitch + x0a, (unsigned)rowbytes, &mbar);
+    for (int i = tid; i < (WP * h + 3) / 4; i += 128) reinterpret_cast<unsigned*>(sc)[i] = 0u;   // overlaps the copies
+    tma::mbar_wait(&mbar, 0);
+  } else {
     const float inv_w = 1.0f / (float)w;               // i / w for i < 72*72 without an integer division
     for (int i = tid; i < w * h; i += 128) {
       const int y = __float2int_rz(__fmul_rn((float)i + 0.5f, inv_w)), x = i - y * w;
-      win[y * WP + x] = img[(long long)(c.y0 + y) * pitch + c.x0 + x];
-      sc[y * WP + x] = 0;
+      win_s[y * WP + x] = img[(long long)(c.y0 + y) * pitch + c.x0 + x];
     }
+    for (int i = tid; i < (WP * h + 3) / 4; i += 128) reinterpret_cast<unsigned*>(sc)[i] = 0u;
   }
   __syncthreads();
   const int dw = w - 6, dh = h - 6;  // detection area
   const int npx = (dw > 0 && dh > 0) ? dw * dh : 0;
   const float inv_dw = dw > 0 ? 1.0f / (float)dw : 0.f;   // i / dw for i < 4096 without an integer division
-  // Phase A: 4-pixel quick reject for every pixel; survivors are compacted into a list so that the expensive arc
-  // evaluation runs on full warps instead of a few divergent lanes.
-  __shared__ unsigned short list[kMaxWin * kMaxWin];
-  __shared__ int nlist;
-  if (tid == 0) nlist = 0;
-  __syncthreads();
-  for (int i0 = 0; i0 < npx; i0 += 128) {
-    const int i = i0 + tid;
-    bool pass = false;
-    if (i < npx) {
-      const int y = __float2int_rz(__fmul_rn((float)i + 0.5f, inv_dw)), x = i - y * dw;
-      const uint8_t* p = &win[(y + 3) * WP + x + 3];
-      const int v = p[0], th = P.minTh;
-      pass = !(abs(v - p[3 * WP]) <= th && abs(v - p[-3 * WP]) <= th) && !(abs(v - p[3]) <= th && abs(v - p[-3]) <= th);
+  // scores: one thread = two adjacent pixels of a row (the second half of an odd row end is computed and dropped)
+  {
+    const int pw = (dw + 1) >> 1, npair = (dw > 0 && dh > 0) ? pw * dh : 0;
+    const float inv_pw = pw > 0 ? 1.0f / (float)pw : 0.f;
+    for (int j = tid; j < npair; j += 128) {
+      const int y = __float2int_rz(__fmul_rn((float)j + 0.5f, inv_pw)), x = 2 * (j - y * pw);
+      const unsigned s2 = fast_score_pair(&win[(y + 3) * WP + x + 3], WP, P.minTh);
+      sc[(y + 3) * WP + x + 3] = (uint8_t)(s2 & 0xffu);
+      if (x + 1 < dw) sc[(y + 3) * WP + x + 4] = (uint8_t)(s2 >> 16);
     }
-    const unsigned m = __ballot_sync(0xffffffffu, pass);
-    int base = 0;
-    if ((tid & 31) == 0 && m) base = atomicAdd(&nlist, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (pass) list[base + __popc(m & ((1u << (tid & 31)) - 1u))] = (unsigned short)i;
   }
   __syncthreads();
-  const int nl = nlist;
-  for (int j = tid; j < nl; j += 128) {
-    const int i = list[j];
-    const int y = __float2int_rz(__fmul_rn((float)i + 0.5f, inv_dw)), x = i - y * dw;
-    sc[(y + 3) * WP + x + 3] = (uint8_t)fast_score_px(&win[(y + 3) * WP + x + 3], WP, P.minTh);
-  }
-  __syncthreads();
-  // NMS flags (reuse win as flag storage: 0 none, 1 max>=minTh, 2 max>=iniTh)
+  // NMS flags (0 none, 1 max>=minTh, 2 max>=iniTh)
   int n20 = 0;
   uint8_t fl[ (kMaxWin * kMaxWin + 127) / 128 ];
   int nfl = 0;
@@ -705,6 +757,7 @@ struct PLOrb {
   long long last_frame_stride = 0;
   int last_B = 0;
   size_t quad_smem = 0;
+  unsigned fast_bulk = 0;    // levels whose FAST windows are staged by bulk copies (bit 0 = level 0, decided per call)
 };
 
 static inline int cvRoundf_h(float v) { return (int)lrintf(v); }
@@ -837,6 +890,8 @@ extern "C" int pl_orb_create(const PLOrbConfig* cfg, PLOrb** out) {
   ORB_TRY(dev_alloc(&h->d_tabs, std::max<size_t>(tabs.size(), 1)));
   if (!tabs.empty()) ORB_CUDA(cudaMemcpy(h->d_tabs, tabs.data(), tabs.size() * sizeof(short4), cudaMemcpyHostToDevice));
   ORB_TRY(dev_alloc(&h->d_pyr, (size_t)std::max<long long>(off, 256) * B));
+  // FAST windows of the pyramid levels are staged by TMA bulk copies (pitch and level offsets are multiples of 64 / 256)
+  h->fast_bulk = getenv("PLSLAM_NO_TMA") ? 0u : (((1u << nl) - 1u) & ~1u);
   ORB_TRY(dev_alloc(&h->d_blur, (size_t)boff * B));
   ORB_TRY(dev_alloc(&h->d_slots, (size_t)P.ncells * P.slotcap * B));
   ORB_TRY(dev_alloc(&h->d_counts, (size_t)P.ncells * B));
@@ -896,7 +951,10 @@ extern "C" int pl_orb_extract_batch_dev(PLOrb* h, const uint8_t* imgs, int strid
                                         D.h, h->d_tabs + D.tab_x, h->d_tabs + D.tab_y);
     PL_LAUNCH_CHECK();
   }
-  k_fast_cells<<<dim3(P.ncells, B), 128, 0, st>>>(P, h->d_cells, imgs, stride, (long long)frame_stride, h->d_pyr,
+  // level 0 is the caller's buffer: bulk copies need its base, row pitch and frame pitch to be multiples of 16 bytes
+  unsigned bulk = h->fast_bulk & ~1u;
+  if (h->fast_bulk && !(((uintptr_t)imgs | (uintptr_t)stride | (uintptr_t)frame_stride) & 15)) bulk |= 1u;
+  k_fast_cells<<<dim3(P.ncells, B), 128, 0, st>>>(P, bulk, h->d_cells, imgs, stride, (long long)frame_stride, h->d_pyr,
                                                   h->d_slots, h->d_counts, h->d_overflow);
   PL_LAUNCH_CHECK();
   k_quadtree<<<dim3(P.nlevels, B), 32, h->quad_smem, st>>>(P, h->d_slots, h->d_counts, h->d_keysA, h->d_keysB,

@@ -8,10 +8,11 @@
 //
 // Exactness of the fp64 parts (what round 1 did not have): LineSegmentDetectorImpl::region2rect / get_theta / refine sum over
 // the region IN LIST ORDER on the CPU.  The lanes load and form the per-pixel terms in parallel (32 pixels per batch), then
-// the three running sums are advanced in list order with warp shuffles - every lane carries the same sums, the order of
-// the additions is the oracle's, so the rectangle is bit-identical.  reduce_region_radius() swap-removes; the order of the
+// the three running sums are advanced in list order, one sum per lane, reading the terms from shared memory (ordered_add3) -
+// the order of the additions is the oracle's, so the rectangle is bit-identical.  reduce_region_radius() swap-removes; the order of the
 // survivors decides the order of the next sums, so it is reproduced exactly: all far flags in parallel (bit mask), then a
-// two-pointer walk over the mask that moves one survivor from the tail into every hole, as the CPU loop does.
+// hole / survivor matching (hole r below the final size <- r-th survivor of the tail, counted from the end: what the CPU's
+// swap-with-last loop leaves behind), computed with warp prefix sums over the mask words.
 #pragma once
 #include "lsd_grow_core.cuh"
 
@@ -26,7 +27,7 @@ constexpr int kUsedO = 0;
 struct Ctx {
   int4* REC; const int* SQ; const float2* S2; const double* wtab; unsigned* R; unsigned* ring; unsigned* mask;
   double* red;          // shared memory, 3 x 32 doubles: the per-pixel terms of one batch, for the ordered sums
-  int sw, sh;
+  int sw, sh, fill_off; // fill_off: scratch area inside R (beyond the largest possible region)
 };
 struct RectD { double x1, y1, x2, y2, width; };
 
@@ -196,7 +197,7 @@ __device__ __noinline__ void region2rect(const Ctx& C, int n, double reg_angle, 
 // reduce_region_radius(), one round: drop the pixels beyond radSq with the reference's swap-remove order.
 // Every pixel is tested exactly once by the CPU loop, so the removed set is "all far pixels" (released in parallel);
 // the survivors end up as: kept elements below the final size K stay, each hole below K (in increasing order) receives
-// the last kept element of the shrinking tail (in decreasing order) - the two-pointer walk below, on the bit mask.
+// the last kept element of the shrinking tail (in decreasing order); both rankings come from prefix sums over the bit mask.
 __device__ __noinline__ int reduce_round(const Ctx& C, int n, double xc, double yc, double radSq, int lane) {
   int kept = 0;
   for (int i0 = 0; i0 < n; i0 += 32) {
@@ -214,23 +215,51 @@ __device__ __noinline__ int reduce_round(const Ctx& C, int n, double xc, double 
   }
   __syncwarp();
   if (kept == n) return n;
-  if (lane == 0) {
-    int hi = n - 1;                                   // tail pointer: last position not yet consumed
-    int lo_word = 0;
-    const int K = kept;
-    // holes below K in increasing order
-    for (int w = 0; w * 32 < K; w++) {
-      unsigned holes = C.mask[w];
-      if (w * 32 + 32 > K) holes &= (1u << (K - w * 32)) - 1u;
-      while (holes) {
-        const int h = w * 32 + __ffs(holes) - 1;
-        holes &= holes - 1u;
-        while ((C.mask[hi >> 5] >> (hi & 31)) & 1u) hi--;   // skip (= remove) far elements at the tail
-        C.R[h] = C.R[hi];
-        hi--;
-      }
+  // survivors: kept elements below K = kept stay; hole number r below K (increasing position) receives kept element
+  // number r of the tail [K, n) counted FROM THE END - exactly what the CPU's swap-with-last loop leaves behind.
+  // Both rankings are prefix sums over the mask words: a warp scan per 32 words, no serial walk over the pixels.
+  const int K = kept, nw = (n + 31) >> 5, wK = K >> 5;
+  unsigned* fill = C.R + C.fill_off;                 // scratch: position of the r-th kept tail element from the end
+  int ntail = 0;                                     // kept elements in [K, n)
+  for (int w0 = wK; w0 < nw; w0 += 32) {
+    const int w = w0 + lane;
+    unsigned km = 0u;
+    if (w < nw) {
+      km = ~C.mask[w];
+      if (w == wK) km &= ~((1u << (K & 31)) - 1u);                       // positions >= K only
+      if (w == nw - 1 && (n & 31)) km &= (1u << (n & 31)) - 1u;          // positions < n only
     }
-    (void)lo_word;
+    int c = __popc(km), incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    int rank = ntail + incl - c;                     // rank from the START of the tail of this word's first kept element
+    while (km) {
+      const int bit = __ffs(km) - 1;
+      km &= km - 1u;
+      fill[rank++] = (unsigned)(w * 32 + bit);
+    }
+    ntail += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncwarp();
+  int nholes = 0;
+  for (int w0 = 0; w0 * 32 < K; w0 += 32) {
+    const int w = w0 + lane;
+    unsigned hm = 0u;
+    if (w * 32 < K) {
+      hm = C.mask[w];
+      if (w == wK) hm &= (1u << (K & 31)) - 1u;                          // holes below K only
+    }
+    int c = __popc(hm), incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    int r = nholes + incl - c;
+    while (hm) {
+      const int bit = __ffs(hm) - 1;
+      hm &= hm - 1u;
+      C.R[w * 32 + bit] = C.R[fill[ntail - 1 - r]];  // r-th hole <- r-th kept tail element from the end
+      r++;
+    }
+    nholes += __shfl_sync(0xffffffffu, incl, 31);
   }
   __syncwarp();
   return kept;
@@ -307,7 +336,7 @@ __global__ void __launch_bounds__(32, 32) k_lsd_grow_ordered(LineParams P, int4*
   const int lane = threadIdx.x & 31;
   for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
     const Ctx C = {REC + (long long)f * P.npx, SQ + (long long)f * P.npx, seedcs + (long long)f * P.npx, wtab,
-                   reg + (long long)f * reg_stride, ring, mask + (long long)f * P.npx, red, P.sw, P.sh};
+                   reg + (long long)f * reg_stride, ring, mask + (long long)f * P.npx, red, P.sw, P.sh, P.npx};
     const unsigned* O = order + (long long)f * P.npx;
     float4* S = segs + (long long)f * P.seg_cap;
     const int n = ndef[f];

@@ -383,6 +383,24 @@ int pl_orb_fuse_search(const PLKeyPoint* keys_un, const uint8_t* desc, int n, co
                        const float* min_dist, const float* max_dist, const uint8_t* mp_desc, float th, int* best_idx,
                        int* best_dist);
 
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:249-314) for n_mp map points: the descriptors of point m are rows
+ * offsets[m] .. offsets[m+1] of desc (its observations in std::map order, bad keyframes dropped by the caller).  best_idx[m] =
+ * index INSIDE the point's list of the descriptor with the least median distance to the others (first wins; -1 for an empty
+ * list: the reference keeps mDescriptor); out_desc (may be NULL) receives the chosen 32 bytes per point. */
+int pl_mappoint_distinctive_descriptors(const uint8_t* desc, const int* offsets, int n_mp, int* best_idx, uint8_t* out_desc);
+/* The search half of LSDmatcher::Fuse(pKF, vpMapLines, th) (src/LSDmatcher.cpp:860-1011; LocalMapping.cc:1600,1627), with the
+ * reference's quirks: the first map line with an end point behind the camera ends the call with `return false` (*stop_at = its
+ * index, n_ml if none: the caller returns 0 and has applied the surgery of the lines before it); candidates are
+ * KeyFrame::GetLinesInArea (KeyFrame.cc:647-682) with kl.octave in [level-1, level], level = unclamped MapLine::PredictScale;
+ * the map line's descriptor is compared with row idx of the keyframe's POINT descriptors (:966; rows beyond n_pdesc skipped);
+ * mvScaleFactorsLine[level] out of range is restated as scale_line^level.  skip[i] = !pML || isBad() || IsInKeyFrame(pKF);
+ * bounds = {mnMinX, mnMinY, mnMaxX, mnMaxY} (IsInImage: min <= x < max); min/max_dist raw.  best_idx = -1 / best_dist = 256 when
+ * skipped or nothing qualifies; the caller applies :986-1006 (Replace / AddObservation) to lines with best_dist <= 50 in order. */
+int pl_lsd_fuse_search(const void* keylines, int nl, const uint8_t* kf_point_desc, int n_pdesc, const float* bounds, const float* Tcw,
+                       const float* Ow, const float* K, float scale_line, float log_scale_factor_line, int n_ml, const uint8_t* skip,
+                       const double* pos, const double* normal, const float* min_dist, const float* max_dist, const uint8_t* ml_desc,
+                       float th, int* best_idx, int* best_dist, int* stop_at);
+
 /* ------------------------------------------------------------------ multi-GPU exchange
  * Frames shard across the GPUs of one box with no data-path collective; the ONE exchange is an all-gather of the per-frame
  * pose records (64 B per frame) over NCCL / NVLink so that the rank running the sequential Tracking logic (Tracking.cc:329)

@@ -546,3 +546,26 @@ def search_by_bow_keyframes(k1, d1, mp1, k2, d2, mp2, fv1, fv2, nnratio=0.75, ch
                                           _p(s1), _p(i1), C.c_int(len(n1a)), _p(n2a), _p(s2), _p(i2), C.c_int(len(n2a)),
                                           C.c_float(nnratio), C.c_int(int(check_orientation)), _p(out))
     return nm, out
+
+
+def distinctive_descriptors(desc, offsets):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:249-314) for a CSR list of map points -> best index per point."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); off = np.ascontiguousarray(offsets, np.int32)
+    best = np.zeros(len(off) - 1, np.int32)
+    lib().oracle_distinctive_descriptors(_p(desc), _p(off), C.c_int(len(off) - 1), _p(best))
+    return best
+
+
+def lsd_fuse_search(keylines, kf_point_desc, bounds, Tcw, Ow, K, scale_line, log_scale_factor_line, skip, pos, normal, min_dist, max_dist,
+                    ml_desc, th=3.0):
+    """Search half of LSDmatcher::Fuse (LSDmatcher.cpp:860-1011) -> (best_idx, best_dist, stop_at)."""
+    kl = np.ascontiguousarray(keylines); pd = np.ascontiguousarray(kf_point_desc, np.uint8).reshape(-1, 32)
+    b = _f32(bounds); T = _f32(Tcw); O = _f32(Ow); Kc = _f32(K)
+    n = len(pos)
+    sk = np.ascontiguousarray(skip, np.uint8); P = np.ascontiguousarray(pos, np.float64); Nn = np.ascontiguousarray(normal, np.float64)
+    mn = _f32(min_dist); mx = _f32(max_dist); md = np.ascontiguousarray(ml_desc, np.uint8).reshape(-1, 32)
+    bi = np.zeros(n, np.int32); bd = np.zeros(n, np.int32); stop = C.c_int(n)
+    lib().oracle_lsd_fuse_search(_p(kl), C.c_int(len(kl)), _p(pd), C.c_int(len(pd)), _p(b), _p(T), _p(O), _p(Kc), C.c_float(scale_line), C.c_int(1),
+                                 C.c_float(log_scale_factor_line), C.c_int(n), _p(sk), _p(P), _p(Nn), _p(mn), _p(mx), _p(md), C.c_float(th),
+                                 _p(bi), _p(bd), C.byref(stop))
+    return bi, bd, stop.value

@@ -778,4 +778,101 @@ int oracle_search_by_bow_keyframes(const void* keys1_, const uint8_t* desc1, con
   }
   return nmatches;
 }
+
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:249-314) for n_mp map points: descriptors of point m are rows
+// offsets[m] .. offsets[m+1]) of desc (the observations in std::map order, bad keyframes already dropped by the caller).
+// best[m] = index inside the point's list of the descriptor with the least median distance to the others (first wins),
+// -1 when the list is empty (the reference returns early and keeps mDescriptor).  median = sorted[int(0.5 * (N - 1))].
+void oracle_distinctive_descriptors(const uint8_t* desc, const int* offsets, int n_mp, int* best) {
+  for (int m = 0; m < n_mp; m++) {
+    const int N = offsets[m + 1] - offsets[m];
+    best[m] = -1;
+    if (N <= 0) continue;
+    const uint8_t* d = desc + (size_t)offsets[m] * 32;
+    std::vector<int> D((size_t)N * N, 0);
+    for (int i = 0; i < N; i++)
+      for (int j = i + 1; j < N; j++) { const int v = descriptor_distance(d + 32 * i, d + 32 * j); D[(size_t)i * N + j] = v; D[(size_t)j * N + i] = v; }
+    int BestMedian = INT_MAX, BestIdx = 0;
+    for (int i = 0; i < N; i++) {
+      std::vector<int> v(D.begin() + (size_t)i * N, D.begin() + (size_t)(i + 1) * N);
+      std::sort(v.begin(), v.end());
+      const int median = v[(size_t)(0.5 * (N - 1))];
+      if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+    }
+    best[m] = BestIdx;
+  }
+}
+
+// The search half of LSDmatcher::Fuse(pKF, vpMapLines, th) (src/LSDmatcher.cpp:860-1011), quirks kept:
+//  * the FIRST map line with an end point behind the camera ends the whole call with `return false` (:907): stop_at = its
+//    index (n_ml if none); lines from there on are not looked at, and the caller returns 0 instead of nFused;
+//  * candidates come from KeyFrame::GetLinesInArea (KeyFrame.cc:647-682: midpoint within r, |cos| of the directions >= 0.998),
+//    filtered by kl.octave in [level-1, level] with level = MapLine::PredictScale (unclamped ceil, MapLine.cpp:395-404);
+//  * the map line's LBD descriptor is compared with row idx of pKF->mDescriptors - the keyframe's POINT descriptors, indexed
+//    with the LINE index (:966).  Rows beyond the point descriptors do not exist (cv::Mat::row would be out of range): skipped;
+//  * mvScaleFactorsLine[level] (:944) is read out of range for level outside [0, n_levels) (one octave: every level != 0):
+//    restated as scale^level, the rule the table is built with (LineExtractor.cpp:7-14).
+// skip[i] = !pML || isBad() || IsInKeyFrame(pKF); min/max_dist = raw mfMinDistance / mfMaxDistance.  best_idx = -1 /
+// best_dist = 256 when skipped or nothing qualifies; the caller applies :986-1006 to lines with best_dist <= TH_LOW (50).
+void oracle_lsd_fuse_search(const void* keylines_, int nl, const uint8_t* kf_point_desc, int n_pdesc, const float* bounds, const float* Tcw,
+                            const float* Ow, const float* K, float scale_line, int n_line_levels, float logScaleFactorLine, int n_ml,
+                            const uint8_t* skip, const double* pos, const double* normal, const float* minDist, const float* maxDist,
+                            const uint8_t* ml_desc, float th, int* best_idx, int* best_dist, int* stop_at) {
+  struct KL { float angle; int class_id; int octave; float ptx, pty; float response; float size; float sx, sy, ex, ey; float o[4]; float len; int npx; };
+  static_assert(sizeof(KL) == 68, "KeyLine");
+  const KL* kl = static_cast<const KL*>(keylines_);
+  for (int i = 0; i < n_ml; i++) { best_idx[i] = -1; best_dist[i] = 256; }
+  *stop_at = n_ml;
+  const float t[3] = {Tcw[3], Tcw[7], Tcw[11]};
+  for (int i = 0; i < n_ml; i++) {
+    if (skip[i]) continue;
+    const float SP[3] = {(float)pos[6 * i], (float)pos[6 * i + 1], (float)pos[6 * i + 2]};
+    const float EP[3] = {(float)pos[6 * i + 3], (float)pos[6 * i + 4], (float)pos[6 * i + 5]};
+    float S[3], E[3];
+    for (int r = 0; r < 3; r++) {
+      S[r] = Tcw[4 * r] * SP[0] + Tcw[4 * r + 1] * SP[1] + Tcw[4 * r + 2] * SP[2] + t[r];
+      E[r] = Tcw[4 * r] * EP[0] + Tcw[4 * r + 1] * EP[1] + Tcw[4 * r + 2] * EP[2] + t[r];
+    }
+    if (S[2] < 0.0f || E[2] < 0.0f) { *stop_at = i; return; }
+    const float invz1 = 1.0f / S[2], u1 = K[0] * S[0] * invz1 + K[2], v1 = K[1] * S[1] * invz1 + K[3];
+    if (!(u1 >= bounds[0] && u1 < bounds[2] && v1 >= bounds[1] && v1 < bounds[3])) continue;      // KeyFrame::IsInImage
+    const float invz2 = 1.0f / E[2], u2 = K[0] * E[0] * invz2 + K[2], v2 = K[1] * E[1] * invz2 + K[3];
+    if (!(u2 >= bounds[0] && u2 < bounds[2] && v2 >= bounds[1] && v2 < bounds[3])) continue;
+    float OM[3];
+    for (int k = 0; k < 3; k++) OM[k] = (float)(0.5 * (double)(SP[k] + EP[k])) - Ow[k];
+    const float dist = (float)std::sqrt((double)OM[0] * OM[0] + (double)OM[1] * OM[1] + (double)OM[2] * OM[2]);
+    if (dist < 0.8f * minDist[i] || dist > 1.2f * maxDist[i]) continue;
+    const float pn[3] = {(float)normal[3 * i], (float)normal[3 * i + 1], (float)normal[3 * i + 2]};
+    const double dot = (double)OM[0] * pn[0] + (double)OM[1] * pn[1] + (double)OM[2] * pn[2];
+    if (dot < 0.5 * dist) continue;
+    const float ratio = maxDist[i] / dist;
+    const int lvl = (int)std::ceil(std::log((double)ratio) / (double)logScaleFactorLine);
+    float sf = 1.0f;                                        // mvScaleFactorsLine[lvl]: cumulative fp32 products, 1/x below zero
+    if (lvl >= 0) for (int k = 0; k < lvl; k++) sf = sf * scale_line;
+    else { for (int k = 0; k < -lvl; k++) sf = sf * scale_line; sf = 1.0f / sf; }
+    (void)n_line_levels;
+    const float radius = th * sf;
+    // KeyFrame::GetLinesInArea(u1, v1, u2, v2, radius, 0.998)
+    float d1x = u1 - u2, d1y = v1 - v2;
+    const float n1 = std::sqrt(d1x * d1x + d1y * d1y);
+    d1x /= n1; d1y /= n1;
+    int bestDist = 256, bestIdx = -1;
+    for (int j = 0; j < nl; j++) {
+      const float distance = (float)((double)((0.5 * (double)(u1 + u2) - (double)kl[j].ptx) * (0.5 * (double)(u1 + u2) - (double)kl[j].ptx)) +
+                                     (double)((0.5 * (double)(v1 + v2) - (double)kl[j].pty) * (0.5 * (double)(v1 + v2) - (double)kl[j].pty)));
+      if (distance > radius * radius) continue;
+      float d2x = kl[j].sx - kl[j].ex, d2y = kl[j].sy - kl[j].ey;
+      const float n2 = std::sqrt(d2x * d2x + d2y * d2y);
+      d2x /= n2; d2y /= n2;
+      const float CosSita = std::fabs(d1x * d2x + d1y * d2y);
+      if (CosSita < 0.998f) continue;
+      const int kpLevel = kl[j].octave;
+      if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
+      if (j >= n_pdesc) continue;                            // pKF->mDescriptors.row(idx) does not exist
+      const int d = descriptor_distance(ml_desc + 32 * (size_t)i, kf_point_desc + 32 * (size_t)j);
+      if (d < bestDist) { bestDist = d; bestIdx = j; }
+    }
+    best_idx[i] = bestIdx; best_dist[i] = bestDist;
+  }
+}
 }

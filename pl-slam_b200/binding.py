@@ -801,3 +801,36 @@ def _search_by_bow_keyframes(self, keys1_un, desc1, has_mp1, keys2_un, desc2, ha
 
 
 ORBmatcher.SearchByBoWKeyFrames = _search_by_bow_keyframes
+
+
+# ---------------------------------------------------------------------------------------------- LocalMapping: map-point descriptor, line fusion
+def ComputeDistinctiveDescriptors(desc, offsets, return_desc=False):
+    """MapPoint::ComputeDistinctiveDescriptors (reference src/MapPoint.cc:249-314) for a batch of map points: descriptors of
+    point m = rows offsets[m]..offsets[m+1] of desc.  Returns best index inside each point's list (-1 for an empty list)."""
+    desc = _u8(desc).reshape(-1, 32); off = np.ascontiguousarray(offsets, np.int32)
+    n = len(off) - 1
+    best = np.zeros(max(n, 1), np.int32); out = np.zeros((max(n, 1), 32), np.uint8) if return_desc else None
+    f = lib().pl_mappoint_distinctive_descriptors
+    f.argtypes = [vp, vp, C.c_int, vp, vp]
+    check(f(_p(desc), _p(off), n, _p(best), _p(out)))
+    return (best[:n], out[:n]) if return_desc else best[:n]
+
+
+def _lsd_fuse_search(self, keylines, kf_point_desc, bounds, Tcw, Ow, K, scale_line, log_scale_factor_line, skip, pos, normal,
+                     min_dist, max_dist, ml_desc, th=3.0):
+    """Search half of LSDmatcher::Fuse(pKF, vpMapLines, th) (reference src/LSDmatcher.cpp:860-1011) -> (best_idx, best_dist,
+    stop_at); quirks in include/plslam_b200.h (pl_lsd_fuse_search)."""
+    kl = np.ascontiguousarray(keylines); pd = _u8(kf_point_desc).reshape(-1, 32)
+    b = _f32(bounds); T = _f32(Tcw); O = _f32(Ow); Kc = _f32(K)
+    n = len(pos)
+    sk = _u8(skip); P = np.ascontiguousarray(pos, np.float64); Nn = np.ascontiguousarray(normal, np.float64)
+    mn = _f32(min_dist); mx = _f32(max_dist); md = _u8(ml_desc).reshape(-1, 32)
+    bi = np.zeros(max(n, 1), np.int32); bd = np.zeros(max(n, 1), np.int32); stop = C.c_int(n)
+    f = lib().pl_lsd_fuse_search
+    f.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, C.c_float, C.c_float, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, vp, vp, vp]
+    check(f(_p(kl), len(kl), _p(pd), len(pd), _p(b), _p(T), _p(O), _p(Kc), scale_line, log_scale_factor_line, n, _p(sk), _p(P), _p(Nn),
+            _p(mn), _p(mx), _p(md), th, _p(bi), _p(bd), C.byref(stop)))
+    return bi[:n], bd[:n], stop.value
+
+
+LSDmatcher.FuseSearch = _lsd_fuse_search

@@ -912,6 +912,112 @@ __global__ void __launch_bounds__(32 * kBowWarps) k_search_by_bow(BowArgs A) {
 // ================================================================================================ C ABI
 using namespace pl;
 
+// ------------------------------------------------------------------------------------------------ MapPoint descriptor choice
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:249-314): one warp per map point.  For every descriptor i of the
+// point the lanes compute the distances to all N descriptors into a 257-bin histogram in shared memory; the median
+// sorted[int(0.5 * (N - 1))] is the bin where the running count passes that rank (distances are integers in [0, 256]).
+constexpr int kDistWarps = 4;
+__global__ void __launch_bounds__(32 * kDistWarps) k_distinctive(const uint8_t* __restrict__ desc, const int* __restrict__ offsets, int n_mp,
+                                                                 int* __restrict__ best, uint8_t* __restrict__ out_desc) {
+  __shared__ int hist[kDistWarps][264];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, m = blockIdx.x * kDistWarps + wid;
+  if (m >= n_mp) return;
+  const int o0 = offsets[m], N = offsets[m + 1] - o0;
+  if (N <= 0) { if (lane == 0) best[m] = -1; return; }
+  const uint8_t* d = desc + (long long)o0 * 32;
+  int* h = hist[wid];
+  const int rank = (int)(0.5 * (double)(N - 1));
+  int bestMedian = 0x7fffffff, bestIdx = 0;
+  for (int i = 0; i < N; i++) {
+    for (int k = lane; k < 257; k += 32) h[k] = 0;
+    __syncwarp();
+    for (int j = lane; j < N; j += 32) atomicAdd(&h[(i == j) ? 0 : hamming256(d + 32 * i, d + 32 * j)], 1);
+    __syncwarp();
+    // first bin whose inclusive prefix count exceeds `rank`
+    int median = 256, run = 0;
+    for (int k0 = 0; k0 < 257 + 31; k0 += 32) {
+      const int k = k0 + lane;
+      const int c = (k < 257) ? h[k] : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      const unsigned hit = __ballot_sync(0xffffffffu, run + incl > rank);
+      if (hit) { median = k0 + __ffs(hit) - 1; break; }
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (median < bestMedian) { bestMedian = median; bestIdx = i; }
+    __syncwarp();
+  }
+  if (lane == 0) best[m] = bestIdx;
+  if (out_desc) out_desc[(long long)m * 32 + lane] = d[32 * bestIdx + lane];
+}
+
+// ------------------------------------------------------------------------------------------------ LSDmatcher::Fuse, search half
+struct LineFuseArgs {
+  const KeyLine68* kl; int nl; const uint8_t* pdesc; int n_pdesc; float bounds[4]; float T[16], Ow[3], K[4];
+  float scale_line, logScaleFactorLine; int n_ml; const uint8_t* skip; const double *pos, *normal; const float *minDist, *maxDist;
+  const uint8_t* ml_desc; float th; int *best_idx, *best_dist, *stop_at;
+};
+// One thread per map line (the keyframe has <= a few hundred lines; every candidate test is a handful of flops).
+// Quirks of the reference are listed at pl_lsd_fuse_search (plslam_b200.h) and restated in oracle_lsd_fuse_search.
+__global__ void __launch_bounds__(128) k_lsd_fuse_search(LineFuseArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n_ml) return;
+  A.best_idx[i] = -1; A.best_dist[i] = 256;
+  if (A.skip[i]) return;
+  const float SP[3] = {(float)A.pos[6 * i], (float)A.pos[6 * i + 1], (float)A.pos[6 * i + 2]};
+  const float EP[3] = {(float)A.pos[6 * i + 3], (float)A.pos[6 * i + 4], (float)A.pos[6 * i + 5]};
+  float S[3], E[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    S[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A.T[4 * r], SP[0]), __fmul_rn(A.T[4 * r + 1], SP[1])), __fmul_rn(A.T[4 * r + 2], SP[2])), A.T[4 * r + 3]);
+    E[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A.T[4 * r], EP[0]), __fmul_rn(A.T[4 * r + 1], EP[1])), __fmul_rn(A.T[4 * r + 2], EP[2])), A.T[4 * r + 3]);
+  }
+  if (S[2] < 0.0f || E[2] < 0.0f) { atomicMin(A.stop_at, i); return; }      // `return false` of the whole call (:907)
+  const float invz1 = __fdiv_rn(1.0f, S[2]);
+  const float u1 = __fadd_rn(__fmul_rn(__fmul_rn(A.K[0], S[0]), invz1), A.K[2]), v1 = __fadd_rn(__fmul_rn(__fmul_rn(A.K[1], S[1]), invz1), A.K[3]);
+  if (!(u1 >= A.bounds[0] && u1 < A.bounds[2] && v1 >= A.bounds[1] && v1 < A.bounds[3])) return;
+  const float invz2 = __fdiv_rn(1.0f, E[2]);
+  const float u2 = __fadd_rn(__fmul_rn(__fmul_rn(A.K[0], E[0]), invz2), A.K[2]), v2 = __fadd_rn(__fmul_rn(__fmul_rn(A.K[1], E[1]), invz2), A.K[3]);
+  if (!(u2 >= A.bounds[0] && u2 < A.bounds[2] && v2 >= A.bounds[1] && v2 < A.bounds[3])) return;
+  float OM[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) OM[k] = __fsub_rn((float)(0.5 * (double)__fadd_rn(SP[k], EP[k])), A.Ow[k]);
+  const float dist = (float)sqrt((double)OM[0] * OM[0] + (double)OM[1] * OM[1] + (double)OM[2] * OM[2]);
+  if (dist < __fmul_rn(0.8f, A.minDist[i]) || dist > __fmul_rn(1.2f, A.maxDist[i])) return;
+  const float pn[3] = {(float)A.normal[3 * i], (float)A.normal[3 * i + 1], (float)A.normal[3 * i + 2]};
+  const double dot = (double)OM[0] * pn[0] + (double)OM[1] * pn[1] + (double)OM[2] * pn[2];
+  if (dot < 0.5 * (double)dist) return;
+  const float ratio = __fdiv_rn(A.maxDist[i], dist);
+  const int lvl = (int)ceil(log((double)ratio) / (double)A.logScaleFactorLine);
+  float sf = 1.0f;
+  if (lvl >= 0) { for (int k = 0; k < lvl; k++) sf = __fmul_rn(sf, A.scale_line); }
+  else { for (int k = 0; k < -lvl; k++) sf = __fmul_rn(sf, A.scale_line); sf = __fdiv_rn(1.0f, sf); }
+  const float radius = __fmul_rn(A.th, sf), r2 = __fmul_rn(radius, radius);
+  float d1x = __fsub_rn(u1, u2), d1y = __fsub_rn(v1, v2);
+  const float n1 = __fsqrt_rn(__fadd_rn(__fmul_rn(d1x, d1x), __fmul_rn(d1y, d1y)));
+  d1x = __fdiv_rn(d1x, n1); d1y = __fdiv_rn(d1y, n1);
+  const double mxd = 0.5 * (double)__fadd_rn(u1, u2), myd = 0.5 * (double)__fadd_rn(v1, v2);
+  int bestDist = 256, bestIdx = -1;
+  const uint8_t* q = A.ml_desc + 32 * (long long)i;
+  for (int j = 0; j < A.nl; j++) {
+    const KeyLine68& kl = A.kl[j];
+    const double ax = mxd - (double)kl.ptx, ay = myd - (double)kl.pty;
+    const float distance = (float)(ax * ax + ay * ay);
+    if (distance > r2) continue;
+    float d2x = __fsub_rn(kl.startPointX, kl.endPointX), d2y = __fsub_rn(kl.startPointY, kl.endPointY);
+    const float n2 = __fsqrt_rn(__fadd_rn(__fmul_rn(d2x, d2x), __fmul_rn(d2y, d2y)));
+    d2x = __fdiv_rn(d2x, n2); d2y = __fdiv_rn(d2y, n2);
+    const float cs = fabsf(__fadd_rn(__fmul_rn(d1x, d2x), __fmul_rn(d1y, d2y)));
+    if (cs < 0.998f) continue;
+    if (kl.octave < lvl - 1 || kl.octave > lvl) continue;
+    if (j >= A.n_pdesc) continue;
+    const int d = hamming256(q, A.pdesc + 32 * (long long)j);
+    if (d < bestDist) { bestDist = d; bestIdx = j; }
+  }
+  A.best_idx[i] = bestIdx; A.best_dist[i] = bestDist;
+}
+
 namespace {
 struct Stage {  // tiny RAII helper for the host-pointer wrappers
   std::vector<void*> ptrs;
@@ -1397,4 +1503,49 @@ extern "C" int pl_orb_search_by_projection_keyframe(const PLKeyPoint* keys_cur, 
   rc = down(&nm, A.nmatches, 1); if (rc) return rc;
   if (n_cur) { rc = down(cur_match, A.match, (size_t)n_cur); if (rc) return rc; }
   return nm;
+}
+
+extern "C" int pl_mappoint_distinctive_descriptors(const uint8_t* desc, const int* offsets, int n_mp, int* best_idx, uint8_t* out_desc) {
+  PL_ARG(offsets && best_idx && n_mp >= 0 && (desc || n_mp == 0));
+  int rc = require_device(); if (rc) return rc;
+  if (n_mp == 0) return PL_OK;
+  const int total = offsets[n_mp];
+  PL_ARG(total >= 0);
+  Stage s;
+  const uint8_t* dd = s.up(desc, (size_t)total * 32); const int* doff = s.up(offsets, (size_t)n_mp + 1);
+  int* db = s.alloc<int>(n_mp); uint8_t* dout = out_desc ? s.alloc<uint8_t>((size_t)n_mp * 32) : nullptr;
+  PL_ARG(dd && doff && db);
+  k_distinctive<<<(n_mp + kDistWarps - 1) / kDistWarps, 32 * kDistWarps>>>(dd, doff, n_mp, db, dout);
+  PL_LAUNCH_CHECK();
+  rc = down(best_idx, db, (size_t)n_mp); if (rc) return rc;
+  if (out_desc) { rc = down(out_desc, dout, (size_t)n_mp * 32); if (rc) return rc; }
+  return PL_OK;
+}
+
+extern "C" int pl_lsd_fuse_search(const void* keylines, int nl, const uint8_t* kf_point_desc, int n_pdesc, const float* bounds, const float* Tcw,
+                                  const float* Ow, const float* K, float scale_line, float log_scale_factor_line, int n_ml,
+                                  const uint8_t* skip, const double* pos, const double* normal, const float* min_dist, const float* max_dist,
+                                  const uint8_t* ml_desc, float th, int* best_idx, int* best_dist, int* stop_at) {
+  PL_ARG(bounds && Tcw && Ow && K && best_idx && best_dist && stop_at && nl >= 0 && n_ml >= 0 && n_pdesc >= 0);
+  PL_ARG(n_ml == 0 || (skip && pos && normal && min_dist && max_dist && ml_desc));
+  int rc = require_device(); if (rc) return rc;
+  *stop_at = n_ml;
+  if (n_ml == 0) return PL_OK;
+  Stage s;
+  LineFuseArgs A;
+  A.kl = reinterpret_cast<const KeyLine68*>(s.up(static_cast<const uint8_t*>(keylines), (size_t)nl * 68)); A.nl = nl;
+  A.pdesc = s.up(kf_point_desc, (size_t)n_pdesc * 32); A.n_pdesc = n_pdesc;
+  memcpy(A.bounds, bounds, 16); memcpy(A.T, Tcw, 64); memcpy(A.Ow, Ow, 12); memcpy(A.K, K, 16);
+  A.scale_line = scale_line; A.logScaleFactorLine = log_scale_factor_line; A.n_ml = n_ml;
+  A.skip = s.up(skip, n_ml); A.pos = s.up(pos, (size_t)n_ml * 6); A.normal = s.up(normal, (size_t)n_ml * 3);
+  A.minDist = s.up(min_dist, n_ml); A.maxDist = s.up(max_dist, n_ml); A.ml_desc = s.up(ml_desc, (size_t)n_ml * 32); A.th = th;
+  A.best_idx = s.alloc<int>(n_ml); A.best_dist = s.alloc<int>(n_ml); A.stop_at = s.up(stop_at, 1);
+  PL_ARG(A.kl && A.pdesc && A.skip && A.pos && A.normal && A.minDist && A.maxDist && A.ml_desc && A.best_idx && A.best_dist && A.stop_at);
+  k_lsd_fuse_search<<<(n_ml + 127) / 128, 128>>>(A);
+  PL_LAUNCH_CHECK();
+  rc = down(best_idx, A.best_idx, (size_t)n_ml); if (rc) return rc;
+  rc = down(best_dist, A.best_dist, (size_t)n_ml); if (rc) return rc;
+  rc = down(stop_at, A.stop_at, 1); if (rc) return rc;
+  for (int i = *stop_at; i < n_ml; i++) { best_idx[i] = -1; best_dist[i] = 256; }     // never reached by the reference's loop
+  return PL_OK;
 }

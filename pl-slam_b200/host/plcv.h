@@ -18,21 +18,34 @@ namespace cv {
 struct Point2f { float x = 0, y = 0; };
 struct KeyPoint { Point2f pt; float size = 0, angle = -1, response = 0; int octave = 0, class_id = -1; };
 static_assert(sizeof(KeyPoint) == 28, "cv::KeyPoint layout");
-enum { CV_8UC1 = 0, CV_8U = 0 };
-// 8-bit single-channel matrix view / owner (all the hot path exchanges)
+enum { CV_8UC1 = 0, CV_8U = 0, CV_32F = 5, CV_32FC1 = 5 };
+// 8-bit or float single-channel matrix view / owner (all the hot path exchanges: images, descriptor rows, 4x4 poses, 3x1 points)
 struct Mat {
-  int rows = 0, cols = 0; size_t step = 0; uint8_t* data = nullptr;
+  int rows = 0, cols = 0; size_t step = 0; uint8_t* data = nullptr; int type_ = CV_8UC1;
   std::vector<uint8_t> store;
   Mat() {}
-  Mat(int r, int c, int /*type*/) { create(r, c, 0); }
-  Mat(int r, int c, int, void* p, size_t s = 0) : rows(r), cols(c), step(s ? s : (size_t)c), data((uint8_t*)p) {}
-  void create(int r, int c, int) { rows = r; cols = c; step = (size_t)c; store.assign((size_t)r * c, 0); data = store.data(); }
+  Mat(int r, int c, int type) { create(r, c, type); }
+  Mat(int r, int c, int type, void* p, size_t s = 0) : rows(r), cols(c), step(s ? s : (size_t)c * (type == CV_32F ? 4 : 1)), data((uint8_t*)p), type_(type) {}
+  Mat(const Mat& o) { *this = o; }
+  Mat& operator=(const Mat& o) {      // owners copy their storage, views stay views (cv::Mat is reference counted: same observable behaviour here)
+    rows = o.rows; cols = o.cols; step = o.step; type_ = o.type_; store = o.store;
+    data = o.store.empty() ? o.data : store.data();
+    return *this;
+  }
+  size_t elemSize() const { return type_ == CV_32F ? 4 : 1; }
+  void create(int r, int c, int type) { rows = r; cols = c; type_ = type; step = (size_t)c * elemSize(); store.assign((size_t)r * step, 0); data = store.data(); }
   void release() { rows = cols = 0; step = 0; store.clear(); data = nullptr; }
   bool empty() const { return rows == 0 || cols == 0 || !data; }
-  int type() const { return CV_8UC1; }
+  int type() const { return type_; }
   uint8_t* ptr(int r = 0) { return data + (size_t)r * step; }
   const uint8_t* ptr(int r = 0) const { return data + (size_t)r * step; }
-  Mat getMat() const { Mat m(rows, cols, 0, data, step); return m; }
+  template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * step); }
+  template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * step); }
+  template <typename T> T& at(int r, int c = 0) { return ptr<T>(r)[c]; }
+  template <typename T> const T& at(int r, int c = 0) const { return ptr<T>(r)[c]; }
+  Mat row(int r) const { return Mat(1, cols, type_, data + (size_t)r * step, step); }
+  Mat clone() const { Mat m(rows, cols, type_); for (int r = 0; r < rows; r++) memcpy(m.ptr(r), ptr(r), (size_t)cols * elemSize()); return m; }
+  Mat getMat() const { Mat m(rows, cols, type_, data, step); return m; }
 };
 typedef const Mat& InputArray;
 typedef Mat& OutputArray;

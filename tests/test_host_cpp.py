@@ -92,3 +92,66 @@ def test_host_pipeline_matches_oracle(tmp_path):
     on, oT, opo, olo, _ = oracle.pose_optimization(0, p["Tcw0"], p["K"], p["pt_obs"], p["pt_inv_sigma2"], p["pt_Xw"], p["line_func"], p["line_Xw"])
     assert inl == on and np.array_equal(po, opo) and np.array_equal(lo, olo)
     assert np.linalg.norm(T[:3, 3] - oT[:3, 3]) <= 1e-4 * np.linalg.norm(oT[:3, 3])
+
+
+GLUE = os.path.join(ROOT, "tests", "host", "glue_track")
+
+
+def test_reference_signature_glue_compiles_and_links():
+    """reference_glue.cc: ORBmatcher / LSDmatcher / Optimizer with the reference's own signatures (Frame&, KeyFrame*, Map*),
+    compiled against the mock map classes of reference_mock.h."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "host"), "-s", "glue_track"])
+    assert os.path.exists(GLUE)
+
+
+@pytest.mark.gpu
+def test_glue_track_with_motion_model_matches_oracle(tmp_path):
+    """Tracking::TrackWithMotionModel's call sequence (Tracking.cc:1345-1372) through the reference-signature classes on mock
+    Frame / MapPoint / MapLine objects; every call recomputed by the CPU oracle from the flat inputs the driver dumps."""
+    if not os.path.exists(GLUE):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "host"), "-s", "glue_track"])
+    K = np.asarray(synth.TUM1_K, np.float32)
+    f = synth.synth_sequence(2, 640, 480, seed=9)
+    (tmp_path / "f1.raw").write_bytes(f[0].tobytes()); (tmp_path / "f2.raw").write_bytes(f[1].tobytes())
+    out = tmp_path / "glue.bin"
+    subprocess.check_call([GLUE, str(tmp_path / "f1.raw"), str(tmp_path / "f2.raw"), "640", "480", str(out)])
+    b = out.read_bytes(); off = 0
+
+    def rd(fmt, n=1):
+        nonlocal off
+        v = np.frombuffer(b, fmt, n, off); off += v.nbytes
+        return v
+    NL_, NLL, NC, NCL = rd("<i4", 4)
+    bounds = rd("<f4", 4); Tcw = rd("<f4", 16).reshape(4, 4); Ow = rd("<f4", 3)
+    lk = rd(pl.KP_DTYPE, NL_); lku = rd(pl.KP_DTYPE, NL_); ldesc = rd("u1", 32 * NL_).reshape(NL_, 32)
+    mp = rd(np.dtype([("valid", "u1"), ("has", "u1"), ("X", "<f4", 3)]), NL_)
+    lkl = rd(pl.KEYLINE_DTYPE, NLL); lld = rd("u1", 32 * NLL).reshape(NLL, 32)
+    ml = rd(np.dtype([("cand", "u1"), ("has", "u1"), ("P", "<f8", 6), ("n", "<f8", 3), ("md", "<f4", 2)]), NLL)
+    cku = rd(pl.KP_DTYPE, NC); cdesc = rd("u1", 32 * NC).reshape(NC, 32)
+    ckl = rd(pl.KEYLINE_DTYPE, NCL); cld = rd("u1", 32 * NCL).reshape(NCL, 32); clf = rd("<f8", 3 * NCL).reshape(NCL, 3)
+    nmatches, lmatches = rd("<i4", 2)
+    cur_mp = rd("<i4", NC); cur_ml = rd("<i4", NCL)
+    inl = rd("<i4")[0]; Tout = rd("<f4", 16).reshape(4, 4); pout = rd("u1", NC).astype(bool); lout = rd("u1", NCL).astype(bool)
+    assert off == len(b)
+    sf = np.cumprod(np.r_[np.float32(1.0), np.full(7, np.float32(1.2))]).astype(np.float32)     # mvScaleFactor: cumulative fp32 products
+    # --- ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, 15, mono)
+    onm, om = oracle.search_by_projection_last(cku, cdesc, bounds, Tcw, K, sf, mp["valid"], mp["X"], ldesc, lk["octave"], lku["angle"], 15.0, True,
+                                               np.zeros(NC, np.uint8))
+    assert nmatches == onm and nmatches >= 20
+    assert np.array_equal(cur_mp, om)              # mnId of a mock MapPoint == its last-frame keypoint index
+    # --- LSDmatcher::SearchByProjection(CurrentFrame, LastFrame, 15): isInFrustum on the candidates, then the search
+    cand = ml["cand"].astype(bool)
+    iv, proj, lvl, vc = oracle.is_in_frustum_lines(Tcw, Ow, K, bounds, float(np.float32(np.log(np.float32(1.2)))), 0.5, ml["P"][cand], ml["n"][cand],
+                                                   ml["md"][cand, 0], ml["md"][cand, 1])
+    valid = np.zeros(NLL, np.uint8); lproj = np.zeros((NLL, 4), np.float32)
+    valid[np.nonzero(cand)[0]] = iv; lproj[np.nonzero(cand)[0]] = proj
+    onl, olm = oracle.line_search_by_projection_last(ckl, clf, cld, bounds, valid, lproj, lld, lkl["lineLength"], 15.0, np.zeros(NCL, np.uint8))
+    assert lmatches == onl and lmatches > 5 and np.array_equal(cur_ml, olm)
+    # --- Optimizer::PoseOptimization(&mCurrentFrame) on exactly these correspondences
+    pi = np.nonzero(cur_mp >= 0)[0]; li = np.nonzero(cur_ml >= 0)[0]
+    inv_sigma2 = (np.float32(1.0) / (sf * sf)).astype(np.float32)
+    on, oT, opo, olo, _ = oracle.pose_optimization(0, Tcw, K, np.stack([cku["x"][pi], cku["y"][pi]], 1), inv_sigma2[cku["octave"][pi]], mp["X"][cur_mp[pi]],
+                                                   clf[li], ml["P"][cur_ml[li]])
+    assert inl == on and np.array_equal(pout[pi], opo) and np.array_equal(lout[li], olo)
+    assert not pout[cur_mp < 0].any() and not lout[cur_ml < 0].any()
+    assert np.linalg.norm(Tout[:3, 3] - oT[:3, 3]) <= 1e-4 * max(np.linalg.norm(oT[:3, 3]), 1e-3)

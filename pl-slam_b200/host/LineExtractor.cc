@@ -38,8 +38,9 @@ void LINEextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std:
     throw std::runtime_error(std::string("plslam_b200: ") + pl_last_error());
   _keylines.assign(kl.begin(), kl.begin() + n);
   if (n == 0) { _descriptors.release(); return; }
-  _descriptors.create(n, 32, cv::CV_8U);
-  for (int i = 0; i < n; i++) memcpy(_descriptors.ptr(i), &desc[(size_t)i * 32], 32);
+  _descriptors.create(n, 32, CV_8U);
+  cv::Mat d = _descriptors.getMat();
+  for (int i = 0; i < n; i++) memcpy(d.ptr(i), &desc[(size_t)i * 32], 32);
   _lineVec2d.clear();
   for (int i = 0; i < n; i++) { Eigen::Vector3d v; v[0] = lf[3 * i]; v[1] = lf[3 * i + 1]; v[2] = lf[3 * i + 2]; _lineVec2d.push_back(v); }
 }

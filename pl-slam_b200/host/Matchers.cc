@@ -17,7 +17,7 @@ FrameUndistorter::FrameUndistorter(const float K[4], const float distCoef[5], in
 FrameUndistorter::~FrameUndistorter() { pl_undistort_destroy(handle_); }
 void FrameUndistorter::remap(const cv::Mat& imGray, cv::Mat& ImageGray) const {
   if (imGray.cols != w_ || imGray.rows != h_) throw std::runtime_error("plslam_b200: image size does not match the camera");
-  ImageGray.create(h_, w_, cv::CV_8UC1);
+  ImageGray.create(h_, w_, CV_8UC1);
   if (pl_undistort_remap(handle_, imGray.ptr(0), (int)imGray.step, ImageGray.ptr(0), (int)ImageGray.step) != PL_OK) fail();
 }
 void FrameUndistorter::UndistortKeyPoints(FrameView& F) const {

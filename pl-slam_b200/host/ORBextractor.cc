@@ -34,14 +34,18 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray, std::vector
   static_assert(sizeof(cv::KeyPoint) == sizeof(PLKeyPoint), "layout");
   if (n) memcpy((void*)_keypoints.data(), kps.data(), (size_t)n * sizeof(PLKeyPoint));
   if (n == 0) _descriptors.release();
-  else { _descriptors.create(n, 32, cv::CV_8U); for (int i = 0; i < n; i++) memcpy(_descriptors.ptr(i), &desc[(size_t)i * 32], 32); }
+  else {
+    _descriptors.create(n, 32, CV_8U);
+    cv::Mat d = _descriptors.getMat();          // cv::OutputArray has no ptr(): rows are written through the Mat it wraps
+    for (int i = 0; i < n; i++) memcpy(d.ptr(i), &desc[(size_t)i * 32], 32);
+  }
 }
 void ORBextractor::FetchImagePyramid() {
   if (!handle) return;
   std::vector<int> lw(nlevels), lh(nlevels);
   pl_orb_tables(handle, nullptr, nullptr, nullptr, nullptr, nullptr, lw.data(), lh.data());
   for (int l = 0; l < nlevels; l++) {
-    mvImagePyramid[l].create(lh[l] + 38, lw[l] + 38, cv::CV_8UC1);   // with the 19-px border, like ComputePyramid's `temp`
+    mvImagePyramid[l].create(lh[l] + 38, lw[l] + 38, CV_8UC1);   // with the 19-px border, like ComputePyramid's `temp`
     pl_orb_get_level(handle, 0, l, mvImagePyramid[l].ptr(0), 1);
   }
 }

@@ -18,7 +18,15 @@ namespace cv {
 struct Point2f { float x = 0, y = 0; };
 struct KeyPoint { Point2f pt; float size = 0, angle = -1, response = 0; int octave = 0, class_id = -1; };
 static_assert(sizeof(KeyPoint) == 28, "cv::KeyPoint layout");
-enum { CV_8UC1 = 0, CV_8U = 0, CV_32F = 5, CV_32FC1 = 5 };
+}  // namespace cv
+// type codes are MACROS in OpenCV (CV_8U is 0, CV_32F is 5): the stand-in defines the same macros, so host code spells them the same way
+#ifndef CV_8U
+#define CV_8U 0
+#define CV_8UC1 0
+#define CV_32F 5
+#define CV_32FC1 5
+#endif
+namespace cv {
 // 8-bit or float single-channel matrix view / owner (all the hot path exchanges: images, descriptor rows, 4x4 poses, 3x1 points)
 struct Mat {
   int rows = 0, cols = 0; size_t step = 0; uint8_t* data = nullptr; int type_ = CV_8UC1;
@@ -45,10 +53,28 @@ struct Mat {
   template <typename T> const T& at(int r, int c = 0) const { return ptr<T>(r)[c]; }
   Mat row(int r) const { return Mat(1, cols, type_, data + (size_t)r * step, step); }
   Mat clone() const { Mat m(rows, cols, type_); for (int r = 0; r < rows; r++) memcpy(m.ptr(r), ptr(r), (size_t)cols * elemSize()); return m; }
-  Mat getMat() const { Mat m(rows, cols, type_, data, step); return m; }
 };
-typedef const Mat& InputArray;
-typedef Mat& OutputArray;
+// Same shape as OpenCV's proxies (core/mat.hpp): only getMat / empty / create / release - NO ptr() - so code that compiles
+// against the stand-in compiles against the real cv::InputArray / cv::OutputArray.
+class _InputArray {
+ public:
+  _InputArray(const Mat& m) : m_(&m) {}
+  Mat getMat() const { return Mat(m_->rows, m_->cols, m_->type(), m_->data, m_->step); }
+  bool empty() const { return m_->empty(); }
+ private:
+  const Mat* m_;
+};
+class _OutputArray {
+ public:
+  _OutputArray(Mat& m) : m_(&m) {}
+  void create(int r, int c, int type) const { m_->create(r, c, type); }
+  void release() const { m_->release(); }
+  Mat getMat() const { return Mat(m_->rows, m_->cols, m_->type(), m_->data, m_->step); }
+ private:
+  Mat* m_;
+};
+typedef const _InputArray& InputArray;
+typedef const _OutputArray& OutputArray;
 namespace line_descriptor {
 struct KeyLine {
   float angle = 0; int class_id = 0; int octave = 0; Point2f pt; float response = 0; float size = 0;

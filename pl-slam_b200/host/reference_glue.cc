@@ -264,7 +264,7 @@ static int pose_optimization(Frame* pFrame, int mode) {
   if ((mode == 2 ? nl : np) < 3) return 0;                       // Optimizer.cc:846-847: nothing happened, pose untouched
   for (int k = 0; k < np; k++) pFrame->mvbOutlier[pidx[k]] = po[k] != 0;
   for (int k = 0; k < nl; k++) pFrame->mvbLineOutlier[lidx[k]] = lo[k] != 0;
-  cv::Mat pose(4, 4, cv::CV_32F);
+  cv::Mat pose(4, 4, CV_32F);
   for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) pose.at<float>(r, c) = Tout[4 * r + c];
   pFrame->SetPose(pose);
   return n;
@@ -370,12 +370,12 @@ void Optimizer::LocalBundleAdjustmentWithLine(KeyFrame* pKF, bool* pbStopFlag, M
   for (size_t e = 0; e < leLn.size(); e++)
     if (leErase[e]) { KeyFrame* k = kfs[leEraseKf[e]]; k->EraseMapLineMatch(vpMapLineEdge[e]); vpMapLineEdge[e]->EraseObservation(k); }
   for (size_t i = 0; i < lLocalKeyFrames.size(); i++) {          // :2069-2076 (local keyframes only)
-    cv::Mat pose(4, 4, cv::CV_32F);
+    cv::Mat pose(4, 4, CV_32F);
     for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) pose.at<float>(r, c) = Tout[16 * i + 4 * r + c];
     kfs[i]->SetPose(pose);
   }
   for (size_t i = 0; i < pts.size(); i++) {
-    cv::Mat X(3, 1, cv::CV_32F);
+    cv::Mat X(3, 1, CV_32F);
     for (int k = 0; k < 3; k++) X.at<float>(k) = Xout[3 * i + k];
     pts[i]->SetWorldPos(X);
     pts[i]->UpdateNormalAndDepth();

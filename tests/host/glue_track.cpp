@@ -29,7 +29,7 @@ static std::vector<uint8_t> slurp(const char* path) {
 static FILE* g_out;
 template <typename T> static void put(const T* p, size_t n) { fwrite(p, sizeof(T), n, g_out); }
 static void puti(int v) { put(&v, 1); }
-static cv::Mat mat31(float a, float b, float c) { cv::Mat m(3, 1, cv::CV_32F); m.at<float>(0) = a; m.at<float>(1) = b; m.at<float>(2) = c; return m; }
+static cv::Mat mat31(float a, float b, float c) { cv::Mat m(3, 1, CV_32F); m.at<float>(0) = a; m.at<float>(1) = b; m.at<float>(2) = c; return m; }
 
 int main(int argc, char** argv) {
   if (argc < 6) { fprintf(stderr, "usage: glue_track f1.raw f2.raw W H out.bin\n"); return 2; }
@@ -48,7 +48,7 @@ int main(int argc, char** argv) {
   Frame F[2];                                                       // Frame::Frame (mono), src/Frame.cc:215-250
   cv::Mat none;
   for (int k = 0; k < 2; k++) {
-    cv::Mat im(H, W, cv::CV_8UC1, img[k].data()), u(H, W, cv::CV_8UC1);
+    cv::Mat im(H, W, CV_8UC1, img[k].data()), u(H, W, CV_8UC1);
     orb(im, none, F[k].mvKeys, F[k].mDescriptors);
     if (pl_undistort_remap(und, im.ptr(0), W, u.ptr(0), W) != PL_OK) return 3;
     lsd(u, none, F[k].mvKeylinesUn, F[k].mLdesc, F[k].mvKeyLineFunctions);
@@ -65,7 +65,7 @@ int main(int argc, char** argv) {
   Frame& Last = F[0];
   Frame& Cur = F[1];
   // the map seen by the last frame: every keypoint / keyline back-projected to a deterministic depth (last pose = identity)
-  cv::Mat I(4, 4, cv::CV_32F);
+  cv::Mat I(4, 4, CV_32F);
   for (int i = 0; i < 4; i++) I.at<float>(i, i) = 1.f;
   Last.mTcw = I; Last.mOw = mat31(0, 0, 0);
   std::vector<std::unique_ptr<MapPoint>> mps;

@@ -12,7 +12,7 @@ int main(int argc, char** argv) {
   FILE* f = fopen(argv[1], "rb");
   if (!f || fread(buf.data(), 1, buf.size(), f) != buf.size()) { fprintf(stderr, "cannot read frame\n"); return 2; }
   fclose(f);
-  cv::Mat im(H, W, cv::CV_8UC1, buf.data()), none;
+  cv::Mat im(H, W, CV_8UC1, buf.data()), none;
   ORB_SLAM2::ORBextractor orb(1000, 1.2f, 8, 20, 7);
   std::vector<cv::KeyPoint> keys; cv::Mat desc;
   orb(im, none, keys, desc);

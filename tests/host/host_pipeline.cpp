@@ -30,7 +30,7 @@ int main(int argc, char** argv) {
   FrameView F[2];
   cv::Mat none;
   for (int k = 0; k < 2; k++) {                                   // Frame::Frame (mono), src/Frame.cc:215-250
-    cv::Mat im(H, W, cv::CV_8UC1, k ? b2.data() : b1.data()), und;
+    cv::Mat im(H, W, CV_8UC1, k ? b2.data() : b1.data()), und;
     orb(im, none, F[k].mvKeys, F[k].mDescriptors);
     cam.remap(im, und);
     lsd(und, none, F[k].mvKeylinesUn, F[k].mLdesc, F[k].mvKeyLineFunctions);

@@ -279,6 +279,19 @@ typedef struct PLBAProblem {
 int pl_local_ba(const PLBAProblem* p, const int* stop_flag_dev, float* kf_Tcw_out, float* pt_Xw_out, double* ln_Xw_out,
                 uint8_t* pe_erase, uint8_t* le_erase, int* le_erase_kf, int* iterations);
 
+/* Optimizer::BundleAdjustment with lines (src/Optimizer.cc:275-638; GlobalBundleAdjustemnt :41-58 passes the whole map):
+ * ONE Levenberg-Marquardt optimize(n_iterations) over all keyframes (kf_fixed = mnId == 0), map points and map-line end points,
+ * Huber kernels (sqrt(5.99) points, sqrt(3.84) line end points) iff robust, line information = identity, every line edge on
+ * the observing keyframe's own intrinsics (K_end of PLBAProblem is not read); no outlier rounds, nothing is erased.
+ * stop_flag_host: the reference's pbStopFlag (HOST int, polled between iterations and trials; NULL = never).
+ * Outputs: every keyframe's pose (the reference calls SetPose(toCvMat(estimate)) on all of them, :549-556), points (a point
+ * without observations keeps its input, :411-416), line end points (through float like Converter::toCvMat, :621-625).
+ * The nLoopKF != 0 variant only changes WHERE the caller stores these (mTcwGBA / mPosGBA, :557-562): caller's business.
+ * Multi-CTA: reduced pose system built per non-zero 6x6 block in landmark order (no atomics: bit-reproducible), dense
+ * blocked Cholesky; solve_ms (may be NULL) = device time of the whole optimisation (CUDA events). */
+int pl_global_ba(const PLBAProblem* p, int n_iterations, int robust, const int* stop_flag_host, float* kf_Tcw_out,
+                 float* pt_Xw_out, double* ln_Xw_out, int* iterations, float* solve_ms);
+
 /* ------------------------------------------------------------------ line matching by projection
  * Frame::AssignFeaturesToGridForLine (Frame.cc:296-320): CSR of mGridForLine (cell = ix*48+iy); returns #items. */
 int pl_frame_assign_grid_lines(const void* keylines_un /*68 B records*/, int n, const float* bounds, int* cell_start /*[3073]*/,

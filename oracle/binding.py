@@ -338,6 +338,25 @@ def local_ba(p, stop_flag=None):
     return out
 
 
+def global_ba(p, n_iterations=5, robust=True, stop_flag=None):
+    """Optimizer::BundleAdjustment with lines (Optimizer.cc:275-638).  Returns dict(kf_Tcw, pt_Xw, ln_Xw, its)."""
+    n_kf, n_pt, n_ln, n_pe, n_le = len(p["kf_fixed"]), len(p["pt_Xw"]), len(p["ln_Xw"]), len(p["pe_kf"]), len(p["le_kf"])
+    out = dict(kf_Tcw=np.zeros((n_kf, 16), np.float32), pt_Xw=np.zeros((max(n_pt, 1), 3), np.float32),
+               ln_Xw=np.zeros((max(n_ln, 1), 6), np.float64))
+    its = C.c_int(0)
+    sf = None if stop_flag is None else np.ascontiguousarray(stop_flag, np.int32)
+    f = lib().oracle_global_ba
+    f.argtypes = [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + \
+                 [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 5
+    a = {k: np.ascontiguousarray(v) for k, v in p.items() if isinstance(v, np.ndarray)}
+    f(n_kf, _p(a["kf_Tcw"]), _p(a["kf_fixed"]), _p(a["kf_K"]), n_pt, _p(a["pt_Xw"]), n_ln, _p(a["ln_Xw"]), n_pe,
+      _p(a["pe_kf"]), _p(a["pe_pt"]), _p(a["pe_obs"]), _p(a["pe_inv_sigma2"]), n_le, _p(a["le_kf"]), _p(a["le_ln"]), _p(a["le_func"]),
+      int(n_iterations), int(bool(robust)), _p(sf), _p(out["kf_Tcw"]), _p(out["pt_Xw"]), _p(out["ln_Xw"]), C.byref(its))
+    out["its"] = its.value
+    out["pt_Xw"] = out["pt_Xw"][:n_pt]; out["ln_Xw"] = out["ln_Xw"][:n_ln]
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- line matching by projection
 def _compact_kl(kl68):
     """68-byte KeyLine records -> the 7-field flat records oracle_match.cpp reads."""

@@ -14,6 +14,12 @@
 // twice (:2030-2031) and pairs observation i with the keyframe of observation i/2 (vpLineEdgeKF is pushed twice per
 // observation, :1924,1948).  Parity status: unpinned (no expected values in the reference); known-answer test =
 // recovery of the ground-truth structure on synthetic windows (tests/test_oracle_ba.py).
+//
+// oracle_global_ba: Optimizer::BundleAdjustment with lines (src/Optimizer.cc:275-638, called by GlobalBundleAdjustemnt :41-58):
+// the same graph types and the same Levenberg-Marquardt, ONE optimize(nIterations) call, no outlier rounds; Huber deltas
+// sqrt(5.99) (points, :316) and sqrt(3.84) (line end points, :318) only if bRobust; line information = identity (invSigma = 1,
+// :278); every line edge uses the OBSERVING keyframe's intrinsics (:472-475,526-529); edges are inserted points first, then
+// all start-point edges, then all end-point edges (:321-536).
 
 #include <cmath>
 #include <cstdint>
@@ -70,6 +76,9 @@ struct BA {
   std::vector<uint8_t> p_lvl, l_lvl;   // level (1 = excluded)
   bool p_robust = true, l_robust = true;
   double info_line = 0.5;           // invSigma = 0.5 (Optimizer.cc:1647)
+  double delta_p = kDeltaMono, delta_l = kDeltaLine;
+  bool end_uses_Kend = true;        // local BA quirk (Optimizer.cc:1939-1942); global BA: the observing keyframe's own K
+  bool starts_first = false;        // global BA inserts all start-point edges, then all end-point edges
   volatile const int* stop = nullptr;
   int n_lm() const { return n_pt + 2 * n_ln; }
   bool terminate() const { return stop && *stop; }
@@ -86,7 +95,7 @@ void point_err(const BA& P, const SE3& T, const double* X, int e, double* out) {
 double line_err(const BA& P, const SE3& T, const double* X, int e, int end) {
   double c[3], k[4], u, v;
   se3_map(T, X, c);
-  if (end == 0) Kd(P.K, P.le_kf[e], k); else for (int i = 0; i < 4; i++) k[i] = P.Kend[i];
+  if (end == 0 || !P.end_uses_Kend) Kd(P.K, P.le_kf[e], k); else for (int i = 0; i < 4; i++) k[i] = P.Kend[i];
   cam(c, k, u, v);
   const double* l = P.le_f + 3 * e;
   return l[0] * u + l[1] * v + l[2];
@@ -103,13 +112,14 @@ double active_chi2(const BA& P) {
   double chi = 0, r0, r1;
   for (int e = 0; e < P.n_pe; e++) if (!P.p_lvl[e]) {
     double w = (double)P.pe_w[e], c2 = P.perr[2 * e] * (w * P.perr[2 * e]) + P.perr[2 * e + 1] * (w * P.perr[2 * e + 1]);
-    if (P.p_robust) { huber(c2, kDeltaMono, r0, r1); chi += r0; } else chi += c2;
+    if (P.p_robust) { huber(c2, P.delta_p, r0, r1); chi += r0; } else chi += c2;
   }
-  for (int e = 0; e < P.n_le; e++) if (!P.l_lvl[e])
-    for (int end = 0; end < 2; end++) {
-      double c2 = P.lerr[2 * e + end] * (P.info_line * P.lerr[2 * e + end]);
-      if (P.l_robust) { huber(c2, kDeltaLine, r0, r1); chi += r0; } else chi += c2;
-    }
+  for (int pass = 0; pass < (P.starts_first ? 2 : 1); pass++)
+    for (int e = 0; e < P.n_le; e++) if (!P.l_lvl[e])
+      for (int end = (P.starts_first ? pass : 0); end < (P.starts_first ? pass + 1 : 2); end++) {
+        double c2 = P.lerr[2 * e + end] * (P.info_line * P.lerr[2 * e + end]);
+        if (P.l_robust) { huber(c2, P.delta_l, r0, r1); chi += r0; } else chi += c2;
+      }
   return chi;
 }
 
@@ -178,11 +188,12 @@ void build_system(BA& P, System& S) {
     B[6] = (1 + y * y / z_2) * fy; B[7] = -x * y / z_2 * fy; B[8] = -x / z * fy; B[9] = 0; B[10] = -1. / z * fy; B[11] = y / z_2 * fy;
     const double w = (double)P.pe_w[e], e0 = P.perr[2 * e], e1 = P.perr[2 * e + 1];
     double omr[2] = {-(w * e0), -(w * e1)}, wgt = w;
-    if (P.p_robust) { huber(e0 * (w * e0) + e1 * (w * e1), kDeltaMono, r0, r1); omr[0] *= r1; omr[1] *= r1; wgt = r1 * w; }
+    if (P.p_robust) { huber(e0 * (w * e0) + e1 * (w * e1), P.delta_p, r0, r1); omr[0] *= r1; omr[1] *= r1; wgt = r1 * w; }
     accumulate(kf, P.pe_pt[e], A, B, omr, wgt, 2);
   }
+  for (int pass = 0; pass < (P.starts_first ? 2 : 1); pass++)
   for (int e = 0; e < P.n_le; e++) if (!P.l_lvl[e])
-    for (int end = 0; end < 2; end++) {
+    for (int end = (P.starts_first ? pass : 0); end < (P.starts_first ? pass + 1 : 2); end++) {
       const int kf = P.le_kf[e], lm = P.n_pt + 2 * P.le_ln[e] + end;
       const double* X = &P.X[3 * lm];
       double A[3], B[6];   // only error component 0 is non-constant
@@ -194,7 +205,7 @@ void build_system(BA& P, System& S) {
       for (int d = 0; d < 6; d++) B[d] = 5e8 * (line_err(P, Tp[(size_t)kf * 6 + d], X, e, end) - line_err(P, Tm[(size_t)kf * 6 + d], X, e, end));
       const double er = P.lerr[2 * e + end], w = P.info_line;
       double omr[1] = {-(w * er)}, wgt = w;
-      if (P.l_robust) { huber(er * (w * er), kDeltaLine, r0, r1); omr[0] *= r1; wgt = r1 * w; }
+      if (P.l_robust) { huber(er * (w * er), P.delta_l, r0, r1); omr[0] *= r1; wgt = r1 * w; }
       accumulate(kf, lm, A, B, omr, wgt, 1);
     }
 }
@@ -354,6 +365,39 @@ extern "C" int oracle_local_ba(int n_kf, const float* kf_Tcw, const uint8_t* kf_
   }
   for (int i = 0; i < 3 * n_pt; i++) pt_Xw_out[i] = (float)P.X[i];
   for (int i = 0; i < 6 * n_ln; i++) ln_Xw_out[i] = (double)(float)P.X[3 * n_pt + i];   // via Converter::toCvMat (float) -> Vector6d
+  if (iterations_out) *iterations_out = its;
+  return 0;
+}
+
+extern "C" int oracle_global_ba(int n_kf, const float* kf_Tcw, const uint8_t* kf_fixed, const float* kf_K, int n_pt, const float* pt_Xw,
+                                int n_ln, const double* ln_Xw, int n_pe, const int* pe_kf, const int* pe_pt, const float* pe_obs,
+                                const float* pe_inv_sigma2, int n_le, const int* le_kf, const int* le_ln, const double* le_func,
+                                int n_iterations, int robust, const int* stop_flag, float* kf_Tcw_out, float* pt_Xw_out, double* ln_Xw_out,
+                                int* iterations_out) {
+  BA P;
+  P.n_kf = n_kf; P.n_pt = n_pt; P.n_ln = n_ln; P.n_pe = n_pe; P.n_le = n_le;
+  P.T.resize(n_kf); P.fixed.assign(kf_fixed, kf_fixed + n_kf); P.K = kf_K;
+  for (int i = 0; i < 4; i++) P.Kend[i] = 0;
+  for (int k = 0; k < n_kf; k++) P.T[k] = se3_from_cv(kf_Tcw + 16 * k);
+  P.X.resize((size_t)3 * (n_pt + 2 * n_ln));
+  for (int i = 0; i < 3 * n_pt; i++) P.X[i] = (double)pt_Xw[i];
+  for (int i = 0; i < 6 * n_ln; i++) P.X[3 * n_pt + i] = ln_Xw[i];
+  P.pe_kf = pe_kf; P.pe_pt = pe_pt; P.pe_obs = pe_obs; P.pe_w = pe_inv_sigma2; P.le_kf = le_kf; P.le_ln = le_ln; P.le_f = le_func;
+  P.perr.assign((size_t)2 * n_pe + 2, 0); P.lerr.assign((size_t)2 * n_le + 2, 0);
+  P.p_lvl.assign(n_pe + 1, 0); P.l_lvl.assign(n_le + 1, 0);
+  P.stop = stop_flag;
+  P.p_robust = P.l_robust = robust != 0;
+  P.info_line = 1.0;
+  P.delta_p = (double)(float)std::sqrt(5.99); P.delta_l = (double)(float)std::sqrt(3.84);
+  P.end_uses_Kend = false; P.starts_first = true;
+  const int its = optimize(P, n_iterations);
+  // landmarks without any observation are not part of the graph (vbNotIncludedMP, :411-416): their input comes back
+  std::vector<uint8_t> seen((size_t)n_pt + 2 * n_ln + 1, 0);
+  for (int e = 0; e < n_pe; e++) seen[pe_pt[e]] = 1;
+  for (int e = 0; e < n_le; e++) { seen[n_pt + 2 * le_ln[e]] = 1; seen[n_pt + 2 * le_ln[e] + 1] = 1; }
+  for (int k = 0; k < n_kf; k++) se3_to_cv(P.T[k], kf_Tcw_out + 16 * k);      // every keyframe gets SetPose(toCvMat(estimate)) (:549-556)
+  for (int i = 0; i < n_pt; i++) for (int a = 0; a < 3; a++) pt_Xw_out[3 * i + a] = seen[i] ? (float)P.X[3 * i + a] : pt_Xw[3 * i + a];
+  for (int i = 0; i < 6 * n_ln; i++) ln_Xw_out[i] = (double)(float)P.X[3 * n_pt + i];
   if (iterations_out) *iterations_out = its;
   return 0;
 }

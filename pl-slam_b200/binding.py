@@ -581,6 +581,31 @@ def LocalBundleAdjustmentWithLine(p, stop_flag_dev=None):
 Optimizer.LocalBundleAdjustmentWithLine = staticmethod(LocalBundleAdjustmentWithLine)
 
 
+def GlobalBundleAdjustemnt(p, nIterations=5, bRobust=True, stop_flag=None):
+    """Optimizer::GlobalBundleAdjustemnt / BundleAdjustment with lines (Optimizer.cc:41-58,275-638; the reference's spelling) on
+    a flattened map (dict as made by synth.synth_ba_problem; K_end is not read).  stop_flag: None or an int32 numpy scalar
+    array the caller may set while the call runs.  Returns dict(kf_Tcw, pt_Xw, ln_Xw, its, solve_ms)."""
+    a = {k: np.ascontiguousarray(v) for k, v in p.items() if isinstance(v, np.ndarray)}
+    n_kf, n_pt, n_ln, n_pe, n_le = len(a["kf_fixed"]), len(a["pt_Xw"]), len(a["ln_Xw"]), len(a["pe_kf"]), len(a["le_kf"])
+    P = PLBAProblem(n_kf, _p(a["kf_Tcw"]), _p(a["kf_fixed"]), _p(a["kf_K"]), (C.c_float * 4)(0, 0, 0, 0),
+                    n_pt, _p(a["pt_Xw"]), n_ln, _p(a["ln_Xw"]), n_pe, _p(a["pe_kf"]), _p(a["pe_pt"]), _p(a["pe_obs"]),
+                    _p(a["pe_inv_sigma2"]), n_le, _p(a["le_kf"]), _p(a["le_ln"]), _p(a["le_func"]))
+    out = dict(kf_Tcw=np.zeros((n_kf, 16), np.float32), pt_Xw=np.zeros((max(n_pt, 1), 3), np.float32),
+               ln_Xw=np.zeros((max(n_ln, 1), 6), np.float64))
+    its = C.c_int(0); ms = C.c_float(0)
+    f = lib().pl_global_ba
+    f.argtypes = [C.POINTER(PLBAProblem), C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
+    sf = None if stop_flag is None else _p(stop_flag)
+    check(f(C.byref(P), int(nIterations), int(bool(bRobust)), sf, _p(out["kf_Tcw"]), _p(out["pt_Xw"]), _p(out["ln_Xw"]),
+            C.byref(its), C.byref(ms)))
+    out["its"] = its.value; out["solve_ms"] = ms.value
+    out["pt_Xw"] = out["pt_Xw"][:n_pt]; out["ln_Xw"] = out["ln_Xw"][:n_ln]
+    return out
+
+
+Optimizer.GlobalBundleAdjustemnt = staticmethod(GlobalBundleAdjustemnt)
+
+
 # ---------------------------------------------------------------------------------------------- line matching by projection
 def frame_assign_grid_lines(keylines_un, bounds):
     """Frame::AssignFeaturesToGridForLine (reference src/Frame.cc:296-320) -> CSR (cell_start[3073], cell_items)."""

@@ -51,6 +51,7 @@ struct LineParams {
   int seg_cap, capL, nfeatures;
   double min_line_length;
   double prec, prec_hi, p, density_th;   // prec_hi: see region_grow_t
+  float sure_ca2, sure_cn2;              // cos^2(prec -/+ 0.05 deg): lsd_grow_ordered.cuh Sure
 };
 
 // ---------------------------------------------------------------------------------------------- shared helpers
@@ -908,6 +909,10 @@ extern "C" int pl_line_create(const PLLineConfig* cfg, PLLine** out) {
     while (!((twopi - c) <= P.prec)) c = nextafter(c, 10.0);
     P.prec_hi = c;
   }
+  {
+    const double M = 0.05 * M_PI / 180.0, ca = cos(P.prec - M), cn = cos(P.prec + M);
+    P.sure_ca2 = (float)(ca * ca); P.sure_cn2 = (float)(cn * cn);
+  }
   const double rho = QUANT / sin(P.prec);
   int s = 0;
   while (sqrt((double)(s + 1) / 4.0) <= rho) s++;   // largest s with sqrt(s/4) <= rho
@@ -1028,8 +1033,13 @@ extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int str
     // many frames: one warp per frame, the 32 lanes on one region at a time (lsd_grow_ordered.cuh); the list pool and the
     // status words of the speculative kernel serve as region list and far-pixel mask
     if (h->timing) PL_CUDA(cudaEventRecord(h->ev0, st));
-    k_lsd_grow_ordered<<<B, 32, 0, st>>>(P, h->d_rec, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_pool, h->GP.pool_cap, h->d_st, h->d_wtab,
-                                         h->d_segs, h->d_nseg, h->d_overflow, B);
+    static const int pre_maxb = getenv("PLSLAM_LSD_PRE_MAXB") ? atoi(getenv("PLSLAM_LSD_PRE_MAXB")) : 256;
+    if (B <= pre_maxb)
+      k_lsd_grow_ordered<true><<<B, 32, 0, st>>>(P, h->d_rec, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_pool, h->GP.pool_cap, h->d_st, h->d_wtab,
+                                                 h->d_segs, h->d_nseg, h->d_overflow, B);
+    else
+      k_lsd_grow_ordered<false><<<B, 32, 0, st>>>(P, h->d_rec, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_pool, h->GP.pool_cap, h->d_st, h->d_wtab,
+                                                  h->d_segs, h->d_nseg, h->d_overflow, B);
     PL_LAUNCH_CHECK();
   }
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev1, st));
@@ -1137,3 +1147,12 @@ extern "C" int pl_line_debug_order(PLLine* h, int frame, unsigned* out, int cap)
   }
   return n;
 }
+
+#ifdef PL_GROW_STATS
+extern "C" int pl_line_grow_stats(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  if (out) cudaMemcpyFromSymbol(out, pl::ord::g_grow_stats, sizeof(unsigned long long) * 24);
+  if (reset) { unsigned long long z[24] = {0}; cudaMemcpyToSymbol(pl::ord::g_grow_stats, z, sizeof(z)); }
+  return 0;
+}
+#endif

@@ -21,15 +21,34 @@ namespace ord {
 
 using lg::kDegToRads;
 using lg::kPI;
-constexpr int kORing = 512;
+#ifndef PL_GROW_RING
+#define PL_GROW_RING 256
+#endif
+#ifndef PL_GROW_BM
+#define PL_GROW_BM 1
+#endif
+#ifndef PL_GROW_SQRT
+#define PL_GROW_SQRT 1
+#endif
+constexpr int kORing = PL_GROW_RING;
+constexpr int kWin = 64, kWinHalf = 32, kWinWords = kWin * kWin / 32;   // per-region window of known not-free pixels (bits)
 constexpr int kUsedO = 0;
 
 struct Ctx {
   int4* REC; const int* SQ; const float2* S2; const double* wtab; unsigned* R; unsigned* ring; unsigned* mask;
   double* red;          // shared memory, 3 x 32 doubles: the per-pixel terms of one batch, for the ordered sums
+  unsigned* bm;         // shared memory, kWinWords: see region_grow
   int sw, sh, fill_off; // fill_off: scratch area inside R (beyond the largest possible region)
 };
 struct RectD { double x1, y1, x2, y2, width; };
+#ifdef PL_GROW_STATS
+__device__ unsigned long long g_grow_stats[24];
+#define GSTAT(i, v) do { if (lane == 0) atomicAdd(&g_grow_stats[i], (unsigned long long)(v)); } while (0)
+#define GSTAT_ALL(i, v) atomicAdd(&g_grow_stats[i], (unsigned long long)(v))
+#else
+#define GSTAT_ALL(i, v) do { } while (0)
+#define GSTAT(i, v) do { } while (0)
+#endif
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ int& own_of(const Ctx& C, int idx) { return reinterpret_cast<int*>(&C.REC[idx])[0]; }
@@ -74,22 +93,40 @@ __device__ __forceinline__ bool is_aligned_generic(double a, double theta, doubl
 // remaining candidate is tested against the CURRENT region angle at once, the first aligned one is added, which changes
 // the angle; a pixel added earlier in the same step invalidates its duplicates in the later neighbourhoods.
 // kFast: prec < pi/2, isAligned folded to  n <= prec || n >= prec_hi  (see lsd_grow_core.cuh aligned()).
+// Requests, not bytes, bound this kernel, and most of the 8 neighbours of a pixel inside a region are pixels the region already
+// owns: a 64 x 64 bit window around the seed (shared memory) remembers every pixel seen NOT free during this growth - taken by
+// this region, by an earlier one, or undefined.  Nothing becomes free while one region grows, so a set bit is final and the
+// record is not fetched again; pixels outside the window are simply always fetched.  The window is wiped at the end over the
+// rows the growth can have reached (a pixel expanded in step s is at most s - 1 away from the seed).
+// Alignment WITHOUT the arctangent for the clear cases (kFast only).  The exact test compares the candidate's angle a with
+// reg_angle = fastAtan2(sumdy, sumdx); the candidate's record also carries (cos a, sin a), so the TRUE angle D between the sum
+// vector and the candidate is known from one dot product: cos D = (sumdx*c + sumdy*s) / |sum|.  fastAtan2's polynomial is within
+// 0.0096 degrees of the true arctangent (measured over 4e7 vectors, tests/test_oracle_line.py pins the bound), float(angle)
+// rounding is < 1e-4 degrees, so with a margin M = 0.05 degrees:  D <= prec - M  implies the exact test says aligned, D >= prec + M
+// implies it says not aligned.  Only candidates inside the 2M band need the exact arctangent (kSure.ca2 / cn2 = cos^2(prec -/+ M)).
+struct Sure { float ca2, cn2; };
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <bool kFast>
-__device__ __forceinline__ int region_grow(const Ctx& C, unsigned seed, double prec, double prec_hi, double& reg_angle_out, int lane) {
+__device__ __forceinline__ int region_grow(const Ctx& C, unsigned seed, double prec, double prec_hi, Sure sure, double& reg_angle_out, int lane) {
   const int sidx = (int)(seed >> 16) * C.sw + (int)(seed & 0xffffu);
   const float2 s0 = __ldg(&C.S2[sidx]);
   double reg_angle = (double)__int_as_float(angle_bits(C, sidx)) * kDegToRads;
   float sumdx = s0.x, sumdy = s0.y;
   bool dirty = false;          // reg_angle lags the sums (it is the seed's own angle until the first pixel is added)
-  if (lane == 0) { C.R[0] = seed; C.ring[0] = seed; own_of(C, sidx) = kUsedO; }
-  int cnt = 1;
+  if (lane == 0) { C.R[0] = seed; C.ring[0] = seed; own_of(C, sidx) = kUsedO; C.bm[kWinHalf * (kWin / 32) + 1] = 1u; }
+  int cnt = 1, nsteps = 0;
   __syncwarp();
   const int grp = lane >> 3, kk8 = lane & 7, kk = kk8 + (kk8 >= 4);
   const int ox = kk % 3 - 1, oy = kk / 3 - 1;
+  const int wx0 = (int)(seed & 0xffffu) - kWinHalf, wy0 = (int)(seed >> 16) - kWinHalf;
   for (int i = 0; i < cnt;) {
     const int m = min(4, cnt - i);
+    GSTAT(kFast ? 1 : 10, 1);
+    nsteps++;
     bool valid = false;
-    int idx = -1;
+    int idx = -1, widx = -1;
+    unsigned wbit = 0u;
     unsigned pk = 0xffff0000u | (unsigned)lane;      // unique per lane unless it names a real pixel
     int ab = 0;
     float2 csv = make_float2(0.f, 0.f);
@@ -98,28 +135,65 @@ __device__ __forceinline__ int region_grow(const Ctx& C, unsigned seed, double p
       const unsigned p = (cnt - qi <= kORing) ? C.ring[qi & (kORing - 1)] : C.R[qi];
       const int xx = (int)(p & 0xffffu) + ox, yy = (int)(p >> 16) + oy;
       if (xx >= 0 && yy >= 0 && xx < C.sw && yy < C.sh) {
-        idx = yy * C.sw + xx;
-        const int4 v = C.REC[idx];
-        if (v.x == lg::kFree) {                       // defined and not USED
-          valid = true; ab = v.y;
-          csv = make_float2(__int_as_float(v.z), __int_as_float(v.w));
-          pk = (unsigned)xx | ((unsigned)yy << 16);
+        const unsigned dxw = (unsigned)(xx - wx0), dyw = (unsigned)(yy - wy0);
+        bool known = false;
+        if (PL_GROW_BM && dxw < (unsigned)kWin && dyw < (unsigned)kWin) {
+          widx = (int)(dyw * (kWin / 32) + (dxw >> 5)); wbit = 1u << (dxw & 31u);
+          known = (C.bm[widx] & wbit) != 0u;
+        }
+        if (!known) {
+          GSTAT_ALL(kFast ? 16 : 17, 1);
+          idx = yy * C.sw + xx;
+          const int4 v = C.REC[idx];
+          if (v.x == lg::kFree) {                       // defined and not USED
+            valid = true; ab = v.y;
+            csv = make_float2(__int_as_float(v.z), __int_as_float(v.w));
+            pk = (unsigned)xx | ((unsigned)yy << 16);
+          } else if (widx >= 0) atomicOr(&C.bm[widx], wbit);
         }
       }
     }
     i += m;
+#ifndef PL_GROW_PF
+#define PL_GROW_PF 0
+#endif
+    if (PL_GROW_PF && i + grp < cnt) {       // the next step's neighbourhoods are already known: into L1 while this step's candidates are decided
+      const int qn = i + grp;
+      const unsigned p = (cnt - qn <= kORing) ? C.ring[qn & (kORing - 1)] : C.R[qn];
+      const int xx = min(max((int)(p & 0xffffu) + ox, 0), C.sw - 1), yy = min(max((int)(p >> 16) + oy, 0), C.sh - 1);
+      if (PL_GROW_PF == 1) prefetch_l1(&C.REC[yy * C.sw + xx]); else prefetch_l2(&C.REC[yy * C.sw + xx]);
+    }
     unsigned live = __ballot_sync(0xffffffffu, valid);
     if (live == 0u) continue;
+    GSTAT(2, 1);
     const double a = (double)__int_as_float(ab) * kDegToRads;
     int mypos = -1;
     while (live) {
-      if (dirty) { reg_angle = (double)lg::fast_atan2_deg(sumdy, sumdx) * kDegToRads; dirty = false; }
-      bool al;
-      if (kFast) { const double n1 = fabs(reg_angle - a); al = (n1 <= prec) || (n1 >= prec_hi); }
-      else al = is_aligned_generic(a, reg_angle, prec);
-      const unsigned A = __ballot_sync(0xffffffffu, al) & live;
-      if (!A) break;
+      GSTAT(3, 1);
+      unsigned A;
+      bool exact = !kFast;
+      if (kFast) {
+        const float n2 = __fmaf_rn(sumdx, sumdx, __fmul_rn(sumdy, sumdy));
+        const float dot = __fmaf_rn(sumdx, csv.x, __fmul_rn(sumdy, csv.y)), d2 = __fmul_rn(dot, dot);
+        const bool sure_al = dot > 0.f && d2 >= __fmul_rn(sure.ca2, n2);
+        const bool maybe = dot > 0.f && d2 > __fmul_rn(sure.cn2, n2);       // not (surely not aligned)
+        const unsigned SA = __ballot_sync(0xffffffffu, sure_al) & live, MB = __ballot_sync(0xffffffffu, maybe) & live;
+        if (n2 < 0.25f) exact = true;                 // (cannot happen with prec < pi/2; the band test needs a direction)
+        else if (MB == 0u) break;
+        else if ((MB & (0u - MB)) & SA) A = SA;       // the first candidate that may be aligned surely is: no arctangent
+        else exact = true;
+      }
+      if (exact) {
+        GSTAT(5, 1);
+        if (dirty) { reg_angle = (double)lg::fast_atan2_deg(sumdy, sumdx) * kDegToRads; dirty = false; }
+        bool al;
+        if (kFast) { const double n1 = fabs(reg_angle - a); al = (n1 <= prec) || (n1 >= prec_hi); }
+        else al = is_aligned_generic(a, reg_angle, prec);
+        A = __ballot_sync(0xffffffffu, al) & live;
+        if (!A) break;
+      }
       const int k = __ffs(A) - 1;
+      GSTAT(kFast ? 4 : 11, 1);
       if (lane == k) mypos = cnt;
       cnt++;
       sumdx = __fadd_rn(sumdx, __shfl_sync(0xffffffffu, csv.x, k));
@@ -129,6 +203,7 @@ __device__ __forceinline__ int region_grow(const Ctx& C, unsigned seed, double p
       live &= ~(((2u << k) - 1u) | __ballot_sync(0xffffffffu, pk == __shfl_sync(0xffffffffu, pk, k)));
     }
     if (mypos >= 0) {      // publish: every accepted lane owns its pixel
+      if (widx >= 0) atomicOr(&C.bm[widx], wbit);
       own_of(C, idx) = kUsedO;
       C.R[mypos] = pk;
       C.ring[mypos & (kORing - 1)] = pk;
@@ -137,23 +212,39 @@ __device__ __forceinline__ int region_grow(const Ctx& C, unsigned seed, double p
   }
   if (dirty) reg_angle = (double)lg::fast_atan2_deg(sumdy, sumdx) * kDegToRads;
   reg_angle_out = reg_angle;
+  {   // wipe the window rows this growth can have reached
+    const int lo = max(0, kWinHalf - nsteps - 1) * (kWin / 32), hi = (min(kWin - 1, kWinHalf + nsteps + 1) + 1) * (kWin / 32);
+    if (PL_GROW_BM) { for (int w = lo + lane; w < hi; w += 32) C.bm[w] = 0u; }
+    __syncwarp();
+  }
   return cnt;
 }
 __device__ __noinline__ int region_grow_cold(const Ctx& C, unsigned seed, double prec, double& reg_angle, int lane) {
-  return region_grow<false>(C, seed, prec, 0.0, reg_angle, lane);
+  return region_grow<false>(C, seed, prec, 0.0, Sure{0.f, 0.f}, reg_angle, lane);
 }
 
 // region2rect + get_theta: sums in list order (see the header), extents by exact max / min
+__device__ __forceinline__ double pixel_weight(const Ctx& C, int px, int py) {
+  // the gradient magnitude sqrt((gx^2 + gy^2) / 4) of the reference, from the integer sum of squares: an IEEE square root
+  // (/ 4.0 is exact) instead of a dependent table load - the kernel is bound by its memory requests, not by fp64
+  if (PL_GROW_SQRT) return sqrt((double)__ldg(&C.SQ[py * C.sw + px]) / 4.0);
+  return __ldg(&C.wtab[__ldg(&C.SQ[py * C.sw + px])]);
+}
 __device__ __noinline__ void region2rect(const Ctx& C, int n, double reg_angle, double prec, RectD& rec, int lane) {
   double acc = 0;                       // lanes 0, 1, 2: sum x*w, sum y*w, sum w
+  GSTAT(9, n); GSTAT(12, 1);
+  // the first two batches (64 pixels: most regions) stay in registers for the second and third pass
+  unsigned pc0 = 0, pc1 = 0;
+  double wc0 = 0, wc1 = 0;
   for (int i0 = 0; i0 < n; i0 += 32) {
     const int i = i0 + lane;
     double tx = 0, ty = 0, w = 0;
     if (i < n) {
       const unsigned p = C.R[i];
       const int px = (int)(p & 0xffffu), py = (int)(p >> 16);
-      w = __ldg(&C.wtab[__ldg(&C.SQ[py * C.sw + px])]);
+      w = pixel_weight(C, px, py);
       tx = (double)px * w; ty = (double)py * w;
+      if (i0 == 0) { pc0 = p; wc0 = w; } else if (i0 == 32) { pc1 = p; wc1 = w; }
     }
     ordered_add3(C, tx, ty, w, min(32, n - i0), acc, lane);
   }
@@ -164,9 +255,10 @@ __device__ __noinline__ void region2rect(const Ctx& C, int n, double reg_angle, 
     const int i = i0 + lane;
     double t1 = 0, t2 = 0, t3 = 0;
     if (i < n) {
-      const unsigned p = C.R[i];
+      unsigned p; double w;
+      if (i0 == 0) { p = pc0; w = wc0; } else if (i0 == 32) { p = pc1; w = wc1; }
+      else { p = C.R[i]; w = pixel_weight(C, (int)(p & 0xffffu), (int)(p >> 16)); }
       const int px = (int)(p & 0xffffu), py = (int)(p >> 16);
-      const double w = __ldg(&C.wtab[__ldg(&C.SQ[py * C.sw + px])]);
       const double dx = (double)px - x, dy = (double)py - y;
       t1 = dy * dy * w; t2 = dx * dx * w; t3 = dx * dy * w;
     }
@@ -181,7 +273,7 @@ __device__ __noinline__ void region2rect(const Ctx& C, int n, double reg_angle, 
   const double dx = cos(theta), dy = sin(theta);
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
   for (int i = lane; i < n; i += 32) {
-    const unsigned p = C.R[i];
+    const unsigned p = (i < 32) ? pc0 : (i < 64) ? pc1 : C.R[i];
     const double rdx = (double)(int)(p & 0xffffu) - x, rdy = (double)(int)(p >> 16) - y;
     const double l = rdx * dx + rdy * dy, w = -rdx * dy + rdy * dx;
     l_max = fmax(l_max, l); l_min = fmin(l_min, l);
@@ -200,6 +292,7 @@ __device__ __noinline__ void region2rect(const Ctx& C, int n, double reg_angle, 
 // the last kept element of the shrinking tail (in decreasing order); both rankings come from prefix sums over the bit mask.
 __device__ __noinline__ int reduce_round(const Ctx& C, int n, double xc, double yc, double radSq, int lane) {
   int kept = 0;
+  GSTAT(8, 1); GSTAT(13, n);
   for (int i0 = 0; i0 < n; i0 += 32) {
     const int i = i0 + lane;
     bool far = false;
@@ -270,6 +363,7 @@ __device__ __noinline__ bool refine(const Ctx& C, int& n, double reg_angle, doub
   double density = (double)n / (lg::dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
   if (density >= density_th) return true;
   released = true;              // from here on USED flags are cleared
+  GSTAT(7, 1);
   const unsigned p0 = C.R[0];
   const double xc = (double)(int)(p0 & 0xffffu), yc = (double)(int)(p0 >> 16);
   const double ang_c = (double)__int_as_float(angle_bits(C, (int)(p0 >> 16) * C.sw + (int)(p0 & 0xffffu))) * kDegToRads;
@@ -326,6 +420,9 @@ __device__ __noinline__ bool refine(const Ctx& C, int& n, double reg_angle, doub
 }  // namespace ord
 
 // One warp per frame; grid = frames (32 one-warp CTAs resident per SM: 4736 frames in one wave on 148 SMs).
+// kPre: examine the neighbourhoods of a whole batch of seeds up front (see below): fewer dependent round trips per frame, but
+// more requests - it pays when the GPU is not full of frames (measured: B = 1 88 -> 81 ms, B = 4736 +7 %).
+template <bool kPre>
 __global__ void __launch_bounds__(32, 32) k_lsd_grow_ordered(LineParams P, int4* __restrict__ REC, const int* __restrict__ SQ, const float2* __restrict__ seedcs,
                                                              const unsigned* __restrict__ order, const int* __restrict__ ndef,
                                                              unsigned* __restrict__ reg, int reg_stride, unsigned* __restrict__ mask, const double* __restrict__ wtab,
@@ -333,10 +430,13 @@ __global__ void __launch_bounds__(32, 32) k_lsd_grow_ordered(LineParams P, int4*
   using namespace ord;
   __shared__ unsigned ring[kORing];
   __shared__ double red[96];
+  __shared__ unsigned bm[kWinWords];
   const int lane = threadIdx.x & 31;
+  for (int w = lane; w < kWinWords; w += 32) bm[w] = 0u;
+  __syncwarp();
   for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
     const Ctx C = {REC + (long long)f * P.npx, SQ + (long long)f * P.npx, seedcs + (long long)f * P.npx, wtab,
-                   reg + (long long)f * reg_stride, ring, mask + (long long)f * P.npx, red, P.sw, P.sh, P.npx};
+                   reg + (long long)f * reg_stride, ring, mask + (long long)f * P.npx, red, bm, P.sw, P.sh, P.npx};
     const unsigned* O = order + (long long)f * P.npx;
     float4* S = segs + (long long)f * P.seg_cap;
     const int n = ndef[f];
@@ -345,22 +445,58 @@ __global__ void __launch_bounds__(32, 32) k_lsd_grow_ordered(LineParams P, int4*
       const int i = i0 + lane;
       const unsigned pix = (i < n) ? O[i] : 0u;
       const int pidx = (int)(pix >> 16) * P.sw + (int)(pix & 0xffffu);
-      unsigned todo = __ballot_sync(0xffffffffu, i < n && own_of(C, pidx) == lg::kFree);
-      // this batch's seeds that will grow: their seed record and 3x3 rows into L2; and the next batch's ownership words
-      if ((todo >> lane) & 1u) {
+      const int4 me = (i < n) ? C.REC[pidx] : make_int4(0, 0, 0, 0);
+      unsigned todo = __ballot_sync(0xffffffffu, i < n && me.x == lg::kFree);
+      // Seeds of this batch whose region cannot get past the seed itself: no FREE neighbour is aligned with the seed's own angle
+      // (the region angle of the first step).  Between two regions the set of free pixels only shrinks (a region releases only
+      // pixels it took itself), so "no free aligned neighbour now" still holds when the seed's turn comes: the region is the
+      // seed alone, below min_reg_size, and all that happens is that the seed becomes USED - at ITS turn, not earlier (an
+      // earlier seed of the batch may still grow over it).  The 8 records per seed are loaded by 32 lanes at once here instead
+      // of one region at a time; they also warm the lines the regions that do grow start from.
+      bool single = false;
+      if (kPre && ((todo >> lane) & 1u)) {
+        const int sx = (int)(pix & 0xffffu), sy = (int)(pix >> 16);
+        const double a0 = (double)__int_as_float(me.y) * lg::kDegToRads;
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const int kq = q + (q >= 4), xx = sx + kq % 3 - 1, yy = sy + kq / 3 - 1;
+          if (xx >= 0 && yy >= 0 && xx < P.sw && yy < P.sh) {
+            const int4 v = C.REC[yy * P.sw + xx];
+            const double n1 = fabs(a0 - (double)__int_as_float(v.y) * lg::kDegToRads);
+            any |= (v.x == lg::kFree) && ((n1 <= P.prec) || (n1 >= P.prec_hi));
+          }
+        }
+        single = !any;
+        prefetch_l2(&C.S2[pidx]);
+      }
+      if (!kPre && ((todo >> lane) & 1u)) {   // this batch's seeds that will grow: their seed record and 3x3 rows into L2
         prefetch_l2(&C.S2[pidx]);
         const int up = max(pidx - P.sw, 1), dn = min(pidx + P.sw, P.npx - 2);
         prefetch_l2(&C.REC[up - 1]); prefetch_l2(&C.REC[up + 1]); prefetch_l2(&C.REC[dn - 1]); prefetch_l2(&C.REC[dn + 1]);
         prefetch_l2(&C.REC[max(pidx, 1) - 1]); prefetch_l2(&C.REC[min(pidx, P.npx - 2) + 1]);
       }
+      const unsigned singles = __ballot_sync(0xffffffffu, single);
       if (i + 32 < n) { const unsigned pn = O[i + 32]; prefetch_l2(&C.REC[(int)(pn >> 16) * P.sw + (int)(pn & 0xffffu)]); }
       while (todo) {
+        {   // the lone seeds in front of the next seed that may grow: USED, nothing else
+          const unsigned grow = todo & ~singles;
+          const unsigned below = grow ? ((grow & (0u - grow)) - 1u) : 0xffffffffu;
+          if ((todo & singles & below) >> lane & 1u) own_of(C, pidx) = kUsedO;
+          todo &= ~below;
+          __syncwarp();
+          if (!todo) break;
+        }
         const int k = __ffs(todo) - 1;
         const unsigned seed = __shfl_sync(0xffffffffu, pix, k);
         double reg_angle;
         bool released = false;
-        int cnt = region_grow<true>(C, seed, P.prec, P.prec_hi, reg_angle, lane);
+        GSTAT(0, 1);
+        int cnt = region_grow<true>(C, seed, P.prec, P.prec_hi, Sure{P.sure_ca2, P.sure_cn2}, reg_angle, lane);
+        if (cnt == 1) GSTAT(14, 1);
+        if (cnt <= 4) GSTAT(15, 1);
         if (cnt >= P.min_reg_size) {
+          GSTAT(6, 1);
           RectD rec;
           region2rect(C, cnt, reg_angle, P.prec, rec, lane);
           if (refine(C, cnt, reg_angle, P.prec, rec, P.density_th, lane, released)) {

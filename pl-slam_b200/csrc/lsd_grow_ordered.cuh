@@ -21,23 +21,12 @@ namespace ord {
 
 using lg::kDegToRads;
 using lg::kPI;
-#ifndef PL_GROW_RING
-#define PL_GROW_RING 256
-#endif
-#ifndef PL_GROW_BM
-#define PL_GROW_BM 1
-#endif
-#ifndef PL_GROW_SQRT
-#define PL_GROW_SQRT 1
-#endif
-constexpr int kORing = PL_GROW_RING;
-constexpr int kWin = 64, kWinHalf = 32, kWinWords = kWin * kWin / 32;   // per-region window of known not-free pixels (bits)
+constexpr int kORing = 256;   // recent queue entries in shared memory (512 entries cost 6 ms at B = 4736: the L1 share matters more)
 constexpr int kUsedO = 0;
 
 struct Ctx {
   int4* REC; const int* SQ; const float2* S2; const double* wtab; unsigned* R; unsigned* ring; unsigned* mask;
   double* red;          // shared memory, 3 x 32 doubles: the per-pixel terms of one batch, for the ordered sums
-  unsigned* bm;         // shared memory, kWinWords: see region_grow
   int sw, sh, fill_off; // fill_off: scratch area inside R (beyond the largest possible region)
 };
 struct RectD { double x1, y1, x2, y2, width; };
@@ -93,11 +82,6 @@ __device__ __forceinline__ bool is_aligned_generic(double a, double theta, doubl
 // remaining candidate is tested against the CURRENT region angle at once, the first aligned one is added, which changes
 // the angle; a pixel added earlier in the same step invalidates its duplicates in the later neighbourhoods.
 // kFast: prec < pi/2, isAligned folded to  n <= prec || n >= prec_hi  (see lsd_grow_core.cuh aligned()).
-// Requests, not bytes, bound this kernel, and most of the 8 neighbours of a pixel inside a region are pixels the region already
-// owns: a 64 x 64 bit window around the seed (shared memory) remembers every pixel seen NOT free during this growth - taken by
-// this region, by an earlier one, or undefined.  Nothing becomes free while one region grows, so a set bit is final and the
-// record is not fetched again; pixels outside the window are simply always fetched.  The window is wiped at the end over the
-// rows the growth can have reached (a pixel expanded in step s is at most s - 1 away from the seed).
 // Alignment WITHOUT the arctangent for the clear cases (kFast only).  The exact test compares the candidate's angle a with
 // reg_angle = fastAtan2(sumdy, sumdx); the candidate's record also carries (cos a, sin a), so the TRUE angle D between the sum
 // vector and the candidate is known from one dot product: cos D = (sumdx*c + sumdy*s) / |sum|.  fastAtan2's polynomial is within
@@ -105,7 +89,6 @@ __device__ __forceinline__ bool is_aligned_generic(double a, double theta, doubl
 // rounding is < 1e-4 degrees, so with a margin M = 0.05 degrees:  D <= prec - M  implies the exact test says aligned, D >= prec + M
 // implies it says not aligned.  Only candidates inside the 2M band need the exact arctangent (kSure.ca2 / cn2 = cos^2(prec -/+ M)).
 struct Sure { float ca2, cn2; };
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 template <bool kFast>
 __device__ __forceinline__ int region_grow(const Ctx& C, unsigned seed, double prec, double prec_hi, Sure sure, double& reg_angle_out, int lane) {
@@ -114,19 +97,16 @@ __device__ __forceinline__ int region_grow(const Ctx& C, unsigned seed, double p
   double reg_angle = (double)__int_as_float(angle_bits(C, sidx)) * kDegToRads;
   float sumdx = s0.x, sumdy = s0.y;
   bool dirty = false;          // reg_angle lags the sums (it is the seed's own angle until the first pixel is added)
-  if (lane == 0) { C.R[0] = seed; C.ring[0] = seed; own_of(C, sidx) = kUsedO; C.bm[kWinHalf * (kWin / 32) + 1] = 1u; }
-  int cnt = 1, nsteps = 0;
+  if (lane == 0) { C.R[0] = seed; C.ring[0] = seed; own_of(C, sidx) = kUsedO; }
+  int cnt = 1;
   __syncwarp();
   const int grp = lane >> 3, kk8 = lane & 7, kk = kk8 + (kk8 >= 4);
   const int ox = kk % 3 - 1, oy = kk / 3 - 1;
-  const int wx0 = (int)(seed & 0xffffu) - kWinHalf, wy0 = (int)(seed >> 16) - kWinHalf;
   for (int i = 0; i < cnt;) {
     const int m = min(4, cnt - i);
     GSTAT(kFast ? 1 : 10, 1);
-    nsteps++;
     bool valid = false;
-    int idx = -1, widx = -1;
-    unsigned wbit = 0u;
+    int idx = -1;
     unsigned pk = 0xffff0000u | (unsigned)lane;      // unique per lane unless it names a real pixel
     int ab = 0;
     float2 csv = make_float2(0.f, 0.f);
@@ -135,34 +115,17 @@ __device__ __forceinline__ int region_grow(const Ctx& C, unsigned seed, double p
       const unsigned p = (cnt - qi <= kORing) ? C.ring[qi & (kORing - 1)] : C.R[qi];
       const int xx = (int)(p & 0xffffu) + ox, yy = (int)(p >> 16) + oy;
       if (xx >= 0 && yy >= 0 && xx < C.sw && yy < C.sh) {
-        const unsigned dxw = (unsigned)(xx - wx0), dyw = (unsigned)(yy - wy0);
-        bool known = false;
-        if (PL_GROW_BM && dxw < (unsigned)kWin && dyw < (unsigned)kWin) {
-          widx = (int)(dyw * (kWin / 32) + (dxw >> 5)); wbit = 1u << (dxw & 31u);
-          known = (C.bm[widx] & wbit) != 0u;
-        }
-        if (!known) {
-          GSTAT_ALL(kFast ? 16 : 17, 1);
-          idx = yy * C.sw + xx;
-          const int4 v = C.REC[idx];
-          if (v.x == lg::kFree) {                       // defined and not USED
-            valid = true; ab = v.y;
-            csv = make_float2(__int_as_float(v.z), __int_as_float(v.w));
-            pk = (unsigned)xx | ((unsigned)yy << 16);
-          } else if (widx >= 0) atomicOr(&C.bm[widx], wbit);
+        idx = yy * C.sw + xx;
+        GSTAT_ALL(kFast ? 16 : 17, 1);
+        const int4 v = C.REC[idx];
+        if (v.x == lg::kFree) {                       // defined and not USED
+          valid = true; ab = v.y;
+          csv = make_float2(__int_as_float(v.z), __int_as_float(v.w));
+          pk = (unsigned)xx | ((unsigned)yy << 16);
         }
       }
     }
     i += m;
-#ifndef PL_GROW_PF
-#define PL_GROW_PF 0
-#endif
-    if (PL_GROW_PF && i + grp < cnt) {       // the next step's neighbourhoods are already known: into L1 while this step's candidates are decided
-      const int qn = i + grp;
-      const unsigned p = (cnt - qn <= kORing) ? C.ring[qn & (kORing - 1)] : C.R[qn];
-      const int xx = min(max((int)(p & 0xffffu) + ox, 0), C.sw - 1), yy = min(max((int)(p >> 16) + oy, 0), C.sh - 1);
-      if (PL_GROW_PF == 1) prefetch_l1(&C.REC[yy * C.sw + xx]); else prefetch_l2(&C.REC[yy * C.sw + xx]);
-    }
     unsigned live = __ballot_sync(0xffffffffu, valid);
     if (live == 0u) continue;
     GSTAT(2, 1);
@@ -203,7 +166,6 @@ __device__ __forceinline__ int region_grow(const Ctx& C, unsigned seed, double p
       live &= ~(((2u << k) - 1u) | __ballot_sync(0xffffffffu, pk == __shfl_sync(0xffffffffu, pk, k)));
     }
     if (mypos >= 0) {      // publish: every accepted lane owns its pixel
-      if (widx >= 0) atomicOr(&C.bm[widx], wbit);
       own_of(C, idx) = kUsedO;
       C.R[mypos] = pk;
       C.ring[mypos & (kORing - 1)] = pk;
@@ -212,11 +174,6 @@ __device__ __forceinline__ int region_grow(const Ctx& C, unsigned seed, double p
   }
   if (dirty) reg_angle = (double)lg::fast_atan2_deg(sumdy, sumdx) * kDegToRads;
   reg_angle_out = reg_angle;
-  {   // wipe the window rows this growth can have reached
-    const int lo = max(0, kWinHalf - nsteps - 1) * (kWin / 32), hi = (min(kWin - 1, kWinHalf + nsteps + 1) + 1) * (kWin / 32);
-    if (PL_GROW_BM) { for (int w = lo + lane; w < hi; w += 32) C.bm[w] = 0u; }
-    __syncwarp();
-  }
   return cnt;
 }
 __device__ __noinline__ int region_grow_cold(const Ctx& C, unsigned seed, double prec, double& reg_angle, int lane) {
@@ -225,9 +182,8 @@ __device__ __noinline__ int region_grow_cold(const Ctx& C, unsigned seed, double
 
 // region2rect + get_theta: sums in list order (see the header), extents by exact max / min
 __device__ __forceinline__ double pixel_weight(const Ctx& C, int px, int py) {
-  // the gradient magnitude sqrt((gx^2 + gy^2) / 4) of the reference, from the integer sum of squares: an IEEE square root
-  // (/ 4.0 is exact) instead of a dependent table load - the kernel is bound by its memory requests, not by fp64
-  if (PL_GROW_SQRT) return sqrt((double)__ldg(&C.SQ[py * C.sw + px]) / 4.0);
+  // the gradient magnitude sqrt((gx^2 + gy^2) / 4) of the reference from the integer sum of squares, through the table of
+  // exact square roots (an in-kernel fp64 sqrt measured 9 ms slower at B = 4736)
   return __ldg(&C.wtab[__ldg(&C.SQ[py * C.sw + px])]);
 }
 __device__ __noinline__ void region2rect(const Ctx& C, int n, double reg_angle, double prec, RectD& rec, int lane) {
@@ -430,13 +386,10 @@ __global__ void __launch_bounds__(32, 32) k_lsd_grow_ordered(LineParams P, int4*
   using namespace ord;
   __shared__ unsigned ring[kORing];
   __shared__ double red[96];
-  __shared__ unsigned bm[kWinWords];
   const int lane = threadIdx.x & 31;
-  for (int w = lane; w < kWinWords; w += 32) bm[w] = 0u;
-  __syncwarp();
   for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
     const Ctx C = {REC + (long long)f * P.npx, SQ + (long long)f * P.npx, seedcs + (long long)f * P.npx, wtab,
-                   reg + (long long)f * reg_stride, ring, mask + (long long)f * P.npx, red, bm, P.sw, P.sh, P.npx};
+                   reg + (long long)f * reg_stride, ring, mask + (long long)f * P.npx, red, P.sw, P.sh, P.npx};
     const unsigned* O = order + (long long)f * P.npx;
     float4* S = segs + (long long)f * P.seg_cap;
     const int n = ndef[f];

@@ -43,14 +43,15 @@ KITTI_K = (718.856, 718.856, 607.1928, 185.2157)      # Examples/Monocular/KITTI
 CONFIGS = {
     "tum": dict(W=640, H=480, orb=(1000, 1.2, 8, 20, 7), camera="tum", scaling="weak", batch=4736, lba=False,
                 workload="640x480 synthetic sequence, TUM1 camera: ORB(1000) + undistort + LSD/LBD(200) extract, frame-to-frame point+line "
-                         "matching, 2x PoseOptimization(300 pts + 80 lines)"),
+                         "matching, the 4 projection searches of steady-state tracking (points: last frame 15/30 px + local map; lines: last frame + local map), "
+                         "2x PoseOptimization(300 pts + 80 lines)"),
     "kitti": dict(W=1241, H=376, orb=(2000, 1.2, 8, 20, 7), camera="kitti", scaling="strong", total=256, lba=True,
                   workload="KITTI-shaped 1241x376 mono (BASELINE configs[3]): ORB(2000) + LSD/LBD(200) extract, frame-to-frame point+line matching, "
-                           "2x PoseOptimization, + one LocalBundleAdjustmentWithLine window (20+40 KFs, 3000 pts, 400 lines) per rank and step; "
+                           "4 tracking projection searches, 2x PoseOptimization, + one LocalBundleAdjustmentWithLine window (20+40 KFs, 3000 pts, 400 lines) per rank and step; "
                            "256 frames sharded over the ranks with a 1-frame halo"),
     "euroc": dict(W=752, H=480, orb=(1000, 1.2, 8, 20, 7), camera="euroc", scaling="strong", total=512, lba=False,
                   workload="EuRoC-shaped 752x480 mono (BASELINE configs[4]): EuRoC camera, ORB(1000) + undistort + LSD/LBD(200) extract, matching, "
-                           "2x PoseOptimization; 512 frames sharded over the ranks with a 1-frame halo, all-gather of the pose records"),
+                           "4 tracking projection searches, 2x PoseOptimization; 512 frames sharded over the ranks with a 1-frame halo, all-gather of the pose records"),
 }
 W, H = CONFIGS["tum"]["W"], CONFIGS["tum"]["H"]
 ORB = CONFIGS["tum"]["orb"]
@@ -108,22 +109,41 @@ def oracle_features(o_orb, img, cfg):
     und = oracle.undistort_remap(img, K, D) if D[0] != 0.0 else img  # Frame.cc:220-222
     kl, ldesc, lf = oracle.line_extract(und, nfeatures=LINES[0], min_line_length=LINES[1])   # Frame.cc:225
     kps = oracle.undistort_keypoints(kps, K, D)                      # Frame.cc:233
-    return kps, desc, ldesc
+    return kps, desc, ldesc, kl, lf
 
 
 def oracle_frame_pipeline(o_orb, prev, img, prob, cfg, bounds):
     """The same per-frame work on the CPU oracle; returns the frame's features (to serve as `prev`)."""
     import oracle
-    kps, desc, ldesc = oracle_features(o_orb, img, cfg)
+    kps, desc, ldesc, kl, lf = oracle_features(o_orb, img, cfg)
     if prev is not None:
-        pk, pd, pl_ = prev
+        pk, pd, pl_, pkl, _ = prev
         pm = np.stack([pk["x"], pk["y"]], 1).astype(np.float32)
         oracle.search_for_initialization(pk, pd, kps, desc, bounds, pm, 100, 0.9, True)
         oracle.search_double(pl_, ldesc, 0.7)
+        # steady-state tracking searches on the previous frame's features as the map (the GPU step's tracking stage, frontend.cu)
+        T = np.asarray(prob["Tcw0"], np.float32).reshape(4, 4); Kc = np.asarray(prob["K"], np.float32)
+        sf = np.cumprod(np.r_[np.float32(1), np.full(cfg["orb"][2] - 1, np.float32(cfg["orb"][1]))]).astype(np.float32)
+        z = (np.float32(1.5) + np.float32(0.25) * (np.arange(len(pk)) & 15).astype(np.float32)).astype(np.float32)
+        Xc = np.stack([(pk["x"] - Kc[2]) / Kc[0] * z, (pk["y"] - Kc[3]) / Kc[1] * z, z], 1).astype(np.float32)
+        pos = ((Xc - T[:3, 3]) @ T[:3, :3]).astype(np.float32)
+        valid = np.ones(len(pk), np.uint8)
+        nm, m = oracle.search_by_projection_last(kps, desc, bounds, T, Kc, sf, valid, pos, pd, pk["octave"], pk["angle"], 15.0, True)
+        if nm < 20:
+            nm, m = oracle.search_by_projection_last(kps, desc, bounds, T, Kc, sf, valid, pos, pd, pk["octave"], pk["angle"], 30.0, True)
+        view = valid.copy(); view[m[m >= 0]] = 0
+        oracle.search_by_projection_points(kps, desc, bounds, sf, view, pm, pk["octave"], np.ones(len(pk), np.float32), pd, 1.0, 0.8,
+                                           (m >= 0).astype(np.uint8))
+        proj = np.stack([pkl["startPointX"], pkl["startPointY"], pkl["endPointX"], pkl["endPointY"]], 1).astype(np.float32)
+        lvalid = np.ones(len(pkl), np.uint8)
+        lnm, lm = oracle.line_search_by_projection_last(kl, lf, ldesc, bounds, lvalid, proj, pl_, pkl["lineLength"], 15.0)
+        lview = lvalid.copy(); lview[lm[lm >= 0]] = 0
+        oracle.line_search_by_projection_lines(kl, lf, ldesc, bounds, lview, proj, np.ones(len(pkl), np.float32), pl_, 1.0, 0.7,
+                                               (lm >= 0).astype(np.uint8))
     for _ in range(2):
         oracle.pose_optimization(0, prob["Tcw0"], prob["K"], prob["pt_obs"], prob["pt_inv_sigma2"], prob["pt_Xw"],
                                  prob["line_func"], prob["line_Xw"])
-    return kps, desc, ldesc
+    return kps, desc, ldesc, kl, lf
 
 
 def cpu_sample(frames, problems, n_frames, threads, cfg=None, per_frame=False):
@@ -309,6 +329,7 @@ def run_config(ctx, name, steps, warmup, batch=None, full=True):
     fe.set_camera(K, D)             # TUM1 / EuRoC: frames and keypoints are undistorted on the device; KITTI: bounds only
     fe.pack_pose_problems(problems, pinned=True)
     prob_bytes = fe.upload_pose_problems(None)
+    fe.set_tracking(True)           # the four projection searches of steady-state tracking (Tracking.cc:1345-1357, :1799, :1855)
     torch.cuda.synchronize()
     d_frames = torch.from_numpy(frames).cuda()
     max_count = -(-total // ctx.world)
@@ -413,6 +434,7 @@ def measure_latency(ctx, frames, problems):
     for B, reps in ((1, 30), (64, 7)):
         fr = np.ascontiguousarray(frames[:B])
         fe.set_pose_problems(problems[:B])
+        fe.set_tracking(True)
         o = fe.alloc_outputs(B)
         t = []
         for r in range(reps + 3):

@@ -226,6 +226,16 @@ long long pl_frontend_set_pose_problems_async(PLFrontend* h, int B, const float*
 /* PL_ERR_CAPACITY if any step since the last check overflowed an extractor capacity (callers of pl_frontend_run_dev) */
 int pl_frontend_check_overflow(PLFrontend* h);
 int pl_frontend_set_wrap(PLFrontend* h, int on);
+/* Steady-state tracking stage of the step (default off): the four projection searches the reference's tracker runs per frame -
+ * ORBmatcher::SearchByProjection(Current, Last, 15, mono) and again with 30 for frames under 20 matches (Tracking.cc:1345-1357),
+ * LSDmatcher::SearchByProjection(Current, Last, 15) (:1347), ORBmatcher(0.8)::SearchByProjection(F, local points, 1) (:1799),
+ * LSDmatcher::SearchByProjection(F, local lines, 1) (:1855) - on the pose guess Tcw0 / K of pl_frontend_set_pose_problems.
+ * The batch step has no map: frame b's map is frame b-1's features (a point on each keypoint's ray, a line per keyline). */
+int pl_frontend_set_tracking(PLFrontend* h, int on);
+/* which: 0 = motion-model searches, 1 = local-map searches.  Matches index the previous frame's features (-1 none, -2 feature
+ * held a match already); map_pos = the synthetic map points [B][capK][3]; *_in_view = the elements each search projected. */
+int pl_frontend_fetch_tracking(PLFrontend* h, int B, int which, int* point_match, int* n_point_matches, int* line_match,
+                               int* n_line_matches, float* map_pos, uint8_t* point_in_view, uint8_t* line_in_view);
 /* mvKeysUn of the last step, [B][cap_keypoints] */
 int pl_frontend_fetch_keys_un(PLFrontend* h, int B, PLKeyPoint* out);
 /* device-resident step (imgs = device pointer; NULL = frames uploaded by the last pl_frontend_run); asynchronous */
@@ -249,6 +259,22 @@ int pl_frontend_wait(PLFrontend* h, int keep_in_flight);
 int pl_frontend_io_bytes(const PLFrontend* h, long long* h2d_per_frame, long long* d2h_per_frame);
 int pl_frontend_fetch(PLFrontend* h, int B, PLKeyPoint* kps, uint8_t* desc, int* n, void* keylines, uint8_t* ldesc, int* nl,
                       int* pt_matches, int* n_pt_matches, int* line_matches, int* n_line_matches, float* poses, int* inliers);
+
+/* ------------------------------------------------------------------ wire / disk formats
+ * Pose record of a frame, 16 floats: Rwc (row-major 3x3) = KeyFrame::GetRotation().t(), Ow = GetCameraCenter() (KeyFrame.cc:52-66),
+ * Converter::toQuaternion(Rwc) as x y z w (Converter.cc:141-153) - what both trajectory writers print, computed on the device so
+ * that the multi-GPU all-gather can ship it as is. */
+int pl_pose_records_dev(const float* Tcw_dev /*[n][16]*/, int n, float* records_dev /*[n][16]*/, void* stream);
+/* System::SaveKeyFrameTrajectoryTUM (System.cc:396-431): "stamp tx ty tz qx qy qz qw\n", fixed, precision 6 / 7; bad[i] = pKF->isBad().
+ * Return: length of the text (>= 0; written NUL-terminated into out if cap is larger - call with out = NULL to size), < 0 = PL_ERR_*. */
+long long pl_trajectory_format_tum(const double* timestamps, const float* poses_Tcw, const uint8_t* bad, int n, char* out, size_t cap);
+/* System::SaveKeyFrameTrajectoryMonoKitti (System.cc:433-464): the 3x4 [Rwc | Ow] row-major, precision 9. */
+long long pl_trajectory_format_mono_kitti(const float* poses_Tcw, const uint8_t* bad, int n, char* out, size_t cap);
+int pl_save_keyframe_trajectory_tum(const char* filename, const double* timestamps, const float* poses_Tcw, const uint8_t* bad, int n);
+int pl_save_keyframe_trajectory_mono_kitti(const char* filename, const float* poses_Tcw, const uint8_t* bad, int n);
+/* Flat little-endian dump of the last step's results (the arrays of pl_frontend_fetch + the line functions) for offline replay:
+ * "PLSB200\x01", int32 B, then per field {int32 len, name, int32 len, numpy dtype text, int32 ndim, int64 shape[], bytes}. */
+int pl_frontend_dump(PLFrontend* h, int B, const char* path);
 
 /* measurement hooks (bench.py): CUDA-event timing of k_lsd_grow on its launching stream, its algorithmic bytes, and
  * a device copy of the second-call poses [B][16] for the multi-GPU all-gather */
@@ -310,6 +336,29 @@ int pl_lsd_search_by_projection_lines(const void* keylines, const double* linefu
                                       const float* bounds, int n_ml, const uint8_t* in_view, const float* proj,
                                       const float* view_cos, const uint8_t* ml_desc, float th, float nnratio,
                                       const uint8_t* preassigned, int* match);
+
+/* Batched, device-resident forms of the projection searches ([B][cap] arrays, one launch, asynchronous on `stream`); the
+ * host-pointer functions above are their B = 1 case.  gate_nmatches / gate_min: frame b runs only if gate_nmatches[b] < gate_min
+ * (the "fill(mvpMapPoints, NULL); search again with 2 * th" retry of Tracking.cc:1352-1357); NULL = every frame runs. */
+int pl_orb_search_by_projection_last_dev(const PLKeyPoint* keys_cur, const uint8_t* desc_cur, const int* n_cur, int cap, int B,
+                                         const float* bounds, const float* Tcw /*[B][16]*/, const float* K /*[4]*/,
+                                         const float* scale_factors, int nlevels, const int* n_last, int cap_last,
+                                         const uint8_t* last_valid, const float* last_pos, const uint8_t* last_desc,
+                                         const int* last_octave, const float* last_angle, float th, int check_orientation,
+                                         const uint8_t* cur_preassigned, const int* gate_nmatches, int gate_min, int* cur_match,
+                                         int* nmatches, void* stream);
+int pl_orb_search_by_projection_points_dev(const PLKeyPoint* keys, const uint8_t* desc, const int* n, int cap, int B,
+                                           const float* bounds, const float* scale_factors, const int* n_mp, int cap_mp,
+                                           const uint8_t* in_view, const float* proj, const int* level, const float* view_cos,
+                                           const uint8_t* mp_desc, float th, float nnratio, const uint8_t* preassigned, int* match,
+                                           int* nmatches, void* stream);
+size_t pl_lsd_search_scratch_bytes(int cap, int B);
+/* variant 0: LSDmatcher::SearchByProjection(CurrentFrame, LastFrame, th), q_length_or_view_cos = last lineLength;
+ * variant 1: SearchByProjection(F, vpMapLines, th), q_length_or_view_cos = mTrackViewCos.  scratch: pl_lsd_search_scratch_bytes. */
+int pl_lsd_search_by_projection_dev(int variant, const void* keylines, const double* linefunc, const uint8_t* desc, const int* n,
+                                    int cap, int B, const float* bounds, const int* n_q, int cap_q, const uint8_t* q_valid,
+                                    const float* q_proj, const uint8_t* q_desc, const float* q_length_or_view_cos, float th,
+                                    float nnratio, const uint8_t* preassigned, int* match, int* nmatches, void* scratch, void* stream);
 
 /* ------------------------------------------------------------------ Frame glue
  * The mono Frame constructor undistorts every frame for the line extractor (initUndistortRectifyMap + remap,

@@ -440,6 +440,26 @@ class Frontend:
         lib().pl_frontend_set_wrap.argtypes = [vp, C.c_int]
         check(lib().pl_frontend_set_wrap(self._h, int(on)))
 
+    def set_tracking(self, on=True):
+        """Add the steady-state projection searches (Tracking.cc:1345-1357,1799,1855) to the step; needs pose problems (Tcw0, K)."""
+        lib().pl_frontend_set_tracking.argtypes = [vp, C.c_int]
+        check(lib().pl_frontend_set_tracking(self._h, int(on)))
+
+    def fetch_tracking(self, B, which=0):
+        """dict(pt_match [B][capK], n_pt, line_match [B][capL], n_line, map_pos [B][capK][3], pt_in_view, line_in_view)."""
+        o = dict(pt_match=np.zeros((B, self.capK), np.int32), n_pt=np.zeros(B, np.int32), line_match=np.zeros((B, self.capL), np.int32),
+                 n_line=np.zeros(B, np.int32), map_pos=np.zeros((B, self.capK, 3), np.float32), pt_in_view=np.zeros((B, self.capK), np.uint8),
+                 line_in_view=np.zeros((B, self.capL), np.uint8))
+        lib().pl_frontend_fetch_tracking.argtypes = [vp, C.c_int, C.c_int] + [vp] * 7
+        check(lib().pl_frontend_fetch_tracking(self._h, B, which, _p(o["pt_match"]), _p(o["n_pt"]), _p(o["line_match"]), _p(o["n_line"]),
+                                               _p(o["map_pos"]), _p(o["pt_in_view"]), _p(o["line_in_view"])))
+        return o
+
+    def dump(self, B, path):
+        """pl_frontend_dump: the last step's results in the replay container trajectory.load_frontend reads."""
+        lib().pl_frontend_dump.argtypes = [vp, C.c_int, C.c_char_p]
+        check(lib().pl_frontend_dump(self._h, B, str(path).encode()))
+
     def pack_pose_problems(self, problems, pinned=True):
         """Pack the batch's pose problems into (pinned) host arrays for upload_pose_problems()."""
         import torch

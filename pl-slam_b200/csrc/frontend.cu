@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include <vector>
+#include <cstdio>
 #include <string.h>
 
 namespace pl {
@@ -19,6 +20,64 @@ __global__ void k_prev_matched_init(const PLKeyPoint* __restrict__ kps_prev, con
   // vbPrevMatched[i] = F1.mvKeysUn[i].pt with F1 = the predecessor of frame b = slot b of the (B+1)-slot arrays
   const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_prev[b]) { pm[((long long)b * cap + i) * 2] = kps_prev[(long long)b * cap + i].x; pm[((long long)b * cap + i) * 2 + 1] = kps_prev[(long long)b * cap + i].y; }
+}
+
+// ---- steady-state tracking stage: the inputs the reference's tracker takes from its map, synthesised from the PREVIOUS frame.
+// TrackWithMotionModel projects the map points / lines seen in the last frame (Tracking.cc:1345-1357), SearchLocalPoints /
+// SearchLocalLines the local map (:1799, :1855).  The batch step has no map, so frame b's "map" is frame b-1's features: a map
+// point per previous keypoint, placed on its viewing ray (depth 1.5 .. 5.25 m) in the world frame of the pose guess Tcw0[b], with
+// the keypoint's descriptor, octave and angle; a map line per previous keyline with its end points as the projection.  The matchers
+// then do exactly the reference's work: project with the pose guess, search the th * scale window, keep the best Hamming
+// distance.  Slot b of the (B+1)-slot arrays is frame b's predecessor.
+__global__ void k_track_points(const PLKeyPoint* __restrict__ ku_prev, const PLKeyPoint* __restrict__ kraw_prev, const int* __restrict__ n_prev,
+                               int cap, const float* __restrict__ Tcw0, const float* __restrict__ K, uint8_t* __restrict__ valid,
+                               float* __restrict__ pos, int* __restrict__ oct, float* __restrict__ ang, float* __restrict__ proj,
+                               float* __restrict__ vcos) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  const long long o = (long long)b * cap + i;
+  const bool v = i < min(n_prev[b], cap);
+  valid[o] = v ? 1 : 0;
+  if (!v) return;
+  const PLKeyPoint k = ku_prev[o];
+  const float* T = Tcw0 + 16 * b;
+  const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+  const float z = __fadd_rn(1.5f, __fmul_rn(0.25f, (float)(i & 15)));
+  const float xc = __fmul_rn(__fdiv_rn(__fsub_rn(k.x, cx), fx), z), yc = __fmul_rn(__fdiv_rn(__fsub_rn(k.y, cy), fy), z);
+  const float dx = __fsub_rn(xc, T[3]), dy = __fsub_rn(yc, T[7]), dz = __fsub_rn(z, T[11]);
+  for (int a = 0; a < 3; a++)      // Xw = R^T (Xc - t)
+    pos[o * 3 + a] = __fadd_rn(__fadd_rn(__fmul_rn(T[a], dx), __fmul_rn(T[4 + a], dy)), __fmul_rn(T[8 + a], dz));
+  oct[o] = kraw_prev[o].octave; ang[o] = k.angle;
+  proj[o * 2] = k.x; proj[o * 2 + 1] = k.y; vcos[o] = 1.0f;
+}
+struct KL68 { float angle; int class_id, octave; float ptx, pty, response, size, sx, sy, ex, ey, sox, soy, eox, eoy, length; int npix; };
+static_assert(sizeof(KL68) == 68, "KeyLine layout");
+__global__ void k_track_lines(const KL68* __restrict__ kl_prev, const int* __restrict__ nl_prev, int cap, uint8_t* __restrict__ valid,
+                              float* __restrict__ proj, float* __restrict__ len, float* __restrict__ vcos) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  const long long o = (long long)b * cap + i;
+  const bool v = i < min(nl_prev[b], cap);
+  valid[o] = v ? 1 : 0;
+  if (!v) return;
+  const KL68& k = kl_prev[o];
+  proj[o * 4] = k.sx; proj[o * 4 + 1] = k.sy; proj[o * 4 + 2] = k.ex; proj[o * 4 + 3] = k.ey;
+  len[o] = k.length; vcos[o] = 1.0f;
+}
+// after the motion-model search: a map element already matched is not searched again in the local-map pass
+// (mnLastFrameSeen == mCurrentFrame.mnId, Tracking.cc:1762-1776), a feature that holds a match is skipped (ORBmatcher.cc:100-102)
+__global__ void __launch_bounds__(256) k_track_mark(const int* __restrict__ match1, const int* __restrict__ n_cur, const uint8_t* __restrict__ valid,
+                                                    int cap, uint8_t* __restrict__ view, uint8_t* __restrict__ pre) {
+  const int b = blockIdx.x;
+  const long long o = (long long)b * cap;
+  for (int i = threadIdx.x; i < cap; i += 256) view[o + i] = valid[o + i];
+  __syncthreads();
+  const int n = min(n_cur[b], cap);
+  for (int j = threadIdx.x; j < cap; j += 256) {
+    const int m = j < n ? match1[o + j] : -1;
+    pre[o + j] = m >= 0 ? 1 : 0;
+    if (m >= 0 && m < cap) view[o + m] = 0;
+  }
 }
 }  // namespace pl
 using namespace pl;
@@ -41,6 +100,16 @@ struct PLFrontend {
   // rotated views so that "previous frame" is a plain pointer offset: copies of frame B-1 placed before frame 0
   PLKeyPoint* d_kps_prev = nullptr; uint8_t* d_desc_prev = nullptr; int* d_n_prev = nullptr;
   uint8_t* d_ldesc_prev = nullptr; int* d_nl_prev = nullptr;
+  uint8_t* d_kl_prev = nullptr;          // keylines hold B+1 slots like the descriptors (d_kl = slot 1)
+  // steady-state tracking stage (pl_frontend_set_tracking): the map seen from frame b is frame b-1's features (see k_track_points)
+  int tracking = 0;
+  float* d_sf = nullptr;
+  float *d_tpos = nullptr, *d_tang = nullptr, *d_tproj = nullptr, *d_tvcos = nullptr;
+  int *d_toct = nullptr, *d_tm1 = nullptr, *d_tnm1 = nullptr, *d_tm2 = nullptr, *d_tnm2 = nullptr;
+  uint8_t *d_tvalid = nullptr, *d_tview = nullptr, *d_tpre = nullptr;
+  float *d_lqproj = nullptr, *d_lqlen = nullptr, *d_lqvcos = nullptr;
+  int *d_lm1 = nullptr, *d_lnm1 = nullptr, *d_lm2 = nullptr, *d_lnm2 = nullptr;
+  uint8_t *d_lqvalid = nullptr, *d_lqview = nullptr, *d_lpre = nullptr, *d_lscratch = nullptr;
   // LM problems
   float *d_T0 = nullptr, *d_K = nullptr, *d_pobs = nullptr, *d_pw = nullptr, *d_pX = nullptr, *d_Tout = nullptr;
   double *d_lfun = nullptr, *d_lX = nullptr, *d_scratch = nullptr;
@@ -69,7 +138,9 @@ extern "C" void pl_frontend_destroy(PLFrontend* h) {
   if (h->sUp) cudaStreamDestroy(h->sUp);
   if (h->sDown) cudaStreamDestroy(h->sDown);
   for (cudaEvent_t e : {h->evUp[0], h->evUp[1], h->evFree[0], h->evFree[1], h->evSnap, h->evOut, h->evStep[0], h->evStep[1]}) if (e) cudaEventDestroy(e);
-  void* ptrs[] = {h->d_img, h->d_kl, h->d_lf, h->d_bounds, h->d_pm, h->d_m12,
+  void* ptrs[] = {h->d_img, h->d_kl_prev, h->d_sf, h->d_tpos, h->d_tang, h->d_tproj, h->d_tvcos, h->d_toct, h->d_tm1, h->d_tnm1, h->d_tm2, h->d_tnm2,
+                  h->d_tvalid, h->d_tview, h->d_tpre, h->d_lqproj, h->d_lqlen, h->d_lqvcos, h->d_lm1, h->d_lnm1, h->d_lm2, h->d_lnm2,
+                  h->d_lqvalid, h->d_lqview, h->d_lpre, h->d_lscratch, h->d_lf, h->d_bounds, h->d_pm, h->d_m12,
                   h->d_nm, h->d_scr, h->d_lm, h->d_nlm, h->d_kps_prev, h->d_desc_prev, h->d_n_prev, h->d_ldesc_prev, h->d_nl_prev,
                   h->d_T0, h->d_K, h->d_pobs, h->d_pw, h->d_pX, h->d_Tout, h->d_lfun, h->d_lX, h->d_scratch, h->d_np, h->d_nl_lm,
                   h->d_inl, h->d_its, h->d_pout, h->d_lout};
@@ -116,7 +187,7 @@ extern "C" int pl_frontend_create(const PLFrontendConfig* cfg, PLFrontend** out)
   FE_TRY(dev_alloc(&h->d_ldesc_prev, cL * 32 * (B + 1))); h->d_ldesc = h->d_ldesc_prev + cL * 32;
   FE_TRY(dev_alloc(&h->d_nl_prev, B + 1)); h->d_nl = h->d_nl_prev + 1;
   FE_CUDA(cudaMemset(h->d_nl_prev, 0, sizeof(int) * (B + 1)));
-  { uint8_t* p = nullptr; FE_TRY(dev_alloc(&p, cL * 68 * B)); h->d_kl = p; }
+  FE_TRY(dev_alloc(&h->d_kl_prev, cL * 68 * (B + 1))); h->d_kl = h->d_kl_prev + cL * 68;
   FE_TRY(dev_alloc(&h->d_lf, cL * 3 * B));
   FE_TRY(dev_alloc(&h->d_bounds, 4)); FE_TRY(dev_alloc(&h->d_pm, cK * 2 * B)); FE_TRY(dev_alloc(&h->d_m12, cK * B));
   FE_TRY(dev_alloc(&h->d_nm, B)); FE_TRY(dev_alloc(&h->d_scr, cK * 2 * B)); FE_TRY(dev_alloc(&h->d_lm, cL * B)); FE_TRY(dev_alloc(&h->d_nlm, B));
@@ -175,6 +246,46 @@ extern "C" long long pl_frontend_set_pose_problems_async(PLFrontend* h, int B, c
   PL_CUDA(cudaMemcpyAsync(h->d_lX, line_Xw, cl * 48 * b, cudaMemcpyHostToDevice, st));
   return (long long)((64 + 16 + 4 + 4 + cp * (8 + 4 + 12) + cl * (24 + 48)) * b);
 }
+// Steady-state tracking stage on / off (default off).  Allocates its arrays on first use.
+extern "C" int pl_frontend_set_tracking(PLFrontend* h, int on) {
+  PL_ARG(h);
+  if (on && !h->d_sf) {
+    const size_t B = h->B, cK = h->capK, cL = h->capL;
+    std::vector<float> sf(std::max(h->cfg.orb_nlevels, 1), 1.0f);
+    for (size_t i = 1; i < sf.size(); i++) sf[i] = sf[i - 1] * h->cfg.orb_scale_factor;     // ORBextractor.cc:419-426
+    int rc;
+#define TR_TRY(e) do { if ((rc = (e))) return rc; } while (0)
+    TR_TRY(dev_alloc(&h->d_sf, sf.size()));
+    PL_CUDA(cudaMemcpy(h->d_sf, sf.data(), sf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    TR_TRY(dev_alloc(&h->d_tpos, cK * 3 * B)); TR_TRY(dev_alloc(&h->d_tang, cK * B)); TR_TRY(dev_alloc(&h->d_tproj, cK * 2 * B));
+    TR_TRY(dev_alloc(&h->d_tvcos, cK * B)); TR_TRY(dev_alloc(&h->d_toct, cK * B)); TR_TRY(dev_alloc(&h->d_tm1, cK * B)); TR_TRY(dev_alloc(&h->d_tnm1, B));
+    TR_TRY(dev_alloc(&h->d_tm2, cK * B)); TR_TRY(dev_alloc(&h->d_tnm2, B)); TR_TRY(dev_alloc(&h->d_tvalid, cK * B)); TR_TRY(dev_alloc(&h->d_tview, cK * B));
+    TR_TRY(dev_alloc(&h->d_tpre, cK * B));
+    TR_TRY(dev_alloc(&h->d_lqproj, cL * 4 * B)); TR_TRY(dev_alloc(&h->d_lqlen, cL * B)); TR_TRY(dev_alloc(&h->d_lqvcos, cL * B));
+    TR_TRY(dev_alloc(&h->d_lm1, cL * B)); TR_TRY(dev_alloc(&h->d_lnm1, B)); TR_TRY(dev_alloc(&h->d_lm2, cL * B)); TR_TRY(dev_alloc(&h->d_lnm2, B));
+    TR_TRY(dev_alloc(&h->d_lqvalid, cL * B)); TR_TRY(dev_alloc(&h->d_lqview, cL * B)); TR_TRY(dev_alloc(&h->d_lpre, cL * B));
+    TR_TRY(dev_alloc(&h->d_lscratch, pl_lsd_search_scratch_bytes((int)cL, (int)B)));
+#undef TR_TRY
+  }
+  h->tracking = on ? 1 : 0;
+  return PL_OK;
+}
+// Results and inputs of the tracking stage of the last step (host arrays, NULL = skip): matches [B][capK] / [B][capL] hold the index
+// of the previous frame's feature (-1 none); which: 0 = motion-model search, 1 = local-map search.
+extern "C" int pl_frontend_fetch_tracking(PLFrontend* h, int B, int which, int* point_match, int* n_point_matches, int* line_match,
+                                          int* n_line_matches, float* map_pos, uint8_t* point_in_view, uint8_t* line_in_view) {
+  PL_ARG(h && h->tracking && h->d_sf && B >= 1 && B <= h->B && (which == 0 || which == 1));
+  const size_t cK = h->capK, cL = h->capL;
+  PL_CUDA(cudaStreamSynchronize(h->stream));
+  if (point_match) PL_CUDA(cudaMemcpy(point_match, which ? h->d_tm2 : h->d_tm1, cK * B * sizeof(int), cudaMemcpyDeviceToHost));
+  if (n_point_matches) PL_CUDA(cudaMemcpy(n_point_matches, which ? h->d_tnm2 : h->d_tnm1, B * sizeof(int), cudaMemcpyDeviceToHost));
+  if (line_match) PL_CUDA(cudaMemcpy(line_match, which ? h->d_lm2 : h->d_lm1, cL * B * sizeof(int), cudaMemcpyDeviceToHost));
+  if (n_line_matches) PL_CUDA(cudaMemcpy(n_line_matches, which ? h->d_lnm2 : h->d_lnm1, B * sizeof(int), cudaMemcpyDeviceToHost));
+  if (map_pos) PL_CUDA(cudaMemcpy(map_pos, h->d_tpos, cK * 3 * B * sizeof(float), cudaMemcpyDeviceToHost));
+  if (point_in_view) PL_CUDA(cudaMemcpy(point_in_view, which ? h->d_tview : h->d_tvalid, cK * B, cudaMemcpyDeviceToHost));
+  if (line_in_view) PL_CUDA(cudaMemcpy(line_in_view, which ? h->d_lqview : h->d_lqvalid, cL * B, cudaMemcpyDeviceToHost));
+  return PL_OK;
+}
 extern "C" int pl_frontend_set_wrap(PLFrontend* h, int on) { PL_ARG(h); h->wrap = on ? 1 : 0; return PL_OK; }
 extern "C" int pl_frontend_check_overflow(PLFrontend* h) {
   PL_ARG(h);
@@ -213,11 +324,23 @@ extern "C" int pl_frontend_run_dev(PLFrontend* h, const uint8_t* imgs, int strid
   auto carry_lines = [&]() -> int {
     PL_CUDA(cudaMemcpyAsync(h->d_ldesc_prev, h->d_ldesc + cL * 32 * (B - 1), cL * 32, cudaMemcpyDeviceToDevice, sL));
     PL_CUDA(cudaMemcpyAsync(h->d_nl_prev, h->d_nl + (B - 1), sizeof(int), cudaMemcpyDeviceToDevice, sL));
+    PL_CUDA(cudaMemcpyAsync(h->d_kl_prev, (const uint8_t*)h->d_kl + cL * 68 * (B - 1), cL * 68, cudaMemcpyDeviceToDevice, sL));
     return PL_OK;
   };
   if (h->wrap && (rc = carry_lines())) return rc;
   if ((rc = pl_lsd_search_double_dev(h->d_ldesc_prev, h->d_nl_prev, h->d_ldesc, h->d_nl, (int)cL, (int)cL, B, 50.f, 0.7f, 1, h->d_lm,
                                      h->d_nlm, sL))) return rc;
+  if (h->tracking) {   // lines: TrackWithMotionModel (Tracking.cc:1347, th = 15) then SearchLocalLines (:1855, th = 1), LSDmatcher(0.7)
+    const dim3 g((unsigned)((cL + 127) / 128), B);
+    k_track_lines<<<g, 128, 0, sL>>>((const KL68*)h->d_kl_prev, h->d_nl_prev, (int)cL, h->d_lqvalid, h->d_lqproj, h->d_lqlen, h->d_lqvcos);
+    PL_LAUNCH_CHECK();
+    if ((rc = pl_lsd_search_by_projection_dev(0, h->d_kl, h->d_lf, h->d_ldesc, h->d_nl, (int)cL, B, h->d_bounds, h->d_nl_prev, (int)cL, h->d_lqvalid,
+                                              h->d_lqproj, h->d_ldesc_prev, h->d_lqlen, 15.f, 0.7f, nullptr, h->d_lm1, h->d_lnm1, h->d_lscratch, sL))) return rc;
+    k_track_mark<<<B, 256, 0, sL>>>(h->d_lm1, h->d_nl, h->d_lqvalid, (int)cL, h->d_lqview, h->d_lpre);
+    PL_LAUNCH_CHECK();
+    if ((rc = pl_lsd_search_by_projection_dev(1, h->d_kl, h->d_lf, h->d_ldesc, h->d_nl, (int)cL, B, h->d_bounds, h->d_nl_prev, (int)cL, h->d_lqview,
+                                              h->d_lqproj, h->d_ldesc_prev, h->d_lqvcos, 1.f, 0.7f, h->d_lpre, h->d_lm2, h->d_lnm2, h->d_lscratch, sL))) return rc;
+  }
   if (!h->wrap && (rc = carry_lines())) return rc;
   // --- ORB chain (slot 0 <- frame B-1 so that frame b's predecessor is slot b, a plain offset)
   if ((rc = pl_orb_extract_batch_dev(h->orb, imgs, stride, frame_stride, B, h->d_kps, h->d_desc, h->d_n, st))) return rc;
@@ -241,6 +364,21 @@ extern "C" int pl_frontend_run_dev(PLFrontend* h, const uint8_t* imgs, int strid
   PL_LAUNCH_CHECK();
   if ((rc = pl_orb_search_for_initialization_dev(ku_prev, h->d_desc_prev, h->d_n_prev, ku, h->d_desc, h->d_n, (int)cK, B,
                                                  h->d_bounds, h->d_pm, h->d_m12, h->d_nm, 100, 0.9f, 1, h->d_scr, st))) return rc;
+  if (h->tracking) {   // points: TrackWithMotionModel (Tracking.cc:1345-1357: th = 15, again with 2 th if < 20 matches), SearchLocalPoints (:1799)
+    const PLKeyPoint* kraw_prev = h->d_kps_prev;
+    const dim3 g((unsigned)((cK + 127) / 128), B);
+    k_track_points<<<g, 128, 0, st>>>(ku_prev, kraw_prev, h->d_n_prev, (int)cK, h->d_T0, h->d_K, h->d_tvalid, h->d_tpos, h->d_toct, h->d_tang,
+                                      h->d_tproj, h->d_tvcos);
+    PL_LAUNCH_CHECK();
+    for (int pass = 0; pass < 2; pass++)
+      if ((rc = pl_orb_search_by_projection_last_dev(ku, h->d_desc, h->d_n, (int)cK, B, h->d_bounds, h->d_T0, h->d_K, h->d_sf, h->cfg.orb_nlevels,
+                                                     h->d_n_prev, (int)cK, h->d_tvalid, h->d_tpos, h->d_desc_prev, h->d_toct, h->d_tang,
+                                                     pass ? 30.f : 15.f, 1, nullptr, pass ? h->d_tnm1 : nullptr, 20, h->d_tm1, h->d_tnm1, st))) return rc;
+    k_track_mark<<<B, 256, 0, st>>>(h->d_tm1, h->d_n, h->d_tvalid, (int)cK, h->d_tview, h->d_tpre);
+    PL_LAUNCH_CHECK();
+    if ((rc = pl_orb_search_by_projection_points_dev(ku, h->d_desc, h->d_n, (int)cK, B, h->d_bounds, h->d_sf, h->d_n_prev, (int)cK, h->d_tview,
+                                                     h->d_tproj, h->d_toct, h->d_tvcos, h->d_desc_prev, 1.f, 0.8f, h->d_tpre, h->d_tm2, h->d_tnm2, st))) return rc;
+  }
   if (!h->wrap && (rc = carry_points())) return rc;
   // --- pose optimisations: TrackWithMotionModel (Tracking.cc:1372) and TrackLocalMapWithLines (:1503)
   for (int call = 0; call < 2; call++)
@@ -437,5 +575,52 @@ extern "C" long long pl_frontend_grow_bytes_per_frame(const PLFrontend* h) { ret
 extern "C" int pl_frontend_copy_poses_dev(PLFrontend* h, int B, float* dst, void* stream) {
   PL_ARG(h && dst && B >= 1 && B <= h->B);
   PL_CUDA(cudaMemcpyAsync(dst, h->d_Tout + 16 * (size_t)B, 64 * (size_t)B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return PL_OK;
+}
+
+// ---- flat binary dump of one front-end step (the arrays pl_frontend_fetch returns), the container trajectory.load_frontend reads:
+// magic "PLSB200\x01", int32 B, then per field: int32 name length, name, int32 dtype length, dtype text (numpy descr), int32 ndim,
+// int64 shape[ndim], raw little-endian bytes.
+extern "C" int pl_frontend_dump(PLFrontend* h, int B, const char* path) {
+  PL_ARG(h && path && B >= 1);
+  int cK = 0, cL = 0;
+  int rc = pl_frontend_capacities(h, &cK, &cL);
+  if (rc) return rc;
+  std::vector<PLKeyPoint> kps((size_t)B * cK); std::vector<uint8_t> desc((size_t)B * cK * 32), kl((size_t)B * cL * 68), ldesc((size_t)B * cL * 32);
+  std::vector<int> n(B), nl(B), m12((size_t)B * cK), nm(B), lm((size_t)B * cL), nlm(B), inl((size_t)2 * B);
+  std::vector<double> lf((size_t)B * cL * 3); std::vector<float> poses((size_t)2 * B * 16);
+  rc = pl_frontend_fetch(h, B, kps.data(), desc.data(), n.data(), kl.data(), ldesc.data(), nl.data(), m12.data(), nm.data(), lm.data(),
+                         nlm.data(), poses.data(), inl.data());
+  if (rc) return rc;
+  PL_CUDA(cudaMemcpy(lf.data(), h->d_lf, lf.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  FILE* f = fopen(path, "wb");
+  if (!f) { set_error("cannot open %s", path); return PL_ERR_ARG; }
+  bool ok = fwrite("PLSB200\x01", 1, 8, f) == 8;
+  const int32_t b32 = B;
+  ok = ok && fwrite(&b32, 4, 1, f) == 1;
+  auto field = [&](const char* name, const char* dtype, std::vector<long long> shape, const void* data, size_t bytes) {
+    const int32_t ln = (int32_t)strlen(name), ld = (int32_t)strlen(dtype), nd = (int32_t)shape.size();
+    ok = ok && fwrite(&ln, 4, 1, f) == 1 && fwrite(name, 1, ln, f) == (size_t)ln && fwrite(&ld, 4, 1, f) == 1 && fwrite(dtype, 1, ld, f) == (size_t)ld;
+    ok = ok && fwrite(&nd, 4, 1, f) == 1 && fwrite(shape.data(), 8, nd, f) == (size_t)nd && (bytes == 0 || fwrite(data, 1, bytes, f) == bytes);
+  };
+  const char* kp_dt = "[('x', '<f4'), ('y', '<f4'), ('size', '<f4'), ('angle', '<f4'), ('response', '<f4'), ('octave', '<i4'), ('class_id', '<i4')]";
+  const char* kl_dt = "[('angle', '<f4'), ('class_id', '<i4'), ('octave', '<i4'), ('ptx', '<f4'), ('pty', '<f4'), ('response', '<f4'), ('size', '<f4'), "
+                      "('startPointX', '<f4'), ('startPointY', '<f4'), ('endPointX', '<f4'), ('endPointY', '<f4'), ('sPointInOctaveX', '<f4'), "
+                      "('sPointInOctaveY', '<f4'), ('ePointInOctaveX', '<f4'), ('ePointInOctaveY', '<f4'), ('lineLength', '<f4'), ('numOfPixels', '<i4')]";
+  field("kps", kp_dt, {B, cK}, kps.data(), kps.size() * sizeof(PLKeyPoint));
+  field("desc", "'|u1'", {B, cK, 32}, desc.data(), desc.size());
+  field("n", "'<i4'", {B}, n.data(), n.size() * 4);
+  field("keylines", kl_dt, {B, cL}, kl.data(), kl.size());
+  field("ldesc", "'|u1'", {B, cL, 32}, ldesc.data(), ldesc.size());
+  field("linefunc", "'<f8'", {B, cL, 3}, lf.data(), lf.size() * 8);
+  field("nl", "'<i4'", {B}, nl.data(), nl.size() * 4);
+  field("pt_matches", "'<i4'", {B, cK}, m12.data(), m12.size() * 4);
+  field("n_pt_matches", "'<i4'", {B}, nm.data(), nm.size() * 4);
+  field("line_matches", "'<i4'", {B, cL}, lm.data(), lm.size() * 4);
+  field("n_line_matches", "'<i4'", {B}, nlm.data(), nlm.size() * 4);
+  field("poses", "'<f4'", {2, B, 16}, poses.data(), poses.size() * 4);
+  field("inliers", "'<i4'", {2, B}, inl.data(), inl.size() * 4);
+  fclose(f);
+  if (!ok) { set_error("short write to %s", path); return PL_ERR_ARG; }
   return PL_OK;
 }

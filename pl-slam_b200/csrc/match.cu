@@ -311,12 +311,16 @@ struct ProjLastArgs {
   float th; int checkOri; const uint8_t* preassigned; int* match; int* nmatches;
   // keyframe overload (ORBmatcher.cc:1587-1716, relocalisation): level from MapPoint::PredictScale(dist3D, F), no invzc < 0 test
   int kfMode = 0, maxDist = 100; const float *min_dist = nullptr, *max_dist = nullptr; float Ow[3] = {0, 0, 0}; float logSF = 1.f;
+  // batched retry (Tracking.cc:1352-1357: "if(nmatches<20) { fill(mvpMapPoints, NULL); SearchByProjection(..., 2*th) }"): frame b runs
+  // only if gate[b] < gate_min; the kernel re-initialises its matches, which is the fill
+  const int* gate = nullptr; int gate_min = 0;
 };
 
 __global__ void __launch_bounds__(32) k_search_proj_last(ProjLastArgs A) {
   extern __shared__ unsigned char smem[];
   __shared__ int hist[HISTO];
   const int b = blockIdx.x, lane = threadIdx.x;
+  if (A.gate && A.gate[b] >= A.gate_min) return;
   SmemGrid sg = carve_grid(smem, A.cap);
   GridP g = make_grid(A.bounds);
   const PLKeyPoint* kc = A.keys + (long long)b * A.cap;
@@ -1180,6 +1184,46 @@ extern "C" int pl_orb_search_by_projection_points(const PLKeyPoint* keys, const 
   return nm;
 }
 
+// ---- batched, device-resident forms of the three projection searches of the steady-state tracking step (one warp per frame,
+// [B][cap] arrays, asynchronous on `stream`): what pl_frontend_run_dev launches; the host-pointer forms above are the B = 1 case.
+extern "C" int pl_orb_search_by_projection_last_dev(const PLKeyPoint* keys_cur, const uint8_t* desc_cur, const int* n_cur, int cap, int B,
+                                                    const float* bounds, const float* Tcw, const float* K, const float* scale_factors,
+                                                    int nlevels, const int* n_last, int cap_last, const uint8_t* last_valid,
+                                                    const float* last_pos, const uint8_t* last_desc, const int* last_octave,
+                                                    const float* last_angle, float th, int check_orientation,
+                                                    const uint8_t* cur_preassigned, const int* gate_nmatches, int gate_min,
+                                                    int* cur_match, int* nmatches, void* stream) {
+  PL_ARG(keys_cur && desc_cur && n_cur && bounds && Tcw && K && scale_factors && n_last && last_valid && last_pos && last_desc &&
+         last_octave && last_angle && cur_match && nmatches && B >= 1 && cap >= 1 && cap <= 6144 && cap_last >= 1);
+  ProjLastArgs A;
+  A.keys = keys_cur; A.desc = desc_cur; A.n = n_cur; A.cap = cap; A.bounds = bounds; A.Tcw = Tcw; A.K = K; A.scaleFactors = scale_factors;
+  A.nlevels = nlevels; A.n_last = n_last; A.cap_last = cap_last; A.last_valid = last_valid; A.last_pos = last_pos; A.last_desc = last_desc;
+  A.last_octave = last_octave; A.last_angle = last_angle; A.th = th; A.checkOri = check_orientation; A.preassigned = cur_preassigned;
+  A.match = cur_match; A.nmatches = nmatches; A.gate = gate_nmatches; A.gate_min = gate_min;
+  const size_t sm = grid_smem_bytes(cap);
+  PL_CUDA(cudaFuncSetAttribute(k_search_proj_last, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_search_proj_last<<<B, 32, sm, (cudaStream_t)stream>>>(A);
+  PL_LAUNCH_CHECK();
+  return PL_OK;
+}
+extern "C" int pl_orb_search_by_projection_points_dev(const PLKeyPoint* keys, const uint8_t* desc, const int* n, int cap, int B,
+                                                      const float* bounds, const float* scale_factors, const int* n_mp, int cap_mp,
+                                                      const uint8_t* in_view, const float* proj, const int* level, const float* view_cos,
+                                                      const uint8_t* mp_desc, float th, float nnratio, const uint8_t* preassigned,
+                                                      int* match, int* nmatches, void* stream) {
+  PL_ARG(keys && desc && n && bounds && scale_factors && n_mp && in_view && proj && level && view_cos && mp_desc && match && nmatches &&
+         B >= 1 && cap >= 1 && cap <= 6144 && cap_mp >= 1);
+  ProjPointsArgs A;
+  A.keys = keys; A.desc = desc; A.n = n; A.cap = cap; A.bounds = bounds; A.scaleFactors = scale_factors; A.n_mp = n_mp; A.cap_mp = cap_mp;
+  A.in_view = in_view; A.proj = proj; A.level = level; A.view_cos = view_cos; A.mp_desc = mp_desc; A.th = th; A.nnratio = nnratio;
+  A.preassigned = preassigned; A.match = match; A.nmatches = nmatches;
+  const size_t sm = grid_smem_bytes(cap);
+  PL_CUDA(cudaFuncSetAttribute(k_search_proj_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_search_proj_points<<<B, 32, sm, (cudaStream_t)stream>>>(A);
+  PL_LAUNCH_CHECK();
+  return PL_OK;
+}
+
 extern "C" int pl_match_bf_knn2(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx, int* dist) {
   PL_ARG(d1 && d2 && idx && dist && n1 >= 0 && n2 >= 0);
   int rc = require_device(); if (rc) return rc;
@@ -1325,6 +1369,33 @@ extern "C" int pl_lsd_search_by_projection_lines(const void* keylines, const dou
                                                  const uint8_t* preassigned, int* match) {
   return line_search_host(1, keylines, linefunc, desc, n, bounds, n_ml, in_view, proj, ml_desc, nullptr, view_cos, th, nnratio,
                           preassigned, match);
+}
+
+extern "C" size_t pl_lsd_search_scratch_bytes(int cap, int B) {
+  const size_t per = (size_t)(NCELL + 1) * 4 + (size_t)cap * kMaxPath * 2 * 2 + (size_t)cap * 2 + (size_t)cap * 4;
+  return per * (size_t)B + 256;
+}
+/* variant 0 = SearchByProjection(CurrentFrame, LastFrame, th) (q_length = last lineLength), 1 = (F, vpMapLines, th) (q_view_cos) */
+extern "C" int pl_lsd_search_by_projection_dev(int variant, const void* keylines, const double* linefunc, const uint8_t* desc, const int* n,
+                                               int cap, int B, const float* bounds, const int* n_q, int cap_q, const uint8_t* q_valid,
+                                               const float* q_proj, const uint8_t* q_desc, const float* q_length_or_view_cos, float th,
+                                               float nnratio, const uint8_t* preassigned, int* match, int* nmatches, void* scratch,
+                                               void* stream) {
+  PL_ARG(keylines && linefunc && desc && n && bounds && n_q && q_valid && q_proj && q_desc && q_length_or_view_cos && match && nmatches &&
+         scratch && B >= 1 && cap >= 1 && cap < 60000 && cap_q >= 1 && (variant == 0 || variant == 1));
+  LineSearchArgs A;
+  A.kl = (const KeyLine68*)keylines; A.lfunc = linefunc; A.desc = desc; A.n = n; A.cap = cap; A.bounds = bounds;
+  A.n_q = n_q; A.cap_q = cap_q; A.q_valid = q_valid; A.q_proj = q_proj; A.q_desc = q_desc;
+  A.q_length = variant == 0 ? q_length_or_view_cos : nullptr; A.q_view_cos = variant == 1 ? q_length_or_view_cos : nullptr;
+  A.th = th; A.nnratio = nnratio; A.variant = variant; A.preassigned = preassigned; A.match = match; A.nmatches = nmatches;
+  unsigned char* p = (unsigned char*)scratch;
+  auto take = [&](size_t bytes) { unsigned char* r = p; p += (bytes + 15) / 16 * 16; return r; };
+  A.g_start = (int*)take((size_t)(NCELL + 1) * 4 * B); A.g_first = (int*)take((size_t)cap * 4 * B);
+  A.g_items = (unsigned short*)take((size_t)cap * kMaxPath * 2 * B); A.g_path = (unsigned short*)take((size_t)cap * kMaxPath * 2 * B);
+  A.g_plen = (unsigned short*)take((size_t)cap * 2 * B);
+  k_line_search<<<B, 32, 0, (cudaStream_t)stream>>>(A);
+  PL_LAUNCH_CHECK();
+  return PL_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ §8f.2 wrappers

@@ -109,3 +109,55 @@ def load_frontend(path):
             (nd,) = struct.unpack("<i", f.read(4)); shape = struct.unpack("<%dq" % nd, f.read(8 * nd))
             out[name] = np.frombuffer(f.read(int(np.prod(shape)) * dt.itemsize), dt).reshape(shape).copy()
     return B, out
+
+
+# ------------------------------------------------------------------------------------------------ the C ABI forms (wire.cu)
+def _lib():
+    from . import binding
+    return binding
+
+
+def c_format_keyframe_trajectory_tum(timestamps, poses_Tcw, bad=None):
+    """pl_trajectory_format_tum: the same text, pose records computed on the GPU."""
+    import ctypes as C
+    b = _lib(); L = b.lib()
+    ts = np.ascontiguousarray(timestamps, np.float64); P = np.ascontiguousarray(poses_Tcw, np.float32).reshape(-1, 16)
+    bd = None if bad is None else np.ascontiguousarray(bad, np.uint8)
+    L.pl_trajectory_format_tum.restype = C.c_longlong
+    L.pl_trajectory_format_tum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    need = L.pl_trajectory_format_tum(b._p(ts), b._p(P), b._p(bd), len(P), None, 0)
+    if need < 0:
+        b.check(int(need))
+    buf = C.create_string_buffer(need + 1)
+    L.pl_trajectory_format_tum(b._p(ts), b._p(P), b._p(bd), len(P), buf, need + 1)
+    return buf.raw[:need].decode()
+
+
+def c_format_keyframe_trajectory_mono_kitti(poses_Tcw, bad=None):
+    import ctypes as C
+    b = _lib(); L = b.lib()
+    P = np.ascontiguousarray(poses_Tcw, np.float32).reshape(-1, 16)
+    bd = None if bad is None else np.ascontiguousarray(bad, np.uint8)
+    L.pl_trajectory_format_mono_kitti.restype = C.c_longlong
+    L.pl_trajectory_format_mono_kitti.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    need = L.pl_trajectory_format_mono_kitti(b._p(P), b._p(bd), len(P), None, 0)
+    if need < 0:
+        b.check(int(need))
+    buf = C.create_string_buffer(need + 1)
+    L.pl_trajectory_format_mono_kitti(b._p(P), b._p(bd), len(P), buf, need + 1)
+    return buf.raw[:need].decode()
+
+
+def c_save(filename, poses_Tcw, timestamps=None, bad=None):
+    """pl_save_keyframe_trajectory_tum (timestamps given) / _mono_kitti."""
+    import ctypes as C
+    b = _lib(); L = b.lib()
+    P = np.ascontiguousarray(poses_Tcw, np.float32).reshape(-1, 16)
+    bd = None if bad is None else np.ascontiguousarray(bad, np.uint8)
+    if timestamps is not None:
+        ts = np.ascontiguousarray(timestamps, np.float64)
+        L.pl_save_keyframe_trajectory_tum.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        b.check(L.pl_save_keyframe_trajectory_tum(str(filename).encode(), b._p(ts), b._p(P), b._p(bd), len(P)))
+    else:
+        L.pl_save_keyframe_trajectory_mono_kitti.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
+        b.check(L.pl_save_keyframe_trajectory_mono_kitti(str(filename).encode(), b._p(P), b._p(bd), len(P)))

@@ -214,3 +214,58 @@ def test_frontend_consecutive_steps_are_one_sequence():
             assert outs[s]["n_pt_matches"][b] == onm and np.array_equal(outs[s]["pt_matches"][b, :len(pk)], om), (s, b)
             onl, olm = oracle.search_double(lfeat[g - 1], lfeat[g], 0.7)
             assert outs[s]["n_line_matches"][b] == onl and np.array_equal(outs[s]["line_matches"][b, :len(lfeat[g - 1])], olm), (s, b)
+
+
+def test_tracking_stage_matches_oracle():
+    """The steady-state projection searches of the step (Tracking.cc:1345-1357, :1799, :1855) on the previous frame's features as
+    the map: each search equals the CPU oracle's on the same inputs, including the 2 x th retry for frames under 20 matches."""
+    B = 4
+    frames = synth.synth_sequence(B, 640, 480, seed=9).copy()
+    frames[2] = 127                                            # featureless: frame 3 has an empty map -> 0 matches -> retry path
+    problems = [synth.synth_pose_problem(80 + k) for k in range(B)]
+    for p in problems[1:]:
+        p["K"] = problems[0]["K"]                              # one camera
+    fe = pl.Frontend(640, 480, max_batch=B, lm_caps=(320, 88))
+    fe.set_wrap(True)
+    fe.set_pose_problems(problems)
+    fe.set_tracking(True)
+    out = fe.run(frames)
+    t0, t1 = fe.fetch_tracking(B, 0), fe.fetch_tracking(B, 1)
+    K = np.asarray(problems[0]["K"], np.float32)
+    sf = np.cumprod(np.r_[np.float32(1), np.full(7, np.float32(1.2))]).astype(np.float32)
+    bounds = [0, 0, 640, 480]
+    retried = 0
+    for b in range(B):
+        a = (b - 1) % B
+        n, npv, nl, nlp = out["n"][b], out["n"][a], out["nl"][b], out["nl"][a]
+        ck, cd, pk, pd = out["kps"][b, :n], out["desc"][b, :n], out["kps"][a, :npv], out["desc"][a, :npv]
+        T = np.asarray(problems[b]["Tcw0"], np.float32).reshape(4, 4)
+        pos = t0["map_pos"][b, :npv]
+        assert np.array_equal(t0["pt_in_view"][b], (np.arange(fe.capK) < npv).astype(np.uint8))
+        if npv:                                                 # the synthetic map point projects back onto the previous keypoint
+            Xc = pos.astype(np.float64) @ T[:3, :3].T.astype(np.float64) + T[:3, 3]
+            uv = np.stack([Xc[:, 0] / Xc[:, 2] * K[0] + K[2], Xc[:, 1] / Xc[:, 2] * K[1] + K[3]], 1)
+            assert np.abs(uv - np.stack([pk["x"], pk["y"]], 1)).max() < 2e-2 and Xc[:, 2].min() > 1.0
+        valid = np.ones(npv, np.uint8)
+        nm, m = oracle.search_by_projection_last(ck, cd, bounds, T, K, sf, valid, pos, pd, pk["octave"], pk["angle"], 15.0, True)
+        if nm < 20:
+            retried += 1
+            nm, m = oracle.search_by_projection_last(ck, cd, bounds, T, K, sf, valid, pos, pd, pk["octave"], pk["angle"], 30.0, True)
+        assert t0["n_pt"][b] == nm and np.array_equal(t0["pt_match"][b, :n], m)
+        view = valid.copy(); view[m[m >= 0]] = 0
+        assert np.array_equal(t1["pt_in_view"][b, :npv], view)
+        nm2, m2 = oracle.search_by_projection_points(ck, cd, bounds, sf, view, np.stack([pk["x"], pk["y"]], 1), pk["octave"],
+                                                     np.ones(npv, np.float32), pd, 1.0, 0.8, (m >= 0).astype(np.uint8))
+        assert t1["n_pt"][b] == nm2 and np.array_equal(t1["pt_match"][b, :n], m2)
+        # lines
+        kl, lf, ld = out["keylines"][b, :nl], out["linefunc"][b, :nl], out["ldesc"][b, :nl]
+        pkl, pld = out["keylines"][a, :nlp], out["ldesc"][a, :nlp]
+        proj = np.stack([pkl["startPointX"], pkl["startPointY"], pkl["endPointX"], pkl["endPointY"]], 1).astype(np.float32)
+        lvalid = np.ones(nlp, np.uint8)
+        lnm, lm = oracle.line_search_by_projection_last(kl, lf, ld, bounds, lvalid, proj, pld, pkl["lineLength"], 15.0)
+        assert t0["n_line"][b] == lnm and np.array_equal(t0["line_match"][b, :nl], lm)
+        lview = lvalid.copy(); lview[lm[lm >= 0]] = 0
+        lnm2, lm2 = oracle.line_search_by_projection_lines(kl, lf, ld, bounds, lview, proj, np.ones(nlp, np.float32), pld, 1.0, 0.7,
+                                                           (lm >= 0).astype(np.uint8))
+        assert t1["n_line"][b] == lnm2 and np.array_equal(t1["line_match"][b, :nl], lm2)
+    assert retried >= 2 and t0["n_pt"].max() > 100 and t0["n_line"].max() > 20

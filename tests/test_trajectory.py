@@ -2,7 +2,9 @@
 replay dump.  Golden lines are hand-derived from the iostream format (`fixed`, setprecision(6/7/9))."""
 import os
 import numpy as np
+import pytest
 from plslam_b200 import trajectory as tr, synth
+traj = tr
 
 
 def _pose(rx, ry, rz, t):
@@ -55,3 +57,43 @@ def test_files_and_binary_dump(tmp_path):
     tr.dump_frontend(str(f), out, B)
     B2, back = tr.load_frontend(str(f))
     assert B2 == B and all(back[k].tobytes() == np.ascontiguousarray(out[k]).tobytes() and back[k].shape == out[k].shape for k in out)
+
+
+@pytest.mark.gpu
+def test_c_abi_writers_equal_the_python_formatters(tmp_path):
+    """pl_trajectory_format_* (pose records from k_pose_records on the GPU, C formatting) byte for byte against the Python
+    restatement of System::SaveKeyFrameTrajectoryTUM / MonoKitti, including the isBad() skip and both quaternion branches."""
+    import plslam_b200 as pl
+    rng = np.random.default_rng(5)
+    poses = []
+    for i in range(300):
+        ang = rng.uniform(-np.pi, np.pi, 3) * (1.0 if i % 3 else 0.05)          # small and large rotations: trace > 0 and the other branch
+        cx, sx, cy, sy, cz, sz = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1]), np.cos(ang[2]), np.sin(ang[2])
+        R = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @ np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        T = np.eye(4); T[:3, :3] = R; T[:3, 3] = rng.normal(0, 3, 3)
+        poses.append(T.astype(np.float32))
+    poses = np.array(poses)
+    ts = 1305031102.175304 + np.arange(len(poses)) * 0.0333
+    bad = (rng.random(len(poses)) < 0.1)
+    assert traj.c_format_keyframe_trajectory_tum(ts, poses, bad) == traj.format_keyframe_trajectory_tum(ts, poses, bad)
+    assert traj.c_format_keyframe_trajectory_mono_kitti(poses, bad) == traj.format_keyframe_trajectory_mono_kitti(poses, bad)
+    assert traj.c_format_keyframe_trajectory_tum(ts[:0], poses[:0]) == ""
+    traj.c_save(tmp_path / "kf_tum.txt", poses, ts); traj.c_save(tmp_path / "kf_kitti.txt", poses)
+    assert (tmp_path / "kf_tum.txt").read_text() == traj.format_keyframe_trajectory_tum(ts, poses)
+    assert (tmp_path / "kf_kitti.txt").read_text() == traj.format_keyframe_trajectory_mono_kitti(poses)
+
+
+@pytest.mark.gpu
+def test_frontend_dump_round_trip(tmp_path):
+    import plslam_b200 as pl
+    from plslam_b200 import synth
+    B = 2
+    frames = synth.synth_sequence(B, 640, 480, seed=3)
+    fe = pl.Frontend(640, 480, max_batch=B, lm_caps=(320, 88))
+    fe.set_pose_problems([synth.synth_pose_problem(40 + k) for k in range(B)])
+    out = fe.run(frames)
+    fe.dump(B, tmp_path / "step.bin")
+    Bq, q = traj.load_frontend(tmp_path / "step.bin")
+    assert Bq == B
+    for k in ("kps", "desc", "n", "keylines", "ldesc", "linefunc", "nl", "pt_matches", "n_pt_matches", "line_matches", "n_line_matches", "poses", "inliers"):
+        assert q[k].tobytes() == np.ascontiguousarray(out[k]).tobytes(), k

@@ -9,9 +9,10 @@ from plslam_b200 import synth
 ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=4736); ap.add_argument("--steps", type=int, default=2)
 a = ap.parse_args()
 B = a.batch
-frames, problems = bench.make_inputs(B, seed=1)
+K, D = bench.camera_of(bench.CONFIGS["tum"])
+frames, problems = bench.make_inputs(B, 1, bench.W, bench.H, K)
 fe = pl.Frontend(bench.W, bench.H, max_batch=B, orb=bench.ORB, lines=bench.LINES, lm_caps=(bench.N_PTS + 20, bench.N_LINES + 8))
-fe.set_pose_problems(problems); fe.set_camera(synth.TUM1_K, synth.TUM1_DIST)
+fe.set_pose_problems(problems); fe.set_camera(K, D); fe.set_tracking(True)
 d = torch.from_numpy(frames).cuda()
 st = torch.cuda.Stream()
 for _ in range(2):

@@ -150,6 +150,9 @@ __global__ void __launch_bounds__(LM_THREADS) k_pose_opt(PoseArgs A) {
   };
 
   int nBadPts = 0, nBadLines = 0, total_its = 0;
+  // The loops are NOT unrolled on purpose: unrolled and unswitched on the two robust flags the kernel grew to 147 k SASS
+  // instructions (2.3 MB) and stalled 12 cycles per issue on instruction fetch (profiles/r02_k_pose_opt.md).
+#pragma unroll 1
   for (int round = 0; round < 4; round++) {
     // ---- optimizer.optimize(10) on the level-0 edges, starting from the frame's initial pose
     int cnt = 0;
@@ -159,6 +162,7 @@ __global__ void __launch_bounds__(LM_THREADS) k_pose_opt(PoseArgs A) {
     if (tid == 0) { S.T = S.T0; S.nBad = 0; }
     __syncthreads();
     if (anyActive) {
+#pragma unroll 1
       for (int it = 0; it < 10; it++) {
         total_its++;
         errors_and_chi2();
@@ -231,6 +235,7 @@ __global__ void __launch_bounds__(LM_THREADS) k_pose_opt(PoseArgs A) {
         }
         __syncthreads();
         // ---- trial steps
+#pragma unroll 1
         while (true) {
           if (tid == 0) {
             S.backup = S.T;

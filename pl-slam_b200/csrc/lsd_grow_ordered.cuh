@@ -61,16 +61,17 @@ __device__ __forceinline__ void ordered_add3(const Ctx& C, double t0, double t1,
   __syncwarp();
 }
 __device__ __forceinline__ double ordered_get(double acc, int j) { return shfl_d(acc, j); }
-__device__ __forceinline__ double wmax_d(double v) {
+__device__ __noinline__ double wmax_d(double v) {          // out of line on purpose (4 uses per rectangle; code size, see §6 of DESIGN.md)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ double wmin_d(double v) {
+__device__ __noinline__ double wmin_d(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+__device__ __noinline__ float fast_atan2_cold(float y, float x) { return lg::fast_atan2_deg(y, x); }
 __device__ __forceinline__ bool is_aligned_generic(double a, double theta, double prec) {
   const double n1 = fabs(theta - a);
   const double n2 = fabs(n1 - 2 * kPI);
@@ -225,11 +226,12 @@ __device__ __noinline__ void region2rect(const Ctx& C, int n, double reg_angle, 
   }
   const double Ixx = ordered_get(acc, 0), Iyy = ordered_get(acc, 1), Ixy = -ordered_get(acc, 2);
   const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
-  double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)lg::fast_atan2_deg((float)(lambda - Ixx), (float)Ixy)
-                                         : (double)lg::fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
+  double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_cold((float)(lambda - Ixx), (float)Ixy)
+                                         : (double)fast_atan2_cold((float)Ixy, (float)(lambda - Iyy));
   theta *= kDegToRads;
   if (fabs(lg::angle_diff_signed(theta, reg_angle)) > prec) theta += kPI;
-  const double dx = cos(theta), dy = sin(theta);
+  double dx, dy;
+  sincos(theta, &dy, &dx);              // one range reduction; same results as cos() / sin() (CUDA's sincos is the pair of them)
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
 #pragma unroll 1
   for (int i = lane; i < n; i += 32) {

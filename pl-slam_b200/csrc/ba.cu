@@ -120,9 +120,10 @@ __device__ double errors_and_chi2(const BAArgs& A, BAShared& S, bool p_robust, b
   return block_sum(S, chi, tid);
 }
 
-// one optimizer.optimize(iterations) call on the level-0 edges
-// __noinline__ and no unrolling of the iteration / trial loops: inlined twice and unrolled the kernel was 81 k SASS instructions
-__device__ __noinline__ int ba_optimize(const BAArgs& A, BAShared& S, int iterations, bool p_robust, bool l_robust, int tid) {
+// one optimizer.optimize(iterations) call on the level-0 edges.  (Unlike k_pose_opt, this kernel is ONE CTA per problem with the SM
+// to itself: keeping the LM loops rolled and this function out of line shrinks it from 81 k to 21 k SASS instructions but costs
+// 28 % - 54.7 -> 70.0 ms on the 20+40-keyframe window - so the inlined, unrolled form stays.)
+__device__ int ba_optimize(const BAArgs& A, BAShared& S, int iterations, bool p_robust, bool l_robust, int tid) {
   const double kDeltaMono = (double)(float)sqrt(5.991), kDeltaLine = (double)(float)sqrt(3.84);
   const int n_lm = A.n_pt + 2 * A.n_ln, n_edges = A.n_pe + 2 * A.n_le;
   // ---- active sets and slots (initializeOptimization)
@@ -148,7 +149,6 @@ __device__ __noinline__ int ba_optimize(const BAArgs& A, BAShared& S, int iterat
   if (np + nl == 0) return 0;
   for (int i = tid; i < n + nl * 3; i += BA_THREADS) A.x[i] = 0.0;
   int done = 0;
-#pragma unroll 1
   for (int it = 0; it < iterations; it++) {
     if (A.stop && *A.stop) break;                       // SparseOptimizer::terminate()
     done++;
@@ -261,7 +261,6 @@ __device__ __noinline__ int ba_optimize(const BAArgs& A, BAShared& S, int iterat
     if (tid == 0) { S.rho = 0; S.qmax = 0; }
     __syncthreads();
     // ---- trial steps
-#pragma unroll 1
     while (true) {
       const double lambda = S.lambda;
       for (int k = tid; k < A.n_kf; k += BA_THREADS) A.Tb[k] = A.T[k];

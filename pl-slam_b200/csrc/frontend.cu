@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include <vector>
+#include <string>
 #include <cstdio>
 #include <string.h>
 
@@ -101,6 +102,7 @@ struct PLFrontend {
   PLKeyPoint* d_kps_prev = nullptr; uint8_t* d_desc_prev = nullptr; int* d_n_prev = nullptr;
   uint8_t* d_ldesc_prev = nullptr; int* d_nl_prev = nullptr;
   uint8_t* d_kl_prev = nullptr;          // keylines hold B+1 slots like the descriptors (d_kl = slot 1)
+  char order[4] = {'L', 'O', 'M', 0};
   // steady-state tracking stage (pl_frontend_set_tracking): the map seen from frame b is frame b-1's features (see k_track_points)
   int tracking = 0;
   float* d_sf = nullptr;
@@ -174,9 +176,14 @@ extern "C" int pl_frontend_create(const PLFrontendConfig* cfg, PLFrontend** out)
   FE_CUDA(cudaEventCreateWithFlags(&h->evStart, cudaEventDisableTiming));
   FE_CUDA(cudaEventCreateWithFlags(&h->evLine, cudaEventDisableTiming));
   FE_CUDA(cudaEventCreateWithFlags(&h->evLm, cudaEventDisableTiming));
-  // measured on B200 (B=4736): running the three chains on separate streams gains nothing (the region-growing kernel
-  // already fills the register file with 32 warps per SM), so the default is one stream; PLSLAM_FRONTEND_OVERLAP=1 enables it
-  { const char* e = getenv("PLSLAM_FRONTEND_OVERLAP"); h->overlap = (e && e[0] == '1'); }
+  // The three chains run on separate streams (PLSLAM_FRONTEND_OVERLAP=0: one stream).  Round 1 measured no gain (the region
+  // growing filled the step); with the round-2 step the low-occupancy kernels (matchers, quadtree, pose optimisation) fill the
+  // tails of the others: 338.5 -> 327.7 ms per step at B = 4736.  The enqueue order of the chains makes no difference (327-330 ms).
+  { const char* e = getenv("PLSLAM_FRONTEND_OVERLAP"); h->overlap = !(e && e[0] == '0'); }
+  if (const char* e = getenv("PLSLAM_FRONTEND_ORDER")) {
+    const std::string o(e);
+    if (o.size() == 3 && o.find('L') != std::string::npos && o.find('O') != std::string::npos && o.find('M') != std::string::npos) memcpy(h->order, o.data(), 3);
+  }
   const size_t B = h->B, cK = h->capK, cL = h->capL, cp = cfg->lm_cap_points, cl = cfg->lm_cap_lines;
   FE_TRY(dev_alloc(&h->d_img, (size_t)cfg->width * cfg->height * B));
   // feature arrays hold B+1 frames: slot 0 = copy of the batch's last frame ("previous" of frame 0), slots 1..B = frames
@@ -311,6 +318,7 @@ extern "C" int pl_frontend_run_dev(PLFrontend* h, const uint8_t* imgs, int strid
     PL_CUDA(cudaStreamWaitEvent(sL, h->evStart, 0));
     PL_CUDA(cudaStreamWaitEvent(sM, h->evStart, 0));
   }
+  auto line_chain = [&]() -> int {
   // --- line chain (on the undistorted frames when the camera has distortion, Frame.cc:220-225)
   const uint8_t* limgs = imgs; int lstride = stride; size_t lframe = frame_stride;
   if (h->und) {
@@ -342,6 +350,9 @@ extern "C" int pl_frontend_run_dev(PLFrontend* h, const uint8_t* imgs, int strid
                                               h->d_lqproj, h->d_ldesc_prev, h->d_lqvcos, 1.f, 0.7f, h->d_lpre, h->d_lm2, h->d_lnm2, h->d_lscratch, sL))) return rc;
   }
   if (!h->wrap && (rc = carry_lines())) return rc;
+  return PL_OK;
+  };
+  auto orb_chain = [&]() -> int {
   // --- ORB chain (slot 0 <- frame B-1 so that frame b's predecessor is slot b, a plain offset)
   if ((rc = pl_orb_extract_batch_dev(h->orb, imgs, stride, frame_stride, B, h->d_kps, h->d_desc, h->d_n, st))) return rc;
   // mvKeysUn: the matcher works on undistorted keypoints (aliases of the raw ones without a distorting camera)
@@ -380,12 +391,22 @@ extern "C" int pl_frontend_run_dev(PLFrontend* h, const uint8_t* imgs, int strid
                                                      h->d_tproj, h->d_toct, h->d_tvcos, h->d_desc_prev, 1.f, 0.8f, h->d_tpre, h->d_tm2, h->d_tnm2, st))) return rc;
   }
   if (!h->wrap && (rc = carry_points())) return rc;
+  return PL_OK;
+  };
+  auto lm_chain = [&]() -> int {
   // --- pose optimisations: TrackWithMotionModel (Tracking.cc:1372) and TrackLocalMapWithLines (:1503)
   for (int call = 0; call < 2; call++)
     if ((rc = pl_pose_optimization_dev(0, B, h->d_T0, h->d_K, h->d_np, (int)cp, h->d_pobs, h->d_pw, h->d_pX, h->d_nl_lm, (int)cl,
                                        h->d_lfun, h->d_lX, h->d_Tout + 16 * (size_t)B * call, h->d_pout + cp * B * call,
                                        h->d_lout + cl * B * call, h->d_inl + (size_t)B * call, h->d_its + (size_t)B * call,
                                        h->d_scratch, sM))) return rc;
+  return PL_OK;
+  };
+  // enqueue order of the chains (it only matters with overlap on: the block scheduler serves the streams in launch order)
+  for (const char* o = h->order; *o; o++) {
+    rc = *o == 'L' ? line_chain() : *o == 'O' ? orb_chain() : lm_chain();
+    if (rc) return rc;
+  }
   if (h->overlap) {
     PL_CUDA(cudaEventRecord(h->evLine, sL));
     PL_CUDA(cudaEventRecord(h->evLm, sM));

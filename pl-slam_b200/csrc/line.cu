@@ -1034,12 +1034,20 @@ extern "C" int pl_line_extract_batch_dev(PLLine* h, const uint8_t* imgs, int str
     // status words of the speculative kernel serve as region list and far-pixel mask
     if (h->timing) PL_CUDA(cudaEventRecord(h->ev0, st));
     static const int pre_maxb = getenv("PLSLAM_LSD_PRE_MAXB") ? atoi(getenv("PLSLAM_LSD_PRE_MAXB")) : 256;
-    if (B <= pre_maxb)
-      k_lsd_grow_ordered<true><<<B, 32, 0, st>>>(P, h->d_rec, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_pool, h->GP.pool_cap, h->d_st, h->d_wtab,
-                                                 h->d_segs, h->d_nseg, h->d_overflow, B);
-    else
-      k_lsd_grow_ordered<false><<<B, 32, 0, st>>>(P, h->d_rec, h->d_sq, h->d_seedcs, h->d_order, h->d_ndef, h->d_pool, h->GP.pool_cap, h->d_st, h->d_wtab,
-                                                  h->d_segs, h->d_nseg, h->d_overflow, B);
+    // the kernel addresses the per-frame arrays with 32-bit element indices (frame * npx + pixel): at most 2^32 / npx frames per grid
+    const int chunk = (int)std::min<long long>(B, 0xffffffffLL / P.npx);
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+      const int nb = std::min(chunk, B - b0);
+      const size_t po = (size_t)b0 * P.npx;
+      if (B <= pre_maxb)
+        k_lsd_grow_ordered<true><<<nb, 32, 0, st>>>(P, h->d_rec + po, h->d_sq + po, h->d_seedcs + po, h->d_order + po, h->d_ndef + b0,
+                                                    h->d_pool + (size_t)b0 * h->GP.pool_cap, h->GP.pool_cap, h->d_st + po, h->d_wtab,
+                                                    h->d_segs + (size_t)b0 * P.seg_cap, h->d_nseg + b0, h->d_overflow, nb);
+      else
+        k_lsd_grow_ordered<false><<<nb, 32, 0, st>>>(P, h->d_rec + po, h->d_sq + po, h->d_seedcs + po, h->d_order + po, h->d_ndef + b0,
+                                                     h->d_pool + (size_t)b0 * h->GP.pool_cap, h->GP.pool_cap, h->d_st + po, h->d_wtab,
+                                                     h->d_segs + (size_t)b0 * P.seg_cap, h->d_nseg + b0, h->d_overflow, nb);
+    }
     PL_LAUNCH_CHECK();
   }
   if (h->timing) PL_CUDA(cudaEventRecord(h->ev1, st));

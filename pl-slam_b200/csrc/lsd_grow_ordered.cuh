@@ -24,11 +24,17 @@ using lg::kPI;
 constexpr int kORing = 256;   // recent queue entries in shared memory (512 entries cost 6 ms at B = 4736: the L1 share matters more)
 constexpr int kUsedO = 0;
 
+// Per-frame arrays are addressed as  kernel-parameter base + 32-bit element index (fb = frame * npx + pixel): one IMAD.WIDE per
+// access and no 64-bit frame pointers held in registers (the host launches at most 2^31 / npx frames per grid).  The queue
+// ring and the term rows of the ordered sums are file-scope __shared__ arrays: addressed directly, not through generic pointers.
 struct Ctx {
-  int4* REC; const int* SQ; const float2* S2; const double* wtab; unsigned* R; unsigned* ring; unsigned* mask;
-  double* red;          // shared memory, 3 x 32 doubles: the per-pixel terms of one batch, for the ordered sums
+  int4* REC; const int* SQ; const float2* S2; unsigned* mask;   // global bases (kernel parameters)
+  unsigned fb;                                                   // element offset of this frame in the arrays above
+  const double* wtab; unsigned* R;
   int sw, sh, fill_off; // fill_off: scratch area inside R (beyond the largest possible region)
 };
+__shared__ unsigned s_ring[kORing];
+__shared__ double s_red[96];          // 3 x 32 doubles: the per-pixel terms of one batch, for the ordered sums
 struct RectD { double x1, y1, x2, y2, width; };
 #ifdef PL_GROW_STATS
 __device__ unsigned long long g_grow_stats[24];
@@ -40,17 +46,25 @@ __device__ unsigned long long g_grow_stats[24];
 #endif
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ int& own_of(const Ctx& C, int idx) { return reinterpret_cast<int*>(&C.REC[idx])[0]; }
-__device__ __forceinline__ int angle_bits(const Ctx& C, int idx) { return reinterpret_cast<const int*>(&C.REC[idx])[1]; }
+__device__ __forceinline__ int& own_of(const Ctx& C, int idx) { return reinterpret_cast<int*>(&C.REC[C.fb + (unsigned)idx])[0]; }
+__device__ __forceinline__ int angle_bits(const Ctx& C, int idx) { return reinterpret_cast<const int*>(&C.REC[C.fb + (unsigned)idx])[1]; }
+// One 16-byte request per record.  (Written as "int4 v = REC[i]; if (v.x == free) use v.y, v.z, v.w" the compiler splits the load
+// into LDG.32 + branch + LDG.32 + LDG.64: two dependent round trips per step for every candidate that is free.)
+__device__ __forceinline__ int4 ld_rec(const Ctx& C, int idx) {
+  int4 v;
+  asm volatile("ld.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(&C.REC[C.fb + (unsigned)idx]) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 // Three running sums advanced in LIST ORDER over one batch of up to 32 pixels.  Every lane has put its three terms into
 // shared memory; lane j < 3 then walks row j (one LDS + one DADD per pixel for the whole warp - the three chains run in
 // three lanes of the same instruction), so the order of the additions is exactly the CPU's and the cost is 2 instructions
 // per pixel.  acc lives in lanes 0..2 (acc of lane j = sum j); ordered_get() hands a finished sum to every lane.
 __device__ __forceinline__ void ordered_add3(const Ctx& C, double t0, double t1, double t2, int m, double& acc, int lane) {
-  C.red[lane] = t0; C.red[32 + lane] = t1; C.red[64 + lane] = t2;
+  s_red[lane] = t0; s_red[32 + lane] = t1; s_red[64 + lane] = t2;
   __syncwarp();
-  const double* row = C.red + 32 * min(lane, 2);
+  const double* row = s_red + 32 * min(lane, 2);
   if (m == 32) {
 #pragma unroll
     for (int k = 0; k < 32; k++) acc += row[k];
@@ -95,11 +109,11 @@ struct Sure { float ca2, cn2; };
 template <bool kFast>
 __device__ __forceinline__ int region_grow(const Ctx& C, unsigned seed, double prec, double prec_hi, Sure sure, double& reg_angle_out, int lane) {
   const int sidx = (int)(seed >> 16) * C.sw + (int)(seed & 0xffffu);
-  const float2 s0 = __ldg(&C.S2[sidx]);
+  const float2 s0 = __ldg(&C.S2[C.fb + (unsigned)sidx]);
   double reg_angle = (double)__int_as_float(angle_bits(C, sidx)) * kDegToRads;
   float sumdx = s0.x, sumdy = s0.y;
   bool dirty = false;          // reg_angle lags the sums (it is the seed's own angle until the first pixel is added)
-  if (lane == 0) { C.R[0] = seed; C.ring[0] = seed; own_of(C, sidx) = kUsedO; }
+  if (lane == 0) { C.R[0] = seed; s_ring[0] = seed; own_of(C, sidx) = kUsedO; }
   int cnt = 1;
   __syncwarp();
   const int grp = lane >> 3, kk8 = lane & 7, kk = kk8 + (kk8 >= 4);
@@ -114,12 +128,12 @@ __device__ __forceinline__ int region_grow(const Ctx& C, unsigned seed, double p
     float2 csv = make_float2(0.f, 0.f);
     if (grp < m) {
       const int qi = i + grp;
-      const unsigned p = (cnt - qi <= kORing) ? C.ring[qi & (kORing - 1)] : C.R[qi];
+      const unsigned p = (cnt - qi <= kORing) ? s_ring[qi & (kORing - 1)] : C.R[qi];
       const int xx = (int)(p & 0xffffu) + ox, yy = (int)(p >> 16) + oy;
       if (xx >= 0 && yy >= 0 && xx < C.sw && yy < C.sh) {
         idx = yy * C.sw + xx;
         GSTAT_ALL(kFast ? 16 : 17, 1);
-        const int4 v = C.REC[idx];
+        const int4 v = ld_rec(C, idx);
         if (v.x == lg::kFree) {                       // defined and not USED
           valid = true; ab = v.y;
           csv = make_float2(__int_as_float(v.z), __int_as_float(v.w));
@@ -131,26 +145,30 @@ __device__ __forceinline__ int region_grow(const Ctx& C, unsigned seed, double p
     unsigned live = __ballot_sync(0xffffffffu, valid);
     if (live == 0u) continue;
     GSTAT(2, 1);
-    const double a = (double)__int_as_float(ab) * kDegToRads;
-    int mypos = -1;
+    // lanes that name the same pixel (a free pixel sits in up to four of the 3x3 windows of one step); invalid lanes are unique
+    const unsigned dups = __match_any_sync(0xffffffffu, pk);
+    unsigned acc = 0u;                                 // lanes accepted in this step, in order
+    const int cnt0 = cnt;
     while (live) {
       GSTAT(3, 1);
       unsigned A;
       bool exact = !kFast;
       if (kFast) {
+        // (|sum| >= 1 here: the seed is a unit vector and every added unit vector is within prec < 90 degrees of the sum)
         const float n2 = __fmaf_rn(sumdx, sumdx, __fmul_rn(sumdy, sumdy));
         const float dot = __fmaf_rn(sumdx, csv.x, __fmul_rn(sumdy, csv.y)), d2 = __fmul_rn(dot, dot);
         const bool sure_al = dot > 0.f && d2 >= __fmul_rn(sure.ca2, n2);
         const bool maybe = dot > 0.f && d2 > __fmul_rn(sure.cn2, n2);       // not (surely not aligned)
-        const unsigned SA = __ballot_sync(0xffffffffu, sure_al) & live, MB = __ballot_sync(0xffffffffu, maybe) & live;
-        if (n2 < 0.25f) exact = true;                 // (cannot happen with prec < pi/2; the band test needs a direction)
-        else if (MB == 0u) break;
-        else if ((MB & (0u - MB)) & SA) A = SA;       // the first candidate that may be aligned surely is: no arctangent
+        const unsigned MB = __ballot_sync(0xffffffffu, maybe) & live;
+        if (MB == 0u) break;
+        const unsigned SA = __ballot_sync(0xffffffffu, sure_al);
+        if ((MB & (0u - MB)) & SA) A = MB;            // the first candidate that may be aligned surely is: no arctangent
         else exact = true;
       }
       if (exact) {
         GSTAT(5, 1);
         if (dirty) { reg_angle = (double)lg::fast_atan2_deg(sumdy, sumdx) * kDegToRads; dirty = false; }
+        const double a = (double)__int_as_float(ab) * kDegToRads;
         bool al;
         if (kFast) { const double n1 = fabs(reg_angle - a); al = (n1 <= prec) || (n1 >= prec_hi); }
         else al = is_aligned_generic(a, reg_angle, prec);
@@ -159,18 +177,19 @@ __device__ __forceinline__ int region_grow(const Ctx& C, unsigned seed, double p
       }
       const int k = __ffs(A) - 1;
       GSTAT(kFast ? 4 : 11, 1);
-      if (lane == k) mypos = cnt;
+      acc |= 1u << k;
       cnt++;
       sumdx = __fadd_rn(sumdx, __shfl_sync(0xffffffffu, csv.x, k));
       sumdy = __fadd_rn(sumdy, __shfl_sync(0xffffffffu, csv.y, k));
       dirty = true;
       // everything up to k has been decided; the same pixel in a later 3x3 is now USED
-      live &= ~(((2u << k) - 1u) | __ballot_sync(0xffffffffu, pk == __shfl_sync(0xffffffffu, pk, k)));
+      live &= ~(((2u << k) - 1u) | __shfl_sync(0xffffffffu, dups, k));
     }
-    if (mypos >= 0) {      // publish: every accepted lane owns its pixel
+    if ((acc >> lane) & 1u) {      // publish: every accepted lane owns its pixel
+      const int mypos = cnt0 + __popc(acc & lanemask_lt());
       own_of(C, idx) = kUsedO;
       C.R[mypos] = pk;
-      C.ring[mypos & (kORing - 1)] = pk;
+      s_ring[mypos & (kORing - 1)] = pk;
     }
     __syncwarp();
   }
@@ -186,7 +205,7 @@ __device__ __noinline__ int region_grow_cold(const Ctx& C, unsigned seed, double
 __device__ __forceinline__ double pixel_weight(const Ctx& C, int px, int py) {
   // the gradient magnitude sqrt((gx^2 + gy^2) / 4) of the reference from the integer sum of squares, through the table of
   // exact square roots (an in-kernel fp64 sqrt measured 9 ms slower at B = 4736)
-  return __ldg(&C.wtab[__ldg(&C.SQ[py * C.sw + px])]);
+  return __ldg(&C.wtab[__ldg(&C.SQ[C.fb + (unsigned)(py * C.sw + px)])]);
 }
 __device__ __noinline__ void region2rect(const Ctx& C, int n, double reg_angle, double prec, RectD& rec, int lane) {
   double acc = 0;                       // lanes 0, 1, 2: sum x*w, sum y*w, sum w
@@ -266,7 +285,7 @@ __device__ __noinline__ int reduce_round(const Ctx& C, int n, double xc, double 
       if (far) own_of(C, (int)(p >> 16) * C.sw + (int)(p & 0xffffu)) = lg::kFree;
     }
     const unsigned mw = __ballot_sync(0xffffffffu, far);
-    if (lane == 0) C.mask[i0 >> 5] = mw;
+    if (lane == 0) C.mask[C.fb + (unsigned)(i0 >> 5)] = mw;
     kept += __popc(~mw & (n - i0 >= 32 ? 0xffffffffu : ((1u << (n - i0)) - 1u)));
   }
   __syncwarp();
@@ -282,7 +301,7 @@ __device__ __noinline__ int reduce_round(const Ctx& C, int n, double xc, double 
     const int w = w0 + lane;
     unsigned km = 0u;
     if (w < nw) {
-      km = ~C.mask[w];
+      km = ~C.mask[C.fb + w];
       if (w == wK) km &= ~((1u << (K & 31)) - 1u);                       // positions >= K only
       if (w == nw - 1 && (n & 31)) km &= (1u << (n & 31)) - 1u;          // positions < n only
     }
@@ -304,7 +323,7 @@ __device__ __noinline__ int reduce_round(const Ctx& C, int n, double xc, double 
     const int w = w0 + lane;
     unsigned hm = 0u;
     if (w * 32 < K) {
-      hm = C.mask[w];
+      hm = C.mask[C.fb + w];
       if (w == wK) hm &= (1u << (K & 31)) - 1u;                          // holes below K only
     }
     int c = __popc(hm), incl = c;
@@ -352,9 +371,9 @@ __device__ __noinline__ bool refine(const Ctx& C, int& n, double reg_angle, doub
     }
     unsigned mi = __ballot_sync(0xffffffffu, in);
     cnt += __popc(mi);
-    C.red[lane] = ad; C.red[32 + lane] = ad2;
+    s_red[lane] = ad; s_red[32 + lane] = ad2;
     __syncwarp();
-    const double* row = C.red + 32 * (lane & 1);       // lane 0: sum, lane 1: s_sum (the additions in list order)
+    const double* row = s_red + 32 * (lane & 1);       // lane 0: sum, lane 1: s_sum (the additions in list order)
     while (mi) {
       const int k = __ffs(mi) - 1;
       mi &= mi - 1u;
@@ -394,12 +413,9 @@ __global__ void __launch_bounds__(32, 32) k_lsd_grow_ordered(LineParams P, int4*
                                                              unsigned* __restrict__ reg, int reg_stride, unsigned* __restrict__ mask, const double* __restrict__ wtab,
                                                              float4* __restrict__ segs, int* __restrict__ nseg, int* __restrict__ overflow, int nframes) {
   using namespace ord;
-  __shared__ unsigned ring[kORing];
-  __shared__ double red[96];
   const int lane = threadIdx.x & 31;
   for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
-    const Ctx C = {REC + (long long)f * P.npx, SQ + (long long)f * P.npx, seedcs + (long long)f * P.npx, wtab,
-                   reg + (long long)f * reg_stride, ring, mask + (long long)f * P.npx, red, P.sw, P.sh, P.npx};
+    const Ctx C = {REC, SQ, seedcs, mask, (unsigned)f * (unsigned)P.npx, wtab, reg + (long long)f * reg_stride, P.sw, P.sh, P.npx};
     const unsigned* O = order + (long long)f * P.npx;
     float4* S = segs + (long long)f * P.seg_cap;
     const int n = ndef[f];
@@ -408,7 +424,7 @@ __global__ void __launch_bounds__(32, 32) k_lsd_grow_ordered(LineParams P, int4*
       const int i = i0 + lane;
       const unsigned pix = (i < n) ? O[i] : 0u;
       const int pidx = (int)(pix >> 16) * P.sw + (int)(pix & 0xffffu);
-      const int4 me = (i < n) ? C.REC[pidx] : make_int4(0, 0, 0, 0);
+      const int4 me = (i < n) ? ld_rec(C, pidx) : make_int4(0, 0, 0, 0);
       unsigned todo = __ballot_sync(0xffffffffu, i < n && me.x == lg::kFree);
       // Seeds of this batch whose region cannot get past the seed itself: no FREE neighbour is aligned with the seed's own angle
       // (the region angle of the first step).  Between two regions the set of free pixels only shrinks (a region releases only
@@ -425,22 +441,22 @@ __global__ void __launch_bounds__(32, 32) k_lsd_grow_ordered(LineParams P, int4*
         for (int q = 0; q < 8; q++) {
           const int kq = q + (q >= 4), xx = sx + kq % 3 - 1, yy = sy + kq / 3 - 1;
           if (xx >= 0 && yy >= 0 && xx < P.sw && yy < P.sh) {
-            const int4 v = C.REC[yy * P.sw + xx];
+            const int4 v = ld_rec(C, yy * P.sw + xx);
             const double n1 = fabs(a0 - (double)__int_as_float(v.y) * lg::kDegToRads);
             any |= (v.x == lg::kFree) && ((n1 <= P.prec) || (n1 >= P.prec_hi));
           }
         }
         single = !any;
-        prefetch_l2(&C.S2[pidx]);
+        prefetch_l2(&C.S2[C.fb + (unsigned)pidx]);
       }
       if (!kPre && ((todo >> lane) & 1u)) {   // this batch's seeds that will grow: their seed record and 3x3 rows into L2
-        prefetch_l2(&C.S2[pidx]);
+        prefetch_l2(&C.S2[C.fb + (unsigned)pidx]);
         const int up = max(pidx - P.sw, 1), dn = min(pidx + P.sw, P.npx - 2);
-        prefetch_l2(&C.REC[up - 1]); prefetch_l2(&C.REC[up + 1]); prefetch_l2(&C.REC[dn - 1]); prefetch_l2(&C.REC[dn + 1]);
-        prefetch_l2(&C.REC[max(pidx, 1) - 1]); prefetch_l2(&C.REC[min(pidx, P.npx - 2) + 1]);
+        prefetch_l2(&C.REC[C.fb + (unsigned)(up - 1)]); prefetch_l2(&C.REC[C.fb + (unsigned)(up + 1)]); prefetch_l2(&C.REC[C.fb + (unsigned)(dn - 1)]); prefetch_l2(&C.REC[C.fb + (unsigned)(dn + 1)]);
+        prefetch_l2(&C.REC[C.fb + (unsigned)(max(pidx, 1) - 1)]); prefetch_l2(&C.REC[C.fb + (unsigned)(min(pidx, P.npx - 2) + 1)]);
       }
       const unsigned singles = __ballot_sync(0xffffffffu, single);
-      if (i + 32 < n) { const unsigned pn = O[i + 32]; prefetch_l2(&C.REC[(int)(pn >> 16) * P.sw + (int)(pn & 0xffffu)]); }
+      if (i + 32 < n) { const unsigned pn = O[i + 32]; prefetch_l2(&C.REC[C.fb + (unsigned)((int)(pn >> 16) * P.sw + (int)(pn & 0xffffu))]); }
       while (todo) {
         {   // the lone seeds in front of the next seed that may grow: USED, nothing else
           const unsigned grow = todo & ~singles;
@@ -470,8 +486,10 @@ __global__ void __launch_bounds__(32, 32) k_lsd_grow_ordered(LineParams P, int4*
           }
         }
         __syncwarp();
-        // seeds later in this batch may have been consumed (or released by refine): re-read their words
-        todo = __ballot_sync(0xffffffffu, i < n && lane > k && own_of(C, pidx) == lg::kFree);
+        // seeds later in this batch may have been consumed (or released by refine): re-read their words - unless the region was
+        // the seed alone (36 % of the regions), which touched no other pixel
+        if (cnt == 1) todo &= ~((2u << k) - 1u);
+        else todo = __ballot_sync(0xffffffffu, i < n && lane > k && own_of(C, pidx) == lg::kFree);
       }
     }
     if (lane == 0) { nseg[f] = min(ns, P.seg_cap); if (ns > P.seg_cap) atomicOr(overflow, 1); }

@@ -4,7 +4,9 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 import this package.  The product package never does.
 
 Pinning (details in each source header and DESIGN.md §2): OpenCV primitives, LSD, undistortion / remap and the fp32 gemm
-order are pinned to cv2 4.13 golden vectors; ORB orchestration, LBD, the matchers, the g2o LM and BA are "parity unpinned"
-(the reference ships no vectors for them and cannot be built here).
+order are pinned to cv2 4.13 golden vectors; the whole ORB extraction is pinned to the reference's OWN src/ORBextractor.cc, compiled
+where it lies into oracle/_ref/libref_orb.so (RefOrb; byte-identical keypoints and descriptors, tests/test_oracle_orb_ref.py and
+tests/golden/orb_ref_*.npz); LBD, the matchers, the g2o LM and BA are "parity unpinned" (the reference ships no vectors for them
+and those files cannot be built here).
 """
 from .binding import *  # noqa

@@ -48,6 +48,73 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+_REF_LIB = os.path.join(_HERE, "_ref", "libref_orb.so")
+_ref = None
+
+
+def ref_orb_available():
+    """True when oracle/_ref/libref_orb.so exists: the reference's OWN src/ORBextractor.cc compiled where it lies
+    (oracle/Makefile target `ref`, oracle/ref_orb_wrap.cpp, oracle/shim/).  Built in the container that has /root/reference;
+    the file travels to the GPU box with the snapshot."""
+    if os.path.isdir("/root/reference/src") and not os.path.exists(_REF_LIB):
+        build()
+        subprocess.call(["make", "-C", _HERE, "-s", "ref"])
+    return os.path.exists(_REF_LIB)
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        lib()   # liboracle.so first (libref_orb.so links it for the cv2-pinned image primitives)
+        _ref = C.CDLL(_REF_LIB)
+        _ref.ref_orb_create.restype = C.c_void_p
+        _ref.ref_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        _ref.ref_orb_destroy.argtypes = [C.c_void_p]
+        _ref.ref_orb_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        _ref.ref_orb_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        _ref.ref_orb_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _ref.ref_orb_set_bump.argtypes = [C.c_int]
+    return _ref
+
+
+class RefOrb:
+    """The reference's ORB_SLAM2::ORBextractor itself (src/ORBextractor.cc compiled unmodified), not a restatement.
+    `ordered_heap=True` (default): list nodes get increasing addresses in allocation order, which fixes the otherwise
+    allocator-dependent pointer tie-break of ORBextractor.cc:684; False: glibc malloc order."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, ordered_heap=True):
+        self.nlevels, self.nfeatures, self.ordered_heap = nlevels, nfeatures, ordered_heap
+        self.h = ref_lib().ref_orb_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            ref_lib().ref_orb_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        n = self.nlevels
+        sc, isc, s2, is2 = (np.zeros(n, np.float32) for _ in range(4))
+        ref_lib().ref_orb_tables(self.h, _p(sc), _p(isc), _p(s2), _p(is2))
+        return dict(scale=sc, inv_scale=isc, sigma2=s2, inv_sigma2=is2)
+
+    def extract(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = self.nfeatures * 2 + 64
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        ref_lib().ref_orb_set_bump(1 if self.ordered_heap else 0)
+        n = ref_lib().ref_orb_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(desc), cap)
+        assert 0 <= n <= cap, n
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, l):
+        w, h = C.c_int(), C.c_int()
+        ref_lib().ref_orb_level(self.h, l, None, C.byref(w), C.byref(h))
+        out = np.zeros((h.value, w.value), np.uint8)
+        ref_lib().ref_orb_level(self.h, l, _p(out), C.byref(w), C.byref(h))
+        return out
+
+
 class OrbOracle:
     """Restatement of ORB_SLAM2::ORBextractor (reference src/ORBextractor.cc)."""
 

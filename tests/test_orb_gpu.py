@@ -45,6 +45,36 @@ def test_extract_matches_committed_golden(name):
     assert np.array_equal(desc, g["desc"])
 
 
+@pytest.mark.parametrize("name", ["640x480_n1000", "640x480_n2000", "752x480_n1000", "1241x376_n2000", "640x480_low",
+                                  "640x480_noise", "640x480_sparse", "640x480_n500_s11"])
+def test_extract_matches_reference_output(name):
+    """CUDA path vs the REFERENCE's own ORBextractor.cc (compiled where it lies by oracle/Makefile `ref`; its outputs on the
+    seeded frames are committed by tools/gen_golden_orb_ref.py because /root/reference does not exist on the GPU box)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from gen_golden_orb_ref import frame
+    g = np.load(os.path.join(G, f"orb_ref_{name}.npz"))
+    w, h, seed, nf, nl = [int(v) for v in g["params"]]
+    img = frame(str(g["kind"]), w, h, seed)
+    assert int(img.astype(np.int64).sum()) == int(g["img_sum"])
+    ex = pl.ORBextractor(nf, float(g["scale_factor"]), nl, 20, 7, width=w, height=h, cell_slot_cap=256 if "noise" in name else 0)
+    kps, desc = ex(img)
+    assert kps.tobytes() == g["kps"].tobytes()
+    assert np.array_equal(desc, g["desc"])
+    assert ex.GetScaleFactors().tobytes() == g["scale"].tobytes() and ex.GetInverseScaleSigmaSquares().tobytes() == g["inv_sigma2"].tobytes()
+    assert [tuple(d) for d in g["level_dims"]] == [ex.mvImagePyramid(l).shape[::-1] for l in range(nl)]
+
+
+@pytest.mark.skipif(not oracle.ref_orb_available(), reason="oracle/_ref/libref_orb.so did not travel")
+def test_extract_matches_live_reference_library():
+    # the prebuilt reference library itself, run on the GPU box's CPU next to the CUDA path (fresh seeds, not in the fixtures)
+    for w, h, seed, nf in [(640, 480, 21, 1000), (752, 480, 22, 1000), (1241, 376, 23, 2000)]:
+        img = synth.synth_frame(w, h, seed)
+        kps, desc = pl.ORBextractor(nf, 1.2, 8, 20, 7, width=w, height=h)(img)
+        rk, rd = oracle.RefOrb(nf, 1.2, 8, 20, 7).extract(img)
+        assert kps.tobytes() == rk.tobytes() and np.array_equal(desc, rd), (w, h, seed)
+
+
 def test_tables_match_reference_ctor():
     ex = pl.ORBextractor(1000, 1.2, 8, 20, 7)
     t = oracle.OrbOracle(1000, 1.2, 8, 20, 7).tables()

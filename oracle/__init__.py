@@ -6,7 +6,8 @@ import this package.  The product package never does.
 Pinning (details in each source header and DESIGN.md §2): OpenCV primitives, LSD, undistortion / remap and the fp32 gemm
 order are pinned to cv2 4.13 golden vectors; the whole ORB extraction is pinned to the reference's OWN src/ORBextractor.cc, compiled
 where it lies into oracle/_ref/libref_orb.so (RefOrb; byte-identical keypoints and descriptors, tests/test_oracle_orb_ref.py and
-tests/golden/orb_ref_*.npz); LBD, the matchers, the g2o LM and BA are "parity unpinned" (the reference ships no vectors for them
-and those files cannot be built here).
+tests/golden/orb_ref_*.npz); KeyLine construction and the LBD descriptor are pinned the same way to the reference tree's
+Thirdparty/line_descriptor sources (oracle/_ref/libref_line.so; tests/test_oracle_line_ref.py, tests/golden/line_ref_*.npz); the
+matchers, the g2o LM and BA are "parity unpinned" (the reference ships no vectors for them and those files cannot be built here).
 """
 from .binding import *  # noqa

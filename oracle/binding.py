@@ -52,6 +52,51 @@ _REF_LIB = os.path.join(_HERE, "_ref", "libref_orb.so")
 _ref = None
 
 
+_REF_LINE_LIB = os.path.join(_HERE, "_ref", "libref_line.so")
+_ref_line = None
+
+
+def ref_line_available():
+    """True when oracle/_ref/libref_line.so exists: the reference tree's own line-descriptor sources
+    (Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp, LSDDetector_custom.cpp) compiled where they lie."""
+    if os.path.isdir("/root/reference/src") and not os.path.exists(_REF_LINE_LIB):
+        build()
+        subprocess.call(["make", "-C", _HERE, "-s", "ref"])
+    return os.path.exists(_REF_LINE_LIB)
+
+
+def ref_line_lib():
+    global _ref_line
+    if _ref_line is None:
+        lib()
+        _ref_line = C.CDLL(_REF_LINE_LIB)
+        _ref_line.ref_lsd_keylines.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        _ref_line.ref_lbd_compute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    return _ref_line
+
+
+def ref_lsd_keylines(img, mask=None, scale=1, num_octaves=1):
+    """LSDDetectorC::detect(image, keylines, scale, numOctaves, mask) of the reference tree itself -> KeyLine records
+    in detection order (LINEextractor passes scale = (int)1.2 = 1 and one octave)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    cap = 65536
+    kl = np.zeros(cap, KEYLINE_DTYPE)
+    n = ref_line_lib().ref_lsd_keylines(_p(img), img.shape[1], img.shape[0], _p(m), scale, num_octaves, _p(kl), cap)
+    assert 0 <= n <= cap
+    return kl[:n].copy()
+
+
+def ref_lbd_compute(img, keylines, want_float=False):
+    """BinaryDescriptor::compute(image, keylines, descriptors) of the reference tree itself (class_id must index the lines)."""
+    img = np.ascontiguousarray(img, np.uint8); kl = np.ascontiguousarray(keylines)
+    desc = np.zeros((max(len(kl), 1), 32), np.uint8)
+    dv = np.zeros((max(len(kl), 1), 72), np.float32) if want_float else None
+    n = ref_line_lib().ref_lbd_compute(_p(img), img.shape[1], img.shape[0], _p(kl), len(kl), _p(desc), _p(dv))
+    assert n == len(kl), n
+    return (desc[:len(kl)], dv[:len(kl)]) if want_float else desc[:len(kl)]
+
+
 def ref_orb_available():
     """True when oracle/_ref/libref_orb.so exists: the reference's OWN src/ORBextractor.cc compiled where it lies
     (oracle/Makefile target `ref`, oracle/ref_orb_wrap.cpp, oracle/shim/).  Built in the container that has /root/reference;

@@ -335,10 +335,14 @@ void make_keylines(const std::vector<float>& lines, int iw, int ih, const uint8_
   int class_counter = -1;
   for (size_t k = 0; k + 3 < lines.size(); k += 4) {
     float e[4] = {lines[k], lines[k + 1], lines[k + 2], lines[k + 3]};
-    if (e[0] < 0) e[0] = 0; if (e[0] >= iw) e[0] = (float)iw - 1.0f;
-    if (e[2] < 0) e[2] = 0; if (e[2] >= iw) e[2] = (float)iw - 1.0f;
-    if (e[1] < 0) e[1] = 0; if (e[1] >= ih) e[1] = (float)ih - 1.0f;
-    if (e[3] < 0) e[3] = 0; if (e[3] >= ih) e[3] = (float)ih - 1.0f;
+    if (e[0] < 0) e[0] = 0;
+    if (e[0] >= iw) e[0] = (float)iw - 1.0f;
+    if (e[2] < 0) e[2] = 0;
+    if (e[2] >= iw) e[2] = (float)iw - 1.0f;
+    if (e[1] < 0) e[1] = 0;
+    if (e[1] >= ih) e[1] = (float)ih - 1.0f;
+    if (e[3] < 0) e[3] = 0;
+    if (e[3] >= ih) e[3] = (float)ih - 1.0f;
     KeyLine kl;
     const float octaveScale = 1.0f;  // pow((float)scale, 0)
     kl.startPointX = e[0] * octaveScale; kl.startPointY = e[1] * octaveScale;
@@ -348,7 +352,9 @@ void make_keylines(const std::vector<float>& lines, int iw, int ih, const uint8_
     // cv::LineIterator(img, Point2f, Point2f).count, 8-connected, end-points rounded half-to-even
     int x0 = (int)lrintf(e[0]), y0 = (int)lrintf(e[1]), x1 = (int)lrintf(e[2]), y1 = (int)lrintf(e[3]);
     kl.numOfPixels = std::max(std::abs(x1 - x0), std::abs(y1 - y0)) + 1;
-    kl.angle = (float)std::atan2((double)(kl.endPointY - kl.startPointY), (double)(kl.endPointX - kl.startPointX));
+    // atan2(float, float) resolves to <cmath>'s float overload: libm's atan2f (nm -u of the reference object: atan2f), not the
+    // rounded fp64 function (they differ by one ulp on ~16 % of the lines)
+    kl.angle = atan2f(kl.endPointY - kl.startPointY, kl.endPointX - kl.startPointX);
     kl.class_id = ++class_counter;
     kl.octave = 0;
     kl.size = (kl.endPointX - kl.startPointX) * (kl.endPointY - kl.startPointY);
@@ -393,6 +399,10 @@ struct Lbd {
     static const int t5[5] = {14, 62, 104, 62, 14};
     blur_sep_u8(img, w, h, b.data(), t5, 5);
     dx.assign((size_t)w * h, 0); dy.assign((size_t)w * h, 0);
+    sobel3(b.data(), w, h, dx.data(), dy.data());
+  }
+  // cv::Sobel(src 8U, dst 16S, 1, 0, 3) and (0, 1, 3), BORDER_REFLECT_101 (binary_descriptor_custom.cpp:395-396)
+  static void sobel3(const uint8_t* b, int w, int h, int16_t* dx, int16_t* dy) {
     for (int y = 0; y < h; y++)
       for (int x = 0; x < w; x++) {
         int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w), ym = reflect101(y - 1, h), yp = reflect101(y + 1, h);
@@ -412,7 +422,7 @@ struct Lbd {
     const float midX = (float)(0.5 * (kl.sPointInOctaveX + kl.ePointInOctaveX));
     const float midY = (float)(0.5 * (kl.sPointInOctaveY + kl.ePointInOctaveY));
     float dL[2], dO[2];
-    dL[0] = (float)std::cos((double)kl.angle); dL[1] = (float)std::sin((double)kl.angle);
+    sincosf(kl.angle, &dL[1], &dL[0]);   // cos / sin of a float: libm's float functions (the reference object calls sincosf)
     dO[0] = -dL[1]; dO[1] = dL[0];
     float sCorX0 = -dL[0] * halfWidth + dL[1] * halfHeight + midX;
     float sCorY0 = -dL[1] * halfWidth - dL[0] * halfHeight + midY;
@@ -521,6 +531,8 @@ void oracle_lbd_compute(const uint8_t* img, int w, int h, const void* keylines, 
   const KeyLine* k = (const KeyLine*)keylines;
   for (int i = 0; i < n; i++) lbd.describe(k[i], desc + 32 * i, desvec ? desvec + 72 * i : nullptr);
 }
+// the Sobel pair alone, on an image that is already blurred (the primitive behind the OpenCV stand-in of oracle/shim/)
+void oracle_sobel3_u8(const uint8_t* img, int w, int h, int16_t* dx, int16_t* dy) { Lbd::sobel3(img, w, h, dx, dy); }
 void oracle_lbd_sobel(const uint8_t* img, int w, int h, int16_t* dx, int16_t* dy) {
   Lbd lbd;
   lbd.prepare(img, w, h);

@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "lsd_grow_core.cuh"
+#include "libm_glibc.cuh"
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
@@ -652,7 +653,7 @@ __global__ void __launch_bounds__(256) k_keylines(LineParams P, const float4* __
       kl.lineLength = seglen(e);
       const int x0 = __float2int_rn(e.x), y0 = __float2int_rn(e.y), x1 = __float2int_rn(e.z), y1 = __float2int_rn(e.w);
       kl.numOfPixels = max(abs(x1 - x0), abs(y1 - y0)) + 1;
-      kl.angle = (float)atan2((double)__fsub_rn(e.w, e.y), (double)__fsub_rn(e.z, e.x));
+      kl.angle = glibc::atan2f_(__fsub_rn(e.w, e.y), __fsub_rn(e.z, e.x));   // libm's atan2f, bit for bit (libm_glibc.cuh)
       kl.octave = 0;
       kl.size = __fmul_rn(__fsub_rn(e.z, e.x), __fsub_rn(e.w, e.y));
       kl.response = __fdiv_rn(kl.lineLength, (float)max(P.w, P.h));
@@ -748,7 +749,7 @@ __global__ void __launch_bounds__(64) k_lbd_describe(LineParams P, const PLKeyLi
   const float midY = (float)(0.5 * (double)__fadd_rn(kl.sPointInOctaveY, kl.ePointInOctaveY));
   __shared__ float s_dL[2], s_gL[21], s_norm2[2];
   if (tid < 21) s_gL[tid] = c_gaussL[tid];
-  if (tid == 0) { s_dL[0] = (float)cos((double)kl.angle); s_dL[1] = (float)sin((double)kl.angle); }   // fp64 libm once per line
+  if (tid == 0) glibc::sincosf_(kl.angle, &s_dL[1], &s_dL[0]);   // libm's sincosf, bit for bit (libm_glibc.cuh); once per line
   __syncthreads();
   const float dL0 = s_dL[0], dL1 = s_dL[1];
   const float dO0 = -dL1, dO1 = dL0;

@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "tma.cuh"
+#include "libm_glibc.cuh"
 #include <math.h>
 #include <vector>
 #include <algorithm>
@@ -699,7 +700,7 @@ __global__ void __launch_bounds__(32 * kDescWarps) k_describe(OrbParams P, const
   const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
   const float ang = __fmul_rn(angle, factorPI);
   float a = 0.f, b = 0.f;
-  if (lane == 0) { a = (float)cos((double)ang); b = (float)sin((double)ang); }   // fp64 libm once per keypoint, not once per lane
+  if (lane == 0) glibc::sincosf_(ang, &b, &a);   // the C library's sincosf, bit for bit (libm_glibc.cuh); once per keypoint
   a = __shfl_sync(0xffffffffu, a, 0); b = __shfl_sync(0xffffffffu, b, 0);
   const int bp = L.bpitch;
   const uint8_t* ctr = blur + (long long)frame * P.blur_frame + L.boff + (long long)py * bp + px;

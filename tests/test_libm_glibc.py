@@ -1,0 +1,26 @@
+"""The float libm restatements of the CUDA path (pl-slam_b200/csrc/libm_glibc.cuh: atan2f, sincosf as glibc 2.39 computes them)
+against the running C library, on the host: the header is plain C++ outside nvcc.  The reference calls exactly these two functions
+(KeyLine::angle, the LBD line direction, the rBRIEF steering); the device code is the same source compiled with -fmad=false."""
+import os
+import subprocess
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _glibc():
+    import ctypes
+    f = ctypes.CDLL(None).gnu_get_libc_version
+    f.restype = ctypes.c_char_p
+    return f().decode()
+
+
+def test_device_libm_equals_host_libm(tmp_path):
+    exe = str(tmp_path / "libm_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-mfma", "-x", "c++", os.path.join(ROOT, "tests", "host", "libm_check.cpp"),
+                           "-o", exe])
+    r = subprocess.run([exe, "20000000"], capture_output=True, text=True)
+    if r.returncode != 0 and not _glibc().startswith("2.39"):
+        pytest.skip(f"glibc {_glibc()} computes these functions differently from the 2.39 the restatement follows: {r.stdout.strip()}")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("mismatches 0 0 0 of"), r.stdout

@@ -47,6 +47,40 @@ def test_stages_match_oracle(monkeypatch, w, h, seed, spec_maxb):
     assert lf.tobytes() == olf.tobytes(), "line equations"
 
 
+@pytest.mark.parametrize("name", ["640x480_s1", "640x480_s2", "752x480_s5", "1241x376_s4"])
+def test_extract_matches_reference_output(name):
+    """CUDA path vs the reference tree's OWN line-descriptor sources (LSDDetector_custom.cpp KeyLines + binary_descriptor_custom.cpp
+    LBD, compiled where they lie by oracle/Makefile `ref`; outputs committed by tools/gen_golden_line_ref.py because /root/reference
+    does not exist on the GPU box): KeyLine records (libm's atan2f angle included) and LBD bytes identical."""
+    g = np.load(os.path.join(G, f"line_ref_{name}.npz"))
+    w, h, seed, nf = [int(v) for v in g["params"]]
+    img = synth.synth_frame(w, h, seed)
+    assert int(img.astype(np.int64).sum()) == int(g["img_sum"])
+    kl, desc, lf = pl.LINEextractor(1, 1.2, nf, 0.0, width=w, height=h)(img)
+    assert kl.tobytes() == g["top"].tobytes(), "KeyLine records vs the reference's"
+    assert np.array_equal(desc, g["desc"]), "LBD descriptors vs the reference's"
+    # every KeyLine of the frame, not only the selection: ask for more lines than there are (one zero record is appended then)
+    n_all = len(g["keylines"])
+    kl2, _, _ = pl.LINEextractor(1, 1.2, n_all + 10, 0.0, width=w, height=h)(img)
+    order = np.argsort(-g["keylines"]["response"], kind="stable")
+    want = g["keylines"][order].copy(); want["class_id"] = np.arange(n_all)
+    assert len(kl2) == n_all + 1 and kl2[:-1].tobytes() == want.tobytes(), "all KeyLines of the frame vs the reference's"
+
+
+@pytest.mark.skipif(not oracle.ref_line_available(), reason="oracle/_ref/libref_line.so did not travel")
+def test_extract_matches_live_reference_library():
+    # the prebuilt reference library itself on the GPU box's CPU (fresh seeds, not in the fixtures): the CUDA KeyLines through the
+    # reference's LBD, and the reference's KeyLines against the CUDA ones
+    for w, h, seed in [(640, 480, 31), (752, 480, 32)]:
+        img = synth.synth_frame(w, h, seed)
+        kl, desc, lf = pl.LINEextractor(1, 1.2, 200, 0.0, width=w, height=h)(img)
+        rk = oracle.ref_lsd_keylines(img)
+        order = np.argsort(-rk["response"], kind="stable")
+        want = rk[order][:201].copy(); want["class_id"] = np.arange(201)
+        assert kl.tobytes() == want.tobytes(), (w, h, seed)
+        assert np.array_equal(desc, oracle.ref_lbd_compute(img, want)), (w, h, seed)
+
+
 def test_lbd_given_oracle_keylines_is_bit_exact():
     """Descriptor stage alone: feed identical frames; every line whose record matches must have identical 32 bytes."""
     img = synth.synth_frame(640, 480, 7)

@@ -1,0 +1,89 @@
+"""CPU tests: the line oracle against the reference tree's OWN line-descriptor sources
+(Thirdparty/line_descriptor/src/LSDDetector_custom.cpp and binary_descriptor_custom.cpp compiled unmodified into
+oracle/_ref/libref_line.so - oracle/Makefile target `ref`, oracle/ref_line_wrap.cpp, oracle/shim/).
+
+(a) committed reference outputs (tests/golden/line_ref_*.npz, tools/gen_golden_line_ref.py): run everywhere;
+(b) live comparison where libref_line.so exists: every KeyLine record of a frame byte-identical (all 17 fields, including the
+    libm-dependent angle), 32-byte LBD descriptors AND the 72-float LBD vectors bit-identical.
+"""
+import os
+import sys
+import numpy as np
+import pytest
+import oracle
+from plslam_b200 import synth
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+from gen_golden_line_ref import CASES, select  # noqa: E402
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+needs_ref = pytest.mark.skipif(not oracle.ref_line_available(), reason="oracle/_ref/libref_line.so not built (needs /root/reference)")
+
+
+def _oracle_all_keylines(img, mask=None):
+    """every KeyLine the oracle makes for the frame, in LINEextractor's sorted order (the trailing record is the default-constructed
+    KeyLine that `resize(index + 1)` appends when nothing is cut, LineExtractor.cpp:64)"""
+    kl, desc, lf = oracle.line_extract(img, mask=mask, nfeatures=100000)
+    return kl[:-1]
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_equals_committed_reference_output(name):
+    g = np.load(os.path.join(G, f"line_ref_{name}.npz"))
+    w, h, seed, nf = [int(v) for v in g["params"]]
+    img = synth.synth_frame(w, h, seed)
+    assert int(img.astype(np.int64).sum()) == int(g["img_sum"])
+    # all KeyLines of the frame (the reference's detection order, sorted here as LINEextractor sorts them)
+    allk = _oracle_all_keylines(img)
+    want = select(g["keylines"], len(g["keylines"]))
+    assert allk.tobytes() == want.tobytes()
+    # the LINEextractor selection and its descriptors
+    kl, desc, lf = oracle.line_extract(img, nfeatures=nf)
+    assert kl.tobytes() == g["top"].tobytes()
+    assert np.array_equal(desc, g["desc"])
+    d2, dv = oracle.lbd_compute(img, kl, want_float=True)
+    assert np.array_equal(d2, g["desc"]) and dv.tobytes() == g["desvec"].tobytes()
+
+
+@needs_ref
+@pytest.mark.parametrize("w,h,seed", [(640, 480, 3), (640, 480, 7), (752, 480, 9), (1241, 376, 10), (320, 240, 3), (800, 600, 12)])
+def test_keylines_equal_live_reference(w, h, seed):
+    img = synth.synth_frame(w, h, seed)
+    rk = oracle.ref_lsd_keylines(img)
+    assert len(rk) > 100
+    assert _oracle_all_keylines(img).tobytes() == select(rk, len(rk)).tobytes()
+
+
+@needs_ref
+def test_keylines_with_mask_equal_live_reference():
+    img = synth.synth_frame(640, 480, 4)
+    mask = np.full((480, 640), 255, np.uint8)
+    mask[100:300, 150:500] = 0          # a line is dropped only if BOTH end points fall on zeros (LSDDetector_custom.cpp:203-213)
+    rk = oracle.ref_lsd_keylines(img, mask)
+    assert len(rk) < len(oracle.ref_lsd_keylines(img))
+    assert _oracle_all_keylines(img, mask).tobytes() == select(rk, len(rk)).tobytes()
+
+
+@needs_ref
+@pytest.mark.parametrize("w,h,seed,nf", [(640, 480, 3, 200), (752, 480, 9, 200), (1241, 376, 10, 400), (320, 240, 3, 100)])
+def test_lbd_equals_live_reference(w, h, seed, nf):
+    img = synth.synth_frame(w, h, seed)
+    kl, desc, lf = oracle.line_extract(img, nfeatures=nf)
+    assert len(kl) == nf + 1
+    rd, rv = oracle.ref_lbd_compute(img, kl, want_float=True)
+    od, ov = oracle.lbd_compute(img, kl, want_float=True)
+    assert np.array_equal(desc, rd) and np.array_equal(od, rd)
+    assert ov.tobytes() == rv.tobytes()                     # the 72 floats behind the bits as well
+
+
+@needs_ref
+def test_lbd_on_short_and_border_lines():
+    # lines clipped at the border and very short lines exercise the coordinate clamps and the 2-pixel support region
+    img = synth.synth_frame(640, 480, 8)
+    rk = oracle.ref_lsd_keylines(img)
+    sel = rk[(rk["lineLength"] < 6) | (rk["startPointX"] < 3) | (rk["endPointY"] > 475) | (rk["startPointY"] < 3) | (rk["endPointX"] > 635)][:150].copy()
+    assert len(sel) > 20
+    sel["class_id"] = np.arange(len(sel))
+    rd, rv = oracle.ref_lbd_compute(img, sel, want_float=True)
+    od, ov = oracle.lbd_compute(img, sel, want_float=True)
+    assert np.array_equal(od, rd) and ov.tobytes() == rv.tobytes()

@@ -97,6 +97,31 @@ def ref_lbd_compute(img, keylines, want_float=False):
     return (desc[:len(kl)], dv[:len(kl)]) if want_float else desc[:len(kl)]
 
 
+_REF_MATCH_LIB = os.path.join(_HERE, "_ref", "libref_match.so")
+_ref_match = None
+
+
+def ref_match_available():
+    """True when oracle/_ref/libref_match.so exists: the reference's OWN src/ORBmatcher.cc and src/MapPoint.cc compiled where they
+    lie against mock Frame / KeyFrame / Map (oracle/shim_slam/, oracle/ref_match_wrap.cpp)."""
+    if os.path.isdir("/root/reference/src") and not os.path.exists(_REF_MATCH_LIB):
+        build()
+        subprocess.call(["make", "-C", _HERE, "-s", "ref"])
+    return os.path.exists(_REF_MATCH_LIB)
+
+
+def _fn(name, impl):
+    """the oracle's restatement (`oracle_<name>` in liboracle.so) or the reference's own code (`ref_<name>` in libref_match.so):
+    same flat-array signature"""
+    global _ref_match
+    if impl == "oracle":
+        return getattr(lib(), "oracle_" + name)
+    assert impl == "ref", impl
+    if _ref_match is None:
+        _ref_match = C.CDLL(_REF_MATCH_LIB)
+    return getattr(_ref_match, "ref_" + name)
+
+
 def ref_orb_available():
     """True when oracle/_ref/libref_orb.so exists: the reference's OWN src/ORBextractor.cc compiled where it lies
     (oracle/Makefile target `ref`, oracle/ref_orb_wrap.cpp, oracle/shim/).  Built in the container that has /root/reference;
@@ -268,9 +293,10 @@ KL_DTYPE = np.dtype([("startX", "<f4"), ("startY", "<f4"), ("endX", "<f4"), ("en
                      ("lineLength", "<f4"), ("angle", "<f4"), ("octave", "<i4")])
 
 
-def descriptor_distance(a, b):
+def descriptor_distance(a, b, impl="oracle"):
     a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
-    return lib().oracle_descriptor_distance(_p(a), _p(b))
+    f = _fn("descriptor_distance", impl); f.argtypes = [C.c_void_p, C.c_void_p]
+    return f(_p(a), _p(b))
 
 
 def assign_grid(keys, bounds):
@@ -280,24 +306,23 @@ def assign_grid(keys, bounds):
     return start, items[:n]
 
 
-def search_for_initialization(k1, d1, k2, d2, bounds, prev_matched, window=100, nnratio=0.9, check_ori=True):
+def search_for_initialization(k1, d1, k2, d2, bounds, prev_matched, window=100, nnratio=0.9, check_ori=True, impl="oracle"):
     k1 = np.ascontiguousarray(k1); k2 = np.ascontiguousarray(k2)
     d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
     pm = np.ascontiguousarray(prev_matched, np.float32).copy()
     m = np.zeros(max(len(k1), 1), np.int32)
     b = np.asarray(bounds, np.float32)
-    lib().oracle_search_for_initialization.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
-                                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
-    nm = lib().oracle_search_for_initialization(_p(k1), _p(d1), len(k1), _p(k2), _p(d2), len(k2), _p(b), _p(pm), _p(m),
-                                                window, nnratio, int(check_ori))
+    f = _fn("search_for_initialization", impl)
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
+    nm = f(_p(k1), _p(d1), len(k1), _p(k2), _p(d2), len(k2), _p(b), _p(pm), _p(m), window, nnratio, int(check_ori))
     return nm, m[:len(k1)], pm
 
 
 def search_by_projection_last(kc, dc, bounds, Tcw, K, scale_factors, last_valid, last_pos, last_desc, last_octave,
-                              last_angle, th, check_ori=True, preassigned=None):
+                              last_angle, th, check_ori=True, preassigned=None, impl="oracle"):
     kc = np.ascontiguousarray(kc); dc = np.ascontiguousarray(dc, np.uint8)
     m = np.zeros(max(len(kc), 1), np.int32)
-    f = lib().oracle_search_by_projection_last
+    f = _fn("search_by_projection_last", impl)
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
     arrs = [np.asarray(bounds, np.float32), np.ascontiguousarray(Tcw, np.float32), np.asarray(K, np.float32),
@@ -312,10 +337,10 @@ def search_by_projection_last(kc, dc, bounds, Tcw, K, scale_factors, last_valid,
 
 
 def search_by_projection_points(k, d, bounds, scale_factors, in_view, proj, level, view_cos, mp_desc, th, nnratio=0.8,
-                                preassigned=None):
+                                preassigned=None, impl="oracle"):
     k = np.ascontiguousarray(k); d = np.ascontiguousarray(d, np.uint8)
     m = np.zeros(max(len(k), 1), np.int32)
-    f = lib().oracle_search_by_projection_points
+    f = _fn("search_by_projection_points", impl)
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                   C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     b = np.asarray(bounds, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
@@ -596,32 +621,35 @@ def _csr(fv):
 
 
 def search_for_triangulation(k1, d1, has_mp1, k2, d2, has_mp2, fv1, fv2, F12, Cw1, R2w, t2w, K2, scale_factors2, level_sigma2_2,
-                             check_orientation=True):
+                             check_orientation=True, impl="oracle"):
     k1 = np.ascontiguousarray(k1, KP_DTYPE); k2 = np.ascontiguousarray(k2, KP_DTYPE)
     d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
     m1 = np.ascontiguousarray(has_mp1, np.uint8); m2 = np.ascontiguousarray(has_mp2, np.uint8)
     n1a, s1, i1 = _csr(fv1); n2a, s2, i2 = _csr(fv2)
     F = _f32(F12); Cw = _f32(Cw1); R = _f32(R2w); t = _f32(t2w); K = _f32(K2); sf = _f32(scale_factors2); sg = _f32(level_sigma2_2)
     out = np.full(len(k1), -1, np.int32)
-    L = lib(); L.oracle_search_for_triangulation.restype = C.c_int
-    nm = L.oracle_search_for_triangulation(_p(k1), _p(d1), _p(m1), C.c_int(len(k1)), _p(k2), _p(d2), _p(m2), C.c_int(len(k2)),
+    f = _fn("search_for_triangulation", impl); f.restype = C.c_int
+    nm = f(_p(k1), _p(d1), _p(m1), C.c_int(len(k1)), _p(k2), _p(d2), _p(m2), C.c_int(len(k2)),
                                            _p(n1a), _p(s1), _p(i1), C.c_int(len(n1a)), _p(n2a), _p(s2), _p(i2), C.c_int(len(n2a)),
                                            _p(F), _p(Cw), _p(R), _p(t), _p(K), _p(sf), _p(sg), C.c_int(int(check_orientation)), _p(out))
     return nm, out
 
 
 def fuse_search(keys, desc, bounds, Tcw, Ow, K, scale_factors, inv_level_sigma2, log_scale_factor, skip, pos, normal, min_dist,
-                max_dist, mp_desc, th=3.0):
+                max_dist, mp_desc, th=3.0, impl="oracle"):
     keys = np.ascontiguousarray(keys, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
     b = _f32(bounds); T = _f32(Tcw); O = _f32(Ow); Kc = _f32(K); sf = _f32(scale_factors); iv = _f32(inv_level_sigma2)
     n_mp = len(pos)
     sk = None if skip is None else np.ascontiguousarray(skip, np.uint8)
     pos = _f32(pos); normal = _f32(normal); mn = _f32(min_dist); mx = _f32(max_dist); md = np.ascontiguousarray(mp_desc, np.uint8)
     bi = np.zeros(n_mp, np.int32); bd = np.zeros(n_mp, np.int32)
-    lib().oracle_fuse_search(_p(keys), _p(desc), C.c_int(len(keys)), _p(b), _p(T), _p(O), _p(Kc), _p(sf), _p(iv),
-                             C.c_float(log_scale_factor), C.c_int(len(sf)), C.c_int(n_mp), _p(sk), _p(pos), _p(normal), _p(mn), _p(mx),
-                             _p(md), C.c_float(th), _p(bi), _p(bd))
-    return bi, bd
+    args = [_p(keys), _p(desc), C.c_int(len(keys)), _p(b), _p(T), _p(O), _p(Kc), _p(sf), _p(iv), C.c_float(log_scale_factor), C.c_int(len(sf)),
+            C.c_int(n_mp), _p(sk), _p(pos), _p(normal), _p(mn), _p(mx), _p(md), C.c_float(th), _p(bi)]
+    if impl == "oracle":
+        _fn("fuse_search", impl)(*args, _p(bd))
+        return bi, bd
+    f = _fn("fuse_search", impl); f.restype = C.c_int     # ORBmatcher::Fuse itself: (chosen keypoint per map point, nFused)
+    return bi, f(*args)
 
 
 def lsd_search_for_triangulation(d1, has_ml1, d2, has_ml2, nnratio=0.8, is_double=True, th=80.0):
@@ -635,14 +663,14 @@ def lsd_search_for_triangulation(d1, has_ml1, d2, has_ml2, nnratio=0.8, is_doubl
     return nm, out
 
 
-def search_by_bow(kK, dK, has_mp_kf, kF, dF, fvK, fvF, nnratio=0.7, check_orientation=True):
+def search_by_bow(kK, dK, has_mp_kf, kF, dF, fvK, fvF, nnratio=0.7, check_orientation=True, impl="oracle"):
     """ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (ORBmatcher.cc:187-327) -> (nmatches, matchesF[nF])."""
     kK = np.ascontiguousarray(kK, KP_DTYPE); kF = np.ascontiguousarray(kF, KP_DTYPE)
     dK = np.ascontiguousarray(dK, np.uint8); dF = np.ascontiguousarray(dF, np.uint8); mp = np.ascontiguousarray(has_mp_kf, np.uint8)
     n1a, s1, i1 = _csr(fvK); n2a, s2, i2 = _csr(fvF)
     out = np.full(len(kF), -1, np.int32)
-    L = lib(); L.oracle_search_by_bow.restype = C.c_int
-    nm = L.oracle_search_by_bow(_p(kK), _p(dK), _p(mp), C.c_int(len(kK)), _p(kF), _p(dF), C.c_int(len(kF)), _p(n1a), _p(s1), _p(i1),
+    f = _fn("search_by_bow", impl); f.restype = C.c_int
+    nm = f(_p(kK), _p(dK), _p(mp), C.c_int(len(kK)), _p(kF), _p(dF), C.c_int(len(kF)), _p(n1a), _p(s1), _p(i1),
                                 C.c_int(len(n1a)), _p(n2a), _p(s2), _p(i2), C.c_int(len(n2a)), C.c_float(nnratio),
                                 C.c_int(int(check_orientation)), _p(out))
     return nm, out
@@ -685,6 +713,23 @@ def distinctive_descriptors(desc, offsets):
     best = np.zeros(len(off) - 1, np.int32)
     lib().oracle_distinctive_descriptors(_p(desc), _p(off), C.c_int(len(off) - 1), _p(best))
     return best
+
+
+def ref_distinctive_descriptors(desc, offsets):
+    """MapPoint::ComputeDistinctiveDescriptors of the reference itself -> the 32 bytes each point ends up with."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); off = np.ascontiguousarray(offsets, np.int32)
+    out = np.zeros((len(off) - 1, 32), np.uint8)
+    f = _fn("distinctive_descriptors", "ref"); f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    f(_p(desc), _p(off), len(off) - 1, _p(out))
+    return out
+
+
+def ref_predict_scale(dist, max_dist, log_scale_factor, n_levels):
+    """MapPoint::PredictScale(currentDist, pKF) of the reference itself."""
+    d = _f32(dist); mx = _f32(max_dist); out = np.zeros(len(d), np.int32)
+    f = _fn("predict_scale", "ref"); f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    f(_p(d), _p(mx), len(d), log_scale_factor, n_levels, _p(out))
+    return out
 
 
 def lsd_fuse_search(keylines, kf_point_desc, bounds, Tcw, Ow, K, scale_line, log_scale_factor_line, skip, pos, normal, min_dist, max_dist,

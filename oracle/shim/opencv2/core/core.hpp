@@ -127,6 +127,16 @@ class Mat {
   Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step; m.rows = b - a; return m; }
   Mat colRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * elemSize(); m.cols = b - a; return m; }
   Mat operator()(const Rect& r) const { return rowRange(r.y, r.y + r.height).colRange(r.x, r.x + r.width); }
+  Mat row(int y) const { return rowRange(y, y + 1); }
+  Mat col(int x) const { return colRange(x, x + 1); }
+  // element i of a vector (3x1 or 1xN), as cv::Mat::at(int) addresses it
+  template <typename T> T& at(int i) { return cols == 1 ? at<T>(i, 0) : at<T>(i / cols, i % cols); }
+  template <typename T> const T& at(int i) const { return cols == 1 ? at<T>(i, 0) : at<T>(i / cols, i % cols); }
+  double dot(const Mat& m) const {     // cv::Mat::dot on CV_32F: products and sum in fp64, row-major order
+    double s = 0;
+    for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) s += get(y, x) * m.get(y, x);
+    return s;
+  }
   Mat clone() const { Mat m; copyTo(m); return m; }
   void copyTo(Mat& m) const {
     if (empty()) { m.release(); return; }
@@ -177,23 +187,48 @@ class Mat {
   int type_;
   std::shared_ptr<uchar> buf_;
 };
-// matrix product / sum of floating-point matrices (EDLine's line fit; not on the tested paths)
+// Matrix arithmetic.  CV_32F operands compute in fp32, the product with cv::gemm's small-matrix order
+// ((a0*b0 + a1*b1) + a2*b2, separately rounded; then "+ c" as its own rounding) - the order the oracle's gemm3 restates and
+// tests/golden/frame_cv2.npz pins against cv2; other depths (EDLine's line fit, never on the tested paths) go through double.
 inline Mat operator*(const Mat& a, const Mat& b) {
   Mat m(a.rows, b.cols, a.type());
-  for (int y = 0; y < a.rows; y++) for (int x = 0; x < b.cols; x++) { double s = 0; for (int k = 0; k < a.cols; k++) s += a.get(y, k) * b.get(k, x); m.put(y, x, s); }
+  const bool f32 = a.depth() == CV_32F && b.depth() == CV_32F;
+  for (int y = 0; y < a.rows; y++) for (int x = 0; x < b.cols; x++) {
+    if (f32) { float s = a.at<float>(y, 0) * b.at<float>(0, x); for (int k = 1; k < a.cols; k++) s = s + a.at<float>(y, k) * b.at<float>(k, x); m.at<float>(y, x) = s; }
+    else { double s = 0; for (int k = 0; k < a.cols; k++) s += a.get(y, k) * b.get(k, x); m.put(y, x, s); }
+  }
   return m;
 }
-inline Mat operator+(const Mat& a, const Mat& b) {
+#define PL_SHIM_ELEMWISE(NAME, EXPRF, EXPRD)                                                            \
+  inline Mat NAME(const Mat& a, const Mat& b) {                                                         \
+    Mat m(a.rows, a.cols, a.type());                                                                    \
+    const bool f32 = a.depth() == CV_32F && b.depth() == CV_32F;                                        \
+    for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) {                                 \
+      if (f32) { const float p = a.at<float>(y, x), q = b.at<float>(y, x); m.at<float>(y, x) = EXPRF; } \
+      else { const double p = a.get(y, x), q = b.get(y, x); m.put(y, x, EXPRD); }                       \
+    }                                                                                                   \
+    return m;                                                                                           \
+  }
+PL_SHIM_ELEMWISE(operator+, p + q, p + q)
+PL_SHIM_ELEMWISE(operator-, p - q, p - q)
+#undef PL_SHIM_ELEMWISE
+// scaling: cv evaluates  alpha * M  through convertTo; for CV_32F the work type is float (cvtScale_<float, float, float>): v * (float)alpha
+inline Mat operator*(double s, const Mat& a) {
   Mat m(a.rows, a.cols, a.type());
-  for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) m.put(y, x, a.get(y, x) + b.get(y, x));
+  for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) {
+    if (a.depth() == CV_32F) m.at<float>(y, x) = a.at<float>(y, x) * (float)s; else m.put(y, x, a.get(y, x) * s);
+  }
   return m;
+}
+inline Mat operator*(const Mat& a, double s) { return s * a; }
+inline Mat operator-(const Mat& a) { return -1.0 * a; }
+inline double norm(const Mat& a) {      // NORM_L2: squares and sum in fp64
+  double s = 0;
+  for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) { const double v = a.get(y, x); s += v * v; }
+  return std::sqrt(s);
 }
 
-inline Mat operator/(const Mat& a, double d) {
-  Mat m(a.rows, a.cols, a.type());
-  for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) m.put(y, x, a.get(y, x) / d);
-  return m;
-}
+inline Mat operator/(const Mat& a, double d) { return (1.0 / d) * a; }     // cv: M / s is M * (1 / s)
 
 template <typename T> struct DataDepth;
 template <> struct DataDepth<uchar> { enum { value = CV_8U }; };

@@ -359,19 +359,19 @@ def bf_knn2(d1, d2):
     return idx[:len(d1)], dist[:len(d1)]
 
 
-def frame_bf_match(d1, d2, th=50.0, nnratio=0.7):
+def frame_bf_match(d1, d2, th=50.0, nnratio=0.7, impl="oracle"):
     d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
     m = np.zeros(max(len(d1), 1), np.int32)
-    f = lib().oracle_frame_bf_match
+    f = _fn("frame_bf_match", impl)
     f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
     f(_p(d1), len(d1), _p(d2), len(d2), th, nnratio, _p(m))
     return m[:len(d1)]
 
 
-def search_double(d1, d2, nnratio=0.7):
+def search_double(d1, d2, nnratio=0.7, impl="oracle"):
     d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
     m = np.zeros(max(len(d1), 1), np.int32)
-    f = lib().oracle_search_double
+    f = _fn("search_double", impl)
     f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p]
     nm = f(_p(d1), len(d1), _p(d2), len(d2), nnratio, _p(m))
     return nm, m[:len(d1)]
@@ -514,9 +514,9 @@ def assign_grid_lines(kl68, bounds):
     return start, items[:n]
 
 
-def line_search_by_projection_last(kl68, lfunc, desc, bounds, last_valid, proj, last_desc, last_length, th, preassigned=None):
+def line_search_by_projection_last(kl68, lfunc, desc, bounds, last_valid, proj, last_desc, last_length, th, preassigned=None, impl="oracle"):
     k = _compact_kl(kl68); m = np.zeros(max(len(k), 1), np.int32)
-    f = lib().oracle_line_search_by_projection_last
+    f = _fn("line_search_by_projection_last", impl)
     f.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_float, C.c_void_p, C.c_void_p]
     a = [np.ascontiguousarray(lfunc, np.float64), np.ascontiguousarray(desc, np.uint8), np.asarray(bounds, np.float32),
          np.ascontiguousarray(last_valid, np.uint8), np.ascontiguousarray(proj, np.float32), np.ascontiguousarray(last_desc, np.uint8),
@@ -526,9 +526,9 @@ def line_search_by_projection_last(kl68, lfunc, desc, bounds, last_valid, proj, 
     return nm, m[:len(k)]
 
 
-def line_search_by_projection_lines(kl68, lfunc, desc, bounds, in_view, proj, view_cos, ml_desc, th, nnratio=0.7, preassigned=None):
+def line_search_by_projection_lines(kl68, lfunc, desc, bounds, in_view, proj, view_cos, ml_desc, th, nnratio=0.7, preassigned=None, impl="oracle"):
     k = _compact_kl(kl68); m = np.zeros(max(len(k), 1), np.int32)
-    f = lib().oracle_line_search_by_projection_lines
+    f = _fn("line_search_by_projection_lines", impl)
     f.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     a = [np.ascontiguousarray(lfunc, np.float64), np.ascontiguousarray(desc, np.uint8), np.asarray(bounds, np.float32),
          np.ascontiguousarray(in_view, np.uint8), np.ascontiguousarray(proj, np.float32), np.ascontiguousarray(view_cos, np.float32),
@@ -652,14 +652,13 @@ def fuse_search(keys, desc, bounds, Tcw, Ow, K, scale_factors, inv_level_sigma2,
     return bi, f(*args)
 
 
-def lsd_search_for_triangulation(d1, has_ml1, d2, has_ml2, nnratio=0.8, is_double=True, th=80.0):
+def lsd_search_for_triangulation(d1, has_ml1, d2, has_ml2, nnratio=0.8, is_double=True, th=80.0, impl="oracle"):
     """LSDmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, isDouble) (LSDmatcher.cpp:727-776)."""
     d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
     m1 = np.ascontiguousarray(has_ml1, np.uint8); m2 = np.ascontiguousarray(has_ml2, np.uint8)
     out = np.full(len(d1), -1, np.int32)
-    L = lib(); L.oracle_lsd_search_for_triangulation.restype = C.c_int
-    nm = L.oracle_lsd_search_for_triangulation(_p(d1), _p(m1), C.c_int(len(d1)), _p(d2), _p(m2), C.c_int(len(d2)),
-                                               C.c_float(th), C.c_float(nnratio), C.c_int(int(is_double)), _p(out))
+    f = _fn("lsd_search_for_triangulation", impl); f.restype = C.c_int
+    nm = f(_p(d1), _p(m1), C.c_int(len(d1)), _p(d2), _p(m2), C.c_int(len(d2)), C.c_float(th), C.c_float(nnratio), C.c_int(int(is_double)), _p(out))
     return nm, out
 
 
@@ -733,14 +732,21 @@ def ref_predict_scale(dist, max_dist, log_scale_factor, n_levels):
 
 
 def lsd_fuse_search(keylines, kf_point_desc, bounds, Tcw, Ow, K, scale_line, log_scale_factor_line, skip, pos, normal, min_dist, max_dist,
-                    ml_desc, th=3.0):
-    """Search half of LSDmatcher::Fuse (LSDmatcher.cpp:860-1011) -> (best_idx, best_dist, stop_at)."""
+                    ml_desc, th=3.0, impl="oracle"):
+    """Search half of LSDmatcher::Fuse (LSDmatcher.cpp:860-1011) -> (best_idx, best_dist, stop_at);
+    impl="ref": LSDmatcher::Fuse itself -> (chosen keyline per map line, Fuse's return value)."""
     kl = np.ascontiguousarray(keylines); pd = np.ascontiguousarray(kf_point_desc, np.uint8).reshape(-1, 32)
     b = _f32(bounds); T = _f32(Tcw); O = _f32(Ow); Kc = _f32(K)
     n = len(pos)
     sk = np.ascontiguousarray(skip, np.uint8); P = np.ascontiguousarray(pos, np.float64); Nn = np.ascontiguousarray(normal, np.float64)
     mn = _f32(min_dist); mx = _f32(max_dist); md = np.ascontiguousarray(ml_desc, np.uint8).reshape(-1, 32)
     bi = np.zeros(n, np.int32); bd = np.zeros(n, np.int32); stop = C.c_int(n)
+    if impl == "ref":
+        ret = C.c_int(0)
+        _fn("lsd_fuse_search", "ref")(_p(kl), C.c_int(len(kl)), _p(pd), C.c_int(len(pd)), _p(b), _p(T), _p(O), _p(Kc), C.c_float(scale_line), C.c_int(1),
+                                      C.c_float(log_scale_factor_line), C.c_int(n), _p(sk), _p(P), _p(Nn), _p(mn), _p(mx), _p(md), C.c_float(th),
+                                      _p(bi), C.byref(ret))
+        return bi, ret.value
     lib().oracle_lsd_fuse_search(_p(kl), C.c_int(len(kl)), _p(pd), C.c_int(len(pd)), _p(b), _p(T), _p(O), _p(Kc), C.c_float(scale_line), C.c_int(1),
                                  C.c_float(log_scale_factor_line), C.c_int(n), _p(sk), _p(P), _p(Nn), _p(mn), _p(mx), _p(md), C.c_float(th),
                                  _p(bi), _p(bd), C.byref(stop))

@@ -132,6 +132,30 @@ class Mat {
   // element i of a vector (3x1 or 1xN), as cv::Mat::at(int) addresses it
   template <typename T> T& at(int i) { return cols == 1 ? at<T>(i, 0) : at<T>(i / cols, i % cols); }
   template <typename T> const T& at(int i) const { return cols == 1 ? at<T>(i, 0) : at<T>(i / cols, i % cols); }
+  Mat inv() const {                     // small dense inverse (Gauss-Jordan in fp64); LSDmatcher::ComputeF12 only, not on the tested paths
+    const int n = rows;
+    std::vector<double> a((size_t)n * 2 * n, 0.0);
+    for (int y = 0; y < n; y++) { for (int x = 0; x < n; x++) a[(size_t)y * 2 * n + x] = get(y, x); a[(size_t)y * 2 * n + n + y] = 1.0; }
+    for (int c = 0; c < n; c++) {
+      int piv = c;
+      for (int y = c + 1; y < n; y++) if (std::fabs(a[(size_t)y * 2 * n + c]) > std::fabs(a[(size_t)piv * 2 * n + c])) piv = y;
+      for (int x = 0; x < 2 * n; x++) std::swap(a[(size_t)c * 2 * n + x], a[(size_t)piv * 2 * n + x]);
+      const double d = a[(size_t)c * 2 * n + c];
+      for (int x = 0; x < 2 * n; x++) a[(size_t)c * 2 * n + x] /= d;
+      for (int y = 0; y < n; y++) if (y != c) { const double f = a[(size_t)y * 2 * n + c]; for (int x = 0; x < 2 * n; x++) a[(size_t)y * 2 * n + x] -= f * a[(size_t)c * 2 * n + x]; }
+    }
+    Mat m(n, n, type_);
+    for (int y = 0; y < n; y++) for (int x = 0; x < n; x++) m.put(y, x, a[(size_t)y * 2 * n + n + x]);
+    return m;
+  }
+  Mat cross(const Mat& b) const {
+    Mat m(rows, cols, type_);
+    const double a0 = get(0, 0), a1 = cols == 1 ? get(1, 0) : get(0, 1), a2 = cols == 1 ? get(2, 0) : get(0, 2);
+    const double b0 = b.get(0, 0), b1 = b.cols == 1 ? b.get(1, 0) : b.get(0, 1), b2 = b.cols == 1 ? b.get(2, 0) : b.get(0, 2);
+    const double c[3] = {a1 * b2 - a2 * b1, a2 * b0 - a0 * b2, a0 * b1 - a1 * b0};
+    for (int i = 0; i < 3; i++) { if (cols == 1) m.put(i, 0, c[i]); else m.put(0, i, c[i]); }
+    return m;
+  }
   double dot(const Mat& m) const {     // cv::Mat::dot on CV_32F: products and sum in fp64, row-major order
     double s = 0;
     for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) s += get(y, x) * m.get(y, x);
@@ -229,6 +253,7 @@ inline double norm(const Mat& a) {      // NORM_L2: squares and sum in fp64
 }
 
 inline Mat operator/(const Mat& a, double d) { return (1.0 / d) * a; }     // cv: M / s is M * (1 / s)
+inline Mat& operator/=(Mat& a, double d) { Mat m = a / d; m.copyTo(a); return a; }
 
 template <typename T> struct DataDepth;
 template <> struct DataDepth<uchar> { enum { value = CV_8U }; };
@@ -249,6 +274,16 @@ template <typename T> class Mat_ : public Mat {
   T* operator[](int y) { return (T*)(data + (size_t)y * step); }
   const T* operator[](int y) const { return (const T*)(data + (size_t)y * step); }
 };
+// (Mat_<float>(3, 1) << a, b, c): row-major fill
+template <typename T> struct MatCommaInitializer_ {
+  Mat_<T> m; int i;
+  MatCommaInitializer_(const Mat_<T>& m_, T v) : m(m_), i(0) { put(v); }
+  void put(T v) { m[i / m.cols][i % m.cols] = v; i++; }
+  template <typename S> MatCommaInitializer_& operator,(S v) { put((T)v); return *this; }
+  operator Mat() const { return m; }
+  operator Mat_<T>() const { return m; }
+};
+template <typename T, typename S> MatCommaInitializer_<T> operator<<(const Mat_<T>& m, S v) { return MatCommaInitializer_<T>(m, (T)v); }
 
 // InputArray / OutputArray: a view of the caller's Mat
 class _InputArray {
@@ -301,6 +336,17 @@ Ptr<LineSegmentDetector> createLineSegmentDetector(int refine = 1, double scale 
                                                    double log_eps = 0, double density_th = 0.7, int n_bins = 1024);
 // cv::LineIterator(img, p1, p2): only .count is used (LSDDetector_custom.cpp:184): 8-connected, end points rounded half-to-even
 class LineIterator { public: LineIterator(const Mat& img, Point2f p1, Point2f p2); int count; };
+
+// k-nearest-neighbour matching of binary descriptors (implemented in oracle/ref_lsd_wrap.cpp on the oracle's cv2-pinned bf_knn2)
+class BFMatcher {
+ public:
+  BFMatcher(int normType = NORM_HAMMING, bool crossCheck = false) { if (normType != NORM_HAMMING || crossCheck) abort(); }
+  void knnMatch(const Mat& query, const Mat& train, std::vector<std::vector<DMatch>>& matches, int k) const;
+};
+// debug drawing inside the reference's matchers: no-ops
+#define CV_AA 16
+inline void line(Mat&, Point, Point, const Scalar&, int = 1, int = 8, int = 0) {}
+inline bool imwrite(const String&, const Mat&) { return true; }
 
 // element-wise helpers of EDLine's edge drawing (binary_descriptor_custom.cpp:1484-1492; not on the tested paths)
 inline Mat abs(const Mat& a) { Mat m(a.rows, a.cols, a.type()); for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) m.put(y, x, std::fabs(a.get(y, x))); return m; }

@@ -15,8 +15,12 @@
 #include <mutex>
 #include <set>
 #include <vector>
+#include <list>
+#include <unordered_set>
 #include "Thirdparty/DBoW2/DBoW2/BowVector.h"
 #include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
+#include "auxiliar.h"        // the reference's own (sort predicates, vector_mad, KeyLine via the line_descriptor header, Vector6d)
+#include "lineIterator.h"    // the reference's own (src/lineIterator.cpp is compiled with the matchers)
 
 using namespace std;    // the reference's Frame.h leaks these two (through LineExtractor.h:16-17); ORBmatcher.h and MapPoint.cc rely on it
 using namespace cv;
@@ -25,6 +29,7 @@ namespace ORB_SLAM2 {
 #define FRAME_GRID_ROWS 48
 #define FRAME_GRID_COLS 64
 class MapPoint;
+class MapLine;
 class KeyFrame;
 class Frame;
 
@@ -94,6 +99,116 @@ class GridView {
     return vIndices;
   }
   bool IsInImage(const float& x, const float& y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }   // KeyFrame.cc:760
+
+  // ---- lines (LSDmatcher.cpp)
+  int NL = 0;
+  std::vector<KeyLine> mvKeyLines, mvKeylinesUn;
+  std::vector<Eigen::Vector3d> mvKeyLineFunctions;
+  cv::Mat mLdesc, mLineDescriptors;                 // Frame names it mLdesc, KeyFrame mLineDescriptors: both kept in step
+  std::vector<MapLine*> mvpMapLines;
+  cv::Mat mK, ImageGray;
+  float mfLogScaleFactorLine = 0.f;
+  // mvScaleFactorsLine[level]: the reference indexes this vector with an UNCLAMPED predicted level (LSDmatcher.cpp:944), out of
+  // range for every level outside [0, octaves): read here as scale^level, the rule the table is built with (LineExtractor.cpp:7-14)
+  struct ScaleTable { float scale = 1.2f; float operator[](int level) const { return powf(scale, (float)level); } } mvScaleFactorsLine;
+  std::vector<std::size_t> mGridForLine[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+  void AssignFeaturesToGridForLine() {                                        // Frame.cc:296-320, with the reference's LineIterator
+    for (int i = 0; i < FRAME_GRID_COLS; i++) for (int j = 0; j < FRAME_GRID_ROWS; j++) mGridForLine[i][j].clear();
+    for (int i = 0; i < NL; i++) {
+      const KeyLine& kl = mvKeylinesUn[i];
+      LineIterator it(kl.startPointX * mfGridElementWidthInv, kl.startPointY * mfGridElementHeightInv, kl.endPointX * mfGridElementWidthInv,
+                      kl.endPointY * mfGridElementHeightInv);
+      std::pair<int, int> p;
+      while (it.getNext(p))
+        if (p.first >= 0 && p.first < FRAME_GRID_COLS && p.second >= 0 && p.second < FRAME_GRID_ROWS) mGridForLine[p.first][p.second].push_back(i);
+    }
+  }
+  std::vector<std::size_t> GetFeaturesInAreaForLine(const float& x1, const float& y1, const float& x2, const float& y2, const float& r,
+                                                    const int minLevel = -1, const int maxLevel = -1, const float TH = 0.998) const {
+    std::vector<std::size_t> vIndices;                                        // Frame.cc:768-842
+    vIndices.reserve(NL);
+    std::unordered_set<std::size_t> vIndices_set;
+    float x[3] = {x1, (float)((x1 + x2) / 2.0), x2};
+    float y[3] = {y1, (float)((y1 + y2) / 2.0), y2};
+    float delta1x = x1 - x2, delta1y = y1 - y2;
+    float norm_delta1 = sqrt(delta1x * delta1x + delta1y * delta1y);
+    delta1x /= norm_delta1; delta1y /= norm_delta1;
+    for (int i = 0; i < 3; i++) {
+      const int nMinCellX = std::max(0, (int)floor((x[i] - mnMinX - r) * mfGridElementWidthInv));
+      if (nMinCellX >= FRAME_GRID_COLS) continue;
+      const int nMaxCellX = std::min((int)FRAME_GRID_COLS - 1, (int)ceil((x[i] - mnMinX + r) * mfGridElementWidthInv));
+      if (nMaxCellX < 0) continue;
+      const int nMinCellY = std::max(0, (int)floor((y[i] - mnMinY - r) * mfGridElementHeightInv));
+      if (nMinCellY >= FRAME_GRID_ROWS) continue;
+      const int nMaxCellY = std::min((int)FRAME_GRID_ROWS - 1, (int)ceil((y[i] - mnMinY + r) * mfGridElementHeightInv));
+      if (nMaxCellY < 0) continue;
+      for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+          const std::vector<std::size_t>& vCell = mGridForLine[ix][iy];
+          for (std::size_t j = 0, jend = vCell.size(); j < jend; j++) {
+            if (vIndices_set.find(vCell[j]) != vIndices_set.end()) continue;
+            const KeyLine& klUn = mvKeylinesUn[vCell[j]];
+            float delta2x = klUn.startPointX - klUn.endPointX, delta2y = klUn.startPointY - klUn.endPointY;
+            float norm_delta2 = sqrt(delta2x * delta2x + delta2y * delta2y);
+            delta2x /= norm_delta2; delta2y /= norm_delta2;
+            float CosSita = abs(delta1x * delta2x + delta1y * delta2y);
+            if (CosSita < TH) continue;
+            Eigen::Vector3d Lfunc = mvKeyLineFunctions[vCell[j]];
+            const float dist = Lfunc(0) * x[i] + Lfunc(1) * y[i] + Lfunc(2);
+            if (fabs(dist) < r) { vIndices.push_back(vCell[j]); vIndices_set.insert(vCell[j]); }
+          }
+        }
+    }
+    return vIndices;
+  }
+  std::vector<std::size_t> GetLinesInArea(const float& x1, const float& y1, const float& x2, const float& y2, const float& r, const float TH = 0.998) const {
+    std::vector<std::size_t> vIndices;                                        // KeyFrame.cc:647-682
+    float delta1x = x1 - x2, delta1y = y1 - y2;
+    float norm_delta1 = sqrt(delta1x * delta1x + delta1y * delta1y);
+    delta1x /= norm_delta1; delta1y /= norm_delta1;
+    for (std::size_t i = 0; i < mvKeyLines.size(); i++) {
+      const KeyLine& keyline = mvKeyLines[i];
+      float distance = (0.5 * (x1 + x2) - keyline.pt.x) * (0.5 * (x1 + x2) - keyline.pt.x) + (0.5 * (y1 + y2) - keyline.pt.y) * (0.5 * (y1 + y2) - keyline.pt.y);
+      if (distance > r * r) continue;
+      float delta2x = keyline.startPointX - keyline.endPointX, delta2y = keyline.startPointY - keyline.endPointY;
+      float norm_delta2 = sqrt(delta2x * delta2x + delta2y * delta2y);
+      delta2x /= norm_delta2; delta2y /= norm_delta2;
+      float CosSita = abs(delta1x * delta2x + delta1y * delta2y);
+      if (CosSita < TH) continue;
+      vIndices.push_back(i);
+    }
+    return vIndices;
+  }
+  MapLine* GetMapLine(const std::size_t& idx) { return mvpMapLines[idx]; }
+  void AddMapLine(MapLine* pML, const std::size_t& idx) { mvpMapLines[idx] = pML; }
+};
+
+// MapLine: plain data + the few rules of MapLine.cpp the matcher relies on (restated: MapLine.cpp needs Eigen proper)
+class MapLine {
+ public:
+  Vector6d mWorldPos; Eigen::Vector3d mNormalVector;
+  cv::Mat mLDescriptor;
+  float mfMinDistance = 0, mfMaxDistance = 0;
+  bool mbBad = false, mbTrackInView = false, mbInFrustum = true;
+  int nObs = 0, mnTrackScaleLevel = 0;
+  float mTrackViewCos = 1.f, mTrackProjX1 = 0, mTrackProjY1 = 0, mTrackProjX2 = 0, mTrackProjY2 = 0;
+  std::map<KeyFrame*, std::size_t> mObservations;
+  MapLine* mpReplaced = nullptr;
+  Vector6d GetWorldPos() { return mWorldPos; }
+  Eigen::Vector3d GetNormal() { return mNormalVector; }
+  cv::Mat GetDescriptor() { return mLDescriptor.clone(); }
+  bool isBad() { return mbBad; }
+  int Observations() { return nObs; }
+  bool IsInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) != 0; }
+  int GetIndexInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) ? (int)mObservations[pKF] : -1; }
+  float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }            // MapLine.cpp:383-393
+  float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
+  int PredictScale(const float& currentDist, const float& logScaleFactor) {    // MapLine.cpp:395-404 (no clamping)
+    float ratio = mfMaxDistance / currentDist;
+    return ceil(log(ratio) / logScaleFactor);
+  }
+  void AddObservation(KeyFrame* pKF, std::size_t idx) { if (mObservations.count(pKF)) return; mObservations[pKF] = idx; nObs++; }
+  void Replace(MapLine* pML) { if (pML == this) return; mbBad = true; mpReplaced = pML; }
 };
 
 class Frame : public GridView {
@@ -101,8 +216,13 @@ class Frame : public GridView {
   long unsigned int mnId = 0;
   cv::Mat mTcw, mOw;
   std::vector<MapPoint*> mvpMapPoints;
-  std::vector<bool> mvbOutlier;
+  std::vector<bool> mvbOutlier, mvbLineOutlier;
   cv::Mat GetCameraCenter() { return mOw.clone(); }
+  // Frame::isInFrustum(MapLine*, viewingCosLimit) (Frame.cc:628-702) belongs to the frame glue (cv2-pinned projection, tests of
+  // oracle_frame); here the wrapper has stored its outcome (flag + mTrackProj*) on the map line
+  bool isInFrustum(MapLine* pML, float) const;
+  // only LSDmatcher::SerachForInitialize (LSDmatcher.cpp:340-373) calls this; no caller of that function exists in the reference
+  void lineDescriptorMAD(std::vector<std::vector<cv::DMatch>>, double&, double&) const { abort(); }
 };
 
 class KeyFrame : public GridView {
@@ -125,5 +245,7 @@ class KeyFrame : public GridView {
   void ReplaceMapPointMatch(const std::size_t& idx, MapPoint* pMP) { calls.push_back({1, mvpMapPoints[idx], pMP, idx}); mvpMapPoints[idx] = pMP; }
   bool isBad() { return mbBad; }
 };
+
+inline bool Frame::isInFrustum(MapLine* pML, float) const { return pML->mbInFrustum; }
 
 }  // namespace ORB_SLAM2

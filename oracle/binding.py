@@ -87,6 +87,20 @@ def ref_lsd_keylines(img, mask=None, scale=1, num_octaves=1):
     return kl[:n].copy()
 
 
+def ref_line_extract(img, mask=None, nfeatures=200, min_line_length=0.0):
+    """LINEextractor::operator() of the reference itself (src/LineExtractor.cpp) -> (keylines, descriptors, line functions).
+    Only for frames with more lines than nfeatures (see oracle/ref_line_wrap.cpp)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = nfeatures + 2
+    kl = np.zeros(cap, KEYLINE_DTYPE); desc = np.zeros((cap, 32), np.uint8); lf = np.zeros((cap, 3), np.float64)
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    f = ref_line_lib().ref_line_extract
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    n = f(_p(img), img.shape[1], img.shape[0], _p(m), nfeatures, float(min_line_length), _p(kl), _p(desc), _p(lf), cap)
+    assert n >= 0, n
+    return kl[:n].copy(), desc[:n].copy(), lf[:n].copy()
+
+
 def ref_lbd_compute(img, keylines, want_float=False):
     """BinaryDescriptor::compute(image, keylines, descriptors) of the reference tree itself (class_id must index the lines)."""
     img = np.ascontiguousarray(img, np.uint8); kl = np.ascontiguousarray(keylines)

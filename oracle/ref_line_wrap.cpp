@@ -10,12 +10,15 @@
 // primitives behind it on the oracle's restatements (liboracle.so), pinned bit for bit to cv2 4.13: GaussianBlur 5x5 sigma 1,
 // Sobel 3x3 8U -> 16S, the full LineSegmentDetector (ordered segment lists, tests/golden/lsd_cv2_*.npz).
 //
-// What this pins: the LBD band arithmetic, weights, normalisation and binary conversion, and the KeyLine record construction,
-// are the reference tree's own code.  Not pinned here: the OpenCV primitives (pinned to cv2 separately) and LineExtractor.cpp's
-// 30 lines of sort / truncate / line equation (it needs Eigen and the contrib header; restated in oracle_line.cpp).
+//   /root/reference/src/LineExtractor.cpp                                          LINEextractor::operator()  (§8 a9)
+// What this pins: the LBD band arithmetic, weights, normalisation and binary conversion, the KeyLine record construction, and
+// LINEextractor's sort / nfeatures(+1) truncation / class ids / line equations are the reference tree's own code (the contrib
+// header name and the three Eigen operations LineExtractor.cpp uses come from oracle/shim/).  Not pinned here: the OpenCV
+// primitives (pinned to cv2 separately).
 #include <opencv2/core/core.hpp>
 #include <cstdint>
 #include "line_descriptor_custom.hpp"   // /root/reference/Thirdparty/line_descriptor/include (-I on the command line)
+#include "LineExtractor.h"              // /root/reference/include: the reference's LINEextractor (src/LineExtractor.cpp is compiled too)
 
 extern "C" {   // liboracle.so
 void oracle_blur_u8(const uint8_t* src, int w, int h, uint8_t* dst, int ksize);
@@ -98,6 +101,23 @@ int ref_lsd_keylines(const uint8_t* img, int w, int h, const uint8_t* mask, int 
   lsd->detect(image, kls, scale, num_octaves, m);
   const int n = (int)kls.size();
   memcpy(keylines_out, kls.data(), sizeof(KeyLine) * (size_t)std::min(n, cap));
+  return n;
+}
+// LINEextractor(1, 1.2f, nfeatures, min_line_length)(image, mask, keylines, descriptors, lineVec2d); returns the KeyLine count.
+// Only defined for frames with MORE lines than nfeatures: otherwise the reference appends a default-constructed (uninitialised)
+// KeyLine and describes it (LineExtractor.cpp:64), which is not reproducible.
+int ref_line_extract(const uint8_t* img, int w, int h, const uint8_t* mask, int nfeatures, double min_line_length, void* keylines_out,
+                     uint8_t* desc_out, double* linefunc_out, int cap) {
+  cv::Mat image(h, w, CV_8UC1, const_cast<uint8_t*>(img)), m, d;
+  if (mask) m = cv::Mat(h, w, CV_8UC1, const_cast<uint8_t*>(mask));
+  std::vector<KeyLine> kls;
+  std::vector<Eigen::Vector3d> lf;
+  ORB_SLAM2::LINEextractor ex(1, 1.2f, (unsigned)nfeatures, min_line_length);
+  ex(image, m, kls, d, lf);
+  const int n = (int)kls.size();
+  if (n > cap || d.rows != n || (int)lf.size() != n) return -1;
+  memcpy(keylines_out, kls.data(), sizeof(KeyLine) * (size_t)n);
+  for (int i = 0; i < n; i++) { memcpy(desc_out + 32 * (size_t)i, d.ptr(i), 32); for (int j = 0; j < 3; j++) linefunc_out[3 * i + j] = lf[i](j); }
   return n;
 }
 // BinaryDescriptor::createBinaryDescriptor()->compute(image, keylines, descriptors[, returnFloatDescr]).

@@ -87,3 +87,26 @@ def test_lbd_on_short_and_border_lines():
     rd, rv = oracle.ref_lbd_compute(img, sel, want_float=True)
     od, ov = oracle.lbd_compute(img, sel, want_float=True)
     assert np.array_equal(od, rd) and ov.tobytes() == rv.tobytes()
+
+
+@needs_ref
+@pytest.mark.parametrize("w,h,seed,nf,mll", [(640, 480, 1, 200, 0.0), (640, 480, 2, 200, 0.0), (752, 480, 5, 300, 0.0), (1241, 376, 4, 200, 0.0),
+                                             (640, 480, 3, 150, 20.0), (640, 480, 6, 400, 30.0), (320, 240, 3, 100, 0.0)])
+def test_line_extractor_equals_live_reference(w, h, seed, nf, mll):
+    """LINEextractor::operator() end to end: the reference's own LineExtractor.cpp (sort by response, the nfeatures + 1 truncation,
+    the min_line_length cut, class ids, line equations through Eigen's cross product) over its own detector and descriptor."""
+    img = synth.synth_frame(w, h, seed)
+    ok, od, ol = oracle.line_extract(img, nfeatures=nf, min_line_length=mll)
+    rk, rd, rl = oracle.ref_line_extract(img, nfeatures=nf, min_line_length=mll)
+    assert len(ok) == len(rk) > 50
+    assert ok.tobytes() == rk.tobytes() and np.array_equal(od, rd)
+    assert ol.tobytes() == rl.tobytes()          # the three fp64 coefficients of every line equation, bit for bit
+
+
+@needs_ref
+def test_line_extractor_with_mask_equals_live_reference():
+    img = synth.synth_frame(640, 480, 4)
+    mask = np.zeros((480, 640), np.uint8); mask[14:465, 14:625] = 255        # the geometry of masks/mask.png
+    ok, od, ol = oracle.line_extract(img, mask=mask, nfeatures=200)
+    rk, rd, rl = oracle.ref_line_extract(img, mask=mask, nfeatures=200)
+    assert ok.tobytes() == rk.tobytes() and np.array_equal(od, rd) and ol.tobytes() == rl.tobytes()

@@ -15,6 +15,7 @@
 // A different keyframe's LBA is an independent problem ("replicas only" across GPUs).
 
 #include "common.cuh"
+#include <mutex>
 #include "se3.cuh"
 #include <vector>
 #include <algorithm>
@@ -492,36 +493,55 @@ extern "C" int pl_local_ba(const PLBAProblem* p, const int* stop_flag_dev, float
   int n_free = 0;
   for (int k = 0; k < n_kf; k++) n_free += !p->kf_fixed[k];
   const size_t n = (size_t)n_free * 6;
-  std::vector<void*> frees;
-  bool fail = false;
-  auto dalloc = [&](size_t bytes) -> void* { void* d = nullptr; if (cudaMalloc(&d, std::max<size_t>(bytes, 16)) != cudaSuccess) { fail = true; return nullptr; } frees.push_back(d); return d; };
-  auto up = [&](const void* h, size_t bytes) -> void* { void* d = dalloc(bytes); if (d && h && bytes) cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice); return d; };
+  // Device workspace: ONE cached block per process, sub-allocated by a bump pointer (57 cudaMalloc + cudaFree pairs per call cost 2 ms
+  // in a fresh process and over 100 ms inside a process that holds tens of GB of other allocations: cudaFree synchronises and unmaps).
+  // Calls are serialised by the mutex (the reference runs one LocalMapping thread); the block only grows.
+  static std::mutex ws_mu;
+  static char* ws_base = nullptr; static size_t ws_cap = 0; static int ws_dev = -1;
+  std::lock_guard<std::mutex> ws_lock(ws_mu);
+  int dev = 0; cudaGetDevice(&dev);
+  bool fail = false, dry = true;
+  size_t off = 0;
+  auto dalloc = [&](size_t bytes) -> void* { void* d = dry ? nullptr : (void*)(ws_base + off); off += (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255; return d; };
+  auto up = [&](const void* h, size_t bytes) -> void* { void* d = dalloc(bytes); if (!dry && h && bytes && cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice) != cudaSuccess) fail = true; return d; };
   BAArgs A;
-  A.n_kf = n_kf; A.n_pt = n_pt; A.n_ln = n_ln; A.n_pe = n_pe; A.n_le = n_le;
-  A.kf_Tcw = (const float*)up(p->kf_Tcw, 64 * (size_t)n_kf); A.kf_fixed = (const uint8_t*)up(p->kf_fixed, n_kf);
-  A.kf_K = (const float*)up(p->kf_K, 16 * (size_t)n_kf);
-  for (int i = 0; i < 4; i++) A.K_end[i] = p->K_end[i];
-  A.pt_Xw = (const float*)up(p->pt_Xw, 12 * (size_t)n_pt); A.ln_Xw = (const double*)up(p->ln_Xw, 48 * (size_t)n_ln);
-  A.pe_kf = (const int*)up(p->pe_kf, 4 * (size_t)n_pe); A.pe_pt = (const int*)up(p->pe_pt, 4 * (size_t)n_pe);
-  A.pe_obs = (const float*)up(p->pe_obs, 8 * (size_t)n_pe); A.pe_w = (const float*)up(p->pe_inv_sigma2, 4 * (size_t)n_pe);
-  A.le_kf = (const int*)up(p->le_kf, 4 * (size_t)n_le); A.le_ln = (const int*)up(p->le_ln, 4 * (size_t)n_le);
-  A.le_f = (const double*)up(p->le_func, 24 * (size_t)n_le);
-  A.lm_start = (const int*)up(lm_start.data(), 4 * (size_t)(n_lm + 1)); A.lm_edges = (const int*)up(lm_edges.data(), 4 * (size_t)std::max(n_edges, 1));
-  A.kf_start = (const int*)up(kf_start.data(), 4 * (size_t)(n_kf + 1)); A.kf_edges = (const int*)up(kf_edges.data(), 4 * (size_t)std::max(n_edges, 1));
-  A.stop = stop_flag_dev;
-  A.kf_Tcw_out = (float*)dalloc(64 * (size_t)n_kf); A.pt_Xw_out = (float*)dalloc(12 * (size_t)n_pt); A.ln_Xw_out = (double*)dalloc(48 * (size_t)n_ln);
-  A.pe_erase = (uint8_t*)dalloc(n_pe); A.le_erase = (uint8_t*)dalloc(n_le); A.le_erase_kf = (int*)dalloc(4 * (size_t)n_le); A.iterations = (int*)dalloc(4);
-  A.T = (SE3*)dalloc(sizeof(SE3) * n_kf); A.Tb = (SE3*)dalloc(sizeof(SE3) * n_kf);
-  A.Tp = (SE3*)dalloc(sizeof(SE3) * n_kf * 6); A.Tm = (SE3*)dalloc(sizeof(SE3) * n_kf * 6);
-  A.X = (double*)dalloc(24 * (size_t)n_lm); A.Xb = (double*)dalloc(24 * (size_t)n_lm);
-  A.err = (double*)dalloc(16 * (size_t)(n_pe + n_le)); A.lvl = (uint8_t*)dalloc(n_pe + n_le);
-  A.JA = (double*)dalloc(48 * (size_t)n_edges); A.JB = (double*)dalloc(96 * (size_t)n_edges);
-  A.omr = (double*)dalloc(16 * (size_t)n_edges); A.wgt = (double*)dalloc(8 * (size_t)n_edges);
-  A.pose_slot = (int*)dalloc(4 * (size_t)n_kf); A.lm_slot = (int*)dalloc(4 * (size_t)n_lm);
-  A.Hpp = (double*)dalloc(288 * (size_t)n_free); A.bp = (double*)dalloc(48 * (size_t)n_free);
-  A.Hll = (double*)dalloc(72 * (size_t)n_lm); A.bl = (double*)dalloc(24 * (size_t)n_lm);
-  A.Dinv = (double*)dalloc(72 * (size_t)n_lm); A.Dinvb = (double*)dalloc(24 * (size_t)n_lm);
-  A.Hs = (double*)dalloc(8 * n * n); A.bs = (double*)dalloc(8 * n); A.x = (double*)dalloc(8 * (n + 3 * (size_t)n_lm)); A.Dd = (double*)dalloc(8 * n);
+  for (int pass = 0; pass < 2; pass++) {
+    dry = pass == 0;
+    if (!dry && cudaMemset(ws_base, 0, off) != cudaSuccess) { fail = true; break; }     // off = this problem's extent, from the dry pass
+    off = 0;
+    A.n_kf = n_kf; A.n_pt = n_pt; A.n_ln = n_ln; A.n_pe = n_pe; A.n_le = n_le;
+    A.kf_Tcw = (const float*)up(p->kf_Tcw, 64 * (size_t)n_kf); A.kf_fixed = (const uint8_t*)up(p->kf_fixed, n_kf);
+    A.kf_K = (const float*)up(p->kf_K, 16 * (size_t)n_kf);
+    for (int i = 0; i < 4; i++) A.K_end[i] = p->K_end[i];
+    A.pt_Xw = (const float*)up(p->pt_Xw, 12 * (size_t)n_pt); A.ln_Xw = (const double*)up(p->ln_Xw, 48 * (size_t)n_ln);
+    A.pe_kf = (const int*)up(p->pe_kf, 4 * (size_t)n_pe); A.pe_pt = (const int*)up(p->pe_pt, 4 * (size_t)n_pe);
+    A.pe_obs = (const float*)up(p->pe_obs, 8 * (size_t)n_pe); A.pe_w = (const float*)up(p->pe_inv_sigma2, 4 * (size_t)n_pe);
+    A.le_kf = (const int*)up(p->le_kf, 4 * (size_t)n_le); A.le_ln = (const int*)up(p->le_ln, 4 * (size_t)n_le);
+    A.le_f = (const double*)up(p->le_func, 24 * (size_t)n_le);
+    A.lm_start = (const int*)up(lm_start.data(), 4 * (size_t)(n_lm + 1)); A.lm_edges = (const int*)up(lm_edges.data(), 4 * (size_t)std::max(n_edges, 1));
+    A.kf_start = (const int*)up(kf_start.data(), 4 * (size_t)(n_kf + 1)); A.kf_edges = (const int*)up(kf_edges.data(), 4 * (size_t)std::max(n_edges, 1));
+    A.stop = stop_flag_dev;
+    A.kf_Tcw_out = (float*)dalloc(64 * (size_t)n_kf); A.pt_Xw_out = (float*)dalloc(12 * (size_t)n_pt); A.ln_Xw_out = (double*)dalloc(48 * (size_t)n_ln);
+    A.pe_erase = (uint8_t*)dalloc(n_pe); A.le_erase = (uint8_t*)dalloc(n_le); A.le_erase_kf = (int*)dalloc(4 * (size_t)n_le); A.iterations = (int*)dalloc(4);
+    A.T = (SE3*)dalloc(sizeof(SE3) * n_kf); A.Tb = (SE3*)dalloc(sizeof(SE3) * n_kf);
+    A.Tp = (SE3*)dalloc(sizeof(SE3) * n_kf * 6); A.Tm = (SE3*)dalloc(sizeof(SE3) * n_kf * 6);
+    A.X = (double*)dalloc(24 * (size_t)n_lm); A.Xb = (double*)dalloc(24 * (size_t)n_lm);
+    A.err = (double*)dalloc(16 * (size_t)(n_pe + n_le)); A.lvl = (uint8_t*)dalloc(n_pe + n_le);
+    A.JA = (double*)dalloc(48 * (size_t)n_edges); A.JB = (double*)dalloc(96 * (size_t)n_edges);
+    A.omr = (double*)dalloc(16 * (size_t)n_edges); A.wgt = (double*)dalloc(8 * (size_t)n_edges);
+    A.pose_slot = (int*)dalloc(4 * (size_t)n_kf); A.lm_slot = (int*)dalloc(4 * (size_t)n_lm);
+    A.Hpp = (double*)dalloc(288 * (size_t)n_free); A.bp = (double*)dalloc(48 * (size_t)n_free);
+    A.Hll = (double*)dalloc(72 * (size_t)n_lm); A.bl = (double*)dalloc(24 * (size_t)n_lm);
+    A.Dinv = (double*)dalloc(72 * (size_t)n_lm); A.Dinvb = (double*)dalloc(24 * (size_t)n_lm);
+    A.Hs = (double*)dalloc(8 * n * n); A.bs = (double*)dalloc(8 * n); A.x = (double*)dalloc(8 * (n + 3 * (size_t)n_lm)); A.Dd = (double*)dalloc(8 * n);
+    if (dry && (off > ws_cap || dev != ws_dev)) {       // grow (or move to the current device)
+      if (ws_base) cudaFree(ws_base);
+      ws_base = nullptr; ws_cap = 0; ws_dev = dev;
+      const size_t want = off + off / 4;
+      if (cudaMalloc((void**)&ws_base, want) != cudaSuccess) { ws_base = nullptr; fail = true; break; }
+      ws_cap = want;
+    }
+  }
   int ret = PL_OK;
   if (fail) { set_error("local BA: device allocation failed"); ret = PL_ERR_CUDA; }
   else {
@@ -538,6 +558,5 @@ extern "C" int pl_local_ba(const PLBAProblem* p, const int* stop_flag_dev, float
     if (e == cudaSuccess && iterations) e = cudaMemcpy(iterations, A.iterations, 4, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { set_error("local BA: %s", cudaGetErrorString(e)); ret = PL_ERR_CUDA; }
   }
-  for (void* d : frees) cudaFree(d);
   return ret;
 }

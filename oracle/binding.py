@@ -737,12 +737,16 @@ def ref_distinctive_descriptors(desc, offsets):
     return out
 
 
-def ref_predict_scale(dist, max_dist, log_scale_factor, n_levels):
-    """MapPoint::PredictScale(currentDist, pKF) of the reference itself."""
+def predict_scale(dist, max_dist, log_scale_factor, n_levels, impl="oracle"):
+    """MapPoint::PredictScale(currentDist, pKF): the oracle's restatement, or (impl="ref") the reference itself."""
     d = _f32(dist); mx = _f32(max_dist); out = np.zeros(len(d), np.int32)
-    f = _fn("predict_scale", "ref"); f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    f = _fn("predict_scale", impl); f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
     f(_p(d), _p(mx), len(d), log_scale_factor, n_levels, _p(out))
     return out
+
+
+def ref_predict_scale(dist, max_dist, log_scale_factor, n_levels):
+    return predict_scale(dist, max_dist, log_scale_factor, n_levels, impl="ref")
 
 
 def lsd_fuse_search(keylines, kf_point_desc, bounds, Tcw, Ow, K, scale_line, log_scale_factor_line, skip, pos, normal, min_dist, max_dist,

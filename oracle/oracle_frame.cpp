@@ -133,7 +133,7 @@ void oracle_is_in_frustum_points(const float* Tcw, const float* Ow, const float*
     const float viewCos = (float)(((double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2]) / dist);
     if (viewCos < viewingCosLimit) continue;
     const float ratio = maxDist[i] / dist;
-    int nScale = (int)std::ceil(std::log((double)ratio) / (double)logScaleFactor);
+    int nScale = (int)ceilf(logf(ratio) / logScaleFactor);
     if (nScale < 0) nScale = 0; else if (nScale >= nScaleLevels) nScale = nScaleLevels - 1;
     inview[i] = 1; proj[2 * i] = u; proj[2 * i + 1] = v; level[i] = nScale; viewcos[i] = viewCos;
   }
@@ -165,7 +165,7 @@ void oracle_is_in_frustum_lines(const float* Tcw, const float* Ow, const float* 
     if (viewCos < viewingCosLimit) continue;
     const float ratio = maxDist[i] / dist;
     inview[i] = 1; proj[4 * i] = u1; proj[4 * i + 1] = v1; proj[4 * i + 2] = u2; proj[4 * i + 3] = v2;
-    level[i] = (int)std::ceil(std::log((double)ratio) / (double)logScaleFactor); viewcos[i] = viewCos;
+    level[i] = (int)ceilf(logf(ratio) / logScaleFactor); viewcos[i] = viewCos;
   }
 }
 }

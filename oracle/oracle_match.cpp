@@ -548,6 +548,16 @@ int oracle_search_for_triangulation(const void* keys1_, const uint8_t* desc1, co
   return nmatches;
 }
 
+// MapPoint::PredictScale(currentDist, pKF) (MapPoint.cc:396-411) on its own: log() of a float is libm's logf, the quotient is fp32
+void oracle_predict_scale(const float* dist, const float* maxDist, int n, float logScaleFactor, int nScaleLevels, int* level) {
+  for (int i = 0; i < n; i++) {
+    const float ratio = maxDist[i] / dist[i];
+    int lvl = (int)ceilf(logf(ratio) / logScaleFactor);
+    if (lvl < 0) lvl = 0; else if (lvl >= nScaleLevels) lvl = nScaleLevels - 1;
+    level[i] = lvl;
+  }
+}
+
 // The search half of ORBmatcher::Fuse(KeyFrame*, vector<MapPoint*>, th) (src/ORBmatcher.cc:914-1065): for every map
 // point the best keypoint of the keyframe (bestIdx, bestDist; -1/256 when it is skipped or nothing qualifies).  The map
 // surgery that follows (Replace / AddObservation, :1036-1061) is sequential map logic outside the path; `skip` carries
@@ -579,7 +589,7 @@ void oracle_fuse_search(const void* keys_, const uint8_t* desc, int n, const flo
     const double dot = (double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2];
     if (dot < 0.5 * dist3D) continue;
     const float ratio = maxDist[i] / dist3D;                                                   // MapPoint::PredictScale(dist, pKF)
-    int lvl = (int)std::ceil(std::log((double)ratio) / (double)logScaleFactor);
+    int lvl = (int)ceilf(logf(ratio) / logScaleFactor);
     if (lvl < 0) lvl = 0; else if (lvl >= nScaleLevels) lvl = nScaleLevels - 1;
     const float radius = th * scaleFactors[lvl];
     features_in_area(g, k, u, v, radius, -1, -1, cand);                                        // KeyFrame::GetFeaturesInArea
@@ -701,7 +711,7 @@ int oracle_search_by_projection_keyframe(const void* keys_cur_, const uint8_t* d
     const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
     if (dist3D < 0.8f * minDist[i] || dist3D > 1.2f * maxDist[i]) continue;   // Get{Min,Max}DistanceInvariance
     const float ratio = maxDist[i] / dist3D;                                   // PredictScale: raw mfMaxDistance (MapPoint.cc:396-411)
-    int lvl = (int)std::ceil(std::log((double)ratio) / (double)logScaleFactor);
+    int lvl = (int)ceilf(logf(ratio) / logScaleFactor);
     if (lvl < 0) lvl = 0; else if (lvl >= nlevels) lvl = nlevels - 1;
     const float radius = th * scaleFactors[lvl];
     features_in_area(g, kc, u, v, radius, lvl - 1, lvl + 1, cand);
@@ -846,7 +856,7 @@ void oracle_lsd_fuse_search(const void* keylines_, int nl, const uint8_t* kf_poi
     const double dot = (double)OM[0] * pn[0] + (double)OM[1] * pn[1] + (double)OM[2] * pn[2];
     if (dot < 0.5 * dist) continue;
     const float ratio = maxDist[i] / dist;
-    const int lvl = (int)std::ceil(std::log((double)ratio) / (double)logScaleFactorLine);
+    const int lvl = (int)ceilf(logf(ratio) / logScaleFactorLine);
     float sf = 1.0f;                                        // mvScaleFactorsLine[lvl]: cumulative fp32 products, 1/x below zero
     if (lvl >= 0) for (int k = 0; k < lvl; k++) sf = sf * scale_line;
     else { for (int k = 0; k < -lvl; k++) sf = sf * scale_line; sf = 1.0f / sf; }

@@ -109,8 +109,11 @@ class GridView {
   cv::Mat mK, ImageGray;
   float mfLogScaleFactorLine = 0.f;
   // mvScaleFactorsLine[level]: the reference indexes this vector with an UNCLAMPED predicted level (LSDmatcher.cpp:944), out of
-  // range for every level outside [0, octaves): read here as scale^level, the rule the table is built with (LineExtractor.cpp:7-14)
-  struct ScaleTable { float scale = 1.2f; float operator[](int level) const { return powf(scale, (float)level); } } mvScaleFactorsLine;
+  // range for every level outside [0, octaves): read here as scale^level by cumulative fp32 products, the rule the table is built with (LineExtractor.cpp:7-14)
+  struct ScaleTable {
+    float scale = 1.2f;
+    float operator[](int level) const { float sf = 1.0f; for (int k = 0; k < (level < 0 ? -level : level); k++) sf = sf * scale; return level < 0 ? 1.0f / sf : sf; }
+  } mvScaleFactorsLine;
   std::vector<std::size_t> mGridForLine[FRAME_GRID_COLS][FRAME_GRID_ROWS];
   void AssignFeaturesToGridForLine() {                                        // Frame.cc:296-320, with the reference's LineIterator
     for (int i = 0; i < FRAME_GRID_COLS; i++) for (int j = 0; j < FRAME_GRID_ROWS; j++) mGridForLine[i][j].clear();

@@ -7,6 +7,7 @@
 // OpenCV arithmetic restated and pinned in the oracle: 1/32-pixel fixed-point bilinear remap with 15-bit weights,
 // BORDER_CONSTANT 0; fp32 3x3 gemm as ((a0*b0 + a1*b1) + a2*b2) + c; cv::norm / dot with fp64 accumulation.
 #include "common.cuh"
+#include "libm_glibc.cuh"
 #include <math.h>
 #include <vector>
 
@@ -90,7 +91,7 @@ __global__ void k_frustum_points(FrustumArgs A, const float* __restrict__ pos, c
   const float viewCos = (float)(((double)PO[0] * normal[3 * i] + (double)PO[1] * normal[3 * i + 1] + (double)PO[2] * normal[3 * i + 2]) / dist);
   if (viewCos < A.viewingCosLimit) return;
   const float ratio = __fdiv_rn(maxDist[i], dist);
-  int nScale = (int)ceil(log((double)ratio) / (double)A.logScaleFactor);
+  int nScale = (int)ceilf(__fdiv_rn(glibc::logf_(ratio), A.logScaleFactor));
   if (nScale < 0) nScale = 0; else if (nScale >= A.nScaleLevels) nScale = A.nScaleLevels - 1;
   inview[i] = 1; proj[2 * i] = u; proj[2 * i + 1] = v; level[i] = nScale; viewcos[i] = viewCos;
 }
@@ -116,7 +117,7 @@ __global__ void k_frustum_lines(FrustumArgs A, const double* __restrict__ pos, c
   if (viewCos < A.viewingCosLimit) return;
   const float ratio = __fdiv_rn(maxDist[i], dist);
   inview[i] = 1; proj[4 * i] = u1; proj[4 * i + 1] = v1; proj[4 * i + 2] = u2; proj[4 * i + 3] = v2;
-  level[i] = (int)ceil(log((double)ratio) / (double)A.logScaleFactor); viewcos[i] = viewCos;
+  level[i] = (int)ceilf(__fdiv_rn(glibc::logf_(ratio), A.logScaleFactor)); viewcos[i] = viewCos;
 }
 }  // namespace pl
 using namespace pl;

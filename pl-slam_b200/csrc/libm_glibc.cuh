@@ -7,6 +7,8 @@
 // by one ulp), so byte parity with the reference needs the same algorithms.  These are restatements of the published algorithms
 // glibc 2.39 (the C library of this image and of the GPU box) uses:
 //   atan2f / atanf : FreeBSD msun / fdlibm e_atan2f.c, s_atanf.c (Sun Microsystems 1993), all arithmetic in fp32;
+//   logf           : Arm Optimized Routines logf.c (16-entry table, degree-3 polynomial, fp64; MapPoint / MapLine::PredictScale call
+//                    log() on a float, MapPoint.cc:404, MapLine.cpp:403);
 //   sincosf        : Arm Optimized Routines sincosf.c (Szabolcs Nagy, Wilco Dijkstra 2018), argument reduction and the two
 //                    minimax polynomials in fp64, one rounding to fp32; the fused multiply-adds are those of the x86-64 FMA build
 //                    glibc selects on every CPU with FMA3 (a different contraction can only change the result when the fp64 value
@@ -112,6 +114,29 @@ PL_LIBM_HD void sincosf_(float y, float* sinp, float* cosp) {
   const double s = fma(x3, S1, x), c = fma(x4, cs * C2, c1);
   const float sv = (float)fma(x5, s1, s), cv = (float)fma(x6, c2, c);
   if (n & 1) { *sinp = cv; *cosp = sv; } else { *sinp = sv; *cosp = cv; }
+}
+
+// logf.c: positive normal arguments (the path passes distance ratios); zero, negatives, subnormals, inf / NaN are outside this restatement
+PL_LIBM_HD float logf_(float x) {
+  const double invc[16] = {0x1.661ec79f8f3bep+0, 0x1.571ed4aaf883dp+0, 0x1.49539f0f010bp+0, 0x1.3c995b0b80385p+0, 0x1.30d190c8864a5p+0, 0x1.25e227b0b8eap+0,
+                           0x1.1bb4a4a1a343fp+0, 0x1.12358f08ae5bap+0, 0x1.0953f419900a7p+0, 0x1p+0, 0x1.e608cfd9a47acp-1, 0x1.ca4b31f026aap-1,
+                           0x1.b2036576afce6p-1, 0x1.9c2d163a1aa2dp-1, 0x1.886e6037841edp-1, 0x1.767dcf5534862p-1};
+  const double logc[16] = {-0x1.57bf7808caadep-2, -0x1.2bef0a7c06ddbp-2, -0x1.01eae7f513a67p-2, -0x1.b31d8a68224e9p-3, -0x1.6574f0ac07758p-3, -0x1.1aa2bc79c81p-3,
+                           -0x1.a4e76ce8c0e5ep-4, -0x1.1973c5a611cccp-4, -0x1.252f438e10c1ep-5, 0x0p+0, 0x1.aa5aa5df25984p-5, 0x1.c5e53aa362eb4p-4,
+                           0x1.526e57720db08p-3, 0x1.bc2860d22477p-3, 0x1.1058bc8a07ee1p-2, 0x1.4043057b6ee09p-2};
+  const double Ln2 = 0x1.62e42fefa39efp-1, A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2;
+  const uint32_t ix = f2u(x);
+  if (ix == 0x3f800000u) return 0.0f;
+  const uint32_t tmp = ix - 0x3f330000u;
+  const int i = (int)((tmp >> 19) & 15u), k = (int32_t)tmp >> 23;
+  const uint32_t iz = ix - (tmp & 0xff800000u);
+  const double z = (double)u2f(iz);
+  const double r = fma(z, invc[i], -1.0), y0 = fma((double)k, Ln2, logc[i]);
+  const double r2 = r * r;
+  double y = fma(A1, r, A2);
+  y = fma(A0, r2, y);
+  y = fma(y, r2, y0 + r);
+  return (float)y;
 }
 
 }  // namespace glibc

@@ -17,6 +17,7 @@
 // Frames of a batch are independent -> one warp (CTA) per frame, grid = B.
 
 #include "common.cuh"
+#include "libm_glibc.cuh"
 #include <vector>
 
 namespace pl {
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(32) k_search_proj_last(ProjLastArgs A) {
       const float dist3D = (float)sqrt((double)p0 * p0 + (double)p1 * p1 + (double)p2 * p2);
       if (dist3D < __fmul_rn(0.8f, A.min_dist[lb + i]) || dist3D > __fmul_rn(1.2f, A.max_dist[lb + i])) continue;   // invariance range; PredictScale below uses the raw mfMaxDistance
       const float ratio = __fdiv_rn(A.max_dist[lb + i], dist3D);
-      oct = (int)ceil(log((double)ratio) / (double)A.logSF);
+      oct = (int)ceilf(__fdiv_rn(glibc::logf_(ratio), A.logSF));
       if (oct < 0) oct = 0; else if (oct >= A.nlevels) oct = A.nlevels - 1;
     } else oct = A.last_octave[lb + i];
     const float radius = __fmul_rn(A.th, A.scaleFactors[oct]);
@@ -834,7 +835,7 @@ __global__ void __launch_bounds__(32 * kFuseWarps) k_fuse_search(FuseArgs A) {
           const double dot = (double)PO[0] * A.normal[3 * i] + (double)PO[1] * A.normal[3 * i + 1] + (double)PO[2] * A.normal[3 * i + 2];
           go = !(dot < 0.5 * (double)dist3D);
           const float ratio = __fdiv_rn(A.maxDist[i], dist3D);
-          lvl = (int)ceil(log((double)ratio) / (double)A.logScaleFactor);
+          lvl = (int)ceilf(__fdiv_rn(glibc::logf_(ratio), A.logScaleFactor));
           if (lvl < 0) lvl = 0; else if (lvl >= A.nLevels) lvl = A.nLevels - 1;
         }
       }
@@ -993,7 +994,7 @@ __global__ void __launch_bounds__(128) k_lsd_fuse_search(LineFuseArgs A) {
   const double dot = (double)OM[0] * pn[0] + (double)OM[1] * pn[1] + (double)OM[2] * pn[2];
   if (dot < 0.5 * (double)dist) return;
   const float ratio = __fdiv_rn(A.maxDist[i], dist);
-  const int lvl = (int)ceil(log((double)ratio) / (double)A.logScaleFactorLine);
+  const int lvl = (int)ceilf(__fdiv_rn(glibc::logf_(ratio), A.logScaleFactorLine));
   float sf = 1.0f;
   if (lvl >= 0) { for (int k = 0; k < lvl; k++) sf = __fmul_rn(sf, A.scale_line); }
   else { for (int k = 0; k < -lvl; k++) sf = __fmul_rn(sf, A.scale_line); sf = __fdiv_rn(1.0f, sf); }

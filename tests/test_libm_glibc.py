@@ -1,6 +1,6 @@
-"""The float libm restatements of the CUDA path (pl-slam_b200/csrc/libm_glibc.cuh: atan2f, sincosf as glibc 2.39 computes them)
-against the running C library, on the host: the header is plain C++ outside nvcc.  The reference calls exactly these two functions
-(KeyLine::angle, the LBD line direction, the rBRIEF steering); the device code is the same source compiled with -fmad=false."""
+"""The float libm restatements of the CUDA path (pl-slam_b200/csrc/libm_glibc.cuh: atan2f, sincosf, logf as glibc 2.39 computes them)
+against the running C library, on the host: the header is plain C++ outside nvcc.  The reference calls exactly these functions
+(KeyLine::angle, the LBD line direction, the rBRIEF steering, PredictScale); the device code is the same source compiled with -fmad=false."""
 import os
 import subprocess
 import pytest
@@ -23,4 +23,4 @@ def test_device_libm_equals_host_libm(tmp_path):
     if r.returncode != 0 and not _glibc().startswith("2.39"):
         pytest.skip(f"glibc {_glibc()} computes these functions differently from the 2.39 the restatement follows: {r.stdout.strip()}")
     assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.startswith("mismatches 0 0 0 of"), r.stdout
+    assert r.stdout.startswith("mismatches 0 0 0 0 of"), r.stdout

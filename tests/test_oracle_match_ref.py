@@ -143,13 +143,18 @@ def test_distinctive_descriptors():
 
 def test_predict_scale():
     rng = np.random.default_rng(1)
-    max_dist = rng.uniform(2.0, 12.0, 20000).astype(np.float32)
-    dist = (max_dist / rng.uniform(0.5, 6.0, 20000)).astype(np.float32)
-    dist[:8] = max_dist[:8] / np.float32(1.2) ** np.arange(8, dtype=np.float32)     # exact level boundaries
-    log_sf = float(np.log(np.float32(1.2)))
-    ref = oracle.ref_predict_scale(dist, max_dist, np.float32(log_sf), 8)
-    ratio = max_dist / dist
-    want = np.clip(np.ceil(np.log(ratio.astype(np.float64)) / np.float64(np.float32(log_sf))), 0, 7).astype(np.int32)
-    # the reference evaluates logf / float division: it may differ from the fp64 formula only where the quotient sits on an integer
-    bad = np.nonzero(ref != want)[0]
-    assert len(bad) <= 8 and all(abs(np.log(float(ratio[i])) / log_sf - round(np.log(float(ratio[i])) / log_sf)) < 1e-5 for i in bad), bad
+    n = 200000
+    max_dist = rng.uniform(2.0, 12.0, n).astype(np.float32)
+    dist = (max_dist / rng.uniform(0.5, 6.0, n)).astype(np.float32)
+    # exact level boundaries and their fp32 neighbours: where logf / the fp32 quotient decide the level
+    k = np.arange(n // 2) % 9
+    edge = (max_dist[:n // 2] / (np.float32(1.2) ** k.astype(np.float32))).astype(np.float32)
+    dist[:n // 2] = np.nextafter(edge, np.where(np.arange(n // 2) % 3 == 0, np.float32(0), np.where(np.arange(n // 2) % 3 == 1, np.float32(1e9), edge)).astype(np.float32))
+    log_sf = np.float32(np.log(np.float32(1.2)))
+    ref = oracle.ref_predict_scale(dist, max_dist, log_sf, 8)
+    got = oracle.predict_scale(dist, max_dist, log_sf, 8)
+    assert np.array_equal(ref, got)
+    # and it is not the fp64 formula: on the boundaries the two disagree somewhere (which is why the float functions matter)
+    ratio = (max_dist / dist).astype(np.float32)
+    f64 = np.clip(np.ceil(np.log(ratio.astype(np.float64)) / np.float64(log_sf)), 0, 7).astype(np.int32)
+    assert (f64 != ref).sum() > 0

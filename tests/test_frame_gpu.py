@@ -107,3 +107,27 @@ def test_is_in_frustum_lines(seed, cosl):
     assert want[0].sum() > 50
     for g, w_ in zip(got, want):
         assert np.array_equal(g, w_)
+
+
+def test_is_in_frustum_predicted_level_on_boundaries():
+    """MapPoint::PredictScale is ceil(logf(ratio) / logScaleFactor) in fp32 (the compiled MapPoint.cc, tests/test_oracle_match_ref.py):
+    points whose ratio sits exactly on a level boundary (and its fp32 neighbours) are where the float functions decide."""
+    v = synth.synth_map_view(13, 20000)
+    PO = (v["pos"] - v["Ow"]).astype(np.float32)
+    dist = np.sqrt((PO.astype(np.float64) ** 2).sum(1)).astype(np.float32)
+    k = (np.arange(len(dist)) % 9).astype(np.float32)
+    mx = (dist * np.float32(1.2) ** k).astype(np.float32)
+    sel = np.arange(len(dist)) % 3
+    mx = np.where(sel == 0, np.nextafter(mx, np.float32(0)), np.where(sel == 1, np.nextafter(mx, np.float32(1e9)), mx)).astype(np.float32)
+    v["max_dist"] = mx; v["min_dist"] = (mx / np.float32(1.2) ** 10).astype(np.float32)
+    b = oracle.image_bounds(synth.TUM1_K, synth.TUM1_DIST, 640, 480)
+    log_sf = float(np.float32(np.log(np.float32(1.2))))
+    a = (v["Tcw"], v["Ow"], synth.TUM1_K, b, log_sf, 8, 0.0, v["pos"], v["normal"], v["min_dist"], v["max_dist"])
+    want = oracle.is_in_frustum_points(*a); got = pl.isInFrustum(*a)
+    assert want[0].sum() > 2000
+    for g, w_ in zip(got, want):
+        assert np.array_equal(g, w_)
+    ratio = (mx / dist).astype(np.float32)
+    f64 = np.clip(np.ceil(np.log(ratio.astype(np.float64)) / np.float64(np.float32(log_sf))), 0, 7).astype(np.int32)
+    inv = want[0].astype(bool)
+    assert (f64[inv] != want[2][inv]).sum() > 0        # the fp64 formula of round 1 would have failed here

@@ -21,7 +21,12 @@ namespace ord {
 
 using lg::kDegToRads;
 using lg::kPI;
-constexpr int kORing = 256;   // recent queue entries in shared memory (512 entries cost 6 ms at B = 4736: the L1 share matters more)
+// recent queue entries in shared memory; older ones are re-read from the region list in global memory (L1 hits).  The L1 share matters
+// more than the ring: B = 4736, 512 entries 190.5 ms -> 256 entries 184.0 (earlier build); this build 256: 159.3, 128: 160.1, 64: 156.7, 32: 157.0, 16: 157.0
+#ifndef PL_GROW_RING
+#define PL_GROW_RING 64
+#endif
+constexpr int kORing = PL_GROW_RING;
 constexpr int kUsedO = 0;
 
 // Per-frame arrays are addressed as  kernel-parameter base + 32-bit element index (fb = frame * npx + pixel): one IMAD.WIDE per
@@ -452,12 +457,14 @@ __global__ void __launch_bounds__(32, 32) k_lsd_grow_ordered(LineParams P, int4*
         single = !any;
         prefetch_l2(&C.S2[C.fb + (unsigned)pidx]);
       }
+#ifndef PL_GROW_NOPF                          // (without these prefetches: 159.0 -> 162.2 ms at B = 4736)
       if (!kPre && ((todo >> lane) & 1u)) {   // this batch's seeds that will grow: their seed record and 3x3 rows into L2
         prefetch_l2(&C.S2[C.fb + (unsigned)pidx]);
         const int up = max(pidx - P.sw, 1), dn = min(pidx + P.sw, P.npx - 2);
         prefetch_l2(&C.REC[C.fb + (unsigned)(up - 1)]); prefetch_l2(&C.REC[C.fb + (unsigned)(up + 1)]); prefetch_l2(&C.REC[C.fb + (unsigned)(dn - 1)]); prefetch_l2(&C.REC[C.fb + (unsigned)(dn + 1)]);
         prefetch_l2(&C.REC[C.fb + (unsigned)(max(pidx, 1) - 1)]); prefetch_l2(&C.REC[C.fb + (unsigned)(min(pidx, P.npx - 2) + 1)]);
       }
+#endif
       const unsigned singles = __ballot_sync(0xffffffffu, single);
       if (i + 32 < n) { const unsigned pn = O[i + 32]; prefetch_l2(&C.REC[C.fb + (unsigned)((int)(pn >> 16) * P.sw + (int)(pn & 0xffffu))]); }
       while (todo) {

@@ -20,74 +20,6 @@
 #include "line_descriptor_custom.hpp"   // /root/reference/Thirdparty/line_descriptor/include (-I on the command line)
 #include "LineExtractor.h"              // /root/reference/include: the reference's LINEextractor (src/LineExtractor.cpp is compiled too)
 
-extern "C" {   // liboracle.so
-void oracle_blur_u8(const uint8_t* src, int w, int h, uint8_t* dst, int ksize);
-void oracle_sobel3_u8(const uint8_t* img, int w, int h, int16_t* dx, int16_t* dy);
-int oracle_lsd_detect(const uint8_t* img, int w, int h, int order_mode, float* lines, int cap);
-}
-
-namespace cv {
-
-static std::vector<uchar> packed(const Mat& m) {
-  std::vector<uchar> v((size_t)m.rows * m.cols + 1);
-  for (int y = 0; y < m.rows; y++) memcpy(v.data() + (size_t)y * m.cols, m.ptr(y), (size_t)m.cols);
-  return v;
-}
-
-void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, double sigmaY, int borderType) {
-  // binary_descriptor_custom.cpp:358: GaussianBlur(img, img, Size(5, 5), 1)  (sigmaY = 0 means sigmaX; default border REFLECT_101)
-  if (src.type() != CV_8UC1 || ksize.width != 5 || ksize.height != 5 || sigmaX != 1 || (sigmaY != 0 && sigmaY != 1) || borderType != BORDER_DEFAULT) abort();
-  const std::vector<uchar> in = packed(src);
-  std::vector<uchar> out(in.size());
-  oracle_blur_u8(in.data(), src.cols, src.rows, out.data(), 5);
-  dst.create(src.rows, src.cols, CV_8UC1);
-  for (int y = 0; y < dst.rows; y++) memcpy(dst.ptr(y), out.data() + (size_t)y * dst.cols, (size_t)dst.cols);
-}
-
-void Sobel(const Mat& src, Mat& dst, int ddepth, int dx, int dy, int ksize) {
-  if (src.type() != CV_8UC1 || ddepth != CV_16SC1 || ksize != 3 || dx + dy != 1) abort();   // binary_descriptor_custom.cpp:395-396
-  const std::vector<uchar> in = packed(src);
-  std::vector<int16_t> gx((size_t)src.rows * src.cols + 1), gy(gx.size());
-  oracle_sobel3_u8(in.data(), src.cols, src.rows, gx.data(), gy.data());
-  dst.create(src.rows, src.cols, CV_16SC1);
-  const std::vector<int16_t>& g = dx ? gx : gy;
-  for (int y = 0; y < dst.rows; y++) memcpy(dst.ptr(y), g.data() + (size_t)y * dst.cols, (size_t)dst.cols * 2);
-}
-
-// the reference runs one octave (LINEextractor passes numOctaves = 1): these three are never reached on the tested paths
-void pyrDown(const Mat&, Mat&, Size) { fprintf(stderr, "ref_line: pyrDown (more than one octave) is not provided\n"); abort(); }
-void cvtColor(const Mat&, Mat&, int) { fprintf(stderr, "ref_line: cvtColor is not provided (grey input only)\n"); abort(); }
-void resize(const Mat&, Mat&, Size, double, double, int) { fprintf(stderr, "ref_line: resize (EDLine octaves) is not provided\n"); abort(); }
-
-namespace {
-class Lsd : public LineSegmentDetector {
- public:
-  void detect(const Mat& image, std::vector<Vec4f>& lines) override {
-    const std::vector<uchar> in = packed(image);
-    std::vector<float> out((size_t)4 * 65536);
-    const int n = oracle_lsd_detect(in.data(), image.cols, image.rows, /*order_mode: cv2's*/ 1, out.data(), 65536);
-    if (n > 65536) abort();
-    lines.resize((size_t)n);
-    for (int i = 0; i < n; i++) for (int k = 0; k < 4; k++) lines[i][k] = out[(size_t)4 * i + k];
-  }
-};
-}  // namespace
-Ptr<LineSegmentDetector> createLineSegmentDetector(int refine, double scale, double sigma_scale, double quant, double ang_th, double log_eps,
-                                                   double density_th, int n_bins) {
-  // LSD_REFINE_STD and the defaults: the only configuration the reference uses (LSDDetector_custom.cpp:150)
-  if (refine != 1 || scale != 0.8 || sigma_scale != 0.6 || quant != 2.0 || ang_th != 22.5 || log_eps != 0 || density_th != 0.7 || n_bins != 1024) abort();
-  return Ptr<LineSegmentDetector>(new Lsd());
-}
-
-// cv::LineIterator(img, Point2f, Point2f): the end points convert to Point by saturate_cast<int> (= cvRound), 8-connected count;
-// both end points lie inside the image here (checkLineExtremes, LSDDetector_custom.cpp:77-103), so no clipping happens
-LineIterator::LineIterator(const Mat&, Point2f p1, Point2f p2) {
-  const int x0 = cvRound(p1.x), y0 = cvRound(p1.y), x1 = cvRound(p2.x), y1 = cvRound(p2.y);
-  count = std::max(std::abs(x1 - x0), std::abs(y1 - y0)) + 1;
-}
-
-}  // namespace cv
-
 using cv::line_descriptor::KeyLine;
 static_assert(sizeof(KeyLine) == 68, "KeyLine layout");
 

@@ -16,85 +16,6 @@
 #include <cstdlib>
 #include "ORBextractor.h"   // /root/reference/include (-I on the command line)
 
-extern "C" {   // liboracle.so (oracle_orb.cpp)
-void oracle_resize_linear_u8(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh);
-void oracle_blur_u8(const uint8_t* src, int w, int h, uint8_t* dst, int ksize);
-float oracle_fast_atan2(float y, float x);
-int oracle_fast_detect(const uint8_t* img, int w, int h, int threshold, void* out, int cap);
-}
-
-namespace cv {
-
-static std::vector<uchar> packed(const Mat& m) {
-  std::vector<uchar> v((size_t)m.rows * m.cols + 1);
-  for (int y = 0; y < m.rows; y++) memcpy(v.data() + (size_t)y * m.cols, m.ptr(y), (size_t)m.cols);
-  return v;
-}
-static void unpack(const std::vector<uchar>& v, Mat& m) {
-  for (int y = 0; y < m.rows; y++) memcpy(m.ptr(y), v.data() + (size_t)y * m.cols, (size_t)m.cols);
-}
-
-float fastAtan2(float y, float x) { return oracle_fast_atan2(y, x); }
-
-// cv::FAST(roi, kps, th, true): the ROI is an image of its own (no pixels outside it are read)
-void FAST(const Mat& image, std::vector<KeyPoint>& keypoints, int threshold, bool nonmaxSuppression) {
-  if (!nonmaxSuppression) abort();                       // ORBextractor.cc always asks for NMS
-  keypoints.clear();
-  if (image.rows < 7 || image.cols < 7) return;
-  const std::vector<uchar> img = packed(image);
-  std::vector<KeyPoint> out((size_t)image.rows * image.cols);
-  const int n = oracle_fast_detect(img.data(), image.cols, image.rows, threshold, out.data(), (int)out.size());
-  keypoints.assign(out.begin(), out.begin() + n);
-}
-
-void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, double sigmaY, int borderType) {
-  if (ksize.width != 7 || ksize.height != 7 || sigmaX != 2 || sigmaY != 2 || borderType != BORDER_REFLECT_101) abort();   // ORBextractor.cc:1086
-  const std::vector<uchar> in = packed(src);
-  std::vector<uchar> out(in.size());
-  oracle_blur_u8(in.data(), src.cols, src.rows, out.data(), 7);
-  dst.create(src.rows, src.cols, CV_8UC1);
-  unpack(out, dst);
-}
-
-void resize(const Mat& src, Mat& dst, Size dsize, double, double, int interpolation) {
-  if (interpolation != INTER_LINEAR) abort();
-  const std::vector<uchar> in = packed(src);
-  std::vector<uchar> out((size_t)dsize.width * dsize.height + 1);
-  oracle_resize_linear_u8(in.data(), src.cols, src.rows, out.data(), dsize.width, dsize.height);
-  dst.create(dsize.height, dsize.width, CV_8UC1);      // keeps the pyramid ROI (same shape)
-  unpack(out, dst);
-}
-
-static int reflect101(int p, int n) {
-  if (n == 1) return 0;
-  while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p;
-  return p;
-}
-// copyMakeBorder(..., BORDER_REFLECT_101 [+ BORDER_ISOLATED]).  Both call sites of ORBextractor.cc:1122-1128 pass a source whose
-// pixels outside the ROI must not be used (level > 0: ISOLATED; level 0: a whole image), so the border is always the reflection
-// of the source itself.  The source may be the interior of dst (level > 0): read it through a packed copy.
-void copyMakeBorder(const Mat& src, Mat& dst, int top, int bottom, int left, int right, int borderType) {
-  if ((borderType & ~BORDER_ISOLATED) != BORDER_REFLECT_101) abort();
-  const std::vector<uchar> in = packed(src);
-  const int w = src.cols, h = src.rows;
-  dst.create(h + top + bottom, w + left + right, CV_8UC1);
-  for (int y = 0; y < dst.rows; y++) {
-    const uchar* row = in.data() + (size_t)reflect101(y - top, h) * w;
-    uchar* o = dst.ptr(y);
-    for (int x = 0; x < dst.cols; x++) o[x] = row[reflect101(x - left, w)];
-  }
-}
-
-// only ComputeKeyPointsOld() uses it, which operator() never calls (ORBextractor.cc:1057); defined so the file links
-void KeyPointsFilter::retainBest(std::vector<KeyPoint>& keypoints, int npoints) {
-  if (npoints < 0 || (int)keypoints.size() <= npoints) return;
-  std::stable_sort(keypoints.begin(), keypoints.end(), [](const KeyPoint& a, const KeyPoint& b) { return a.response > b.response; });
-  keypoints.resize((size_t)npoints);
-}
-
-}  // namespace cv
-
-
 // ---- allocation order = address order ---------------------------------------------------------------------------------------
 // DistributeOctTree sorts pair<int, ExtractorNode*> (ORBextractor.cc:684): nodes holding the same number of keypoints are ordered
 // by their HEAP ADDRESS, which the C++ program does not define (with glibc's malloc the freed list nodes are handed out again

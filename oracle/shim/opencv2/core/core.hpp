@@ -167,7 +167,20 @@ class Mat {
     m.create(rows, cols, type_);
     for (int y = 0; y < rows; y++) memcpy(m.data + (size_t)y * m.step, data + (size_t)y * step, (size_t)cols * elemSize());
   }
+  void copyTo(Mat&& view) const {           // into an existing view of the same shape (Tcw.colRange(0, 3) as a destination)
+    if (view.rows != rows || view.cols != cols || view.type() != type_) abort();
+    for (int y = 0; y < rows; y++) memcpy(view.data + (size_t)y * view.step, data + (size_t)y * step, (size_t)cols * elemSize());
+  }
   void copyTo(const _OutputArray& o) const;
+  Mat reshape(int cn) const {               // same data, another channel count (N x 2 one-channel <-> N x 1 two-channel)
+    Mat m(*this);
+    const int per_row = cols * channels();
+    if (per_row % cn) abort();
+    m.type_ = CV_MAKETYPE(depth(), cn); m.cols = per_row / cn;
+    return m;
+  }
+  void convertTo(Mat& m, int type) const { Mat r = convertedTo(type); m = r; }
+  static Mat ones(int r, int c, int type) { Mat m(r, c, type); m.setTo(1.0); return m; }
   Mat& setTo(double v) {
     for (int y = 0; y < rows; y++)
       for (int x = 0; x < cols * channels(); x++) put(y, x, v);
@@ -246,6 +259,12 @@ inline Mat operator*(double s, const Mat& a) {
 }
 inline Mat operator*(const Mat& a, double s) { return s * a; }
 inline Mat operator-(const Mat& a) { return -1.0 * a; }
+inline double norm(const Mat& a, const Mat& b, int type) {
+  if (type != 2 /* NORM_L1 */) abort();
+  double s = 0;
+  for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) s += std::fabs(a.get(y, x) - b.get(y, x));
+  return s;
+}
 inline double norm(const Mat& a) {      // NORM_L2: squares and sum in fp64
   double s = 0;
   for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) { const double v = a.get(y, x); s += v * v; }
@@ -266,6 +285,7 @@ template <typename T> class Mat_ : public Mat {
   Mat_() : Mat() { type_ = DataDepth<T>::value; }
   Mat_(int r, int c) : Mat(r, c, DataDepth<T>::value) {}
   Mat_(const Mat& m) : Mat() { *this = m; }
+  static Mat_ eye(int r, int c) { Mat_ m(r, c); for (int y = 0; y < r; y++) for (int x = 0; x < c; x++) m[y][x] = (T)(x == y); return m; }
   Mat_& operator=(const Mat& m) {   // shares the data when the type matches, converts otherwise (as OpenCV does)
     if (m.type() == DataDepth<T>::value || m.empty()) { Mat::operator=(m); type_ = DataDepth<T>::value; }
     else Mat::operator=(m.convertedTo(DataDepth<T>::value));
@@ -319,7 +339,7 @@ enum { INTER_NEAREST = 0, INTER_LINEAR = 1 };
 enum { COLOR_BGR2GRAY = 6 };
 enum { THRESH_BINARY = 0, THRESH_TOZERO = 3 };
 enum { CMP_EQ = 0, CMP_GT = 1, CMP_GE = 2, CMP_LT = 3, CMP_LE = 4, CMP_NE = 5 };
-enum { NORM_HAMMING = 6 };
+enum { NORM_L1 = 2, NORM_L2 = 4, NORM_HAMMING = 6 };
 
 // ---- implemented in oracle/ref_orb_wrap.cpp / oracle/ref_line_wrap.cpp on the oracle's cv2-pinned primitives
 float fastAtan2(float y, float x);
@@ -334,6 +354,11 @@ struct KeyPointsFilter { static void retainBest(std::vector<KeyPoint>& keypoints
 class LineSegmentDetector { public: virtual ~LineSegmentDetector() {} virtual void detect(const Mat& image, std::vector<Vec4f>& lines) = 0; };
 Ptr<LineSegmentDetector> createLineSegmentDetector(int refine = 1, double scale = 0.8, double sigma_scale = 0.6, double quant = 2.0, double ang_th = 22.5,
                                                    double log_eps = 0, double density_th = 0.7, int n_bins = 1024);
+void initUndistortRectifyMap(const Mat& K, const Mat& D, const Mat& R, const Mat& newK, Size size, int m1type, Mat& map1, Mat& map2);
+void remap(const Mat& src, Mat& dst, const Mat& map1, const Mat& map2, int interpolation);
+void undistortPoints(const Mat& src, Mat& dst, const Mat& K, const Mat& D, const Mat& R, const Mat& P);
+// cv::SVD::compute and norm(a, b, type): Frame::ComputeLine3D / ComputeStereoMatches only (stereo; never reached on the tested paths)
+struct SVD { enum { MODIFY_A = 1, FULL_UV = 4 }; static void compute(const Mat&, Mat&, Mat&, Mat&, int = 0) { abort(); } };
 // cv::LineIterator(img, p1, p2): only .count is used (LSDDetector_custom.cpp:184): 8-connected, end points rounded half-to-even
 class LineIterator { public: LineIterator(const Mat& img, Point2f p1, Point2f p2); int count; };
 

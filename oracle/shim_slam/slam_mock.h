@@ -214,6 +214,7 @@ class MapLine {
   void Replace(MapLine* pML) { if (pML == this) return; mbBad = true; mpReplaced = pML; }
 };
 
+#ifndef PL_SHIM_REAL_FRAME
 class Frame : public GridView {
  public:
   long unsigned int mnId = 0;
@@ -227,6 +228,7 @@ class Frame : public GridView {
   // only LSDmatcher::SerachForInitialize (LSDmatcher.cpp:340-373) calls this; no caller of that function exists in the reference
   void lineDescriptorMAD(std::vector<std::vector<cv::DMatch>>, double&, double&) const { abort(); }
 };
+#endif
 
 class KeyFrame : public GridView {
  public:
@@ -249,6 +251,8 @@ class KeyFrame : public GridView {
   bool isBad() { return mbBad; }
 };
 
+#ifndef PL_SHIM_REAL_FRAME
 inline bool Frame::isInFrustum(MapLine* pML, float) const { return pML->mbInFrustum; }
+#endif
 
 }  // namespace ORB_SLAM2

@@ -8,6 +8,8 @@ order are pinned to cv2 4.13 golden vectors; the whole ORB extraction is pinned 
 where it lies into oracle/_ref/libref_orb.so (RefOrb; byte-identical keypoints and descriptors, tests/test_oracle_orb_ref.py and
 tests/golden/orb_ref_*.npz); KeyLine construction and the LBD descriptor are pinned the same way to the reference tree's
 Thirdparty/line_descriptor sources (oracle/_ref/libref_line.so; tests/test_oracle_line_ref.py, tests/golden/line_ref_*.npz); the
-matchers, the g2o LM and BA are "parity unpinned" (the reference ships no vectors for them and those files cannot be built here).
+point and line matchers (ORBmatcher.cc, LSDmatcher.cpp, MapPoint.cc -> libref_match.so) and the frame glue (the reference's Frame.cc
+against its real Frame.h -> libref_frame.so: the whole monocular Frame constructor, grids, isInFrustum) are pinned the same way; the g2o LM
+and BA are "parity unpinned" (the reference ships no vectors for them and Optimizer.cc cannot be built here).
 """
 from .binding import *  # noqa

@@ -111,6 +111,80 @@ def ref_lbd_compute(img, keylines, want_float=False):
     return (desc[:len(kl)], dv[:len(kl)]) if want_float else desc[:len(kl)]
 
 
+_REF_FRAME_LIB = os.path.join(_HERE, "_ref", "libref_frame.so")
+_ref_frame = None
+
+
+def ref_frame_available():
+    """True when oracle/_ref/libref_frame.so exists: the reference's OWN src/Frame.cc against its real Frame.h, with its ORBextractor,
+    LINEextractor, MapPoint and the vendored line-descriptor sources (oracle/ref_frame_wrap.cpp, oracle/shim_frame/)."""
+    if os.path.isdir("/root/reference/src") and not os.path.exists(_REF_FRAME_LIB):
+        build()
+        subprocess.call(["make", "-C", _HERE, "-s", "ref"])
+    return os.path.exists(_REF_FRAME_LIB)
+
+
+def _ref_frame_lib():
+    global _ref_frame
+    if _ref_frame is None:
+        lib()
+        _ref_frame = C.CDLL(_REF_FRAME_LIB)
+    return _ref_frame
+
+
+def ref_frame_construct(img, K, D, mask=None, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, nlines=200, min_line_length=0.0):
+    """The reference's monocular Frame constructor itself (Frame.cc:193-276) -> dict(keys, keysUn, desc, keylines, ldesc, lfunc, bounds,
+    grid (start, items), line_grid (start, items)).  The frame stays alive for ref_frame_features_in_area(_line)."""
+    img = np.ascontiguousarray(img, np.uint8); h, w = img.shape
+    cap, capl = 2 * nfeatures + 64, nlines + 2
+    counts = np.zeros(2, np.int32)
+    keys = np.zeros(cap, KP_DTYPE); keysUn = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+    kl = np.zeros(capl, KEYLINE_DTYPE); ldesc = np.zeros((capl, 32), np.uint8); lfunc = np.zeros((capl, 3), np.float64)
+    bounds = np.zeros(4, np.float32)
+    gs = np.zeros(64 * 48 + 1, np.int32); gi = np.zeros(cap, np.int32)
+    lcap = capl * 200
+    ls = np.zeros(64 * 48 + 1, np.int32); li = np.zeros(lcap, np.int32); ln = C.c_int(0)
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    Kc = _f32(K); Dc = _f32(D)
+    f = _ref_frame_lib().ref_frame_construct
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                  C.c_int, C.c_int] + [C.c_void_p] * 12 + [C.c_int, C.c_void_p]
+    rc = f(_p(img), w, h, _p(m), _p(Kc), _p(Dc), nfeatures, scale_factor, nlevels, ini_th, min_th, nlines, float(min_line_length), cap, capl,
+           _p(counts), _p(keys), _p(keysUn), _p(desc), _p(kl), _p(ldesc), _p(lfunc), _p(bounds), _p(gs), _p(gi), _p(ls), _p(li), lcap, C.byref(ln))
+    assert rc == 0, rc
+    n, nl = int(counts[0]), int(counts[1])
+    return dict(keys=keys[:n].copy(), keysUn=keysUn[:n].copy(), desc=desc[:n].copy(), keylines=kl[:nl].copy(), ldesc=ldesc[:nl].copy(),
+                lfunc=lfunc[:nl].copy(), bounds=bounds, grid=(gs, gi[:gs[-1]].copy()), line_grid=(ls, li[:ln.value].copy()))
+
+
+def ref_frame_features_in_area(x, y, r, min_level=-1, max_level=-1):
+    out = np.zeros(8192, np.int32)
+    f = _ref_frame_lib().ref_frame_features_in_area
+    f.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    n = f(x, y, r, min_level, max_level, _p(out), len(out))
+    return out[:n].copy()
+
+
+def ref_frame_is_in_frustum_points(Tcw, K, bounds, log_scale_factor, n_levels, cos_limit, pos, normal, min_dist, max_dist):
+    """Frame::isInFrustum(MapPoint*) of the reference itself -> (inview, proj, level, viewcos, Ow as the frame derives it)."""
+    n = len(pos)
+    T = _f32(Tcw); Kc = _f32(K); b = _f32(bounds); pos = _f32(pos); normal = _f32(normal); mn = _f32(min_dist); mx = _f32(max_dist)
+    inview = np.zeros(n, np.uint8); proj = np.zeros((n, 2), np.float32); level = np.zeros(n, np.int32); vc = np.zeros(n, np.float32); Ow = np.zeros(3, np.float32)
+    _ref_frame_lib().ref_frame_is_in_frustum_points(_p(T), _p(Kc), _p(b), C.c_float(log_scale_factor), C.c_int(n_levels), C.c_float(cos_limit), C.c_int(n),
+                                                    _p(pos), _p(normal), _p(mn), _p(mx), _p(inview), _p(proj), _p(level), _p(vc), _p(Ow))
+    return inview, proj, level, vc, Ow
+
+
+def ref_frame_is_in_frustum_lines(Tcw, K, bounds, log_scale_factor, cos_limit, pos, normal, min_dist, max_dist):
+    n = len(pos)
+    T = _f32(Tcw); Kc = _f32(K); b = _f32(bounds); mn = _f32(min_dist); mx = _f32(max_dist)
+    pos = np.ascontiguousarray(pos, np.float64); normal = np.ascontiguousarray(normal, np.float64)
+    inview = np.zeros(n, np.uint8); proj = np.zeros((n, 4), np.float32); level = np.zeros(n, np.int32); vc = np.zeros(n, np.float32); Ow = np.zeros(3, np.float32)
+    _ref_frame_lib().ref_frame_is_in_frustum_lines(_p(T), _p(Kc), _p(b), C.c_float(log_scale_factor), C.c_float(cos_limit), C.c_int(n), _p(pos), _p(normal),
+                                                   _p(mn), _p(mx), _p(inview), _p(proj), _p(level), _p(vc), _p(Ow))
+    return inview, proj, level, vc, Ow
+
+
 _REF_MATCH_LIB = os.path.join(_HERE, "_ref", "libref_match.so")
 _ref_match = None
 

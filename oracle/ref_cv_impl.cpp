@@ -4,7 +4,7 @@
 // oracle's restatements (liboracle.so), which are pinned bit for bit to the cv2 4.13 wheel (tests/test_oracle_{orb,line,frame}.py,
 // tests/golden/*cv2*.npz): resize 8U INTER_LINEAR, GaussianBlur 7x7 sigma 2 / 5x5 sigma 1, FAST 9/16 + NMS, copyMakeBorder
 // REFLECT_101, fastAtan2, Sobel 3x3 8U -> 16S, the LineSegmentDetector, initUndistortRectifyMap + remap INTER_LINEAR,
-// undistortPoints.  Everything the compiled reference files never reach on the tested paths aborts.
+// undistortPoints, BFMatcher::knnMatch (k = 2, Hamming).  Everything the compiled reference files never reach on the tested paths aborts.
 #include <opencv2/core/core.hpp>
 #include <cstdint>
 
@@ -18,6 +18,7 @@ int oracle_lsd_detect(const uint8_t* img, int w, int h, int order_mode, float* l
 void oracle_undistort_map(const float* K, const float* D, int w, int h, float* mx, float* my);
 void oracle_remap(const uint8_t* src, int w, int h, const float* mx, const float* my, uint8_t* dst);
 void oracle_undistort_keypoints(const void* kps, int n, const float* K, const float* D, void* out);
+void oracle_bf_knn2(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx, int* dist);
 }
 
 namespace cv {
@@ -167,6 +168,23 @@ void undistortPoints(const Mat& src, Mat& dst, const Mat& K, const Mat& D, const
   Mat r(src.rows, src.cols, src.type());
   for (int i = 0; i < n; i++) { float* p = r.ptr<float>(i / r.cols) + 2 * (i % r.cols); p[0] = out[i].pt.x; p[1] = out[i].pt.y; }
   dst = r;
+}
+
+
+// BFMatcher(NORM_HAMMING).knnMatch(query, train, matches, 2): per query the two nearest train rows, ties -> lower index (cv2-pinned);
+// with fewer than two train rows OpenCV returns shorter lists, which the reference then indexes out of range ([i][1]): see the tests
+void BFMatcher::knnMatch(const Mat& query, const Mat& train, std::vector<std::vector<DMatch>>& matches, int k) const {
+  if (k != 2) abort();
+  const int n1 = query.rows, n2 = train.rows;
+  matches.assign((size_t)n1, std::vector<DMatch>());
+  if (n1 == 0 || n2 < 2) abort();
+  std::vector<uint8_t> q((size_t)n1 * 32), t((size_t)n2 * 32);
+  for (int i = 0; i < n1; i++) memcpy(q.data() + 32 * (size_t)i, query.ptr(i), 32);
+  for (int i = 0; i < n2; i++) memcpy(t.data() + 32 * (size_t)i, train.ptr(i), 32);
+  std::vector<int> idx((size_t)n1 * 2), dist((size_t)n1 * 2);
+  oracle_bf_knn2(q.data(), n1, t.data(), n2, idx.data(), dist.data());
+  for (int i = 0; i < n1; i++)
+    for (int j = 0; j < 2; j++) { DMatch m; m.queryIdx = i; m.trainIdx = idx[2 * i + j]; m.imgIdx = 0; m.distance = (float)dist[2 * i + j]; matches[i].push_back(m); }
 }
 
 }  // namespace cv

@@ -14,26 +14,6 @@
 
 using namespace ORB_SLAM2;
 
-extern "C" void oracle_bf_knn2(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx, int* dist);   // liboracle.so
-
-namespace cv {
-// BFMatcher(NORM_HAMMING).knnMatch(query, train, matches, 2): per query the two nearest train rows, ties -> lower index (cv2-pinned);
-// with fewer than two train rows OpenCV returns shorter lists, which the reference then indexes out of range ([i][1]): see the tests
-void BFMatcher::knnMatch(const Mat& query, const Mat& train, std::vector<std::vector<DMatch>>& matches, int k) const {
-  if (k != 2) abort();
-  const int n1 = query.rows, n2 = train.rows;
-  matches.assign((size_t)n1, std::vector<DMatch>());
-  if (n1 == 0 || n2 < 2) abort();
-  std::vector<uint8_t> q((size_t)n1 * 32), t((size_t)n2 * 32);
-  for (int i = 0; i < n1; i++) memcpy(q.data() + 32 * (size_t)i, query.ptr(i), 32);
-  for (int i = 0; i < n2; i++) memcpy(t.data() + 32 * (size_t)i, train.ptr(i), 32);
-  std::vector<int> idx((size_t)n1 * 2), dist((size_t)n1 * 2);
-  oracle_bf_knn2(q.data(), n1, t.data(), n2, idx.data(), dist.data());
-  for (int i = 0; i < n1; i++)
-    for (int j = 0; j < 2; j++) { DMatch m; m.queryIdx = i; m.trainIdx = idx[2 * i + j]; m.imgIdx = 0; m.distance = (float)dist[2 * i + j]; matches[i].push_back(m); }
-}
-}  // namespace cv
-
 namespace {
 struct FlatKL { float startX, startY, endX, endY, lineLength, angle; int octave; };     // oracle_match.cpp's flat KeyLine
 KeyLine keyline(const FlatKL& f) {

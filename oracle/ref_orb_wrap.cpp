@@ -24,35 +24,7 @@
 // memory: a later allocation has a higher address.  That is one legal execution of the reference program, and it is the tie
 // rule the oracle documents ("the later-created node counts as the larger pointer").  ref_orb_set_bump(0) restores malloc,
 // for measuring how far glibc's order moves the result (tests/test_oracle_orb_ref.py).
-#include <new>
-#include <sys/mman.h>
-static int g_bump = 1;                 // ref_orb_set_bump()
-static bool g_in_call = false;         // only allocations made inside operator() go to the arena (all of them are temporaries of the call)
-static char* g_base = nullptr;
-static const size_t kArena = (size_t)64 << 20;
-static size_t g_off = 0;
-static int g_overflow = 0;
-static inline bool in_arena(void* p) { return g_base && (char*)p >= g_base && (char*)p < g_base + kArena; }
-static void* pl_alloc(size_t n) {
-  if (g_bump && g_in_call && n >= 64 && n <= 128) {          // std::list<ExtractorNode> nodes are 88 bytes
-    const size_t need = (n + 15) & ~(size_t)15;
-    if (!g_base) {
-      void* m = mmap(nullptr, kArena, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-      if (m != MAP_FAILED) g_base = (char*)m;
-    }
-    if (g_base && g_off + need <= kArena) { void* r = g_base + g_off; g_off += need; return r; }
-    g_overflow = 1;                                            // reported by ref_orb_extract (negative return)
-  }
-  void* r = malloc(n ? n : 1);
-  if (!r) throw std::bad_alloc();
-  return r;
-}
-void* operator new(size_t n) { return pl_alloc(n); }
-void* operator new[](size_t n) { return pl_alloc(n); }
-void operator delete(void* p) noexcept { if (p && !in_arena(p)) free(p); }
-void operator delete[](void* p) noexcept { if (p && !in_arena(p)) free(p); }
-void operator delete(void* p, size_t) noexcept { if (p && !in_arena(p)) free(p); }
-void operator delete[](void* p, size_t) noexcept { if (p && !in_arena(p)) free(p); }
+#include "ref_alloc.inc"
 extern "C" void ref_orb_set_bump(int on) { g_bump = on; }
 
 extern "C" {
@@ -63,8 +35,7 @@ void ref_orb_destroy(void* h) { delete (ORB_SLAM2::ORBextractor*)h; }
 // ORBextractor::operator()(image, Mat(), keypoints, descriptors); returns the keypoint count (which may exceed cap)
 int ref_orb_extract(void* h, const uint8_t* img, int w, int hh, int stride, void* kps, uint8_t* desc, int cap) {
   int n;
-  g_off = 0; g_overflow = 0;       // every arena block of the previous call is dead (they are all temporaries of operator())
-  g_in_call = true;
+  ref_arena_begin(true);           // every arena block of the previous call is dead (they are all temporaries of operator())
   {
     cv::Mat image(hh, w, CV_8UC1, const_cast<uint8_t*>(img), (size_t)stride), d;
     std::vector<cv::KeyPoint> k;
@@ -74,8 +45,7 @@ int ref_orb_extract(void* h, const uint8_t* img, int w, int hh, int stride, void
     memcpy(kps, k.data(), sizeof(cv::KeyPoint) * (size_t)m);
     for (int i = 0; i < m; i++) memcpy(desc + 32 * (size_t)i, d.ptr(i), 32);
   }
-  g_in_call = false;
-  return g_overflow ? -1 : n;
+  return ref_arena_end() ? -1 : n;
 }
 void ref_orb_tables(void* h, float* scale, float* invScale, float* sigma2, float* invSigma2) {
   ORB_SLAM2::ORBextractor* e = (ORB_SLAM2::ORBextractor*)h;

@@ -269,3 +269,26 @@ def test_tracking_stage_matches_oracle():
                                                            (lm >= 0).astype(np.uint8))
         assert t1["n_line"][b] == lnm2 and np.array_equal(t1["line_match"][b, :nl], lm2)
     assert retried >= 2 and t0["n_pt"].max() > 100 and t0["n_line"].max() > 20
+
+
+@pytest.mark.skipif(not oracle.ref_frame_available(), reason="oracle/_ref/libref_frame.so did not travel")
+@pytest.mark.parametrize("K,D,w,h,seed", [(synth.TUM1_K, synth.TUM1_DIST, 640, 480, 16), (synth.EUROC_K, synth.EUROC_DIST, 752, 480, 17)])
+def test_frontend_equals_the_reference_frame_constructor(K, D, w, h, seed):
+    """The CUDA front-end against the REFERENCE's own monocular Frame constructor (src/Frame.cc compiled with its ORBextractor,
+    LINEextractor and line-descriptor sources into oracle/_ref/libref_frame.so, run on this box's CPU): keypoints, undistorted
+    keypoints, ORB descriptors, keylines and LBD descriptors of every frame, byte for byte."""
+    B = 3
+    frames = synth.synth_sequence(B, w, h, seed=seed)
+    fe = pl.Frontend(w, h, max_batch=B, lm_caps=(320, 88))
+    fe.set_wrap(True)
+    fe.set_pose_problems([synth.synth_pose_problem(90 + k) for k in range(B)])
+    fe.set_camera(K, D)
+    out = fe.run(frames)
+    ku = fe.fetch_keys_un(B)
+    for b in range(B):
+        F = oracle.ref_frame_construct(frames[b], K, D)
+        n, nl = out["n"][b], out["nl"][b]
+        assert n == len(F["keys"]) and out["kps"][b, :n].tobytes() == F["keys"].tobytes(), b
+        assert np.array_equal(out["desc"][b, :n], F["desc"]) and ku[b, :n].tobytes() == F["keysUn"].tobytes(), b
+        assert nl == len(F["keylines"]) and out["keylines"][b, :nl].tobytes() == F["keylines"].tobytes(), b
+        assert np.array_equal(out["ldesc"][b, :nl], F["ldesc"]), b

@@ -126,3 +126,33 @@ def test_bf_knn_and_line_matching():
         nm, m = pl.LSDmatcher(0.7).SearchDouble(a, b)
         onm, om = oracle.search_double(a, b, 0.7)
         assert nm == onm and np.array_equal(m, om)
+
+
+@pytest.mark.skipif(not oracle.ref_match_available(), reason="oracle/_ref/libref_match.so did not travel")
+def test_matchers_equal_the_reference_matcher_code(frames):
+    """The CUDA matchers against the REFERENCE's own ORBmatcher.cc (compiled into oracle/_ref/libref_match.so, run on this box's CPU):
+    SearchForInitialization and the two tracking searches, same inputs, identical match lists."""
+    (k1, d1), (k2, d2) = frames[1000][0], frames[1000][1]
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    nm, m, pm = pl.ORBmatcher(0.9, True).SearchForInitialization(k1, d1, k2, d2, BOUNDS, prev, 100)
+    rnm, rm, rpm = oracle.search_for_initialization(k1, d1, k2, d2, BOUNDS, prev, 100, 0.9, True, impl="ref")
+    assert rnm > 50 and nm == rnm and np.array_equal(m, rm) and pm.tobytes() == rpm.tobytes()
+    rng = np.random.default_rng(14)
+    K = np.array(synth.TUM1_K, np.float32)
+    X = _fake_map(k1, rng, K)
+    valid = rng.random(len(k1)) < 0.8
+    T = np.eye(4, dtype=np.float32); T[:3, 3] = [0.004, -0.003, 0.002]
+    sf = oracle.OrbOracle(1000, 1.2, 8, 20, 7).tables()["scale"]
+    pre = (rng.random(len(k2)) < 0.05).astype(np.uint8)
+    args = (k2, d2, BOUNDS, T, K, sf, valid, X, d1, k1["octave"], k1["angle"], 15.0)
+    nm, m = pl.ORBmatcher(0.9, True).SearchByProjectionLast(*args, preassigned=pre)
+    rnm, rm = oracle.search_by_projection_last(*args, check_ori=True, preassigned=pre, impl="ref")
+    assert rnm > 100 and nm == rnm and np.array_equal(m, rm)
+    n_mp = 1500
+    src = rng.integers(0, len(k1), n_mp)
+    proj = np.stack([k1["x"][src], k1["y"][src]], 1).astype(np.float32) + rng.normal(0, 2.0, (n_mp, 2)).astype(np.float32)
+    level = np.clip(k1["octave"][src] + rng.integers(-1, 2, n_mp), 0, 7).astype(np.int32)
+    a = (k2, d2, BOUNDS, sf, rng.random(n_mp) < 0.85, proj, level, rng.uniform(0.99, 1.0, n_mp).astype(np.float32), d1[src])
+    nm, m = pl.ORBmatcher(0.8).SearchByProjectionPoints(*a, th=3.0)
+    rnm, rm = oracle.search_by_projection_points(*a, 3.0, 0.8, impl="ref")
+    assert rnm > 100 and nm == rnm and np.array_equal(m, rm)

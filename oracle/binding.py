@@ -764,14 +764,21 @@ def search_by_bow(kK, dK, has_mp_kf, kF, dF, fvK, fvF, nnratio=0.7, check_orient
 
 
 def search_by_projection_keyframe(kc, dc, bounds, Tcw, Ow, K, scale_factors, log_scale_factor, kf_valid, pos, mp_desc, min_dist,
-                                  max_dist, kf_angle, th, orb_dist, check_orientation=True, preassigned=None):
-    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1587-1716)."""
+                                  max_dist, kf_angle, th, orb_dist, check_orientation=True, preassigned=None, impl="oracle"):
+    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1587-1716).
+    impl="ref": the reference itself; it derives the camera centre from Tcw and returns it as a third value."""
     kc = np.ascontiguousarray(kc, KP_DTYPE); dc = np.ascontiguousarray(dc, np.uint8)
     b = _f32(bounds); T = _f32(Tcw); O = _f32(Ow); Kc = _f32(K); sf = _f32(scale_factors)
     v = np.ascontiguousarray(kf_valid, np.uint8); pos = _f32(pos); md = np.ascontiguousarray(mp_desc, np.uint8)
     mn = _f32(min_dist); mx = _f32(max_dist); ang = _f32(kf_angle)
     pre = None if preassigned is None else np.ascontiguousarray(preassigned, np.uint8)
     out = np.full(len(kc), -1, np.int32)
+    if impl == "ref":
+        ow = np.zeros(3, np.float32)
+        f = _fn("search_by_projection_keyframe", "ref"); f.restype = C.c_int
+        nm = f(_p(kc), _p(dc), C.c_int(len(kc)), _p(b), _p(T), _p(Kc), _p(sf), C.c_int(len(sf)), C.c_float(log_scale_factor), C.c_int(len(v)), _p(v),
+               _p(pos), _p(md), _p(mn), _p(mx), _p(ang), C.c_float(th), C.c_int(orb_dist), C.c_int(int(check_orientation)), _p(pre), _p(out), _p(ow))
+        return nm, out, ow
     L = lib(); L.oracle_search_by_projection_keyframe.restype = C.c_int
     nm = L.oracle_search_by_projection_keyframe(_p(kc), _p(dc), C.c_int(len(kc)), _p(b), _p(T), _p(O), _p(Kc), _p(sf), C.c_int(len(sf)),
                                                 C.c_float(log_scale_factor), C.c_int(len(v)), _p(v), _p(pos), _p(md), _p(mn), _p(mx),
@@ -780,15 +787,15 @@ def search_by_projection_keyframe(kc, dc, bounds, Tcw, Ow, K, scale_factors, log
     return nm, out
 
 
-def search_by_bow_keyframes(k1, d1, mp1, k2, d2, mp2, fv1, fv2, nnratio=0.75, check_orientation=True):
+def search_by_bow_keyframes(k1, d1, mp1, k2, d2, mp2, fv1, fv2, nnratio=0.75, check_orientation=True, impl="oracle"):
     """ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (ORBmatcher.cc:574-709) -> (nmatches, matches12[n1])."""
     k1 = np.ascontiguousarray(k1, KP_DTYPE); k2 = np.ascontiguousarray(k2, KP_DTYPE)
     d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
     m1 = np.ascontiguousarray(mp1, np.uint8); m2 = np.ascontiguousarray(mp2, np.uint8)
     n1a, s1, i1 = _csr(fv1); n2a, s2, i2 = _csr(fv2)
     out = np.full(len(k1), -1, np.int32)
-    L = lib(); L.oracle_search_by_bow_keyframes.restype = C.c_int
-    nm = L.oracle_search_by_bow_keyframes(_p(k1), _p(d1), _p(m1), C.c_int(len(k1)), _p(k2), _p(d2), _p(m2), C.c_int(len(k2)), _p(n1a),
+    f = _fn("search_by_bow_keyframes", impl); f.restype = C.c_int
+    nm = f(_p(k1), _p(d1), _p(m1), C.c_int(len(k1)), _p(k2), _p(d2), _p(m2), C.c_int(len(k2)), _p(n1a),
                                           _p(s1), _p(i1), C.c_int(len(n1a)), _p(n2a), _p(s2), _p(i2), C.c_int(len(n2a)),
                                           C.c_float(nnratio), C.c_int(int(check_orientation)), _p(out))
     return nm, out

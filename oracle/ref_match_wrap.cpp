@@ -247,6 +247,67 @@ int ref_search_by_bow(const void* keysKF, const uint8_t* descKF, const uint8_t* 
   return r;
 }
 
+// ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (loop closing); mp1 / mp2: the keypoint holds a good map point
+int ref_search_by_bow_keyframes(const void* keys1, const uint8_t* desc1, const uint8_t* mp1, int n1, const void* keys2, const uint8_t* desc2,
+                                const uint8_t* mp2, int n2, const unsigned* fv1_nodes, const int* fv1_start, const int* fv1_items, int nn1,
+                                const unsigned* fv2_nodes, const int* fv2_start, const int* fv2_items, int nn2, float nnratio, int check_orientation,
+                                int* matches12) {
+  static KeyFrame K1, K2;
+  K1 = KeyFrame(); K2 = KeyFrame();
+  World W;
+  set_view(K1, keys1, desc1, n1, nullptr, nullptr);
+  set_view(K2, keys2, desc2, n2, nullptr, nullptr);
+  K1.mvpMapPoints.assign((size_t)n1, nullptr); K2.mvpMapPoints.assign((size_t)n2, nullptr);
+  std::map<MapPoint*, int> index2;
+  for (int i = 0; i < n1; i++) if (mp1[i]) K1.mvpMapPoints[i] = W.point(nullptr, nullptr, 1);
+  for (int i = 0; i < n2; i++) if (mp2[i]) { MP* p = W.point(nullptr, nullptr, 1); K2.mvpMapPoints[i] = p; index2[p] = i; }
+  set_featvec(K1.mFeatVec, fv1_nodes, fv1_start, fv1_items, nn1);
+  set_featvec(K2.mFeatVec, fv2_nodes, fv2_start, fv2_items, nn2);
+  std::vector<MapPoint*> out;
+  ORBmatcher matcher(nnratio, check_orientation != 0);
+  const int r = matcher.SearchByBoW(&K1, &K2, out);
+  for (int i = 0; i < n1; i++) matches12[i] = out[i] ? index2[out[i]] : -1;
+  return r;
+}
+
+// ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (relocalisation).  kf_valid[i]: the keyframe's i-th
+// map point exists, is good and is not in sAlreadyFound.  Ow_out: the camera centre the function derives from Tcw (-Rcw^T tcw).
+int ref_search_by_projection_keyframe(const void* keys_cur, const uint8_t* desc_cur, int n_cur, const float* bounds, const float* Tcw,
+                                      const float* K, const float* scaleFactors, int nlevels, float logScaleFactor, int n_kf,
+                                      const uint8_t* kf_valid, const float* pos, const uint8_t* mp_desc, const float* minDist, const float* maxDist,
+                                      const float* kf_angle, float th, int ORBdist, int checkOri, const uint8_t* cur_preassigned, int* cur_match,
+                                      float* Ow_out) {
+  static Frame Cur; static KeyFrame KF;
+  Cur = Frame(); KF = KeyFrame();
+  World W;
+  set_view(Cur, keys_cur, desc_cur, n_cur, bounds, scaleFactors, nlevels);
+  set_K(Cur, K);
+  Cur.mfLogScaleFactor = logScaleFactor;
+  Cur.mTcw = pose44(Tcw);
+  Cur.mvpMapPoints.assign((size_t)n_cur, nullptr);
+  MP* pre = W.point(nullptr, nullptr, 1);
+  for (int i = 0; i < n_cur; i++) if (cur_preassigned && cur_preassigned[i]) Cur.mvpMapPoints[i] = pre;
+  KF.N = n_kf;
+  KF.mvKeysUn.resize((size_t)n_kf); KF.mvKeys.resize((size_t)n_kf);
+  KF.mvpMapPoints.assign((size_t)n_kf, nullptr);
+  std::map<MapPoint*, int> index;
+  for (int i = 0; i < n_kf; i++) {
+    KF.mvKeysUn[i].angle = KF.mvKeys[i].angle = kf_angle[i];
+    if (!kf_valid[i]) continue;
+    MP* p = W.point(pos + 3 * i, mp_desc + 32 * i, 1);
+    p->set_dist(minDist[i], maxDist[i]);
+    KF.mvpMapPoints[i] = p; index[p] = i;
+  }
+  const std::set<MapPoint*> none;
+  ORBmatcher matcher(0.9f, checkOri != 0);
+  const int r = matcher.SearchByProjection(Cur, &KF, none, th, ORBdist);
+  for (int i = 0; i < n_cur; i++) { MapPoint* p = Cur.mvpMapPoints[i]; cur_match[i] = !p ? -1 : (p == pre ? -2 : index[p]); }
+  const cv::Mat Rcw = Cur.mTcw.rowRange(0, 3).colRange(0, 3), tcw = Cur.mTcw.rowRange(0, 3).col(3);
+  const cv::Mat Ow = -Rcw.t() * tcw;
+  for (int i = 0; i < 3; i++) Ow_out[i] = Ow.at<float>(i);
+  return r;
+}
+
 // MapPoint::ComputeDistinctiveDescriptors for n_mp points; observation k of point m is row offsets[m] + k of desc.  The reference
 // walks std::map<KeyFrame*, size_t>, i.e. keyframes in ADDRESS order: the keyframes of one point are consecutive elements of
 // one array here, so that order is the row order.  chosen: n_mp x 32 bytes (the descriptor the point ends up with).

@@ -158,3 +158,24 @@ def test_predict_scale():
     ratio = (max_dist / dist).astype(np.float32)
     f64 = np.clip(np.ceil(np.log(ratio.astype(np.float64)) / np.float64(log_sf)), 0, 7).astype(np.int32)
     assert (f64 != ref).sum() > 0
+
+
+@pytest.mark.parametrize("seed,ori,ratio", [(5, True, 0.75), (7, False, 0.75), (11, True, 0.6)])
+def test_search_by_bow_keyframes(seed, ori, ratio):
+    s = synth.synth_two_view(seed)
+    a, b = s["1"], s["2"]
+    args = (a["keys"], a["desc"], 1 - a["has_mp"], b["keys"], b["desc"], 1 - b["has_mp"], a["fv"], b["fv"])
+    onm, om = oracle.search_by_bow_keyframes(*args, ratio, ori)
+    rnm, rm = oracle.search_by_bow_keyframes(*args, ratio, ori, impl="ref")
+    assert onm > 100 and onm == rnm and np.array_equal(om, rm)
+
+
+@pytest.mark.parametrize("seed,th,dist,ori", [(6, 10.0, 100, True), (8, 3.0, 64, True), (9, 10.0, 100, False), (10, 3.0, 64, False)])
+def test_search_by_projection_keyframe(seed, th, dist, ori):
+    from test_oracle_localmap import _reloc_args
+    args, pre = _reloc_args(seed, th, dist)
+    rnm, rm, ow = oracle.search_by_projection_keyframe(*args, ori, pre, impl="ref")
+    a = list(args); a[4] = ow                       # the camera centre as the reference derives it from Tcw (fp32 gemm of -Rcw^T tcw)
+    onm, om = oracle.search_by_projection_keyframe(*a, ori, pre)
+    assert onm > 10 and onm == rnm and np.array_equal(om, rm)
+    assert np.allclose(ow, args[4], rtol=0, atol=1e-5)

@@ -56,3 +56,26 @@ def test_search_by_projection_lines(lines, th):
     nm, m = pl.LSDmatcher(0.7).SearchByProjectionLines(*a, th=th)
     onm, om = oracle.line_search_by_projection_lines(*a, th, 0.7)
     assert onm > 20 and nm == onm and np.array_equal(m, om)
+
+
+@pytest.mark.skipif(not oracle.ref_match_available(), reason="oracle/_ref/libref_match.so did not travel")
+def test_line_matchers_equal_the_reference_matcher_code(lines):
+    """The CUDA line matchers against the REFERENCE's own LSDmatcher.cpp (compiled into oracle/_ref/libref_match.so, run on this box's
+    CPU): SearchDouble and the two projection searches, same inputs, identical match lists."""
+    d0, d1 = lines[0][1][:-1], lines[1][1][:-1]
+    nm, m = pl.LSDmatcher(0.7).SearchDouble(d0, d1)
+    rnm, rm = oracle.search_double(d0, d1, 0.7, impl="ref")
+    assert rnm > 30 and nm == rnm and np.array_equal(m, rm)
+    rng = np.random.default_rng(13)
+    kl0, dd0, proj, valid = _queries(lines, rng, 1.5)
+    kl1, dd1, lf1 = (x[:-1] for x in lines[1])
+    pre = (rng.random(len(kl1)) < 0.05).astype(np.uint8)
+    a = (kl1, lf1, dd1, BOUNDS, valid, proj, dd0, kl0["lineLength"], 15.0)
+    nm, m = pl.LSDmatcher(0.7).SearchByProjectionLast(*a, preassigned=pre)
+    rnm, rm = oracle.line_search_by_projection_last(*a, preassigned=pre, impl="ref")
+    assert rnm > 30 and nm == rnm and np.array_equal(m, rm)
+    vc = rng.uniform(0.99, 1.0, len(kl0)).astype(np.float32)
+    a = (kl1, lf1, dd1, BOUNDS, valid, proj, vc, dd0)
+    nm, m = pl.LSDmatcher(0.7).SearchByProjectionLines(*a, th=3.0)
+    rnm, rm = oracle.line_search_by_projection_lines(*a, 3.0, 0.7, impl="ref")
+    assert rnm > 20 and nm == rnm and np.array_equal(m, rm)

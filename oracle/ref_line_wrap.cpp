@@ -1,16 +1,16 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product path.
 //
-// C ABI around the line-descriptor sources of the reference tree, compiled unmodified and where they lie
+// C ABI around the line-extraction sources of the reference tree, compiled unmodified and where they lie
 // (oracle/Makefile, target `ref` -> oracle/_ref/libref_line.so; nothing of the reference is copied into the repository):
-//   /root/reference/Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp   BinaryDescriptor::compute (LBD)
+//   /root/reference/src/LineExtractor.cpp                                          LINEextractor::operator()
 //   /root/reference/Thirdparty/line_descriptor/src/LSDDetector_custom.cpp         LSDDetectorC::detect      (KeyLines, §8 a10)
-// (The reference's LineExtractor.cpp includes <opencv2/line_descriptor/descriptor.hpp> of opencv_contrib, which is absent from
-// /root/reference; Thirdparty/line_descriptor is the vendored copy of the same module and the source the oracle cites.)
-// OpenCV itself is not in this image: oracle/shim/ declares what these two files use, and this file implements the image
+//   /root/reference/Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp   BinaryDescriptor::compute (LBD, §8 a11)
+// (LineExtractor.cpp includes <opencv2/line_descriptor/descriptor.hpp> of opencv_contrib, which is absent from /root/reference;
+// Thirdparty/line_descriptor is the vendored copy of the same module and the source the oracle cites.)
+// OpenCV itself is not in this image: oracle/shim/ declares what these files use, and oracle/ref_cv_impl.cpp implements the image
 // primitives behind it on the oracle's restatements (liboracle.so), pinned bit for bit to cv2 4.13: GaussianBlur 5x5 sigma 1,
 // Sobel 3x3 8U -> 16S, the full LineSegmentDetector (ordered segment lists, tests/golden/lsd_cv2_*.npz).
 //
-//   /root/reference/src/LineExtractor.cpp                                          LINEextractor::operator()  (§8 a9)
 // What this pins: the LBD band arithmetic, weights, normalisation and binary conversion, the KeyLine record construction, and
 // LINEextractor's sort / nfeatures(+1) truncation / class ids / line equations are the reference tree's own code (the contrib
 // header name and the three Eigen operations LineExtractor.cpp uses come from oracle/shim/).  Not pinned here: the OpenCV

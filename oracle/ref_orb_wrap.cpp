@@ -3,7 +3,7 @@
 // C ABI around the REFERENCE's own ORBextractor: /root/reference/src/ORBextractor.cc is compiled unmodified, where it lies,
 // next to this file (oracle/Makefile, target `ref` -> oracle/_ref/libref_orb.so; nothing of the reference is copied into the
 // repository).  The reference needs OpenCV, which this image does not have; oracle/shim/ declares the handful of OpenCV types
-// and functions that one source file uses, and THIS file implements the image primitives behind them on the oracle's
+// and functions that one source file uses, and oracle/ref_cv_impl.cpp implements the image primitives behind them on the oracle's
 // restatements (liboracle.so: oracle_resize_linear_u8, oracle_blur_u8, oracle_fast_detect, oracle_fast_atan2), which are pinned
 // bit for bit to the cv2 4.13 wheel (tests/test_oracle_orb.py, tests/golden/orb_cv2_primitives.npz).
 //
@@ -19,11 +19,10 @@
 // ---- allocation order = address order ---------------------------------------------------------------------------------------
 // DistributeOctTree sorts pair<int, ExtractorNode*> (ORBextractor.cc:684): nodes holding the same number of keypoints are ordered
 // by their HEAP ADDRESS, which the C++ program does not define (with glibc's malloc the freed list nodes are handed out again
-// last-in-first-out, so the order depends on the allocator's history).  Inside this library (linked -Bsymbolic, so only the
-// reference code compiled here is affected) operator new serves list-node-sized blocks from a bump arena that never reuses
-// memory: a later allocation has a higher address.  That is one legal execution of the reference program, and it is the tie
-// rule the oracle documents ("the later-created node counts as the larger pointer").  ref_orb_set_bump(0) restores malloc,
-// for measuring how far glibc's order moves the result (tests/test_oracle_orb_ref.py).
+// last-in-first-out, so the order depends on the allocator's history).  ref_alloc.inc gives this library an operator new whose
+// list-node-sized blocks have increasing addresses: one legal execution of the reference program, and the tie rule the oracle
+// documents ("the later-created node counts as the larger pointer").  ref_orb_set_bump(0) restores malloc, for measuring how far
+// glibc's order moves the result (tests/test_oracle_orb_ref.py).
 #include "ref_alloc.inc"
 extern "C" void ref_orb_set_bump(int on) { g_bump = on; }
 

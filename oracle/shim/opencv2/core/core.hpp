@@ -1,13 +1,13 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  Minimal stand-in for the OpenCV headers that a few reference source files include, so that
 // those files compile here unmodified and where they lie (recipe: oracle/Makefile target `ref` -> oracle/_ref/*.so):
-//   /root/reference/src/ORBextractor.cc                                         (ORB extraction)
-//   /root/reference/Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp  (LBD)
-//   /root/reference/Thirdparty/line_descriptor/src/LSDDetector_custom.cpp        (KeyLines from LSD segments)
-// This is not OpenCV: it declares the types and functions those files use, nothing else.  The image primitives behind the
-// declarations (resize, GaussianBlur, FAST, copyMakeBorder, fastAtan2, Sobel, LineSegmentDetector) are implemented in
-// oracle/ref_*_wrap.cpp on top of the oracle's restatements, which are pinned bit for bit to cv2 4.13
-// (tests/test_oracle_orb.py, tests/test_oracle_line.py); everything never executed on the tested paths (EDLine's helpers, colour
-// conversion, pyrDown for more than one octave) aborts.
+//   src/ORBextractor.cc, src/LineExtractor.cpp, src/ORBmatcher.cc, src/LSDmatcher.cpp, src/MapPoint.cc, src/Frame.cc, src/lineIterator.cpp,
+//   Thirdparty/line_descriptor/src/{binary_descriptor_custom,LSDDetector_custom}.cpp, Thirdparty/DBoW2/DBoW2/{BowVector,FeatureVector}.cpp
+// This is not OpenCV: it declares the types and functions those files use, nothing else.  cv::Mat arithmetic on CV_32F follows
+// cv::gemm's small-matrix fp32 order (pinned to cv2 by tests/golden/frame_cv2.npz through the oracle's gemm3); the image primitives
+// behind the declarations (resize, GaussianBlur, FAST, copyMakeBorder, fastAtan2, Sobel, LineSegmentDetector, initUndistortRectifyMap,
+// remap, undistortPoints, BFMatcher::knnMatch) are implemented in oracle/ref_cv_impl.cpp on top of the oracle's restatements, which
+// are pinned bit for bit to cv2 4.13 (tests/test_oracle_{orb,line,frame,match}.py); everything never executed on the tested paths
+// (EDLine's helpers, colour conversion, pyrDown for more than one octave, SVD, the stereo matcher's helpers) aborts or is a plain loop.
 #pragma once
 #include <algorithm>
 #include <cassert>
